@@ -1,0 +1,237 @@
+/*
+ * parseable_b200.h — C ABI of the B200-native columnar query hot path for Parseable.
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference):
+ *
+ *   pq_init / pq_shutdown     QUERY_SESSION / QUERY_RUNTIME singletons        src/query/mod.rs:86-98
+ *   pq_query_open             StandardTableProvider::scan +
+ *                             create_parquet_physical_plan (+ the FilterExec /
+ *                             AggregateExec DataFusion stacks on top)         src/query/stream_schema_provider.rs:114-189, 526-659
+ *   pq_query_next             SendableRecordBatchStream::poll_next driven by
+ *                             collect_partitioned / execute_stream_partitioned src/query/mod.rs:287, 310-334
+ *   pq_query_metrics          get_total_bytes_scanned ("bytes_scanned")        src/query/mod.rs:437-452
+ *   pq_last_error             ExecuteError / DataFusionError::External         src/query/mod.rs:904-917
+ *   pq_query_close            dropping the stream (cancellation)               src/query/mod.rs:300-340
+ *   pq_table_*                the hot tier (local Parquet cache), here in HBM  src/hottier.rs:1541,1609
+ *   pq_comm_*                 Partial -> RepartitionExec(Hash) -> Final merge,
+ *                             here one NCCL all-reduce of partial tables       (DataFusion AggregateExec)
+ *
+ * Plain C: pointers and sizes only.  Results leave through the Arrow C Data
+ * Interface (ArrowArray / ArrowSchema below, ABI-identical to arrow/c/abi.h).
+ * Inputs are borrowed for the duration of the call.  Every function is
+ * re-entrant and thread-safe; a PqQuery may be driven from any thread but by one
+ * thread at a time.  There is no CPU fallback: without a CUDA device every
+ * compute entry point returns PQ_ERR_CUDA.
+ */
+#ifndef PARSEABLE_B200_H
+#define PARSEABLE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+
+/* ---- status codes (SURVEY §8b "Error convention") ---- */
+enum {
+  PQ_OK = 0,
+  PQ_END_OF_STREAM = 1,
+  PQ_ERR_INVALID_ARG = -1,
+  PQ_ERR_UNSUPPORTED = -2, /* plan/encoding not handled: the shim raises an error, it never falls back */
+  PQ_ERR_IO = -3,
+  PQ_ERR_CORRUPT = -4,
+  PQ_ERR_CUDA = -5, /* CUDA or NCCL */
+  PQ_ERR_OOM = -6
+};
+
+/* ---- literal / column value types ---- */
+typedef enum {
+  PQ_T_NULL = 0,
+  PQ_T_BOOL = 1,
+  PQ_T_I64 = 2,   /* Int64 */
+  PQ_T_F64 = 3,   /* Float64 */
+  PQ_T_UTF8 = 4,  /* Utf8 */
+  PQ_T_TS_MS = 5  /* Timestamp(Millisecond, None) */
+} PqType;
+
+/* ---- predicate: flat postfix program (SURVEY §8a "Predicate vocabulary") ---- */
+typedef enum {
+  PQ_OP_CMP = 1,      /* push  col <cmp> literal          (NULL input -> NULL)        */
+  PQ_OP_IS_NULL = 2,  /* push  col IS NULL                                            */
+  PQ_OP_IS_NOT_NULL = 3,
+  PQ_OP_LIKE = 4,     /* push  col LIKE pattern  ESCAPE '\'  (flags: NOT, case-insens) */
+  PQ_OP_AND = 5,      /* pop 2, push Kleene AND                                       */
+  PQ_OP_OR = 6,       /* pop 2, push Kleene OR                                        */
+  PQ_OP_NOT = 7,      /* pop 1, push Kleene NOT                                       */
+  PQ_OP_CONST = 8     /* push literal TRUE/FALSE/NULL (lit.type BOOL or NULL)         */
+} PqOpKind;
+
+typedef enum { PQ_EQ = 0, PQ_NE = 1, PQ_LT = 2, PQ_LE = 3, PQ_GT = 4, PQ_GE = 5 } PqCmp;
+
+#define PQ_LIKE_NEGATED 1u
+#define PQ_LIKE_CASE_INSENSITIVE 2u
+
+typedef struct {
+  int32_t type; /* PqType */
+  int32_t _pad;
+  int64_t i64;  /* BOOL (0/1), I64, TS_MS */
+  double f64;   /* F64 */
+  const char* str; /* UTF8 / LIKE pattern, not NUL-terminated */
+  uint64_t str_len;
+} PqLiteral;
+
+typedef struct {
+  int32_t kind;  /* PqOpKind */
+  int32_t col;   /* index into PqQueryDesc.columns for leaf ops */
+  int32_t cmp;   /* PqCmp for PQ_OP_CMP */
+  uint32_t flags;
+  PqLiteral lit;
+} PqPredOp;
+
+/* ---- aggregates (alert_enums.rs:216-223: Avg, Count, CountDistinct, Min, Max, Sum) ---- */
+typedef enum {
+  PQ_AGG_COUNT_STAR = 0,
+  PQ_AGG_COUNT = 1,
+  PQ_AGG_SUM = 2,
+  PQ_AGG_MIN = 3,
+  PQ_AGG_MAX = 4,
+  PQ_AGG_AVG = 5
+} PqAggFn;
+
+typedef struct {
+  int32_t fn;  /* PqAggFn */
+  int32_t col; /* index into PqQueryDesc.columns; ignored for COUNT_STAR */
+} PqAgg;
+
+/* ---- inputs ---- */
+typedef struct {
+  const char* path;   /* file to read, or NULL when buf is given */
+  const uint8_t* buf; /* whole Parquet file image in host memory, or NULL */
+  uint64_t size;      /* bytes of buf (ignored for path) */
+} PqFile;
+
+typedef struct {
+  const char* name; /* matched against the Parquet schema BY NAME (streams.rs:1024-1037) */
+  int32_t type;     /* PqType expected by the plan; a missing column reads as all-NULL */
+  int32_t _pad;
+} PqColumn;
+
+typedef struct PqTable PqTable; /* HBM-resident encoded column chunks */
+typedef struct PqQuery PqQuery;
+
+typedef struct {
+  /* scan inputs: either a resident table, or a file list (host buffers / paths) */
+  const PqTable* table;
+  const PqFile* files;
+  uint32_t n_files;
+
+  /* every column the plan references; all indices below point into this array */
+  const PqColumn* columns;
+  uint32_t n_columns;
+
+  /* output projection for non-aggregate queries (TableProvider::scan `projection`) */
+  const int32_t* projection;
+  uint32_t n_projection;
+
+  /* WHERE: postfix program; n_pred == 0 means no filter */
+  const PqPredOp* pred;
+  uint32_t n_pred;
+
+  /* GROUP BY + aggregates; n_aggs == 0 means a filter/projection scan */
+  const int32_t* group_by;
+  uint32_t n_group_by;
+  const PqAgg* aggs;
+  uint32_t n_aggs;
+
+  int64_t limit;       /* < 0: none (TableProvider::scan `limit`) */
+  uint32_t batch_size; /* rows per output batch; 0 -> 20000 (stream_schema_provider.rs:160) */
+
+  /* row-group sharding for multi-GPU: this process scans row groups g with
+   * g % shard_count == shard_index (mirrors partitioned_files round-robin, :351-364) */
+  uint32_t shard_index;
+  uint32_t shard_count; /* 0 or 1: no sharding */
+  uint32_t flags;
+} PqQueryDesc;
+
+#define PQ_QUERY_COUNT_ONLY 1u    /* filter scan: only rows_selected is wanted, emit no batches */
+#define PQ_QUERY_ALLREDUCE 2u     /* aggregate: all-reduce partial tables over the pq_comm communicator */
+#define PQ_QUERY_EMIT_ROW_IDS 4u  /* filter scan: append a UInt64 `__row_id` column (global row ordinal) */
+
+typedef struct {
+  uint64_t bytes_scanned;   /* compressed bytes of the column chunks read (plan metric "bytes_scanned") */
+  uint64_t rows_scanned;    /* rows in the row groups that survived pruning */
+  uint64_t rows_selected;   /* rows passing the predicate */
+  uint64_t row_groups_total;
+  uint64_t row_groups_pruned;
+  uint64_t algorithmic_bytes; /* uncompressed encoded bytes of the pages read + bitmap bytes written */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  uint64_t kernel_launches;
+  double device_ms;         /* CUDA-event time of the device work of this query */
+  double scan_kernel_ms;    /* CUDA-event time of the fused scan kernel alone */
+  uint64_t groups;          /* output groups (aggregate queries) */
+} PqMetrics;
+
+/* ---- lifecycle ---- */
+int pq_init(const int* device_ids, int n); /* n == 0: current device / device 0 */
+void pq_shutdown(void);
+const char* pq_version(void);
+int pq_device_count(void);
+
+/* ---- HBM-resident table (hot tier) ---- */
+int pq_table_open(const PqFile* files, uint32_t n_files, const char* const* columns, uint32_t n_columns,
+                  uint32_t shard_index, uint32_t shard_count, PqTable** out);
+uint64_t pq_table_rows(const PqTable*);
+uint64_t pq_table_device_bytes(const PqTable*);
+void pq_table_close(PqTable*);
+
+/* ---- query ---- */
+int pq_query_open(const PqQueryDesc* desc, PqQuery** out);
+int pq_query_next(PqQuery* q, int partition, struct ArrowArray* out, struct ArrowSchema* out_schema);
+int pq_query_metrics(PqQuery* q, PqMetrics* out);
+const char* pq_last_error(PqQuery* q); /* q == NULL: last error of the calling thread */
+void pq_query_close(PqQuery* q);
+
+/* ---- multi-GPU: one process per GPU, NCCL communicator owned by the library ---- */
+#define PQ_COMM_ID_BYTES 128
+int pq_comm_unique_id(uint8_t id[PQ_COMM_ID_BYTES]);
+int pq_comm_init_rank(const uint8_t id[PQ_COMM_ID_BYTES], int nranks, int rank);
+int pq_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARSEABLE_B200_H */

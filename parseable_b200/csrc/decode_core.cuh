@@ -1,0 +1,291 @@
+// Pure (host + device) pieces of the Parquet page decoder: RLE / bit-packed
+// hybrid run walking, bit extraction, PLAIN value loads, order-preserving f64
+// keys.  Restates, for one GPU thread at a time, what parquet 58.1.0's
+// RleDecoder / BitReader / PlainDecoder do for the reference
+// (format: Apache Parquet "Encodings" spec).
+//
+// Everything here is free of CUDA-only constructs so the same code is exercised
+// on the CPU by tests/test_decode_core.py through tools/decode_core_host.cpp
+// (test harness only; it is never linked into libparseable_b200.so).
+#pragma once
+#include <cstdint>
+
+#include "device_structs.hpp"
+
+#if defined(__CUDACC__)
+#define PQ_HD __host__ __device__ __forceinline__
+#else
+#define PQ_HD inline
+#endif
+
+namespace pqb {
+
+// One encoded stream of a page: either the definition levels (bw = 1) or the
+// dictionary indices (bw = page bit width).  Offsets are arena byte offsets.
+struct StreamState {
+  uint64_t pos;            // next run header
+  uint64_t end;            // end of the stream
+  uint64_t data_pos;       // bit-packed run: first byte of the run's packed data
+  uint32_t run_remaining;  // values left in the current run
+  uint32_t run_consumed;   // values already taken from the current bit-packed run
+  uint32_t rle_value;
+  uint8_t kind;            // 0 RLE, 1 bit-packed
+  uint8_t bw;
+  uint16_t _pad;
+};
+
+// A staged copy of arena bytes [arena_base, arena_base + len) (shared memory on the GPU).
+struct Window {
+  const uint8_t* data;
+  uint64_t arena_base;
+  uint32_t len;
+};
+
+PQ_HD void stream_init(StreamState& s, uint64_t begin, uint64_t end, uint32_t bw) {
+  s.pos = begin; s.end = end; s.data_pos = begin;
+  s.run_remaining = 0; s.run_consumed = 0; s.rle_value = 0; s.kind = 0; s.bw = uint8_t(bw); s._pad = 0;
+}
+
+// First arena byte the stream still needs (where the next window must start).
+PQ_HD uint64_t stream_window_start(const StreamState& s) {
+  if (s.run_remaining != 0 && s.kind == 1)
+    return s.data_pos + ((uint64_t(s.run_consumed) * s.bw) >> 3);
+  return s.pos;
+}
+
+// Bytes a window must hold so that `rows` values of a bw-bit stream always fit,
+// whatever the run structure: the worst legal case is one header + one value per
+// run (RLE runs of length 1).
+PQ_HD uint32_t stream_window_cap(uint32_t rows, uint32_t bw) {
+  uint32_t per_value = 1 + ((bw + 7) >> 3);
+  return ((rows * per_value + 64 + 15) & ~15u) + 16;
+}
+
+// Walk run headers until `need` values are covered, the directory is full or the
+// window ends.  Appends DirEntry records; returns the values covered.
+PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEntry* dir,
+                           uint32_t& nent, uint32_t max_ent) {
+  uint32_t covered = 0;
+  const uint64_t wend = w.arena_base + w.len;
+  const uint32_t bw = s.bw;
+  while (covered < need) {
+    if (s.run_remaining == 0) {
+      // parse the next header: ULEB128, at most 5 bytes for a 32-bit count
+      uint64_t p = s.pos;
+      if (p >= s.end) break;  // stream exhausted (corrupt page or padding); caller flags it
+      uint32_t h = 0;
+      int shift = 0;
+      bool ok = false;
+      while (p < wend && p < s.end && shift < 35) {
+        uint32_t b = w.data[p - w.arena_base];
+        p++;
+        h |= (b & 0x7f) << shift;
+        shift += 7;
+        if (!(b & 0x80)) { ok = true; break; }
+      }
+      if (!ok) break;  // header straddles the window end
+      if (h & 1) {
+        uint32_t groups = h >> 1;
+        s.kind = 1;
+        s.run_remaining = groups * 8;
+        s.run_consumed = 0;
+        s.data_pos = p;
+        s.pos = p + uint64_t(groups) * bw;
+        if (groups == 0) continue;
+      } else {
+        uint32_t vbytes = (bw + 7) >> 3;
+        if (p + vbytes > wend) break;
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < vbytes; i++) v |= uint32_t(w.data[p + i - w.arena_base]) << (8 * i);
+        s.kind = 0;
+        s.run_remaining = h >> 1;
+        s.run_consumed = 0;
+        s.rle_value = v;
+        s.pos = p + vbytes;
+        if (s.run_remaining == 0) continue;
+      }
+    }
+    if (nent >= max_ent) break;
+    uint32_t take = s.run_remaining;
+    if (take > need - covered) take = need - covered;
+    if (take > uint32_t(kDirEntryMaxValues)) take = kDirEntryMaxValues;
+    DirEntry e;
+    e.start = covered;
+    if (s.kind == 1) {
+      // the bytes of values [run_consumed, run_consumed+take) must lie inside the window
+      uint64_t avail_bits = (wend > s.data_pos) ? (wend - s.data_pos) * 8 : 0;
+      if (bw != 0) {
+        uint64_t fit = avail_bits / bw;
+        if (fit <= s.run_consumed) break;
+        if (fit - s.run_consumed < take) take = uint32_t(fit - s.run_consumed);
+      }
+      e.kind = 1;
+      e.payload = uint32_t((s.data_pos - w.arena_base) * 8 + uint64_t(s.run_consumed) * bw);
+    } else {
+      e.kind = 0;
+      e.payload = s.rle_value;
+    }
+    e.count = uint16_t(take);
+    dir[nent++] = e;
+    covered += take;
+    s.run_remaining -= take;
+    s.run_consumed += take;
+  }
+  return covered;
+}
+
+// Value j of a bit-packed run whose first value starts at bit `bitoff` of a
+// 4-byte aligned word array.  bw <= 32.
+PQ_HD uint32_t bp_get(const uint32_t* words, uint32_t bitoff, uint32_t bw, uint32_t j) {
+  uint32_t bit = bitoff + j * bw;
+  uint32_t wi = bit >> 5, sh = bit & 31;
+  uint32_t lo = words[wi];
+  uint32_t hi = words[wi + 1];
+  uint64_t both = (uint64_t(hi) << 32) | lo;
+  uint32_t v = uint32_t(both >> sh);
+  return bw >= 32 ? v : (v & ((1u << bw) - 1u));
+}
+
+// Unaligned little-endian 8-byte load built from two aligned 8-byte loads.  The
+// arena keeps 16 bytes of slack after every chunk, so the second load is in bounds.
+PQ_HD uint64_t load_u64_unaligned(const uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~uintptr_t(7));
+  uint32_t sh = uint32_t(a & 7) * 8;
+  uint64_t lo = q[0];
+  if (sh == 0) return lo;
+  uint64_t hi = q[1];
+  return (lo >> sh) | (hi << (64 - sh));
+}
+PQ_HD uint32_t load_u32_unaligned(const uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  uint32_t sh = uint32_t(a & 3) * 8;
+  uint32_t lo = q[0];
+  if (sh == 0) return lo;
+  uint32_t hi = q[1];
+  return (lo >> sh) | (hi << (32 - sh));
+}
+
+// IEEE-754 totalOrder as a signed-integer order: DataFusion / arrow-ord compare
+// and min/max floats this way: -NaN < -inf < ... < -0.0 <
+// +0.0 < ... < +inf < +NaN.
+PQ_HD int64_t f64_order_key(uint64_t bits) {
+  int64_t b = int64_t(bits);
+  return b ^ int64_t(uint64_t(b >> 63) >> 1);
+}
+PQ_HD uint64_t f64_from_order_key(int64_t k) {
+  return uint64_t(k ^ int64_t(uint64_t(k >> 63) >> 1));
+}
+
+// compare with PqCmp codes: 0 EQ 1 NE 2 LT 3 LE 4 GT 5 GE
+PQ_HD bool cmp_i64(int64_t a, int64_t b, uint32_t op) {
+  switch (op) {
+    case 0: return a == b;
+    case 1: return a != b;
+    case 2: return a < b;
+    case 3: return a <= b;
+    case 4: return a > b;
+    default: return a >= b;
+  }
+}
+
+// bytes: lexicographic unsigned compare (arrow-ord on Utf8), returns <0, 0, >0
+PQ_HD int cmp_bytes(const uint8_t* a, uint32_t na, const uint8_t* b, uint32_t nb) {
+  uint32_t n = na < nb ? na : nb;
+  for (uint32_t i = 0; i < n; i++) {
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  }
+  return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+PQ_HD bool cmp_result(int c, uint32_t op) {
+  switch (op) {
+    case 0: return c == 0;
+    case 1: return c != 0;
+    case 2: return c < 0;
+    case 3: return c <= 0;
+    case 4: return c > 0;
+    default: return c >= 0;
+  }
+}
+
+// 64-bit mix (splitmix64 finaliser) and FNV-style byte hash for dictionary keys.
+PQ_HD uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+PQ_HD uint64_t hash_bytes(const uint8_t* p, uint32_t n) {
+  uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t(n) * 0x9e3779b97f4a7c15ull);
+  for (uint32_t i = 0; i < n; i++) { h ^= p[i]; h *= 0x100000001b3ull; }
+  return mix64(h);
+}
+
+// ---- SQL LIKE over raw bytes (arrow-string like.rs semantics: '%' any run, '_' one
+// character, ESCAPE '\').  Patterns are classified on the host; the device sees the
+// cooked needle.  kinds: 0 equals, 1 starts-with, 2 ends-with, 3 contains, 4 general.
+enum LikeKind : uint32_t { LIKE_EQ = 0, LIKE_PREFIX = 1, LIKE_SUFFIX = 2, LIKE_CONTAINS = 3, LIKE_GENERAL = 4 };
+
+PQ_HD uint8_t ascii_lower(uint8_t c) { return (c >= 'A' && c <= 'Z') ? uint8_t(c + 32) : c; }
+
+PQ_HD bool bytes_eq_ci(const uint8_t* a, const uint8_t* b, uint32_t n, bool ci) {
+  for (uint32_t i = 0; i < n; i++) {
+    uint8_t x = a[i], y = b[i];
+    if (ci) { x = ascii_lower(x); y = ascii_lower(y); }
+    if (x != y) return false;
+  }
+  return true;
+}
+
+// utf-8 aware advance by one character
+PQ_HD uint32_t utf8_next(const uint8_t* s, uint32_t i, uint32_t n) {
+  i++;
+  while (i < n && (s[i] & 0xc0) == 0x80) i++;
+  return i;
+}
+
+// General matcher on the raw pattern (with escapes), iterative with single backtrack
+// point (classic wildcard algorithm).
+PQ_HD bool like_general(const uint8_t* s, uint32_t n, const uint8_t* p, uint32_t m, bool ci) {
+  uint32_t si = 0, pi = 0;
+  uint32_t star_p = 0xffffffffu, star_s = 0;
+  while (si < n) {
+    bool adv = false;
+    if (pi < m) {
+      uint8_t c = p[pi];
+      if (c == '%') { star_p = ++pi; star_s = si; continue; }
+      if (c == '_') { si = utf8_next(s, si, n); pi++; continue; }
+      uint32_t lit = pi;
+      if (c == '\\' && pi + 1 < m) lit = pi + 1;
+      uint8_t x = s[si], y = p[lit];
+      if (ci) { x = ascii_lower(x); y = ascii_lower(y); }
+      if (x == y) { si++; pi = lit + 1; adv = true; }
+    }
+    if (adv) continue;
+    if (star_p == 0xffffffffu) return false;
+    star_s = utf8_next(s, star_s, n);
+    si = star_s;
+    pi = star_p;
+  }
+  while (pi < m && p[pi] == '%') pi++;
+  return pi == m;
+}
+
+PQ_HD bool like_match(const uint8_t* s, uint32_t n, const uint8_t* needle, uint32_t m, uint32_t kind, bool ci) {
+  switch (kind) {
+    case LIKE_EQ: return n == m && bytes_eq_ci(s, needle, m, ci);
+    case LIKE_PREFIX: return n >= m && bytes_eq_ci(s, needle, m, ci);
+    case LIKE_SUFFIX: return n >= m && bytes_eq_ci(s + (n - m), needle, m, ci);
+    case LIKE_CONTAINS: {
+      if (m == 0) return true;
+      if (n < m) return false;
+      for (uint32_t i = 0; i + m <= n; i++)
+        if (bytes_eq_ci(s + i, needle, m, ci)) return true;
+      return false;
+    }
+    default: return like_general(s, n, needle, m, ci);
+  }
+}
+
+}  // namespace pqb

@@ -1,0 +1,156 @@
+// POD structures shared by the host planner and the sm_100a kernels.
+// Vocabulary follows the reference's domain: row groups, column chunks, pages,
+// dictionaries, not ML terms.
+#pragma once
+#include <cstdint>
+
+namespace pqb {
+
+constexpr int kMaxCols = 12;      // columns one query may reference
+constexpr int kMaxLeaves = 16;    // leaf predicates
+constexpr int kMaxPredOps = 40;   // postfix program length
+constexpr int kMaxKeys = 4;       // GROUP BY columns
+constexpr int kMaxAggs = 8;       // aggregates
+constexpr int kSlabRows = 2048;   // rows decoded per CTA iteration
+constexpr int kSlabWords = kSlabRows / 32;
+constexpr int kMaxDirEntries = 64;  // run-directory entries per stream per slab
+constexpr int kDirEntryMaxValues = 512;
+constexpr int kPredStack = 8;
+
+// page value encodings as the kernels see them
+enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2 };
+// physical value kinds
+enum DevKind : uint8_t { DK_I64 = 0, DK_F64 = 1, DK_STR = 2, DK_BOOL = 3, DK_I32 = 4, DK_F32 = 5 };
+
+struct DevPage {               // one data page
+  uint64_t off;                // arena byte offset of the page payload (after its header)
+  uint32_t len;                // payload bytes
+  uint32_t num_rows;           // values incl. nulls == rows (flat schema)
+  uint32_t first_row;          // within the row group
+  uint32_t def_off, def_len;   // RLE def-level bytes inside the payload (def_len==0: no nulls possible)
+  uint32_t val_off;            // values section inside the payload
+  uint8_t enc;                 // DevEnc
+  uint8_t bit_width;           // DE_DICT: index bit width
+  uint16_t chunk_slot;         // which DevChunk of the row group (== column slot)
+  uint32_t chunk;              // index into chunks[]
+};
+
+struct DevChunk {              // one column chunk (row group x referenced column)
+  uint64_t dict_off;           // arena offset of the PLAIN dictionary payload
+  uint32_t dict_len;
+  uint32_t dict_n;             // dictionary entries (0: no dictionary page)
+  uint32_t first_page;         // into pages[]
+  uint32_t n_pages;
+  uint32_t lut_base;           // base into per-entry side tables (str offsets / leaf LUTs / gid LUTs)
+  uint32_t present;            // 0: column missing from this file -> all NULL
+};
+
+struct DevItem {               // unit of CTA work: rows between two page boundaries common to all columns
+  uint32_t rg;                 // dense row-group slot
+  uint32_t row0;               // first row inside the row group
+  uint32_t nrows;
+  uint32_t bitmap_word0;       // first word of this item's region in the selection bitmap
+  uint64_t global_row0;        // ordinal of row0 in the scanned table (row-id output)
+  uint32_t page[kMaxCols];     // page index (into pages[]) holding row0, per column slot
+};
+
+struct DevColumn {
+  uint8_t kind;                // DevKind
+  uint8_t max_def;             // 0: REQUIRED
+  uint8_t need_idx;            // stage dictionary indices in the row phase
+  uint8_t is_key;
+  uint32_t max_bw;             // widest dictionary index over all pages read
+  uint32_t has_delta, has_plain, has_dict;
+};
+
+enum DevLeafKind : uint8_t { LK_CMP = 1, LK_IS_NULL = 2, LK_IS_NOT_NULL = 3, LK_LIKE = 4 };
+
+struct DevLeaf {
+  uint8_t kind;                // DevLeafKind
+  uint8_t cmp;                 // PqCmp
+  uint8_t col;                 // column slot
+  uint8_t lit_kind;            // DevKind of the literal after coercion
+  uint32_t flags;              // like flags
+  int64_t lit_i64;             // I64/TS/BOOL literal or f64 bits
+  uint32_t str_off, str_len;   // UTF8 literal / LIKE pattern in the literal pool
+  uint32_t lut_off;            // this leaf's per-dictionary-entry LUT (bytes) starts at lut_off; entry = chunk.lut_base+idx
+  uint32_t _pad;
+};
+
+enum DevPredKind : uint8_t { PK_LEAF = 1, PK_AND = 2, PK_OR = 3, PK_NOT = 4, PK_CONST = 5 };
+struct DevPredOp { uint8_t kind; uint8_t arg; /* leaf id, or const: 0 F, 1 T, 2 NULL */ };
+
+enum DevAggFn : uint8_t { AG_COUNT_STAR = 0, AG_COUNT = 1, AG_SUM = 2, AG_MIN = 3, AG_MAX = 4, AG_AVG = 5 };
+struct DevAgg {
+  uint8_t fn;
+  uint8_t col;       // column slot
+  uint8_t kind;      // DevKind of the input (I64 / F64 / BOOL)
+  uint8_t acc_slot;  // which 8-byte accumulator array
+  uint8_t nn_slot;   // which non-null counter array (one per aggregated column)
+  uint8_t update_nn; // 1: this aggregate bumps nn[nn_slot] (first aggregate over its column)
+  uint8_t _pad[2];
+};
+
+enum DevKeyKind : uint8_t { KK_DICT_LUT = 0, KK_BOOL = 1 };
+struct DevKey {
+  uint8_t col;
+  uint8_t kind;       // DevKeyKind
+  uint16_t _pad;
+  uint32_t card;      // global distinct values; NULL takes id == card
+  uint32_t stride;    // mixed-radix stride of this key in the dense group slot
+  uint32_t gid_off;   // gid LUT base (u32 per dictionary entry, entry = chunk.lut_base+idx)
+};
+
+enum ScanMode : uint32_t { SM_FILTER = 0, SM_AGG = 1 };
+
+struct DevPlan {
+  uint32_t mode;               // ScanMode
+  uint32_t ncols;
+  uint32_t nleaves;
+  uint32_t npred;
+  uint32_t nkeys;
+  uint32_t naggs;
+  uint32_t n_acc;              // 8-byte accumulator arrays
+  uint32_t n_nn;               // non-null counter arrays
+  uint32_t nslots;             // dense group slots
+  uint32_t smem_acc;           // 1: accumulate in shared memory, flush per CTA
+  uint32_t write_bitmap;       // filter mode: store the selection bitmap
+  uint32_t n_items;
+  DevColumn cols[kMaxCols];
+  DevLeaf leaves[kMaxLeaves];
+  DevPredOp pred[kMaxPredOps];
+  DevKey keys[kMaxKeys];
+  DevAgg aggs[kMaxAggs];
+  // per accumulator array, how cells start and merge: 0 integer add (0), 1 f64 add (0.0),
+  // 2 signed min (INT64_MAX), 3 signed max (INT64_MIN); f64 MIN/MAX run on order keys
+  uint8_t acc_init[kMaxAggs * 2];
+};
+
+// Accumulator table layout (device, 8-byte cells, struct of arrays over nslots):
+//   rows[nslots]                       selected rows per group  (COUNT(*))
+//   acc[a][nslots]  a < n_acc          SUM / MIN / MAX cells (i64, f64 bits, or order-preserving f64 keys)
+//   nn[k][nslots]   k < n_nn           non-null inputs per aggregated column
+
+struct DevScanArgs {
+  const uint8_t* arena;        // encoded column chunks, HBM resident
+  const DevPage* pages;
+  const DevChunk* chunks;      // [rg_slot * ncols + col]
+  const DevItem* items;
+  const uint8_t* luts;         // leaf LUT bytes (0 false, 1 true) per dictionary entry
+  const uint32_t* gid_luts;    // group ids per dictionary entry
+  const uint8_t* lit_pool;
+  uint32_t* bitmap;            // selection bitmap, per-item word regions
+  uint32_t* item_counts;       // selected rows per item
+  unsigned long long* acc;     // accumulator table (global)
+  unsigned long long* counters;  // [0] rows selected, [1] error flag, [2] work-queue head
+};
+
+// run-directory entry produced by the stream walker
+struct DirEntry {
+  uint32_t start;    // first value (slab relative)
+  uint16_t count;
+  uint16_t kind;     // 0 RLE, 1 bit-packed
+  uint32_t payload;  // RLE: value; bit-packed: bit offset of the first value inside the window
+};
+
+}  // namespace pqb

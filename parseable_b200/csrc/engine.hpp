@@ -1,0 +1,167 @@
+// Host side of the B200 query path: HBM-resident tables of encoded column
+// chunks, query planning (row-group pruning, work items, predicate/aggregate
+// compilation) and the kernel launch sequence.  Mirrors, on the host, what
+// StandardTableProvider::scan + create_parquet_physical_plan do before
+// DataFusion's operators run (/root/reference/src/query/stream_schema_provider.rs:114-189, 526-659).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/parseable_b200.h"
+#include "device_structs.hpp"
+#include "parquet_meta.hpp"
+
+namespace pqb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define PQB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw ::pqb::Error(_e == cudaErrorMemoryAllocation ? PQ_ERR_OOM : PQ_ERR_CUDA,            \
+                         std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+  } while (0)
+
+// ---- process-wide state ----
+class Context {
+ public:
+  static Context& get();
+  void init(const int* devices, int n);
+  void shutdown();
+  void ensure();  // throws PQ_ERR_CUDA when no device is usable; binds the device to the calling thread
+  int device() const { return device_; }
+  int sm_count() const { return sm_count_; }
+  size_t smem_optin() const { return smem_optin_; }
+  // pinned staging buffers, grow-only cache
+  uint8_t* pinned_acquire(size_t bytes);
+  void pinned_release(uint8_t* p);
+  bool is_pinned(const void* p);
+
+ private:
+  std::mutex mu_;
+  bool inited_ = false;
+  int device_ = 0;
+  int sm_count_ = 0;
+  size_t smem_optin_ = 0;
+  struct Pinned { uint8_t* p; size_t cap; bool busy; };
+  std::vector<Pinned> pinned_;
+};
+
+// ---- host view of a Parquet file ----
+struct HostFile {
+  std::string path;
+  const uint8_t* data = nullptr;  // whole file image (mmap or caller buffer)
+  uint64_t size = 0;
+  bool mapped = false;
+  FileMeta meta;
+  ~HostFile();
+};
+
+struct TablePageRef {
+  uint32_t first_page = 0;  // into Table::pages (data pages only)
+  uint32_t n_pages = 0;
+};
+
+struct TableChunk {
+  bool present = false;
+  int leaf = -1;
+  const ColumnChunkMeta* meta = nullptr;
+  uint64_t arena_off = 0;   // where the chunk's bytes start in the arena
+  uint64_t file_off = 0;
+  uint64_t bytes = 0;       // compressed == uncompressed (codec NONE)
+  uint64_t dict_off = 0;    // arena offset of the dictionary payload
+  uint32_t dict_len = 0, dict_n = 0;
+  TablePageRef pages;
+  bool has_dict_pages = false, has_plain_pages = false, has_delta_pages = false;
+  uint32_t max_bw = 0;
+};
+
+struct TableColumn {
+  std::string name;
+  uint8_t kind = 0;      // DevKind
+  bool is_ts = false;
+  uint8_t max_def = 0;
+};
+
+struct TableRowGroup {
+  uint32_t file = 0, rg_in_file = 0;
+  uint32_t num_rows = 0;
+  uint64_t global_row0 = 0;         // ordinal over ALL row groups of the file list (before sharding)
+  std::vector<TableChunk> chunks;   // per table column
+};
+
+// Encoded column chunks of a set of files, resident in HBM ("hot tier in HBM").
+class Table {
+ public:
+  Table() = default;
+  ~Table();
+  Table(const Table&) = delete;
+  void open(const PqFile* files, uint32_t n_files, const std::vector<std::string>& columns, uint32_t shard_index,
+            uint32_t shard_count, cudaStream_t stream);
+
+  std::vector<std::unique_ptr<HostFile>> files;
+  std::vector<TableColumn> columns;
+  std::vector<TableRowGroup> row_groups;
+  std::vector<DevPage> pages;       // host copy
+  uint8_t* d_arena = nullptr;
+  uint64_t arena_bytes = 0;
+  DevPage* d_pages = nullptr;
+  uint64_t total_rows = 0;
+  uint64_t h2d_bytes = 0;
+  uint64_t chunk_bytes = 0;
+  int find_column(const std::string& name) const;
+};
+
+struct OutColumn {
+  std::string name;
+  int type = PQ_T_I64;               // PqType
+  std::vector<uint8_t> values;       // 8-byte values, bit-packed bools, or utf8 bytes
+  std::vector<int32_t> offsets;      // utf8
+  std::vector<uint8_t> validity;     // empty when null_count == 0
+  int64_t null_count = 0;
+};
+
+struct OutBatch {
+  int64_t rows = 0;
+  std::vector<OutColumn> cols;
+};
+
+class Query {
+ public:
+  explicit Query(const PqQueryDesc& d);
+  ~Query();
+  int next(int partition, ArrowArray* out, ArrowSchema* schema);
+  PqMetrics metrics{};
+  std::string error;
+
+ private:
+  void run(const PqQueryDesc& d);
+  std::unique_ptr<Table> owned_table_;
+  std::vector<OutBatch> batches_;
+  size_t next_batch_ = 0;
+  bool schema_only_done_ = false;
+};
+
+void export_batch(const OutBatch& b, ArrowArray* out, ArrowSchema* schema);
+
+// NCCL communicator owned by the library (one process per GPU)
+int comm_unique_id(uint8_t* id);
+int comm_init_rank(const uint8_t* id, int nranks, int rank);
+int comm_destroy();
+bool comm_active();
+int comm_nranks();
+int comm_rank();
+void comm_allreduce_u64(void* buf, size_t count, int op /*0 sum,1 min(s64),2 max(s64),3 sum f64*/, cudaStream_t s);
+void comm_allgather_bytes(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
+
+}  // namespace pqb

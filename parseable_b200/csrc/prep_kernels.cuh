@@ -1,0 +1,194 @@
+// Dictionary-side kernels that run before the fused scan:
+//   * string dictionary entry offsets (PLAIN BYTE_ARRAY = 4-byte length + bytes),
+//   * leaf predicates evaluated once per DICTIONARY ENTRY into byte LUTs, so the
+//     scan tests one byte per row instead of comparing strings / floats,
+//   * GROUP BY key unification: every per-chunk dictionary entry is hashed into a
+//     global open-addressing table; its dense group id lands in a per-entry LUT.
+// This is where arrow-ord / arrow-string comparison kernels and DataFusion's
+// GroupValues interning are restated for the GPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "decode_core.cuh"
+#include "device_structs.hpp"
+
+namespace pqb {
+
+struct DevPrepArgs {
+  const uint8_t* arena;
+  const DevChunk* chunks;   // [rg_slot * ncols + col]
+  uint32_t n_chunks;        // rg_slots * ncols
+  uint32_t ncols;
+  uint64_t* ent_off;        // per dictionary entry: arena offset of its bytes (strings: after the length prefix)
+  uint8_t* luts;
+  uint32_t* gid_luts;
+  const uint8_t* lit_pool;
+  unsigned long long* counters;  // [1] error flag
+};
+
+// needs[col] bit 0: entry offsets wanted for this column
+__global__ void k_dict_entry_offsets(DevPrepArgs a, const uint8_t* __restrict__ col_kind,
+                                     const uint8_t* __restrict__ col_needs) {
+  uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= a.n_chunks) return;
+  const DevChunk ch = a.chunks[ci];
+  uint32_t col = ci % a.ncols;
+  if (!ch.present || ch.dict_n == 0 || !col_needs[col]) return;
+  uint64_t* out = a.ent_off + ch.lut_base;
+  if (col_kind[col] == DK_STR) {
+    uint64_t p = ch.dict_off, end = ch.dict_off + ch.dict_len;
+    for (uint32_t i = 0; i < ch.dict_n; i++) {
+      if (p + 4 > end) { atomicExch(&a.counters[1], 3ull); return; }
+      uint32_t len = load_u32_unaligned(a.arena + p);
+      out[i] = p + 4;
+      p += 4 + uint64_t(len);
+    }
+    if (p > end) atomicExch(&a.counters[1], 3ull);
+  } else {
+    for (uint32_t i = 0; i < ch.dict_n; i++) out[i] = ch.dict_off + uint64_t(i) * 8;
+  }
+}
+
+__device__ __forceinline__ uint32_t entry_len(const uint8_t* arena, uint64_t off, uint8_t kind) {
+  return kind == DK_STR ? load_u32_unaligned(arena + off - 4) : 8u;
+}
+
+// grid.x = chunk, grid.y = blocks over entries
+__global__ void k_leaf_luts(DevPrepArgs a, const __grid_constant__ DevPlan plan) {
+  uint32_t ci = blockIdx.x;
+  const DevChunk ch = a.chunks[ci];
+  uint32_t col = ci % a.ncols;
+  if (!ch.present || ch.dict_n == 0) return;
+  const uint8_t kind = plan.cols[col].kind;
+  for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
+    for (uint32_t l = 0; l < plan.nleaves; l++) {
+      const DevLeaf& lf = plan.leaves[l];
+      if (lf.col != col || (lf.kind != LK_CMP && lf.kind != LK_LIKE)) continue;
+      bool t;
+      if (kind == DK_STR) {
+        uint64_t off = a.ent_off[ch.lut_base + e];
+        uint32_t len = load_u32_unaligned(a.arena + off - 4);
+        const uint8_t* s = a.arena + off;
+        const uint8_t* lit = a.lit_pool + lf.str_off;
+        if (lf.kind == LK_CMP) t = cmp_result(cmp_bytes(s, len, lit, lf.str_len), lf.cmp);
+        else {
+          t = like_match(s, len, lit, lf.str_len, lf.cmp, (lf.flags & 2u) != 0);
+          if (lf.flags & 1u) t = !t;
+        }
+      } else if (kind == DK_I64) {
+        t = cmp_i64((int64_t)load_u64_unaligned(a.arena + ch.dict_off + uint64_t(e) * 8), lf.lit_i64, lf.cmp);
+      } else if (kind == DK_F64) {
+        t = cmp_i64(f64_order_key(load_u64_unaligned(a.arena + ch.dict_off + uint64_t(e) * 8)),
+                    f64_order_key((uint64_t)lf.lit_i64), lf.cmp);
+      } else {
+        t = false;
+      }
+      a.luts[lf.lut_off + ch.lut_base + e] = t ? 1 : 0;
+    }
+  }
+}
+
+// ---- GROUP BY key interning ----
+struct DevKeyTable {
+  unsigned long long* slots;  // 0 empty, else (hash32 << 32) | (global entry index + 1)
+  uint32_t* gid_of_slot;
+  uint32_t* rep_of_gid;       // representative global entry index per group id
+  uint32_t* counter;          // [0] distinct count, [1] overflow flag
+  uint32_t cap_mask;
+  uint32_t col;
+  uint32_t gid_off;           // into gid_luts
+  uint32_t kind;              // DevKind
+};
+
+__device__ __forceinline__ bool entry_equal(const uint8_t* arena, uint64_t oa, uint64_t ob, uint32_t len, uint8_t kind) {
+  if (kind != DK_STR) return load_u64_unaligned(arena + oa) == load_u64_unaligned(arena + ob);
+  if (load_u32_unaligned(arena + ob - 4) != len) return false;
+  for (uint32_t i = 0; i < len; i++)
+    if (arena[oa + i] != arena[ob + i]) return false;
+  return true;
+}
+
+// mode 0: insert + number; mode 1: lookup -> gid_luts
+__global__ void k_key_intern(DevPrepArgs a, DevKeyTable t, int mode) {
+  uint32_t ci = blockIdx.x * a.ncols + t.col;  // grid.x = row-group slots
+  const DevChunk ch = a.chunks[ci];
+  if (!ch.present || ch.dict_n == 0) return;
+  for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
+    uint32_t ge = ch.lut_base + e;
+    uint64_t off = a.ent_off[ge];
+    uint32_t len = entry_len(a.arena, off, (uint8_t)t.kind);
+    uint64_t h = t.kind == DK_STR ? hash_bytes(a.arena + off, len) : mix64(load_u64_unaligned(a.arena + off));
+    uint32_t h32 = uint32_t(h >> 32);
+    unsigned long long word = ((unsigned long long)h32 << 32) | (unsigned long long)(ge + 1);
+    uint32_t slot = uint32_t(h) & t.cap_mask;
+    uint32_t probes = 0;
+    for (;;) {
+      unsigned long long cur = t.slots[slot];
+      if (cur == 0 && mode == 0) {
+        unsigned long long prev = atomicCAS(&t.slots[slot], 0ull, word);
+        if (prev == 0) {
+          uint32_t gid = atomicAdd(&t.counter[0], 1u);
+          t.gid_of_slot[slot] = gid;
+          t.rep_of_gid[gid] = ge;
+          break;
+        }
+        cur = prev;
+      }
+      if (cur == 0) { atomicExch(&t.counter[1], 2u); break; }  // lookup miss: cannot happen
+      if (uint32_t(cur >> 32) == h32) {
+        uint32_t other = uint32_t(cur & 0xffffffffull) - 1;
+        if (other == ge || entry_equal(a.arena, off, a.ent_off[other], len, (uint8_t)t.kind)) {
+          if (mode == 1) a.gid_luts[t.gid_off + ge] = t.gid_of_slot[slot];
+          break;
+        }
+      }
+      slot = (slot + 1) & t.cap_mask;
+      if (++probes > t.cap_mask) { atomicExch(&t.counter[1], 1u); break; }
+    }
+  }
+}
+
+// accumulator table initialisation: rows / sums / nn = 0, MIN = INT64_MAX, MAX = INT64_MIN
+__global__ void k_acc_init(unsigned long long* acc, uint32_t nslots, uint32_t n_acc, uint32_t cells,
+                           const __grid_constant__ DevPlan plan) {
+  uint64_t n = uint64_t(nslots) * cells;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    uint32_t arr = uint32_t(i / nslots);
+    unsigned long long init = 0;
+    if (arr >= 1 && arr < 1 + n_acc) {
+      uint8_t k = plan.acc_init[arr - 1];
+      init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
+    }
+    acc[i] = init;
+  }
+}
+
+// compact non-empty groups: out_slot[n], out_cells[cell][n]
+__global__ void k_agg_compact(const unsigned long long* acc, uint32_t nslots, uint32_t cells, uint32_t* out_count,
+                              uint32_t* out_slot, unsigned long long* out_cells, uint32_t out_cap) {
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    if (acc[s] == 0) continue;
+    uint32_t o = atomicAdd(out_count, 1u);
+    if (o >= out_cap) continue;
+    out_slot[o] = s;
+    for (uint32_t c = 0; c < cells; c++) out_cells[uint64_t(c) * out_cap + o] = acc[uint64_t(c) * nslots + s];
+  }
+}
+
+// key value export: lengths, then bytes at host-computed offsets
+__global__ void k_key_lens(const uint8_t* arena, const uint64_t* ent_off, const uint32_t* rep_of_gid, uint32_t card,
+                           uint8_t kind, uint32_t* lens) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= card) return;
+  lens[g] = entry_len(arena, ent_off[rep_of_gid[g]], kind);
+}
+__global__ void k_key_bytes(const uint8_t* arena, const uint64_t* ent_off, const uint32_t* rep_of_gid, uint32_t card,
+                            uint8_t kind, const uint32_t* offsets, uint8_t* out) {
+  uint32_t g = blockIdx.x;
+  if (g >= card) return;
+  uint64_t off = ent_off[rep_of_gid[g]];
+  uint32_t len = entry_len(arena, off, kind);
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) out[offsets[g] + i] = arena[off + i];
+}
+
+}  // namespace pqb

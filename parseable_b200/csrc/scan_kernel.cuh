@@ -1,0 +1,601 @@
+// The fused scan kernel: Parquet page decode -> predicate bitmap -> (count /
+// selection bitmap | hash group-by accumulation) in ONE pass over the encoded
+// bytes.  Replaces, for the reference, the DataFusion operator chain
+//   DataSourceExec(Parquet) -> FilterExec -> AggregateExec(Partial)
+// that Query::execute drives (/root/reference/src/query/mod.rs:287;
+// SURVEY.md §8 rows a10-a12).
+//
+// Shape: persistent CTAs pull work items (row ranges between page boundaries
+// common to all referenced columns) from a queue.  Per 2048-row slab a CTA
+//   1. waits for the TMA bulk copies (cp.async.bulk + mbarrier) that staged the
+//      next window of every encoded stream in shared memory,
+//   2. one thread per column walks the RLE/bit-packed run headers (the only
+//      sequential part of the format) into a run directory,
+//   3. issues the TMA copies for the NEXT slab (double buffered),
+//   4. all warps expand definition levels to validity bitmaps and unpack
+//      dictionary indices from the staged bytes,
+//   5. evaluates leaf predicates (dictionary LUT hit, or compare on PLAIN
+//      values read straight from HBM with 8-byte loads), combines them with
+//      Kleene logic on 32-row words, and
+//   6. counts / stores the selection bitmap, or accumulates aggregates with
+//      shared-memory (or L2) atomics.
+// HBM traffic = the encoded bytes once + the bitmap; nothing decoded is written back.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "decode_core.cuh"
+#include "device_structs.hpp"
+#include "ptx_utils.cuh"
+
+namespace pqb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+
+// byte offsets of the dynamic shared-memory regions, computed on the host
+struct SmemLayout {
+  uint32_t defwin[kMaxCols][2];
+  uint32_t valwin[kMaxCols][2];
+  uint32_t defwin_cap[kMaxCols];
+  uint32_t valwin_cap[kMaxCols];
+  uint32_t valid[kMaxCols];   // uint32[kSlabWords + 2]
+  uint32_t rank[kMaxCols];    // uint32[kSlabWords]
+  uint32_t idx[kMaxCols];     // uint32[kSlabRows]  (0: column never dictionary encoded)
+  uint32_t defdir[kMaxCols];  // DirEntry[kMaxDirEntries]
+  uint32_t valdir[kMaxCols];
+  uint32_t leafT, leafN;      // uint32[nleaves][kSlabWords]
+  uint32_t sel;               // uint32[kSlabWords]
+  uint32_t acc;               // shared accumulator table
+  uint32_t total;
+};
+
+// per-column cursor over the pages of one column chunk
+struct ColCursor {
+  StreamState def, val;
+  uint64_t val_base;        // arena offset of the values section of the current page
+  uint64_t defwin_base[2];  // arena base of the staged windows
+  uint64_t valwin_base[2];
+  uint32_t page;
+  uint32_t page_end;        // one past the chunk's last page
+  uint32_t page_rows_left;
+  uint32_t vals_done;       // non-null values consumed in the current page
+  uint32_t enc;
+  uint32_t has_def;
+  uint32_t present;
+  uint32_t _pad;
+};
+
+// what the row phase needs to know about a column for the CURRENT slab
+struct SlabCol {
+  uint64_t val_base;
+  uint64_t dict_off;
+  uint32_t vals_done;
+  uint32_t enc;
+  uint32_t bw;
+  uint32_t present;
+  uint32_t all_valid;
+  uint32_t nv;
+  uint32_t ndef, nval;
+  uint32_t lut_base;
+  uint32_t _pad;
+};
+
+struct ScanCtl {
+  uint64_t mbar[2];
+  uint32_t item;
+  uint32_t error;
+  uint32_t sel_count;
+  uint32_t _pad;
+  uint32_t rmin[kMaxCols];
+  ColCursor cur[kMaxCols];
+  SlabCol slab[kMaxCols];
+};
+
+__device__ __forceinline__ void page_enter(ColCursor& c, const DevPage* pages, uint32_t pg) {
+  const DevPage p = pages[pg];
+  c.page = pg;
+  c.page_rows_left = p.num_rows;
+  c.vals_done = 0;
+  c.enc = p.enc;
+  c.has_def = p.def_len != 0;
+  c.val_base = p.off + p.val_off;
+  stream_init(c.def, p.off + p.def_off, p.off + p.def_off + p.def_len, 1);
+  stream_init(c.val, p.off + p.val_off, p.off + p.len, p.bit_width);
+}
+
+// thread 0: stage the windows every stream needs next into buffer `buf`
+__device__ __forceinline__ void issue_windows(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                              const uint8_t* arena, uint32_t ncols, uint32_t buf) {
+  uint32_t bytes = 0;
+  for (uint32_t c = 0; c < ncols; c++) {
+    const ColCursor& cr = ctl.cur[c];
+    if (!cr.present) continue;
+    if (cr.has_def) bytes += L.defwin_cap[c];
+    if (cr.enc == DE_DICT) bytes += L.valwin_cap[c];
+  }
+  mbar_arrive_expect_tx(&ctl.mbar[buf], bytes);
+  for (uint32_t c = 0; c < ncols; c++) {
+    ColCursor& cr = ctl.cur[c];
+    if (!cr.present) continue;
+    if (cr.has_def) {
+      uint64_t s = stream_window_start(cr.def) & ~15ull;
+      cr.defwin_base[buf] = s;
+      tma_load_1d(smem + L.defwin[c][buf], arena + s, L.defwin_cap[c], &ctl.mbar[buf]);
+    }
+    if (cr.enc == DE_DICT) {
+      uint64_t s = stream_window_start(cr.val) & ~15ull;
+      cr.valwin_base[buf] = s;
+      tma_load_1d(smem + L.valwin[c][buf], arena + s, L.valwin_cap[c], &ctl.mbar[buf]);
+    }
+  }
+}
+
+// expand a run directory of 1-bit values into a bitmap (OR into pre-zeroed words)
+__device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent, const uint32_t* win,
+                                              uint32_t* bm) {
+  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
+    const DirEntry d = dir[e];
+    for (uint32_t k = 0; k < d.count; k += 32) {
+      uint32_t j = k + lane_id();
+      uint32_t bit = 0;
+      if (j < d.count) bit = d.kind ? bp_get(win, d.payload, 1, j) : (d.payload & 1);
+      uint32_t word = __ballot_sync(0xffffffffu, bit);
+      if (lane_id() == 0 && word) {
+        uint32_t pos = d.start + k;
+        uint32_t sh = pos & 31;
+        atomicOr(&bm[pos >> 5], word << sh);
+        if (sh) {
+          uint32_t hi = word >> (32 - sh);
+          if (hi) atomicOr(&bm[(pos >> 5) + 1], hi);
+        }
+      }
+    }
+  }
+}
+
+// unpack a run directory of dictionary indices into idx[0..nv)
+__device__ __forceinline__ void dir_to_idx(const DirEntry* dir, uint32_t nent, const uint32_t* win, uint32_t bw,
+                                           uint32_t* idx) {
+  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
+    const DirEntry d = dir[e];
+    if (d.kind) {
+      for (uint32_t j = lane_id(); j < d.count; j += 32) idx[d.start + j] = bp_get(win, d.payload, bw, j);
+    } else {
+      for (uint32_t j = lane_id(); j < d.count; j += 32) idx[d.start + j] = d.payload;
+    }
+  }
+}
+
+struct RowVal {
+  bool valid;
+  uint32_t j;  // rank among the non-null values of the slab
+};
+
+__device__ __forceinline__ RowVal row_rank(const SlabCol& c, const uint32_t* valid, const uint32_t* rank, uint32_t r) {
+  RowVal o;
+  if (!c.present) { o.valid = false; o.j = 0; return o; }
+  if (c.all_valid) { o.valid = true; o.j = r; return o; }
+  uint32_t w = valid[r >> 5];
+  o.valid = (w >> (r & 31)) & 1;
+  o.j = rank[r >> 5] + __popc(w & ((1u << (r & 31)) - 1u));
+  return o;
+}
+
+// 8-byte value of a non-null row: dictionary entry or PLAIN slot
+__device__ __forceinline__ uint64_t value_u64(const SlabCol& c, const uint8_t* arena, const uint32_t* idx, uint32_t j) {
+  if (c.enc == DE_DICT) return load_u64_unaligned(arena + c.dict_off + uint64_t(idx[j]) * 8);
+  return load_u64_unaligned(arena + c.val_base + uint64_t(c.vals_done + j) * 8);
+}
+__device__ __forceinline__ uint32_t value_bool(const SlabCol& c, const uint8_t* arena, uint32_t j) {
+  uint32_t k = c.vals_done + j;
+  return (arena[c.val_base + (k >> 3)] >> (k & 7)) & 1;
+}
+
+template <typename T>
+__device__ __forceinline__ T* smem_at(uint8_t* base, uint32_t off) {
+  return reinterpret_cast<T*>(base + off);
+}
+
+__device__ __forceinline__ void acc_apply(unsigned long long* cell, uint32_t fn, uint32_t kind, uint64_t bits) {
+  if (fn == AG_SUM) {
+    if (kind == DK_F64) atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double((long long)bits));
+    else atomicAdd(cell, (unsigned long long)bits);  // wrapping, like DataFusion's SUM(Int64)
+  } else if (fn == AG_AVG) {
+    double v = kind == DK_F64 ? __longlong_as_double((long long)bits) : double((long long)bits);
+    atomicAdd(reinterpret_cast<double*>(cell), v);
+  } else {
+    long long k = kind == DK_F64 ? (long long)f64_order_key(bits) : (long long)bits;
+    if (fn == AG_MIN) atomicMin(reinterpret_cast<long long*>(cell), k);
+    else atomicMax(reinterpret_cast<long long*>(cell), k);
+  }
+}
+
+// merge one accumulator cell of a CTA-private (shared memory) table into the global table
+__device__ __forceinline__ void acc_merge(unsigned long long* cell, uint32_t how, unsigned long long v) {
+  // how: 0 integer add, 1 f64 add, 2 min (signed), 3 max (signed)
+  if (how == 0) atomicAdd(cell, v);
+  else if (how == 1) atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double((long long)v));
+  else if (how == 2) atomicMin(reinterpret_cast<long long*>(cell), (long long)v);
+  else atomicMax(reinterpret_cast<long long*>(cell), (long long)v);
+}
+
+__device__ __forceinline__ uint32_t row_mask(uint32_t w, uint32_t R) {
+  uint32_t lo = w * 32;
+  if (R <= lo) return 0;
+  uint32_t n = R - lo;
+  return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  ScanCtl& ctl = *reinterpret_cast<ScanCtl*>(smem);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ncols = plan.ncols;
+  const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
+  const bool agg_mode = plan.mode == SM_AGG;
+
+  if (tid == 0) {
+    mbar_init(&ctl.mbar[0], 1);
+    mbar_init(&ctl.mbar[1], 1);
+    mbar_fence_init();
+    ctl.error = 0;
+  }
+  unsigned long long* sacc = smem_at<unsigned long long>(smem, L.acc);
+  if (agg_mode && plan.smem_acc) {
+    for (uint32_t i = tid; i < cells * plan.nslots; i += kScanThreads) {
+      uint32_t arr = i / plan.nslots;
+      unsigned long long init = 0;
+      if (arr >= 1 && arr < 1 + plan.n_acc) {
+        uint8_t k = plan.acc_init[arr - 1];
+        init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
+      }
+      sacc[i] = init;
+    }
+  }
+  __syncthreads();
+  unsigned long long* acc = (agg_mode && plan.smem_acc) ? sacc : a.acc;
+  const uint32_t nslots = plan.nslots;
+
+  uint32_t phases = 0;  // bit b: parity to wait for on mbar[b]
+  uint32_t* selw = smem_at<uint32_t>(smem, L.sel);
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) ctl.item = (uint32_t)atomicAdd(&a.counters[2], 1ull);
+    __syncthreads();
+    const uint32_t item_id = ctl.item;
+    if (item_id >= plan.n_items) break;
+    const DevItem& item = a.items[item_id];
+
+    if (tid < ncols) {
+      ColCursor& c = ctl.cur[tid];
+      const DevChunk ch = a.chunks[item.rg * ncols + tid];
+      SlabCol& s = ctl.slab[tid];
+      s.lut_base = ch.lut_base;
+      s.dict_off = ch.dict_off;
+      s.present = ch.present;
+      c.present = ch.present;
+      c.page_end = ch.first_page + ch.n_pages;
+      if (ch.present) page_enter(c, a.pages, item.page[tid]);
+      else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
+    }
+    if (tid == 0) ctl.sel_count = 0;
+    __syncthreads();
+
+    uint32_t rows_left = item.nrows;
+    uint32_t r_item = 0;
+    uint32_t buf = 0;
+    if (tid == 0) issue_windows(ctl, L, smem, a.arena, ncols, buf);
+
+    while (rows_left > 0) {
+      // ---- 1. wait for this slab's staged bytes ----
+      mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+
+      uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
+      for (uint32_t c = 0; c < ncols; c++) {
+        uint32_t pl = ctl.cur[c].page_rows_left;
+        R = pl < R ? pl : R;
+      }
+
+      // ---- 2. walk run headers: one thread per column; retries only for pathological encodings ----
+      StreamState snap_def, snap_val;
+      if (tid < ncols) { snap_def = ctl.cur[tid].def; snap_val = ctl.cur[tid].val; }
+      for (int attempt = 0; attempt < 4 && R > 0; attempt++) {
+        if (tid < ncols) {  // 2a. definition levels
+          ColCursor& c = ctl.cur[tid];
+          SlabCol& s = ctl.slab[tid];
+          uint32_t got = R;
+          s.ndef = 0;
+          s.all_valid = 1;
+          if (c.present && c.has_def) {
+            Window w{smem + L.defwin[tid][buf], c.defwin_base[buf], L.defwin_cap[tid]};
+            DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[tid]);
+            uint32_t n = 0;
+            got = walk_stream(c.def, w, R, dir, n, kMaxDirEntries);
+            s.ndef = n;
+            uint32_t allv = 1;
+            for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
+            s.all_valid = allv;
+          }
+          ctl.rmin[tid] = got;
+        }
+        for (uint32_t c = 0; c < ncols; c++) {
+          uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
+          for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kScanThreads) bm[w] = 0;
+        }
+        __syncthreads();
+        uint32_t R1 = R;
+        for (uint32_t c = 0; c < ncols; c++) R1 = ctl.rmin[c] < R1 ? ctl.rmin[c] : R1;
+        if (R1 < R) {  // a definition-level window / directory ran out: shrink the slab, redo
+          if (tid < ncols) ctl.cur[tid].def = snap_def;
+          R = R1;
+          __syncthreads();
+          continue;
+        }
+        // 2b. validity bitmaps, ranks, non-null counts
+        for (uint32_t c = 0; c < ncols; c++) {
+          const SlabCol& s = ctl.slab[c];
+          if (s.present && !s.all_valid)
+            dir_to_bitmap(smem_at<DirEntry>(smem, L.defdir[c]), s.ndef, smem_at<uint32_t>(smem, L.defwin[c][buf]),
+                          smem_at<uint32_t>(smem, L.valid[c]));
+        }
+        __syncthreads();
+        for (uint32_t c = warp_id(); c < ncols; c += kScanWarps) {
+          SlabCol& s = ctl.slab[c];
+          if (!s.present) { if (lane_id() == 0) s.nv = 0; continue; }
+          if (s.all_valid) { if (lane_id() == 0) s.nv = R; continue; }
+          uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
+          uint32_t* rk = smem_at<uint32_t>(smem, L.rank[c]);
+          uint32_t w0 = lane_id() * 2, w1 = w0 + 1;
+          uint32_t a0 = bm[w0] & row_mask(w0, R), a1 = bm[w1] & row_mask(w1, R);
+          uint32_t p0 = __popc(a0), p1 = __popc(a1);
+          uint32_t sum = p0 + p1, incl = sum;
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane_id() >= o) incl += t;
+          }
+          uint32_t excl = incl - sum;
+          rk[w0] = excl;
+          rk[w1] = excl + p0;
+          bm[w0] = a0;
+          bm[w1] = a1;
+          if (lane_id() == 31) s.nv = incl;
+        }
+        __syncthreads();
+        if (tid < ncols) {  // 2c. dictionary-index streams
+          ColCursor& c = ctl.cur[tid];
+          SlabCol& s = ctl.slab[tid];
+          uint32_t rc = R;
+          s.nval = 0;
+          if (c.present && c.enc == DE_DICT && s.nv > 0) {
+            Window w{smem + L.valwin[tid][buf], c.valwin_base[buf], L.valwin_cap[tid]};
+            DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[tid]);
+            uint32_t n = 0;
+            uint32_t got = walk_stream(c.val, w, s.nv, dir, n, kMaxDirEntries);
+            s.nval = n;
+            if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
+              if (s.all_valid) rc = got;
+              else {
+                const uint32_t* bm = smem_at<uint32_t>(smem, L.valid[tid]);
+                uint32_t seen = 0;
+                rc = 0;
+                for (uint32_t r = 0; r < R; r++) {
+                  uint32_t b = (bm[r >> 5] >> (r & 31)) & 1;
+                  if (b && seen == got) break;
+                  seen += b;
+                  rc = r + 1;
+                }
+              }
+            }
+          }
+          ctl.rmin[tid] = rc;
+        }
+        __syncthreads();
+        uint32_t R2 = R;
+        for (uint32_t c = 0; c < ncols; c++) R2 = ctl.rmin[c] < R2 ? ctl.rmin[c] : R2;
+        if (R2 < R) {  // an index window / directory ran out: shrink and redo everything
+          if (tid < ncols) { ctl.cur[tid].def = snap_def; ctl.cur[tid].val = snap_val; }
+          R = R2;
+          __syncthreads();
+          continue;
+        }
+        break;
+      }
+      if (R == 0) {  // no progress possible: corrupt page
+        if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
+        break;
+      }
+
+      // ---- 3. freeze this slab's view, advance cursors, prefetch the next slab ----
+      if (tid < ncols) {
+        ColCursor& c = ctl.cur[tid];
+        SlabCol& s = ctl.slab[tid];
+        s.val_base = c.val_base;
+        s.vals_done = c.vals_done;
+        s.enc = c.enc;
+        s.bw = c.val.bw;
+        if (c.present) {
+          c.vals_done += s.nv;
+          c.page_rows_left -= R;
+          if (c.page_rows_left == 0 && rows_left > R) {
+            if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+            else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+          }
+        }
+      }
+      __syncthreads();
+      if (ctl.error) break;
+      if (tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1);
+
+      // ---- 4. unpack dictionary indices ----
+      for (uint32_t c = 0; c < ncols; c++) {
+        const SlabCol& s = ctl.slab[c];
+        if (s.present && s.enc == DE_DICT && s.nv > 0)
+          dir_to_idx(smem_at<DirEntry>(smem, L.valdir[c]), s.nval, smem_at<uint32_t>(smem, L.valwin[c][buf]), s.bw,
+                     smem_at<uint32_t>(smem, L.idx[c]));
+      }
+      __syncthreads();
+
+      // ---- 5. leaf predicates -> (T, N) bitmaps, 32 rows per warp step ----
+      const uint32_t nwords = (R + 31) >> 5;
+      for (uint32_t l = 0; l < plan.nleaves; l++) {
+        const DevLeaf& lf = plan.leaves[l];
+        const SlabCol& s = ctl.slab[lf.col];
+        const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
+        const uint32_t* rk = smem_at<uint32_t>(smem, L.rank[lf.col]);
+        const uint32_t* idx = smem_at<uint32_t>(smem, L.idx[lf.col]);
+        uint32_t* Tw = smem_at<uint32_t>(smem, L.leafT) + l * kSlabWords;
+        uint32_t* Nw = smem_at<uint32_t>(smem, L.leafN) + l * kSlabWords;
+        const uint8_t kind = plan.cols[lf.col].kind;
+        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
+          uint32_t r = r0 + lane_id();
+          bool t = false, n = false;
+          if (r < R) {
+            RowVal rv = row_rank(s, vbm, rk, r);
+            if (lf.kind == LK_IS_NULL) t = !rv.valid;
+            else if (lf.kind == LK_IS_NOT_NULL) t = rv.valid;
+            else if (!rv.valid) n = true;
+            else if (s.enc == DE_DICT) t = a.luts[lf.lut_off + s.lut_base + idx[rv.j]] != 0;
+            else if (kind == DK_BOOL) {
+              uint32_t v = value_bool(s, a.arena, rv.j);
+              t = cmp_i64((int64_t)v, lf.lit_i64, lf.cmp);
+            } else if (kind == DK_I64) {
+              t = cmp_i64((int64_t)value_u64(s, a.arena, idx, rv.j), lf.lit_i64, lf.cmp);
+            } else if (kind == DK_F64) {
+              t = cmp_i64(f64_order_key(value_u64(s, a.arena, idx, rv.j)), f64_order_key((uint64_t)lf.lit_i64), lf.cmp);
+            } else {  // PLAIN byte arrays are rejected on the host (PQ_ERR_UNSUPPORTED)
+              n = true;
+            }
+          }
+          uint32_t tw = __ballot_sync(0xffffffffu, t);
+          uint32_t nw = __ballot_sync(0xffffffffu, n);
+          if (lane_id() == 0) { Tw[r0 >> 5] = tw; Nw[r0 >> 5] = nw; }
+        }
+      }
+      __syncthreads();
+
+      // ---- 6. Kleene combine on words -> selection ----
+      for (uint32_t w = tid; w < nwords; w += kScanThreads) {
+        uint32_t st_t[kPredStack], st_n[kPredStack];
+        int sp = 0;
+        const uint32_t* LT = smem_at<uint32_t>(smem, L.leafT);
+        const uint32_t* LN = smem_at<uint32_t>(smem, L.leafN);
+        for (uint32_t i = 0; i < plan.npred; i++) {
+          const DevPredOp op = plan.pred[i];
+          if (op.kind == PK_LEAF) {
+            st_t[sp] = LT[op.arg * kSlabWords + w];
+            st_n[sp] = LN[op.arg * kSlabWords + w];
+            sp++;
+          } else if (op.kind == PK_CONST) {
+            st_t[sp] = op.arg == 1 ? 0xffffffffu : 0u;
+            st_n[sp] = op.arg == 2 ? 0xffffffffu : 0u;
+            sp++;
+          } else if (op.kind == PK_NOT) {
+            st_t[sp - 1] = ~(st_t[sp - 1] | st_n[sp - 1]);
+          } else {
+            uint32_t tb = st_t[sp - 1], nb = st_n[sp - 1], ta = st_t[sp - 2], na = st_n[sp - 2];
+            sp--;
+            if (op.kind == PK_AND) {
+              uint32_t fa = ~(ta | na), fb = ~(tb | nb);
+              st_t[sp - 1] = ta & tb;
+              st_n[sp - 1] = (na | nb) & ~fa & ~fb;
+            } else {
+              uint32_t t = ta | tb;
+              st_t[sp - 1] = t;
+              st_n[sp - 1] = (na | nb) & ~t;
+            }
+          }
+        }
+        uint32_t sel = (plan.npred ? st_t[0] : 0xffffffffu) & row_mask(w, R);
+        selw[w] = sel;
+      }
+      __syncthreads();
+
+      // ---- 7. consume ----
+      if (!agg_mode) {
+        uint32_t cnt = 0;
+        for (uint32_t w = tid; w < nwords; w += kScanThreads) {
+          uint32_t sel = selw[w];
+          cnt += __popc(sel);
+          if (plan.write_bitmap && sel) {
+            uint32_t pos = r_item + w * 32;
+            uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+            uint32_t sh = pos & 31;
+            if (sh == 0) *dst = sel;  // slabs are word aligned except after a pathological shrink
+            else {
+              atomicOr(dst, sel << sh);
+              uint32_t hi = sel >> (32 - sh);
+              if (hi) atomicOr(dst + 1, hi);
+            }
+          }
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
+      } else {
+        uint32_t cnt = 0;
+        for (uint32_t r = tid; r < R; r += kScanThreads) {
+          if (!((selw[r >> 5] >> (r & 31)) & 1)) continue;
+          cnt++;
+          uint32_t slot = 0;
+          for (uint32_t k = 0; k < plan.nkeys; k++) {
+            const DevKey& key = plan.keys[k];
+            const SlabCol& s = ctl.slab[key.col];
+            RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
+            uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
+            if (rv.valid) {
+              if (key.kind == KK_BOOL) gid = value_bool(s, a.arena, rv.j);
+              else gid = a.gid_luts[key.gid_off + s.lut_base + smem_at<uint32_t>(smem, L.idx[key.col])[rv.j]];
+            }
+            slot += gid * key.stride;
+          }
+          atomicAdd(&acc[slot], 1ull);
+          for (uint32_t g = 0; g < plan.naggs; g++) {
+            const DevAgg& ag = plan.aggs[g];
+            if (ag.fn == AG_COUNT_STAR) continue;
+            const SlabCol& s = ctl.slab[ag.col];
+            RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
+            if (!rv.valid) continue;
+            if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+            if (ag.fn == AG_COUNT) continue;
+            uint64_t bits = ag.kind == DK_BOOL ? value_bool(s, a.arena, rv.j)
+                                               : value_u64(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j);
+            acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
+          }
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
+      }
+
+      rows_left -= R;
+      r_item += R;
+      buf ^= 1;
+      __syncthreads();
+    }  // slabs
+    __syncthreads();
+    if (ctl.error) break;
+    if (tid == 0) {
+      if (a.item_counts) a.item_counts[item_id] = ctl.sel_count;
+      if (ctl.sel_count) atomicAdd(&a.counters[0], (unsigned long long)ctl.sel_count);
+    }
+  }  // items
+
+  // ---- flush the CTA-private accumulator table ----
+  __syncthreads();
+  if (agg_mode && plan.smem_acc && !ctl.error) {
+    for (uint32_t slot = tid; slot < nslots; slot += kScanThreads) {
+      unsigned long long rows = sacc[slot];
+      if (rows == 0) continue;
+      atomicAdd(&a.acc[slot], rows);
+      for (uint32_t arr = 0; arr < plan.n_acc; arr++)
+        acc_merge(&a.acc[(1 + arr) * nslots + slot], plan.acc_init[arr], sacc[(1 + arr) * nslots + slot]);
+      for (uint32_t k = 0; k < plan.n_nn; k++) {
+        unsigned long long v = sacc[(1 + plan.n_acc + k) * nslots + slot];
+        if (v) atomicAdd(&a.acc[(1 + plan.n_acc + k) * nslots + slot], v);
+      }
+    }
+  }
+}
+
+}  // namespace pqb

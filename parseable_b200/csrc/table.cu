@@ -1,0 +1,409 @@
+// Context + Table: footer parsing, page-header walk, and the upload of encoded
+// column chunks into one HBM arena.  Only the referenced columns of the row
+// groups this process owns (g % shard_count == shard_index, the GPU analogue of
+// partitioned_files' round-robin, stream_schema_provider.rs:351-364) are read.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+#include "engine.hpp"
+
+namespace pqb {
+
+// ---------------- Context ----------------
+Context& Context::get() {
+  static Context c;
+  return c;
+}
+
+void Context::init(const int* devices, int n) {
+  std::lock_guard<std::mutex> lk(mu_);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(PQ_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0"));
+  int dev = 0;
+  if (n > 0 && devices) dev = devices[0];
+  else if (inited_) dev = device_;
+  else {
+    const char* lr = getenv("LOCAL_RANK");
+    if (lr) dev = atoi(lr) % count;
+  }
+  if (dev < 0 || dev >= count) throw Error(PQ_ERR_INVALID_ARG, "device id out of range");
+  PQB_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PQB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) throw Error(PQ_ERR_CUDA, "parseable_b200 needs an sm_100a device (found sm_" +
+                                                     std::to_string(prop.major * 10 + prop.minor) + ")");
+  device_ = dev;
+  sm_count_ = prop.multiProcessorCount;
+  smem_optin_ = prop.sharedMemPerBlockOptin;
+  // keep freed blocks in the stream-ordered pool: query-time cudaMallocAsync stays cheap
+  cudaMemPool_t pool;
+  PQB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thresh = ~0ull;
+  PQB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  inited_ = true;
+}
+
+void Context::ensure() {
+  if (!inited_) init(nullptr, 0);
+  PQB_CUDA(cudaSetDevice(device_));
+}
+
+void Context::shutdown() {
+  std::lock_guard<std::mutex> lk(mu_);
+  for (auto& p : pinned_) cudaFreeHost(p.p);
+  pinned_.clear();
+  inited_ = false;
+}
+
+uint8_t* Context::pinned_acquire(size_t bytes) {
+  std::lock_guard<std::mutex> lk(mu_);
+  for (auto& p : pinned_)
+    if (!p.busy && p.cap >= bytes) { p.busy = true; return p.p; }
+  Pinned np{nullptr, std::max<size_t>(bytes, 1 << 20), true};
+  cudaError_t e = cudaHostAlloc((void**)&np.p, np.cap, cudaHostAllocDefault);
+  if (e != cudaSuccess) throw Error(PQ_ERR_OOM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  pinned_.push_back(np);
+  return np.p;
+}
+
+void Context::pinned_release(uint8_t* ptr) {
+  std::lock_guard<std::mutex> lk(mu_);
+  for (auto& p : pinned_)
+    if (p.p == ptr) p.busy = false;
+}
+
+bool Context::is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// ---------------- HostFile ----------------
+HostFile::~HostFile() {
+  if (mapped && data) munmap(const_cast<uint8_t*>(data), size);
+}
+
+static std::unique_ptr<HostFile> open_host_file(const PqFile& f) {
+  auto hf = std::make_unique<HostFile>();
+  if (f.buf) {
+    hf->data = f.buf;
+    hf->size = f.size;
+  } else if (f.path) {
+    hf->path = f.path;
+    int fd = ::open(f.path, O_RDONLY);
+    if (fd < 0) throw Error(PQ_ERR_IO, std::string("open ") + f.path + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); throw Error(PQ_ERR_IO, std::string("stat ") + f.path); }
+    hf->size = uint64_t(st.st_size);
+    if (hf->size) {
+      void* m = mmap(nullptr, hf->size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) { ::close(fd); throw Error(PQ_ERR_IO, std::string("mmap ") + f.path); }
+      hf->data = static_cast<const uint8_t*>(m);
+      hf->mapped = true;
+    }
+    ::close(fd);
+  } else {
+    throw Error(PQ_ERR_INVALID_ARG, "PqFile needs a path or a buffer");
+  }
+  try {
+    hf->meta = parse_footer(hf->data, hf->size);
+  } catch (const std::exception& e) {
+    throw Error(PQ_ERR_CORRUPT, (hf->path.empty() ? std::string("<buffer>") : hf->path) + ": " + e.what());
+  }
+  return hf;
+}
+
+// ---------------- Table ----------------
+Table::~Table() {
+  if (d_arena) cudaFree(d_arena);
+  if (d_pages) cudaFree(d_pages);
+}
+
+int Table::find_column(const std::string& name) const {
+  for (size_t i = 0; i < columns.size(); i++)
+    if (columns[i].name == name) return int(i);
+  return -1;
+}
+
+static uint8_t kind_of_leaf(const LeafColumn& l) {
+  switch (l.phys_type) {
+    case PT_INT64: return DK_I64;
+    case PT_DOUBLE: return DK_F64;
+    case PT_BYTE_ARRAY: return DK_STR;
+    case PT_BOOLEAN: return DK_BOOL;
+    case PT_INT32: return DK_I32;
+    case PT_FLOAT: return DK_F32;
+    default: return 0xff;
+  }
+}
+
+static uint32_t rd_u32(const uint8_t* p) {
+  uint32_t v;
+  std::memcpy(&v, p, 4);
+  return v;
+}
+
+void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std::string>& col_names,
+                 uint32_t shard_index, uint32_t shard_count, cudaStream_t stream) {
+  Context& ctx = Context::get();
+  if (shard_count == 0) shard_count = 1;
+  if (shard_index >= shard_count) throw Error(PQ_ERR_INVALID_ARG, "shard_index >= shard_count");
+  for (uint32_t i = 0; i < n_files; i++) files.push_back(open_host_file(in_files[i]));
+
+  // ---- resolve columns by NAME in every file (streams.rs:1024-1037: table schema is
+  // sorted by name, files keep write order) ----
+  columns.resize(col_names.size());
+  for (size_t c = 0; c < col_names.size(); c++) {
+    columns[c].name = col_names[c];
+    columns[c].kind = 0xff;
+  }
+  struct Copy { uint32_t file; uint64_t src_off; uint64_t dst_off; uint64_t bytes; };
+  std::vector<Copy> copies;
+  uint64_t arena = 0;
+  uint64_t global_row = 0;
+  uint64_t global_rg = 0;
+  for (uint32_t fi = 0; fi < files.size(); fi++) {
+    HostFile& hf = *files[fi];
+    std::vector<int> leaf_of(col_names.size(), -1);
+    for (size_t c = 0; c < col_names.size(); c++) {
+      int li = hf.meta.find_leaf(col_names[c]);
+      if (li < 0) {
+        // a nested column referenced by its top-level name is not a flat leaf
+        for (auto& l : hf.meta.leaves)
+          if (l.name.compare(0, col_names[c].size() + 1, col_names[c] + ".") == 0)
+            throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "' is nested (list/struct); only flat columns are on the GPU path");
+        continue;  // missing in this file: reads as all-NULL (schema adapter behaviour)
+      }
+      const LeafColumn& l = hf.meta.leaves[li];
+      if (l.max_rep != 0 || l.depth != 1 || l.max_def > 1)
+        throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "' is nested; only flat columns are on the GPU path");
+      uint8_t k = kind_of_leaf(l);
+      if (k == 0xff || k == DK_I32 || k == DK_F32)
+        throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': physical type " + std::to_string(l.phys_type) + " not supported");
+      if (columns[c].kind == 0xff) {
+        columns[c].kind = k;
+        columns[c].is_ts = l.is_timestamp_ms;
+      } else if (columns[c].kind != k) {
+        throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "' changes physical type across files");
+      }
+      if (l.is_timestamp_other)
+        throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': only Timestamp(ms) is supported");
+      columns[c].max_def = std::max<uint8_t>(columns[c].max_def, uint8_t(l.max_def));
+      leaf_of[c] = li;
+    }
+    for (uint32_t gi = 0; gi < hf.meta.row_groups.size(); gi++, global_rg++) {
+      const RowGroupMeta& g = hf.meta.row_groups[gi];
+      uint64_t row0 = global_row;
+      global_row += uint64_t(g.num_rows);
+      if (global_rg % shard_count != shard_index) continue;
+      if (g.num_rows == 0) continue;
+      TableRowGroup trg;
+      trg.file = fi;
+      trg.rg_in_file = gi;
+      trg.num_rows = uint32_t(g.num_rows);
+      trg.global_row0 = row0;
+      trg.chunks.resize(col_names.size());
+      for (size_t c = 0; c < col_names.size(); c++) {
+        TableChunk& tc = trg.chunks[c];
+        if (leaf_of[c] < 0) continue;
+        const ColumnChunkMeta& cm = g.columns[leaf_of[c]];
+        if (cm.codec != CODEC_UNCOMPRESSED)
+          throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page compression codec " +
+                                              std::to_string(cm.codec) + " is not decoded on the GPU yet (write with P_PARQUET_COMPRESSION_ALGO=uncompressed)");
+        tc.present = true;
+        tc.leaf = leaf_of[c];
+        tc.meta = &cm;
+        tc.file_off = uint64_t(cm.start());
+        tc.bytes = uint64_t(cm.total_compressed_size);
+        if (tc.file_off + tc.bytes > hf.size) throw Error(PQ_ERR_CORRUPT, "column chunk outside the file");
+        tc.arena_off = arena;
+        arena = (arena + tc.bytes + 64 + 255) & ~255ull;
+        copies.push_back({fi, tc.file_off, tc.arena_off, tc.bytes});
+        chunk_bytes += tc.bytes;
+        // ---- page walk ----
+        std::vector<PageInfo> pis;
+        try {
+          pis = walk_pages(hf.data + tc.file_off, tc.bytes, cm.num_values);
+        } catch (const std::exception& e) {
+          throw Error(PQ_ERR_CORRUPT, col_names[c] + ": " + e.what());
+        }
+        tc.pages.first_page = uint32_t(pages.size());
+        uint32_t first_row = 0;
+        const uint8_t max_def = uint8_t(hf.meta.leaves[leaf_of[c]].max_def);
+        for (const PageInfo& pi : pis) {
+          const uint8_t* payload = hf.data + tc.file_off + pi.offset_in_chunk + pi.header_len;
+          uint64_t payload_arena = tc.arena_off + pi.offset_in_chunk + pi.header_len;
+          if (pi.type == PAGE_DICTIONARY) {
+            if (pi.encoding != ENC_PLAIN && pi.encoding != ENC_PLAIN_DICTIONARY)
+              throw Error(PQ_ERR_UNSUPPORTED, "dictionary page encoding " + std::to_string(pi.encoding));
+            tc.dict_off = payload_arena;
+            tc.dict_len = pi.compressed_size;
+            tc.dict_n = pi.num_values;
+            continue;
+          }
+          if (pi.type != PAGE_DATA && pi.type != PAGE_DATA_V2) continue;
+          DevPage dp{};
+          dp.off = payload_arena;
+          dp.len = pi.compressed_size;
+          dp.num_rows = pi.num_values;
+          dp.first_row = first_row;
+          first_row += pi.num_values;
+          uint32_t pos = 0;
+          if (pi.type == PAGE_DATA) {
+            if (max_def > 0) {
+              if (pi.def_encoding != ENC_RLE) throw Error(PQ_ERR_UNSUPPORTED, "definition levels not RLE encoded");
+              if (pi.compressed_size < 4) throw Error(PQ_ERR_CORRUPT, "data page too short");
+              uint32_t dl = rd_u32(payload);
+              if (uint64_t(dl) + 4 > pi.compressed_size) throw Error(PQ_ERR_CORRUPT, "definition levels run past the page");
+              dp.def_off = 4;
+              dp.def_len = dl;
+              pos = 4 + dl;
+            }
+          } else {
+            if (pi.v2_compressed && cm.codec != CODEC_UNCOMPRESSED) throw Error(PQ_ERR_UNSUPPORTED, "compressed v2 page");
+            pos = pi.v2_rep_len;
+            if (max_def > 0) { dp.def_off = pos; dp.def_len = pi.v2_def_len; }
+            pos += pi.v2_def_len;
+          }
+          dp.val_off = pos;
+          switch (pi.encoding) {
+            case ENC_PLAIN:
+              dp.enc = DE_PLAIN;
+              tc.has_plain_pages = true;
+              break;
+            case ENC_RLE_DICTIONARY:
+            case ENC_PLAIN_DICTIONARY:
+              dp.enc = DE_DICT;
+              if (pos >= pi.compressed_size && pi.num_values > 0) {
+                // an all-null page may legally carry no index bytes
+                dp.bit_width = 0;
+              } else if (pi.num_values > 0) {
+                dp.bit_width = payload[pos];
+                dp.val_off = pos + 1;
+              }
+              if (dp.bit_width > 32) throw Error(PQ_ERR_CORRUPT, "dictionary index bit width > 32");
+              tc.has_dict_pages = true;
+              tc.max_bw = std::max<uint32_t>(tc.max_bw, dp.bit_width);
+              break;
+            case ENC_DELTA_BINARY_PACKED:
+              dp.enc = DE_DELTA;
+              tc.has_delta_pages = true;
+              break;
+            default:
+              throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page encoding " + std::to_string(pi.encoding) + " not supported");
+          }
+          pages.push_back(dp);
+        }
+        tc.pages.n_pages = uint32_t(pages.size()) - tc.pages.first_page;
+        if (first_row != trg.num_rows)
+          throw Error(PQ_ERR_CORRUPT, col_names[c] + ": page rows do not add up to the row group's");
+        if (tc.has_dict_pages && tc.dict_n == 0 && cm.num_values > 0 &&
+            (cm.stats.null_count < 0 || cm.stats.null_count < cm.num_values)) {
+          // dictionary-encoded pages without a dictionary page
+          throw Error(PQ_ERR_CORRUPT, col_names[c] + ": dictionary-encoded pages but no dictionary page");
+        }
+      }
+      total_rows += trg.num_rows;
+      row_groups.push_back(std::move(trg));
+    }
+  }
+  for (size_t c = 0; c < columns.size(); c++)
+    if (columns[c].kind == 0xff) columns[c].kind = 0xfe;  // present in no file: all NULL everywhere
+
+  // ---- one HBM arena, 64 KiB of slack so staged windows may over-read ----
+  arena_bytes = arena + (64u << 10);
+  PQB_CUDA(cudaMalloc((void**)&d_arena, arena_bytes));
+  // tail slack must be defined (walkers may look at it)
+  PQB_CUDA(cudaMemsetAsync(d_arena + arena, 0, arena_bytes - arena, stream));
+
+  // ---- upload: straight from pinned caller buffers, else staged through pinned memory ----
+  std::vector<Copy> staged;
+  std::vector<size_t> staged_orig;
+  std::vector<char> file_pinned(files.size(), 0);
+  for (size_t f = 0; f < files.size(); f++) file_pinned[f] = !files[f]->mapped && ctx.is_pinned(files[f]->data);
+  for (size_t k = 0; k < copies.size(); k++) {
+    const Copy& cp = copies[k];
+    const HostFile& hf = *files[cp.file];
+    if (file_pinned[cp.file]) {
+      PQB_CUDA(cudaMemcpyAsync(d_arena + cp.dst_off, hf.data + cp.src_off, cp.bytes, cudaMemcpyHostToDevice, stream));
+    } else {
+      staged.push_back(cp);
+      staged_orig.push_back(k);
+    }
+    h2d_bytes += cp.bytes;
+  }
+  if (!staged.empty()) {
+    // gather into pinned staging slices with a few host threads, one cudaMemcpyAsync per slice;
+    // three rotating slices bound the pinned footprint
+    const size_t kSlice = 32u << 20;
+    const int kRing = 3;
+    unsigned nthr = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    size_t i = 0;
+    uint8_t* ring[kRing] = {nullptr, nullptr, nullptr};
+    size_t ring_cap[kRing] = {0, 0, 0};
+    cudaEvent_t ring_ev[kRing];
+    for (int r = 0; r < kRing; r++) PQB_CUDA(cudaEventCreateWithFlags(&ring_ev[r], cudaEventDisableTiming));
+    int slot = 0;
+    while (i < staged.size()) {
+      // pack copies that were adjacent in the arena (nothing else lives in the gaps) into one slice
+      size_t j = i;
+      uint64_t lo = staged[i].dst_off, hi = lo;
+      while (j < staged.size() && staged[j].dst_off + staged[j].bytes - lo <= kSlice &&
+             (j == i || staged_orig[j] == staged_orig[j - 1] + 1)) {
+        hi = staged[j].dst_off + staged[j].bytes;
+        j++;
+      }
+      if (j == i) { hi = staged[i].dst_off + staged[i].bytes; j = i + 1; }
+      const int r = slot % kRing;
+      slot++;
+      if (ring[r]) PQB_CUDA(cudaEventSynchronize(ring_ev[r]));
+      if (ring_cap[r] < size_t(hi - lo)) {
+        if (ring[r]) ctx.pinned_release(ring[r]);
+        ring[r] = ctx.pinned_acquire(std::max<size_t>(size_t(hi - lo), kSlice));
+        ring_cap[r] = std::max<size_t>(size_t(hi - lo), kSlice);
+      }
+      uint8_t* buf = ring[r];
+      std::atomic<size_t> next{i};
+      auto work = [&]() {
+        for (;;) {
+          size_t k = next.fetch_add(1);
+          if (k >= j) break;
+          const Copy& cp = staged[k];
+          std::memcpy(buf + (cp.dst_off - lo), files[cp.file]->data + cp.src_off, cp.bytes);
+        }
+      };
+      unsigned use = unsigned(std::min<size_t>(nthr, j - i));
+      if (use <= 1) work();
+      else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < use; t++) th.emplace_back(work);
+        for (auto& t : th) t.join();
+      }
+      // gaps between chunks inside the slice are alignment padding: harmless to overwrite
+      PQB_CUDA(cudaMemcpyAsync(d_arena + lo, buf, size_t(hi - lo), cudaMemcpyHostToDevice, stream));
+      PQB_CUDA(cudaEventRecord(ring_ev[r], stream));
+      i = j;
+    }
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    for (int r = 0; r < kRing; r++) {
+      if (ring[r]) ctx.pinned_release(ring[r]);
+      cudaEventDestroy(ring_ev[r]);
+    }
+  }
+  if (!pages.empty()) {
+    PQB_CUDA(cudaMalloc((void**)&d_pages, pages.size() * sizeof(DevPage)));
+    PQB_CUDA(cudaMemcpyAsync(d_pages, pages.data(), pages.size() * sizeof(DevPage), cudaMemcpyHostToDevice, stream));
+  }
+  PQB_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace pqb
