@@ -225,6 +225,17 @@ int pq_query_metrics(PqQuery* q, PqMetrics* out);
 const char* pq_last_error(PqQuery* q); /* q == NULL: last error of the calling thread */
 void pq_query_close(PqQuery* q);
 
+/* ---- host helpers (no GPU work) ---- */
+/* Page-locked host memory for file images: PqFile.buf inside such a block is DMA'd straight
+ * to HBM, other host memory is staged through the library's own pinned slices. */
+void* pq_host_alloc(uint64_t bytes);
+void pq_host_free(void* p);
+/* JSON description of a Parquet file as the host metadata layer parsed it (schema leaves, row
+ * groups, column chunks, every page header).  Returns the JSON length (excluding NUL), or a
+ * negative status; writes at most cap bytes.  Replaces nothing at run time: it exists so the
+ * footer/page-header reader can be checked against an independent reader without a GPU. */
+int64_t pq_file_describe(const PqFile* file, char* out, uint64_t cap);
+
 /* ---- multi-GPU: one process per GPU, NCCL communicator owned by the library ---- */
 #define PQ_COMM_ID_BYTES 128
 int pq_comm_unique_id(uint8_t id[PQ_COMM_ID_BYTES]);

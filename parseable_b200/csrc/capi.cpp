@@ -128,6 +128,33 @@ void pq_query_close(PqQuery* q) {
   delete q;
 }
 
+void* pq_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  int rc = guard([&] {
+    Context::get().ensure();
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) throw Error(PQ_ERR_OOM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return PQ_OK;
+  });
+  return rc == PQ_OK ? p : nullptr;
+}
+void pq_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int64_t pq_file_describe(const PqFile* file, char* out, uint64_t cap) {
+  if (!file) return PQ_ERR_INVALID_ARG;
+  std::string js;
+  int rc = guard([&] { js = describe_file(*file); return PQ_OK; });
+  if (rc != PQ_OK) return rc;
+  if (out && cap) {
+    uint64_t n = js.size() < cap - 1 ? js.size() : cap - 1;
+    std::memcpy(out, js.data(), n);
+    out[n] = 0;
+  }
+  return int64_t(js.size());
+}
+
 int pq_comm_unique_id(uint8_t id[PQ_COMM_ID_BYTES]) {
   return guard([&] { return comm_unique_id(id); });
 }

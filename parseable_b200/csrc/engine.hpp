@@ -153,6 +153,7 @@ class Query {
 };
 
 void export_batch(const OutBatch& b, ArrowArray* out, ArrowSchema* schema);
+std::string describe_file(const PqFile& f);
 
 // NCCL communicator owned by the library (one process per GPU)
 int comm_unique_id(uint8_t* id);

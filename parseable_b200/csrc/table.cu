@@ -122,6 +122,65 @@ static std::unique_ptr<HostFile> open_host_file(const PqFile& f) {
   return hf;
 }
 
+static void js_str(std::string& o, const std::string& s) {
+  o.push_back('"');
+  for (unsigned char c : s) {
+    if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back(char(c)); }
+    else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o.push_back(char(c));
+  }
+  o.push_back('"');
+}
+
+std::string describe_file(const PqFile& f) {
+  auto hf = open_host_file(f);
+  std::string o = "{\"num_rows\":" + std::to_string(hf->meta.num_rows) + ",\"created_by\":";
+  js_str(o, hf->meta.created_by);
+  o += ",\"leaves\":[";
+  for (size_t i = 0; i < hf->meta.leaves.size(); i++) {
+    const LeafColumn& l = hf->meta.leaves[i];
+    if (i) o += ",";
+    o += "{\"name\":";
+    js_str(o, l.name);
+    o += ",\"phys_type\":" + std::to_string(l.phys_type) + ",\"max_def\":" + std::to_string(l.max_def) +
+         ",\"max_rep\":" + std::to_string(l.max_rep) + ",\"is_timestamp_ms\":" + (l.is_timestamp_ms ? "true" : "false") + "}";
+  }
+  o += "],\"row_groups\":[";
+  for (size_t g = 0; g < hf->meta.row_groups.size(); g++) {
+    const RowGroupMeta& rg = hf->meta.row_groups[g];
+    if (g) o += ",";
+    o += "{\"num_rows\":" + std::to_string(rg.num_rows) + ",\"columns\":[";
+    for (size_t c = 0; c < rg.columns.size(); c++) {
+      const ColumnChunkMeta& cm = rg.columns[c];
+      if (c) o += ",";
+      o += "{\"type\":" + std::to_string(cm.type) + ",\"codec\":" + std::to_string(cm.codec) +
+           ",\"num_values\":" + std::to_string(cm.num_values) +
+           ",\"total_uncompressed_size\":" + std::to_string(cm.total_uncompressed_size) +
+           ",\"total_compressed_size\":" + std::to_string(cm.total_compressed_size) +
+           ",\"data_page_offset\":" + std::to_string(cm.data_page_offset) +
+           ",\"dictionary_page_offset\":" + std::to_string(cm.dictionary_page_offset) +
+           ",\"null_count\":" + std::to_string(cm.stats.null_count) + ",\"encodings\":[";
+      for (size_t e = 0; e < cm.encodings.size(); e++) o += (e ? "," : "") + std::to_string(cm.encodings[e]);
+      o += "],\"pages\":[";
+      if (uint64_t(cm.start()) + uint64_t(cm.total_compressed_size) > hf->size) throw Error(PQ_ERR_CORRUPT, "column chunk outside the file");
+      std::vector<PageInfo> pis;
+      try { pis = walk_pages(hf->data + cm.start(), uint64_t(cm.total_compressed_size), cm.num_values); }
+      catch (const std::exception& e) { throw Error(PQ_ERR_CORRUPT, e.what()); }
+      for (size_t p = 0; p < pis.size(); p++) {
+        const PageInfo& pi = pis[p];
+        if (p) o += ",";
+        o += "{\"type\":" + std::to_string(pi.type) + ",\"num_values\":" + std::to_string(pi.num_values) +
+             ",\"encoding\":" + std::to_string(pi.encoding) + ",\"compressed_size\":" + std::to_string(pi.compressed_size) +
+             ",\"uncompressed_size\":" + std::to_string(pi.uncompressed_size) + ",\"header_len\":" + std::to_string(pi.header_len) + "}";
+      }
+      o += "]}";
+    }
+    o += "]}";
+  }
+  o += "]}";
+  return o;
+}
+
 // ---------------- Table ----------------
 Table::~Table() {
   if (d_arena) cudaFree(d_arena);
