@@ -230,7 +230,7 @@ std::vector<PageInfo> walk_pages(const uint8_t* chunk, uint64_t len, int64_t num
   uint64_t pos = 0;
   int64_t seen = 0;
   try {
-    while (pos < len && seen < num_values_expected) {
+    while (pos < len) {
       ThriftReader r(chunk + pos, len - pos);
       PageInfo pg;
       pg.offset_in_chunk = pos;

@@ -42,7 +42,7 @@ struct ColumnChunkMeta {
   ColumnStats stats;
   // byte range of the chunk in the file
   int64_t start() const {
-    return (dictionary_page_offset > 0 && dictionary_page_offset < data_page_offset)
+    return (dictionary_page_offset > 0 && (data_page_offset <= 0 || dictionary_page_offset < data_page_offset))
                ? dictionary_page_offset : data_page_offset;
   }
 };

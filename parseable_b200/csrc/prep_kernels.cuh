@@ -175,6 +175,89 @@ __global__ void k_agg_compact(const unsigned long long* acc, uint32_t nslots, ui
   }
 }
 
+// ---- bitmap-driven stream compaction (arrow-select `filter` in the reference) ----
+// exclusive prefix of the per-item selected-row counts; one block
+__global__ void k_item_prefix(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ base,
+                              unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+    uint32_t i = i0 + threadIdx.x;
+    unsigned long long v = i < n ? counts[i] : 0, incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = lane < nwarps ? warp_sums[lane] : 0, wi = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+        if ((int)lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    unsigned long long excl = carry + warp_sums[warp] + incl - v;
+    if (i < n) base[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// one CTA per item (grid-strided): selection bitmap -> ascending global row ordinals
+__global__ void k_compact_row_ids(const uint32_t* __restrict__ bitmap, const DevItem* __restrict__ items,
+                                  const uint32_t* __restrict__ item_counts, const unsigned long long* __restrict__ base,
+                                  uint32_t n_items, unsigned long long* __restrict__ out, unsigned long long out_cap) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    if (item_counts[it] == 0) continue;  // uniform per block
+    const DevItem item = items[it];
+    const uint32_t nwords = (item.nrows + 31) >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t w0 = 0; w0 < nwords; w0 += blockDim.x) {
+      uint32_t w = w0 + threadIdx.x;
+      uint32_t word = w < nwords ? bitmap[item.bitmap_word0 + w] : 0;
+      uint32_t c = __popc(word), incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      if (lane == 31) warp_sums[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t s = lane < nwarps ? warp_sums[lane] : 0, si = s;
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+          if ((int)lane >= o) si += t;
+        }
+        warp_sums[lane] = si - s;
+      }
+      __syncthreads();
+      unsigned long long pos = base[it] + carry + warp_sums[warp] + incl - c;
+      unsigned long long row = item.global_row0 + uint64_t(w) * 32;
+      while (word) {
+        int b = __ffs(word) - 1;
+        word &= word - 1;
+        if (pos < out_cap) out[pos] = row + b;
+        pos++;
+      }
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) carry += warp_sums[warp] + incl;
+      __syncthreads();
+    }
+  }
+}
+
 // key value export: lengths, then bytes at host-computed offsets
 __global__ void k_key_lens(const uint8_t* arena, const uint64_t* ent_off, const uint32_t* rep_of_gid, uint32_t card,
                            uint8_t kind, uint32_t* lens) {

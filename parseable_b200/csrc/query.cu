@@ -878,11 +878,31 @@ void Query::run(const PqQueryDesc& d) {
     }
   } else {
     // ---- filter / COUNT(*) ----
-    std::vector<uint32_t> item_counts;
+    // bitmap-driven stream compaction on the device: per-item prefix, then one CTA per item
+    DevBuf<unsigned long long> d_item_base, d_total, d_ids;
+    std::vector<uint64_t> ids;
     if (want_rows && !items.empty()) {
-      item_counts.resize(items.size());
-      PQB_CUDA(cudaMemcpyAsync(item_counts.data(), d_item_counts.p, items.size() * 4, cudaMemcpyDeviceToHost, stream));
-      metrics.d2h_bytes += items.size() * 4;
+      if (d.n_projection && !(d.flags & PQ_QUERY_EMIT_ROW_IDS))
+        throw Error(PQ_ERR_UNSUPPORTED, "projection of column values is not on the GPU path yet: ask for PQ_QUERY_EMIT_ROW_IDS or PQ_QUERY_COUNT_ONLY");
+      d_item_base.alloc(items.size(), stream);
+      d_total.alloc(1, stream);
+      k_item_prefix<<<1, 1024, 0, stream>>>(d_item_counts.p, uint32_t(items.size()), d_item_base.p, d_total.p);
+      launches++;
+      unsigned long long total = 0;
+      PQB_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      metrics.d2h_bytes += 8;
+      unsigned long long keep = total;
+      if (d.limit >= 0 && (unsigned long long)d.limit < keep) keep = (unsigned long long)d.limit;
+      if (keep) {
+        d_ids.alloc(keep, stream);
+        uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * 8));
+        k_compact_row_ids<<<grid, 256, 0, stream>>>(d_bitmap.p, d_items.p, d_item_counts.p, d_item_base.p, uint32_t(items.size()), d_ids.p, keep);
+        launches++;
+        ids.resize(keep);
+        PQB_CUDA(cudaMemcpyAsync(ids.data(), d_ids.p, keep * 8, cudaMemcpyDeviceToHost, stream));
+        metrics.d2h_bytes += keep * 8;
+      }
     }
     PQB_CUDA(cudaEventRecord(t_all.b, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
@@ -909,32 +929,7 @@ void Query::run(const PqQueryDesc& d) {
       metrics.groups = 1;
       batches_.push_back(std::move(ob));
     } else if (want_rows) {
-      // selected row ordinals, ascending; built from the bitmap on the host side of the boundary
-      // (projection of column VALUES is the next widening step)
-      if (d.n_projection && !(d.flags & PQ_QUERY_EMIT_ROW_IDS))
-        throw Error(PQ_ERR_UNSUPPORTED, "projection of column values is not on the GPU path yet: ask for PQ_QUERY_EMIT_ROW_IDS or PQ_QUERY_COUNT_ONLY");
-      std::vector<uint32_t> bm(bitmap_words);
-      if (bitmap_words) {
-        PQB_CUDA(cudaMemcpyAsync(bm.data(), d_bitmap.p, size_t(bitmap_words) * 4, cudaMemcpyDeviceToHost, stream));
-        PQB_CUDA(cudaStreamSynchronize(stream));
-        metrics.d2h_bytes += size_t(bitmap_words) * 4;
-      }
-      int64_t limit = d.limit;
-      std::vector<uint64_t> ids;
-      for (size_t it = 0; it < items.size() && (limit < 0 || int64_t(ids.size()) < limit); it++) {
-        if (!item_counts[it]) continue;
-        const DevItem& di = items[it];
-        uint32_t nw = (di.nrows + 31) / 32;
-        for (uint32_t w = 0; w < nw; w++) {
-          uint32_t word = bm[di.bitmap_word0 + w];
-          while (word) {
-            int b = __builtin_ctz(word);
-            word &= word - 1;
-            ids.push_back(di.global_row0 + uint64_t(w) * 32 + b);
-          }
-        }
-      }
-      if (limit >= 0 && int64_t(ids.size()) > limit) ids.resize(size_t(limit));
+      // selected row ordinals, ascending (projection of column VALUES is the next widening step)
       for (size_t r0 = 0; r0 < ids.size() || (r0 == 0 && ids.empty()); r0 += batch_rows) {
         size_t nb = std::min<size_t>(batch_rows, ids.size() - r0);
         OutBatch ob;

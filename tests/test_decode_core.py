@@ -1,0 +1,143 @@
+"""CPU tests of the pure host/device decode functions (decode_core.cuh) through the test-only
+harness tools/libdecode_core_host.so.  The same source is compiled into the CUDA kernels."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def dc(built):
+    lib = C.CDLL(os.path.join(built, "tools", "libdecode_core_host.so"))
+    lib.dc_decode_hybrid.restype = C.c_int64
+    lib.dc_f64_key.restype = C.c_int64
+    lib.dc_f64_key.argtypes = [C.c_uint64]
+    lib.dc_f64_from_key.restype = C.c_uint64
+    lib.dc_f64_from_key.argtypes = [C.c_int64]
+    lib.dc_load_u64.restype = C.c_uint64
+    return lib
+
+
+def _uleb(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def encode_hybrid(values, bw, rng, rle_bias=0.5, min_rle=1):
+    """Reference encoder for tests: random mix of RLE runs and bit-packed runs (Parquet
+    'RLE/bit-packing hybrid'), including runs of 1 and long bit-packed runs with multi-byte headers."""
+    out = bytearray()
+    i, n = 0, len(values)
+    while i < n:
+        # length of the run of equal values at i
+        j = i
+        while j < n and values[j] == values[i]:
+            j += 1
+        run = j - i
+        if run >= min_rle and rng.random() < rle_bias:
+            take = int(rng.integers(1, run + 1))
+            out += _uleb(take << 1)
+            out += int(values[i]).to_bytes((bw + 7) // 8, "little")
+            i += take
+        else:
+            groups = int(rng.integers(1, 80))
+            take = min(groups * 8, n - i)
+            groups = (take + 7) // 8
+            chunk = list(values[i:i + take]) + [0] * (groups * 8 - take)
+            out += _uleb((groups << 1) | 1)
+            acc, nbits = 0, 0
+            buf = bytearray()
+            for v in chunk:
+                acc |= int(v) << nbits
+                nbits += bw
+                while nbits >= 8:
+                    buf.append(acc & 0xFF)
+                    acc >>= 8
+                    nbits -= 8
+            assert nbits == 0
+            out += buf
+            i += take
+    return bytes(out)
+
+
+@pytest.mark.parametrize("bw", [0, 1, 2, 3, 5, 8, 11, 13, 16, 17, 24, 31, 32])
+@pytest.mark.parametrize("pattern", ["random", "runs"])
+def test_hybrid_roundtrip(dc, bw, pattern):
+    rng = np.random.default_rng(bw * 7 + (pattern == "runs"))
+    n = 9000
+    hi = (1 << bw) if bw else 1
+    if pattern == "random":
+        vals = rng.integers(0, hi, n, dtype=np.uint64)
+    else:
+        vals = np.repeat(rng.integers(0, hi, n // 7 + 1, dtype=np.uint64), rng.integers(1, 40, n // 7 + 1))[:n]
+    vals = vals.astype(np.uint64)
+    enc = encode_hybrid(vals, bw, rng)
+    out = np.zeros(n, np.uint32)
+    # the kernel's real geometry
+    slab = 2048
+    cap = ((slab * bw // 8 + slab // 8 + 64 + 15) // 16) * 16
+    got = dc.dc_decode_hybrid(enc, C.c_uint64(len(enc)), bw, n, slab, cap, 64, out.ctypes.data_as(C.c_void_p))
+    assert got == n
+    assert np.array_equal(out.astype(np.uint64), vals)
+
+
+@pytest.mark.parametrize("bw,cap,max_ent", [(1, 64, 4), (3, 48, 2), (13, 160, 3), (7, 32, 64)])
+def test_hybrid_tiny_windows_force_slab_shrink(dc, bw, cap, max_ent):
+    """Windows / directories far smaller than a slab: the walker must stop early and resume without
+    losing or duplicating values (the kernel's slab-shrink path)."""
+    rng = np.random.default_rng(99 + bw)
+    n = 5000
+    vals = np.repeat(rng.integers(0, 1 << bw, n, dtype=np.uint64), rng.integers(1, 12, n))[:n]
+    enc = encode_hybrid(vals, bw, rng, rle_bias=0.7)
+    out = np.zeros(n, np.uint32)
+    got = dc.dc_decode_hybrid(enc, C.c_uint64(len(enc)), bw, n, 2048, cap, max_ent, out.ctypes.data_as(C.c_void_p))
+    assert got == n
+    assert np.array_equal(out.astype(np.uint64), vals)
+
+
+def test_f64_order_key_is_total_order(dc):
+    vals = [float("-inf"), -1e300, -1.5, -0.0, 0.0, 5e-324, 1.5, 1e300, float("inf")]
+    nan_pos = struct.unpack("<d", struct.pack("<Q", 0x7FF8000000000001))[0]
+    nan_neg_bits = 0xFFF8000000000001
+    keys = [dc.dc_f64_key(struct.unpack("<Q", struct.pack("<d", v))[0]) for v in vals]
+    assert keys == sorted(keys) and len(set(keys)) == len(keys)
+    k_nan = dc.dc_f64_key(struct.unpack("<Q", struct.pack("<d", nan_pos))[0])
+    assert k_nan > keys[-1]                                  # +NaN greatest
+    assert dc.dc_f64_key(nan_neg_bits) < keys[0]             # -NaN smallest
+    for v in vals:
+        b = struct.unpack("<Q", struct.pack("<d", v))[0]
+        assert dc.dc_f64_from_key(dc.dc_f64_key(b)) == b
+
+
+def test_unaligned_loads(dc):
+    raw = bytes(range(1, 65))
+    buf = C.create_string_buffer(raw, 80)
+    base = C.addressof(buf)
+    for off in range(0, 40):
+        want = int.from_bytes(raw[off:off + 8], "little")
+        assert dc.dc_load_u64(C.c_void_p(base), off) == want
+
+
+LIKE_CASES = [
+    (b"hello world", b"hello world", 0, False, True), (b"hello", b"hell", 0, False, False),
+    (b"hello world", b"hello", 1, False, True), (b"hello world", b"world", 2, False, True),
+    (b"a timeout-xyzzy b", b"timeout-xyzzy", 3, False, True), (b"abc", b"", 3, False, True),
+    (b"Hello", b"hello", 0, True, True), (b"abc", b"a_c", 4, False, True), (b"abbc", b"a_c", 4, False, False),
+    (b"a%c", b"a\\%c", 4, False, True), (b"abc", b"a\\%c", 4, False, False), (b"xaybzc", b"%a%b%c", 4, False, True),
+    (b"xaybz", b"%a%b%c", 4, False, False), ("héllo".encode(), "h_llo".encode(), 4, False, True),
+    (b"", b"%", 4, False, True), (b"", b"_", 4, False, False),
+]
+
+
+@pytest.mark.parametrize("s,p,kind,ci,want", LIKE_CASES)
+def test_like_match(dc, s, p, kind, ci, want):
+    assert bool(dc.dc_like(s, len(s), p, len(p), kind, int(ci))) == want

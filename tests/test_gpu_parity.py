@@ -1,0 +1,334 @@
+"""GPU parity tests: every query goes through the C ABI (pq_query_open / pq_query_next) and is
+compared with the CPU oracle on the same files.  Bit-exact for counts, row ids, integer aggregates,
+MIN/MAX; 1e-9 relative for f64 SUM/AVG (BASELINE.json north_star: accumulation order differs)."""
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+from oracle.oracle import Oracle
+from parseable_b200 import _lib as L
+from parseable_b200 import synth
+from parseable_b200.query import (DeviceTable, HostFile, Query, QueryError, StandardTableProvider, TimeRange,
+                                  avg, col, count, count_star, execute, lit, max_, min_, sum_)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+F64_REL = 1e-9
+
+
+def assert_tables_equal(got: pa.Table, exp: pa.Table, keys):
+    assert got.num_rows == exp.num_rows
+    assert got.column_names == exp.column_names
+    if keys and got.num_rows:
+        order = [(k, "ascending") for k in keys]
+        got, exp = got.sort_by(order), exp.sort_by(order)
+    for name in exp.column_names:
+        a, b = got[name].to_pylist(), exp[name].to_pylist()
+        f64_sum = pa.types.is_floating(exp[name].type) and (name.startswith("sum(") or name.startswith("avg("))
+        if f64_sum:
+            for x, y in zip(a, b):
+                assert (x is None) == (y is None), name
+                if x is not None:
+                    assert math.isclose(x, y, rel_tol=F64_REL, abs_tol=0.0) or (math.isnan(x) and math.isnan(y)), (name, x, y)
+        else:
+            a = [None if (isinstance(v, float) and math.isnan(v)) else v for v in a]
+            b = [None if (isinstance(v, float) and math.isnan(v)) else v for v in b]
+            assert a == b, name
+
+
+@pytest.fixture(scope="module")
+def env(built, small_files):
+    out = {}
+    for tag, path in small_files.items():
+        ora = Oracle.from_parquet(path)
+        out[tag] = (path, ora, StandardTableProvider([path], schema=ora.table.schema))
+    return out
+
+
+FILTERS = {
+    "c2_level_and_latency": [(col("level") == "ERROR") & (col("latency_ms") > 100)],
+    "c1_status_eq": [col("status") == 200],
+    "f64_vs_int_literal": [col("duration_s") >= 1],
+    "or_mixed": [(col("level") == "FATAL") | (col("bytes") < 1000)],
+    "not": [~(col("level") == "INFO")],
+    "not_or": [~((col("status") == 200) | (col("cpu") >= 0.25))],
+    "plain_f64": [col("cpu") > 0.5],
+    "plain_f64_and_dict": [(col("mem_gb") <= 32.0) & (col("method") != "GET")],
+    "is_null": [col("host").is_null()],
+    "is_not_null_and": [col("pod").is_not_null() & (col("region") == "region-03")],
+    "like_contains": [col("message").like("%timeout-xyzzy%")],
+    "like_prefix": [col("host").like("host-000%")],
+    "like_suffix": [col("host").like("%7")],
+    "like_underscore": [col("path").like("/api/v1/resource/00_1")],
+    "not_like": [col("service").like("svc-00%", negated=True)],
+    "ilike": [col("level").ilike("err%")],
+    "str_range": [(col("host") >= "host-05000") & (col("host") < "host-05100")],
+    "conjunction_list": [col("level") == "WARN", col("latency_ms") <= 20, col("score") < 0.0],
+    "never": [col("level") == "NOPE"],
+    "always": [],
+    "deep": [((col("level") == "ERROR") | (col("level") == "FATAL")) & ((col("status") == 500) | (col("status") == 503))
+             & ~(col("region") == "region-00") & (col("bytes") > 10)],
+}
+
+
+@pytest.mark.parametrize("tag", ["nn", "nulls"])
+@pytest.mark.parametrize("name", sorted(FILTERS))
+def test_filter_count(env, tag, name):
+    path, ora, prov = env[tag]
+    flt = FILTERS[name]
+    got = prov.scan(filters=flt, count_only=True)
+    assert got.metrics["rows_selected"] == ora.count(flt)
+    assert got.metrics["rows_scanned"] + 70_000 * got.metrics["row_groups_pruned"] == ora.n
+
+
+@pytest.mark.parametrize("tag", ["nn", "nulls"])
+@pytest.mark.parametrize("name", ["c2_level_and_latency", "like_contains", "or_mixed", "never", "is_null"])
+def test_filter_row_ids(env, tag, name):
+    path, ora, prov = env[tag]
+    flt = FILTERS[name]
+    res = prov.scan(filters=flt)
+    ids = np.concatenate([b.column(0).to_numpy() for b in res.batches]) if res.batches else np.array([], np.int64)
+    assert np.array_equal(ids, ora.row_ids(flt))
+    assert all(b.num_rows <= 20000 for b in res.batches)          # batch size of the reference scan
+
+
+def test_limit(env):
+    path, ora, prov = env["nn"]
+    flt = FILTERS["or_mixed"]
+    res = prov.scan(filters=flt, limit=37)
+    ids = np.concatenate([b.column(0).to_numpy() for b in res.batches])
+    assert np.array_equal(ids, ora.row_ids(flt)[:37])
+
+
+AGGS = {
+    "c3_host": (["host"], [count_star(), sum_("bytes")], []),
+    "c4_host_status_6aggs": (["host", "status"], [count_star(), sum_("bytes"), min_("latency_ms"), max_("latency_ms"),
+                                                  sum_("duration_s"), max_("cpu")], []),
+    "level_avg_count": (["level"], [count_star(), avg("latency_ms"), count("cpu"), avg("score")], [col("status") == 200]),
+    "global": ([], [count_star(), sum_("bytes"), min_("cpu"), max_("score"), avg("mem_gb")], [col("level") == "ERROR"]),
+    "global_empty": ([], [count_star(), sum_("bytes"), min_("cpu")], [col("level") == "NOPE"]),
+    "grouped_empty": (["region"], [count_star()], [col("level") == "NOPE"]),
+    "count_star_only": ([], [count_star()], [col("status") == 404]),
+    "three_keys": (["region", "method", "level"], [count_star(), max_("bytes")], [col("latency_ms") > 30]),
+    "numeric_key": (["status"], [count_star(), min_("score"), max_("mem_gb")], []),
+    "f64_key": (["duration_s"], [count_star()], [col("latency_ms") < 40]),
+    "filtered_c3": (["host"], [count_star(), sum_("bytes")], [(col("level") == "ERROR") & (col("latency_ms") > 100)]),
+    "ts_minmax": (["service"], [min_("latency_ms"), max_("latency_ms"), count("host")], []),
+}
+
+
+@pytest.mark.parametrize("tag", ["nn", "nulls"])
+@pytest.mark.parametrize("name", sorted(AGGS))
+def test_group_by(env, tag, name):
+    path, ora, prov = env[tag]
+    keys, aggs, flt = AGGS[name]
+    got = prov.aggregate(keys, aggs, flt)
+    exp = ora.group_by(keys, aggs, flt)
+    assert_tables_equal(got.table() if got.batches else exp.slice(0, 0), exp, keys)
+
+
+def test_golden_field_stats_through_gpu(built):
+    """The reference's own known answers (src/storage/field_stats.rs:927-1327) through the GPU path."""
+    exp = json.load(open(os.path.join(GOLD, "expected.json")))
+    path = os.path.join(GOLD, "field_stats_10rows.parquet")
+    schema = {"name": pa.string(), "score": pa.float64(), "active": pa.bool_(), "created_at": pa.timestamp("ms"),
+              "single_value": pa.string(), "id": pa.int64()}
+    prov = StandardTableProvider([path], schema=schema)
+
+    def stats(field):
+        t = prov.aggregate([field], [count_star()]).table()
+        return dict(zip(t[field].to_pylist(), t["count(*)"].to_pylist())), t
+
+    name, t = stats("name")
+    assert t["count(*)"].type == pa.int64()
+    assert sum(name.values()) == 10 and len(name) == 7
+    assert name["Alice"] == 3 and name["Bob"] == 2 and name["Charlie"] == 1 and name[None] == 1
+    score, _ = stats("score")
+    assert len(score) == 9 and score[95.5] == 2 and sum(score.values()) == 10
+    active, _ = stats("active")
+    assert active == {True: 6, False: 3, None: 1}
+    created, t = stats("created_at")
+    assert len(created) == 9 and max(created.values()) == 2 and pa.types.is_timestamp(t["created_at"].type)
+    single, _ = stats("single_value")
+    assert single == {"constant": 10}
+
+    prov = StandardTableProvider([os.path.join(GOLD, "field_stats_1000rows.parquet")], schema={"category": pa.string()})
+    cat = prov.aggregate(["category"], [count_star()]).table()
+    assert cat.num_rows == 10 and set(cat["count(*)"].to_pylist()) == {100}
+    prov = StandardTableProvider([os.path.join(GOLD, "field_stats_empty.parquet")], schema={"name": pa.string()})
+    assert prov.aggregate(["name"], [count_star()]).batches == []
+    # nested (list) columns are outside the GPU path and say so instead of guessing
+    prov = StandardTableProvider([path], schema={})
+    with pytest.raises(QueryError) as ei:
+        prov.aggregate(["int_list"], [count_star()])
+    assert ei.value.code == L.PQ_ERR_UNSUPPORTED
+
+
+def test_sql_front_and_time_range_elision(env):
+    path, ora, prov = env["nn"]
+    ts = ora.table["p_timestamp"].cast(pa.int64()).to_numpy()
+    tr = TimeRange(int(ts.min()), int(ts.max()) + 1)                 # covers everything: elided by statistics
+    q = Query("SELECT host, COUNT(*), SUM(bytes) FROM logs16 WHERE level = 'ERROR' AND latency_ms > 100 GROUP BY host", tr)
+    got = execute(q, prov)
+    exp = ora.group_by(["host"], [count_star(), sum_("bytes")], FILTERS["c2_level_and_latency"])
+    assert_tables_equal(got.table(), exp, ["host"])
+    q = Query("SELECT COUNT(*) FROM demo WHERE status=200", tr)
+    got = execute(q, prov)
+    assert got.table()["count(*)"].to_pylist() == [ora.count([col("status") == 200])]
+    # a range that excludes every row group prunes them all
+    q = Query("SELECT COUNT(*) FROM demo WHERE status=200", TimeRange(0, 1000))
+    got = execute(q, prov)
+    assert got.table()["count(*)"].to_pylist() == [0]
+    assert got.metrics["row_groups_pruned"] == got.metrics["row_groups_total"] == 3
+
+
+def test_resident_table_and_host_buffers(env):
+    path, ora, _ = env["nulls"]
+    cols = ["level", "latency_ms", "host", "bytes"]
+    flt = FILTERS["c2_level_and_latency"]
+    want = ora.count(flt)
+    tbl = DeviceTable([path], cols)
+    assert tbl.rows == ora.n and tbl.device_bytes > 0
+    prov = StandardTableProvider(tbl, schema=ora.table.schema)
+    for _ in range(3):
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == want
+    got = prov.aggregate(["host"], [count_star(), sum_("bytes")], flt)
+    assert got.metrics["h2d_bytes"] < 1 << 20                      # the column chunks were already in HBM
+    assert_tables_equal(got.table(), ora.group_by(["host"], [count_star(), sum_("bytes")], flt), ["host"])
+    tbl.close()
+    data = open(path, "rb").read()
+    for pinned in (False, True):
+        hf = HostFile(data=data, pinned=pinned)
+        prov = StandardTableProvider([hf], schema=ora.table.schema)
+        r = prov.scan(filters=flt, count_only=True)
+        assert r.metrics["rows_selected"] == want
+        assert r.metrics["h2d_bytes"] >= r.metrics["bytes_scanned"] > 0
+        hf.close()
+
+
+def test_multiple_files_missing_columns_and_shards(env, data_dir):
+    """Several files (one per minute in Parseable), one of them written before a column existed:
+    the missing column reads as NULL; shards partition the row groups."""
+    p0, ora0, _ = env["nn"]
+    p1 = os.path.join(data_dir, "older.parquet")
+    cols = [c for c in synth.LOGS16_COLUMNS if c not in ("pod", "score")]
+    synth.write_logs16(p1, n_row_groups=2, first_rg=7, rows_per_group=50_000, null_rate=0.01, columns=cols)
+    ora = Oracle.from_parquet([p0, p1])
+    schema = {f.name: f.type for f in ora0.table.schema}
+    prov = StandardTableProvider([p0, p1], schema=schema)
+    for flt in ([col("pod").is_null()], [col("pod") == "pod-0007-4e0f"], [(col("score") < 0.0) | (col("level") == "ERROR")]):
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt)
+    keys, aggs = ["level"], [count_star(), count("score"), max_("score"), sum_("bytes")]
+    assert_tables_equal(prov.aggregate(keys, aggs).table(), ora.group_by(keys, aggs), keys)
+    flt = FILTERS["c2_level_and_latency"]
+    ids = []
+    total = 0
+    for s in range(3):
+        sp = StandardTableProvider([p0, p1], schema=schema, shard_index=s, shard_count=3)
+        r = sp.scan(filters=flt)
+        total += r.metrics["rows_scanned"]
+        ids += [b.column(0).to_numpy() for b in r.batches]
+    assert total == ora.n
+    assert np.array_equal(np.sort(np.concatenate(ids)), ora.row_ids(flt))
+
+
+def test_arrow_default_pages_and_v2(data_dir, built):
+    """Files NOT written the Parseable way: pyarrow defaults (1 MiB pages, misaligned across columns),
+    data page v2, required (non-nullable) columns, small dictionaries with long RLE runs."""
+    rng = np.random.default_rng(5)
+    n = 300_000
+    t = pa.table({
+        "k": pa.array(np.repeat(rng.integers(0, 50, n // 100), 100).astype(np.int64)),            # long RLE runs
+        "v": pa.array(rng.integers(-10**12, 10**12, n).astype(np.int64)),                           # PLAIN
+        "f": pa.array(rng.standard_normal(n)),
+        "s": pa.array(rng.choice(["a", "bb", "ccc", "dddd"], n)),
+        "b": pa.array(rng.random(n) < 0.3),
+    })
+    t = t.set_column(2, "f", pa.array(np.where(rng.random(n) < 0.1, None, t["f"].to_numpy()), pa.float64(), from_pandas=True))
+    req = pa.schema([pa.field("k", pa.int64(), False), pa.field("v", pa.int64(), False), pa.field("f", pa.float64(), True),
+                     pa.field("s", pa.string(), False), pa.field("b", pa.bool_(), True)])
+    t = t.cast(req)
+    for ver, kw in (("1.0", {}), ("2.0", {}), ("1.0", {"use_dictionary": ["k", "s"], "data_page_size": 64 << 10})):
+        p = os.path.join(data_dir, f"arrow_default_{ver}_{len(kw)}.parquet")
+        pq.write_table(t, p, compression="NONE", data_page_version=ver, row_group_size=120_000, **kw)
+        ora = Oracle.from_parquet(p)
+        prov = StandardTableProvider([p], schema=ora.table.schema)
+        for flt in ([col("k") == 7], [(col("v") > 0) & (col("s") == "ccc")], [col("f") < -1.0], [col("b") == True],  # noqa: E712
+                    [~(col("b") == True) | col("f").is_null()]):                                                       # noqa: E712
+            assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt), (ver, kw, flt)
+        keys, aggs = ["k"], [count_star(), sum_("v"), min_("f"), max_("f"), count("f")]
+        assert_tables_equal(prov.aggregate(keys, aggs, [col("s") != "a"]).table(), ora.group_by(keys, aggs, [col("s") != "a"]), keys)
+        keys, aggs = ["b", "s"], [count_star(), avg("f")]
+        assert_tables_equal(prov.aggregate(keys, aggs).table(), ora.group_by(keys, aggs), keys)
+
+
+def test_edge_values_total_order_and_wrapping(data_dir, built):
+    nan = float("nan")
+    t = pa.table({
+        "g": pa.array(["a", "a", "a", "b", "b", None, None, "c"]),
+        "x": pa.array([nan, 1.0, -0.0, 0.0, None, 5.0, nan, None]),
+        "big": pa.array([2**62, 2**62, 2**62, -2**63, -1, 7, None, None]),
+    })
+    p = os.path.join(data_dir, "edge.parquet")
+    pq.write_table(t, p, compression="NONE")
+    ora = Oracle(t)
+    prov = StandardTableProvider([p], schema=t.schema)
+    for flt in ([col("x") == nan], [col("x") > 1e308], [col("x") < 0.0], [col("x") == 0.0], [col("x") >= -0.0],
+                [col("big") < 0], [col("g").is_null() & col("x").is_not_null()]):
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt), flt
+    keys, aggs = ["g"], [count_star(), sum_("big"), min_("x"), max_("x"), count("x"), sum_("x")]
+    got = prov.aggregate(keys, aggs).table().sort_by("g")
+    exp = ora.group_by(keys, aggs).sort_by("g")
+    assert got["sum(big)"].to_pylist() == exp["sum(big)"].to_pylist()            # wrapping SUM(Int64)
+    assert [str(v) for v in got["min(x)"].to_pylist()] == [str(v) for v in exp["min(x)"].to_pylist()]
+    assert [str(v) for v in got["max(x)"].to_pylist()] == [str(v) for v in exp["max(x)"].to_pylist()]
+    assert got["count(x)"].to_pylist() == exp["count(x)"].to_pylist()
+    assert got["g"].to_pylist() == exp["g"].to_pylist()
+
+
+def test_errors_are_codes_not_crashes(env, data_dir):
+    path, ora, prov = env["nn"]
+    with pytest.raises(QueryError) as ei:
+        StandardTableProvider([os.path.join(data_dir, "missing.parquet")]).scan(filters=[col("a") == 1], count_only=True)
+    assert ei.value.code == L.PQ_ERR_IO
+    with pytest.raises(QueryError) as ei:
+        prov.aggregate(["host"], [sum_("level")])
+    assert ei.value.code == L.PQ_ERR_UNSUPPORTED
+    with pytest.raises(QueryError) as ei:
+        prov.scan(filters=[col("level") == 5], count_only=True)
+    assert ei.value.code == L.PQ_ERR_INVALID_ARG
+    lz4 = os.path.join(data_dir, "lz4.parquet")
+    synth.write_logs16(lz4, n_row_groups=1, rows_per_group=10_000, compression="LZ4_RAW", columns=["level", "status"])
+    with pytest.raises(QueryError) as ei:
+        StandardTableProvider([lz4], schema={"level": pa.string()}).scan(filters=[col("level") == "INFO"], count_only=True)
+    assert ei.value.code == L.PQ_ERR_UNSUPPORTED and "codec" in ei.value.message
+
+
+def test_concurrent_queries_from_threads(env):
+    """The reference drives partitions and several queries concurrently from tokio workers
+    (src/query/mod.rs:287, 317-334): the C ABI must be re-entrant."""
+    import threading
+    path, ora, prov = env["nulls"]
+    names = ["c2_level_and_latency", "or_mixed", "like_contains", "plain_f64", "deep", "not_or"]
+    want = {n: ora.count(FILTERS[n]) for n in names}
+    errs = []
+
+    def work(n):
+        try:
+            for _ in range(3):
+                got = prov.scan(filters=FILTERS[n], count_only=True).metrics["rows_selected"]
+                if got != want[n]:
+                    errs.append((n, got, want[n]))
+        except Exception as e:  # pragma: no cover
+            errs.append((n, repr(e)))
+
+    th = [threading.Thread(target=work, args=(n,)) for n in names]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
