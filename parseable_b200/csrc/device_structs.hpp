@@ -18,7 +18,9 @@ constexpr int kDirEntryMaxValues = 512;
 constexpr int kPredStack = 8;
 
 // page value encodings as the kernels see them
-enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2 };
+enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2, DE_RLE_BOOL = 3 };
+// DE_DICT and DE_RLE_BOOL carry an RLE / bit-packed hybrid value stream (staged + walked)
+#define PQB_ENC_HAS_STREAM(e) ((e) == ::pqb::DE_DICT || (e) == ::pqb::DE_RLE_BOOL)
 // physical value kinds
 enum DevKind : uint8_t { DK_I64 = 0, DK_F64 = 1, DK_STR = 2, DK_BOOL = 3, DK_I32 = 4, DK_F32 = 5 };
 

@@ -148,6 +148,17 @@ __global__ void k_key_intern(DevPrepArgs a, DevKeyTable t, int mode) {
   }
 }
 
+// multi-GPU: rewrite local group ids into the numbering every rank agreed on
+__global__ void k_gid_remap(DevPrepArgs a, uint32_t col, uint32_t gid_off, const uint32_t* __restrict__ remap, uint32_t card_local) {
+  uint32_t ci = blockIdx.x * a.ncols + col;
+  const DevChunk ch = a.chunks[ci];
+  if (!ch.present || ch.dict_n == 0) return;
+  for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
+    uint32_t g = a.gid_luts[gid_off + ch.lut_base + e];
+    if (g < card_local) a.gid_luts[gid_off + ch.lut_base + e] = remap[g];
+  }
+}
+
 // accumulator table initialisation: rows / sums / nn = 0, MIN = INT64_MAX, MAX = INT64_MIN
 __global__ void k_acc_init(unsigned long long* acc, uint32_t nslots, uint32_t n_acc, uint32_t cells,
                            const __grid_constant__ DevPlan plan) {

@@ -537,6 +537,11 @@ void Query::run(const PqQueryDesc& d) {
   plan.n_items = uint32_t(items.size());
   metrics.bytes_scanned = scanned_bytes;
 
+  // columns whose dictionary indices the row phase needs (GROUP BY keys, aggregate inputs)
+  for (uint32_t k = 0; k < d.n_group_by; k++) plan.cols[slot_of[d.group_by[k]]].need_idx = 1;
+  for (uint32_t a = 0; a < d.n_aggs; a++)
+    if (d.aggs[a].fn != PQ_AGG_COUNT_STAR) plan.cols[slot_of[d.aggs[a].col]].need_idx = 1;
+
   // GROUP BY keys
   plan.nkeys = d.n_group_by;
   for (uint32_t k = 0; k < d.n_group_by; k++) {
@@ -560,12 +565,11 @@ void Query::run(const PqQueryDesc& d) {
     for (int b = 0; b < 2; b++) { L.valwin[s][b] = off; off += align_up(L.valwin_cap[s] + 16, 128); }
     L.valid[s] = off; off += align_up((kSlabWords + 2) * 4, 16);
     L.rank[s] = off; off += kSlabWords * 4;
-    L.idx[s] = off; if (plan.cols[s].has_dict) off += kSlabRows * 4;
+    L.idx[s] = plan.cols[s].has_dict ? off : 0; if (plan.cols[s].has_dict) off += kSlabRows * 4;
     L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
     L.valdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
   }
-  L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kSlabWords * 4;
-  L.leafN = off; off += std::max<uint32_t>(nleaves, 1) * kSlabWords * 4;
+  L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
   L.sel = off; off += kSlabWords * 4;
   off = align_up(off, 128);
   L.acc = off;
@@ -623,27 +627,38 @@ void Query::run(const PqQueryDesc& d) {
   }
 
   // ---- GROUP BY key interning ----
+  // Local: every dictionary entry of a key column is interned into a device hash table and gets a
+  // dense id.  The distinct values are then packed to the host (they are also the output key
+  // dictionary).  Multi-GPU: the packed sets are all-gathered and numbered identically on every
+  // rank (rank order, first occurrence), local ids are remapped, so partial tables are slot-aligned
+  // for one ncclAllReduce.
   struct KeyBufs { DevBuf<unsigned long long> slots; DevBuf<uint32_t> gid_of_slot, rep, counter; uint32_t cap = 0; };
+  struct KeyDict { std::vector<uint32_t> offs; std::vector<uint8_t> bytes; };
   std::vector<std::unique_ptr<KeyBufs>> keybufs(d.n_group_by);
   std::vector<uint32_t> key_card(d.n_group_by, 0);
-  if (agg_kernel && d.n_group_by && nrg) {
-    for (uint32_t k = 0; k < d.n_group_by; k++) {
-      DevKey& key = plan.keys[k];
-      key.gid_off = uint32_t(uint64_t(k) * total_entries);
-      if (key.kind == KK_BOOL) { key_card[k] = 2; continue; }
-      uint32_t maxn = 1;
+  std::vector<KeyDict> kd(d.n_group_by);
+  const bool multi = agg_kernel && (d.flags & PQ_QUERY_ALLREDUCE) && comm_active() && comm_nranks() > 1;
+  if ((d.flags & PQ_QUERY_ALLREDUCE) && !comm_active()) throw Error(PQ_ERR_INVALID_ARG, "PQ_QUERY_ALLREDUCE without pq_comm_init_rank");
+  for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++) {
+    DevKey& key = plan.keys[k];
+    key.gid_off = uint32_t(uint64_t(k) * total_entries);
+    if (key.kind == KK_BOOL) { key_card[k] = 2; continue; }
+    const uint8_t kkind = plan.cols[key.col].kind;
+    uint32_t card_l = 0;
+    uint32_t maxn = 1;
+    if (nrg) {
       uint64_t sumn = 0;
       for (uint32_t gi = 0; gi < nrg; gi++) { uint32_t n = chunks[size_t(gi) * ncols + key.col].dict_n; maxn = std::max(maxn, n); sumn += n; }
       uint64_t cap = 64;
       while (cap < 4ull * maxn) cap <<= 1;
-      for (int attempt = 0;; attempt++) {
+      for (;;) {
         auto kb = std::make_unique<KeyBufs>();
         kb->cap = uint32_t(cap);
         kb->slots.alloc(cap, stream); kb->slots.zero();
         kb->gid_of_slot.alloc(cap, stream);
         kb->rep.alloc(cap, stream);
         kb->counter.alloc(2, stream); kb->counter.zero();
-        DevKeyTable t{kb->slots.p, kb->gid_of_slot.p, kb->rep.p, kb->counter.p, uint32_t(cap - 1), key.col, key.gid_off, plan.cols[key.col].kind};
+        DevKeyTable t{kb->slots.p, kb->gid_of_slot.p, kb->rep.p, kb->counter.p, uint32_t(cap - 1), key.col, key.gid_off, kkind};
         dim3 grid(nrg, std::min<uint32_t>((maxn + 255) / 256, 64));
         k_key_intern<<<grid, 256, 0, stream>>>(pa, t, 0);
         k_key_intern<<<grid, 256, 0, stream>>>(pa, t, 1);
@@ -658,13 +673,99 @@ void Query::run(const PqQueryDesc& d) {
           continue;
         }
         if (cnt[1]) throw Error(PQ_ERR_CUDA, "group key lookup failed");
-        key_card[k] = cnt[0];
+        card_l = cnt[0];
         keybufs[k] = std::move(kb);
         break;
       }
     }
-  } else if (agg_kernel) {
-    for (uint32_t k = 0; k < d.n_group_by; k++) key_card[k] = plan.keys[k].kind == KK_BOOL ? 2 : 0;
+    // pack the local distinct values: lengths -> offsets (host) -> bytes
+    KeyDict loc;
+    loc.offs.assign(size_t(card_l) + 1, 0);
+    if (card_l) {
+      DevBuf<uint32_t> lens;
+      lens.alloc(card_l, stream);
+      k_key_lens<<<(card_l + 255) / 256, 256, 0, stream>>>(table->d_arena, d_ent.p, keybufs[k]->rep.p, card_l, kkind, lens.p);
+      std::vector<uint32_t> hl(card_l);
+      PQB_CUDA(cudaMemcpyAsync(hl.data(), lens.p, card_l * 4ull, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      uint64_t tot = 0;
+      for (uint32_t g = 0; g < card_l; g++) { loc.offs[g] = uint32_t(tot); tot += hl[g]; }
+      loc.offs[card_l] = uint32_t(tot);
+      if (tot > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "group key strings exceed 2 GiB");
+      DevBuf<uint32_t> doffs;
+      doffs.upload(loc.offs, stream);
+      DevBuf<uint8_t> dbytes;
+      dbytes.alloc(std::max<uint64_t>(tot, 1), stream);
+      k_key_bytes<<<card_l, 64, 0, stream>>>(table->d_arena, d_ent.p, keybufs[k]->rep.p, card_l, kkind, doffs.p, dbytes.p);
+      launches += 2;
+      loc.bytes.resize(tot);
+      if (tot) PQB_CUDA(cudaMemcpyAsync(loc.bytes.data(), dbytes.p, tot, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      metrics.d2h_bytes += card_l * 4ull + tot;
+    }
+    if (!multi) {
+      key_card[k] = card_l;
+      kd[k] = std::move(loc);
+      continue;
+    }
+    // ---- multi-GPU: agree on one numbering ----
+    const int nr = comm_nranks(), me = comm_rank();
+    std::vector<unsigned long long> sizes(size_t(nr) * 2);
+    {
+      unsigned long long mine[2] = {card_l, loc.bytes.size()};
+      DevBuf<unsigned long long> dsend, drecv;
+      dsend.alloc(2, stream);
+      drecv.alloc(size_t(nr) * 2, stream);
+      PQB_CUDA(cudaMemcpyAsync(dsend.p, mine, 16, cudaMemcpyHostToDevice, stream));
+      comm_allgather_bytes(dsend.p, drecv.p, 16, stream);
+      PQB_CUDA(cudaMemcpyAsync(sizes.data(), drecv.p, size_t(nr) * 16, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+    }
+    unsigned long long cardmax = 0, bytesmax = 0;
+    for (int r = 0; r < nr; r++) { cardmax = std::max(cardmax, sizes[2 * r]); bytesmax = std::max(bytesmax, sizes[2 * r + 1]); }
+    const size_t per_rank = ((4 * (cardmax + 1) + bytesmax) + 15) & ~size_t(15);
+    std::vector<uint8_t> sendbuf(per_rank, 0), recvbuf(per_rank * nr);
+    std::memcpy(sendbuf.data(), loc.offs.data(), loc.offs.size() * 4);
+    if (!loc.bytes.empty()) std::memcpy(sendbuf.data() + 4 * (cardmax + 1), loc.bytes.data(), loc.bytes.size());
+    {
+      DevBuf<uint8_t> dsend, drecv;
+      dsend.upload(sendbuf, stream);
+      drecv.alloc(per_rank * nr, stream);
+      comm_allgather_bytes(dsend.p, drecv.p, per_rank, stream);
+      PQB_CUDA(cudaMemcpyAsync(recvbuf.data(), drecv.p, per_rank * nr, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      metrics.d2h_bytes += per_rank * nr;
+      metrics.h2d_bytes += per_rank;
+    }
+    std::map<std::string, uint32_t> ids;  // identical content + identical insertion order on every rank
+    std::vector<uint32_t> remap(std::max<uint32_t>(card_l, 1), 0);
+    KeyDict glob;
+    glob.offs.push_back(0);
+    for (int r = 0; r < nr; r++) {
+      const uint8_t* base = recvbuf.data() + per_rank * r;
+      const uint32_t* offs = reinterpret_cast<const uint32_t*>(base);
+      const uint8_t* bytes = base + 4 * (cardmax + 1);
+      for (unsigned long long i = 0; i < sizes[2 * r]; i++) {
+        std::string v(reinterpret_cast<const char*>(bytes + offs[i]), offs[i + 1] - offs[i]);
+        auto it = ids.find(v);
+        if (it == ids.end()) {
+          it = ids.emplace(v, uint32_t(ids.size())).first;
+          glob.bytes.insert(glob.bytes.end(), v.begin(), v.end());
+          glob.offs.push_back(uint32_t(glob.bytes.size()));
+        }
+        if (r == me) remap[i] = it->second;
+      }
+    }
+    if (card_l) {
+      DevBuf<uint32_t> dremap;
+      dremap.upload(remap, stream);
+      dim3 grid(nrg, std::min<uint32_t>((maxn + 255) / 256, 64));
+      k_gid_remap<<<grid, 256, 0, stream>>>(pa, key.col, key.gid_off, dremap.p, card_l);
+      launches++;
+      PQB_CUDA(cudaStreamSynchronize(stream));
+    }
+    key_card[k] = uint32_t(ids.size());
+    kd[k] = std::move(glob);
   }
   uint64_t nslots64 = 1;
   for (uint32_t k = 0; k < d.n_group_by; k++) {
@@ -739,8 +840,6 @@ void Query::run(const PqQueryDesc& d) {
     d_out_cells.alloc(size_t(out_cap) * cells, stream);
     // multi-GPU: one all-reduce of the partial tables
     if (d.flags & PQ_QUERY_ALLREDUCE) {
-      if (!comm_active()) throw Error(PQ_ERR_INVALID_ARG, "PQ_QUERY_ALLREDUCE without pq_comm_init_rank");
-      if (d.n_group_by) throw Error(PQ_ERR_UNSUPPORTED, "all-reduce of keyed partial tables needs canonical group ids (pending)");
       comm_allreduce_u64(d_acc.p, plan.nslots, 0, stream);
       for (uint32_t a = 0; a < plan.n_acc; a++) {
         uint8_t how = plan.acc_init[a];
@@ -760,38 +859,6 @@ void Query::run(const PqQueryDesc& d) {
       PQB_CUDA(cudaMemcpyAsync(out_slot.data(), d_out_slot.p, n_out * 4, cudaMemcpyDeviceToHost, stream));
       for (uint32_t c = 0; c < cells; c++)
         PQB_CUDA(cudaMemcpyAsync(out_cells.data() + size_t(c) * n_out, d_out_cells.p + size_t(c) * out_cap, n_out * 8ull, cudaMemcpyDeviceToHost, stream));
-    }
-    // key dictionaries
-    struct KeyDict { std::vector<uint32_t> offs; std::vector<uint8_t> bytes; };
-    std::vector<KeyDict> kd(d.n_group_by);
-    std::vector<std::unique_ptr<DevBuf<uint32_t>>> tmp_u32;
-    std::vector<std::unique_ptr<DevBuf<uint8_t>>> tmp_u8;
-    for (uint32_t k = 0; k < d.n_group_by && n_out; k++) {
-      if (plan.keys[k].kind == KK_BOOL || key_card[k] == 0) continue;
-      uint32_t card = key_card[k];
-      uint8_t kind = plan.cols[plan.keys[k].col].kind;
-      auto lens = std::make_unique<DevBuf<uint32_t>>();
-      lens->alloc(card, stream);
-      k_key_lens<<<(card + 255) / 256, 256, 0, stream>>>(table->d_arena, d_ent.p, keybufs[k]->rep.p, card, kind, lens->p);
-      launches++;
-      std::vector<uint32_t> hl(card);
-      PQB_CUDA(cudaMemcpyAsync(hl.data(), lens->p, card * 4ull, cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaStreamSynchronize(stream));
-      kd[k].offs.resize(card + 1);
-      uint64_t tot = 0;
-      for (uint32_t g = 0; g < card; g++) { kd[k].offs[g] = uint32_t(tot); tot += hl[g]; }
-      kd[k].offs[card] = uint32_t(tot);
-      if (tot > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "group key strings exceed 2 GiB");
-      auto doffs = std::make_unique<DevBuf<uint32_t>>();
-      doffs->upload(kd[k].offs, stream);
-      auto dbytes = std::make_unique<DevBuf<uint8_t>>();
-      dbytes->alloc(std::max<uint64_t>(tot, 1), stream);
-      k_key_bytes<<<card, 64, 0, stream>>>(table->d_arena, d_ent.p, keybufs[k]->rep.p, card, kind, doffs->p, dbytes->p);
-      launches++;
-      kd[k].bytes.resize(tot);
-      if (tot) PQB_CUDA(cudaMemcpyAsync(kd[k].bytes.data(), dbytes->p, tot, cudaMemcpyDeviceToHost, stream));
-      metrics.d2h_bytes += card * 4ull + tot;
-      tmp_u32.push_back(std::move(lens)); tmp_u32.push_back(std::move(doffs)); tmp_u8.push_back(std::move(dbytes));
     }
     PQB_CUDA(cudaEventRecord(t_all.b, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));

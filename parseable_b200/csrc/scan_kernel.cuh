@@ -9,16 +9,17 @@
 // common to all referenced columns) from a queue.  Per 2048-row slab a CTA
 //   1. waits for the TMA bulk copies (cp.async.bulk + mbarrier) that staged the
 //      next window of every encoded stream in shared memory,
-//   2. one thread per column walks the RLE/bit-packed run headers (the only
-//      sequential part of the format) into a run directory,
+//   2. one lane per column (on different warps) walks the RLE/bit-packed run
+//      headers — the only sequential part of the format — into a run directory,
 //   3. issues the TMA copies for the NEXT slab (double buffered),
-//   4. all warps expand definition levels to validity bitmaps and unpack
-//      dictionary indices from the staged bytes,
-//   5. evaluates leaf predicates (dictionary LUT hit, or compare on PLAIN
-//      values read straight from HBM with 8-byte loads), combines them with
-//      Kleene logic on 32-row words, and
-//   6. counts / stores the selection bitmap, or accumulates aggregates with
-//      shared-memory (or L2) atomics.
+//   4. all warps unpack bit-packed dictionary indices straight into leaf-predicate
+//      bits (dictionary LUT byte per value, warp ballot -> 32-row words); columns
+//      that feed GROUP BY / aggregates also stage their indices,
+//   5. PLAIN pages are compared straight from HBM with 8-byte loads,
+//   6. words are combined with Kleene logic and either counted / stored as the
+//      selection bitmap, or drive shared-memory (or L2) atomics into the
+//      accumulator table.
+// Columns with NULLs take the general path (validity bitmap, rank, expansion).
 // HBM traffic = the encoded bytes once + the bitmap; nothing decoded is written back.
 #pragma once
 #include <cuda_runtime.h>
@@ -40,14 +41,15 @@ struct SmemLayout {
   uint32_t valwin_cap[kMaxCols];
   uint32_t valid[kMaxCols];   // uint32[kSlabWords + 2]
   uint32_t rank[kMaxCols];    // uint32[kSlabWords]
-  uint32_t idx[kMaxCols];     // uint32[kSlabRows]  (0: column never dictionary encoded)
+  uint32_t idx[kMaxCols];     // uint32[kSlabRows]  (0: indices of this column are never staged)
   uint32_t defdir[kMaxCols];  // DirEntry[kMaxDirEntries]
   uint32_t valdir[kMaxCols];
-  uint32_t leafT, leafN;      // uint32[nleaves][kSlabWords]
+  uint32_t leafT;             // uint32[nleaves][kSlabWords + 2]
   uint32_t sel;               // uint32[kSlabWords]
   uint32_t acc;               // shared accumulator table
   uint32_t total;
 };
+constexpr int kLeafWords = kSlabWords + 2;
 
 // per-column cursor over the pages of one column chunk
 struct ColCursor {
@@ -85,7 +87,9 @@ struct ScanCtl {
   uint32_t item;
   uint32_t error;
   uint32_t sel_count;
-  uint32_t _pad;
+  uint32_t rmin_all;     // min over columns of the rows the fast walk covered
+  uint32_t any_nulls;    // some column of this slab has a NULL (general path)
+  uint32_t target;       // rows the next slab should try to take
   uint32_t rmin[kMaxCols];
   ColCursor cur[kMaxCols];
   SlabCol slab[kMaxCols];
@@ -103,16 +107,22 @@ __device__ __forceinline__ void page_enter(ColCursor& c, const DevPage* pages, u
   stream_init(c.val, p.off + p.val_off, p.off + p.len, p.bit_width);
 }
 
-// thread 0: stage the windows every stream needs next into buffer `buf`
+// thread 0: stage the windows every stream needs next into buffer `buf`, and publish the row
+// target of the next slab
 __device__ __forceinline__ void issue_windows(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
-                                              const uint8_t* arena, uint32_t ncols, uint32_t buf) {
+                                              const uint8_t* arena, uint32_t ncols, uint32_t buf, uint32_t rows_left) {
   uint32_t bytes = 0;
+  uint32_t target = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
   for (uint32_t c = 0; c < ncols; c++) {
     const ColCursor& cr = ctl.cur[c];
     if (!cr.present) continue;
+    target = cr.page_rows_left < target ? cr.page_rows_left : target;
     if (cr.has_def) bytes += L.defwin_cap[c];
-    if (cr.enc == DE_DICT) bytes += L.valwin_cap[c];
+    if (PQB_ENC_HAS_STREAM(cr.enc)) bytes += L.valwin_cap[c];
   }
+  ctl.target = target;
+  ctl.rmin_all = target;
+  ctl.any_nulls = 0;
   mbar_arrive_expect_tx(&ctl.mbar[buf], bytes);
   for (uint32_t c = 0; c < ncols; c++) {
     ColCursor& cr = ctl.cur[c];
@@ -122,12 +132,21 @@ __device__ __forceinline__ void issue_windows(ScanCtl& ctl, const SmemLayout& L,
       cr.defwin_base[buf] = s;
       tma_load_1d(smem + L.defwin[c][buf], arena + s, L.defwin_cap[c], &ctl.mbar[buf]);
     }
-    if (cr.enc == DE_DICT) {
+    if (PQB_ENC_HAS_STREAM(cr.enc)) {
       uint64_t s = stream_window_start(cr.val) & ~15ull;
       cr.valwin_base[buf] = s;
       tma_load_1d(smem + L.valwin[c][buf], arena + s, L.valwin_cap[c], &ctl.mbar[buf]);
     }
   }
+}
+
+// OR a 32-bit group of bits into a bitmap at an arbitrary bit position
+__device__ __forceinline__ void or_bits(uint32_t* bm, uint32_t pos, uint32_t word) {
+  uint32_t sh = pos & 31;
+  if (sh == 0) { atomicOr(&bm[pos >> 5], word); return; }
+  atomicOr(&bm[pos >> 5], word << sh);
+  uint32_t hi = word >> (32 - sh);
+  if (hi) atomicOr(&bm[(pos >> 5) + 1], hi);
 }
 
 // expand a run directory of 1-bit values into a bitmap (OR into pre-zeroed words)
@@ -140,15 +159,7 @@ __device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent
       uint32_t bit = 0;
       if (j < d.count) bit = d.kind ? bp_get(win, d.payload, 1, j) : (d.payload & 1);
       uint32_t word = __ballot_sync(0xffffffffu, bit);
-      if (lane_id() == 0 && word) {
-        uint32_t pos = d.start + k;
-        uint32_t sh = pos & 31;
-        atomicOr(&bm[pos >> 5], word << sh);
-        if (sh) {
-          uint32_t hi = word >> (32 - sh);
-          if (hi) atomicOr(&bm[(pos >> 5) + 1], hi);
-        }
-      }
+      if (lane_id() == 0 && word) or_bits(bm, d.start + k, word);
     }
   }
 }
@@ -162,6 +173,44 @@ __device__ __forceinline__ void dir_to_idx(const DirEntry* dir, uint32_t nent, c
       for (uint32_t j = lane_id(); j < d.count; j += 32) idx[d.start + j] = bp_get(win, d.payload, bw, j);
     } else {
       for (uint32_t j = lane_id(); j < d.count; j += 32) idx[d.start + j] = d.payload;
+    }
+  }
+}
+
+// Fused unpack -> leaf LUT -> ballot: no index staging.  Up to two leaves of the same column are
+// evaluated from one unpacked index; bits land in VALUE space (== row space when the slab has no NULLs).
+__device__ __forceinline__ void dir_to_leafbits(const DirEntry* dir, uint32_t nent, const uint32_t* win, uint32_t bw,
+                                                const uint8_t* __restrict__ lut0, uint32_t* T0,
+                                                const uint8_t* __restrict__ lut1, uint32_t* T1, uint32_t* idx) {
+  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
+    const DirEntry d = dir[e];
+    if (d.kind) {
+      for (uint32_t k = 0; k < d.count; k += 32) {
+        uint32_t j = k + lane_id();
+        bool in = j < d.count;
+        uint32_t v = in ? bp_get(win, d.payload, bw, j) : 0;
+        if (idx && in) idx[d.start + j] = v;
+        uint32_t w0 = __ballot_sync(0xffffffffu, in && lut0[v]);
+        uint32_t w1 = lut1 ? __ballot_sync(0xffffffffu, in && lut1[v]) : 0;
+        if (lane_id() == 0) {
+          if (w0) or_bits(T0, d.start + k, w0);
+          if (w1) or_bits(T1, d.start + k, w1);
+        }
+      }
+    } else {
+      // an RLE run: one LUT probe decides the whole run
+      const bool t0 = lut0[d.payload] != 0;
+      const bool t1 = lut1 ? lut1[d.payload] != 0 : false;
+      for (uint32_t k = 0; k < d.count; k += 32) {
+        uint32_t j = k + lane_id();
+        bool in = j < d.count;
+        if (idx && in) idx[d.start + j] = d.payload;
+        uint32_t m = __ballot_sync(0xffffffffu, in);
+        if (lane_id() == 0) {
+          if (t0) or_bits(T0, d.start + k, m);
+          if (t1) or_bits(T1, d.start + k, m);
+        }
+      }
     }
   }
 }
@@ -186,7 +235,8 @@ __device__ __forceinline__ uint64_t value_u64(const SlabCol& c, const uint8_t* a
   if (c.enc == DE_DICT) return load_u64_unaligned(arena + c.dict_off + uint64_t(idx[j]) * 8);
   return load_u64_unaligned(arena + c.val_base + uint64_t(c.vals_done + j) * 8);
 }
-__device__ __forceinline__ uint32_t value_bool(const SlabCol& c, const uint8_t* arena, uint32_t j) {
+__device__ __forceinline__ uint32_t value_bool(const SlabCol& c, const uint8_t* arena, const uint32_t* idx, uint32_t j) {
+  if (c.enc == DE_RLE_BOOL) return idx[j] & 1;  // v2 pages: booleans as an RLE / bit-packed hybrid stream
   uint32_t k = c.vals_done + j;
   return (arena[c.val_base + (k >> 3)] >> (k & 7)) & 1;
 }
@@ -226,6 +276,126 @@ __device__ __forceinline__ uint32_t row_mask(uint32_t w, uint32_t R) {
   return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
 }
 
+// which thread walks column c: lane (c / warps) of warp (c % warps), so walkers of up to
+// kScanWarps columns sit on different warps and do not serialise each other
+__device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
+  uint32_t l = lane_id();
+  col = l * kScanWarps + warp_id();
+  return l < 2 && col < ncols;
+}
+
+// The general per-slab walk (columns with NULLs, window / directory overflow): definition levels ->
+// validity bitmap + ranks -> index streams, shrinking the slab until every column is covered.
+// All threads call it; returns the rows of the slab (0: corrupt page).
+__device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t ncols,
+                                              uint32_t buf, uint32_t R, const StreamState& snap_def,
+                                              const StreamState& snap_val) {
+  uint32_t mycol;
+  const bool walker = walker_of(ncols, mycol);
+  const uint32_t tid = threadIdx.x;
+  for (int attempt = 0; attempt < 4 && R > 0; attempt++) {
+    if (walker) {  // definition levels
+      ColCursor& c = ctl.cur[mycol];
+      SlabCol& s = ctl.slab[mycol];
+      uint32_t got = R;
+      s.ndef = 0;
+      s.all_valid = 1;
+      if (c.present && c.has_def) {
+        Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
+        DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
+        uint32_t n = 0;
+        got = walk_stream(c.def, w, R, dir, n, kMaxDirEntries);
+        s.ndef = n;
+        uint32_t allv = 1;
+        for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
+        s.all_valid = allv;
+      }
+      ctl.rmin[mycol] = got;
+    }
+    for (uint32_t c = 0; c < ncols; c++) {
+      uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
+      for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kScanThreads) bm[w] = 0;
+    }
+    __syncthreads();
+    uint32_t R1 = R;
+    for (uint32_t c = 0; c < ncols; c++) R1 = ctl.rmin[c] < R1 ? ctl.rmin[c] : R1;
+    if (R1 < R) {  // a definition-level window / directory ran out: shrink the slab, redo
+      if (walker) ctl.cur[mycol].def = snap_def;
+      R = R1;
+      __syncthreads();
+      continue;
+    }
+    for (uint32_t c = 0; c < ncols; c++) {
+      const SlabCol& s = ctl.slab[c];
+      if (s.present && !s.all_valid)
+        dir_to_bitmap(smem_at<DirEntry>(smem, L.defdir[c]), s.ndef, smem_at<uint32_t>(smem, L.defwin[c][buf]),
+                      smem_at<uint32_t>(smem, L.valid[c]));
+    }
+    __syncthreads();
+    for (uint32_t c = warp_id(); c < ncols; c += kScanWarps) {
+      SlabCol& s = ctl.slab[c];
+      if (!s.present) { if (lane_id() == 0) s.nv = 0; continue; }
+      if (s.all_valid) { if (lane_id() == 0) s.nv = R; continue; }
+      uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
+      uint32_t* rk = smem_at<uint32_t>(smem, L.rank[c]);
+      uint32_t w0 = lane_id() * 2, w1 = w0 + 1;
+      uint32_t a0 = bm[w0] & row_mask(w0, R), a1 = bm[w1] & row_mask(w1, R);
+      uint32_t p0 = __popc(a0), p1 = __popc(a1);
+      uint32_t sum = p0 + p1, incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += t;
+      }
+      uint32_t excl = incl - sum;
+      rk[w0] = excl;
+      rk[w1] = excl + p0;
+      bm[w0] = a0;
+      bm[w1] = a1;
+      if (lane_id() == 31) s.nv = incl;
+    }
+    __syncthreads();
+    if (walker) {  // dictionary-index streams
+      ColCursor& c = ctl.cur[mycol];
+      SlabCol& s = ctl.slab[mycol];
+      uint32_t rc = R;
+      s.nval = 0;
+      if (c.present && PQB_ENC_HAS_STREAM(c.enc) && s.nv > 0) {
+        Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
+        DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[mycol]);
+        uint32_t n = 0;
+        uint32_t got = walk_stream(c.val, w, s.nv, dir, n, kMaxDirEntries);
+        s.nval = n;
+        if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
+          if (s.all_valid) rc = got;
+          else {
+            const uint32_t* bm = smem_at<uint32_t>(smem, L.valid[mycol]);
+            uint32_t seen = 0;
+            rc = 0;
+            for (uint32_t r = 0; r < R; r++) {
+              uint32_t b = (bm[r >> 5] >> (r & 31)) & 1;
+              if (b && seen == got) break;
+              seen += b;
+              rc = r + 1;
+            }
+          }
+        }
+      }
+      ctl.rmin[mycol] = rc;
+    }
+    __syncthreads();
+    uint32_t R2 = R;
+    for (uint32_t c = 0; c < ncols; c++) R2 = ctl.rmin[c] < R2 ? ctl.rmin[c] : R2;
+    if (R2 < R) {  // an index window / directory ran out: shrink and redo everything
+      if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; }
+      R = R2;
+      __syncthreads();
+      continue;
+    }
+    return R;
+  }
+  return 0;
+}
+
 __global__ void __launch_bounds__(kScanThreads)
 k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -234,6 +404,8 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
   const uint32_t ncols = plan.ncols;
   const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
   const bool agg_mode = plan.mode == SM_AGG;
+  uint32_t mycol;
+  const bool walker = walker_of(ncols, mycol);
 
   if (tid == 0) {
     mbar_init(&ctl.mbar[0], 1);
@@ -259,6 +431,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
 
   uint32_t phases = 0;  // bit b: parity to wait for on mbar[b]
   uint32_t* selw = smem_at<uint32_t>(smem, L.sel);
+  uint32_t* leafT = smem_at<uint32_t>(smem, L.leafT);
 
   for (;;) {
     __syncthreads();
@@ -286,122 +459,58 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     uint32_t rows_left = item.nrows;
     uint32_t r_item = 0;
     uint32_t buf = 0;
-    if (tid == 0) issue_windows(ctl, L, smem, a.arena, ncols, buf);
+    if (tid == 0) issue_windows(ctl, L, smem, a.arena, ncols, buf, rows_left);
+    __syncthreads();
 
     while (rows_left > 0) {
       // ---- 1. wait for this slab's staged bytes ----
       mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
       phases ^= 1u << buf;
+      const uint32_t R0 = ctl.target;
 
-      uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
-      for (uint32_t c = 0; c < ncols; c++) {
-        uint32_t pl = ctl.cur[c].page_rows_left;
-        R = pl < R ? pl : R;
-      }
-
-      // ---- 2. walk run headers: one thread per column; retries only for pathological encodings ----
+      // ---- 2. fast walk: definition levels say "no NULLs" -> walk the index stream right away ----
       StreamState snap_def, snap_val;
-      if (tid < ncols) { snap_def = ctl.cur[tid].def; snap_val = ctl.cur[tid].val; }
-      for (int attempt = 0; attempt < 4 && R > 0; attempt++) {
-        if (tid < ncols) {  // 2a. definition levels
-          ColCursor& c = ctl.cur[tid];
-          SlabCol& s = ctl.slab[tid];
-          uint32_t got = R;
-          s.ndef = 0;
-          s.all_valid = 1;
-          if (c.present && c.has_def) {
-            Window w{smem + L.defwin[tid][buf], c.defwin_base[buf], L.defwin_cap[tid]};
-            DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[tid]);
+      if (walker) {
+        ColCursor& c = ctl.cur[mycol];
+        SlabCol& s = ctl.slab[mycol];
+        snap_def = c.def;
+        snap_val = c.val;
+        uint32_t rc = R0;
+        s.ndef = 0;
+        s.nval = 0;
+        s.all_valid = 1;
+        s.nv = c.present ? R0 : 0;
+        if (c.present) {
+          if (c.has_def) {
+            Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
+            DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
             uint32_t n = 0;
-            got = walk_stream(c.def, w, R, dir, n, kMaxDirEntries);
+            uint32_t got = walk_stream(c.def, w, R0, dir, n, kMaxDirEntries);
             s.ndef = n;
             uint32_t allv = 1;
             for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
             s.all_valid = allv;
+            rc = got;
+            if (!allv) ctl.any_nulls = 1;
           }
-          ctl.rmin[tid] = got;
-        }
-        for (uint32_t c = 0; c < ncols; c++) {
-          uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
-          for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kScanThreads) bm[w] = 0;
-        }
-        __syncthreads();
-        uint32_t R1 = R;
-        for (uint32_t c = 0; c < ncols; c++) R1 = ctl.rmin[c] < R1 ? ctl.rmin[c] : R1;
-        if (R1 < R) {  // a definition-level window / directory ran out: shrink the slab, redo
-          if (tid < ncols) ctl.cur[tid].def = snap_def;
-          R = R1;
-          __syncthreads();
-          continue;
-        }
-        // 2b. validity bitmaps, ranks, non-null counts
-        for (uint32_t c = 0; c < ncols; c++) {
-          const SlabCol& s = ctl.slab[c];
-          if (s.present && !s.all_valid)
-            dir_to_bitmap(smem_at<DirEntry>(smem, L.defdir[c]), s.ndef, smem_at<uint32_t>(smem, L.defwin[c][buf]),
-                          smem_at<uint32_t>(smem, L.valid[c]));
-        }
-        __syncthreads();
-        for (uint32_t c = warp_id(); c < ncols; c += kScanWarps) {
-          SlabCol& s = ctl.slab[c];
-          if (!s.present) { if (lane_id() == 0) s.nv = 0; continue; }
-          if (s.all_valid) { if (lane_id() == 0) s.nv = R; continue; }
-          uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
-          uint32_t* rk = smem_at<uint32_t>(smem, L.rank[c]);
-          uint32_t w0 = lane_id() * 2, w1 = w0 + 1;
-          uint32_t a0 = bm[w0] & row_mask(w0, R), a1 = bm[w1] & row_mask(w1, R);
-          uint32_t p0 = __popc(a0), p1 = __popc(a1);
-          uint32_t sum = p0 + p1, incl = sum;
-          for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane_id() >= o) incl += t;
-          }
-          uint32_t excl = incl - sum;
-          rk[w0] = excl;
-          rk[w1] = excl + p0;
-          bm[w0] = a0;
-          bm[w1] = a1;
-          if (lane_id() == 31) s.nv = incl;
-        }
-        __syncthreads();
-        if (tid < ncols) {  // 2c. dictionary-index streams
-          ColCursor& c = ctl.cur[tid];
-          SlabCol& s = ctl.slab[tid];
-          uint32_t rc = R;
-          s.nval = 0;
-          if (c.present && c.enc == DE_DICT && s.nv > 0) {
-            Window w{smem + L.valwin[tid][buf], c.valwin_base[buf], L.valwin_cap[tid]};
-            DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[tid]);
+          if (s.all_valid && rc == R0 && PQB_ENC_HAS_STREAM(c.enc)) {
+            Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
+            DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[mycol]);
             uint32_t n = 0;
-            uint32_t got = walk_stream(c.val, w, s.nv, dir, n, kMaxDirEntries);
+            rc = walk_stream(c.val, w, R0, dir, n, kMaxDirEntries);
             s.nval = n;
-            if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
-              if (s.all_valid) rc = got;
-              else {
-                const uint32_t* bm = smem_at<uint32_t>(smem, L.valid[tid]);
-                uint32_t seen = 0;
-                rc = 0;
-                for (uint32_t r = 0; r < R; r++) {
-                  uint32_t b = (bm[r >> 5] >> (r & 31)) & 1;
-                  if (b && seen == got) break;
-                  seen += b;
-                  rc = r + 1;
-                }
-              }
-            }
           }
-          ctl.rmin[tid] = rc;
         }
+        if (rc < R0) atomicMin(&ctl.rmin_all, rc);
+      }
+      // leaf bitmaps accumulate with OR: clear them while the walkers run
+      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
+      __syncthreads();
+      uint32_t R = R0;
+      if (ctl.rmin_all < R0 || ctl.any_nulls) {  // uniform: general path from the snapshots
+        if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; }
         __syncthreads();
-        uint32_t R2 = R;
-        for (uint32_t c = 0; c < ncols; c++) R2 = ctl.rmin[c] < R2 ? ctl.rmin[c] : R2;
-        if (R2 < R) {  // an index window / directory ran out: shrink and redo everything
-          if (tid < ncols) { ctl.cur[tid].def = snap_def; ctl.cur[tid].val = snap_val; }
-          R = R2;
-          __syncthreads();
-          continue;
-        }
-        break;
+        R = general_walk(ctl, L, smem, ncols, buf, R0, snap_def, snap_val);
       }
       if (R == 0) {  // no progress possible: corrupt page
         if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
@@ -409,9 +518,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       }
 
       // ---- 3. freeze this slab's view, advance cursors, prefetch the next slab ----
-      if (tid < ncols) {
-        ColCursor& c = ctl.cur[tid];
-        SlabCol& s = ctl.slab[tid];
+      if (walker) {
+        ColCursor& c = ctl.cur[mycol];
+        SlabCol& s = ctl.slab[mycol];
         s.val_base = c.val_base;
         s.vals_done = c.vals_done;
         s.enc = c.enc;
@@ -427,66 +536,98 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       }
       __syncthreads();
       if (ctl.error) break;
-      if (tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1);
+      if (tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
 
-      // ---- 4. unpack dictionary indices ----
+      // ---- 4. unpack: fused index -> leaf bits where possible, else stage indices ----
+      const uint32_t nwords = (R + 31) >> 5;
       for (uint32_t c = 0; c < ncols; c++) {
         const SlabCol& s = ctl.slab[c];
-        if (s.present && s.enc == DE_DICT && s.nv > 0)
-          dir_to_idx(smem_at<DirEntry>(smem, L.valdir[c]), s.nval, smem_at<uint32_t>(smem, L.valwin[c][buf]), s.bw,
-                     smem_at<uint32_t>(smem, L.idx[c]));
-      }
-      __syncthreads();
-
-      // ---- 5. leaf predicates -> (T, N) bitmaps, 32 rows per warp step ----
-      const uint32_t nwords = (R + 31) >> 5;
-      for (uint32_t l = 0; l < plan.nleaves; l++) {
-        const DevLeaf& lf = plan.leaves[l];
-        const SlabCol& s = ctl.slab[lf.col];
-        const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
-        const uint32_t* rk = smem_at<uint32_t>(smem, L.rank[lf.col]);
-        const uint32_t* idx = smem_at<uint32_t>(smem, L.idx[lf.col]);
-        uint32_t* Tw = smem_at<uint32_t>(smem, L.leafT) + l * kSlabWords;
-        uint32_t* Nw = smem_at<uint32_t>(smem, L.leafN) + l * kSlabWords;
-        const uint8_t kind = plan.cols[lf.col].kind;
-        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
-          uint32_t r = r0 + lane_id();
-          bool t = false, n = false;
-          if (r < R) {
-            RowVal rv = row_rank(s, vbm, rk, r);
-            if (lf.kind == LK_IS_NULL) t = !rv.valid;
-            else if (lf.kind == LK_IS_NOT_NULL) t = rv.valid;
-            else if (!rv.valid) n = true;
-            else if (s.enc == DE_DICT) t = a.luts[lf.lut_off + s.lut_base + idx[rv.j]] != 0;
-            else if (kind == DK_BOOL) {
-              uint32_t v = value_bool(s, a.arena, rv.j);
-              t = cmp_i64((int64_t)v, lf.lit_i64, lf.cmp);
-            } else if (kind == DK_I64) {
-              t = cmp_i64((int64_t)value_u64(s, a.arena, idx, rv.j), lf.lit_i64, lf.cmp);
-            } else if (kind == DK_F64) {
-              t = cmp_i64(f64_order_key(value_u64(s, a.arena, idx, rv.j)), f64_order_key((uint64_t)lf.lit_i64), lf.cmp);
-            } else {  // PLAIN byte arrays are rejected on the host (PQ_ERR_UNSUPPORTED)
-              n = true;
-            }
+        if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
+        uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
+        const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
+        const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
+        // leaves of this column that a dictionary LUT answers
+        int l0 = -1, l1 = -1, extra = 0;
+        if (s.enc == DE_DICT && s.all_valid) {
+          for (uint32_t l = 0; l < plan.nleaves; l++) {
+            const DevLeaf& lf = plan.leaves[l];
+            if (lf.col != c || (lf.kind != LK_CMP && lf.kind != LK_LIKE)) continue;
+            if (l0 < 0) l0 = int(l); else if (l1 < 0) l1 = int(l); else extra = 1;
           }
-          uint32_t tw = __ballot_sync(0xffffffffu, t);
-          uint32_t nw = __ballot_sync(0xffffffffu, n);
-          if (lane_id() == 0) { Tw[r0 >> 5] = tw; Nw[r0 >> 5] = nw; }
+        }
+        if (l0 >= 0 && !extra) {
+          const uint8_t* lut0 = a.luts + plan.leaves[l0].lut_off + s.lut_base;
+          const uint8_t* lut1 = l1 >= 0 ? a.luts + plan.leaves[l1].lut_off + s.lut_base : nullptr;
+          dir_to_leafbits(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords, lut1,
+                          l1 >= 0 ? leafT + l1 * kLeafWords : nullptr, plan.cols[c].need_idx ? idx : nullptr);
+        } else if (idx) {
+          dir_to_idx(dir, s.nval, win, s.bw, idx);
         }
       }
       __syncthreads();
 
-      // ---- 6. Kleene combine on words -> selection ----
+      // ---- 5. leaves the fused pass did not answer: PLAIN pages, NULL-carrying slabs, booleans ----
+      for (uint32_t l = 0; l < plan.nleaves; l++) {
+        const DevLeaf& lf = plan.leaves[l];
+        if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
+        const SlabCol& s = ctl.slab[lf.col];
+        if (!s.present) continue;                                 // all NULL: T stays 0
+        if (s.enc == DE_DICT && s.all_valid) {
+          // fused unless the column had more than two LUT leaves
+          int seen = 0;
+          for (uint32_t m = 0; m < l; m++)
+            seen += (plan.leaves[m].col == lf.col && (plan.leaves[m].kind == LK_CMP || plan.leaves[m].kind == LK_LIKE));
+          int total = seen;
+          for (uint32_t m = l; m < plan.nleaves; m++)
+            total += (plan.leaves[m].col == lf.col && (plan.leaves[m].kind == LK_CMP || plan.leaves[m].kind == LK_LIKE));
+          if (total <= 2) continue;
+        }
+        const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
+        const uint32_t* rk = smem_at<uint32_t>(smem, L.rank[lf.col]);
+        const uint32_t* idx = smem_at<uint32_t>(smem, L.idx[lf.col]);
+        uint32_t* Tw = leafT + l * kLeafWords;
+        const uint8_t kind = plan.cols[lf.col].kind;
+        const uint8_t* lut = a.luts + lf.lut_off + s.lut_base;
+        const int64_t lit = lf.lit_i64;
+        const int64_t litk = f64_order_key((uint64_t)lf.lit_i64);
+        const uint32_t op = lf.cmp;
+        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
+          uint32_t r = r0 + lane_id();
+          bool t = false;
+          if (r < R) {
+            RowVal rv = row_rank(s, vbm, rk, r);
+            if (rv.valid) {
+              if (s.enc == DE_DICT) t = lut[idx[rv.j]] != 0;
+              else if (kind == DK_BOOL) t = cmp_i64((int64_t)value_bool(s, a.arena, idx, rv.j), lit, op);
+              else if (kind == DK_I64) t = cmp_i64((int64_t)value_u64(s, a.arena, idx, rv.j), lit, op);
+              else if (kind == DK_F64) t = cmp_i64(f64_order_key(value_u64(s, a.arena, idx, rv.j)), litk, op);
+            }
+          }
+          uint32_t tw = __ballot_sync(0xffffffffu, t);
+          if (lane_id() == 0) Tw[r0 >> 5] = tw;
+        }
+      }
+      __syncthreads();
+
+      // ---- 6. Kleene combine on words -> selection; filter mode consumes right here ----
+      uint32_t cnt = 0;
       for (uint32_t w = tid; w < nwords; w += kScanThreads) {
         uint32_t st_t[kPredStack], st_n[kPredStack];
         int sp = 0;
-        const uint32_t* LT = smem_at<uint32_t>(smem, L.leafT);
-        const uint32_t* LN = smem_at<uint32_t>(smem, L.leafN);
+        const uint32_t rm = row_mask(w, R);
+#pragma unroll 1
         for (uint32_t i = 0; i < plan.npred; i++) {
           const DevPredOp op = plan.pred[i];
           if (op.kind == PK_LEAF) {
-            st_t[sp] = LT[op.arg * kSlabWords + w];
-            st_n[sp] = LN[op.arg * kSlabWords + w];
+            const DevLeaf& lf = plan.leaves[op.arg];
+            const SlabCol& s = ctl.slab[lf.col];
+            uint32_t V = !s.present ? 0u : (s.all_valid ? 0xffffffffu : smem_at<uint32_t>(smem, L.valid[lf.col])[w]);
+            uint32_t t, n;
+            if (lf.kind == LK_IS_NULL) { t = ~V; n = 0; }
+            else if (lf.kind == LK_IS_NOT_NULL) { t = V; n = 0; }
+            else { t = leafT[op.arg * kLeafWords + w] & V; n = ~V; }
+            st_t[sp] = t;
+            st_n[sp] = n;
             sp++;
           } else if (op.kind == PK_CONST) {
             st_t[sp] = op.arg == 1 ? 0xffffffffu : 0u;
@@ -508,16 +649,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             }
           }
         }
-        uint32_t sel = (plan.npred ? st_t[0] : 0xffffffffu) & row_mask(w, R);
-        selw[w] = sel;
-      }
-      __syncthreads();
-
-      // ---- 7. consume ----
-      if (!agg_mode) {
-        uint32_t cnt = 0;
-        for (uint32_t w = tid; w < nwords; w += kScanThreads) {
-          uint32_t sel = selw[w];
+        uint32_t sel = (plan.npred ? st_t[0] : 0xffffffffu) & rm;
+        if (agg_mode) selw[w] = sel;
+        else {
           cnt += __popc(sel);
           if (plan.write_bitmap && sel) {
             uint32_t pos = r_item + w * 32;
@@ -531,10 +665,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             }
           }
         }
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
-      } else {
-        uint32_t cnt = 0;
+      }
+      if (agg_mode) {
+        __syncthreads();
         for (uint32_t r = tid; r < R; r += kScanThreads) {
           if (!((selw[r >> 5] >> (r & 31)) & 1)) continue;
           cnt++;
@@ -545,7 +678,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
             uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
             if (rv.valid) {
-              if (key.kind == KK_BOOL) gid = value_bool(s, a.arena, rv.j);
+              if (key.kind == KK_BOOL) gid = value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[key.col]), rv.j);
               else gid = a.gid_luts[key.gid_off + s.lut_base + smem_at<uint32_t>(smem, L.idx[key.col])[rv.j]];
             }
             slot += gid * key.stride;
@@ -559,14 +692,14 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             if (!rv.valid) continue;
             if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
             if (ag.fn == AG_COUNT) continue;
-            uint64_t bits = ag.kind == DK_BOOL ? value_bool(s, a.arena, rv.j)
+            uint64_t bits = ag.kind == DK_BOOL ? value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j)
                                                : value_u64(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j);
             acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
           }
         }
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
       }
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
 
       rows_left -= R;
       r_item += R;

@@ -353,6 +353,16 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
               tc.has_dict_pages = true;
               tc.max_bw = std::max<uint32_t>(tc.max_bw, dp.bit_width);
               break;
+            case ENC_RLE:
+              // booleans in v2 data pages: 4-byte length + RLE / bit-packed hybrid, bit width 1
+              if (hf.meta.leaves[leaf_of[c]].phys_type != PT_BOOLEAN)
+                throw Error(PQ_ERR_UNSUPPORTED, "RLE value encoding on a non-boolean column");
+              dp.enc = DE_RLE_BOOL;
+              dp.bit_width = 1;
+              if (pi.num_values > 0 && pos + 4 <= pi.compressed_size) dp.val_off = pos + 4;
+              tc.has_dict_pages = true;  // needs an index window + staging like a dictionary page
+              tc.max_bw = std::max<uint32_t>(tc.max_bw, 1);
+              break;
             case ENC_DELTA_BINARY_PACKED:
               dp.enc = DE_DELTA;
               tc.has_delta_pages = true;
@@ -365,7 +375,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         tc.pages.n_pages = uint32_t(pages.size()) - tc.pages.first_page;
         if (first_row != trg.num_rows)
           throw Error(PQ_ERR_CORRUPT, col_names[c] + ": page rows do not add up to the row group's");
-        if (tc.has_dict_pages && tc.dict_n == 0 && cm.num_values > 0 &&
+        if (tc.has_dict_pages && hf.meta.leaves[leaf_of[c]].phys_type != PT_BOOLEAN && tc.dict_n == 0 && cm.num_values > 0 &&
             (cm.stats.null_count < 0 || cm.stats.null_count < cm.num_values)) {
           // dictionary-encoded pages without a dictionary page
           throw Error(PQ_ERR_CORRUPT, col_names[c] + ": dictionary-encoded pages but no dictionary page");
