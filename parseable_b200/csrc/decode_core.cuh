@@ -65,19 +65,27 @@ PQ_HD uint32_t stream_window_cap(uint32_t rows, uint32_t bw) {
 // window ends.  Appends DirEntry records; returns the values covered.
 PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEntry* dir,
                            uint32_t& nent, uint32_t max_ent) {
+  // All arithmetic is 32-bit and window relative (windows are < 64 KiB); the 64-bit arena
+  // offsets of the persistent state are rebuilt on exit.  rdata may wrap below the window for a
+  // run whose data began before it (only the not-yet-consumed tail must be inside).
   uint32_t covered = 0;
-  const uint64_t wend = w.arena_base + w.len;
+  const uint32_t wlen = w.len;
   const uint32_t bw = s.bw;
+  const uint64_t end_rel = s.end - w.arena_base;
+  const uint32_t rend = end_rel > 0xffffffffull ? 0xffffffffu : uint32_t(end_rel);
+  uint32_t rp = uint32_t(s.pos - w.arena_base);          // next header
+  int32_t rdata = int32_t(int64_t(s.data_pos) - int64_t(w.arena_base));  // current bit-packed run's data
+  uint32_t remaining = s.run_remaining, consumed = s.run_consumed, rle_value = s.rle_value, kind = s.kind;
   while (covered < need) {
-    if (s.run_remaining == 0) {
+    if (remaining == 0) {
       // parse the next header: ULEB128, at most 5 bytes for a 32-bit count
-      uint64_t p = s.pos;
-      if (p >= s.end) break;  // stream exhausted (corrupt page or padding); caller flags it
+      uint32_t p = rp;
+      if (p >= rend) break;  // stream exhausted (corrupt page or padding); caller flags it
       uint32_t h = 0;
       int shift = 0;
       bool ok = false;
-      while (p < wend && p < s.end && shift < 35) {
-        uint32_t b = w.data[p - w.arena_base];
+      while (p < wlen && p < rend && shift < 35) {
+        uint32_t b = w.data[p];
         p++;
         h |= (b & 0x7f) << shift;
         shift += 7;
@@ -86,51 +94,59 @@ PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEn
       if (!ok) break;  // header straddles the window end
       if (h & 1) {
         uint32_t groups = h >> 1;
-        s.kind = 1;
-        s.run_remaining = groups * 8;
-        s.run_consumed = 0;
-        s.data_pos = p;
-        s.pos = p + uint64_t(groups) * bw;
+        kind = 1;
+        remaining = groups * 8;
+        consumed = 0;
+        rdata = int32_t(p);
+        rp = p + groups * bw;
         if (groups == 0) continue;
       } else {
         uint32_t vbytes = (bw + 7) >> 3;
-        if (p + vbytes > wend) break;
+        if (p + vbytes > wlen) break;
         uint32_t v = 0;
-        for (uint32_t i = 0; i < vbytes; i++) v |= uint32_t(w.data[p + i - w.arena_base]) << (8 * i);
-        s.kind = 0;
-        s.run_remaining = h >> 1;
-        s.run_consumed = 0;
-        s.rle_value = v;
-        s.pos = p + vbytes;
-        if (s.run_remaining == 0) continue;
+        for (uint32_t i = 0; i < vbytes; i++) v |= uint32_t(w.data[p + i]) << (8 * i);
+        kind = 0;
+        remaining = h >> 1;
+        consumed = 0;
+        rle_value = v;
+        rp = p + vbytes;
+        if (remaining == 0) continue;
       }
     }
     if (nent >= max_ent) break;
-    uint32_t take = s.run_remaining;
+    uint32_t take = remaining;
     if (take > need - covered) take = need - covered;
     if (take > uint32_t(kDirEntryMaxValues)) take = kDirEntryMaxValues;
     DirEntry e;
     e.start = covered;
-    if (s.kind == 1) {
-      // the bytes of values [run_consumed, run_consumed+take) must lie inside the window
-      uint64_t avail_bits = (wend > s.data_pos) ? (wend - s.data_pos) * 8 : 0;
-      if (bw != 0) {
-        uint64_t fit = avail_bits / bw;
-        if (fit <= s.run_consumed) break;
-        if (fit - s.run_consumed < take) take = uint32_t(fit - s.run_consumed);
+    if (kind == 1) {
+      // the bits of values [consumed, consumed+take) must lie inside the window
+      int32_t avail_bits = (int32_t(wlen) - rdata) * 8;   // rdata may be negative: more bits, all before `consumed`
+      int32_t first_bit = int32_t(consumed * bw);
+      if (int32_t((consumed + take) * bw) > avail_bits) {
+        if (bw == 0 || avail_bits <= first_bit) break;
+        uint32_t fit = uint32_t(avail_bits) / bw;
+        if (fit <= consumed) break;
+        take = fit - consumed;
       }
       e.kind = 1;
-      e.payload = uint32_t((s.data_pos - w.arena_base) * 8 + uint64_t(s.run_consumed) * bw);
+      e.payload = uint32_t(rdata * 8 + first_bit);   // >= 0: the window starts at or before the first unread bit
     } else {
       e.kind = 0;
-      e.payload = s.rle_value;
+      e.payload = rle_value;
     }
     e.count = uint16_t(take);
     dir[nent++] = e;
     covered += take;
-    s.run_remaining -= take;
-    s.run_consumed += take;
+    remaining -= take;
+    consumed += take;
   }
+  s.pos = w.arena_base + rp;
+  s.data_pos = uint64_t(int64_t(w.arena_base) + rdata);
+  s.run_remaining = remaining;
+  s.run_consumed = consumed;
+  s.rle_value = rle_value;
+  s.kind = uint8_t(kind);
   return covered;
 }
 

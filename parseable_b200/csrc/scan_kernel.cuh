@@ -91,6 +91,8 @@ struct ScanCtl {
   uint32_t any_nulls;    // some column of this slab has a NULL (general path)
   uint32_t target;       // rows the next slab should try to take
   uint32_t rmin[kMaxCols];
+  uint32_t wcur[kScanWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
+  uint32_t stk[kScanWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
   ColCursor cur[kMaxCols];
   SlabCol slab[kMaxCols];
 };
@@ -284,6 +286,178 @@ __device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
   return l < 2 && col < ncols;
 }
 
+
+// ---- the no-NULL fast row pass --------------------------------------------------------------
+// Dictionary index of row r (== value r: the slab has no NULLs) of column c, straight from the
+// staged bytes through the run directory.  Control flow is warp uniform except the (rare) walk
+// across directory entries inside one 32-row word.
+__device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
+                                             uint32_t base_row, uint32_t r, bool in) {
+  const SlabCol& s = ctl.slab[c];
+  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
+  const uint32_t n = s.nval;
+  uint32_t e = ctl.wcur[warp_id()][c];
+  while (e + 1 < n && dir[e + 1].start <= base_row) e++;
+  ctl.wcur[warp_id()][c] = e;
+  if (!in) return 0;
+  while (e + 1 < n && dir[e + 1].start <= r) e++;
+  const DirEntry d = dir[e];
+  return d.kind ? bp_get(smem_at<uint32_t>(smem, L.valwin[c][buf]), d.payload, s.bw, r - d.start) : d.payload;
+}
+
+__device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const uint8_t* arena,
+                                                   uint32_t c, uint32_t buf, uint32_t base_row, uint32_t r, bool in, bool want) {
+  const SlabCol& s = ctl.slab[c];
+  if (PQB_ENC_HAS_STREAM(s.enc)) {
+    uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
+    if (s.enc == DE_RLE_BOOL) return v & 1;
+    return (in && want) ? load_u64_unaligned(arena + s.dict_off + uint64_t(v) * 8) : 0;
+  }
+  return (in && want) ? load_u64_unaligned(arena + s.val_base + uint64_t(s.vals_done + r) * 8) : 0;
+}
+
+// One 32-row word of one leaf: returns T (and N through *nw); all lanes get the same words.
+__device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                                   const DevScanArgs& a, uint32_t l, uint32_t buf, uint32_t base_row,
+                                                   uint32_t r, bool in, uint32_t* nw) {
+  const DevLeaf& lf = plan.leaves[l];
+  const uint32_t c = lf.col;
+  const SlabCol& s = ctl.slab[c];
+  *nw = 0;
+  if (!s.present) {  // column missing from this file: every row NULL
+    if (lf.kind == LK_IS_NULL) return 0xffffffffu;
+    if (lf.kind == LK_IS_NOT_NULL) return 0;
+    *nw = 0xffffffffu;
+    return 0;
+  }
+  if (lf.kind == LK_IS_NULL) return 0;
+  if (lf.kind == LK_IS_NOT_NULL) return 0xffffffffu;
+  const uint8_t kind = plan.cols[c].kind;
+  bool t = false;
+  if (PQB_ENC_HAS_STREAM(s.enc)) {
+    uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
+    if (in) t = s.enc == DE_DICT ? a.luts[lf.lut_off + s.lut_base + v] != 0 : cmp_i64((int64_t)(v & 1), lf.lit_i64, lf.cmp);
+  } else if (in) {
+    if (kind == DK_BOOL) {
+      uint32_t k = s.vals_done + r;
+      t = cmp_i64((int64_t)((a.arena[s.val_base + (k >> 3)] >> (k & 7)) & 1), lf.lit_i64, lf.cmp);
+    } else {
+      uint64_t v = load_u64_unaligned(a.arena + s.val_base + uint64_t(s.vals_done + r) * 8);
+      t = kind == DK_F64 ? cmp_i64(f64_order_key(v), f64_order_key((uint64_t)lf.lit_i64), lf.cmp)
+                         : cmp_i64((int64_t)v, lf.lit_i64, lf.cmp);
+    }
+  }
+  return __ballot_sync(0xffffffffu, t);
+}
+
+// Every warp owns whole 32-row words of the slab: leaves -> Kleene combine -> consume, all in
+// registers / per-warp scratch.  No leaf bitmaps, no staging, no block barrier.  Returns the rows
+// this thread's warp selected (lane 0 carries the count).
+__device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                              const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
+                                              uint32_t r_item, unsigned long long* acc, bool agg_mode) {
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const uint32_t nwords = (R + 31) >> 5;
+  const uint32_t nslots = plan.nslots;
+  if (lane < plan.ncols) ctl.wcur[warp][lane] = 0;
+  __syncwarp();
+  uint32_t* st = ctl.stk[warp];
+  uint32_t cnt = 0;
+  for (uint32_t w = warp; w < nwords; w += kScanWarps) {
+    const uint32_t base_row = w * 32, r = base_row + lane;
+    const bool in = r < R;
+    int sp = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < plan.npred; i++) {
+      const DevPredOp op = plan.pred[i];
+      if (op.kind == PK_LEAF) {
+        uint32_t n;
+        uint32_t t = fast_leaf_word(plan, ctl, L, smem, a, op.arg, buf, base_row, r, in, &n);
+        st[2 * sp] = t;
+        st[2 * sp + 1] = n;
+        sp++;
+      } else if (op.kind == PK_CONST) {
+        st[2 * sp] = op.arg == 1 ? 0xffffffffu : 0u;
+        st[2 * sp + 1] = op.arg == 2 ? 0xffffffffu : 0u;
+        sp++;
+      } else if (op.kind == PK_NOT) {
+        st[2 * sp - 2] = ~(st[2 * sp - 2] | st[2 * sp - 1]);
+      } else {
+        uint32_t tb = st[2 * sp - 2], nb = st[2 * sp - 1], ta = st[2 * sp - 4], na = st[2 * sp - 3];
+        sp--;
+        if (op.kind == PK_AND) {
+          uint32_t fa = ~(ta | na), fb = ~(tb | nb);
+          st[2 * sp - 2] = ta & tb;
+          st[2 * sp - 1] = (na | nb) & ~fa & ~fb;
+        } else {
+          uint32_t t = ta | tb;
+          st[2 * sp - 2] = t;
+          st[2 * sp - 1] = (na | nb) & ~t;
+        }
+      }
+    }
+    const uint32_t sel = (plan.npred ? st[0] : 0xffffffffu) & row_mask(w, R);
+    if (!agg_mode) {
+      if (lane == 0) {
+        cnt += __popc(sel);
+        if (plan.write_bitmap && sel) {
+          uint32_t pos = r_item + base_row;
+          uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+          uint32_t sh = pos & 31;
+          if (sh == 0) *dst = sel;
+          else {
+            atomicOr(dst, sel << sh);
+            uint32_t hi = sel >> (32 - sh);
+            if (hi) atomicOr(dst + 1, hi);
+          }
+        }
+      }
+      continue;
+    }
+    if (sel == 0) continue;  // uniform
+    const bool mine = (sel >> lane) & 1;
+    if (lane == 0) cnt += __popc(sel);
+    uint32_t slot = 0;
+    for (uint32_t k = 0; k < plan.nkeys; k++) {
+      const DevKey& key = plan.keys[k];
+      const SlabCol& s = ctl.slab[key.col];
+      uint32_t gid = key.card;  // column missing: NULL group
+      if (s.present) {
+        if (key.kind == KK_BOOL) {
+          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+          if (!PQB_ENC_HAS_STREAM(s.enc)) {
+            uint32_t kk = s.vals_done + r;
+            gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
+          }
+        } else {
+          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
+          gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
+        }
+      }
+      slot += gid * key.stride;
+    }
+    if (mine) atomicAdd(&acc[slot], 1ull);
+    for (uint32_t g = 0; g < plan.naggs; g++) {
+      const DevAgg& ag = plan.aggs[g];
+      if (ag.fn == AG_COUNT_STAR) continue;
+      const SlabCol& s = ctl.slab[ag.col];
+      if (!s.present) continue;  // all NULL: contributes nothing
+      uint64_t bits;
+      if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
+        uint32_t kk = s.vals_done + r;
+        bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
+      } else {
+        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+      }
+      if (!mine) continue;
+      if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+      if (ag.fn == AG_COUNT) continue;
+      acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
+    }
+  }
+  return cnt;
+}
+
 // The general per-slab walk (columns with NULLs, window / directory overflow): definition levels ->
 // validity bitmap + ranks -> index streams, shrinking the slab until every column is covered.
 // All threads call it; returns the rows of the slab (0: corrupt page).
@@ -396,7 +570,7 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
   return 0;
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   ScanCtl& ctl = *reinterpret_cast<ScanCtl*>(smem);
@@ -503,8 +677,6 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         }
         if (rc < R0) atomicMin(&ctl.rmin_all, rc);
       }
-      // leaf bitmaps accumulate with OR: clear them while the walkers run
-      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
       __syncthreads();
       uint32_t R = R0;
       if (ctl.rmin_all < R0 || ctl.any_nulls) {  // uniform: general path from the snapshots
@@ -538,8 +710,17 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       if (ctl.error) break;
       if (tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
 
-      // ---- 4. unpack: fused index -> leaf bits where possible, else stage indices ----
       const uint32_t nwords = (R + 31) >> 5;
+      bool has_nulls = false;
+      for (uint32_t c = 0; c < ncols; c++) has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
+      uint32_t cnt = 0;
+      if (!has_nulls) {
+        // ---- 4-6 (fast): row-major pass, one warp per 32-row word ----
+        cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+      } else {
+      // ---- 4. (general) unpack: fused index -> leaf bits where possible, else stage indices ----
+      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
+      __syncthreads();
       for (uint32_t c = 0; c < ncols; c++) {
         const SlabCol& s = ctl.slab[c];
         if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
@@ -610,7 +791,6 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       __syncthreads();
 
       // ---- 6. Kleene combine on words -> selection; filter mode consumes right here ----
-      uint32_t cnt = 0;
       for (uint32_t w = tid; w < nwords; w += kScanThreads) {
         uint32_t st_t[kPredStack], st_n[kPredStack];
         int sp = 0;
@@ -698,6 +878,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           }
         }
       }
+      }  // general row phase
       for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
 
