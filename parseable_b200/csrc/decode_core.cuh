@@ -76,6 +76,7 @@ PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEn
   uint32_t rp = uint32_t(s.pos - w.arena_base);          // next header
   int32_t rdata = int32_t(int64_t(s.data_pos) - int64_t(w.arena_base));  // current bit-packed run's data
   uint32_t remaining = s.run_remaining, consumed = s.run_consumed, rle_value = s.rle_value, kind = s.kind;
+  uint32_t chunks = nent ? uint32_t(dir[nent - 1].chunk0) + ((uint32_t(dir[nent - 1].count) + 31u) >> 5) : 0u;
   while (covered < need) {
     if (remaining == 0) {
       // parse the next header: ULEB128, at most 5 bytes for a 32-bit count
@@ -136,6 +137,8 @@ PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEn
       e.payload = rle_value;
     }
     e.count = uint16_t(take);
+    e.chunk0 = uint8_t(chunks);
+    chunks += (take + 31u) >> 5;
     dir[nent++] = e;
     covered += take;
     remaining -= take;
@@ -148,6 +151,150 @@ PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEn
   s.rle_value = rle_value;
   s.kind = uint8_t(kind);
   return covered;
+}
+
+// ---- DELTA_BINARY_PACKED (Parseable's p_timestamp, streams.rs:587-590) ----------------------
+// header: block size, miniblocks per block, total count, first value (zigzag); then per block:
+// min delta (zigzag), one bit width per miniblock, miniblock bodies (values - min delta, bit packed).
+struct DeltaState {
+  int64_t last_value;       // running prefix: value of the last decoded row of this page
+  int64_t min_delta;
+  int64_t first_value;
+  uint64_t pos;             // next unread structure (page header / block header / miniblock body)
+  uint64_t end;
+  uint64_t mini_data;       // body of the current miniblock
+  uint32_t vals_per_mini;
+  uint32_t n_mini;
+  uint32_t mini_idx;        // next miniblock of the current block (== n_mini: a block header comes next)
+  uint32_t mini_remaining;  // values left in the current miniblock
+  uint32_t mini_consumed;
+  uint32_t total_left;      // deltas left in the page
+  uint8_t bws[8];
+  uint8_t header_done;
+  uint8_t first_pending;    // the page's first value has not been emitted yet
+  uint8_t cur_bw;
+  uint8_t bad;              // malformed / unsupported geometry
+};
+
+struct DeltaEntry {
+  uint32_t start;      // first value (slab relative)
+  uint16_t count;
+  uint8_t bw;
+  uint8_t kind;        // 0: packed deltas, 1: the page's first value (absolute, in min_delta)
+  uint32_t bitoff;     // of the first value inside the window
+  uint32_t _pad;
+  int64_t min_delta;
+};
+
+PQ_HD void delta_init(DeltaState& s, uint64_t begin, uint64_t end) {
+  s.last_value = 0; s.min_delta = 0; s.first_value = 0;
+  s.pos = begin; s.end = end; s.mini_data = begin;
+  s.vals_per_mini = 0; s.n_mini = 0; s.mini_idx = 0; s.mini_remaining = 0; s.mini_consumed = 0; s.total_left = 0;
+  for (int i = 0; i < 8; i++) s.bws[i] = 0;
+  s.header_done = 0; s.first_pending = 0; s.cur_bw = 0; s.bad = 0;
+}
+
+PQ_HD uint64_t delta_window_start(const DeltaState& s) {
+  if (s.header_done && s.mini_remaining != 0) return s.mini_data + ((uint64_t(s.mini_consumed) * s.cur_bw) >> 3);
+  return s.pos;
+}
+
+// ULEB128 inside a window; returns false when it runs past `lim`
+PQ_HD bool win_varint(const Window& w, uint32_t& p, uint32_t lim, uint64_t& out) {
+  uint64_t v = 0;
+  for (int shift = 0; shift < 70; shift += 7) {
+    if (p >= lim) return false;
+    uint32_t b = w.data[p++];
+    if (shift < 64) v |= uint64_t(b & 0x7f) << shift;
+    if (!(b & 0x80)) { out = v; return true; }
+  }
+  return false;
+}
+
+PQ_HD uint32_t walk_delta(DeltaState& s, const Window& w, uint32_t need, DeltaEntry* dir, uint32_t& nent,
+                          uint32_t max_ent) {
+  uint32_t covered = 0;
+  if (s.bad) return 0;
+  const uint64_t end_rel = s.end - w.arena_base;
+  const uint32_t lim = end_rel < w.len ? uint32_t(end_rel) : w.len;   // readable bytes of the stream in this window
+  if (!s.header_done) {
+    uint32_t p = uint32_t(s.pos - w.arena_base);
+    uint64_t bs, nm, total, fz;
+    if (!win_varint(w, p, lim, bs) || !win_varint(w, p, lim, nm) || !win_varint(w, p, lim, total) ||
+        !win_varint(w, p, lim, fz))
+      return 0;
+    if (nm == 0 || nm > 8 || bs == 0 || bs % nm != 0 || bs > (1u << 20)) { s.bad = 1; return 0; }
+    s.vals_per_mini = uint32_t(bs / nm);
+    s.n_mini = uint32_t(nm);
+    s.mini_idx = s.n_mini;
+    s.first_value = int64_t(fz >> 1) ^ -int64_t(fz & 1);
+    s.first_pending = total > 0;
+    s.total_left = total > 0 ? uint32_t(total - 1) : 0;
+    s.pos = w.arena_base + p;
+    s.header_done = 1;
+  }
+  while (covered < need) {
+    if (nent >= max_ent) break;
+    if (s.first_pending) {
+      DeltaEntry e;
+      e.start = covered; e.count = 1; e.bw = 0; e.kind = 1; e.bitoff = 0; e._pad = 0; e.min_delta = s.first_value;
+      dir[nent++] = e;
+      s.first_pending = 0;
+      covered++;
+      continue;
+    }
+    if (s.mini_remaining == 0) {
+      if (s.total_left == 0) break;
+      uint32_t p = uint32_t(s.pos - w.arena_base);
+      if (s.mini_idx >= s.n_mini) {  // block header
+        uint64_t mz;
+        uint32_t q = p;
+        if (!win_varint(w, q, lim, mz) || q + s.n_mini > lim) break;
+        s.min_delta = int64_t(mz >> 1) ^ -int64_t(mz & 1);
+        for (uint32_t i = 0; i < s.n_mini; i++) s.bws[i] = w.data[q + i];
+        p = q + s.n_mini;
+        s.mini_idx = 0;
+      }
+      s.cur_bw = s.bws[s.mini_idx];
+      if (s.cur_bw > 64) { s.bad = 1; break; }
+      s.mini_data = w.arena_base + p;
+      s.pos = s.mini_data + (uint64_t(s.vals_per_mini) * s.cur_bw) / 8;
+      s.mini_consumed = 0;
+      s.mini_remaining = s.vals_per_mini < s.total_left ? s.vals_per_mini : s.total_left;
+      s.mini_idx++;
+    }
+    uint32_t take = s.mini_remaining;
+    if (take > need - covered) take = need - covered;
+    int64_t rdata = int64_t(s.mini_data) - int64_t(w.arena_base);
+    int64_t avail_bits = (int64_t(w.len) - rdata) * 8;
+    int64_t first_bit = int64_t(s.mini_consumed) * s.cur_bw;
+    if (first_bit + int64_t(take) * s.cur_bw > avail_bits) {
+      if (s.cur_bw == 0 || avail_bits <= first_bit) break;
+      uint32_t fit = uint32_t((avail_bits - first_bit) / s.cur_bw);
+      if (fit == 0) break;
+      take = fit;
+    }
+    DeltaEntry e;
+    e.start = covered; e.count = uint16_t(take); e.bw = s.cur_bw; e.kind = 0;
+    e.bitoff = uint32_t(rdata * 8 + first_bit); e._pad = 0; e.min_delta = s.min_delta;
+    dir[nent++] = e;
+    covered += take;
+    s.mini_remaining -= take;
+    s.mini_consumed += take;
+    s.total_left -= take;
+  }
+  return covered;
+}
+
+// bw <= 64; the window keeps 8 bytes of slack so the third word is readable
+PQ_HD uint64_t bp_get64(const uint32_t* words, uint32_t bitoff, uint32_t bw, uint32_t j) {
+  if (bw == 0) return 0;
+  uint32_t bit = bitoff + j * bw;
+  uint32_t wi = bit >> 5, sh = bit & 31;
+  uint64_t lo = uint64_t(words[wi]) | (uint64_t(words[wi + 1]) << 32);
+  uint64_t v = lo >> sh;
+  if (sh && bw + sh > 64) v |= uint64_t(words[wi + 2]) << (64 - sh);
+  return bw >= 64 ? v : (v & ((1ull << bw) - 1ull));
 }
 
 // Value j of a bit-packed run whose first value starts at bit `bitoff` of a

@@ -15,12 +15,16 @@ constexpr int kSlabRows = 2048;   // rows decoded per CTA iteration
 constexpr int kSlabWords = kSlabRows / 32;
 constexpr int kMaxDirEntries = 64;  // run-directory entries per stream per slab
 constexpr int kDirEntryMaxValues = 512;
+constexpr int kMaxDeltaEntries = 80;  // DELTA_BINARY_PACKED miniblock directory entries per slab
+constexpr int kDeltaWindowBytes = 8192 + 64;
 constexpr int kPredStack = 8;
 
 // page value encodings as the kernels see them
 enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2, DE_RLE_BOOL = 3 };
 // DE_DICT and DE_RLE_BOOL carry an RLE / bit-packed hybrid value stream (staged + walked)
 #define PQB_ENC_HAS_STREAM(e) ((e) == ::pqb::DE_DICT || (e) == ::pqb::DE_RLE_BOOL)
+// ... and DE_DELTA pages are staged too (their own walker: block / miniblock headers)
+#define PQB_ENC_HAS_WINDOW(e) (PQB_ENC_HAS_STREAM(e) || (e) == ::pqb::DE_DELTA)
 // physical value kinds
 enum DevKind : uint8_t { DK_I64 = 0, DK_F64 = 1, DK_STR = 2, DK_BOOL = 3, DK_I32 = 4, DK_F32 = 5 };
 
@@ -126,6 +130,11 @@ struct DevPlan {
   // per accumulator array, how cells start and merge: 0 integer add (0), 1 f64 add (0.0),
   // 2 signed min (INT64_MAX), 3 signed max (INT64_MIN); f64 MIN/MAX run on order keys
   uint8_t acc_init[kMaxAggs * 2];
+  // leaves a dictionary LUT answers, per column (host precomputed): how many, and the first two
+  uint8_t col_nlut[kMaxCols];
+  int8_t col_l0[kMaxCols];
+  int8_t col_l1[kMaxCols];
+  uint32_t row_major;          // 1: no-NULL slabs use the register-only row-major pass
 };
 
 // Accumulator table layout (device, 8-byte cells, struct of arrays over nslots):
@@ -151,7 +160,8 @@ struct DevScanArgs {
 struct DirEntry {
   uint32_t start;    // first value (slab relative)
   uint16_t count;
-  uint16_t kind;     // 0 RLE, 1 bit-packed
+  uint8_t kind;      // 0 RLE, 1 bit-packed
+  uint8_t chunk0;    // running count of 32-value chunks before this entry (balances warps)
   uint32_t payload;  // RLE: value; bit-packed: bit offset of the first value inside the window
 };
 

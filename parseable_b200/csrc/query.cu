@@ -404,6 +404,19 @@ void Query::run(const PqQueryDesc& d) {
     nleaves++;
   }
   plan.nleaves = nleaves;
+  // per column: the leaves a dictionary LUT answers (the kernel fuses up to two into the unpack)
+  for (uint32_t c = 0; c < (uint32_t)kMaxCols; c++) { plan.col_nlut[c] = 0; plan.col_l0[c] = -1; plan.col_l1[c] = -1; }
+  for (uint32_t l = 0; l < nleaves; l++) {
+    const DevLeaf& lf = plan.leaves[l];
+    if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;
+    if (plan.col_nlut[lf.col] == 0) plan.col_l0[lf.col] = int8_t(l);
+    else if (plan.col_nlut[lf.col] == 1) plan.col_l1[lf.col] = int8_t(l);
+    plan.col_nlut[lf.col]++;
+  }
+  {
+    const char* rm = getenv("PQB_ROW_MAJOR");  // experiment switch: register-only row-major pass for no-NULL slabs
+    plan.row_major = rm && rm[0] == '1';
+  }
   plan.npred = uint32_t(prog.size());
   for (size_t i = 0; i < prog.size(); i++) {
     plan.pred[i] = prog[i];
@@ -487,7 +500,9 @@ void Query::run(const PqQueryDesc& d) {
         total_entries += tc.dict_n;
         if (total_entries > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "too many dictionary entries for one query");
       }
-      if (tc.has_delta_pages) throw Error(PQ_ERR_UNSUPPORTED, "column '" + table->columns[tcol[qcol_of_slot[s]]].name + "': DELTA_BINARY_PACKED pages are read only when statistics cannot decide the predicate (not yet decoded on the GPU)");
+      if (tc.has_delta_pages && kind != DK_I64)
+        throw Error(PQ_ERR_UNSUPPORTED, "column '" + table->columns[tcol[qcol_of_slot[s]]].name + "': DELTA_BINARY_PACKED is decoded for INT64 columns only");
+      plan.cols[s].has_delta |= tc.has_delta_pages;
       if (tc.has_plain_pages && kind == DK_STR)
         throw Error(PQ_ERR_UNSUPPORTED, "column '" + table->columns[tcol[qcol_of_slot[s]]].name + "': PLAIN (dictionary-fallback) string pages are not decoded on the GPU yet");
       if (kind == DK_STR && tc.dict_n == 0 && tc.has_dict_pages && false) {}
@@ -549,7 +564,7 @@ void Query::run(const PqQueryDesc& d) {
     key.col = uint8_t(slot_of[d.group_by[k]]);
     uint8_t kind = plan.cols[key.col].kind;
     key.kind = kind == DK_BOOL ? KK_BOOL : KK_DICT_LUT;
-    if (key.kind == KK_DICT_LUT && plan.cols[key.col].has_plain)
+    if (key.kind == KK_DICT_LUT && (plan.cols[key.col].has_plain || plan.cols[key.col].has_delta))
       throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has PLAIN (dictionary-fallback) pages; only dictionary-encoded keys are on the GPU path");
   }
 
@@ -561,13 +576,17 @@ void Query::run(const PqQueryDesc& d) {
     // anything denser makes the kernel shrink the slab (always correct, only slower)
     L.defwin_cap[s] = plan.cols[s].max_def ? align_up(kSlabRows / 8 + kSlabRows / 16 + 64, 16) : 0;
     L.valwin_cap[s] = plan.cols[s].has_dict ? align_up(kSlabRows * plan.cols[s].max_bw / 8 + kSlabRows / 8 + 64, 16) : 0;
+    if (plan.cols[s].has_delta) L.valwin_cap[s] = std::max<uint32_t>(L.valwin_cap[s], align_up(kDeltaWindowBytes, 16));
     for (int b = 0; b < 2; b++) { L.defwin[s][b] = off; off += align_up(L.defwin_cap[s] + 16, 128); }
     for (int b = 0; b < 2; b++) { L.valwin[s][b] = off; off += align_up(L.valwin_cap[s] + 16, 128); }
     L.valid[s] = off; off += align_up((kSlabWords + 2) * 4, 16);
     L.rank[s] = off; off += kSlabWords * 4;
-    L.idx[s] = plan.cols[s].has_dict ? off : 0; if (plan.cols[s].has_dict) off += kSlabRows * 4;
+    // staging: u32 dictionary indices, or i64 values of DELTA_BINARY_PACKED pages
+    L.idx[s] = (plan.cols[s].has_dict || plan.cols[s].has_delta) ? off : 0;
+    off += plan.cols[s].has_delta ? kSlabRows * 8 : (plan.cols[s].has_dict ? kSlabRows * 4 : 0);
     L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
-    L.valdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
+    L.valdir[s] = off;
+    off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
   }
   L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
   L.sel = off; off += kSlabWords * 4;

@@ -54,6 +54,7 @@ constexpr int kLeafWords = kSlabWords + 2;
 // per-column cursor over the pages of one column chunk
 struct ColCursor {
   StreamState def, val;
+  DeltaState dl;            // value stream of a DELTA_BINARY_PACKED page
   uint64_t val_base;        // arena offset of the values section of the current page
   uint64_t defwin_base[2];  // arena base of the staged windows
   uint64_t valwin_base[2];
@@ -80,6 +81,7 @@ struct SlabCol {
   uint32_t ndef, nval;
   uint32_t lut_base;
   uint32_t _pad;
+  int64_t dl_last;          // DELTA pages: value of the last row decoded so far in this page
 };
 
 struct ScanCtl {
@@ -91,6 +93,7 @@ struct ScanCtl {
   uint32_t any_nulls;    // some column of this slab has a NULL (general path)
   uint32_t target;       // rows the next slab should try to take
   uint32_t rmin[kMaxCols];
+  int64_t scan_tmp[kScanWarps];             // DELTA prefix scan: per-warp totals
   uint32_t wcur[kScanWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
   uint32_t stk[kScanWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
   ColCursor cur[kMaxCols];
@@ -107,6 +110,11 @@ __device__ __forceinline__ void page_enter(ColCursor& c, const DevPage* pages, u
   c.val_base = p.off + p.val_off;
   stream_init(c.def, p.off + p.def_off, p.off + p.def_off + p.def_len, 1);
   stream_init(c.val, p.off + p.val_off, p.off + p.len, p.bit_width);
+  if (p.enc == DE_DELTA) delta_init(c.dl, p.off + p.val_off, p.off + p.len);
+}
+
+__device__ __forceinline__ uint64_t value_window_start(const ColCursor& c) {
+  return c.enc == DE_DELTA ? delta_window_start(c.dl) : stream_window_start(c.val);
 }
 
 // thread 0: stage the windows every stream needs next into buffer `buf`, and publish the row
@@ -120,7 +128,7 @@ __device__ __forceinline__ void issue_windows(ScanCtl& ctl, const SmemLayout& L,
     if (!cr.present) continue;
     target = cr.page_rows_left < target ? cr.page_rows_left : target;
     if (cr.has_def) bytes += L.defwin_cap[c];
-    if (PQB_ENC_HAS_STREAM(cr.enc)) bytes += L.valwin_cap[c];
+    if (PQB_ENC_HAS_WINDOW(cr.enc)) bytes += L.valwin_cap[c];
   }
   ctl.target = target;
   ctl.rmin_all = target;
@@ -134,8 +142,8 @@ __device__ __forceinline__ void issue_windows(ScanCtl& ctl, const SmemLayout& L,
       cr.defwin_base[buf] = s;
       tma_load_1d(smem + L.defwin[c][buf], arena + s, L.defwin_cap[c], &ctl.mbar[buf]);
     }
-    if (PQB_ENC_HAS_STREAM(cr.enc)) {
-      uint64_t s = stream_window_start(cr.val) & ~15ull;
+    if (PQB_ENC_HAS_WINDOW(cr.enc)) {
+      uint64_t s = value_window_start(cr) & ~15ull;
       cr.valwin_base[buf] = s;
       tma_load_1d(smem + L.valwin[c][buf], arena + s, L.valwin_cap[c], &ctl.mbar[buf]);
     }
@@ -180,39 +188,37 @@ __device__ __forceinline__ void dir_to_idx(const DirEntry* dir, uint32_t nent, c
 }
 
 // Fused unpack -> leaf LUT -> ballot: no index staging.  Up to two leaves of the same column are
-// evaluated from one unpacked index; bits land in VALUE space (== row space when the slab has no NULLs).
+// evaluated from one unpacked index; bits land in VALUE space (== row space when the slab has no
+// NULLs).  Work is dealt to warps in 32-value chunks (DirEntry.chunk0), not whole runs, so a slab
+// with five 504-value runs still keeps all eight warps busy.
+template <bool kTwo>
 __device__ __forceinline__ void dir_to_leafbits(const DirEntry* dir, uint32_t nent, const uint32_t* win, uint32_t bw,
                                                 const uint8_t* __restrict__ lut0, uint32_t* T0,
                                                 const uint8_t* __restrict__ lut1, uint32_t* T1, uint32_t* idx) {
-  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
-    const DirEntry d = dir[e];
-    if (d.kind) {
-      for (uint32_t k = 0; k < d.count; k += 32) {
-        uint32_t j = k + lane_id();
-        bool in = j < d.count;
-        uint32_t v = in ? bp_get(win, d.payload, bw, j) : 0;
-        if (idx && in) idx[d.start + j] = v;
-        uint32_t w0 = __ballot_sync(0xffffffffu, in && lut0[v]);
-        uint32_t w1 = lut1 ? __ballot_sync(0xffffffffu, in && lut1[v]) : 0;
-        if (lane_id() == 0) {
-          if (w0) or_bits(T0, d.start + k, w0);
-          if (w1) or_bits(T1, d.start + k, w1);
-        }
-      }
-    } else {
-      // an RLE run: one LUT probe decides the whole run
-      const bool t0 = lut0[d.payload] != 0;
-      const bool t1 = lut1 ? lut1[d.payload] != 0 : false;
-      for (uint32_t k = 0; k < d.count; k += 32) {
-        uint32_t j = k + lane_id();
-        bool in = j < d.count;
-        if (idx && in) idx[d.start + j] = d.payload;
-        uint32_t m = __ballot_sync(0xffffffffu, in);
-        if (lane_id() == 0) {
-          if (t0) or_bits(T0, d.start + k, m);
-          if (t1) or_bits(T1, d.start + k, m);
-        }
-      }
+  if (nent == 0) return;
+  const DirEntry last = dir[nent - 1];
+  const uint32_t nchunks = uint32_t(last.chunk0) + ((uint32_t(last.count) + 31u) >> 5);
+  const uint32_t lane = lane_id();
+  uint32_t e = 0;
+  DirEntry d = dir[0];
+  uint32_t next0 = nent > 1 ? uint32_t(dir[1].chunk0) : 0xffffffffu;
+  for (uint32_t q = warp_id(); q < nchunks; q += kScanWarps) {
+    while (q >= next0) {  // warp uniform; chunks are visited in increasing order
+      e++;
+      d = dir[e];
+      next0 = e + 1 < nent ? uint32_t(dir[e + 1].chunk0) : 0xffffffffu;
+    }
+    const uint32_t k = (q - d.chunk0) * 32;
+    const uint32_t j = k + lane;
+    const bool in = j < d.count;
+    const uint32_t v = d.kind ? (in ? bp_get(win, d.payload, bw, j) : 0u) : d.payload;
+    if (idx && in) idx[d.start + j] = v;
+    const uint32_t w0 = __ballot_sync(0xffffffffu, in && lut0[v]);
+    uint32_t w1 = 0;
+    if (kTwo) w1 = __ballot_sync(0xffffffffu, in && lut1[v]);
+    if (lane == 0) {
+      if (w0) or_bits(T0, d.start + k, w0);
+      if (kTwo && w1) or_bits(T1, d.start + k, w1);
     }
   }
 }
@@ -235,6 +241,7 @@ __device__ __forceinline__ RowVal row_rank(const SlabCol& c, const uint32_t* val
 // 8-byte value of a non-null row: dictionary entry or PLAIN slot
 __device__ __forceinline__ uint64_t value_u64(const SlabCol& c, const uint8_t* arena, const uint32_t* idx, uint32_t j) {
   if (c.enc == DE_DICT) return load_u64_unaligned(arena + c.dict_off + uint64_t(idx[j]) * 8);
+  if (c.enc == DE_DELTA) return reinterpret_cast<const uint64_t*>(idx)[j];  // decoded + prefix-summed in place
   return load_u64_unaligned(arena + c.val_base + uint64_t(c.vals_done + j) * 8);
 }
 __device__ __forceinline__ uint32_t value_bool(const SlabCol& c, const uint8_t* arena, const uint32_t* idx, uint32_t j) {
@@ -287,6 +294,49 @@ __device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
 }
 
 
+// ---- DELTA_BINARY_PACKED: miniblock directory -> deltas -> block-wide inclusive scan -> values ----
+__device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf) {
+  SlabCol& s = ctl.slab[c];
+  const uint32_t nv = s.nv;
+  int64_t* vals = smem_at<int64_t>(smem, L.idx[c]);
+  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c]);
+  const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
+  for (uint32_t e = warp_id(); e < s.nval; e += kScanWarps) {
+    const DeltaEntry d = dir[e];
+    for (uint32_t j = lane_id(); j < d.count; j += 32)
+      vals[d.start + j] = d.kind ? d.min_delta : int64_t(uint64_t(d.min_delta) + bp_get64(win, d.bitoff, d.bw, j));
+  }
+  __syncthreads();
+  // a slab that starts a page begins with the page's first value (absolute): no carry
+  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : s.dl_last;
+  constexpr uint32_t kPer = kSlabRows / kScanThreads;
+  const uint32_t b = threadIdx.x * kPer;
+  int64_t loc[kPer];
+  int64_t sum = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kPer; i++) {
+    int64_t v = (b + i < nv) ? vals[b + i] : 0;
+    sum = int64_t(uint64_t(sum) + uint64_t(v));
+    loc[i] = sum;
+  }
+  int64_t incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane_id() >= o) incl = int64_t(uint64_t(incl) + uint64_t(t));
+  }
+  if (lane_id() == 31) ctl.scan_tmp[warp_id()] = incl;
+  __syncthreads();
+  int64_t base = carry;
+  for (uint32_t w = 0; w < warp_id(); w++) base = int64_t(uint64_t(base) + uint64_t(ctl.scan_tmp[w]));
+  base = int64_t(uint64_t(base) + uint64_t(incl) - uint64_t(sum));
+#pragma unroll
+  for (uint32_t i = 0; i < kPer; i++)
+    if (b + i < nv) vals[b + i] = int64_t(uint64_t(base) + uint64_t(loc[i]));
+  __syncthreads();
+  if (threadIdx.x == 0 && nv) s.dl_last = vals[nv - 1];
+  __syncthreads();
+}
+
 // ---- the no-NULL fast row pass --------------------------------------------------------------
 // Dictionary index of row r (== value r: the slab has no NULLs) of column c, straight from the
 // staged bytes through the run directory.  Control flow is warp uniform except the (rare) walk
@@ -313,6 +363,7 @@ __device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, const SmemLayou
     if (s.enc == DE_RLE_BOOL) return v & 1;
     return (in && want) ? load_u64_unaligned(arena + s.dict_off + uint64_t(v) * 8) : 0;
   }
+  if (s.enc == DE_DELTA) return (in && want) ? smem_at<uint64_t>(smem, L.idx[c])[r] : 0;
   return (in && want) ? load_u64_unaligned(arena + s.val_base + uint64_t(s.vals_done + r) * 8) : 0;
 }
 
@@ -342,7 +393,8 @@ __device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl&
       uint32_t k = s.vals_done + r;
       t = cmp_i64((int64_t)((a.arena[s.val_base + (k >> 3)] >> (k & 7)) & 1), lf.lit_i64, lf.cmp);
     } else {
-      uint64_t v = load_u64_unaligned(a.arena + s.val_base + uint64_t(s.vals_done + r) * 8);
+      uint64_t v = s.enc == DE_DELTA ? smem_at<uint64_t>(smem, L.idx[c])[r]
+                                     : load_u64_unaligned(a.arena + s.val_base + uint64_t(s.vals_done + r) * 8);
       t = kind == DK_F64 ? cmp_i64(f64_order_key(v), f64_order_key((uint64_t)lf.lit_i64), lf.cmp)
                          : cmp_i64((int64_t)v, lf.lit_i64, lf.cmp);
     }
@@ -463,7 +515,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
 // All threads call it; returns the rows of the slab (0: corrupt page).
 __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t ncols,
                                               uint32_t buf, uint32_t R, const StreamState& snap_def,
-                                              const StreamState& snap_val) {
+                                              const StreamState& snap_val, const DeltaState& snap_dl) {
   uint32_t mycol;
   const bool walker = walker_of(ncols, mycol);
   const uint32_t tid = threadIdx.x;
@@ -533,11 +585,12 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
       SlabCol& s = ctl.slab[mycol];
       uint32_t rc = R;
       s.nval = 0;
-      if (c.present && PQB_ENC_HAS_STREAM(c.enc) && s.nv > 0) {
+      if (c.present && PQB_ENC_HAS_WINDOW(c.enc) && s.nv > 0) {
         Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
-        DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[mycol]);
         uint32_t n = 0;
-        uint32_t got = walk_stream(c.val, w, s.nv, dir, n, kMaxDirEntries);
+        uint32_t got = c.enc == DE_DELTA
+                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
+                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries);
         s.nval = n;
         if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
           if (s.all_valid) rc = got;
@@ -560,7 +613,7 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
     uint32_t R2 = R;
     for (uint32_t c = 0; c < ncols; c++) R2 = ctl.rmin[c] < R2 ? ctl.rmin[c] : R2;
     if (R2 < R) {  // an index window / directory ran out: shrink and redo everything
-      if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; }
+      if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
       R = R2;
       __syncthreads();
       continue;
@@ -644,11 +697,13 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
 
       // ---- 2. fast walk: definition levels say "no NULLs" -> walk the index stream right away ----
       StreamState snap_def, snap_val;
+      DeltaState snap_dl;
       if (walker) {
         ColCursor& c = ctl.cur[mycol];
         SlabCol& s = ctl.slab[mycol];
         snap_def = c.def;
         snap_val = c.val;
+        snap_dl = c.dl;
         uint32_t rc = R0;
         s.ndef = 0;
         s.nval = 0;
@@ -667,11 +722,12 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             rc = got;
             if (!allv) ctl.any_nulls = 1;
           }
-          if (s.all_valid && rc == R0 && PQB_ENC_HAS_STREAM(c.enc)) {
+          if (s.all_valid && rc == R0 && PQB_ENC_HAS_WINDOW(c.enc)) {
             Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
-            DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[mycol]);
             uint32_t n = 0;
-            rc = walk_stream(c.val, w, R0, dir, n, kMaxDirEntries);
+            rc = c.enc == DE_DELTA
+                     ? walk_delta(c.dl, w, R0, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
+                     : walk_stream(c.val, w, R0, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries);
             s.nval = n;
           }
         }
@@ -680,9 +736,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       __syncthreads();
       uint32_t R = R0;
       if (ctl.rmin_all < R0 || ctl.any_nulls) {  // uniform: general path from the snapshots
-        if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; }
+        if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
         __syncthreads();
-        R = general_walk(ctl, L, smem, ncols, buf, R0, snap_def, snap_val);
+        R = general_walk(ctl, L, smem, ncols, buf, R0, snap_def, snap_val, snap_dl);
       }
       if (R == 0) {  // no progress possible: corrupt page
         if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
@@ -710,12 +766,15 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       if (ctl.error) break;
       if (tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
 
+      // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
+      for (uint32_t c = 0; c < ncols; c++)
+        if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
       const uint32_t nwords = (R + 31) >> 5;
       bool has_nulls = false;
       for (uint32_t c = 0; c < ncols; c++) has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
       uint32_t cnt = 0;
-      if (!has_nulls) {
-        // ---- 4-6 (fast): row-major pass, one warp per 32-row word ----
+      if (!has_nulls && plan.row_major) {
+        // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
         cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
       } else {
       // ---- 4. (general) unpack: fused index -> leaf bits where possible, else stage indices ----
@@ -727,20 +786,17 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
         const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
         const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
-        // leaves of this column that a dictionary LUT answers
-        int l0 = -1, l1 = -1, extra = 0;
-        if (s.enc == DE_DICT && s.all_valid) {
-          for (uint32_t l = 0; l < plan.nleaves; l++) {
-            const DevLeaf& lf = plan.leaves[l];
-            if (lf.col != c || (lf.kind != LK_CMP && lf.kind != LK_LIKE)) continue;
-            if (l0 < 0) l0 = int(l); else if (l1 < 0) l1 = int(l); else extra = 1;
-          }
-        }
-        if (l0 >= 0 && !extra) {
+        // leaves of this column that a dictionary LUT answers (host precomputed lists)
+        const uint32_t nlut = plan.col_nlut[c];
+        if (s.enc == DE_DICT && s.all_valid && nlut >= 1 && nlut <= 2) {
+          const int l0 = plan.col_l0[c], l1 = plan.col_l1[c];
           const uint8_t* lut0 = a.luts + plan.leaves[l0].lut_off + s.lut_base;
-          const uint8_t* lut1 = l1 >= 0 ? a.luts + plan.leaves[l1].lut_off + s.lut_base : nullptr;
-          dir_to_leafbits(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords, lut1,
-                          l1 >= 0 ? leafT + l1 * kLeafWords : nullptr, plan.cols[c].need_idx ? idx : nullptr);
+          uint32_t* i_st = plan.cols[c].need_idx ? idx : nullptr;
+          if (nlut == 2)
+            dir_to_leafbits<true>(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords,
+                                  a.luts + plan.leaves[l1].lut_off + s.lut_base, leafT + l1 * kLeafWords, i_st);
+          else
+            dir_to_leafbits<false>(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords, nullptr, nullptr, i_st);
         } else if (idx) {
           dir_to_idx(dir, s.nval, win, s.bw, idx);
         }
@@ -753,16 +809,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
         const SlabCol& s = ctl.slab[lf.col];
         if (!s.present) continue;                                 // all NULL: T stays 0
-        if (s.enc == DE_DICT && s.all_valid) {
-          // fused unless the column had more than two LUT leaves
-          int seen = 0;
-          for (uint32_t m = 0; m < l; m++)
-            seen += (plan.leaves[m].col == lf.col && (plan.leaves[m].kind == LK_CMP || plan.leaves[m].kind == LK_LIKE));
-          int total = seen;
-          for (uint32_t m = l; m < plan.nleaves; m++)
-            total += (plan.leaves[m].col == lf.col && (plan.leaves[m].kind == LK_CMP || plan.leaves[m].kind == LK_LIKE));
-          if (total <= 2) continue;
-        }
+        if (s.enc == DE_DICT && s.all_valid && plan.col_nlut[lf.col] <= 2) continue;  // answered by the fused pass
         const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
         const uint32_t* rk = smem_at<uint32_t>(smem, L.rank[lf.col]);
         const uint32_t* idx = smem_at<uint32_t>(smem, L.idx[lf.col]);

@@ -141,3 +141,59 @@ LIKE_CASES = [
 @pytest.mark.parametrize("s,p,kind,ci,want", LIKE_CASES)
 def test_like_match(dc, s, p, kind, ci, want):
     assert bool(dc.dc_like(s, len(s), p, len(p), kind, int(ci))) == want
+
+
+def _page_payloads(path, col):
+    """Raw data-page payloads of column `col` (row group 0) located with the library's own page walk."""
+    import ctypes as C
+    import json
+    from parseable_b200 import _lib as L
+    lib = L.load()
+    f = L.PqFile(path=path.encode())
+    n = lib.pq_file_describe(C.byref(f), None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.pq_file_describe(C.byref(f), buf, n + 1)
+    d = json.loads(buf.value.decode())
+    cc = d["row_groups"][0]["columns"][col]
+    off = cc["dictionary_page_offset"] if 0 < cc["dictionary_page_offset"] < cc["data_page_offset"] else cc["data_page_offset"]
+    raw = open(path, "rb").read()
+    out = []
+    for p in cc["pages"]:
+        start = off + p["header_len"]
+        if p["type"] in (0, 3):
+            out.append((raw[start:start + p["compressed_size"]], p["num_values"], p["encoding"]))
+        off = start + p["compressed_size"]
+    return out
+
+
+@pytest.mark.parametrize("kind", ["timestamps", "random_wide", "constant", "negative_steps"])
+def test_delta_binary_packed_pages_from_pyarrow(dc, built, tmp_path, kind):
+    """DELTA_BINARY_PACKED pages written by pyarrow (an independent encoder) decode to the source values
+    through walk_delta / bp_get64 with the kernel's slab and window geometry."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(11)
+    n = 50_000
+    if kind == "timestamps":
+        vals = (1_700_000_000_000 - np.cumsum(rng.integers(0, 3, n) * rng.integers(1, 50, n))).astype(np.int64)
+    elif kind == "random_wide":
+        vals = rng.integers(-2**62, 2**62, n, dtype=np.int64)
+    elif kind == "constant":
+        vals = np.full(n, 42, np.int64)
+    else:
+        vals = np.cumsum(rng.integers(-1000, 5, n)).astype(np.int64)
+    path = str(tmp_path / f"delta_{kind}.parquet")
+    t = pa.table({"v": pa.array(vals)}).cast(pa.schema([pa.field("v", pa.int64(), False)]))
+    pq.write_table(t, path, compression="NONE", use_dictionary=False, column_encoding={"v": "DELTA_BINARY_PACKED"},
+                   data_page_size=1 << 20, max_rows_per_page=20_000)
+    dc.dc_decode_delta.restype = C.c_int64
+    pos = 0
+    for payload, nv, enc in _page_payloads(path, 0):
+        assert enc == 5
+        out = np.zeros(nv, np.int64)
+        for cap in (8192 + 64, 640):                     # the kernel's window, and a tiny one that forces resumes
+            got = dc.dc_decode_delta(payload, C.c_uint64(len(payload)), nv, 2048, cap, 80, out.ctypes.data_as(C.c_void_p))
+            assert got == nv, (kind, cap, got)
+            assert np.array_equal(out, vals[pos:pos + nv]), (kind, cap)
+        pos += nv
+    assert pos == n

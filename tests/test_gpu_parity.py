@@ -332,3 +332,29 @@ def test_concurrent_queries_from_threads(env):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs
+
+
+@pytest.mark.parametrize("tag", ["nn", "nulls"])
+def test_delta_binary_packed_time_column(env, tag):
+    """p_timestamp is DELTA_BINARY_PACKED in every Parseable file (streams.rs:587-590).  A time range that
+    cuts THROUGH row groups cannot be decided by footer statistics: the column is decoded on the GPU
+    (miniblock unpack + block-wide prefix scan)."""
+    path, ora, prov = env[tag]
+    ts = ora.table["p_timestamp"].cast(pa.int64()).drop_null().to_numpy()
+    lo, hi = int(np.quantile(ts, 0.31)), int(np.quantile(ts, 0.78))
+    from parseable_b200.query import Timestamp
+    rng = [col("p_timestamp") >= Timestamp(lo), col("p_timestamp") < Timestamp(hi)]
+    got = prov.scan(filters=rng, count_only=True)
+    assert got.metrics["rows_selected"] == ora.count(rng)
+    flt = rng + [col("level") == "ERROR"]
+    res = prov.scan(filters=flt)
+    ids = np.concatenate([b.column(0).to_numpy() for b in res.batches]) if res.batches else np.array([], np.int64)
+    assert np.array_equal(ids, ora.row_ids(flt))
+    keys, aggs = ["level"], [count_star(), min_("p_timestamp"), max_("p_timestamp"), count("p_timestamp")]
+    assert_tables_equal(prov.aggregate(keys, aggs, rng).table(), ora.group_by(keys, aggs, rng), keys)
+    q = Query("SELECT COUNT(*) FROM t WHERE status = 200", TimeRange(lo, hi))
+    assert execute(q, prov).table()["count(*)"].to_pylist() == [ora.count(rng + [col("status") == 200])]
+    # equality / inequality on the raw values as well
+    probe = int(ts[len(ts) // 2])
+    for f in ([col("p_timestamp") == Timestamp(probe)], [col("p_timestamp") != Timestamp(probe)], [col("p_timestamp") > Timestamp(probe)]):
+        assert prov.scan(filters=f, count_only=True).metrics["rows_selected"] == ora.count(f)
