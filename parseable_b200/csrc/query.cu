@@ -417,6 +417,19 @@ void Query::run(const PqQueryDesc& d) {
     const char* rm = getenv("PQB_ROW_MAJOR");  // experiment switch: register-only row-major pass for no-NULL slabs
     plan.row_major = rm && rm[0] == '1';
   }
+  {
+    // conjunction of 1-4 CMP/LIKE leaves (folded TRUE constants are neutral): specialised row pass
+    bool conj = nleaves >= 1 && nleaves <= 4;
+    uint32_t leaves_seen = 0;
+    for (const DevPredOp& op : prog) {
+      if (op.kind == PK_LEAF) { leaves_seen++; conj &= plan.leaves[leaf_slot[op.arg]].kind == LK_CMP || plan.leaves[leaf_slot[op.arg]].kind == LK_LIKE; }
+      else if (op.kind == PK_AND) {}
+      else if (op.kind == PK_CONST && op.arg == 1) {}
+      else conj = false;
+    }
+    const char* fa = getenv("PQB_FAST_AND");
+    plan.fast_and = conj && leaves_seen == nleaves && !(fa && fa[0] == '0');
+  }
   plan.npred = uint32_t(prog.size());
   for (size_t i = 0; i < prog.size(); i++) {
     plan.pred[i] = prog[i];
@@ -590,6 +603,7 @@ void Query::run(const PqQueryDesc& d) {
   }
   L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
   L.sel = off; off += kSlabWords * 4;
+  L.lutc = off; if (plan.fast_and) off += nleaves * kLutCacheBytes;
   off = align_up(off, 128);
   L.acc = off;
   const uint32_t smem_fixed = off;

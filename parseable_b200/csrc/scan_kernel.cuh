@@ -47,9 +47,11 @@ struct SmemLayout {
   uint32_t leafT;             // uint32[nleaves][kSlabWords + 2]
   uint32_t sel;               // uint32[kSlabWords]
   uint32_t acc;               // shared accumulator table
+  uint32_t lutc;              // uint8[nleaves][kLutCacheBytes]: leaf LUTs of the current row group (fast AND path)
   uint32_t total;
 };
 constexpr int kLeafWords = kSlabWords + 2;
+constexpr int kLutCacheBytes = 2048;
 
 // per-column cursor over the pages of one column chunk
 struct ColCursor {
@@ -96,6 +98,7 @@ struct ScanCtl {
   int64_t scan_tmp[kScanWarps];             // DELTA prefix scan: per-warp totals
   uint32_t wcur[kScanWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
   uint32_t stk[kScanWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
+  uint32_t lut_smem[kMaxLeaves];            // fast AND path: leaf LUT of this item's row group is cached in smem
   ColCursor cur[kMaxCols];
   SlabCol slab[kMaxCols];
 };
@@ -510,6 +513,147 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
   return cnt;
 }
 
+// ---- specialised row pass: WHERE leaf AND leaf AND ... over dictionary pages, no NULLs ----------
+// The common log-analytics filter shape (level = 'ERROR' AND latency_ms > 100 AND ...).  Each warp
+// owns whole 32-row words; per leaf it keeps the current and the next run-directory entry in
+// registers (warp uniform), every lane unpacks its own row's index, probes the leaf's LUT, one
+// ballot makes the word, words are AND-ed in a register and the word is consumed at once.  No
+// leaf bitmaps, no atomics, no block barrier inside the slab.
+struct FastLeaf {
+  const DirEntry* dir;
+  const uint32_t* win;
+  const uint8_t* lut;   // bytes per dictionary entry: shared-memory copy when it fits, else global
+  uint32_t nent, bw;
+  uint32_t e;           // index of entry A
+  DirEntry A, B;        // A covers base_row, B is the next entry (start == ~0u: none)
+  uint32_t c_start;     // start of the entry after B (~0u: none)
+};
+
+__device__ __forceinline__ void fast_leaf_init(FastLeaf& f, const DirEntry* dir, uint32_t nent, const uint32_t* win,
+                                               uint32_t bw, const uint8_t* lut) {
+  f.dir = dir; f.nent = nent; f.win = win; f.bw = bw; f.lut = lut; f.e = 0;
+  f.A = dir[0];
+  if (nent > 1) f.B = dir[1]; else { f.B.start = 0xffffffffu; f.B.count = 0; f.B.kind = 0; f.B.chunk0 = 0; f.B.payload = 0; }
+  f.c_start = nent > 2 ? dir[2].start : 0xffffffffu;
+}
+
+// index of row r (r < R guaranteed by the caller for lanes with in == true)
+__device__ __forceinline__ uint32_t fast_leaf_idx(FastLeaf& f, uint32_t base_row, uint32_t r, bool in) {
+  while (f.B.start <= base_row) {  // warp uniform advance
+    f.e++;
+    f.A = f.B;
+    if (f.e + 1 < f.nent) f.B = f.dir[f.e + 1]; else f.B.start = 0xffffffffu;
+    f.c_start = f.e + 2 < f.nent ? f.dir[f.e + 2].start : 0xffffffffu;
+  }
+  uint32_t start, kind, payload;
+  if (base_row + 31 >= f.c_start) {
+    // three or more entries inside one word (very short runs): per-lane search
+    uint32_t e = f.e;
+    if (in) while (e + 1 < f.nent && f.dir[e + 1].start <= r) e++;
+    const DirEntry d = f.dir[e];
+    start = d.start; kind = d.kind; payload = d.payload;
+  } else {
+    const bool useB = r >= f.B.start;
+    start = useB ? f.B.start : f.A.start;
+    kind = useB ? f.B.kind : f.A.kind;
+    payload = useB ? f.B.payload : f.A.payload;
+  }
+  if (!in) return 0;
+  return kind ? bp_get(f.win, payload, f.bw, r - start) : payload;
+}
+
+template <int NL>
+__device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                                  const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
+                                                  uint32_t r_item, unsigned long long* acc, bool agg_mode) {
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const uint32_t nwords = (R + 31) >> 5;
+  const uint32_t nslots = plan.nslots;
+  FastLeaf fl[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    const DevLeaf& lf = plan.leaves[l];
+    const SlabCol& s = ctl.slab[lf.col];
+    const uint8_t* lut = ctl.lut_smem[l] ? smem + L.lutc + l * kLutCacheBytes : a.luts + lf.lut_off + s.lut_base;
+    fast_leaf_init(fl[l], smem_at<DirEntry>(smem, L.valdir[lf.col]), s.nval, smem_at<uint32_t>(smem, L.valwin[lf.col][buf]),
+                   s.bw, lut);
+  }
+  if (agg_mode) {
+    if (lane < plan.ncols) ctl.wcur[warp][lane] = 0;
+    __syncwarp();
+  }
+  uint32_t cnt = 0;
+  for (uint32_t w = warp; w < nwords; w += kScanWarps) {
+    const uint32_t base_row = w * 32, r = base_row + lane;
+    const bool in = r < R;
+    uint32_t sel = row_mask(w, R);
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const uint32_t v = fast_leaf_idx(fl[l], base_row, r, in);
+      sel &= __ballot_sync(0xffffffffu, in && fl[l].lut[v]);
+      if (sel == 0) break;  // warp uniform: nothing left to select in this word
+    }
+    if (!agg_mode) {
+      if (lane == 0 && sel) {
+        cnt += __popc(sel);
+        if (plan.write_bitmap) {
+          uint32_t pos = r_item + base_row;
+          uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+          uint32_t sh = pos & 31;
+          if (sh == 0) *dst = sel;
+          else {
+            atomicOr(dst, sel << sh);
+            uint32_t hi = sel >> (32 - sh);
+            if (hi) atomicOr(dst + 1, hi);
+          }
+        }
+      }
+      continue;
+    }
+    if (sel == 0) continue;
+    const bool mine = (sel >> lane) & 1;
+    if (lane == 0) cnt += __popc(sel);
+    uint32_t slot = 0;
+    for (uint32_t k = 0; k < plan.nkeys; k++) {
+      const DevKey& key = plan.keys[k];
+      const SlabCol& s = ctl.slab[key.col];
+      uint32_t gid = key.card;
+      if (s.present) {
+        if (key.kind == KK_BOOL) {
+          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+          if (!PQB_ENC_HAS_STREAM(s.enc)) {
+            uint32_t kk = s.vals_done + r;
+            gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
+          }
+        } else {
+          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
+          gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
+        }
+      }
+      slot += gid * key.stride;
+    }
+    if (mine) atomicAdd(&acc[slot], 1ull);
+    for (uint32_t g = 0; g < plan.naggs; g++) {
+      const DevAgg& ag = plan.aggs[g];
+      if (ag.fn == AG_COUNT_STAR) continue;
+      const SlabCol& s = ctl.slab[ag.col];
+      if (!s.present) continue;
+      uint64_t bits;
+      if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
+        uint32_t kk = s.vals_done + r;
+        bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
+      } else {
+        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+      }
+      if (!mine) continue;
+      if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+      if (ag.fn == AG_COUNT) continue;
+      acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
+    }
+  }
+  return cnt;
+}
+
 // The general per-slab walk (columns with NULLs, window / directory overflow): definition levels ->
 // validity bitmap + ranks -> index streams, shrinking the slab until every column is covered.
 // All threads call it; returns the rows of the slab (0: corrupt page).
@@ -681,6 +825,20 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
     }
     if (tid == 0) ctl.sel_count = 0;
+    if (plan.fast_and) {
+      // cache this row group's leaf LUTs (one byte per dictionary entry) in shared memory
+      for (uint32_t l = 0; l < plan.nleaves; l++) {
+        const DevLeaf& lf = plan.leaves[l];
+        const DevChunk ch = a.chunks[item.rg * ncols + lf.col];
+        const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
+        if (tid == 0) ctl.lut_smem[l] = fits;
+        if (fits) {
+          const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
+          uint8_t* dst = smem + L.lutc + l * kLutCacheBytes;
+          for (uint32_t i = tid; i < ch.dict_n; i += kScanThreads) dst[i] = src[i];
+        }
+      }
+    }
     __syncthreads();
 
     uint32_t rows_left = item.nrows;
@@ -773,7 +931,21 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       bool has_nulls = false;
       for (uint32_t c = 0; c < ncols; c++) has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
       uint32_t cnt = 0;
-      if (!has_nulls && plan.row_major) {
+      bool fast_and = plan.fast_and && !has_nulls;
+      if (fast_and)
+        for (uint32_t l = 0; l < plan.nleaves; l++) {
+          const SlabCol& s = ctl.slab[plan.leaves[l].col];
+          fast_and &= s.present && s.enc == DE_DICT && s.nval > 0;
+        }
+      if (fast_and) {
+        // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
+        switch (plan.nleaves) {
+          case 1: cnt = fast_and_rows<1>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
+          case 2: cnt = fast_and_rows<2>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
+          case 3: cnt = fast_and_rows<3>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
+          default: cnt = fast_and_rows<4>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
+        }
+      } else if (!has_nulls && plan.row_major) {
         // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
         cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
       } else {
