@@ -86,6 +86,8 @@ struct SlabCol {
   int64_t dl_last;          // DELTA pages: value of the last row decoded so far in this page
 };
 
+enum SlabMode : uint32_t { MODE_GENERIC = 0, MODE_FAST_AND = 1, MODE_ROW_MAJOR = 2, MODE_GENERAL_WALK = 3 };
+
 struct ScanCtl {
   uint64_t mbar[2];
   uint32_t item;
@@ -94,6 +96,9 @@ struct ScanCtl {
   uint32_t rmin_all;     // min over columns of the rows the fast walk covered
   uint32_t any_nulls;    // some column of this slab has a NULL (general path)
   uint32_t target;       // rows the next slab should try to take
+  uint32_t mode;         // row pass chosen by the control warp for the current slab
+  uint32_t R;            // rows of the current slab
+  uint32_t has_delta;    // some column of this slab is DELTA_BINARY_PACKED
   uint32_t rmin[kMaxCols];
   int64_t scan_tmp[kScanWarps];             // DELTA prefix scan: per-warp totals
   uint32_t wcur[kScanWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
@@ -288,12 +293,11 @@ __device__ __forceinline__ uint32_t row_mask(uint32_t w, uint32_t R) {
   return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
 }
 
-// which thread walks column c: lane (c / warps) of warp (c % warps), so walkers of up to
-// kScanWarps columns sit on different warps and do not serialise each other
+// which thread walks column c: lane c of warp 0, the control warp.  All per-slab control lives on
+// that one warp so the other warps park at the block barrier instead of burning issue slots.
 __device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
-  uint32_t l = lane_id();
-  col = l * kScanWarps + warp_id();
-  return l < 2 && col < ncols;
+  col = lane_id();
+  return warp_id() == 0 && col < ncols;
 }
 
 
@@ -848,95 +852,147 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     __syncthreads();
 
     while (rows_left > 0) {
-      // ---- 1. wait for this slab's staged bytes ----
-      mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
-      phases ^= 1u << buf;
-      const uint32_t R0 = ctl.target;
-
-      // ---- 2. fast walk: definition levels say "no NULLs" -> walk the index stream right away ----
+      // ---- 1-3. control, WARP 0 ONLY (the other warps park at the barrier and spend no issue
+      //      slots): wait for the staged bytes, walk the run headers (one lane per column),
+      //      commit the cursors, prefetch the next slab, choose the row pass ----
       StreamState snap_def, snap_val;
       DeltaState snap_dl;
-      if (walker) {
-        ColCursor& c = ctl.cur[mycol];
-        SlabCol& s = ctl.slab[mycol];
-        snap_def = c.def;
-        snap_val = c.val;
-        snap_dl = c.dl;
-        uint32_t rc = R0;
-        s.ndef = 0;
-        s.nval = 0;
-        s.all_valid = 1;
-        s.nv = c.present ? R0 : 0;
-        if (c.present) {
-          if (c.has_def) {
-            Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
-            DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
-            uint32_t n = 0;
-            uint32_t got = walk_stream(c.def, w, R0, dir, n, kMaxDirEntries);
-            s.ndef = n;
-            uint32_t allv = 1;
-            for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
-            s.all_valid = allv;
-            rc = got;
-            if (!allv) ctl.any_nulls = 1;
+      if (warp_id() == 0) {
+        if (lane_id() == 0) mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
+        __syncwarp();
+        const uint32_t R0w = ctl.target;
+        if (walker) {
+          ColCursor& c = ctl.cur[mycol];
+          SlabCol& s = ctl.slab[mycol];
+          snap_def = c.def;
+          snap_val = c.val;
+          snap_dl = c.dl;
+          uint32_t rc = R0w;
+          s.ndef = 0;
+          s.nval = 0;
+          s.all_valid = 1;
+          s.nv = c.present ? R0w : 0;
+          if (c.present) {
+            if (c.has_def) {
+              Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
+              DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
+              uint32_t n = 0;
+              uint32_t got = walk_stream(c.def, w, R0w, dir, n, kMaxDirEntries);
+              s.ndef = n;
+              uint32_t allv = 1;
+              for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
+              s.all_valid = allv;
+              rc = got;
+              if (!allv) ctl.any_nulls = 1;
+            }
+            if (s.all_valid && rc == R0w && PQB_ENC_HAS_WINDOW(c.enc)) {
+              Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
+              uint32_t n = 0;
+              rc = c.enc == DE_DELTA
+                       ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
+                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries);
+              s.nval = n;
+            }
           }
-          if (s.all_valid && rc == R0 && PQB_ENC_HAS_WINDOW(c.enc)) {
-            Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
-            uint32_t n = 0;
-            rc = c.enc == DE_DELTA
-                     ? walk_delta(c.dl, w, R0, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                     : walk_stream(c.val, w, R0, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries);
-            s.nval = n;
-          }
+          if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
         }
-        if (rc < R0) atomicMin(&ctl.rmin_all, rc);
+        __syncwarp();
+        const bool general = ctl.rmin_all < R0w || ctl.any_nulls;
+        if (!general) {
+          if (walker) {  // freeze this slab's view, advance the cursor
+            ColCursor& c = ctl.cur[mycol];
+            SlabCol& s = ctl.slab[mycol];
+            s.val_base = c.val_base;
+            s.vals_done = c.vals_done;
+            s.enc = c.enc;
+            s.bw = c.val.bw;
+            if (c.present) {
+              c.vals_done += s.nv;
+              c.page_rows_left -= R0w;
+              if (c.page_rows_left == 0 && rows_left > R0w) {
+                if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+                else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane_id() == 0) {
+            uint32_t mode = MODE_GENERIC, has_delta = 0;
+            bool fa = plan.fast_and != 0;
+            for (uint32_t c = 0; c < ncols; c++) has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
+            for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+              const SlabCol& s = ctl.slab[plan.leaves[l].col];
+              fa = s.present && s.enc == DE_DICT && s.nval > 0;
+            }
+            if (fa) mode = MODE_FAST_AND;
+            else if (plan.row_major) mode = MODE_ROW_MAJOR;
+            ctl.mode = mode;
+            ctl.has_delta = has_delta;
+            ctl.R = R0w;
+            if (!ctl.error && rows_left > R0w) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R0w);
+          }
+        } else if (lane_id() == 0) {
+          ctl.mode = MODE_GENERAL_WALK;
+          ctl.R = R0w;
+        }
       }
+      phases ^= 1u << buf;
       __syncthreads();
-      uint32_t R = R0;
-      if (ctl.rmin_all < R0 || ctl.any_nulls) {  // uniform: general path from the snapshots
+      uint32_t mode = ctl.mode;
+      uint32_t R = ctl.R;
+      bool has_nulls = false;
+      uint32_t has_delta = ctl.has_delta;
+      if (mode == MODE_GENERAL_WALK) {  // uniform: NULLs or an exhausted window -> the general walk, all threads
         if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
         __syncthreads();
-        R = general_walk(ctl, L, smem, ncols, buf, R0, snap_def, snap_val, snap_dl);
-      }
-      if (R == 0) {  // no progress possible: corrupt page
-        if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
-        break;
-      }
-
-      // ---- 3. freeze this slab's view, advance cursors, prefetch the next slab ----
-      if (walker) {
-        ColCursor& c = ctl.cur[mycol];
-        SlabCol& s = ctl.slab[mycol];
-        s.val_base = c.val_base;
-        s.vals_done = c.vals_done;
-        s.enc = c.enc;
-        s.bw = c.val.bw;
-        if (c.present) {
-          c.vals_done += s.nv;
-          c.page_rows_left -= R;
-          if (c.page_rows_left == 0 && rows_left > R) {
-            if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
-            else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+        R = general_walk(ctl, L, smem, ncols, buf, R, snap_def, snap_val, snap_dl);
+        if (R == 0) {  // no progress possible: corrupt page
+          if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
+          break;
+        }
+        if (walker) {
+          ColCursor& c = ctl.cur[mycol];
+          SlabCol& s = ctl.slab[mycol];
+          s.val_base = c.val_base;
+          s.vals_done = c.vals_done;
+          s.enc = c.enc;
+          s.bw = c.val.bw;
+          if (c.present) {
+            c.vals_done += s.nv;
+            c.page_rows_left -= R;
+            if (c.page_rows_left == 0 && rows_left > R) {
+              if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+              else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+            }
           }
         }
+        __syncthreads();
+        if (!ctl.error && tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
+        has_delta = 0;
+        for (uint32_t c = 0; c < ncols; c++) {
+          has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
+          has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
+        }
+        mode = MODE_GENERIC;
+        if (!has_nulls) {
+          bool fa = plan.fast_and != 0;
+          for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+            const SlabCol& s = ctl.slab[plan.leaves[l].col];
+            fa = s.present && s.enc == DE_DICT && s.nval > 0;
+          }
+          if (fa) mode = MODE_FAST_AND;
+          else if (plan.row_major) mode = MODE_ROW_MAJOR;
+        }
       }
-      __syncthreads();
       if (ctl.error) break;
-      if (tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
 
       // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
-      for (uint32_t c = 0; c < ncols; c++)
-        if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
+      if (has_delta)
+        for (uint32_t c = 0; c < ncols; c++)
+          if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
       const uint32_t nwords = (R + 31) >> 5;
-      bool has_nulls = false;
-      for (uint32_t c = 0; c < ncols; c++) has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
       uint32_t cnt = 0;
-      bool fast_and = plan.fast_and && !has_nulls;
-      if (fast_and)
-        for (uint32_t l = 0; l < plan.nleaves; l++) {
-          const SlabCol& s = ctl.slab[plan.leaves[l].col];
-          fast_and &= s.present && s.enc == DE_DICT && s.nval > 0;
-        }
+      const bool fast_and = mode == MODE_FAST_AND;
       if (fast_and) {
         // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
         switch (plan.nleaves) {
@@ -945,7 +1001,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           case 3: cnt = fast_and_rows<3>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
           default: cnt = fast_and_rows<4>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
         }
-      } else if (!has_nulls && plan.row_major) {
+      } else if (mode == MODE_ROW_MAJOR) {
         // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
         cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
       } else {

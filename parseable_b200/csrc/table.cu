@@ -183,8 +183,9 @@ std::string describe_file(const PqFile& f) {
 
 // ---------------- Table ----------------
 Table::~Table() {
-  if (d_arena) cudaFree(d_arena);
-  if (d_pages) cudaFree(d_pages);
+  // stream-ordered frees into the pool: a per-query table costs no device-wide synchronisation
+  if (d_arena) cudaFreeAsync(d_arena, cudaStreamPerThread);
+  if (d_pages) cudaFreeAsync(d_pages, cudaStreamPerThread);
 }
 
 int Table::find_column(const std::string& name) const {
@@ -216,7 +217,27 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   Context& ctx = Context::get();
   if (shard_count == 0) shard_count = 1;
   if (shard_index >= shard_count) throw Error(PQ_ERR_INVALID_ARG, "shard_index >= shard_count");
-  for (uint32_t i = 0; i < n_files; i++) files.push_back(open_host_file(in_files[i]));
+  // footers are parsed on a few host threads (one Parquet file per ingest minute: many small footers)
+  files.resize(n_files);
+  {
+    const unsigned nthr = std::min<unsigned>({8u, std::max(1u, std::thread::hardware_concurrency()), n_files});
+    std::atomic<uint32_t> next{0};
+    std::vector<std::exception_ptr> errs(n_files);
+    auto work = [&]() {
+      for (;;) {
+        uint32_t i = next.fetch_add(1);
+        if (i >= n_files) break;
+        try { files[i] = open_host_file(in_files[i]); } catch (...) { errs[i] = std::current_exception(); }
+      }
+    };
+    if (nthr <= 1) work();
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nthr; t++) th.emplace_back(work);
+      for (auto& t : th) t.join();
+    }
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+  }
 
   // ---- resolve columns by NAME in every file (streams.rs:1024-1037: table schema is
   // sorted by name, files keep write order) ----
@@ -225,6 +246,106 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     columns[c].name = col_names[c];
     columns[c].kind = 0xff;
   }
+  // page-header walk of one column chunk -> DevPage records (runs on worker threads, after the
+  // H2D copies were queued, so host parsing overlaps the PCIe transfer)
+  struct WalkJob { uint32_t rg; uint32_t col; uint32_t file; };
+  std::vector<WalkJob> jobs;
+  auto walk_chunk = [](TableChunk& tc, const HostFile& hf, const std::string& colname, uint32_t rg_rows,
+                       std::vector<DevPage>& out) {
+    const ColumnChunkMeta& cm = *tc.meta;
+    const LeafColumn& leaf = hf.meta.leaves[tc.leaf];
+        std::vector<PageInfo> pis;
+        try {
+          pis = walk_pages(hf.data + tc.file_off, tc.bytes, cm.num_values);
+        } catch (const std::exception& e) {
+          throw Error(PQ_ERR_CORRUPT, colname + ": " + e.what());
+        }
+        
+        uint32_t first_row = 0;
+        const uint8_t max_def = uint8_t(leaf.max_def);
+        for (const PageInfo& pi : pis) {
+          const uint8_t* payload = hf.data + tc.file_off + pi.offset_in_chunk + pi.header_len;
+          uint64_t payload_arena = tc.arena_off + pi.offset_in_chunk + pi.header_len;
+          if (pi.type == PAGE_DICTIONARY) {
+            if (pi.encoding != ENC_PLAIN && pi.encoding != ENC_PLAIN_DICTIONARY)
+              throw Error(PQ_ERR_UNSUPPORTED, "dictionary page encoding " + std::to_string(pi.encoding));
+            tc.dict_off = payload_arena;
+            tc.dict_len = pi.compressed_size;
+            tc.dict_n = pi.num_values;
+            continue;
+          }
+          if (pi.type != PAGE_DATA && pi.type != PAGE_DATA_V2) continue;
+          DevPage dp{};
+          dp.off = payload_arena;
+          dp.len = pi.compressed_size;
+          dp.num_rows = pi.num_values;
+          dp.first_row = first_row;
+          first_row += pi.num_values;
+          uint32_t pos = 0;
+          if (pi.type == PAGE_DATA) {
+            if (max_def > 0) {
+              if (pi.def_encoding != ENC_RLE) throw Error(PQ_ERR_UNSUPPORTED, "definition levels not RLE encoded");
+              if (pi.compressed_size < 4) throw Error(PQ_ERR_CORRUPT, "data page too short");
+              uint32_t dl = rd_u32(payload);
+              if (uint64_t(dl) + 4 > pi.compressed_size) throw Error(PQ_ERR_CORRUPT, "definition levels run past the page");
+              dp.def_off = 4;
+              dp.def_len = dl;
+              pos = 4 + dl;
+            }
+          } else {
+            if (pi.v2_compressed && cm.codec != CODEC_UNCOMPRESSED) throw Error(PQ_ERR_UNSUPPORTED, "compressed v2 page");
+            pos = pi.v2_rep_len;
+            if (max_def > 0) { dp.def_off = pos; dp.def_len = pi.v2_def_len; }
+            pos += pi.v2_def_len;
+          }
+          dp.val_off = pos;
+          switch (pi.encoding) {
+            case ENC_PLAIN:
+              dp.enc = DE_PLAIN;
+              tc.has_plain_pages = true;
+              break;
+            case ENC_RLE_DICTIONARY:
+            case ENC_PLAIN_DICTIONARY:
+              dp.enc = DE_DICT;
+              if (pos >= pi.compressed_size && pi.num_values > 0) {
+                // an all-null page may legally carry no index bytes
+                dp.bit_width = 0;
+              } else if (pi.num_values > 0) {
+                dp.bit_width = payload[pos];
+                dp.val_off = pos + 1;
+              }
+              if (dp.bit_width > 32) throw Error(PQ_ERR_CORRUPT, "dictionary index bit width > 32");
+              tc.has_dict_pages = true;
+              tc.max_bw = std::max<uint32_t>(tc.max_bw, dp.bit_width);
+              break;
+            case ENC_RLE:
+              // booleans in v2 data pages: 4-byte length + RLE / bit-packed hybrid, bit width 1
+              if (leaf.phys_type != PT_BOOLEAN)
+                throw Error(PQ_ERR_UNSUPPORTED, "RLE value encoding on a non-boolean column");
+              dp.enc = DE_RLE_BOOL;
+              dp.bit_width = 1;
+              if (pi.num_values > 0 && pos + 4 <= pi.compressed_size) dp.val_off = pos + 4;
+              tc.has_dict_pages = true;  // needs an index window + staging like a dictionary page
+              tc.max_bw = std::max<uint32_t>(tc.max_bw, 1);
+              break;
+            case ENC_DELTA_BINARY_PACKED:
+              dp.enc = DE_DELTA;
+              tc.has_delta_pages = true;
+              break;
+            default:
+              throw Error(PQ_ERR_UNSUPPORTED, "column '" + colname + "': page encoding " + std::to_string(pi.encoding) + " not supported");
+          }
+          out.push_back(dp);
+        }
+        
+        if (first_row != rg_rows)
+          throw Error(PQ_ERR_CORRUPT, colname + ": page rows do not add up to the row group's");
+        if (tc.has_dict_pages && leaf.phys_type != PT_BOOLEAN && tc.dict_n == 0 && cm.num_values > 0 &&
+            (cm.stats.null_count < 0 || cm.stats.null_count < cm.num_values)) {
+          // dictionary-encoded pages without a dictionary page
+          throw Error(PQ_ERR_CORRUPT, colname + ": dictionary-encoded pages but no dictionary page");
+        }
+  };
   struct Copy { uint32_t file; uint64_t src_off; uint64_t dst_off; uint64_t bytes; };
   std::vector<Copy> copies;
   uint64_t arena = 0;
@@ -288,98 +409,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         arena = (arena + tc.bytes + 64 + 255) & ~255ull;
         copies.push_back({fi, tc.file_off, tc.arena_off, tc.bytes});
         chunk_bytes += tc.bytes;
-        // ---- page walk ----
-        std::vector<PageInfo> pis;
-        try {
-          pis = walk_pages(hf.data + tc.file_off, tc.bytes, cm.num_values);
-        } catch (const std::exception& e) {
-          throw Error(PQ_ERR_CORRUPT, col_names[c] + ": " + e.what());
-        }
-        tc.pages.first_page = uint32_t(pages.size());
-        uint32_t first_row = 0;
-        const uint8_t max_def = uint8_t(hf.meta.leaves[leaf_of[c]].max_def);
-        for (const PageInfo& pi : pis) {
-          const uint8_t* payload = hf.data + tc.file_off + pi.offset_in_chunk + pi.header_len;
-          uint64_t payload_arena = tc.arena_off + pi.offset_in_chunk + pi.header_len;
-          if (pi.type == PAGE_DICTIONARY) {
-            if (pi.encoding != ENC_PLAIN && pi.encoding != ENC_PLAIN_DICTIONARY)
-              throw Error(PQ_ERR_UNSUPPORTED, "dictionary page encoding " + std::to_string(pi.encoding));
-            tc.dict_off = payload_arena;
-            tc.dict_len = pi.compressed_size;
-            tc.dict_n = pi.num_values;
-            continue;
-          }
-          if (pi.type != PAGE_DATA && pi.type != PAGE_DATA_V2) continue;
-          DevPage dp{};
-          dp.off = payload_arena;
-          dp.len = pi.compressed_size;
-          dp.num_rows = pi.num_values;
-          dp.first_row = first_row;
-          first_row += pi.num_values;
-          uint32_t pos = 0;
-          if (pi.type == PAGE_DATA) {
-            if (max_def > 0) {
-              if (pi.def_encoding != ENC_RLE) throw Error(PQ_ERR_UNSUPPORTED, "definition levels not RLE encoded");
-              if (pi.compressed_size < 4) throw Error(PQ_ERR_CORRUPT, "data page too short");
-              uint32_t dl = rd_u32(payload);
-              if (uint64_t(dl) + 4 > pi.compressed_size) throw Error(PQ_ERR_CORRUPT, "definition levels run past the page");
-              dp.def_off = 4;
-              dp.def_len = dl;
-              pos = 4 + dl;
-            }
-          } else {
-            if (pi.v2_compressed && cm.codec != CODEC_UNCOMPRESSED) throw Error(PQ_ERR_UNSUPPORTED, "compressed v2 page");
-            pos = pi.v2_rep_len;
-            if (max_def > 0) { dp.def_off = pos; dp.def_len = pi.v2_def_len; }
-            pos += pi.v2_def_len;
-          }
-          dp.val_off = pos;
-          switch (pi.encoding) {
-            case ENC_PLAIN:
-              dp.enc = DE_PLAIN;
-              tc.has_plain_pages = true;
-              break;
-            case ENC_RLE_DICTIONARY:
-            case ENC_PLAIN_DICTIONARY:
-              dp.enc = DE_DICT;
-              if (pos >= pi.compressed_size && pi.num_values > 0) {
-                // an all-null page may legally carry no index bytes
-                dp.bit_width = 0;
-              } else if (pi.num_values > 0) {
-                dp.bit_width = payload[pos];
-                dp.val_off = pos + 1;
-              }
-              if (dp.bit_width > 32) throw Error(PQ_ERR_CORRUPT, "dictionary index bit width > 32");
-              tc.has_dict_pages = true;
-              tc.max_bw = std::max<uint32_t>(tc.max_bw, dp.bit_width);
-              break;
-            case ENC_RLE:
-              // booleans in v2 data pages: 4-byte length + RLE / bit-packed hybrid, bit width 1
-              if (hf.meta.leaves[leaf_of[c]].phys_type != PT_BOOLEAN)
-                throw Error(PQ_ERR_UNSUPPORTED, "RLE value encoding on a non-boolean column");
-              dp.enc = DE_RLE_BOOL;
-              dp.bit_width = 1;
-              if (pi.num_values > 0 && pos + 4 <= pi.compressed_size) dp.val_off = pos + 4;
-              tc.has_dict_pages = true;  // needs an index window + staging like a dictionary page
-              tc.max_bw = std::max<uint32_t>(tc.max_bw, 1);
-              break;
-            case ENC_DELTA_BINARY_PACKED:
-              dp.enc = DE_DELTA;
-              tc.has_delta_pages = true;
-              break;
-            default:
-              throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page encoding " + std::to_string(pi.encoding) + " not supported");
-          }
-          pages.push_back(dp);
-        }
-        tc.pages.n_pages = uint32_t(pages.size()) - tc.pages.first_page;
-        if (first_row != trg.num_rows)
-          throw Error(PQ_ERR_CORRUPT, col_names[c] + ": page rows do not add up to the row group's");
-        if (tc.has_dict_pages && hf.meta.leaves[leaf_of[c]].phys_type != PT_BOOLEAN && tc.dict_n == 0 && cm.num_values > 0 &&
-            (cm.stats.null_count < 0 || cm.stats.null_count < cm.num_values)) {
-          // dictionary-encoded pages without a dictionary page
-          throw Error(PQ_ERR_CORRUPT, col_names[c] + ": dictionary-encoded pages but no dictionary page");
-        }
+        jobs.push_back({uint32_t(row_groups.size()), uint32_t(c), fi});
       }
       total_rows += trg.num_rows;
       row_groups.push_back(std::move(trg));
@@ -390,7 +420,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
 
   // ---- one HBM arena, 64 KiB of slack so staged windows may over-read ----
   arena_bytes = arena + (64u << 10);
-  PQB_CUDA(cudaMalloc((void**)&d_arena, arena_bytes));
+  PQB_CUDA(cudaMallocAsync((void**)&d_arena, arena_bytes, stream));
   // tail slack must be defined (walkers may look at it)
   PQB_CUDA(cudaMemsetAsync(d_arena + arena, 0, arena_bytes - arena, stream));
 
@@ -468,8 +498,41 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       cudaEventDestroy(ring_ev[r]);
     }
   }
+  // ---- page walks, in parallel, while the copies above are in flight ----
+  {
+    std::vector<std::vector<DevPage>> out(jobs.size());
+    std::vector<std::exception_ptr> errs(jobs.size());
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        size_t j = next.fetch_add(1);
+        if (j >= jobs.size()) break;
+        const WalkJob& jb = jobs[j];
+        try {
+          walk_chunk(row_groups[jb.rg].chunks[jb.col], *files[jb.file], col_names[jb.col], row_groups[jb.rg].num_rows, out[j]);
+        } catch (...) { errs[j] = std::current_exception(); }
+      }
+    };
+    const unsigned nthr = unsigned(std::min<size_t>({size_t(8), size_t(std::max(1u, std::thread::hardware_concurrency())), jobs.size() / 64 + 1}));
+    if (nthr <= 1) work();
+    else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nthr; t++) th.emplace_back(work);
+      for (auto& t : th) t.join();
+    }
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+    size_t total = 0;
+    for (auto& v : out) total += v.size();
+    pages.reserve(total);
+    for (size_t j = 0; j < jobs.size(); j++) {
+      TableChunk& tc = row_groups[jobs[j].rg].chunks[jobs[j].col];
+      tc.pages.first_page = uint32_t(pages.size());
+      tc.pages.n_pages = uint32_t(out[j].size());
+      pages.insert(pages.end(), out[j].begin(), out[j].end());
+    }
+  }
   if (!pages.empty()) {
-    PQB_CUDA(cudaMalloc((void**)&d_pages, pages.size() * sizeof(DevPage)));
+    PQB_CUDA(cudaMallocAsync((void**)&d_pages, pages.size() * sizeof(DevPage), stream));
     PQB_CUDA(cudaMemcpyAsync(d_pages, pages.data(), pages.size() * sizeof(DevPage), cudaMemcpyHostToDevice, stream));
   }
   PQB_CUDA(cudaStreamSynchronize(stream));
