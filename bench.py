@@ -276,6 +276,7 @@ def main():
     launches = 0
     scan_ms = []
     dev_ms = []
+    host_ms = []
     algo_bytes = r.metrics["algorithmic_bytes"]
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -283,6 +284,7 @@ def main():
         launches += r.metrics["kernel_launches"]
         scan_ms.append(r.metrics["scan_kernel_ms"])
         dev_ms.append(r.metrics["device_ms"])
+        host_ms.append(r.metrics["host_ms"])
     barrier()
     dt = time.perf_counter() - t0
     clk = clocks.stop()
@@ -294,6 +296,10 @@ def main():
     dt = float(t_local.item())
     ms_per_step = 1000.0 * dt / args.steps
     value = rows_per_step * world / (dt / args.steps)
+    if rank == 0:
+        print(f"[bench] resident step: wall {ms_per_step:.3f} ms = pq_query_open {sum(host_ms)/len(host_ms):.3f} ms "
+              f"(device {sum(dev_ms)/len(dev_ms):.3f} ms, k_scan {sum(scan_ms)/len(scan_ms):.3f} ms) + binding/Arrow import",
+              file=sys.stderr)
 
     # ---- e2e: host buffers (page-locked file images), H2D + D2H inside every step ----
     e2e = None
@@ -315,6 +321,10 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dte = float(te.item())
         assert sum(b.num_rows for b in re_.batches) == sel_expected
+        if rank == 0:
+            print(f"[bench] e2e step: wall {1000.0*dte/k:.3f} ms = pq_query_open {re_.metrics['host_ms']:.3f} ms "
+                  f"(footers+page walk+H2D {re_.metrics['upload_ms']:.3f} ms, device {re_.metrics['device_ms']:.3f} ms) + binding",
+                  file=sys.stderr)
         e2e = {"value": rows_per_step * world / (dte / k), "unit": "rows/s", "h2d_bytes_per_step": re_.metrics["h2d_bytes"],
                "d2h_bytes_per_step": re_.metrics["d2h_bytes"], "ms_per_step": 1000.0 * dte / k, "steps": k}
         for h in hfs:

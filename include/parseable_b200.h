@@ -203,6 +203,8 @@ typedef struct {
   double device_ms;         /* CUDA-event time of the device work of this query */
   double scan_kernel_ms;    /* CUDA-event time of the fused scan kernel alone */
   uint64_t groups;          /* output groups (aggregate queries) */
+  double host_ms;           /* wall time of pq_query_open (planning + uploads + device work + result copy) */
+  double upload_ms;         /* of which: footer parse, page walk and H2D of the column chunks (file-list queries) */
 } PqMetrics;
 
 /* ---- lifecycle ---- */

@@ -29,6 +29,7 @@ void release_schema(ArrowSchema* s) {
 }
 
 struct ArrayPriv {
+  std::shared_ptr<PinnedBlock> keep;
   std::vector<std::vector<uint8_t>> owned;
   std::vector<const void*> buffers;
   std::vector<ArrowArray> children;
@@ -100,10 +101,17 @@ void export_batch(const OutBatch& b, ArrowArray* out, ArrowSchema* schema) {
       else { offs.assign(4, 0); }
       p->owned.push_back(std::move(offs));
     }
-    p->owned.push_back(c.values);
-    if (p->owned.back().empty()) p->owned.back().assign(8, 0);  // never hand out a NULL data pointer
-    for (size_t k = 0; k < p->owned.size(); k++)
-      p->buffers.push_back((k == 0 && !c.null_count) ? nullptr : static_cast<const void*>(p->owned[k].data()));
+    if (c.ext) { p->keep = c.ext; p->owned.emplace_back(); }
+    else {
+      p->owned.push_back(c.values);
+      if (p->owned.back().empty()) p->owned.back().assign(8, 0);  // never hand out a NULL data pointer
+    }
+    for (size_t k = 0; k < p->owned.size(); k++) {
+      const void* ptr = static_cast<const void*>(p->owned[k].data());
+      if (k == 0 && !c.null_count) ptr = nullptr;
+      if (c.ext && k + 1 == p->owned.size()) ptr = c.ext->p + c.ext_off;
+      p->buffers.push_back(ptr);
+    }
     a.n_buffers = int64_t(p->buffers.size());
     a.buffers = p->buffers.data();
     a.release = release_array;

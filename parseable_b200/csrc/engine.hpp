@@ -122,10 +122,20 @@ class Table {
   int find_column(const std::string& name) const;
 };
 
+// page-locked host block that result batches can alias (zero copy); returns to the pool when
+// the last batch that references it is released by the consumer
+struct PinnedBlock {
+  uint8_t* p = nullptr;
+  size_t bytes = 0;
+  ~PinnedBlock();
+};
+
 struct OutColumn {
   std::string name;
   int type = PQ_T_I64;               // PqType
   std::vector<uint8_t> values;       // 8-byte values, bit-packed bools, or utf8 bytes
+  std::shared_ptr<PinnedBlock> ext;  // when set, the values are ext->p + ext_off (not `values`)
+  size_t ext_off = 0;
   std::vector<int32_t> offsets;      // utf8
   std::vector<uint8_t> validity;     // empty when null_count == 0
   int64_t null_count = 0;

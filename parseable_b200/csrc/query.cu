@@ -11,6 +11,7 @@
 //   * SQL three-valued logic, NULL group keys, COUNT -> Int64, SUM(Int64) wrapping,
 //     float totalOrder.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -188,6 +189,12 @@ Query::Query(const PqQueryDesc& d) {
 Query::~Query() = default;
 
 void Query::run(const PqQueryDesc& d) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  struct HostTimer {
+    std::chrono::steady_clock::time_point t0;
+    PqMetrics* m;
+    ~HostTimer() { m->host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+  } host_timer{t_begin, &metrics};
   Context& ctx = Context::get();
   ctx.ensure();
   if (d.n_columns > (uint32_t)kMaxCols) throw Error(PQ_ERR_UNSUPPORTED, "too many referenced columns");
@@ -209,6 +216,7 @@ void Query::run(const PqQueryDesc& d) {
     for (uint32_t c = 0; c < d.n_columns; c++) names.push_back(d.columns[c].name ? d.columns[c].name : "");
     owned_table_ = std::make_unique<Table>();
     owned_table_->open(d.files, d.n_files, names, d.shard_index, d.shard_count, stream);
+    metrics.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     table = owned_table_.get();
     metrics.h2d_bytes += table->h2d_bytes;
   }
@@ -980,7 +988,8 @@ void Query::run(const PqQueryDesc& d) {
     // ---- filter / COUNT(*) ----
     // bitmap-driven stream compaction on the device: per-item prefix, then one CTA per item
     DevBuf<unsigned long long> d_item_base, d_total, d_ids;
-    std::vector<uint64_t> ids;
+    std::shared_ptr<PinnedBlock> ids_block;   // selected row ordinals land in page-locked memory, batches alias it
+    unsigned long long n_ids = 0;
     if (want_rows && !items.empty()) {
       if (d.n_projection && !(d.flags & PQ_QUERY_EMIT_ROW_IDS))
         throw Error(PQ_ERR_UNSUPPORTED, "projection of column values is not on the GPU path yet: ask for PQ_QUERY_EMIT_ROW_IDS or PQ_QUERY_COUNT_ONLY");
@@ -999,8 +1008,11 @@ void Query::run(const PqQueryDesc& d) {
         uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * 8));
         k_compact_row_ids<<<grid, 256, 0, stream>>>(d_bitmap.p, d_items.p, d_item_counts.p, d_item_base.p, uint32_t(items.size()), d_ids.p, keep);
         launches++;
-        ids.resize(keep);
-        PQB_CUDA(cudaMemcpyAsync(ids.data(), d_ids.p, keep * 8, cudaMemcpyDeviceToHost, stream));
+        ids_block = std::make_shared<PinnedBlock>();
+        ids_block->p = ctx.pinned_acquire(keep * 8);
+        ids_block->bytes = keep * 8;
+        n_ids = keep;
+        PQB_CUDA(cudaMemcpyAsync(ids_block->p, d_ids.p, keep * 8, cudaMemcpyDeviceToHost, stream));
         metrics.d2h_bytes += keep * 8;
       }
     }
@@ -1030,18 +1042,17 @@ void Query::run(const PqQueryDesc& d) {
       batches_.push_back(std::move(ob));
     } else if (want_rows) {
       // selected row ordinals, ascending (projection of column VALUES is the next widening step)
-      for (size_t r0 = 0; r0 < ids.size() || (r0 == 0 && ids.empty()); r0 += batch_rows) {
-        size_t nb = std::min<size_t>(batch_rows, ids.size() - r0);
+      for (size_t r0 = 0; r0 < n_ids || (r0 == 0 && n_ids == 0); r0 += batch_rows) {
+        size_t nb = std::min<size_t>(batch_rows, n_ids - r0);
         OutBatch ob;
         ob.rows = int64_t(nb);
         OutColumn oc;
         oc.name = "__row_id";
         oc.type = PQ_T_I64;
-        oc.values.resize(nb * 8);
-        if (nb) std::memcpy(oc.values.data(), ids.data() + r0, nb * 8);
+        if (nb) { oc.ext = ids_block; oc.ext_off = r0 * 8; }
         ob.cols.push_back(std::move(oc));
         batches_.push_back(std::move(ob));
-        if (ids.empty()) break;
+        if (n_ids == 0) break;
       }
     }
   }

@@ -167,6 +167,13 @@ __device__ __forceinline__ void or_bits(uint32_t* bm, uint32_t pos, uint32_t wor
   if (hi) atomicOr(&bm[(pos >> 5) + 1], hi);
 }
 
+// two sentinel entries (start = ~0) behind the last directory entry: the row pass may always look
+// one and two entries ahead without a bounds test
+__device__ __forceinline__ void dir_sentinels(DirEntry* dir, uint32_t n) {
+  dir[n].start = 0xffffffffu; dir[n].count = 0; dir[n].kind = 0; dir[n].chunk0 = 0; dir[n].payload = 0;
+  dir[n + 1] = dir[n];
+}
+
 // expand a run directory of 1-bit values into a bitmap (OR into pre-zeroed words)
 __device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent, const uint32_t* win,
                                               uint32_t* bm) {
@@ -523,82 +530,81 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
 // registers (warp uniform), every lane unpacks its own row's index, probes the leaf's LUT, one
 // ballot makes the word, words are AND-ed in a register and the word is consumed at once.  No
 // leaf bitmaps, no atomics, no block barrier inside the slab.
-struct FastLeaf {
-  const DirEntry* dir;
-  const uint32_t* win;
-  const uint8_t* lut;   // bytes per dictionary entry: shared-memory copy when it fits, else global
-  uint32_t nent, bw;
-  uint32_t e;           // index of entry A
-  DirEntry A, B;        // A covers base_row, B is the next entry (start == ~0u: none)
-  uint32_t c_start;     // start of the entry after B (~0u: none)
-};
+// Each warp owns kWordsPerWarp CONSECUTIVE 32-row words (256 rows).  Leaves are the outer loop,
+// so only one leaf's cursor (current directory entry + start of the next) is live in registers;
+// the per-word selection lives in a small unrolled register array.
+constexpr int kWordsPerWarp = kSlabWords / kScanWarps;
 
-__device__ __forceinline__ void fast_leaf_init(FastLeaf& f, const DirEntry* dir, uint32_t nent, const uint32_t* win,
-                                               uint32_t bw, const uint8_t* lut) {
-  f.dir = dir; f.nent = nent; f.win = win; f.bw = bw; f.lut = lut; f.e = 0;
-  f.A = dir[0];
-  if (nent > 1) f.B = dir[1]; else { f.B.start = 0xffffffffu; f.B.count = 0; f.B.kind = 0; f.B.chunk0 = 0; f.B.payload = 0; }
-  f.c_start = nent > 2 ? dir[2].start : 0xffffffffu;
-}
-
-// index of row r (r < R guaranteed by the caller for lanes with in == true)
-__device__ __forceinline__ uint32_t fast_leaf_idx(FastLeaf& f, uint32_t base_row, uint32_t r, bool in) {
-  while (f.B.start <= base_row) {  // warp uniform advance
-    f.e++;
-    f.A = f.B;
-    if (f.e + 1 < f.nent) f.B = f.dir[f.e + 1]; else f.B.start = 0xffffffffu;
-    f.c_start = f.e + 2 < f.nent ? f.dir[f.e + 2].start : 0xffffffffu;
-  }
-  uint32_t start, kind, payload;
-  if (base_row + 31 >= f.c_start) {
-    // three or more entries inside one word (very short runs): per-lane search
-    uint32_t e = f.e;
-    if (in) while (e + 1 < f.nent && f.dir[e + 1].start <= r) e++;
-    const DirEntry d = f.dir[e];
-    start = d.start; kind = d.kind; payload = d.payload;
-  } else {
-    const bool useB = r >= f.B.start;
-    start = useB ? f.B.start : f.A.start;
-    kind = useB ? f.B.kind : f.A.kind;
-    payload = useB ? f.B.payload : f.A.payload;
-  }
-  if (!in) return 0;
-  return kind ? bp_get(f.win, payload, f.bw, r - start) : payload;
-}
-
-template <int NL>
 __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
                                                   const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
                                                   uint32_t r_item, unsigned long long* acc, bool agg_mode) {
   const uint32_t warp = warp_id(), lane = lane_id();
-  const uint32_t nwords = (R + 31) >> 5;
   const uint32_t nslots = plan.nslots;
-  FastLeaf fl[NL];
+  const uint32_t w0 = warp * kWordsPerWarp;
+  uint32_t selw[kWordsPerWarp];
 #pragma unroll
-  for (int l = 0; l < NL; l++) {
+  for (int i = 0; i < kWordsPerWarp; i++) selw[i] = row_mask(w0 + i, R);
+  for (uint32_t l = 0; l < plan.nleaves; l++) {
     const DevLeaf& lf = plan.leaves[l];
     const SlabCol& s = ctl.slab[lf.col];
-    const uint8_t* lut = ctl.lut_smem[l] ? smem + L.lutc + l * kLutCacheBytes : a.luts + lf.lut_off + s.lut_base;
-    fast_leaf_init(fl[l], smem_at<DirEntry>(smem, L.valdir[lf.col]), s.nval, smem_at<uint32_t>(smem, L.valwin[lf.col][buf]),
-                   s.bw, lut);
+    // directory as plain words: {start, count|kind<<16|chunk0<<24, payload}; the walker left two
+    // sentinel entries (start = ~0) behind the last one, so e+1 / e+2 are always readable
+    const uint32_t* dirw = smem_at<uint32_t>(smem, L.valdir[lf.col]);
+    const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[lf.col][buf]);
+    const uint32_t nent = s.nval, bw = s.bw;
+    const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
+    // lanes 0..7 each find the entry holding the first row of "their" word; broadcast per word below
+    uint32_t my_e = 0;
+    if (lane < (uint32_t)kWordsPerWarp) {
+      const uint32_t first = (w0 + lane) * 32;
+      while (my_e + 1 < nent && dirw[(my_e + 1) * 3] <= first) my_e++;
+    }
+    const bool smem_lut = ctl.lut_smem[l] != 0;
+    const uint8_t* lut_s = smem + L.lutc + l * kLutCacheBytes;
+    const uint8_t* lut_g = a.luts + lf.lut_off + s.lut_base;
+#pragma unroll
+    for (int i = 0; i < kWordsPerWarp; i++) {
+      const uint32_t e = __shfl_sync(0xffffffffu, my_e, i);
+      if (selw[i] == 0) continue;  // warp uniform: nothing left in this word
+      const uint32_t r = (w0 + i) * 32 + lane;
+      const uint32_t* A = dirw + e * 3;
+      const uint32_t b_start = A[3], c_start = A[6];
+      const bool useB = r >= b_start;
+      uint32_t start = useB ? b_start : A[0];
+      uint32_t meta = useB ? A[4] : A[1];
+      uint32_t payload = useB ? A[5] : A[2];
+      if (r >= c_start && r < R) {  // three or more entries inside one word (very short runs): rare
+        uint32_t el = e + 2;
+        while (el + 1 < nent && dirw[(el + 1) * 3] <= r) el++;
+        start = dirw[el * 3]; meta = dirw[el * 3 + 1]; payload = dirw[el * 3 + 2];
+      }
+      // bit-packed: extract; RLE: the payload is the value.  Rows past R read in-bounds garbage and
+      // are masked out by selw (row_mask); their LUT index is clamped by the mask / the guard below.
+      uint32_t v = payload;
+      if (meta & 0x10000u) {
+        const uint32_t bit = payload + (r - start) * bw;
+        const uint32_t wi = bit >> 5;
+        v = __funnelshift_r(win[wi], win[wi + 1], bit & 31) & vmask;
+      }
+      bool t;
+      if (smem_lut) t = lut_s[v & (kLutCacheBytes - 1)] != 0;
+      else t = r < R && lut_g[v] != 0;
+      selw[i] &= __ballot_sync(0xffffffffu, t);
+    }
   }
   if (agg_mode) {
     if (lane < plan.ncols) ctl.wcur[warp][lane] = 0;
     __syncwarp();
   }
   uint32_t cnt = 0;
-  for (uint32_t w = warp; w < nwords; w += kScanWarps) {
-    const uint32_t base_row = w * 32, r = base_row + lane;
-    const bool in = r < R;
-    uint32_t sel = row_mask(w, R);
 #pragma unroll
-    for (int l = 0; l < NL; l++) {
-      const uint32_t v = fast_leaf_idx(fl[l], base_row, r, in);
-      sel &= __ballot_sync(0xffffffffu, in && fl[l].lut[v]);
-      if (sel == 0) break;  // warp uniform: nothing left to select in this word
-    }
+  for (int i = 0; i < kWordsPerWarp; i++) {
+    const uint32_t sel = selw[i];
+    if (sel == 0) continue;
+    const uint32_t base_row = (w0 + i) * 32, r = base_row + lane;
+    const bool in = r < R;
     if (!agg_mode) {
-      if (lane == 0 && sel) {
+      if (lane == 0) {
         cnt += __popc(sel);
         if (plan.write_bitmap) {
           uint32_t pos = r_item + base_row;
@@ -614,7 +620,6 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
       }
       continue;
     }
-    if (sel == 0) continue;
     const bool mine = (sel >> lane) & 1;
     if (lane == 0) cnt += __popc(sel);
     uint32_t slot = 0;
@@ -738,8 +743,9 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
         uint32_t n = 0;
         uint32_t got = c.enc == DE_DELTA
                            ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries);
+                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
         s.nval = n;
+        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
         if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
           if (s.all_valid) rc = got;
           else {
@@ -890,8 +896,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
               uint32_t n = 0;
               rc = c.enc == DE_DELTA
                        ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries);
+                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
               s.nval = n;
+              if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
             }
           }
           if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
@@ -995,12 +1002,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       const bool fast_and = mode == MODE_FAST_AND;
       if (fast_and) {
         // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
-        switch (plan.nleaves) {
-          case 1: cnt = fast_and_rows<1>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
-          case 2: cnt = fast_and_rows<2>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
-          case 3: cnt = fast_and_rows<3>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
-          default: cnt = fast_and_rows<4>(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode); break;
-        }
+        cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
       } else if (mode == MODE_ROW_MAJOR) {
         // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
         cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);

@@ -87,6 +87,10 @@ bool Context::is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+PinnedBlock::~PinnedBlock() {
+  if (p) Context::get().pinned_release(p);
+}
+
 // ---------------- HostFile ----------------
 HostFile::~HostFile() {
   if (mapped && data) munmap(const_cast<uint8_t*>(data), size);
