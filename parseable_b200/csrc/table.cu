@@ -16,6 +16,27 @@
 
 namespace pqb {
 
+struct GatherCopy { const uint8_t* src; uint64_t dst_off; uint64_t bytes; };
+
+// src (mapped page-locked host memory) and arena + dst_off share their 16-byte phase
+__global__ void k_gather_copy(const GatherCopy* __restrict__ copies, uint8_t* __restrict__ arena) {
+  const GatherCopy c = copies[blockIdx.x];
+  const uint8_t* src = c.src;
+  uint8_t* dst = arena + c.dst_off;
+  const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15;
+  const uint64_t h = head < c.bytes ? head : c.bytes;
+  if (blockIdx.y == 0 && threadIdx.x < h) dst[threadIdx.x] = src[threadIdx.x];
+  const uint64_t nvec = (c.bytes - h) / 16;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + h);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + h);
+  for (uint64_t i = uint64_t(blockIdx.y) * blockDim.x + threadIdx.x; i < nvec; i += uint64_t(gridDim.y) * blockDim.x) {
+    uint4 v0 = s4[i];
+    d4[i] = v0;
+  }
+  const uint64_t tail0 = h + nvec * 16;
+  if (blockIdx.y == 0 && tail0 + threadIdx.x < c.bytes) dst[tail0 + threadIdx.x] = src[tail0 + threadIdx.x];
+}
+
 // ---------------- Context ----------------
 Context& Context::get() {
   static Context c;
@@ -409,8 +430,9 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         tc.file_off = uint64_t(cm.start());
         tc.bytes = uint64_t(cm.total_compressed_size);
         if (tc.file_off + tc.bytes > hf.size) throw Error(PQ_ERR_CORRUPT, "column chunk outside the file");
-        tc.arena_off = arena;
-        arena = (arena + tc.bytes + 64 + 255) & ~255ull;
+        // same 16-byte phase as the source bytes: the gather kernel moves whole 16-byte vectors
+        tc.arena_off = arena + ((uintptr_t(hf.data) + tc.file_off) & 15);
+        arena = (tc.arena_off + tc.bytes + 64 + 255) & ~255ull;
         copies.push_back({fi, tc.file_off, tc.arena_off, tc.bytes});
         chunk_bytes += tc.bytes;
         jobs.push_back({uint32_t(row_groups.size()), uint32_t(c), fi});
@@ -433,16 +455,39 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   std::vector<size_t> staged_orig;
   std::vector<char> file_pinned(files.size(), 0);
   for (size_t f = 0; f < files.size(); f++) file_pinned[f] = !files[f]->mapped && ctx.is_pinned(files[f]->data);
+  // page-locked file images: ONE gather kernel pulls every chunk over PCIe (the SMs read the
+  // mapped host memory directly) instead of hundreds of cudaMemcpyAsync calls
+  std::vector<GatherCopy> gathers;
+  std::vector<const uint8_t*> file_dev(files.size(), nullptr);  // device-visible alias of a page-locked image
+  for (size_t f = 0; f < files.size(); f++) {
+    if (!file_pinned[f]) continue;
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(files[f]->data), 0) == cudaSuccess && dp &&
+        ((uintptr_t(dp) ^ uintptr_t(files[f]->data)) & 15) == 0)
+      file_dev[f] = static_cast<const uint8_t*>(dp);
+    else cudaGetLastError();
+  }
   for (size_t k = 0; k < copies.size(); k++) {
     const Copy& cp = copies[k];
     const HostFile& hf = *files[cp.file];
     if (file_pinned[cp.file]) {
-      PQB_CUDA(cudaMemcpyAsync(d_arena + cp.dst_off, hf.data + cp.src_off, cp.bytes, cudaMemcpyHostToDevice, stream));
+      if (file_dev[cp.file]) gathers.push_back({file_dev[cp.file] + cp.src_off, cp.dst_off, cp.bytes});
+      else PQB_CUDA(cudaMemcpyAsync(d_arena + cp.dst_off, hf.data + cp.src_off, cp.bytes, cudaMemcpyHostToDevice, stream));
     } else {
       staged.push_back(cp);
       staged_orig.push_back(k);
     }
     h2d_bytes += cp.bytes;
+  }
+  GatherCopy* d_gathers = nullptr;
+  if (!gathers.empty()) {
+    PQB_CUDA(cudaMallocAsync((void**)&d_gathers, gathers.size() * sizeof(GatherCopy), stream));
+    PQB_CUDA(cudaMemcpyAsync(d_gathers, gathers.data(), gathers.size() * sizeof(GatherCopy), cudaMemcpyHostToDevice, stream));
+    // ~64 KiB per CTA pass keeps a few thousand 16-byte reads in flight per SM
+    dim3 grid(uint32_t(gathers.size()), 4);
+    k_gather_copy<<<grid, 256, 0, stream>>>(d_gathers, d_arena);
+    PQB_CUDA(cudaGetLastError());
+    PQB_CUDA(cudaFreeAsync(d_gathers, stream));
   }
   if (!staged.empty()) {
     // gather into pinned staging slices with a few host threads, one cudaMemcpyAsync per slice;
