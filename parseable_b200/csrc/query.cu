@@ -606,12 +606,14 @@ void Query::run(const PqQueryDesc& d) {
     L.idx[s] = (plan.cols[s].has_dict || plan.cols[s].has_delta) ? off : 0;
     off += plan.cols[s].has_delta ? kSlabRows * 8 : (plan.cols[s].has_dict ? kSlabRows * 4 : 0);
     L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
-    L.valdir[s] = off;
-    off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
+    for (int b = 0; b < 2; b++) {
+      L.valdir[s][b] = off;
+      off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
+    }
   }
   L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
   L.sel = off; off += kSlabWords * 4;
-  L.lutc = off; if (plan.fast_and) off += nleaves * kLutCacheBytes;
+  L.lutc = off; if (plan.fast_and) off += 2 * nleaves * kLutCacheBytes;
   off = align_up(off, 128);
   L.acc = off;
   const uint32_t smem_fixed = off;
@@ -837,6 +839,7 @@ void Query::run(const PqQueryDesc& d) {
   DevBuf<uint32_t> d_bitmap, d_item_counts;
   if (want_rows) { d_bitmap.alloc(std::max<uint32_t>(bitmap_words, 1), stream); d_bitmap.zero(); }
   d_item_counts.alloc(std::max<size_t>(items.size(), 1), stream);
+  d_item_counts.zero();  // row warps add their per-slab counts with atomics
   if (want_rows) algo_bytes += metrics.rows_scanned / 8;
   metrics.algorithmic_bytes = algo_bytes;
 

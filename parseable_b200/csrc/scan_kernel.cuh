@@ -30,8 +30,15 @@
 
 namespace pqb {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanWarps = kScanThreads / 32;
+// 8 row warps do the data-parallel work of a slab; one more warp — the CONTROL warp — runs one
+// slab ahead: it waits for the TMA windows, walks the run headers, commits the cursors, prefetches
+// the next windows and publishes a SlabView.  Row warps and control warp meet through mbarriers
+// (full[b] / empty[b], double buffered), so the sequential part of the format never stalls the
+// wide part.
+constexpr int kRowWarps = 8;
+constexpr int kRowThreads = kRowWarps * 32;
+constexpr int kCtlWarp = kRowWarps;
+constexpr int kScanThreads = kRowThreads + 32;
 
 // byte offsets of the dynamic shared-memory regions, computed on the host
 struct SmemLayout {
@@ -43,11 +50,11 @@ struct SmemLayout {
   uint32_t rank[kMaxCols];    // uint32[kSlabWords]
   uint32_t idx[kMaxCols];     // uint32[kSlabRows]  (0: indices of this column are never staged)
   uint32_t defdir[kMaxCols];  // DirEntry[kMaxDirEntries]
-  uint32_t valdir[kMaxCols];
+  uint32_t valdir[kMaxCols][2];  // DirEntry / DeltaEntry directory of the value stream, double buffered
   uint32_t leafT;             // uint32[nleaves][kSlabWords + 2]
   uint32_t sel;               // uint32[kSlabWords]
   uint32_t acc;               // shared accumulator table
-  uint32_t lutc;              // uint8[nleaves][kLutCacheBytes]: leaf LUTs of the current row group (fast AND path)
+  uint32_t lutc;              // uint8[2][nleaves][kLutCacheBytes]: leaf LUTs of the slab's row group, double buffered
   uint32_t total;
 };
 constexpr int kLeafWords = kSlabWords + 2;
@@ -86,7 +93,14 @@ struct SlabCol {
   int64_t dl_last;          // DELTA pages: value of the last row decoded so far in this page
 };
 
-enum SlabMode : uint32_t { MODE_GENERIC = 0, MODE_FAST_AND = 1, MODE_ROW_MAJOR = 2, MODE_GENERAL_WALK = 3 };
+enum SlabMode : uint32_t { MODE_GENERIC = 0, MODE_FAST_AND = 1, MODE_ROW_MAJOR = 2, MODE_GENERAL_WALK = 3, MODE_STOP = 4 };
+
+// everything the row warps need to know about one slab, published by the control warp
+struct SlabView {
+  uint32_t mode, R, has_delta, item_id, r_item, bitmap_word0, rg, _pad;
+  uint64_t global_row0;
+  SlabCol col[kMaxCols];
+};
 
 struct ScanCtl {
   uint64_t mbar[2];
@@ -100,12 +114,14 @@ struct ScanCtl {
   uint32_t R;            // rows of the current slab
   uint32_t has_delta;    // some column of this slab is DELTA_BINARY_PACKED
   uint32_t rmin[kMaxCols];
-  int64_t scan_tmp[kScanWarps];             // DELTA prefix scan: per-warp totals
-  uint32_t wcur[kScanWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
-  uint32_t stk[kScanWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
-  uint32_t lut_smem[kMaxLeaves];            // fast AND path: leaf LUT of this item's row group is cached in smem
+  int64_t scan_tmp[kRowWarps];             // DELTA prefix scan: per-warp totals
+  uint32_t wcur[kRowWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
+  uint32_t stk[kRowWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
+  uint32_t lut_smem[2][kMaxLeaves];            // fast AND path: leaf LUT of this item's row group is cached in smem
   ColCursor cur[kMaxCols];
-  SlabCol slab[kMaxCols];
+  uint64_t full[2], empty[2];               // control -> rows "slab published", rows -> control "slab consumed"
+  uint32_t lut_rg[2];                       // row group (+1) whose LUTs sit in lutc[b]
+  SlabView view[2];
 };
 
 __device__ __forceinline__ void page_enter(ColCursor& c, const DevPage* pages, uint32_t pg) {
@@ -177,7 +193,7 @@ __device__ __forceinline__ void dir_sentinels(DirEntry* dir, uint32_t n) {
 // expand a run directory of 1-bit values into a bitmap (OR into pre-zeroed words)
 __device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent, const uint32_t* win,
                                               uint32_t* bm) {
-  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
+  for (uint32_t e = warp_id(); e < nent; e += kRowWarps) {
     const DirEntry d = dir[e];
     for (uint32_t k = 0; k < d.count; k += 32) {
       uint32_t j = k + lane_id();
@@ -192,7 +208,7 @@ __device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent
 // unpack a run directory of dictionary indices into idx[0..nv)
 __device__ __forceinline__ void dir_to_idx(const DirEntry* dir, uint32_t nent, const uint32_t* win, uint32_t bw,
                                            uint32_t* idx) {
-  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
+  for (uint32_t e = warp_id(); e < nent; e += kRowWarps) {
     const DirEntry d = dir[e];
     if (d.kind) {
       for (uint32_t j = lane_id(); j < d.count; j += 32) idx[d.start + j] = bp_get(win, d.payload, bw, j);
@@ -217,7 +233,7 @@ __device__ __forceinline__ void dir_to_leafbits(const DirEntry* dir, uint32_t ne
   uint32_t e = 0;
   DirEntry d = dir[0];
   uint32_t next0 = nent > 1 ? uint32_t(dir[1].chunk0) : 0xffffffffu;
-  for (uint32_t q = warp_id(); q < nchunks; q += kScanWarps) {
+  for (uint32_t q = warp_id(); q < nchunks; q += kRowWarps) {
     while (q >= next0) {  // warp uniform; chunks are visited in increasing order
       e++;
       d = dir[e];
@@ -265,6 +281,9 @@ __device__ __forceinline__ uint32_t value_bool(const SlabCol& c, const uint8_t* 
   return (arena[c.val_base + (k >> 3)] >> (k & 7)) & 1;
 }
 
+// barrier among the row warps only (the control warp runs ahead and must not be waited for)
+__device__ __forceinline__ void row_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kRowThreads) : "memory"); }
+
 template <typename T>
 __device__ __forceinline__ T* smem_at(uint8_t* base, uint32_t off) {
   return reinterpret_cast<T*>(base + off);
@@ -304,26 +323,26 @@ __device__ __forceinline__ uint32_t row_mask(uint32_t w, uint32_t R) {
 // that one warp so the other warps park at the block barrier instead of burning issue slots.
 __device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
   col = lane_id();
-  return warp_id() == 0 && col < ncols;
+  return warp_id() == kCtlWarp && col < ncols;
 }
 
 
 // ---- DELTA_BINARY_PACKED: miniblock directory -> deltas -> block-wide inclusive scan -> values ----
-__device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf) {
-  SlabCol& s = ctl.slab[c];
+__device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf) {
+  SlabCol& s = slab[c];
   const uint32_t nv = s.nv;
   int64_t* vals = smem_at<int64_t>(smem, L.idx[c]);
-  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c]);
+  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c][buf]);
   const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
-  for (uint32_t e = warp_id(); e < s.nval; e += kScanWarps) {
+  for (uint32_t e = warp_id(); e < s.nval; e += kRowWarps) {
     const DeltaEntry d = dir[e];
     for (uint32_t j = lane_id(); j < d.count; j += 32)
       vals[d.start + j] = d.kind ? d.min_delta : int64_t(uint64_t(d.min_delta) + bp_get64(win, d.bitoff, d.bw, j));
   }
-  __syncthreads();
+  row_sync();
   // a slab that starts a page begins with the page's first value (absolute): no carry
   const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : s.dl_last;
-  constexpr uint32_t kPer = kSlabRows / kScanThreads;
+  constexpr uint32_t kPer = kSlabRows / kRowThreads;
   const uint32_t b = threadIdx.x * kPer;
   int64_t loc[kPer];
   int64_t sum = 0;
@@ -339,26 +358,26 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout
     if ((int)lane_id() >= o) incl = int64_t(uint64_t(incl) + uint64_t(t));
   }
   if (lane_id() == 31) ctl.scan_tmp[warp_id()] = incl;
-  __syncthreads();
+  row_sync();
   int64_t base = carry;
   for (uint32_t w = 0; w < warp_id(); w++) base = int64_t(uint64_t(base) + uint64_t(ctl.scan_tmp[w]));
   base = int64_t(uint64_t(base) + uint64_t(incl) - uint64_t(sum));
 #pragma unroll
   for (uint32_t i = 0; i < kPer; i++)
     if (b + i < nv) vals[b + i] = int64_t(uint64_t(base) + uint64_t(loc[i]));
-  __syncthreads();
+  row_sync();
   if (threadIdx.x == 0 && nv) s.dl_last = vals[nv - 1];
-  __syncthreads();
+  row_sync();
 }
 
 // ---- the no-NULL fast row pass --------------------------------------------------------------
 // Dictionary index of row r (== value r: the slab has no NULLs) of column c, straight from the
 // staged bytes through the run directory.  Control flow is warp uniform except the (rare) walk
 // across directory entries inside one 32-row word.
-__device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
+__device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
                                              uint32_t base_row, uint32_t r, bool in) {
-  const SlabCol& s = ctl.slab[c];
-  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
+  const SlabCol& s = slab[c];
+  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
   const uint32_t n = s.nval;
   uint32_t e = ctl.wcur[warp_id()][c];
   while (e + 1 < n && dir[e + 1].start <= base_row) e++;
@@ -369,11 +388,11 @@ __device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, 
   return d.kind ? bp_get(smem_at<uint32_t>(smem, L.valwin[c][buf]), d.payload, s.bw, r - d.start) : d.payload;
 }
 
-__device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const uint8_t* arena,
+__device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, const uint8_t* arena,
                                                    uint32_t c, uint32_t buf, uint32_t base_row, uint32_t r, bool in, bool want) {
-  const SlabCol& s = ctl.slab[c];
+  const SlabCol& s = slab[c];
   if (PQB_ENC_HAS_STREAM(s.enc)) {
-    uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
+    uint32_t v = fast_idx(ctl, slab, L, smem, c, buf, base_row, r, in);
     if (s.enc == DE_RLE_BOOL) return v & 1;
     return (in && want) ? load_u64_unaligned(arena + s.dict_off + uint64_t(v) * 8) : 0;
   }
@@ -382,12 +401,12 @@ __device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, const SmemLayou
 }
 
 // One 32-row word of one leaf: returns T (and N through *nw); all lanes get the same words.
-__device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+__device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem,
                                                    const DevScanArgs& a, uint32_t l, uint32_t buf, uint32_t base_row,
                                                    uint32_t r, bool in, uint32_t* nw) {
   const DevLeaf& lf = plan.leaves[l];
   const uint32_t c = lf.col;
-  const SlabCol& s = ctl.slab[c];
+  const SlabCol& s = slab[c];
   *nw = 0;
   if (!s.present) {  // column missing from this file: every row NULL
     if (lf.kind == LK_IS_NULL) return 0xffffffffu;
@@ -400,7 +419,7 @@ __device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl&
   const uint8_t kind = plan.cols[c].kind;
   bool t = false;
   if (PQB_ENC_HAS_STREAM(s.enc)) {
-    uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
+    uint32_t v = fast_idx(ctl, slab, L, smem, c, buf, base_row, r, in);
     if (in) t = s.enc == DE_DICT ? a.luts[lf.lut_off + s.lut_base + v] != 0 : cmp_i64((int64_t)(v & 1), lf.lit_i64, lf.cmp);
   } else if (in) {
     if (kind == DK_BOOL) {
@@ -419,9 +438,9 @@ __device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl&
 // Every warp owns whole 32-row words of the slab: leaves -> Kleene combine -> consume, all in
 // registers / per-warp scratch.  No leaf bitmaps, no staging, no block barrier.  Returns the rows
 // this thread's warp selected (lane 0 carries the count).
-__device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
-                                              const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
-                                              uint32_t r_item, unsigned long long* acc, bool agg_mode) {
+__device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem,
+                                              const DevScanArgs& a, const SlabView& v, uint32_t buf, uint32_t R,
+                                              unsigned long long* acc, bool agg_mode) {
   const uint32_t warp = warp_id(), lane = lane_id();
   const uint32_t nwords = (R + 31) >> 5;
   const uint32_t nslots = plan.nslots;
@@ -429,7 +448,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
   __syncwarp();
   uint32_t* st = ctl.stk[warp];
   uint32_t cnt = 0;
-  for (uint32_t w = warp; w < nwords; w += kScanWarps) {
+  for (uint32_t w = warp; w < nwords; w += kRowWarps) {
     const uint32_t base_row = w * 32, r = base_row + lane;
     const bool in = r < R;
     int sp = 0;
@@ -438,7 +457,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
       const DevPredOp op = plan.pred[i];
       if (op.kind == PK_LEAF) {
         uint32_t n;
-        uint32_t t = fast_leaf_word(plan, ctl, L, smem, a, op.arg, buf, base_row, r, in, &n);
+        uint32_t t = fast_leaf_word(plan, ctl, slab, L, smem, a, op.arg, buf, base_row, r, in, &n);
         st[2 * sp] = t;
         st[2 * sp + 1] = n;
         sp++;
@@ -467,8 +486,8 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
       if (lane == 0) {
         cnt += __popc(sel);
         if (plan.write_bitmap && sel) {
-          uint32_t pos = r_item + base_row;
-          uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+          uint32_t pos = v.r_item + base_row;
+          uint32_t* dst = a.bitmap + v.bitmap_word0 + (pos >> 5);
           uint32_t sh = pos & 31;
           if (sh == 0) *dst = sel;
           else {
@@ -486,17 +505,17 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
     uint32_t slot = 0;
     for (uint32_t k = 0; k < plan.nkeys; k++) {
       const DevKey& key = plan.keys[k];
-      const SlabCol& s = ctl.slab[key.col];
+      const SlabCol& s = slab[key.col];
       uint32_t gid = key.card;  // column missing: NULL group
       if (s.present) {
         if (key.kind == KK_BOOL) {
-          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+          gid = (uint32_t)fast_value_u64(ctl, slab, L, smem, a.arena, key.col, buf, base_row, r, in, false);
           if (!PQB_ENC_HAS_STREAM(s.enc)) {
             uint32_t kk = s.vals_done + r;
             gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
           }
         } else {
-          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
+          uint32_t v = fast_idx(ctl, slab, L, smem, key.col, buf, base_row, r, in);
           gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
         }
       }
@@ -506,14 +525,14 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = ctl.slab[ag.col];
+      const SlabCol& s = slab[ag.col];
       if (!s.present) continue;  // all NULL: contributes nothing
       uint64_t bits;
       if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
         uint32_t kk = s.vals_done + r;
         bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
       } else {
-        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+        bits = fast_value_u64(ctl, slab, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
       }
       if (!mine) continue;
       if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -533,11 +552,11 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
 // Each warp owns kWordsPerWarp CONSECUTIVE 32-row words (256 rows).  Leaves are the outer loop,
 // so only one leaf's cursor (current directory entry + start of the next) is live in registers;
 // the per-word selection lives in a small unrolled register array.
-constexpr int kWordsPerWarp = kSlabWords / kScanWarps;
+constexpr int kWordsPerWarp = kSlabWords / kRowWarps;
 
-__device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
-                                                  const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
-                                                  uint32_t r_item, unsigned long long* acc, bool agg_mode) {
+__device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem,
+                                                  const DevScanArgs& a, const SlabView& v, uint32_t buf, uint32_t R,
+                                                  unsigned long long* acc, bool agg_mode) {
   const uint32_t warp = warp_id(), lane = lane_id();
   const uint32_t nslots = plan.nslots;
   const uint32_t w0 = warp * kWordsPerWarp;
@@ -546,10 +565,10 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
   for (int i = 0; i < kWordsPerWarp; i++) selw[i] = row_mask(w0 + i, R);
   for (uint32_t l = 0; l < plan.nleaves; l++) {
     const DevLeaf& lf = plan.leaves[l];
-    const SlabCol& s = ctl.slab[lf.col];
+    const SlabCol& s = slab[lf.col];
     // directory as plain words: {start, count|kind<<16|chunk0<<24, payload}; the walker left two
     // sentinel entries (start = ~0) behind the last one, so e+1 / e+2 are always readable
-    const uint32_t* dirw = smem_at<uint32_t>(smem, L.valdir[lf.col]);
+    const uint32_t* dirw = smem_at<uint32_t>(smem, L.valdir[lf.col][buf]);
     const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[lf.col][buf]);
     const uint32_t nent = s.nval, bw = s.bw;
     const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
@@ -559,8 +578,8 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
       const uint32_t first = (w0 + lane) * 32;
       while (my_e + 1 < nent && dirw[(my_e + 1) * 3] <= first) my_e++;
     }
-    const bool smem_lut = ctl.lut_smem[l] != 0;
-    const uint8_t* lut_s = smem + L.lutc + l * kLutCacheBytes;
+    const bool smem_lut = ctl.lut_smem[buf][l] != 0;
+    const uint8_t* lut_s = smem + L.lutc + (buf * plan.nleaves + l) * kLutCacheBytes;
     const uint8_t* lut_g = a.luts + lf.lut_off + s.lut_base;
 #pragma unroll
     for (int i = 0; i < kWordsPerWarp; i++) {
@@ -607,8 +626,8 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
       if (lane == 0) {
         cnt += __popc(sel);
         if (plan.write_bitmap) {
-          uint32_t pos = r_item + base_row;
-          uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+          uint32_t pos = v.r_item + base_row;
+          uint32_t* dst = a.bitmap + v.bitmap_word0 + (pos >> 5);
           uint32_t sh = pos & 31;
           if (sh == 0) *dst = sel;
           else {
@@ -625,17 +644,17 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     uint32_t slot = 0;
     for (uint32_t k = 0; k < plan.nkeys; k++) {
       const DevKey& key = plan.keys[k];
-      const SlabCol& s = ctl.slab[key.col];
+      const SlabCol& s = slab[key.col];
       uint32_t gid = key.card;
       if (s.present) {
         if (key.kind == KK_BOOL) {
-          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+          gid = (uint32_t)fast_value_u64(ctl, slab, L, smem, a.arena, key.col, buf, base_row, r, in, false);
           if (!PQB_ENC_HAS_STREAM(s.enc)) {
             uint32_t kk = s.vals_done + r;
             gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
           }
         } else {
-          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
+          uint32_t v = fast_idx(ctl, slab, L, smem, key.col, buf, base_row, r, in);
           gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
         }
       }
@@ -645,14 +664,14 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = ctl.slab[ag.col];
+      const SlabCol& s = slab[ag.col];
       if (!s.present) continue;
       uint64_t bits;
       if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
         uint32_t kk = s.vals_done + r;
         bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
       } else {
-        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+        bits = fast_value_u64(ctl, slab, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
       }
       if (!mine) continue;
       if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -666,16 +685,17 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
 // The general per-slab walk (columns with NULLs, window / directory overflow): definition levels ->
 // validity bitmap + ranks -> index streams, shrinking the slab until every column is covered.
 // All threads call it; returns the rows of the slab (0: corrupt page).
-__device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t ncols,
+__device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, uint32_t ncols,
                                               uint32_t buf, uint32_t R, const StreamState& snap_def,
                                               const StreamState& snap_val, const DeltaState& snap_dl) {
   uint32_t mycol;
   const bool walker = walker_of(ncols, mycol);
   const uint32_t tid = threadIdx.x;
+  const bool is_row = warp_id() < kRowWarps;
   for (int attempt = 0; attempt < 4 && R > 0; attempt++) {
     if (walker) {  // definition levels
       ColCursor& c = ctl.cur[mycol];
-      SlabCol& s = ctl.slab[mycol];
+      SlabCol& s = slab[mycol];
       uint32_t got = R;
       s.ndef = 0;
       s.all_valid = 1;
@@ -691,10 +711,11 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
       }
       ctl.rmin[mycol] = got;
     }
-    for (uint32_t c = 0; c < ncols; c++) {
-      uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
-      for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kScanThreads) bm[w] = 0;
-    }
+    if (is_row)
+      for (uint32_t c = 0; c < ncols; c++) {
+        uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
+        for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kRowThreads) bm[w] = 0;
+      }
     __syncthreads();
     uint32_t R1 = R;
     for (uint32_t c = 0; c < ncols; c++) R1 = ctl.rmin[c] < R1 ? ctl.rmin[c] : R1;
@@ -704,15 +725,15 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
       __syncthreads();
       continue;
     }
-    for (uint32_t c = 0; c < ncols; c++) {
-      const SlabCol& s = ctl.slab[c];
+    if (is_row) for (uint32_t c = 0; c < ncols; c++) {
+      const SlabCol& s = slab[c];
       if (s.present && !s.all_valid)
         dir_to_bitmap(smem_at<DirEntry>(smem, L.defdir[c]), s.ndef, smem_at<uint32_t>(smem, L.defwin[c][buf]),
                       smem_at<uint32_t>(smem, L.valid[c]));
     }
     __syncthreads();
-    for (uint32_t c = warp_id(); c < ncols; c += kScanWarps) {
-      SlabCol& s = ctl.slab[c];
+    if (is_row) for (uint32_t c = warp_id(); c < ncols; c += kRowWarps) {
+      SlabCol& s = slab[c];
       if (!s.present) { if (lane_id() == 0) s.nv = 0; continue; }
       if (s.all_valid) { if (lane_id() == 0) s.nv = R; continue; }
       uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
@@ -735,17 +756,17 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
     __syncthreads();
     if (walker) {  // dictionary-index streams
       ColCursor& c = ctl.cur[mycol];
-      SlabCol& s = ctl.slab[mycol];
+      SlabCol& s = slab[mycol];
       uint32_t rc = R;
       s.nval = 0;
       if (c.present && PQB_ENC_HAS_WINDOW(c.enc) && s.nv > 0) {
         Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
         uint32_t n = 0;
         uint32_t got = c.enc == DE_DELTA
-                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
+                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol][buf]), n, kMaxDeltaEntries)
+                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n, kMaxDirEntries - 2);
         s.nval = n;
-        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
+        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n);
         if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
           if (s.all_valid) rc = got;
           else {
@@ -777,244 +798,27 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
   return 0;
 }
 
-__global__ void __launch_bounds__(kScanThreads, 4)
-k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  ScanCtl& ctl = *reinterpret_cast<ScanCtl*>(smem);
+
+// ---- the generic row phase (stages 4-6): any predicate program, NULLs, PLAIN / DELTA pages.  Row
+// warps only; block-level steps meet at row_sync(). ----
+__device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SlabView& v,
+                                                 const SmemLayout& L, uint8_t* smem, const DevScanArgs& a, uint32_t buf,
+                                                 uint32_t R, unsigned long long* acc, bool agg_mode) {
   const uint32_t tid = threadIdx.x;
   const uint32_t ncols = plan.ncols;
-  const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
-  const bool agg_mode = plan.mode == SM_AGG;
-  uint32_t mycol;
-  const bool walker = walker_of(ncols, mycol);
-
-  if (tid == 0) {
-    mbar_init(&ctl.mbar[0], 1);
-    mbar_init(&ctl.mbar[1], 1);
-    mbar_fence_init();
-    ctl.error = 0;
-  }
-  unsigned long long* sacc = smem_at<unsigned long long>(smem, L.acc);
-  if (agg_mode && plan.smem_acc) {
-    for (uint32_t i = tid; i < cells * plan.nslots; i += kScanThreads) {
-      uint32_t arr = i / plan.nslots;
-      unsigned long long init = 0;
-      if (arr >= 1 && arr < 1 + plan.n_acc) {
-        uint8_t k = plan.acc_init[arr - 1];
-        init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
-      }
-      sacc[i] = init;
-    }
-  }
-  __syncthreads();
-  unsigned long long* acc = (agg_mode && plan.smem_acc) ? sacc : a.acc;
   const uint32_t nslots = plan.nslots;
-
-  uint32_t phases = 0;  // bit b: parity to wait for on mbar[b]
+  const uint32_t nwords = (R + 31) >> 5;
   uint32_t* selw = smem_at<uint32_t>(smem, L.sel);
   uint32_t* leafT = smem_at<uint32_t>(smem, L.leafT);
-
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) ctl.item = (uint32_t)atomicAdd(&a.counters[2], 1ull);
-    __syncthreads();
-    const uint32_t item_id = ctl.item;
-    if (item_id >= plan.n_items) break;
-    const DevItem& item = a.items[item_id];
-
-    if (tid < ncols) {
-      ColCursor& c = ctl.cur[tid];
-      const DevChunk ch = a.chunks[item.rg * ncols + tid];
-      SlabCol& s = ctl.slab[tid];
-      s.lut_base = ch.lut_base;
-      s.dict_off = ch.dict_off;
-      s.present = ch.present;
-      c.present = ch.present;
-      c.page_end = ch.first_page + ch.n_pages;
-      if (ch.present) page_enter(c, a.pages, item.page[tid]);
-      else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
-    }
-    if (tid == 0) ctl.sel_count = 0;
-    if (plan.fast_and) {
-      // cache this row group's leaf LUTs (one byte per dictionary entry) in shared memory
-      for (uint32_t l = 0; l < plan.nleaves; l++) {
-        const DevLeaf& lf = plan.leaves[l];
-        const DevChunk ch = a.chunks[item.rg * ncols + lf.col];
-        const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
-        if (tid == 0) ctl.lut_smem[l] = fits;
-        if (fits) {
-          const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
-          uint8_t* dst = smem + L.lutc + l * kLutCacheBytes;
-          for (uint32_t i = tid; i < ch.dict_n; i += kScanThreads) dst[i] = src[i];
-        }
-      }
-    }
-    __syncthreads();
-
-    uint32_t rows_left = item.nrows;
-    uint32_t r_item = 0;
-    uint32_t buf = 0;
-    if (tid == 0) issue_windows(ctl, L, smem, a.arena, ncols, buf, rows_left);
-    __syncthreads();
-
-    while (rows_left > 0) {
-      // ---- 1-3. control, WARP 0 ONLY (the other warps park at the barrier and spend no issue
-      //      slots): wait for the staged bytes, walk the run headers (one lane per column),
-      //      commit the cursors, prefetch the next slab, choose the row pass ----
-      StreamState snap_def, snap_val;
-      DeltaState snap_dl;
-      if (warp_id() == 0) {
-        if (lane_id() == 0) mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
-        __syncwarp();
-        const uint32_t R0w = ctl.target;
-        if (walker) {
-          ColCursor& c = ctl.cur[mycol];
-          SlabCol& s = ctl.slab[mycol];
-          snap_def = c.def;
-          snap_val = c.val;
-          snap_dl = c.dl;
-          uint32_t rc = R0w;
-          s.ndef = 0;
-          s.nval = 0;
-          s.all_valid = 1;
-          s.nv = c.present ? R0w : 0;
-          if (c.present) {
-            if (c.has_def) {
-              Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
-              DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
-              uint32_t n = 0;
-              uint32_t got = walk_stream(c.def, w, R0w, dir, n, kMaxDirEntries);
-              s.ndef = n;
-              uint32_t allv = 1;
-              for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
-              s.all_valid = allv;
-              rc = got;
-              if (!allv) ctl.any_nulls = 1;
-            }
-            if (s.all_valid && rc == R0w && PQB_ENC_HAS_WINDOW(c.enc)) {
-              Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
-              uint32_t n = 0;
-              rc = c.enc == DE_DELTA
-                       ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
-              s.nval = n;
-              if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
-            }
-          }
-          if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
-        }
-        __syncwarp();
-        const bool general = ctl.rmin_all < R0w || ctl.any_nulls;
-        if (!general) {
-          if (walker) {  // freeze this slab's view, advance the cursor
-            ColCursor& c = ctl.cur[mycol];
-            SlabCol& s = ctl.slab[mycol];
-            s.val_base = c.val_base;
-            s.vals_done = c.vals_done;
-            s.enc = c.enc;
-            s.bw = c.val.bw;
-            if (c.present) {
-              c.vals_done += s.nv;
-              c.page_rows_left -= R0w;
-              if (c.page_rows_left == 0 && rows_left > R0w) {
-                if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
-                else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
-              }
-            }
-          }
-          __syncwarp();
-          if (lane_id() == 0) {
-            uint32_t mode = MODE_GENERIC, has_delta = 0;
-            bool fa = plan.fast_and != 0;
-            for (uint32_t c = 0; c < ncols; c++) has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
-            for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
-              const SlabCol& s = ctl.slab[plan.leaves[l].col];
-              fa = s.present && s.enc == DE_DICT && s.nval > 0;
-            }
-            if (fa) mode = MODE_FAST_AND;
-            else if (plan.row_major) mode = MODE_ROW_MAJOR;
-            ctl.mode = mode;
-            ctl.has_delta = has_delta;
-            ctl.R = R0w;
-            if (!ctl.error && rows_left > R0w) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R0w);
-          }
-        } else if (lane_id() == 0) {
-          ctl.mode = MODE_GENERAL_WALK;
-          ctl.R = R0w;
-        }
-      }
-      phases ^= 1u << buf;
-      __syncthreads();
-      uint32_t mode = ctl.mode;
-      uint32_t R = ctl.R;
-      bool has_nulls = false;
-      uint32_t has_delta = ctl.has_delta;
-      if (mode == MODE_GENERAL_WALK) {  // uniform: NULLs or an exhausted window -> the general walk, all threads
-        if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
-        __syncthreads();
-        R = general_walk(ctl, L, smem, ncols, buf, R, snap_def, snap_val, snap_dl);
-        if (R == 0) {  // no progress possible: corrupt page
-          if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
-          break;
-        }
-        if (walker) {
-          ColCursor& c = ctl.cur[mycol];
-          SlabCol& s = ctl.slab[mycol];
-          s.val_base = c.val_base;
-          s.vals_done = c.vals_done;
-          s.enc = c.enc;
-          s.bw = c.val.bw;
-          if (c.present) {
-            c.vals_done += s.nv;
-            c.page_rows_left -= R;
-            if (c.page_rows_left == 0 && rows_left > R) {
-              if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
-              else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
-            }
-          }
-        }
-        __syncthreads();
-        if (!ctl.error && tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
-        has_delta = 0;
-        for (uint32_t c = 0; c < ncols; c++) {
-          has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
-          has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
-        }
-        mode = MODE_GENERIC;
-        if (!has_nulls) {
-          bool fa = plan.fast_and != 0;
-          for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
-            const SlabCol& s = ctl.slab[plan.leaves[l].col];
-            fa = s.present && s.enc == DE_DICT && s.nval > 0;
-          }
-          if (fa) mode = MODE_FAST_AND;
-          else if (plan.row_major) mode = MODE_ROW_MAJOR;
-        }
-      }
-      if (ctl.error) break;
-
-      // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
-      if (has_delta)
-        for (uint32_t c = 0; c < ncols; c++)
-          if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
-      const uint32_t nwords = (R + 31) >> 5;
-      uint32_t cnt = 0;
-      const bool fast_and = mode == MODE_FAST_AND;
-      if (fast_and) {
-        // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
-        cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
-      } else if (mode == MODE_ROW_MAJOR) {
-        // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
-        cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
-      } else {
+  uint32_t cnt = 0;
       // ---- 4. (general) unpack: fused index -> leaf bits where possible, else stage indices ----
-      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
-      __syncthreads();
+      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kRowThreads) leafT[w] = 0;
+      row_sync();
       for (uint32_t c = 0; c < ncols; c++) {
-        const SlabCol& s = ctl.slab[c];
+        const SlabCol& s = slab[c];
         if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
         uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
-        const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
+        const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
         const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
         // leaves of this column that a dictionary LUT answers (host precomputed lists)
         const uint32_t nlut = plan.col_nlut[c];
@@ -1031,13 +835,13 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           dir_to_idx(dir, s.nval, win, s.bw, idx);
         }
       }
-      __syncthreads();
+      row_sync();
 
       // ---- 5. leaves the fused pass did not answer: PLAIN pages, NULL-carrying slabs, booleans ----
       for (uint32_t l = 0; l < plan.nleaves; l++) {
         const DevLeaf& lf = plan.leaves[l];
         if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
-        const SlabCol& s = ctl.slab[lf.col];
+        const SlabCol& s = slab[lf.col];
         if (!s.present) continue;                                 // all NULL: T stays 0
         if (s.enc == DE_DICT && s.all_valid && plan.col_nlut[lf.col] <= 2) continue;  // answered by the fused pass
         const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
@@ -1049,7 +853,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         const int64_t lit = lf.lit_i64;
         const int64_t litk = f64_order_key((uint64_t)lf.lit_i64);
         const uint32_t op = lf.cmp;
-        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
+        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kRowThreads) {
           uint32_t r = r0 + lane_id();
           bool t = false;
           if (r < R) {
@@ -1065,10 +869,10 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           if (lane_id() == 0) Tw[r0 >> 5] = tw;
         }
       }
-      __syncthreads();
+      row_sync();
 
       // ---- 6. Kleene combine on words -> selection; filter mode consumes right here ----
-      for (uint32_t w = tid; w < nwords; w += kScanThreads) {
+      for (uint32_t w = tid; w < nwords; w += kRowThreads) {
         uint32_t st_t[kPredStack], st_n[kPredStack];
         int sp = 0;
         const uint32_t rm = row_mask(w, R);
@@ -1077,7 +881,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           const DevPredOp op = plan.pred[i];
           if (op.kind == PK_LEAF) {
             const DevLeaf& lf = plan.leaves[op.arg];
-            const SlabCol& s = ctl.slab[lf.col];
+            const SlabCol& s = slab[lf.col];
             uint32_t V = !s.present ? 0u : (s.all_valid ? 0xffffffffu : smem_at<uint32_t>(smem, L.valid[lf.col])[w]);
             uint32_t t, n;
             if (lf.kind == LK_IS_NULL) { t = ~V; n = 0; }
@@ -1111,8 +915,8 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         else {
           cnt += __popc(sel);
           if (plan.write_bitmap && sel) {
-            uint32_t pos = r_item + w * 32;
-            uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+            uint32_t pos = v.r_item + w * 32;
+            uint32_t* dst = a.bitmap + v.bitmap_word0 + (pos >> 5);
             uint32_t sh = pos & 31;
             if (sh == 0) *dst = sel;  // slabs are word aligned except after a pathological shrink
             else {
@@ -1124,14 +928,14 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         }
       }
       if (agg_mode) {
-        __syncthreads();
-        for (uint32_t r = tid; r < R; r += kScanThreads) {
+        row_sync();
+        for (uint32_t r = tid; r < R; r += kRowThreads) {
           if (!((selw[r >> 5] >> (r & 31)) & 1)) continue;
           cnt++;
           uint32_t slot = 0;
           for (uint32_t k = 0; k < plan.nkeys; k++) {
             const DevKey& key = plan.keys[k];
-            const SlabCol& s = ctl.slab[key.col];
+            const SlabCol& s = slab[key.col];
             RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
             uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
             if (rv.valid) {
@@ -1144,7 +948,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           for (uint32_t g = 0; g < plan.naggs; g++) {
             const DevAgg& ag = plan.aggs[g];
             if (ag.fn == AG_COUNT_STAR) continue;
-            const SlabCol& s = ctl.slab[ag.col];
+            const SlabCol& s = slab[ag.col];
             RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
             if (!rv.valid) continue;
             if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -1155,27 +959,320 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           }
         }
       }
-      }  // general row phase
-      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
+  return cnt;
+}
 
-      rows_left -= R;
-      r_item += R;
-      buf ^= 1;
-      __syncthreads();
-    }  // slabs
-    __syncthreads();
-    if (ctl.error) break;
-    if (tid == 0) {
-      if (a.item_counts) a.item_counts[item_id] = ctl.sel_count;
-      if (ctl.sel_count) atomicAdd(&a.counters[0], (unsigned long long)ctl.sel_count);
+
+__global__ void __launch_bounds__(kScanThreads, 3)
+k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  ScanCtl& ctl = *reinterpret_cast<ScanCtl*>(smem);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = lane_id();
+  const uint32_t ncols = plan.ncols;
+  const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
+  const bool agg_mode = plan.mode == SM_AGG;
+  const bool is_ctl = warp_id() == kCtlWarp;
+  const bool is_row = !is_ctl;
+  uint32_t mycol;
+  const bool walker = walker_of(ncols, mycol);
+
+  if (tid == 0) {
+    mbar_init(&ctl.mbar[0], 1);
+    mbar_init(&ctl.mbar[1], 1);
+    mbar_init(&ctl.full[0], 1);
+    mbar_init(&ctl.full[1], 1);
+    mbar_init(&ctl.empty[0], kRowWarps);
+    mbar_init(&ctl.empty[1], kRowWarps);
+    mbar_fence_init();
+    ctl.error = 0;
+    ctl.lut_rg[0] = ctl.lut_rg[1] = 0;
+  }
+  unsigned long long* sacc = smem_at<unsigned long long>(smem, L.acc);
+  if (agg_mode && plan.smem_acc && is_row) {
+    for (uint32_t i = tid; i < cells * plan.nslots; i += kRowThreads) {
+      uint32_t arr = i / plan.nslots;
+      unsigned long long init = 0;
+      if (arr >= 1 && arr < 1 + plan.n_acc) {
+        uint8_t k = plan.acc_init[arr - 1];
+        init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
+      }
+      sacc[i] = init;
     }
-  }  // items
+  }
+  __syncthreads();
+  unsigned long long* acc = (agg_mode && plan.smem_acc) ? sacc : a.acc;
+  const uint32_t nslots = plan.nslots;
 
+  // control-warp private state (uniform across its lanes)
+  bool have_item = false;
+  uint32_t item_id = 0, rows_left = 0, r_item = 0, item_rg = 0, item_word0 = 0;
+  uint64_t item_grow0 = 0;
+  unsigned long long my_selected = 0;  // row warps, lane 0
+
+  // slab sequence number s; buffers and mbarrier parities derive from it:
+  //   b = s & 1, every barrier of buffer b completes once per slab, parity (s >> 1) & 1
+  for (uint32_t s = 0;; s++) {
+    const uint32_t b = s & 1, par = (s >> 1) & 1;
+    SlabView& view = ctl.view[b];
+    SlabCol* slab = view.col;
+    StreamState snap_def, snap_val;
+    DeltaState snap_dl;
+    uint32_t R0w = 0;
+    if (is_ctl) {
+      // ---------------- control warp: prepare slab s ----------------
+      bool stop = false;
+      if (!have_item) {
+        uint32_t it = 0;
+        if (lane == 0) it = (uint32_t)atomicAdd(&a.counters[2], 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        // buffers b were last used by slab s-2
+        if (s >= 2) { if (lane == 0) mbar_wait(&ctl.empty[b], ((s - 2) >> 1) & 1); __syncwarp(); }
+        if (it >= plan.n_items || ctl.error) stop = true;
+        else {
+          item_id = it;
+          const DevItem& item = a.items[it];
+          item_rg = item.rg; item_word0 = item.bitmap_word0; item_grow0 = item.global_row0;
+          rows_left = item.nrows; r_item = 0;
+          if (lane < ncols) {
+            ColCursor& c = ctl.cur[lane];
+            const DevChunk ch = a.chunks[item.rg * ncols + lane];
+            c.present = ch.present;
+            c.page_end = ch.first_page + ch.n_pages;
+            if (ch.present) page_enter(c, a.pages, item.page[lane]);
+            else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
+          }
+          __syncwarp();
+          if (lane == 0) issue_windows(ctl, L, smem, a.arena, ncols, b, rows_left);
+          __syncwarp();
+          have_item = true;
+        }
+      }
+      if (stop) {
+        if (lane == 0) { view.mode = MODE_STOP; __threadfence_block(); mbar_arrive(&ctl.full[b]); }
+        break;
+      }
+      if (lane == 0) mbar_wait(&ctl.mbar[b], par);
+      __syncwarp();
+      // per-slab constants of the columns (the chunk of this row group)
+      if (lane < ncols) {
+        const DevChunk ch = a.chunks[item_rg * ncols + lane];
+        slab[lane].lut_base = ch.lut_base;
+        slab[lane].dict_off = ch.dict_off;
+        slab[lane].present = ch.present;
+      }
+      if (plan.fast_and && ctl.lut_rg[b] != item_rg + 1) {
+        // leaf LUTs of this row group -> lutc[b] (one byte per dictionary entry)
+        for (uint32_t l = 0; l < plan.nleaves; l++) {
+          const DevLeaf& lf = plan.leaves[l];
+          const DevChunk ch = a.chunks[item_rg * ncols + lf.col];
+          const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
+          if (lane == 0) ctl.lut_smem[b][l] = fits;
+          if (fits) {
+            const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
+            uint8_t* dst = smem + L.lutc + (b * plan.nleaves + l) * kLutCacheBytes;
+            for (uint32_t i = lane; i < ch.dict_n; i += 32) dst[i] = src[i];
+          }
+        }
+        if (lane == 0) ctl.lut_rg[b] = item_rg + 1;
+      }
+      __syncwarp();
+      R0w = ctl.target;
+      const uint32_t buf = b;
+      if (walker) {  // fast walk: definition levels say "no NULLs" -> walk the value stream right away
+        ColCursor& c = ctl.cur[mycol];
+        SlabCol& sc = slab[mycol];
+        snap_def = c.def;
+        snap_val = c.val;
+        snap_dl = c.dl;
+        uint32_t rc = R0w;
+        sc.ndef = 0;
+        sc.nval = 0;
+        sc.all_valid = 1;
+        sc.nv = c.present ? R0w : 0;
+        if (c.present) {
+          if (c.has_def) {
+            Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
+            DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
+            uint32_t n = 0;
+            uint32_t got = walk_stream(c.def, w, R0w, dir, n, kMaxDirEntries);
+            sc.ndef = n;
+            uint32_t allv = 1;
+            for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
+            sc.all_valid = allv;
+            rc = got;
+            if (!allv) ctl.any_nulls = 1;
+          }
+          if (sc.all_valid && rc == R0w && PQB_ENC_HAS_WINDOW(c.enc)) {
+            Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
+            uint32_t n = 0;
+            rc = c.enc == DE_DELTA
+                     ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol][buf]), n, kMaxDeltaEntries)
+                     : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n, kMaxDirEntries - 2);
+            sc.nval = n;
+            if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n);
+          }
+        }
+        if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
+      }
+      __syncwarp();
+      const bool general = ctl.rmin_all < R0w || ctl.any_nulls;
+      if (!general) {
+        if (walker) {  // freeze this slab's view, advance the cursor
+          ColCursor& c = ctl.cur[mycol];
+          SlabCol& sc = slab[mycol];
+          sc.val_base = c.val_base;
+          sc.vals_done = c.vals_done;
+          sc.enc = c.enc;
+          sc.bw = c.val.bw;
+          if (c.present) {
+            c.vals_done += sc.nv;
+            c.page_rows_left -= R0w;
+            if (c.page_rows_left == 0 && rows_left > R0w) {
+              if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+              else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t mode = MODE_GENERIC, has_delta = 0;
+          bool fa = plan.fast_and != 0;
+          for (uint32_t c = 0; c < ncols; c++) has_delta |= slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv;
+          for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+            const SlabCol& sc = slab[plan.leaves[l].col];
+            fa = sc.present && sc.enc == DE_DICT && sc.nval > 0;
+          }
+          if (fa) mode = MODE_FAST_AND;
+          else if (plan.row_major) mode = MODE_ROW_MAJOR;
+          if (ctl.error) mode = MODE_STOP;
+          view.mode = mode;
+          view.has_delta = has_delta;
+          view.R = R0w;
+          view.item_id = item_id;
+          view.r_item = r_item;
+          view.bitmap_word0 = item_word0;
+          view.global_row0 = item_grow0;
+          view.rg = item_rg;
+          __threadfence_block();
+          mbar_arrive(&ctl.full[b]);
+        }
+        __syncwarp();
+        if (ctl.error) break;
+        rows_left -= R0w;
+        r_item += R0w;
+        if (rows_left == 0) have_item = false;
+        else {
+          // prefetch slab s+1 into buffers b^1, free once slab s-1 was consumed
+          if (s >= 1) { if (lane == 0) mbar_wait(&ctl.empty[b ^ 1], ((s - 1) >> 1) & 1); __syncwarp(); }
+          if (lane == 0) issue_windows(ctl, L, smem, a.arena, ncols, b ^ 1, rows_left);
+          __syncwarp();
+        }
+        continue;  // the control warp never touches the row phase of a fast slab
+      }
+      if (lane == 0) {
+        view.mode = MODE_GENERAL_WALK;
+        view.R = R0w;
+        view.item_id = item_id;
+        view.r_item = r_item;
+        view.bitmap_word0 = item_word0;
+        view.global_row0 = item_grow0;
+        view.rg = item_rg;
+        __threadfence_block();
+        mbar_arrive(&ctl.full[b]);
+      }
+      __syncwarp();
+    } else {
+      // ---------------- row warps: wait until slab s is published ----------------
+      if (lane == 0) mbar_wait(&ctl.full[b], par);
+      __syncwarp();
+    }
+    uint32_t mode = view.mode;
+    if (mode == MODE_STOP) break;
+    uint32_t R = view.R;
+    uint32_t has_delta = view.has_delta;
+    const uint32_t buf = b;
+    if (mode == MODE_GENERAL_WALK) {
+      // ---- NULLs or an exhausted window: the general walk needs every thread; synchronous ----
+      __syncthreads();
+      if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
+      __syncthreads();
+      R = general_walk(ctl, slab, L, smem, ncols, buf, R, snap_def, snap_val, snap_dl);
+      if (R == 0) {  // no progress possible: corrupt page
+        if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
+        break;
+      }
+      if (walker) {
+        ColCursor& c = ctl.cur[mycol];
+        SlabCol& sc = slab[mycol];
+        sc.val_base = c.val_base;
+        sc.vals_done = c.vals_done;
+        sc.enc = c.enc;
+        sc.bw = c.val.bw;
+        if (c.present) {
+          c.vals_done += sc.nv;
+          c.page_rows_left -= R;
+          if (c.page_rows_left == 0 && rows_left > R) {
+            if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+            else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+          }
+        }
+      }
+      __syncthreads();
+      if (ctl.error) break;
+      bool has_nulls = false;
+      has_delta = 0;
+      for (uint32_t c = 0; c < ncols; c++) {
+        has_nulls |= slab[c].present && !slab[c].all_valid;
+        has_delta |= slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv;
+      }
+      mode = MODE_GENERIC;
+      if (!has_nulls) {
+        bool fa = plan.fast_and != 0;
+        for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+          const SlabCol& sc = slab[plan.leaves[l].col];
+          fa = sc.present && sc.enc == DE_DICT && sc.nval > 0;
+        }
+        if (fa) mode = MODE_FAST_AND;
+        else if (plan.row_major) mode = MODE_ROW_MAJOR;
+      }
+      if (is_ctl) {
+        rows_left -= R;
+        r_item += R;
+        if (rows_left == 0) have_item = false;
+        else {
+          if (s >= 1) { if (lane == 0) mbar_wait(&ctl.empty[b ^ 1], ((s - 1) >> 1) & 1); __syncwarp(); }
+          if (lane == 0) issue_windows(ctl, L, smem, a.arena, ncols, b ^ 1, rows_left);
+          __syncwarp();
+        }
+        continue;
+      }
+    }
+    // ---------------- row phase (row warps only) ----------------
+    if (has_delta)
+      for (uint32_t c = 0; c < ncols; c++)
+        if (slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv) delta_decode_scan(ctl, slab, L, smem, c, buf);
+    uint32_t cnt = 0;
+    if (mode == MODE_FAST_AND) cnt = fast_and_rows(plan, ctl, slab, L, smem, a, view, buf, R, acc, agg_mode);
+    else if (mode == MODE_ROW_MAJOR) cnt = fast_rows(plan, ctl, slab, L, smem, a, view, buf, R, acc, agg_mode);
+    else cnt = generic_rows(plan, ctl, slab, view, L, smem, a, buf, R, acc, agg_mode);
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+      if (cnt) {
+        if (a.item_counts) atomicAdd(&a.item_counts[view.item_id], cnt);
+        my_selected += cnt;
+      }
+      __threadfence_block();
+      mbar_arrive(&ctl.empty[b]);  // buffers b may be refilled
+    }
+    __syncwarp();
+  }
+
+  if (is_row && lane == 0 && my_selected) atomicAdd(&a.counters[0], my_selected);
   // ---- flush the CTA-private accumulator table ----
   __syncthreads();
-  if (agg_mode && plan.smem_acc && !ctl.error) {
-    for (uint32_t slot = tid; slot < nslots; slot += kScanThreads) {
+  if (agg_mode && plan.smem_acc && !ctl.error && is_row) {
+    for (uint32_t slot = tid; slot < nslots; slot += kRowThreads) {
       unsigned long long rows = sacc[slot];
       if (rows == 0) continue;
       atomicAdd(&a.acc[slot], rows);
