@@ -424,6 +424,8 @@ void Query::run(const PqQueryDesc& d) {
   {
     const char* rm = getenv("PQB_ROW_MAJOR");  // experiment switch: register-only row-major pass for no-NULL slabs
     plan.row_major = rm && rm[0] == '1';
+    const char* ds = getenv("PQB_SYNC_CTL");
+    plan.debug_sync = ds && ds[0] == '1';
   }
   {
     // conjunction of 1-4 CMP/LIKE leaves (folded TRUE constants are neutral): specialised row pass

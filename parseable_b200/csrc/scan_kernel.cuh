@@ -121,6 +121,7 @@ struct ScanCtl {
   ColCursor cur[kMaxCols];
   uint64_t full[2], empty[2];               // control -> rows "slab published", rows -> control "slab consumed"
   uint32_t lut_rg[2];                       // row group (+1) whose LUTs sit in lutc[b]
+  int64_t dl_last[kMaxCols];                // DELTA pages: value of the last row decoded so far (row warps)
   SlabView view[2];
 };
 
@@ -341,7 +342,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, SlabCol* slab, c
   }
   row_sync();
   // a slab that starts a page begins with the page's first value (absolute): no carry
-  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : s.dl_last;
+  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : ctl.dl_last[c];
   constexpr uint32_t kPer = kSlabRows / kRowThreads;
   const uint32_t b = threadIdx.x * kPer;
   int64_t loc[kPer];
@@ -366,7 +367,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, SlabCol* slab, c
   for (uint32_t i = 0; i < kPer; i++)
     if (b + i < nv) vals[b + i] = int64_t(uint64_t(base) + uint64_t(loc[i]));
   row_sync();
-  if (threadIdx.x == 0 && nv) s.dl_last = vals[nv - 1];
+  if (threadIdx.x == 0 && nv) ctl.dl_last[c] = vals[nv - 1];
   row_sync();
 }
 
@@ -1159,6 +1160,10 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         }
         __syncwarp();
         if (ctl.error) break;
+        if (plan.debug_sync) {  // PQB_SYNC_CTL=1: no overlap between control and row warps (race bisection)
+          if (lane == 0) mbar_wait(&ctl.empty[b], par);
+          __syncwarp();
+        }
         rows_left -= R0w;
         r_item += R0w;
         if (rows_left == 0) have_item = false;
@@ -1184,7 +1189,13 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       __syncwarp();
     } else {
       // ---------------- row warps: wait until slab s is published ----------------
-      if (lane == 0) mbar_wait(&ctl.full[b], par);
+      if (lane == 0) {
+        mbar_wait(&ctl.full[b], par);
+        // observe the TMA completion of this slab's windows directly as well: the bulk copies were
+        // written through the async proxy, and this wait is what makes them visible to this warp
+        // (a STOP view carries no windows)
+        if (*reinterpret_cast<volatile uint32_t*>(&view.mode) != MODE_STOP) mbar_wait(&ctl.mbar[b], par);
+      }
       __syncwarp();
     }
     uint32_t mode = view.mode;

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <thread>
 
+#include "decomp_kernels.cuh"
 #include "engine.hpp"
 
 namespace pqb {
@@ -273,7 +274,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   }
   // page-header walk of one column chunk -> DevPage records (runs on worker threads, after the
   // H2D copies were queued, so host parsing overlaps the PCIe transfer)
-  struct WalkJob { uint32_t rg; uint32_t col; uint32_t file; };
+  struct WalkJob { uint32_t rg; uint32_t col; uint32_t file; std::vector<DevPage> prebuilt; bool compressed = false; };
   std::vector<WalkJob> jobs;
   auto walk_chunk = [](TableChunk& tc, const HostFile& hf, const std::string& colname, uint32_t rg_rows,
                        std::vector<DevPage>& out) {
@@ -372,7 +373,9 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         }
   };
   struct Copy { uint32_t file; uint64_t src_off; uint64_t dst_off; uint64_t bytes; };
-  std::vector<Copy> copies;
+  std::vector<Copy> copies, ccopies;   // -> arena, -> compressed staging buffer
+  std::vector<DecompJob> djobs;
+  uint64_t comp = 0;
   uint64_t arena = 0;
   uint64_t global_row = 0;
   uint64_t global_rg = 0;
@@ -421,21 +424,65 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         TableChunk& tc = trg.chunks[c];
         if (leaf_of[c] < 0) continue;
         const ColumnChunkMeta& cm = g.columns[leaf_of[c]];
-        if (cm.codec != CODEC_UNCOMPRESSED)
-          throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page compression codec " +
-                                              std::to_string(cm.codec) + " is not decoded on the GPU yet (write with P_PARQUET_COMPRESSION_ALGO=uncompressed)");
+        const bool compressed = cm.codec != CODEC_UNCOMPRESSED;
+        if (compressed && cm.codec != CODEC_LZ4_RAW && cm.codec != CODEC_SNAPPY)
+          throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page compression codec " + std::to_string(cm.codec) +
+                                              " is not decoded on the GPU (LZ4_RAW, SNAPPY and UNCOMPRESSED are)");
         tc.present = true;
         tc.leaf = leaf_of[c];
         tc.meta = &cm;
         tc.file_off = uint64_t(cm.start());
         tc.bytes = uint64_t(cm.total_compressed_size);
         if (tc.file_off + tc.bytes > hf.size) throw Error(PQ_ERR_CORRUPT, "column chunk outside the file");
+        chunk_bytes += tc.bytes;
+        if (compressed) {
+          // the chunk's bytes go to a staging buffer; every page is decoded into its own arena slot
+          const uint64_t coff = comp + ((uintptr_t(hf.data) + tc.file_off) & 15);
+          comp = (coff + tc.bytes + 255) & ~255ull;
+          ccopies.push_back({fi, tc.file_off, coff, tc.bytes});
+          std::vector<PageInfo> pis;
+          try { pis = walk_pages(hf.data + tc.file_off, tc.bytes, cm.num_values); }
+          catch (const std::exception& e) { throw Error(PQ_ERR_CORRUPT, col_names[c] + ": " + e.what()); }
+          WalkJob wj{uint32_t(row_groups.size()), uint32_t(c), fi, {}, true};
+          const LeafColumn& leaf = hf.meta.leaves[leaf_of[c]];
+          uint32_t first_row = 0;
+          tc.arena_off = arena;
+          for (const PageInfo& pi : pis) {
+            const uint64_t slot = (arena + 15) & ~15ull;
+            arena = slot + pi.uncompressed_size + 16;
+            if (pi.type == PAGE_DICTIONARY) {
+              tc.dict_off = slot; tc.dict_len = pi.uncompressed_size; tc.dict_n = pi.num_values;
+            } else if (pi.type == PAGE_DATA) {
+              DevPage dp{};
+              dp.off = slot; dp.len = pi.uncompressed_size; dp.num_rows = pi.num_values; dp.first_row = first_row;
+              first_row += pi.num_values;
+              dp.def_len = leaf.max_def > 0 ? 0xffffffffu : 0;   // resolved by k_page_fixup from the decoded bytes
+              switch (pi.encoding) {
+                case ENC_PLAIN: dp.enc = DE_PLAIN; tc.has_plain_pages = true; break;
+                case ENC_RLE_DICTIONARY: case ENC_PLAIN_DICTIONARY: dp.enc = DE_DICT; tc.has_dict_pages = true; break;
+                case ENC_DELTA_BINARY_PACKED: dp.enc = DE_DELTA; tc.has_delta_pages = true; break;
+                case ENC_RLE:
+                  if (leaf.phys_type != PT_BOOLEAN) throw Error(PQ_ERR_UNSUPPORTED, "RLE value encoding on a non-boolean column");
+                  dp.enc = DE_RLE_BOOL; tc.has_dict_pages = true; break;
+                default: throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page encoding " + std::to_string(pi.encoding) + " not supported");
+              }
+              wj.prebuilt.push_back(dp);
+            } else if (pi.type == PAGE_DATA_V2) {
+              throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': compressed data page v2 (Parseable writes v1)");
+            } else continue;
+            djobs.push_back({coff + pi.offset_in_chunk + pi.header_len, slot, pi.compressed_size, pi.uncompressed_size,
+                             uint32_t(pi.compressed_size == pi.uncompressed_size && cm.codec == CODEC_SNAPPY ? cm.codec : cm.codec), 0});
+          }
+          if (first_row != trg.num_rows) throw Error(PQ_ERR_CORRUPT, col_names[c] + ": page rows do not add up to the row group's");
+          arena = (arena + 64 + 255) & ~255ull;
+          jobs.push_back(std::move(wj));
+          continue;
+        }
         // same 16-byte phase as the source bytes: the gather kernel moves whole 16-byte vectors
         tc.arena_off = arena + ((uintptr_t(hf.data) + tc.file_off) & 15);
         arena = (tc.arena_off + tc.bytes + 64 + 255) & ~255ull;
         copies.push_back({fi, tc.file_off, tc.arena_off, tc.bytes});
-        chunk_bytes += tc.bytes;
-        jobs.push_back({uint32_t(row_groups.size()), uint32_t(c), fi});
+        jobs.push_back({uint32_t(row_groups.size()), uint32_t(c), fi, {}, false});
       }
       total_rows += trg.num_rows;
       row_groups.push_back(std::move(trg));
@@ -449,8 +496,11 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   PQB_CUDA(cudaMallocAsync((void**)&d_arena, arena_bytes, stream));
   // tail slack must be defined (walkers may look at it)
   PQB_CUDA(cudaMemsetAsync(d_arena + arena, 0, arena_bytes - arena, stream));
+  uint8_t* d_comp = nullptr;   // compressed chunks wait here for k_decompress_pages
+  if (comp) PQB_CUDA(cudaMallocAsync((void**)&d_comp, comp + 256, stream));
 
   // ---- upload: straight from pinned caller buffers, else staged through pinned memory ----
+  auto upload_to = [&](const std::vector<Copy>& copies, uint8_t* d_arena) {
   std::vector<Copy> staged;
   std::vector<size_t> staged_orig;
   std::vector<char> file_pinned(files.size(), 0);
@@ -547,6 +597,19 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       cudaEventDestroy(ring_ev[r]);
     }
   }
+  };
+  upload_to(copies, d_arena);
+  if (!ccopies.empty()) upload_to(ccopies, d_comp);
+  DecompJob* d_djobs = nullptr;
+  unsigned long long* d_dflag = nullptr;
+  if (!djobs.empty()) {
+    PQB_CUDA(cudaMallocAsync((void**)&d_djobs, djobs.size() * sizeof(DecompJob), stream));
+    PQB_CUDA(cudaMallocAsync((void**)&d_dflag, 8, stream));
+    PQB_CUDA(cudaMemsetAsync(d_dflag, 0, 8, stream));
+    PQB_CUDA(cudaMemcpyAsync(d_djobs, djobs.data(), djobs.size() * sizeof(DecompJob), cudaMemcpyHostToDevice, stream));
+    k_decompress_pages<<<uint32_t((djobs.size() + 3) / 4), 128, 0, stream>>>(d_djobs, uint32_t(djobs.size()), d_comp, d_arena, d_dflag);
+    PQB_CUDA(cudaGetLastError());
+  }
   // ---- page walks, in parallel, while the copies above are in flight ----
   {
     std::vector<std::vector<DevPage>> out(jobs.size());
@@ -557,6 +620,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         size_t j = next.fetch_add(1);
         if (j >= jobs.size()) break;
         const WalkJob& jb = jobs[j];
+        if (jb.compressed) { out[j] = jb.prebuilt; continue; }
         try {
           walk_chunk(row_groups[jb.rg].chunks[jb.col], *files[jb.file], col_names[jb.col], row_groups[jb.rg].num_rows, out[j]);
         } catch (...) { errs[j] = std::current_exception(); }
@@ -583,6 +647,42 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   if (!pages.empty()) {
     PQB_CUDA(cudaMallocAsync((void**)&d_pages, pages.size() * sizeof(DevPage), stream));
     PQB_CUDA(cudaMemcpyAsync(d_pages, pages.data(), pages.size() * sizeof(DevPage), cudaMemcpyHostToDevice, stream));
+  }
+  if (!djobs.empty()) {
+    // decoded pages: fetch the two bytes the host normally reads from the file (def-level length, index bit width)
+    std::vector<uint32_t> fix;
+    for (size_t j = 0; j < jobs.size(); j++)
+      if (jobs[j].compressed) {
+        const TableChunk& tc = row_groups[jobs[j].rg].chunks[jobs[j].col];
+        for (uint32_t k = 0; k < tc.pages.n_pages; k++) fix.push_back(tc.pages.first_page + k);
+      }
+    if (!fix.empty()) {
+      uint32_t* d_fix = nullptr;
+      PQB_CUDA(cudaMallocAsync((void**)&d_fix, fix.size() * 4, stream));
+      PQB_CUDA(cudaMemcpyAsync(d_fix, fix.data(), fix.size() * 4, cudaMemcpyHostToDevice, stream));
+      k_page_fixup<<<uint32_t((fix.size() + 127) / 128), 128, 0, stream>>>(d_pages, d_fix, uint32_t(fix.size()), d_arena, d_dflag);
+      PQB_CUDA(cudaGetLastError());
+      PQB_CUDA(cudaMemcpyAsync(pages.data(), d_pages, pages.size() * sizeof(DevPage), cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaFreeAsync(d_fix, stream));
+    }
+    unsigned long long flag = 0;
+    PQB_CUDA(cudaMemcpyAsync(&flag, d_dflag, 8, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    PQB_CUDA(cudaFreeAsync(d_djobs, stream));
+    PQB_CUDA(cudaFreeAsync(d_dflag, stream));
+    PQB_CUDA(cudaFreeAsync(d_comp, stream));
+    if (flag) throw Error(PQ_ERR_CORRUPT, "a compressed page did not decode to its declared size (LZ4_RAW / SNAPPY)");
+    for (size_t j = 0; j < jobs.size(); j++)
+      if (jobs[j].compressed) {
+        TableChunk& tc = row_groups[jobs[j].rg].chunks[jobs[j].col];
+        for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
+          const DevPage& dp = pages[tc.pages.first_page + k];
+          if (dp.enc == DE_DICT || dp.enc == DE_RLE_BOOL) {
+            if (dp.bit_width > 32) throw Error(PQ_ERR_CORRUPT, "dictionary index bit width > 32");
+            tc.max_bw = std::max<uint32_t>(tc.max_bw, dp.bit_width);
+          }
+        }
+      }
   }
   PQB_CUDA(cudaStreamSynchronize(stream));
 }

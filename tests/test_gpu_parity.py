@@ -303,11 +303,38 @@ def test_errors_are_codes_not_crashes(env, data_dir):
     with pytest.raises(QueryError) as ei:
         prov.scan(filters=[col("level") == 5], count_only=True)
     assert ei.value.code == L.PQ_ERR_INVALID_ARG
-    lz4 = os.path.join(data_dir, "lz4.parquet")
-    synth.write_logs16(lz4, n_row_groups=1, rows_per_group=10_000, compression="LZ4_RAW", columns=["level", "status"])
+    zstd = os.path.join(data_dir, "zstd.parquet")
+    synth.write_logs16(zstd, n_row_groups=1, rows_per_group=10_000, compression="ZSTD", columns=["level", "status"])
     with pytest.raises(QueryError) as ei:
-        StandardTableProvider([lz4], schema={"level": pa.string()}).scan(filters=[col("level") == "INFO"], count_only=True)
+        StandardTableProvider([zstd], schema={"level": pa.string()}).scan(filters=[col("level") == "INFO"], count_only=True)
     assert ei.value.code == L.PQ_ERR_UNSUPPORTED and "codec" in ei.value.message
+
+
+@pytest.mark.parametrize("codec", ["LZ4_RAW", "SNAPPY"])
+@pytest.mark.parametrize("null_rate", [0.0, 0.02])
+def test_compressed_pages_decoded_on_gpu(data_dir, built, codec, null_rate):
+    """Parseable's default codec is lz4_raw (src/cli.rs:441-448), its CI pins snappy
+    (docker-compose-test.yaml:45): pages are decompressed on the GPU (one warp per page) into the
+    arena, then the same scan runs."""
+    p = os.path.join(data_dir, f"comp_{codec}_{int(null_rate * 100)}.parquet")
+    synth.write_logs16(p, n_row_groups=2, rows_per_group=60_000, null_rate=null_rate, compression=codec)
+    ora = Oracle.from_parquet(p)
+    prov = StandardTableProvider([p], schema=ora.table.schema)
+    for name in ("c2_level_and_latency", "plain_f64", "like_contains", "is_null", "deep", "c1_status_eq"):
+        flt = FILTERS[name]
+        got = prov.scan(filters=flt, count_only=True)
+        assert got.metrics["rows_selected"] == ora.count(flt), (codec, name)
+    assert got.metrics["bytes_scanned"] < got.metrics["algorithmic_bytes"]      # compressed bytes read < decoded bytes
+    flt = FILTERS["c2_level_and_latency"]
+    res = prov.scan(filters=flt)
+    ids = np.concatenate([b.column(0).to_numpy() for b in res.batches]) if res.batches else np.array([], np.int64)
+    assert np.array_equal(ids, ora.row_ids(flt))
+    keys, aggs, f = AGGS["c4_host_status_6aggs"]
+    assert_tables_equal(prov.aggregate(keys, aggs, f).table(), ora.group_by(keys, aggs, f), keys)
+    ts = ora.table["p_timestamp"].cast(pa.int64()).drop_null().to_numpy()
+    from parseable_b200.query import Timestamp
+    rng = [col("p_timestamp") >= Timestamp(int(np.quantile(ts, 0.4))), col("p_timestamp") < Timestamp(int(np.quantile(ts, 0.9)))]
+    assert prov.scan(filters=rng, count_only=True).metrics["rows_selected"] == ora.count(rng)
 
 
 def test_concurrent_queries_from_threads(env):
