@@ -1260,6 +1260,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       }
     }
     // ---------------- row phase (row warps only) ----------------
+    // the generic pass and the DELTA decode use block-shared scratch (leaf bitmaps, staging arrays):
+    // no row warp may start overwriting it while a slower one still reads the previous slab's
+    if (mode == MODE_GENERIC || has_delta) row_sync();
     if (has_delta)
       for (uint32_t c = 0; c < ncols; c++)
         if (slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv) delta_decode_scan(ctl, slab, L, smem, c, buf);
