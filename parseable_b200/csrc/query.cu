@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -425,7 +426,7 @@ void Query::run(const PqQueryDesc& d) {
     const char* rm = getenv("PQB_ROW_MAJOR");  // experiment switch: register-only row-major pass for no-NULL slabs
     plan.row_major = rm && rm[0] == '1';
     const char* ds = getenv("PQB_SYNC_CTL");
-    plan.debug_sync = ds && ds[0] == '1';
+    plan.debug_sync = ds ? uint32_t(atoi(ds)) : 0;   // bit 0: serialise control / rows, bit 1: every row lane waits
   }
   {
     // conjunction of 1-4 CMP/LIKE leaves (folded TRUE constants are neutral): specialised row pass
@@ -864,6 +865,7 @@ void Query::run(const PqQueryDesc& d) {
     PQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, kScanThreads, smem_total));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * occ));
+    if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));   // debugging aid
     PQB_CUDA(cudaEventRecord(t_scan.a, stream));
     k_scan<<<grid, kScanThreads, smem_total, stream>>>(plan, L, sa);
     PQB_CUDA(cudaEventRecord(t_scan.b, stream));
@@ -871,6 +873,14 @@ void Query::run(const PqQueryDesc& d) {
     launches++;
   }
 
+  if (getenv("PQB_DEBUG_ITEMS")) {
+    std::vector<uint32_t> ic(items.size());
+    PQB_CUDA(cudaMemcpyAsync(ic.data(), d_item_counts.p, ic.size() * 4, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < ic.size(); i++)
+      fprintf(stderr, "item %zu rg %u row0 %u nrows %u g0 %llu count %u\n", i, items[i].rg, items[i].row0, items[i].nrows,
+              (unsigned long long)items[i].global_row0, ic[i]);
+  }
   unsigned long long h_counters[4] = {0, 0, 0, 0};
   PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
   metrics.d2h_bytes += sizeof(h_counters);

@@ -1062,7 +1062,12 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         slab[lane].dict_off = ch.dict_off;
         slab[lane].present = ch.present;
       }
-      if (plan.fast_and && ctl.lut_rg[b] != item_rg + 1) {
+      // every lane must take the same decision: the lanes diverged just above, and lane 0 updates
+      // lut_rg at the end of the refill — read it once, between two warp barriers
+      __syncwarp();
+      const bool refill = plan.fast_and && ctl.lut_rg[b] != item_rg + 1;
+      __syncwarp();
+      if (refill) {
         // leaf LUTs of this row group -> lutc[b] (one byte per dictionary entry)
         for (uint32_t l = 0; l < plan.nleaves; l++) {
           const DevLeaf& lf = plan.leaves[l];
@@ -1160,7 +1165,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         }
         __syncwarp();
         if (ctl.error) break;
-        if (plan.debug_sync) {  // PQB_SYNC_CTL=1: no overlap between control and row warps (race bisection)
+        if (plan.debug_sync & 1) {  // PQB_SYNC_CTL=1: no overlap between control and row warps (race bisection)
           if (lane == 0) mbar_wait(&ctl.empty[b], par);
           __syncwarp();
         }
@@ -1189,7 +1194,10 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       __syncwarp();
     } else {
       // ---------------- row warps: wait until slab s is published ----------------
-      if (lane == 0) {
+      if (plan.debug_sync & 2) {
+        mbar_wait(&ctl.full[b], par);
+        if (*reinterpret_cast<volatile uint32_t*>(&view.mode) != MODE_STOP) mbar_wait(&ctl.mbar[b], par);
+      } else if (lane == 0) {
         mbar_wait(&ctl.full[b], par);
         // observe the TMA completion of this slab's windows directly as well: the bulk copies were
         // written through the async proxy, and this wait is what makes them visible to this warp
@@ -1262,7 +1270,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     // ---------------- row phase (row warps only) ----------------
     // the generic pass and the DELTA decode use block-shared scratch (leaf bitmaps, staging arrays):
     // no row warp may start overwriting it while a slower one still reads the previous slab's
-    if (mode == MODE_GENERIC || has_delta) row_sync();
+    if (mode == MODE_GENERIC || has_delta || (plan.debug_sync & 4)) row_sync();
     if (has_delta)
       for (uint32_t c = 0; c < ncols; c++)
         if (slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv) delta_decode_scan(ctl, slab, L, smem, c, buf);
