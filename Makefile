@@ -9,10 +9,11 @@ NCCL_INC  := $(if $(PY_NCCL),-I$(PY_NCCL)/include,)
 # process that also imports torch ends up with a single NCCL)
 NCCL_LIB  := $(if $(PY_NCCL),-L$(PY_NCCL)/lib -l:libnccl.so.2 -Xlinker -rpath -Xlinker $(PY_NCCL)/lib,-lnccl)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr $(NCCL_INC) -Iinclude
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr $(NCCL_INC) -Iinclude $(EXTRA)
 CSRC      := parseable_b200/csrc
-OBJDIR    := build
-LIB       := parseable_b200/libparseable_b200.so
+OBJDIR    ?= build
+LIB       ?= parseable_b200/libparseable_b200.so
+EXTRA     ?=
 
 CU_SRCS   := $(CSRC)/table.cu $(CSRC)/query.cu
 CPP_SRCS  := $(CSRC)/parquet_meta.cpp $(CSRC)/arrow_export.cpp $(CSRC)/capi.cpp $(CSRC)/comm.cpp

@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libparseable_b200.so")
+# PQB_LIB: load a differently tuned build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PQB_LIB") or os.path.join(_HERE, "libparseable_b200.so")
 
 PQ_OK, PQ_END_OF_STREAM = 0, 1
 PQ_ERR_INVALID_ARG, PQ_ERR_UNSUPPORTED, PQ_ERR_IO, PQ_ERR_CORRUPT, PQ_ERR_CUDA, PQ_ERR_OOM = -1, -2, -3, -4, -5, -6

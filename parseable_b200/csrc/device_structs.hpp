@@ -136,7 +136,6 @@ struct DevPlan {
   int8_t col_l1[kMaxCols];
   uint32_t row_major;          // 1: no-NULL slabs use the register-only row-major pass
   uint32_t fast_and;           // 1: the predicate is leaf AND leaf AND ... (1-4 CMP/LIKE leaves): specialised pass
-  uint32_t debug_sync;         // 1: control warp waits for the row warps every slab (debugging aid)
 };
 
 // Accumulator table layout (device, 8-byte cells, struct of arrays over nslots):

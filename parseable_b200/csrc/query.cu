@@ -425,8 +425,6 @@ void Query::run(const PqQueryDesc& d) {
   {
     const char* rm = getenv("PQB_ROW_MAJOR");  // experiment switch: register-only row-major pass for no-NULL slabs
     plan.row_major = rm && rm[0] == '1';
-    const char* ds = getenv("PQB_SYNC_CTL");
-    plan.debug_sync = ds ? uint32_t(atoi(ds)) : 0;   // bit 0: serialise control / rows, bit 1: every row lane waits
   }
   {
     // conjunction of 1-4 CMP/LIKE leaves (folded TRUE constants are neutral): specialised row pass
@@ -609,14 +607,12 @@ void Query::run(const PqQueryDesc& d) {
     L.idx[s] = (plan.cols[s].has_dict || plan.cols[s].has_delta) ? off : 0;
     off += plan.cols[s].has_delta ? kSlabRows * 8 : (plan.cols[s].has_dict ? kSlabRows * 4 : 0);
     L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
-    for (int b = 0; b < 2; b++) {
-      L.valdir[s][b] = off;
-      off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
-    }
+    L.valdir[s] = off;
+    off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
   }
   L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
   L.sel = off; off += kSlabWords * 4;
-  L.lutc = off; if (plan.fast_and) off += 2 * nleaves * kLutCacheBytes;
+  L.lutc = off; if (plan.fast_and) off += nleaves * kLutCacheBytes;
   off = align_up(off, 128);
   L.acc = off;
   const uint32_t smem_fixed = off;
@@ -842,7 +838,6 @@ void Query::run(const PqQueryDesc& d) {
   DevBuf<uint32_t> d_bitmap, d_item_counts;
   if (want_rows) { d_bitmap.alloc(std::max<uint32_t>(bitmap_words, 1), stream); d_bitmap.zero(); }
   d_item_counts.alloc(std::max<size_t>(items.size(), 1), stream);
-  d_item_counts.zero();  // row warps add their per-slab counts with atomics
   if (want_rows) algo_bytes += metrics.rows_scanned / 8;
   metrics.algorithmic_bytes = algo_bytes;
 
@@ -865,7 +860,10 @@ void Query::run(const PqQueryDesc& d) {
     PQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, kScanThreads, smem_total));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * occ));
-    if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));   // debugging aid
+    if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));   // debugging aid: forces several items per CTA
+    if (getenv("PQB_VERBOSE"))
+      fprintf(stderr, "[pqb] k_scan: %u CTAs x %d threads, %zu B smem/CTA, %d CTAs/SM, %zu items\n", grid, kScanThreads,
+              size_t(smem_total), occ, items.size());
     PQB_CUDA(cudaEventRecord(t_scan.a, stream));
     k_scan<<<grid, kScanThreads, smem_total, stream>>>(plan, L, sa);
     PQB_CUDA(cudaEventRecord(t_scan.b, stream));

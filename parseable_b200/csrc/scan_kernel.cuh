@@ -30,15 +30,16 @@
 
 namespace pqb {
 
-// 8 row warps do the data-parallel work of a slab; one more warp — the CONTROL warp — runs one
-// slab ahead: it waits for the TMA windows, walks the run headers, commits the cursors, prefetches
-// the next windows and publishes a SlabView.  Row warps and control warp meet through mbarriers
-// (full[b] / empty[b], double buffered), so the sequential part of the format never stalls the
-// wide part.
-constexpr int kRowWarps = 8;
-constexpr int kRowThreads = kRowWarps * 32;
-constexpr int kCtlWarp = kRowWarps;
-constexpr int kScanThreads = kRowThreads + 32;
+// tuning knobs (make EXTRA=-DPQB_SCAN_THREADS=128 ...): threads per CTA and the occupancy the
+// register allocator is asked to allow
+#ifndef PQB_SCAN_THREADS
+#define PQB_SCAN_THREADS 256
+#endif
+#ifndef PQB_SCAN_MIN_BLOCKS
+#define PQB_SCAN_MIN_BLOCKS 4
+#endif
+constexpr int kScanThreads = PQB_SCAN_THREADS;
+constexpr int kScanWarps = kScanThreads / 32;
 
 // byte offsets of the dynamic shared-memory regions, computed on the host
 struct SmemLayout {
@@ -50,11 +51,11 @@ struct SmemLayout {
   uint32_t rank[kMaxCols];    // uint32[kSlabWords]
   uint32_t idx[kMaxCols];     // uint32[kSlabRows]  (0: indices of this column are never staged)
   uint32_t defdir[kMaxCols];  // DirEntry[kMaxDirEntries]
-  uint32_t valdir[kMaxCols][2];  // DirEntry / DeltaEntry directory of the value stream, double buffered
+  uint32_t valdir[kMaxCols];
   uint32_t leafT;             // uint32[nleaves][kSlabWords + 2]
   uint32_t sel;               // uint32[kSlabWords]
   uint32_t acc;               // shared accumulator table
-  uint32_t lutc;              // uint8[2][nleaves][kLutCacheBytes]: leaf LUTs of the slab's row group, double buffered
+  uint32_t lutc;              // uint8[nleaves][kLutCacheBytes]: leaf LUTs of the current row group (fast AND path)
   uint32_t total;
 };
 constexpr int kLeafWords = kSlabWords + 2;
@@ -93,14 +94,7 @@ struct SlabCol {
   int64_t dl_last;          // DELTA pages: value of the last row decoded so far in this page
 };
 
-enum SlabMode : uint32_t { MODE_GENERIC = 0, MODE_FAST_AND = 1, MODE_ROW_MAJOR = 2, MODE_GENERAL_WALK = 3, MODE_STOP = 4 };
-
-// everything the row warps need to know about one slab, published by the control warp
-struct SlabView {
-  uint32_t mode, R, has_delta, item_id, r_item, bitmap_word0, rg, _pad;
-  uint64_t global_row0;
-  SlabCol col[kMaxCols];
-};
+enum SlabMode : uint32_t { MODE_GENERIC = 0, MODE_FAST_AND = 1, MODE_ROW_MAJOR = 2, MODE_GENERAL_WALK = 3 };
 
 struct ScanCtl {
   uint64_t mbar[2];
@@ -114,15 +108,12 @@ struct ScanCtl {
   uint32_t R;            // rows of the current slab
   uint32_t has_delta;    // some column of this slab is DELTA_BINARY_PACKED
   uint32_t rmin[kMaxCols];
-  int64_t scan_tmp[kRowWarps];             // DELTA prefix scan: per-warp totals
-  uint32_t wcur[kRowWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
-  uint32_t stk[kRowWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
-  uint32_t lut_smem[2][kMaxLeaves];            // fast AND path: leaf LUT of this item's row group is cached in smem
+  int64_t scan_tmp[kScanWarps];             // DELTA prefix scan: per-warp totals
+  uint32_t wcur[kScanWarps][kMaxCols];      // fast row pass: per warp, per column run-directory cursor
+  uint32_t stk[kScanWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
+  uint32_t lut_smem[kMaxLeaves];            // fast AND path: leaf LUT of this item's row group is cached in smem
   ColCursor cur[kMaxCols];
-  uint64_t full[2], empty[2];               // control -> rows "slab published", rows -> control "slab consumed"
-  uint32_t lut_rg[2];                       // row group (+1) whose LUTs sit in lutc[b]
-  int64_t dl_last[kMaxCols];                // DELTA pages: value of the last row decoded so far (row warps)
-  SlabView view[2];
+  SlabCol slab[kMaxCols];
 };
 
 __device__ __forceinline__ void page_enter(ColCursor& c, const DevPage* pages, uint32_t pg) {
@@ -194,7 +185,7 @@ __device__ __forceinline__ void dir_sentinels(DirEntry* dir, uint32_t n) {
 // expand a run directory of 1-bit values into a bitmap (OR into pre-zeroed words)
 __device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent, const uint32_t* win,
                                               uint32_t* bm) {
-  for (uint32_t e = warp_id(); e < nent; e += kRowWarps) {
+  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
     const DirEntry d = dir[e];
     for (uint32_t k = 0; k < d.count; k += 32) {
       uint32_t j = k + lane_id();
@@ -209,7 +200,7 @@ __device__ __forceinline__ void dir_to_bitmap(const DirEntry* dir, uint32_t nent
 // unpack a run directory of dictionary indices into idx[0..nv)
 __device__ __forceinline__ void dir_to_idx(const DirEntry* dir, uint32_t nent, const uint32_t* win, uint32_t bw,
                                            uint32_t* idx) {
-  for (uint32_t e = warp_id(); e < nent; e += kRowWarps) {
+  for (uint32_t e = warp_id(); e < nent; e += kScanWarps) {
     const DirEntry d = dir[e];
     if (d.kind) {
       for (uint32_t j = lane_id(); j < d.count; j += 32) idx[d.start + j] = bp_get(win, d.payload, bw, j);
@@ -234,7 +225,7 @@ __device__ __forceinline__ void dir_to_leafbits(const DirEntry* dir, uint32_t ne
   uint32_t e = 0;
   DirEntry d = dir[0];
   uint32_t next0 = nent > 1 ? uint32_t(dir[1].chunk0) : 0xffffffffu;
-  for (uint32_t q = warp_id(); q < nchunks; q += kRowWarps) {
+  for (uint32_t q = warp_id(); q < nchunks; q += kScanWarps) {
     while (q >= next0) {  // warp uniform; chunks are visited in increasing order
       e++;
       d = dir[e];
@@ -282,9 +273,6 @@ __device__ __forceinline__ uint32_t value_bool(const SlabCol& c, const uint8_t* 
   return (arena[c.val_base + (k >> 3)] >> (k & 7)) & 1;
 }
 
-// barrier among the row warps only (the control warp runs ahead and must not be waited for)
-__device__ __forceinline__ void row_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kRowThreads) : "memory"); }
-
 template <typename T>
 __device__ __forceinline__ T* smem_at(uint8_t* base, uint32_t off) {
   return reinterpret_cast<T*>(base + off);
@@ -324,26 +312,26 @@ __device__ __forceinline__ uint32_t row_mask(uint32_t w, uint32_t R) {
 // that one warp so the other warps park at the block barrier instead of burning issue slots.
 __device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
   col = lane_id();
-  return warp_id() == kCtlWarp && col < ncols;
+  return warp_id() == 0 && col < ncols;
 }
 
 
 // ---- DELTA_BINARY_PACKED: miniblock directory -> deltas -> block-wide inclusive scan -> values ----
-__device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf) {
-  SlabCol& s = slab[c];
+__device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf) {
+  SlabCol& s = ctl.slab[c];
   const uint32_t nv = s.nv;
   int64_t* vals = smem_at<int64_t>(smem, L.idx[c]);
-  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c][buf]);
+  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c]);
   const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
-  for (uint32_t e = warp_id(); e < s.nval; e += kRowWarps) {
+  for (uint32_t e = warp_id(); e < s.nval; e += kScanWarps) {
     const DeltaEntry d = dir[e];
     for (uint32_t j = lane_id(); j < d.count; j += 32)
       vals[d.start + j] = d.kind ? d.min_delta : int64_t(uint64_t(d.min_delta) + bp_get64(win, d.bitoff, d.bw, j));
   }
-  row_sync();
+  __syncthreads();
   // a slab that starts a page begins with the page's first value (absolute): no carry
-  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : ctl.dl_last[c];
-  constexpr uint32_t kPer = kSlabRows / kRowThreads;
+  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : s.dl_last;
+  constexpr uint32_t kPer = kSlabRows / kScanThreads;
   const uint32_t b = threadIdx.x * kPer;
   int64_t loc[kPer];
   int64_t sum = 0;
@@ -359,26 +347,26 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, SlabCol* slab, c
     if ((int)lane_id() >= o) incl = int64_t(uint64_t(incl) + uint64_t(t));
   }
   if (lane_id() == 31) ctl.scan_tmp[warp_id()] = incl;
-  row_sync();
+  __syncthreads();
   int64_t base = carry;
   for (uint32_t w = 0; w < warp_id(); w++) base = int64_t(uint64_t(base) + uint64_t(ctl.scan_tmp[w]));
   base = int64_t(uint64_t(base) + uint64_t(incl) - uint64_t(sum));
 #pragma unroll
   for (uint32_t i = 0; i < kPer; i++)
     if (b + i < nv) vals[b + i] = int64_t(uint64_t(base) + uint64_t(loc[i]));
-  row_sync();
-  if (threadIdx.x == 0 && nv) ctl.dl_last[c] = vals[nv - 1];
-  row_sync();
+  __syncthreads();
+  if (threadIdx.x == 0 && nv) s.dl_last = vals[nv - 1];
+  __syncthreads();
 }
 
 // ---- the no-NULL fast row pass --------------------------------------------------------------
 // Dictionary index of row r (== value r: the slab has no NULLs) of column c, straight from the
 // staged bytes through the run directory.  Control flow is warp uniform except the (rare) walk
 // across directory entries inside one 32-row word.
-__device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
+__device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
                                              uint32_t base_row, uint32_t r, bool in) {
-  const SlabCol& s = slab[c];
-  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
+  const SlabCol& s = ctl.slab[c];
+  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
   const uint32_t n = s.nval;
   uint32_t e = ctl.wcur[warp_id()][c];
   while (e + 1 < n && dir[e + 1].start <= base_row) e++;
@@ -389,11 +377,11 @@ __device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, SlabCol* slab, const 
   return d.kind ? bp_get(smem_at<uint32_t>(smem, L.valwin[c][buf]), d.payload, s.bw, r - d.start) : d.payload;
 }
 
-__device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, const uint8_t* arena,
+__device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const uint8_t* arena,
                                                    uint32_t c, uint32_t buf, uint32_t base_row, uint32_t r, bool in, bool want) {
-  const SlabCol& s = slab[c];
+  const SlabCol& s = ctl.slab[c];
   if (PQB_ENC_HAS_STREAM(s.enc)) {
-    uint32_t v = fast_idx(ctl, slab, L, smem, c, buf, base_row, r, in);
+    uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
     if (s.enc == DE_RLE_BOOL) return v & 1;
     return (in && want) ? load_u64_unaligned(arena + s.dict_off + uint64_t(v) * 8) : 0;
   }
@@ -402,12 +390,12 @@ __device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, SlabCol* slab, 
 }
 
 // One 32-row word of one leaf: returns T (and N through *nw); all lanes get the same words.
-__device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem,
+__device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
                                                    const DevScanArgs& a, uint32_t l, uint32_t buf, uint32_t base_row,
                                                    uint32_t r, bool in, uint32_t* nw) {
   const DevLeaf& lf = plan.leaves[l];
   const uint32_t c = lf.col;
-  const SlabCol& s = slab[c];
+  const SlabCol& s = ctl.slab[c];
   *nw = 0;
   if (!s.present) {  // column missing from this file: every row NULL
     if (lf.kind == LK_IS_NULL) return 0xffffffffu;
@@ -420,7 +408,7 @@ __device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl&
   const uint8_t kind = plan.cols[c].kind;
   bool t = false;
   if (PQB_ENC_HAS_STREAM(s.enc)) {
-    uint32_t v = fast_idx(ctl, slab, L, smem, c, buf, base_row, r, in);
+    uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
     if (in) t = s.enc == DE_DICT ? a.luts[lf.lut_off + s.lut_base + v] != 0 : cmp_i64((int64_t)(v & 1), lf.lit_i64, lf.cmp);
   } else if (in) {
     if (kind == DK_BOOL) {
@@ -439,9 +427,9 @@ __device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl&
 // Every warp owns whole 32-row words of the slab: leaves -> Kleene combine -> consume, all in
 // registers / per-warp scratch.  No leaf bitmaps, no staging, no block barrier.  Returns the rows
 // this thread's warp selected (lane 0 carries the count).
-__device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem,
-                                              const DevScanArgs& a, const SlabView& v, uint32_t buf, uint32_t R,
-                                              unsigned long long* acc, bool agg_mode) {
+__device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                              const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
+                                              uint32_t r_item, unsigned long long* acc, bool agg_mode) {
   const uint32_t warp = warp_id(), lane = lane_id();
   const uint32_t nwords = (R + 31) >> 5;
   const uint32_t nslots = plan.nslots;
@@ -449,7 +437,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
   __syncwarp();
   uint32_t* st = ctl.stk[warp];
   uint32_t cnt = 0;
-  for (uint32_t w = warp; w < nwords; w += kRowWarps) {
+  for (uint32_t w = warp; w < nwords; w += kScanWarps) {
     const uint32_t base_row = w * 32, r = base_row + lane;
     const bool in = r < R;
     int sp = 0;
@@ -458,7 +446,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
       const DevPredOp op = plan.pred[i];
       if (op.kind == PK_LEAF) {
         uint32_t n;
-        uint32_t t = fast_leaf_word(plan, ctl, slab, L, smem, a, op.arg, buf, base_row, r, in, &n);
+        uint32_t t = fast_leaf_word(plan, ctl, L, smem, a, op.arg, buf, base_row, r, in, &n);
         st[2 * sp] = t;
         st[2 * sp + 1] = n;
         sp++;
@@ -487,8 +475,8 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
       if (lane == 0) {
         cnt += __popc(sel);
         if (plan.write_bitmap && sel) {
-          uint32_t pos = v.r_item + base_row;
-          uint32_t* dst = a.bitmap + v.bitmap_word0 + (pos >> 5);
+          uint32_t pos = r_item + base_row;
+          uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
           uint32_t sh = pos & 31;
           if (sh == 0) *dst = sel;
           else {
@@ -506,17 +494,17 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
     uint32_t slot = 0;
     for (uint32_t k = 0; k < plan.nkeys; k++) {
       const DevKey& key = plan.keys[k];
-      const SlabCol& s = slab[key.col];
+      const SlabCol& s = ctl.slab[key.col];
       uint32_t gid = key.card;  // column missing: NULL group
       if (s.present) {
         if (key.kind == KK_BOOL) {
-          gid = (uint32_t)fast_value_u64(ctl, slab, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
           if (!PQB_ENC_HAS_STREAM(s.enc)) {
             uint32_t kk = s.vals_done + r;
             gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
           }
         } else {
-          uint32_t v = fast_idx(ctl, slab, L, smem, key.col, buf, base_row, r, in);
+          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
           gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
         }
       }
@@ -526,14 +514,14 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = slab[ag.col];
+      const SlabCol& s = ctl.slab[ag.col];
       if (!s.present) continue;  // all NULL: contributes nothing
       uint64_t bits;
       if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
         uint32_t kk = s.vals_done + r;
         bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
       } else {
-        bits = fast_value_u64(ctl, slab, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
       }
       if (!mine) continue;
       if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -545,72 +533,129 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
 }
 
 // ---- specialised row pass: WHERE leaf AND leaf AND ... over dictionary pages, no NULLs ----------
-// The common log-analytics filter shape (level = 'ERROR' AND latency_ms > 100 AND ...).  Each warp
-// owns whole 32-row words; per leaf it keeps the current and the next run-directory entry in
-// registers (warp uniform), every lane unpacks its own row's index, probes the leaf's LUT, one
-// ballot makes the word, words are AND-ed in a register and the word is consumed at once.  No
-// leaf bitmaps, no atomics, no block barrier inside the slab.
-// Each warp owns kWordsPerWarp CONSECUTIVE 32-row words (256 rows).  Leaves are the outer loop,
-// so only one leaf's cursor (current directory entry + start of the next) is live in registers;
-// the per-word selection lives in a small unrolled register array.
-constexpr int kWordsPerWarp = kSlabWords / kRowWarps;
+// The common log-analytics filter shape (level = 'ERROR' AND latency_ms > 100 AND ...).  Every
+// thread owns 8 consecutive rows of the slab (one byte of the selection): per leaf it finds its
+// run-directory entry, unpacks its 8 indices from the staged window into registers, probes the
+// leaf's LUT and ANDs the byte.  No leaf bitmaps, no atomics, no block barrier inside the slab.
+// The aggregate consume pass still walks 32-row words (a warp owns kWordsPerWarp consecutive ones).
+constexpr int kWordsPerWarp = kSlabWords / kScanWarps;
+constexpr int kRowsPerThread = kSlabRows / kScanThreads;
+static_assert(kRowsPerThread == 8, "the octet pass gives every thread 8 consecutive rows (one selection byte)");
 
-__device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem,
-                                                  const DevScanArgs& a, const SlabView& v, uint32_t buf, uint32_t R,
-                                                  unsigned long long* acc, bool agg_mode) {
+// One leaf over one thread's octet: rows [r, r + 8) of the slab.  Returns the LUT answers as a byte
+// (bit k = row r + k); bits outside `need` are don't-care.  Parquet packs dictionary indices in
+// groups of 8 values = bw bytes, so a thread that owns 8 consecutive rows reads one short byte
+// range of the staged window and keeps everything else in registers: per-row cost is a shift, a
+// mask, one LUT byte and one LEA, against ~2 warp-instructions per row for the ballot-per-word
+// scheme this replaces (profiles/k_scan_r1c: 65 % of all executed instructions).
+__device__ __forceinline__ uint32_t octet_leaf(const uint32_t* __restrict__ dirw, uint32_t nent, const uint32_t* __restrict__ win,
+                                               uint32_t bw, uint32_t r, uint32_t need, bool smem_lut,
+                                               const uint8_t* __restrict__ lut_s, const uint8_t* __restrict__ lut_g) {
+  // directory entry holding row r: {start, count | kind << 16 | chunk0 << 24, payload}; two sentinel
+  // entries (start = ~0) follow the last one
+  uint32_t e = 0;
+  if (nent > 6) {
+#pragma unroll
+    for (uint32_t step = 32; step; step >>= 1) {
+      const uint32_t c = e + step;
+      if (c < nent && dirw[c * 3] <= r) e = c;
+    }
+  } else {
+    while (dirw[(e + 1) * 3] <= r) e++;
+  }
+  const uint32_t* A = dirw + e * 3;
+  const uint32_t start = A[0], meta = A[1], payload = A[2], next = A[3];
+  const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
+  uint32_t m = 0;
+  if (r + 8 <= next) {
+    if (!(meta & 0x10000u)) {  // RLE run: one value answers the whole octet
+      const uint32_t t = smem_lut ? lut_s[payload & (kLutCacheBytes - 1)] : lut_g[payload];
+      return t ? 0xffu : 0u;
+    }
+    const uint32_t bit0 = payload + (r - start) * bw;
+    if (bw <= 8) {
+      // the octet is at most 64 bits: three words cover it at any bit phase
+      const uint32_t wi = bit0 >> 5, sh = bit0 & 31;
+      const uint32_t x0 = win[wi], x1 = win[wi + 1], x2 = win[wi + 2];
+      const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+      if (smem_lut) {
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+          const uint32_t s = uint32_t(k) * bw;
+          const uint32_t v = (s < 32 ? __funnelshift_r(lo, hi, s) : (hi >> (s - 32))) & vmask;
+          m = m * 2 + lut_s[v];
+        }
+      } else {
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+          const uint32_t s = uint32_t(k) * bw;
+          const uint32_t v = (s < 32 ? __funnelshift_r(lo, hi, s) : (hi >> (s - 32))) & vmask;
+          m = m * 2 + (((need >> k) & 1) ? uint32_t(lut_g[v]) : 0u);
+        }
+      }
+      return m;
+    }
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+      uint32_t t = 0;
+      if ((need >> k) & 1) {
+        const uint32_t bit = bit0 + uint32_t(k) * bw;
+        const uint32_t wi = bit >> 5;
+        const uint32_t v = __funnelshift_r(win[wi], win[wi + 1], bit & 31) & vmask;
+        t = smem_lut ? lut_s[v & (kLutCacheBytes - 1)] : lut_g[v];
+      }
+      m = m * 2 + t;
+    }
+    return m;
+  }
+  // the octet straddles directory entries (short runs): row by row
+  for (uint32_t k = 0; k < 8; k++) {
+    if (!((need >> k) & 1)) continue;
+    const uint32_t rr = r + k;
+    while (dirw[(e + 1) * 3] <= rr) e++;
+    const uint32_t* B = dirw + e * 3;
+    uint32_t v = B[2];
+    if (B[1] & 0x10000u) {
+      const uint32_t bit = B[2] + (rr - B[0]) * bw;
+      const uint32_t wi = bit >> 5;
+      v = __funnelshift_r(win[wi], win[wi + 1], bit & 31) & vmask;
+    }
+    const uint32_t t = smem_lut ? lut_s[v & (kLutCacheBytes - 1)] : lut_g[v];
+    m |= (t ? 1u : 0u) << k;
+  }
+  return m;
+}
+
+__device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                                  const DevScanArgs& a, const DevItem& item, uint32_t buf, uint32_t R,
+                                                  uint32_t r_item, unsigned long long* acc, bool agg_mode) {
   const uint32_t warp = warp_id(), lane = lane_id();
   const uint32_t nslots = plan.nslots;
   const uint32_t w0 = warp * kWordsPerWarp;
-  uint32_t selw[kWordsPerWarp];
-#pragma unroll
-  for (int i = 0; i < kWordsPerWarp; i++) selw[i] = row_mask(w0 + i, R);
+  // ---- leaves: every thread answers its own 8 rows ----
+  const uint32_t r8 = threadIdx.x * kRowsPerThread;
+  uint32_t sel8 = r8 >= R ? 0u : (R - r8 >= 8 ? 0xffu : ((1u << (R - r8)) - 1u));
   for (uint32_t l = 0; l < plan.nleaves; l++) {
+    if (sel8 == 0) break;  // per thread: nothing left in its octet (most octets once a selective leaf ran)
     const DevLeaf& lf = plan.leaves[l];
-    const SlabCol& s = slab[lf.col];
-    // directory as plain words: {start, count|kind<<16|chunk0<<24, payload}; the walker left two
-    // sentinel entries (start = ~0) behind the last one, so e+1 / e+2 are always readable
-    const uint32_t* dirw = smem_at<uint32_t>(smem, L.valdir[lf.col][buf]);
-    const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[lf.col][buf]);
-    const uint32_t nent = s.nval, bw = s.bw;
-    const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
-    // lanes 0..7 each find the entry holding the first row of "their" word; broadcast per word below
-    uint32_t my_e = 0;
-    if (lane < (uint32_t)kWordsPerWarp) {
-      const uint32_t first = (w0 + lane) * 32;
-      while (my_e + 1 < nent && dirw[(my_e + 1) * 3] <= first) my_e++;
-    }
-    const bool smem_lut = ctl.lut_smem[buf][l] != 0;
-    const uint8_t* lut_s = smem + L.lutc + (buf * plan.nleaves + l) * kLutCacheBytes;
-    const uint8_t* lut_g = a.luts + lf.lut_off + s.lut_base;
+    const SlabCol& s = ctl.slab[lf.col];
+    sel8 &= octet_leaf(smem_at<uint32_t>(smem, L.valdir[lf.col]), s.nval, smem_at<uint32_t>(smem, L.valwin[lf.col][buf]), s.bw, r8,
+                       sel8, ctl.lut_smem[l] != 0, smem + L.lutc + l * kLutCacheBytes, a.luts + lf.lut_off + s.lut_base);
+  }
+  if (!agg_mode && (!plan.write_bitmap || ((r_item & 7u) == 0))) {
+    // count / selection bitmap straight from the bytes (the item's bitmap region is byte addressable)
+    if (sel8 && plan.write_bitmap)
+      reinterpret_cast<uint8_t*>(a.bitmap + item.bitmap_word0)[(r_item + r8) >> 3] = uint8_t(sel8);
+    return __popc(sel8);
+  }
+  // selection words for the consume pass below: word j of this warp = the bytes of lanes 4j .. 4j+3
+  uint32_t selw[kWordsPerWarp];
+  {
+    const uint32_t src = (lane & 7u) * 4u;
+    const uint32_t wv = __shfl_sync(0xffffffffu, sel8, src) | (__shfl_sync(0xffffffffu, sel8, src + 1) << 8) |
+                        (__shfl_sync(0xffffffffu, sel8, src + 2) << 16) | (__shfl_sync(0xffffffffu, sel8, src + 3) << 24);
 #pragma unroll
-    for (int i = 0; i < kWordsPerWarp; i++) {
-      const uint32_t e = __shfl_sync(0xffffffffu, my_e, i);
-      if (selw[i] == 0) continue;  // warp uniform: nothing left in this word
-      const uint32_t r = (w0 + i) * 32 + lane;
-      const uint32_t* A = dirw + e * 3;
-      const uint32_t b_start = A[3], c_start = A[6];
-      const bool useB = r >= b_start;
-      uint32_t start = useB ? b_start : A[0];
-      uint32_t meta = useB ? A[4] : A[1];
-      uint32_t payload = useB ? A[5] : A[2];
-      if (r >= c_start && r < R) {  // three or more entries inside one word (very short runs): rare
-        uint32_t el = e + 2;
-        while (el + 1 < nent && dirw[(el + 1) * 3] <= r) el++;
-        start = dirw[el * 3]; meta = dirw[el * 3 + 1]; payload = dirw[el * 3 + 2];
-      }
-      // bit-packed: extract; RLE: the payload is the value.  Rows past R read in-bounds garbage and
-      // are masked out by selw (row_mask); their LUT index is clamped by the mask / the guard below.
-      uint32_t v = payload;
-      if (meta & 0x10000u) {
-        const uint32_t bit = payload + (r - start) * bw;
-        const uint32_t wi = bit >> 5;
-        v = __funnelshift_r(win[wi], win[wi + 1], bit & 31) & vmask;
-      }
-      bool t;
-      if (smem_lut) t = lut_s[v & (kLutCacheBytes - 1)] != 0;
-      else t = r < R && lut_g[v] != 0;
-      selw[i] &= __ballot_sync(0xffffffffu, t);
-    }
+    for (int i = 0; i < kWordsPerWarp; i++) selw[i] = __shfl_sync(0xffffffffu, wv, i);
   }
   if (agg_mode) {
     if (lane < plan.ncols) ctl.wcur[warp][lane] = 0;
@@ -627,8 +672,8 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
       if (lane == 0) {
         cnt += __popc(sel);
         if (plan.write_bitmap) {
-          uint32_t pos = v.r_item + base_row;
-          uint32_t* dst = a.bitmap + v.bitmap_word0 + (pos >> 5);
+          uint32_t pos = r_item + base_row;
+          uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
           uint32_t sh = pos & 31;
           if (sh == 0) *dst = sel;
           else {
@@ -645,17 +690,17 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     uint32_t slot = 0;
     for (uint32_t k = 0; k < plan.nkeys; k++) {
       const DevKey& key = plan.keys[k];
-      const SlabCol& s = slab[key.col];
+      const SlabCol& s = ctl.slab[key.col];
       uint32_t gid = key.card;
       if (s.present) {
         if (key.kind == KK_BOOL) {
-          gid = (uint32_t)fast_value_u64(ctl, slab, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
           if (!PQB_ENC_HAS_STREAM(s.enc)) {
             uint32_t kk = s.vals_done + r;
             gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
           }
         } else {
-          uint32_t v = fast_idx(ctl, slab, L, smem, key.col, buf, base_row, r, in);
+          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
           gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
         }
       }
@@ -665,14 +710,14 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = slab[ag.col];
+      const SlabCol& s = ctl.slab[ag.col];
       if (!s.present) continue;
       uint64_t bits;
       if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
         uint32_t kk = s.vals_done + r;
         bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
       } else {
-        bits = fast_value_u64(ctl, slab, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
       }
       if (!mine) continue;
       if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -686,17 +731,16 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
 // The general per-slab walk (columns with NULLs, window / directory overflow): definition levels ->
 // validity bitmap + ranks -> index streams, shrinking the slab until every column is covered.
 // All threads call it; returns the rows of the slab (0: corrupt page).
-__device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, SlabCol* slab, const SmemLayout& L, uint8_t* smem, uint32_t ncols,
+__device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t ncols,
                                               uint32_t buf, uint32_t R, const StreamState& snap_def,
                                               const StreamState& snap_val, const DeltaState& snap_dl) {
   uint32_t mycol;
   const bool walker = walker_of(ncols, mycol);
   const uint32_t tid = threadIdx.x;
-  const bool is_row = warp_id() < kRowWarps;
   for (int attempt = 0; attempt < 4 && R > 0; attempt++) {
     if (walker) {  // definition levels
       ColCursor& c = ctl.cur[mycol];
-      SlabCol& s = slab[mycol];
+      SlabCol& s = ctl.slab[mycol];
       uint32_t got = R;
       s.ndef = 0;
       s.all_valid = 1;
@@ -712,11 +756,10 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, SlabCol* slab, const
       }
       ctl.rmin[mycol] = got;
     }
-    if (is_row)
-      for (uint32_t c = 0; c < ncols; c++) {
-        uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
-        for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kRowThreads) bm[w] = 0;
-      }
+    for (uint32_t c = 0; c < ncols; c++) {
+      uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
+      for (uint32_t w = tid; w < (uint32_t)kSlabWords + 2; w += kScanThreads) bm[w] = 0;
+    }
     __syncthreads();
     uint32_t R1 = R;
     for (uint32_t c = 0; c < ncols; c++) R1 = ctl.rmin[c] < R1 ? ctl.rmin[c] : R1;
@@ -726,15 +769,15 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, SlabCol* slab, const
       __syncthreads();
       continue;
     }
-    if (is_row) for (uint32_t c = 0; c < ncols; c++) {
-      const SlabCol& s = slab[c];
+    for (uint32_t c = 0; c < ncols; c++) {
+      const SlabCol& s = ctl.slab[c];
       if (s.present && !s.all_valid)
         dir_to_bitmap(smem_at<DirEntry>(smem, L.defdir[c]), s.ndef, smem_at<uint32_t>(smem, L.defwin[c][buf]),
                       smem_at<uint32_t>(smem, L.valid[c]));
     }
     __syncthreads();
-    if (is_row) for (uint32_t c = warp_id(); c < ncols; c += kRowWarps) {
-      SlabCol& s = slab[c];
+    for (uint32_t c = warp_id(); c < ncols; c += kScanWarps) {
+      SlabCol& s = ctl.slab[c];
       if (!s.present) { if (lane_id() == 0) s.nv = 0; continue; }
       if (s.all_valid) { if (lane_id() == 0) s.nv = R; continue; }
       uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
@@ -757,17 +800,17 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, SlabCol* slab, const
     __syncthreads();
     if (walker) {  // dictionary-index streams
       ColCursor& c = ctl.cur[mycol];
-      SlabCol& s = slab[mycol];
+      SlabCol& s = ctl.slab[mycol];
       uint32_t rc = R;
       s.nval = 0;
       if (c.present && PQB_ENC_HAS_WINDOW(c.enc) && s.nv > 0) {
         Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
         uint32_t n = 0;
         uint32_t got = c.enc == DE_DELTA
-                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol][buf]), n, kMaxDeltaEntries)
-                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n, kMaxDirEntries - 2);
+                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
+                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
         s.nval = n;
-        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n);
+        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
         if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
           if (s.all_valid) rc = got;
           else {
@@ -799,27 +842,244 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, SlabCol* slab, const
   return 0;
 }
 
-
-// ---- the generic row phase (stages 4-6): any predicate program, NULLs, PLAIN / DELTA pages.  Row
-// warps only; block-level steps meet at row_sync(). ----
-__device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& ctl, SlabCol* slab, const SlabView& v,
-                                                 const SmemLayout& L, uint8_t* smem, const DevScanArgs& a, uint32_t buf,
-                                                 uint32_t R, unsigned long long* acc, bool agg_mode) {
+__global__ void __launch_bounds__(kScanThreads, PQB_SCAN_MIN_BLOCKS)
+k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  ScanCtl& ctl = *reinterpret_cast<ScanCtl*>(smem);
   const uint32_t tid = threadIdx.x;
   const uint32_t ncols = plan.ncols;
+  const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
+  const bool agg_mode = plan.mode == SM_AGG;
+  uint32_t mycol;
+  const bool walker = walker_of(ncols, mycol);
+
+  if (tid == 0) {
+    mbar_init(&ctl.mbar[0], 1);
+    mbar_init(&ctl.mbar[1], 1);
+    mbar_fence_init();
+    ctl.error = 0;
+  }
+  unsigned long long* sacc = smem_at<unsigned long long>(smem, L.acc);
+  if (agg_mode && plan.smem_acc) {
+    for (uint32_t i = tid; i < cells * plan.nslots; i += kScanThreads) {
+      uint32_t arr = i / plan.nslots;
+      unsigned long long init = 0;
+      if (arr >= 1 && arr < 1 + plan.n_acc) {
+        uint8_t k = plan.acc_init[arr - 1];
+        init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
+      }
+      sacc[i] = init;
+    }
+  }
+  __syncthreads();
+  unsigned long long* acc = (agg_mode && plan.smem_acc) ? sacc : a.acc;
   const uint32_t nslots = plan.nslots;
-  const uint32_t nwords = (R + 31) >> 5;
+
+  uint32_t phases = 0;  // bit b: parity to wait for on mbar[b]
   uint32_t* selw = smem_at<uint32_t>(smem, L.sel);
   uint32_t* leafT = smem_at<uint32_t>(smem, L.leafT);
-  uint32_t cnt = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) ctl.item = (uint32_t)atomicAdd(&a.counters[2], 1ull);
+    __syncthreads();
+    const uint32_t item_id = ctl.item;
+    if (item_id >= plan.n_items) break;
+    const DevItem& item = a.items[item_id];
+
+    if (tid < ncols) {
+      ColCursor& c = ctl.cur[tid];
+      const DevChunk ch = a.chunks[item.rg * ncols + tid];
+      SlabCol& s = ctl.slab[tid];
+      s.lut_base = ch.lut_base;
+      s.dict_off = ch.dict_off;
+      s.present = ch.present;
+      c.present = ch.present;
+      c.page_end = ch.first_page + ch.n_pages;
+      if (ch.present) page_enter(c, a.pages, item.page[tid]);
+      else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
+    }
+    if (tid == 0) ctl.sel_count = 0;
+    if (plan.fast_and) {
+      // cache this row group's leaf LUTs (one byte per dictionary entry) in shared memory
+      for (uint32_t l = 0; l < plan.nleaves; l++) {
+        const DevLeaf& lf = plan.leaves[l];
+        const DevChunk ch = a.chunks[item.rg * ncols + lf.col];
+        const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
+        if (tid == 0) ctl.lut_smem[l] = fits;
+        if (fits) {
+          const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
+          uint8_t* dst = smem + L.lutc + l * kLutCacheBytes;
+          for (uint32_t i = tid; i < ch.dict_n; i += kScanThreads) dst[i] = src[i];
+        }
+      }
+    }
+    __syncthreads();
+
+    uint32_t rows_left = item.nrows;
+    uint32_t r_item = 0;
+    uint32_t buf = 0;
+    if (tid == 0) issue_windows(ctl, L, smem, a.arena, ncols, buf, rows_left);
+    __syncthreads();
+
+    while (rows_left > 0) {
+      // ---- 1-3. control, WARP 0 ONLY (the other warps park at the barrier and spend no issue
+      //      slots): wait for the staged bytes, walk the run headers (one lane per column),
+      //      commit the cursors, prefetch the next slab, choose the row pass ----
+      StreamState snap_def, snap_val;
+      DeltaState snap_dl;
+      if (warp_id() == 0) {
+        if (lane_id() == 0) mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
+        __syncwarp();
+        const uint32_t R0w = ctl.target;
+        if (walker) {
+          ColCursor& c = ctl.cur[mycol];
+          SlabCol& s = ctl.slab[mycol];
+          snap_def = c.def;
+          snap_val = c.val;
+          snap_dl = c.dl;
+          uint32_t rc = R0w;
+          s.ndef = 0;
+          s.nval = 0;
+          s.all_valid = 1;
+          s.nv = c.present ? R0w : 0;
+          if (c.present) {
+            if (c.has_def) {
+              Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
+              DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
+              uint32_t n = 0;
+              uint32_t got = walk_stream(c.def, w, R0w, dir, n, kMaxDirEntries);
+              s.ndef = n;
+              uint32_t allv = 1;
+              for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
+              s.all_valid = allv;
+              rc = got;
+              if (!allv) ctl.any_nulls = 1;
+            }
+            if (s.all_valid && rc == R0w && PQB_ENC_HAS_WINDOW(c.enc)) {
+              Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
+              uint32_t n = 0;
+              rc = c.enc == DE_DELTA
+                       ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
+                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
+              s.nval = n;
+              if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
+            }
+          }
+          if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
+        }
+        __syncwarp();
+        const bool general = ctl.rmin_all < R0w || ctl.any_nulls;
+        if (!general) {
+          if (walker) {  // freeze this slab's view, advance the cursor
+            ColCursor& c = ctl.cur[mycol];
+            SlabCol& s = ctl.slab[mycol];
+            s.val_base = c.val_base;
+            s.vals_done = c.vals_done;
+            s.enc = c.enc;
+            s.bw = c.val.bw;
+            if (c.present) {
+              c.vals_done += s.nv;
+              c.page_rows_left -= R0w;
+              if (c.page_rows_left == 0 && rows_left > R0w) {
+                if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+                else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane_id() == 0) {
+            uint32_t mode = MODE_GENERIC, has_delta = 0;
+            bool fa = plan.fast_and != 0;
+            for (uint32_t c = 0; c < ncols; c++) has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
+            for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+              const SlabCol& s = ctl.slab[plan.leaves[l].col];
+              fa = s.present && s.enc == DE_DICT && s.nval > 0;
+            }
+            if (fa) mode = MODE_FAST_AND;
+            else if (plan.row_major) mode = MODE_ROW_MAJOR;
+            ctl.mode = mode;
+            ctl.has_delta = has_delta;
+            ctl.R = R0w;
+            if (!ctl.error && rows_left > R0w) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R0w);
+          }
+        } else if (lane_id() == 0) {
+          ctl.mode = MODE_GENERAL_WALK;
+          ctl.R = R0w;
+        }
+      }
+      phases ^= 1u << buf;
+      __syncthreads();
+      uint32_t mode = ctl.mode;
+      uint32_t R = ctl.R;
+      bool has_nulls = false;
+      uint32_t has_delta = ctl.has_delta;
+      if (mode == MODE_GENERAL_WALK) {  // uniform: NULLs or an exhausted window -> the general walk, all threads
+        if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
+        __syncthreads();
+        R = general_walk(ctl, L, smem, ncols, buf, R, snap_def, snap_val, snap_dl);
+        if (R == 0) {  // no progress possible: corrupt page
+          if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
+          break;
+        }
+        if (walker) {
+          ColCursor& c = ctl.cur[mycol];
+          SlabCol& s = ctl.slab[mycol];
+          s.val_base = c.val_base;
+          s.vals_done = c.vals_done;
+          s.enc = c.enc;
+          s.bw = c.val.bw;
+          if (c.present) {
+            c.vals_done += s.nv;
+            c.page_rows_left -= R;
+            if (c.page_rows_left == 0 && rows_left > R) {
+              if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
+              else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
+            }
+          }
+        }
+        __syncthreads();
+        if (!ctl.error && tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
+        has_delta = 0;
+        for (uint32_t c = 0; c < ncols; c++) {
+          has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
+          has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
+        }
+        mode = MODE_GENERIC;
+        if (!has_nulls) {
+          bool fa = plan.fast_and != 0;
+          for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+            const SlabCol& s = ctl.slab[plan.leaves[l].col];
+            fa = s.present && s.enc == DE_DICT && s.nval > 0;
+          }
+          if (fa) mode = MODE_FAST_AND;
+          else if (plan.row_major) mode = MODE_ROW_MAJOR;
+        }
+      }
+      if (ctl.error) break;
+
+      // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
+      if (has_delta)
+        for (uint32_t c = 0; c < ncols; c++)
+          if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
+      const uint32_t nwords = (R + 31) >> 5;
+      uint32_t cnt = 0;
+      const bool fast_and = mode == MODE_FAST_AND;
+      if (fast_and) {
+        // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
+        cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+      } else if (mode == MODE_ROW_MAJOR) {
+        // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
+        cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+      } else {
       // ---- 4. (general) unpack: fused index -> leaf bits where possible, else stage indices ----
-      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kRowThreads) leafT[w] = 0;
-      row_sync();
+      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
+      __syncthreads();
       for (uint32_t c = 0; c < ncols; c++) {
-        const SlabCol& s = slab[c];
+        const SlabCol& s = ctl.slab[c];
         if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
         uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
-        const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
+        const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
         const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
         // leaves of this column that a dictionary LUT answers (host precomputed lists)
         const uint32_t nlut = plan.col_nlut[c];
@@ -836,13 +1096,13 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
           dir_to_idx(dir, s.nval, win, s.bw, idx);
         }
       }
-      row_sync();
+      __syncthreads();
 
       // ---- 5. leaves the fused pass did not answer: PLAIN pages, NULL-carrying slabs, booleans ----
       for (uint32_t l = 0; l < plan.nleaves; l++) {
         const DevLeaf& lf = plan.leaves[l];
         if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
-        const SlabCol& s = slab[lf.col];
+        const SlabCol& s = ctl.slab[lf.col];
         if (!s.present) continue;                                 // all NULL: T stays 0
         if (s.enc == DE_DICT && s.all_valid && plan.col_nlut[lf.col] <= 2) continue;  // answered by the fused pass
         const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
@@ -854,7 +1114,7 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
         const int64_t lit = lf.lit_i64;
         const int64_t litk = f64_order_key((uint64_t)lf.lit_i64);
         const uint32_t op = lf.cmp;
-        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kRowThreads) {
+        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
           uint32_t r = r0 + lane_id();
           bool t = false;
           if (r < R) {
@@ -870,10 +1130,10 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
           if (lane_id() == 0) Tw[r0 >> 5] = tw;
         }
       }
-      row_sync();
+      __syncthreads();
 
       // ---- 6. Kleene combine on words -> selection; filter mode consumes right here ----
-      for (uint32_t w = tid; w < nwords; w += kRowThreads) {
+      for (uint32_t w = tid; w < nwords; w += kScanThreads) {
         uint32_t st_t[kPredStack], st_n[kPredStack];
         int sp = 0;
         const uint32_t rm = row_mask(w, R);
@@ -882,7 +1142,7 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
           const DevPredOp op = plan.pred[i];
           if (op.kind == PK_LEAF) {
             const DevLeaf& lf = plan.leaves[op.arg];
-            const SlabCol& s = slab[lf.col];
+            const SlabCol& s = ctl.slab[lf.col];
             uint32_t V = !s.present ? 0u : (s.all_valid ? 0xffffffffu : smem_at<uint32_t>(smem, L.valid[lf.col])[w]);
             uint32_t t, n;
             if (lf.kind == LK_IS_NULL) { t = ~V; n = 0; }
@@ -916,8 +1176,8 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
         else {
           cnt += __popc(sel);
           if (plan.write_bitmap && sel) {
-            uint32_t pos = v.r_item + w * 32;
-            uint32_t* dst = a.bitmap + v.bitmap_word0 + (pos >> 5);
+            uint32_t pos = r_item + w * 32;
+            uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
             uint32_t sh = pos & 31;
             if (sh == 0) *dst = sel;  // slabs are word aligned except after a pathological shrink
             else {
@@ -929,14 +1189,14 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
         }
       }
       if (agg_mode) {
-        row_sync();
-        for (uint32_t r = tid; r < R; r += kRowThreads) {
+        __syncthreads();
+        for (uint32_t r = tid; r < R; r += kScanThreads) {
           if (!((selw[r >> 5] >> (r & 31)) & 1)) continue;
           cnt++;
           uint32_t slot = 0;
           for (uint32_t k = 0; k < plan.nkeys; k++) {
             const DevKey& key = plan.keys[k];
-            const SlabCol& s = slab[key.col];
+            const SlabCol& s = ctl.slab[key.col];
             RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
             uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
             if (rv.valid) {
@@ -949,7 +1209,7 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
           for (uint32_t g = 0; g < plan.naggs; g++) {
             const DevAgg& ag = plan.aggs[g];
             if (ag.fn == AG_COUNT_STAR) continue;
-            const SlabCol& s = slab[ag.col];
+            const SlabCol& s = ctl.slab[ag.col];
             RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
             if (!rv.valid) continue;
             if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -960,341 +1220,27 @@ __device__ __forceinline__ uint32_t generic_rows(const DevPlan& plan, ScanCtl& c
           }
         }
       }
-  return cnt;
-}
+      }  // general row phase
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
 
-
-__global__ void __launch_bounds__(kScanThreads, 3)
-k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout L, const DevScanArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  ScanCtl& ctl = *reinterpret_cast<ScanCtl*>(smem);
-  const uint32_t tid = threadIdx.x;
-  const uint32_t lane = lane_id();
-  const uint32_t ncols = plan.ncols;
-  const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
-  const bool agg_mode = plan.mode == SM_AGG;
-  const bool is_ctl = warp_id() == kCtlWarp;
-  const bool is_row = !is_ctl;
-  uint32_t mycol;
-  const bool walker = walker_of(ncols, mycol);
-
-  if (tid == 0) {
-    mbar_init(&ctl.mbar[0], 1);
-    mbar_init(&ctl.mbar[1], 1);
-    mbar_init(&ctl.full[0], 1);
-    mbar_init(&ctl.full[1], 1);
-    mbar_init(&ctl.empty[0], kRowWarps);
-    mbar_init(&ctl.empty[1], kRowWarps);
-    mbar_fence_init();
-    ctl.error = 0;
-    ctl.lut_rg[0] = ctl.lut_rg[1] = 0;
-  }
-  unsigned long long* sacc = smem_at<unsigned long long>(smem, L.acc);
-  if (agg_mode && plan.smem_acc && is_row) {
-    for (uint32_t i = tid; i < cells * plan.nslots; i += kRowThreads) {
-      uint32_t arr = i / plan.nslots;
-      unsigned long long init = 0;
-      if (arr >= 1 && arr < 1 + plan.n_acc) {
-        uint8_t k = plan.acc_init[arr - 1];
-        init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
-      }
-      sacc[i] = init;
-    }
-  }
-  __syncthreads();
-  unsigned long long* acc = (agg_mode && plan.smem_acc) ? sacc : a.acc;
-  const uint32_t nslots = plan.nslots;
-
-  // control-warp private state (uniform across its lanes)
-  bool have_item = false;
-  uint32_t item_id = 0, rows_left = 0, r_item = 0, item_rg = 0, item_word0 = 0;
-  uint64_t item_grow0 = 0;
-  unsigned long long my_selected = 0;  // row warps, lane 0
-
-  // slab sequence number s; buffers and mbarrier parities derive from it:
-  //   b = s & 1, every barrier of buffer b completes once per slab, parity (s >> 1) & 1
-  for (uint32_t s = 0;; s++) {
-    const uint32_t b = s & 1, par = (s >> 1) & 1;
-    SlabView& view = ctl.view[b];
-    SlabCol* slab = view.col;
-    StreamState snap_def, snap_val;
-    DeltaState snap_dl;
-    uint32_t R0w = 0;
-    if (is_ctl) {
-      // ---------------- control warp: prepare slab s ----------------
-      bool stop = false;
-      if (!have_item) {
-        uint32_t it = 0;
-        if (lane == 0) it = (uint32_t)atomicAdd(&a.counters[2], 1ull);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        // buffers b were last used by slab s-2
-        if (s >= 2) { if (lane == 0) mbar_wait(&ctl.empty[b], ((s - 2) >> 1) & 1); __syncwarp(); }
-        if (it >= plan.n_items || ctl.error) stop = true;
-        else {
-          item_id = it;
-          const DevItem& item = a.items[it];
-          item_rg = item.rg; item_word0 = item.bitmap_word0; item_grow0 = item.global_row0;
-          rows_left = item.nrows; r_item = 0;
-          if (lane < ncols) {
-            ColCursor& c = ctl.cur[lane];
-            const DevChunk ch = a.chunks[item.rg * ncols + lane];
-            c.present = ch.present;
-            c.page_end = ch.first_page + ch.n_pages;
-            if (ch.present) page_enter(c, a.pages, item.page[lane]);
-            else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
-          }
-          __syncwarp();
-          if (lane == 0) issue_windows(ctl, L, smem, a.arena, ncols, b, rows_left);
-          __syncwarp();
-          have_item = true;
-        }
-      }
-      if (stop) {
-        if (lane == 0) { view.mode = MODE_STOP; __threadfence_block(); mbar_arrive(&ctl.full[b]); }
-        break;
-      }
-      if (lane == 0) mbar_wait(&ctl.mbar[b], par);
-      __syncwarp();
-      // per-slab constants of the columns (the chunk of this row group)
-      if (lane < ncols) {
-        const DevChunk ch = a.chunks[item_rg * ncols + lane];
-        slab[lane].lut_base = ch.lut_base;
-        slab[lane].dict_off = ch.dict_off;
-        slab[lane].present = ch.present;
-      }
-      // every lane must take the same decision: the lanes diverged just above, and lane 0 updates
-      // lut_rg at the end of the refill — read it once, between two warp barriers
-      __syncwarp();
-      const bool refill = plan.fast_and && ctl.lut_rg[b] != item_rg + 1;
-      __syncwarp();
-      if (refill) {
-        // leaf LUTs of this row group -> lutc[b] (one byte per dictionary entry)
-        for (uint32_t l = 0; l < plan.nleaves; l++) {
-          const DevLeaf& lf = plan.leaves[l];
-          const DevChunk ch = a.chunks[item_rg * ncols + lf.col];
-          const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
-          if (lane == 0) ctl.lut_smem[b][l] = fits;
-          if (fits) {
-            const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
-            uint8_t* dst = smem + L.lutc + (b * plan.nleaves + l) * kLutCacheBytes;
-            for (uint32_t i = lane; i < ch.dict_n; i += 32) dst[i] = src[i];
-          }
-        }
-        if (lane == 0) ctl.lut_rg[b] = item_rg + 1;
-      }
-      __syncwarp();
-      R0w = ctl.target;
-      const uint32_t buf = b;
-      if (walker) {  // fast walk: definition levels say "no NULLs" -> walk the value stream right away
-        ColCursor& c = ctl.cur[mycol];
-        SlabCol& sc = slab[mycol];
-        snap_def = c.def;
-        snap_val = c.val;
-        snap_dl = c.dl;
-        uint32_t rc = R0w;
-        sc.ndef = 0;
-        sc.nval = 0;
-        sc.all_valid = 1;
-        sc.nv = c.present ? R0w : 0;
-        if (c.present) {
-          if (c.has_def) {
-            Window w{smem + L.defwin[mycol][buf], c.defwin_base[buf], L.defwin_cap[mycol]};
-            DirEntry* dir = smem_at<DirEntry>(smem, L.defdir[mycol]);
-            uint32_t n = 0;
-            uint32_t got = walk_stream(c.def, w, R0w, dir, n, kMaxDirEntries);
-            sc.ndef = n;
-            uint32_t allv = 1;
-            for (uint32_t e = 0; e < n; e++) allv &= (dir[e].kind == 0 && (dir[e].payload & 1)) ? 1u : 0u;
-            sc.all_valid = allv;
-            rc = got;
-            if (!allv) ctl.any_nulls = 1;
-          }
-          if (sc.all_valid && rc == R0w && PQB_ENC_HAS_WINDOW(c.enc)) {
-            Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
-            uint32_t n = 0;
-            rc = c.enc == DE_DELTA
-                     ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol][buf]), n, kMaxDeltaEntries)
-                     : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n, kMaxDirEntries - 2);
-            sc.nval = n;
-            if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n);
-          }
-        }
-        if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
-      }
-      __syncwarp();
-      const bool general = ctl.rmin_all < R0w || ctl.any_nulls;
-      if (!general) {
-        if (walker) {  // freeze this slab's view, advance the cursor
-          ColCursor& c = ctl.cur[mycol];
-          SlabCol& sc = slab[mycol];
-          sc.val_base = c.val_base;
-          sc.vals_done = c.vals_done;
-          sc.enc = c.enc;
-          sc.bw = c.val.bw;
-          if (c.present) {
-            c.vals_done += sc.nv;
-            c.page_rows_left -= R0w;
-            if (c.page_rows_left == 0 && rows_left > R0w) {
-              if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
-              else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) {
-          uint32_t mode = MODE_GENERIC, has_delta = 0;
-          bool fa = plan.fast_and != 0;
-          for (uint32_t c = 0; c < ncols; c++) has_delta |= slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv;
-          for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
-            const SlabCol& sc = slab[plan.leaves[l].col];
-            fa = sc.present && sc.enc == DE_DICT && sc.nval > 0;
-          }
-          if (fa) mode = MODE_FAST_AND;
-          else if (plan.row_major) mode = MODE_ROW_MAJOR;
-          if (ctl.error) mode = MODE_STOP;
-          view.mode = mode;
-          view.has_delta = has_delta;
-          view.R = R0w;
-          view.item_id = item_id;
-          view.r_item = r_item;
-          view.bitmap_word0 = item_word0;
-          view.global_row0 = item_grow0;
-          view.rg = item_rg;
-          __threadfence_block();
-          mbar_arrive(&ctl.full[b]);
-        }
-        __syncwarp();
-        if (ctl.error) break;
-        if (plan.debug_sync & 1) {  // PQB_SYNC_CTL=1: no overlap between control and row warps (race bisection)
-          if (lane == 0) mbar_wait(&ctl.empty[b], par);
-          __syncwarp();
-        }
-        rows_left -= R0w;
-        r_item += R0w;
-        if (rows_left == 0) have_item = false;
-        else {
-          // prefetch slab s+1 into buffers b^1, free once slab s-1 was consumed
-          if (s >= 1) { if (lane == 0) mbar_wait(&ctl.empty[b ^ 1], ((s - 1) >> 1) & 1); __syncwarp(); }
-          if (lane == 0) issue_windows(ctl, L, smem, a.arena, ncols, b ^ 1, rows_left);
-          __syncwarp();
-        }
-        continue;  // the control warp never touches the row phase of a fast slab
-      }
-      if (lane == 0) {
-        view.mode = MODE_GENERAL_WALK;
-        view.R = R0w;
-        view.item_id = item_id;
-        view.r_item = r_item;
-        view.bitmap_word0 = item_word0;
-        view.global_row0 = item_grow0;
-        view.rg = item_rg;
-        __threadfence_block();
-        mbar_arrive(&ctl.full[b]);
-      }
-      __syncwarp();
-    } else {
-      // ---------------- row warps: wait until slab s is published ----------------
-      if (plan.debug_sync & 2) {
-        mbar_wait(&ctl.full[b], par);
-        if (*reinterpret_cast<volatile uint32_t*>(&view.mode) != MODE_STOP) mbar_wait(&ctl.mbar[b], par);
-      } else if (lane == 0) {
-        mbar_wait(&ctl.full[b], par);
-        // observe the TMA completion of this slab's windows directly as well: the bulk copies were
-        // written through the async proxy, and this wait is what makes them visible to this warp
-        // (a STOP view carries no windows)
-        if (*reinterpret_cast<volatile uint32_t*>(&view.mode) != MODE_STOP) mbar_wait(&ctl.mbar[b], par);
-      }
-      __syncwarp();
-    }
-    uint32_t mode = view.mode;
-    if (mode == MODE_STOP) break;
-    uint32_t R = view.R;
-    uint32_t has_delta = view.has_delta;
-    const uint32_t buf = b;
-    if (mode == MODE_GENERAL_WALK) {
-      // ---- NULLs or an exhausted window: the general walk needs every thread; synchronous ----
+      rows_left -= R;
+      r_item += R;
+      buf ^= 1;
       __syncthreads();
-      if (walker) { ctl.cur[mycol].def = snap_def; ctl.cur[mycol].val = snap_val; ctl.cur[mycol].dl = snap_dl; }
-      __syncthreads();
-      R = general_walk(ctl, slab, L, smem, ncols, buf, R, snap_def, snap_val, snap_dl);
-      if (R == 0) {  // no progress possible: corrupt page
-        if (tid == 0) { ctl.error = 1; atomicExch(&a.counters[1], 1ull); }
-        break;
-      }
-      if (walker) {
-        ColCursor& c = ctl.cur[mycol];
-        SlabCol& sc = slab[mycol];
-        sc.val_base = c.val_base;
-        sc.vals_done = c.vals_done;
-        sc.enc = c.enc;
-        sc.bw = c.val.bw;
-        if (c.present) {
-          c.vals_done += sc.nv;
-          c.page_rows_left -= R;
-          if (c.page_rows_left == 0 && rows_left > R) {
-            if (c.page + 1 < c.page_end) page_enter(c, a.pages, c.page + 1);
-            else { ctl.error = 1; atomicExch(&a.counters[1], 2ull); }
-          }
-        }
-      }
-      __syncthreads();
-      if (ctl.error) break;
-      bool has_nulls = false;
-      has_delta = 0;
-      for (uint32_t c = 0; c < ncols; c++) {
-        has_nulls |= slab[c].present && !slab[c].all_valid;
-        has_delta |= slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv;
-      }
-      mode = MODE_GENERIC;
-      if (!has_nulls) {
-        bool fa = plan.fast_and != 0;
-        for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
-          const SlabCol& sc = slab[plan.leaves[l].col];
-          fa = sc.present && sc.enc == DE_DICT && sc.nval > 0;
-        }
-        if (fa) mode = MODE_FAST_AND;
-        else if (plan.row_major) mode = MODE_ROW_MAJOR;
-      }
-      if (is_ctl) {
-        rows_left -= R;
-        r_item += R;
-        if (rows_left == 0) have_item = false;
-        else {
-          if (s >= 1) { if (lane == 0) mbar_wait(&ctl.empty[b ^ 1], ((s - 1) >> 1) & 1); __syncwarp(); }
-          if (lane == 0) issue_windows(ctl, L, smem, a.arena, ncols, b ^ 1, rows_left);
-          __syncwarp();
-        }
-        continue;
-      }
+    }  // slabs
+    __syncthreads();
+    if (ctl.error) break;
+    if (tid == 0) {
+      if (a.item_counts) a.item_counts[item_id] = ctl.sel_count;
+      if (ctl.sel_count) atomicAdd(&a.counters[0], (unsigned long long)ctl.sel_count);
     }
-    // ---------------- row phase (row warps only) ----------------
-    // the generic pass and the DELTA decode use block-shared scratch (leaf bitmaps, staging arrays):
-    // no row warp may start overwriting it while a slower one still reads the previous slab's
-    if (mode == MODE_GENERIC || has_delta || (plan.debug_sync & 4)) row_sync();
-    if (has_delta)
-      for (uint32_t c = 0; c < ncols; c++)
-        if (slab[c].present && slab[c].enc == DE_DELTA && slab[c].nv) delta_decode_scan(ctl, slab, L, smem, c, buf);
-    uint32_t cnt = 0;
-    if (mode == MODE_FAST_AND) cnt = fast_and_rows(plan, ctl, slab, L, smem, a, view, buf, R, acc, agg_mode);
-    else if (mode == MODE_ROW_MAJOR) cnt = fast_rows(plan, ctl, slab, L, smem, a, view, buf, R, acc, agg_mode);
-    else cnt = generic_rows(plan, ctl, slab, view, L, smem, a, buf, R, acc, agg_mode);
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) {
-      if (cnt) {
-        if (a.item_counts) atomicAdd(&a.item_counts[view.item_id], cnt);
-        my_selected += cnt;
-      }
-      __threadfence_block();
-      mbar_arrive(&ctl.empty[b]);  // buffers b may be refilled
-    }
-    __syncwarp();
-  }
+  }  // items
 
-  if (is_row && lane == 0 && my_selected) atomicAdd(&a.counters[0], my_selected);
   // ---- flush the CTA-private accumulator table ----
   __syncthreads();
-  if (agg_mode && plan.smem_acc && !ctl.error && is_row) {
-    for (uint32_t slot = tid; slot < nslots; slot += kRowThreads) {
+  if (agg_mode && plan.smem_acc && !ctl.error) {
+    for (uint32_t slot = tid; slot < nslots; slot += kScanThreads) {
       unsigned long long rows = sacc[slot];
       if (rows == 0) continue;
       atomicAdd(&a.acc[slot], rows);
