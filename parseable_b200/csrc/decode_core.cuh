@@ -138,6 +138,7 @@ PQ_HD uint32_t walk_stream(StreamState& s, const Window& w, uint32_t need, DirEn
     }
     e.count = uint16_t(take);
     e.chunk0 = uint8_t(chunks);
+    e._pad = 0;
     chunks += (take + 31u) >> 5;
     dir[nent++] = e;
     covered += take;

@@ -18,6 +18,8 @@ constexpr int kDirEntryMaxValues = 512;
 constexpr int kMaxDeltaEntries = 80;  // DELTA_BINARY_PACKED miniblock directory entries per slab
 constexpr int kDeltaWindowBytes = 8192 + 64;
 constexpr int kPredStack = 8;
+constexpr int kFastDirEntries = 32;   // prebuilt run directory: entries per (slab, column) incl. 2 sentinels
+constexpr int kRecBatch = 16;         // slab records a CTA keeps in shared memory at a time
 
 // page value encodings as the kernels see them
 enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2, DE_RLE_BOOL = 3 };
@@ -58,6 +60,20 @@ struct DevItem {               // unit of CTA work: rows between two page bounda
   uint32_t bitmap_word0;       // first word of this item's region in the selection bitmap
   uint64_t global_row0;        // ordinal of row0 in the scanned table (row-id output)
   uint32_t page[kMaxCols];     // page index (into pages[]) holding row0, per column slot
+  uint32_t slab0;              // first slab of this item in the prebuilt slab directory
+  uint32_t _pad;
+};
+
+// One (slab, column) of the prebuilt slab directory (k_slab_dirs): what the per-slab control of
+// k_scan would have derived by walking the run headers, computed for every slab at once.
+struct DevSlabRec {
+  uint64_t win_off;            // arena offset the value window is staged from (16-byte aligned)
+  uint64_t val_base;           // arena offset of the page's values section
+  uint32_t vals_done;          // values of the page consumed before this slab
+  uint16_t nent;               // run-directory entries (two sentinels follow)
+  uint8_t enc;                 // DevEnc
+  uint8_t bw;                  // index bit width
+  uint32_t _pad[2];
 };
 
 struct DevColumn {
@@ -155,15 +171,21 @@ struct DevScanArgs {
   uint32_t* item_counts;       // selected rows per item
   unsigned long long* acc;     // accumulator table (global)
   unsigned long long* counters;  // [0] rows selected, [1] error flag, [2] work-queue head
+  // prebuilt slab directory (fast items): flags[item] != 0 -> every slab of the item has records
+  uint32_t* item_flags;
+  DevSlabRec* slab_recs;       // [(item.slab0 + k) * ncols + col]
+  struct DirEntry* slab_dirs;  // [((item.slab0 + k) * ncols + col) * kFastDirEntries + e]
 };
 
 // run-directory entry produced by the stream walker
-struct DirEntry {
+struct DirEntry {     // 16 bytes: bulk-copyable (TMA) from the prebuilt slab directory
   uint32_t start;    // first value (slab relative)
   uint16_t count;
   uint8_t kind;      // 0 RLE, 1 bit-packed
   uint8_t chunk0;    // running count of 32-value chunks before this entry (balances warps)
   uint32_t payload;  // RLE: value; bit-packed: bit offset of the first value inside the window
+  uint32_t _pad;
 };
+constexpr int kDirWords = 4;  // DirEntry as 32-bit words: {start, count | kind << 16 | chunk0 << 24, payload, -}
 
 }  // namespace pqb

@@ -487,6 +487,9 @@ void Query::run(const PqQueryDesc& d) {
   const uint32_t nrg = uint32_t(rgs.size());
   std::vector<DevChunk> chunks(size_t(nrg) * std::max<uint32_t>(ncols, 1));
   std::vector<DevItem> items;
+  std::vector<uint32_t> item_flags;   // 1: every referenced column has exactly one page over the item -> slab directory pre-pass
+  uint32_t total_slabs = 0, n_fast_items = 0;
+  const bool use_slab_dirs = ncols > 0 && !(getenv("PQB_SLAB_DIRS") && getenv("PQB_SLAB_DIRS")[0] == '0');   // A/B switch
   std::vector<uint8_t> col_needs_ent(ncols, 0);  // entry offsets (string leaf / any key column)
   std::vector<uint8_t> col_has_lut(ncols, 0);
   for (uint32_t l = 0; l < nleaves; l++) {
@@ -557,6 +560,7 @@ void Query::run(const PqQueryDesc& d) {
       it.global_row0 = rg.global_row0 + common[i];
       it.bitmap_word0 = bitmap_words;
       bitmap_words += (it.nrows + 31) / 32 + 1;
+      bool fast = use_slab_dirs;
       for (uint32_t s = 0; s < ncols; s++) {
         const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
         if (!tc.present) continue;
@@ -567,7 +571,12 @@ void Query::run(const PqQueryDesc& d) {
           if (table->pages[tc.pages.first_page + mid].first_row <= it.row0) lo = mid; else hi = mid;
         }
         it.page[s] = tc.pages.first_page + lo;
+        const DevPage& pg = table->pages[it.page[s]];
+        if (pg.first_row != it.row0 || pg.num_rows != it.nrows || pg.enc == DE_DELTA) fast = false;
       }
+      it.slab0 = total_slabs;
+      if (fast && it.nrows) { total_slabs += (it.nrows + kSlabRows - 1) / kSlabRows; n_fast_items++; }
+      item_flags.push_back(fast && it.nrows ? 1u : 0u);
       items.push_back(it);
     }
   }
@@ -607,9 +616,14 @@ void Query::run(const PqQueryDesc& d) {
     L.idx[s] = (plan.cols[s].has_dict || plan.cols[s].has_delta) ? off : 0;
     off += plan.cols[s].has_delta ? kSlabRows * 8 : (plan.cols[s].has_dict ? kSlabRows * 4 : 0);
     L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
-    L.valdir[s] = off;
-    off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
+    for (int b = 0; b < 2; b++) {   // bulk-copy destination for prebuilt directories: 16-byte aligned
+      off = align_up(off, 16);
+      L.valdir[s][b] = off;
+      off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
+    }
   }
+  off = align_up(off, 16);
+  L.recs = off; off += uint32_t(kRecBatch * std::max<uint32_t>(ncols, 1) * sizeof(DevSlabRec));
   L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
   L.sel = off; off += kSlabWords * 4;
   L.lutc = off; if (plan.fast_and) off += nleaves * kLutCacheBytes;
@@ -841,6 +855,31 @@ void Query::run(const PqQueryDesc& d) {
   if (want_rows) algo_bytes += metrics.rows_scanned / 8;
   metrics.algorithmic_bytes = algo_bytes;
 
+  // ---- slab directory pre-pass: every (item, column) run-header walk at once ----
+  DevBuf<uint32_t> d_item_flags;
+  DevBuf<DevSlabRec> d_slab_recs;
+  DevBuf<DirEntry> d_slab_dirs;
+  if (n_fast_items) {
+    d_item_flags.upload(item_flags, stream);
+    d_slab_recs.alloc(size_t(total_slabs) * ncols, stream);
+    d_slab_dirs.alloc(size_t(total_slabs) * ncols * kFastDirEntries, stream);
+    SlabDirArgs sd{};
+    sd.arena = table->d_arena;
+    sd.pages = table->d_pages;
+    sd.chunks = d_chunks.p;
+    sd.items = d_items.p;
+    sd.n_items = uint32_t(items.size());
+    sd.ncols = ncols;
+    for (uint32_t s = 0; s < ncols; s++) sd.valwin_cap[s] = L.valwin_cap[s];
+    sd.item_flags = d_item_flags.p;
+    sd.slab_recs = d_slab_recs.p;
+    sd.slab_dirs = d_slab_dirs.p;
+    const uint32_t nthreads = uint32_t(items.size()) * ncols;
+    k_slab_dirs<<<(nthreads + 63) / 64, 64, 0, stream>>>(sd);
+    PQB_CUDA(cudaGetLastError());
+    launches++;
+  }
+
   // ---- the fused scan ----
   DevScanArgs sa{};
   sa.arena = table->d_arena;
@@ -854,6 +893,9 @@ void Query::run(const PqQueryDesc& d) {
   sa.item_counts = d_item_counts.p;
   sa.acc = d_acc.p;
   sa.counters = d_counters.p;
+  sa.item_flags = d_item_flags.p;
+  sa.slab_recs = d_slab_recs.p;
+  sa.slab_dirs = d_slab_dirs.p;
   if (!items.empty()) {
     PQB_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
     int occ = 1;

@@ -51,10 +51,11 @@ struct SmemLayout {
   uint32_t rank[kMaxCols];    // uint32[kSlabWords]
   uint32_t idx[kMaxCols];     // uint32[kSlabRows]  (0: indices of this column are never staged)
   uint32_t defdir[kMaxCols];  // DirEntry[kMaxDirEntries]
-  uint32_t valdir[kMaxCols];
+  uint32_t valdir[kMaxCols][2];  // DirEntry / DeltaEntry directory of the value stream, double buffered
   uint32_t leafT;             // uint32[nleaves][kSlabWords + 2]
   uint32_t sel;               // uint32[kSlabWords]
   uint32_t acc;               // shared accumulator table
+  uint32_t recs;              // DevSlabRec[kRecBatch][ncols]: slab records of the current fast item
   uint32_t lutc;              // uint8[nleaves][kLutCacheBytes]: leaf LUTs of the current row group (fast AND path)
   uint32_t total;
 };
@@ -178,7 +179,7 @@ __device__ __forceinline__ void or_bits(uint32_t* bm, uint32_t pos, uint32_t wor
 // two sentinel entries (start = ~0) behind the last directory entry: the row pass may always look
 // one and two entries ahead without a bounds test
 __device__ __forceinline__ void dir_sentinels(DirEntry* dir, uint32_t n) {
-  dir[n].start = 0xffffffffu; dir[n].count = 0; dir[n].kind = 0; dir[n].chunk0 = 0; dir[n].payload = 0;
+  dir[n].start = 0xffffffffu; dir[n].count = 0; dir[n].kind = 0; dir[n].chunk0 = 0; dir[n].payload = 0; dir[n]._pad = 0;
   dir[n + 1] = dir[n];
 }
 
@@ -321,7 +322,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout
   SlabCol& s = ctl.slab[c];
   const uint32_t nv = s.nv;
   int64_t* vals = smem_at<int64_t>(smem, L.idx[c]);
-  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c]);
+  const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c][buf]);
   const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
   for (uint32_t e = warp_id(); e < s.nval; e += kScanWarps) {
     const DeltaEntry d = dir[e];
@@ -366,7 +367,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout
 __device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
                                              uint32_t base_row, uint32_t r, bool in) {
   const SlabCol& s = ctl.slab[c];
-  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
+  const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
   const uint32_t n = s.nval;
   uint32_t e = ctl.wcur[warp_id()][c];
   while (e + 1 < n && dir[e + 1].start <= base_row) e++;
@@ -558,13 +559,13 @@ __device__ __forceinline__ uint32_t octet_leaf(const uint32_t* __restrict__ dirw
 #pragma unroll
     for (uint32_t step = 32; step; step >>= 1) {
       const uint32_t c = e + step;
-      if (c < nent && dirw[c * 3] <= r) e = c;
+      if (c < nent && dirw[c * kDirWords] <= r) e = c;
     }
   } else {
-    while (dirw[(e + 1) * 3] <= r) e++;
+    while (dirw[(e + 1) * kDirWords] <= r) e++;
   }
-  const uint32_t* A = dirw + e * 3;
-  const uint32_t start = A[0], meta = A[1], payload = A[2], next = A[3];
+  const uint32_t* A = dirw + e * kDirWords;
+  const uint32_t start = A[0], meta = A[1], payload = A[2], next = A[kDirWords];
   const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
   uint32_t m = 0;
   if (r + 8 <= next) {
@@ -612,8 +613,8 @@ __device__ __forceinline__ uint32_t octet_leaf(const uint32_t* __restrict__ dirw
   for (uint32_t k = 0; k < 8; k++) {
     if (!((need >> k) & 1)) continue;
     const uint32_t rr = r + k;
-    while (dirw[(e + 1) * 3] <= rr) e++;
-    const uint32_t* B = dirw + e * 3;
+    while (dirw[(e + 1) * kDirWords] <= rr) e++;
+    const uint32_t* B = dirw + e * kDirWords;
     uint32_t v = B[2];
     if (B[1] & 0x10000u) {
       const uint32_t bit = B[2] + (rr - B[0]) * bw;
@@ -639,7 +640,7 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     if (sel8 == 0) break;  // per thread: nothing left in its octet (most octets once a selective leaf ran)
     const DevLeaf& lf = plan.leaves[l];
     const SlabCol& s = ctl.slab[lf.col];
-    sel8 &= octet_leaf(smem_at<uint32_t>(smem, L.valdir[lf.col]), s.nval, smem_at<uint32_t>(smem, L.valwin[lf.col][buf]), s.bw, r8,
+    sel8 &= octet_leaf(smem_at<uint32_t>(smem, L.valdir[lf.col][buf]), s.nval, smem_at<uint32_t>(smem, L.valwin[lf.col][buf]), s.bw, r8,
                        sel8, ctl.lut_smem[l] != 0, smem + L.lutc + l * kLutCacheBytes, a.luts + lf.lut_off + s.lut_base);
   }
   if (!agg_mode && (!plan.write_bitmap || ((r_item & 7u) == 0))) {
@@ -807,10 +808,10 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
         Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
         uint32_t n = 0;
         uint32_t got = c.enc == DE_DELTA
-                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
+                           ? walk_delta(c.dl, w, s.nv, smem_at<DeltaEntry>(smem, L.valdir[mycol][buf]), n, kMaxDeltaEntries)
+                           : walk_stream(c.val, w, s.nv, smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n, kMaxDirEntries - 2);
         s.nval = n;
-        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
+        if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n);
         if (got < s.nv) {  // rows [0, rc) hold exactly `got` non-null values
           if (s.all_valid) rc = got;
           else {
@@ -840,6 +841,300 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
     return R;
   }
   return 0;
+}
+
+// cache this row group's leaf LUTs (one byte per dictionary entry) in shared memory (fast AND pass)
+__device__ __forceinline__ void fill_lut_cache(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem,
+                                               const DevScanArgs& a, uint32_t rg) {
+  if (!plan.fast_and) return;
+  for (uint32_t l = 0; l < plan.nleaves; l++) {
+    const DevLeaf& lf = plan.leaves[l];
+    const DevChunk ch = a.chunks[rg * plan.ncols + lf.col];
+    const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
+    if (threadIdx.x == 0) ctl.lut_smem[l] = fits;
+    if (fits) {
+      const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
+      uint8_t* dst = smem + L.lutc + l * kLutCacheBytes;
+      for (uint32_t i = threadIdx.x; i < ch.dict_n; i += kScanThreads) dst[i] = src[i];
+    }
+  }
+}
+
+// thread 0: stage slab k (of the record batch in shared memory) of a fast item into buffer `buf`:
+// the value windows and the prebuilt run directories, one mbarrier transaction
+__device__ __forceinline__ void fast_issue(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const DevScanArgs& a,
+                                           const DevSlabRec* recs, uint32_t slab_global, uint32_t k, uint32_t ncols, uint32_t buf) {
+  uint32_t bytes = 0;
+  for (uint32_t c = 0; c < ncols; c++) {
+    const DevSlabRec& rc = recs[k * ncols + c];
+    if (PQB_ENC_HAS_STREAM(rc.enc) && rc.nent) bytes += L.valwin_cap[c] + (uint32_t(rc.nent) + 2u) * uint32_t(sizeof(DirEntry));
+  }
+  mbar_arrive_expect_tx(&ctl.mbar[buf], bytes);
+  for (uint32_t c = 0; c < ncols; c++) {
+    const DevSlabRec& rc = recs[k * ncols + c];
+    if (!(PQB_ENC_HAS_STREAM(rc.enc) && rc.nent)) continue;
+    tma_load_1d(smem + L.valwin[c][buf], a.arena + rc.win_off, L.valwin_cap[c], &ctl.mbar[buf]);
+    tma_load_1d(smem + L.valdir[c][buf], a.slab_dirs + (size_t(slab_global + k) * ncols + c) * kFastDirEntries,
+                (uint32_t(rc.nent) + 2u) * uint32_t(sizeof(DirEntry)), &ctl.mbar[buf]);
+  }
+}
+
+// ---- slab directory pre-pass -------------------------------------------------------------------
+// The run headers of an RLE / bit-packed hybrid stream can only be walked sequentially, and inside
+// k_scan that walk sat on the critical path of every slab (one lane busy, 255 waiting: 40 % of all
+// stall samples in profiles/k_scan_r1c).  But every (item, column) stream is independent of every
+// other, so this kernel walks them all at once, one thread each, reading the few header bytes
+// straight from HBM/L2, and leaves per slab exactly what the in-kernel control would have built:
+// the window start, the run directory (window-relative bit offsets) and the page cursor.  Items it
+// cannot cover (NULLs in the definition levels, DELTA pages, more runs than kFastDirEntries, a
+// window that does not hold a whole slab) are flagged back to the in-kernel path.
+struct SlabDirArgs {
+  const uint8_t* arena;
+  const DevPage* pages;
+  const DevChunk* chunks;
+  const DevItem* items;
+  uint32_t n_items, ncols;
+  uint32_t valwin_cap[kMaxCols];
+  uint32_t* item_flags;
+  DevSlabRec* slab_recs;
+  DirEntry* slab_dirs;
+};
+
+__global__ void k_slab_dirs(const __grid_constant__ SlabDirArgs p) {
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n_items * p.ncols) return;
+  const uint32_t it = idx / p.ncols, c = idx % p.ncols;
+  if (!p.item_flags[it]) return;
+  const DevItem& item = p.items[it];
+  const DevChunk ch = p.chunks[item.rg * p.ncols + c];
+  const uint32_t nslabs = (item.nrows + kSlabRows - 1) / kSlabRows;
+  DevSlabRec rec{};
+  if (!ch.present) {
+    rec.enc = DE_PLAIN;
+    for (uint32_t k = 0; k < nslabs; k++) p.slab_recs[size_t(item.slab0 + k) * p.ncols + c] = rec;
+    return;
+  }
+  ColCursor cur;
+  page_enter(cur, p.pages, item.page[c]);
+  if (cur.enc == DE_DELTA) { p.item_flags[it] = 0; return; }
+  uint32_t rows_left = item.nrows;
+  for (uint32_t k = 0; k < nslabs; k++) {
+    const uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
+    if (cur.has_def) {  // every definition level of the slab must be 1 (RLE runs of 1s)
+      const uint64_t base = stream_window_start(cur.def) & ~15ull;
+      const Window w{p.arena + base, base, uint32_t(cur.def.end - base)};
+      uint32_t covered = 0;
+      bool ok = true;
+      while (covered < R && ok) {
+        DirEntry tmp[4];
+        uint32_t n = 0;
+        const uint32_t got = walk_stream(cur.def, w, R - covered, tmp, n, 4);
+        for (uint32_t e = 0; e < n; e++) ok = ok && tmp[e].kind == 0 && (tmp[e].payload & 1);
+        ok = ok && got != 0;
+        covered += got;
+      }
+      if (!ok) { p.item_flags[it] = 0; return; }
+    }
+    rec.win_off = 0;
+    rec.nent = 0;
+    rec.bw = 0;
+    if (PQB_ENC_HAS_STREAM(cur.enc)) {
+      const uint64_t base = stream_window_start(cur.val) & ~15ull;
+      const Window w{p.arena + base, base, p.valwin_cap[c]};
+      DirEntry* out = p.slab_dirs + (size_t(item.slab0 + k) * p.ncols + c) * kFastDirEntries;
+      uint32_t n = 0;
+      const uint32_t got = walk_stream(cur.val, w, R, out, n, kFastDirEntries - 2);
+      if (got < R || n == 0) { p.item_flags[it] = 0; return; }
+      dir_sentinels(out, n);
+      rec.win_off = base;
+      rec.nent = uint16_t(n);
+      rec.bw = cur.val.bw;
+    }
+    rec.val_base = cur.val_base;
+    rec.vals_done = cur.vals_done;
+    rec.enc = uint8_t(cur.enc);
+    p.slab_recs[size_t(item.slab0 + k) * p.ncols + c] = rec;
+    cur.vals_done += R;
+    rows_left -= R;
+  }
+}
+
+// ---- the row phase of one slab: DELTA decode, then the row pass the slab qualifies for; adds the
+// selected rows to ctl.sel_count.  All threads of the CTA call it. ----
+__device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const DevScanArgs& a,
+                                          const DevItem& item, uint32_t mode, uint32_t has_delta, uint32_t buf, uint32_t R,
+                                          uint32_t r_item, unsigned long long* acc, bool agg_mode) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ncols = plan.ncols;
+  const uint32_t nslots = plan.nslots;
+  uint32_t* selw = smem_at<uint32_t>(smem, L.sel);
+  uint32_t* leafT = smem_at<uint32_t>(smem, L.leafT);
+  // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
+  if (has_delta)
+    for (uint32_t c = 0; c < ncols; c++)
+      if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
+  const uint32_t nwords = (R + 31) >> 5;
+  uint32_t cnt = 0;
+  const bool fast_and = mode == MODE_FAST_AND;
+  if (fast_and) {
+    // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
+    cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+  } else if (mode == MODE_ROW_MAJOR) {
+    // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
+    cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+  } else {
+  // ---- 4. (general) unpack: fused index -> leaf bits where possible, else stage indices ----
+  for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
+  __syncthreads();
+  for (uint32_t c = 0; c < ncols; c++) {
+    const SlabCol& s = ctl.slab[c];
+    if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
+    uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
+    const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
+    const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
+    // leaves of this column that a dictionary LUT answers (host precomputed lists)
+    const uint32_t nlut = plan.col_nlut[c];
+    if (s.enc == DE_DICT && s.all_valid && nlut >= 1 && nlut <= 2) {
+      const int l0 = plan.col_l0[c], l1 = plan.col_l1[c];
+      const uint8_t* lut0 = a.luts + plan.leaves[l0].lut_off + s.lut_base;
+      uint32_t* i_st = plan.cols[c].need_idx ? idx : nullptr;
+      if (nlut == 2)
+        dir_to_leafbits<true>(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords,
+                              a.luts + plan.leaves[l1].lut_off + s.lut_base, leafT + l1 * kLeafWords, i_st);
+      else
+        dir_to_leafbits<false>(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords, nullptr, nullptr, i_st);
+    } else if (idx) {
+      dir_to_idx(dir, s.nval, win, s.bw, idx);
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. leaves the fused pass did not answer: PLAIN pages, NULL-carrying slabs, booleans ----
+  for (uint32_t l = 0; l < plan.nleaves; l++) {
+    const DevLeaf& lf = plan.leaves[l];
+    if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
+    const SlabCol& s = ctl.slab[lf.col];
+    if (!s.present) continue;                                 // all NULL: T stays 0
+    if (s.enc == DE_DICT && s.all_valid && plan.col_nlut[lf.col] <= 2) continue;  // answered by the fused pass
+    const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
+    const uint32_t* rk = smem_at<uint32_t>(smem, L.rank[lf.col]);
+    const uint32_t* idx = smem_at<uint32_t>(smem, L.idx[lf.col]);
+    uint32_t* Tw = leafT + l * kLeafWords;
+    const uint8_t kind = plan.cols[lf.col].kind;
+    const uint8_t* lut = a.luts + lf.lut_off + s.lut_base;
+    const int64_t lit = lf.lit_i64;
+    const int64_t litk = f64_order_key((uint64_t)lf.lit_i64);
+    const uint32_t op = lf.cmp;
+    for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
+      uint32_t r = r0 + lane_id();
+      bool t = false;
+      if (r < R) {
+        RowVal rv = row_rank(s, vbm, rk, r);
+        if (rv.valid) {
+          if (s.enc == DE_DICT) t = lut[idx[rv.j]] != 0;
+          else if (kind == DK_BOOL) t = cmp_i64((int64_t)value_bool(s, a.arena, idx, rv.j), lit, op);
+          else if (kind == DK_I64) t = cmp_i64((int64_t)value_u64(s, a.arena, idx, rv.j), lit, op);
+          else if (kind == DK_F64) t = cmp_i64(f64_order_key(value_u64(s, a.arena, idx, rv.j)), litk, op);
+        }
+      }
+      uint32_t tw = __ballot_sync(0xffffffffu, t);
+      if (lane_id() == 0) Tw[r0 >> 5] = tw;
+    }
+  }
+  __syncthreads();
+
+  // ---- 6. Kleene combine on words -> selection; filter mode consumes right here ----
+  for (uint32_t w = tid; w < nwords; w += kScanThreads) {
+    uint32_t st_t[kPredStack], st_n[kPredStack];
+    int sp = 0;
+    const uint32_t rm = row_mask(w, R);
+#pragma unroll 1
+    for (uint32_t i = 0; i < plan.npred; i++) {
+      const DevPredOp op = plan.pred[i];
+      if (op.kind == PK_LEAF) {
+        const DevLeaf& lf = plan.leaves[op.arg];
+        const SlabCol& s = ctl.slab[lf.col];
+        uint32_t V = !s.present ? 0u : (s.all_valid ? 0xffffffffu : smem_at<uint32_t>(smem, L.valid[lf.col])[w]);
+        uint32_t t, n;
+        if (lf.kind == LK_IS_NULL) { t = ~V; n = 0; }
+        else if (lf.kind == LK_IS_NOT_NULL) { t = V; n = 0; }
+        else { t = leafT[op.arg * kLeafWords + w] & V; n = ~V; }
+        st_t[sp] = t;
+        st_n[sp] = n;
+        sp++;
+      } else if (op.kind == PK_CONST) {
+        st_t[sp] = op.arg == 1 ? 0xffffffffu : 0u;
+        st_n[sp] = op.arg == 2 ? 0xffffffffu : 0u;
+        sp++;
+      } else if (op.kind == PK_NOT) {
+        st_t[sp - 1] = ~(st_t[sp - 1] | st_n[sp - 1]);
+      } else {
+        uint32_t tb = st_t[sp - 1], nb = st_n[sp - 1], ta = st_t[sp - 2], na = st_n[sp - 2];
+        sp--;
+        if (op.kind == PK_AND) {
+          uint32_t fa = ~(ta | na), fb = ~(tb | nb);
+          st_t[sp - 1] = ta & tb;
+          st_n[sp - 1] = (na | nb) & ~fa & ~fb;
+        } else {
+          uint32_t t = ta | tb;
+          st_t[sp - 1] = t;
+          st_n[sp - 1] = (na | nb) & ~t;
+        }
+      }
+    }
+    uint32_t sel = (plan.npred ? st_t[0] : 0xffffffffu) & rm;
+    if (agg_mode) selw[w] = sel;
+    else {
+      cnt += __popc(sel);
+      if (plan.write_bitmap && sel) {
+        uint32_t pos = r_item + w * 32;
+        uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
+        uint32_t sh = pos & 31;
+        if (sh == 0) *dst = sel;  // slabs are word aligned except after a pathological shrink
+        else {
+          atomicOr(dst, sel << sh);
+          uint32_t hi = sel >> (32 - sh);
+          if (hi) atomicOr(dst + 1, hi);
+        }
+      }
+    }
+  }
+  if (agg_mode) {
+    __syncthreads();
+    for (uint32_t r = tid; r < R; r += kScanThreads) {
+      if (!((selw[r >> 5] >> (r & 31)) & 1)) continue;
+      cnt++;
+      uint32_t slot = 0;
+      for (uint32_t k = 0; k < plan.nkeys; k++) {
+        const DevKey& key = plan.keys[k];
+        const SlabCol& s = ctl.slab[key.col];
+        RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
+        uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
+        if (rv.valid) {
+          if (key.kind == KK_BOOL) gid = value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[key.col]), rv.j);
+          else gid = a.gid_luts[key.gid_off + s.lut_base + smem_at<uint32_t>(smem, L.idx[key.col])[rv.j]];
+        }
+        slot += gid * key.stride;
+      }
+      atomicAdd(&acc[slot], 1ull);
+      for (uint32_t g = 0; g < plan.naggs; g++) {
+        const DevAgg& ag = plan.aggs[g];
+        if (ag.fn == AG_COUNT_STAR) continue;
+        const SlabCol& s = ctl.slab[ag.col];
+        RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
+        if (!rv.valid) continue;
+        if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+        if (ag.fn == AG_COUNT) continue;
+        uint64_t bits = ag.kind == DK_BOOL ? value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j)
+                                           : value_u64(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j);
+        acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
+      }
+    }
+  }
+  }  // general row phase
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
+
 }
 
 __global__ void __launch_bounds__(kScanThreads, PQB_SCAN_MIN_BLOCKS)
@@ -876,8 +1171,6 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
   const uint32_t nslots = plan.nslots;
 
   uint32_t phases = 0;  // bit b: parity to wait for on mbar[b]
-  uint32_t* selw = smem_at<uint32_t>(smem, L.sel);
-  uint32_t* leafT = smem_at<uint32_t>(smem, L.leafT);
 
   for (;;) {
     __syncthreads();
@@ -886,6 +1179,77 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     const uint32_t item_id = ctl.item;
     if (item_id >= plan.n_items) break;
     const DevItem& item = a.items[item_id];
+
+    if (a.item_flags && a.item_flags[item_id]) {
+      // ---------------- fast item: k_slab_dirs prebuilt every slab's run directory ----------------
+      // no header walk, no cursor: per slab one wait for the staged bytes, the row phase, and the
+      // bulk copies of the slab after next
+      if (tid < ncols) {
+        const DevChunk ch = a.chunks[item.rg * ncols + tid];
+        SlabCol& s = ctl.slab[tid];
+        s.lut_base = ch.lut_base;
+        s.dict_off = ch.dict_off;
+        s.present = ch.present;
+        s.ndef = 0;
+        s.all_valid = 1;
+      }
+      if (tid == 0) ctl.sel_count = 0;
+      fill_lut_cache(plan, ctl, L, smem, a, item.rg);
+      DevSlabRec* recs = smem_at<DevSlabRec>(smem, L.recs);
+      const uint32_t nslabs = (item.nrows + kSlabRows - 1) / kSlabRows;
+      uint32_t r_item = 0;
+      for (uint32_t k0 = 0; k0 < nslabs; k0 += kRecBatch) {
+        const uint32_t nb = nslabs - k0 < (uint32_t)kRecBatch ? nslabs - k0 : (uint32_t)kRecBatch;
+        {  // this batch's slab records -> shared memory
+          const uint4* src = reinterpret_cast<const uint4*>(a.slab_recs + size_t(item.slab0 + k0) * ncols);
+          uint4* dst = reinterpret_cast<uint4*>(recs);
+          for (uint32_t i = tid; i < nb * ncols * uint32_t(sizeof(DevSlabRec) / 16); i += kScanThreads) dst[i] = src[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+          fast_issue(ctl, L, smem, a, recs, item.slab0 + k0, 0, ncols, 0);
+          if (nb > 1) fast_issue(ctl, L, smem, a, recs, item.slab0 + k0, 1, ncols, 1);
+        }
+        for (uint32_t k = 0; k < nb; k++) {
+          const uint32_t buf = k & 1u;
+          const uint32_t R = item.nrows - r_item < (uint32_t)kSlabRows ? item.nrows - r_item : (uint32_t)kSlabRows;
+          if (tid < ncols) {
+            const DevSlabRec& rc = recs[k * ncols + tid];
+            SlabCol& s = ctl.slab[tid];
+            s.val_base = rc.val_base;
+            s.vals_done = rc.vals_done;
+            s.enc = rc.enc;
+            s.bw = rc.bw;
+            s.nval = rc.nent;
+            s.nv = s.present ? R : 0;
+          }
+          if (tid == 0) {
+            uint32_t mode = MODE_GENERIC;
+            bool fa = plan.fast_and != 0;
+            for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
+              const uint32_t c = plan.leaves[l].col;
+              const DevSlabRec& rc = recs[k * ncols + c];
+              fa = ctl.slab[c].present && rc.enc == DE_DICT && rc.nent > 0;
+            }
+            if (fa) mode = MODE_FAST_AND;
+            else if (plan.row_major) mode = MODE_ROW_MAJOR;
+            ctl.mode = mode;
+            mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
+          }
+          phases ^= 1u << buf;
+          __syncthreads();
+          row_phase(plan, ctl, L, smem, a, item, ctl.mode, 0, buf, R, r_item, acc, agg_mode);
+          r_item += R;
+          __syncthreads();
+          if (tid == 0 && k + 2 < nb) fast_issue(ctl, L, smem, a, recs, item.slab0 + k0, k + 2, ncols, buf);
+        }
+      }
+      if (tid == 0) {
+        if (a.item_counts) a.item_counts[item_id] = ctl.sel_count;
+        if (ctl.sel_count) atomicAdd(&a.counters[0], (unsigned long long)ctl.sel_count);
+      }
+      continue;
+    }
 
     if (tid < ncols) {
       ColCursor& c = ctl.cur[tid];
@@ -900,20 +1264,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       else { c.page_rows_left = 0xffffffffu; c.enc = DE_PLAIN; c.has_def = 0; c.vals_done = 0; }
     }
     if (tid == 0) ctl.sel_count = 0;
-    if (plan.fast_and) {
-      // cache this row group's leaf LUTs (one byte per dictionary entry) in shared memory
-      for (uint32_t l = 0; l < plan.nleaves; l++) {
-        const DevLeaf& lf = plan.leaves[l];
-        const DevChunk ch = a.chunks[item.rg * ncols + lf.col];
-        const bool fits = ch.present && ch.dict_n <= (uint32_t)kLutCacheBytes;
-        if (tid == 0) ctl.lut_smem[l] = fits;
-        if (fits) {
-          const uint8_t* src = a.luts + lf.lut_off + ch.lut_base;
-          uint8_t* dst = smem + L.lutc + l * kLutCacheBytes;
-          for (uint32_t i = tid; i < ch.dict_n; i += kScanThreads) dst[i] = src[i];
-        }
-      }
-    }
+    fill_lut_cache(plan, ctl, L, smem, a, item.rg);
     __syncthreads();
 
     uint32_t rows_left = item.nrows;
@@ -960,10 +1311,10 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
               Window w{smem + L.valwin[mycol][buf], c.valwin_base[buf], L.valwin_cap[mycol]};
               uint32_t n = 0;
               rc = c.enc == DE_DELTA
-                       ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol]), n, kMaxDeltaEntries)
-                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol]), n, kMaxDirEntries - 2);
+                       ? walk_delta(c.dl, w, R0w, smem_at<DeltaEntry>(smem, L.valdir[mycol][buf]), n, kMaxDeltaEntries)
+                       : walk_stream(c.val, w, R0w, smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n, kMaxDirEntries - 2);
               s.nval = n;
-              if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol]), n);
+              if (c.enc != DE_DELTA) dir_sentinels(smem_at<DirEntry>(smem, L.valdir[mycol][buf]), n);
             }
           }
           if (rc < R0w) atomicMin(&ctl.rmin_all, rc);
@@ -1058,171 +1409,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       }
       if (ctl.error) break;
 
-      // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
-      if (has_delta)
-        for (uint32_t c = 0; c < ncols; c++)
-          if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
-      const uint32_t nwords = (R + 31) >> 5;
-      uint32_t cnt = 0;
-      const bool fast_and = mode == MODE_FAST_AND;
-      if (fast_and) {
-        // ---- 4-6 (specialised): conjunction of dictionary-LUT leaves, registers only ----
-        cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
-      } else if (mode == MODE_ROW_MAJOR) {
-        // ---- 4-6 (row-major variant): one warp per 32-row word, registers only ----
-        cnt = fast_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
-      } else {
-      // ---- 4. (general) unpack: fused index -> leaf bits where possible, else stage indices ----
-      for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
-      __syncthreads();
-      for (uint32_t c = 0; c < ncols; c++) {
-        const SlabCol& s = ctl.slab[c];
-        if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
-        uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
-        const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c]);
-        const uint32_t* win = smem_at<uint32_t>(smem, L.valwin[c][buf]);
-        // leaves of this column that a dictionary LUT answers (host precomputed lists)
-        const uint32_t nlut = plan.col_nlut[c];
-        if (s.enc == DE_DICT && s.all_valid && nlut >= 1 && nlut <= 2) {
-          const int l0 = plan.col_l0[c], l1 = plan.col_l1[c];
-          const uint8_t* lut0 = a.luts + plan.leaves[l0].lut_off + s.lut_base;
-          uint32_t* i_st = plan.cols[c].need_idx ? idx : nullptr;
-          if (nlut == 2)
-            dir_to_leafbits<true>(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords,
-                                  a.luts + plan.leaves[l1].lut_off + s.lut_base, leafT + l1 * kLeafWords, i_st);
-          else
-            dir_to_leafbits<false>(dir, s.nval, win, s.bw, lut0, leafT + l0 * kLeafWords, nullptr, nullptr, i_st);
-        } else if (idx) {
-          dir_to_idx(dir, s.nval, win, s.bw, idx);
-        }
-      }
-      __syncthreads();
-
-      // ---- 5. leaves the fused pass did not answer: PLAIN pages, NULL-carrying slabs, booleans ----
-      for (uint32_t l = 0; l < plan.nleaves; l++) {
-        const DevLeaf& lf = plan.leaves[l];
-        if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
-        const SlabCol& s = ctl.slab[lf.col];
-        if (!s.present) continue;                                 // all NULL: T stays 0
-        if (s.enc == DE_DICT && s.all_valid && plan.col_nlut[lf.col] <= 2) continue;  // answered by the fused pass
-        const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
-        const uint32_t* rk = smem_at<uint32_t>(smem, L.rank[lf.col]);
-        const uint32_t* idx = smem_at<uint32_t>(smem, L.idx[lf.col]);
-        uint32_t* Tw = leafT + l * kLeafWords;
-        const uint8_t kind = plan.cols[lf.col].kind;
-        const uint8_t* lut = a.luts + lf.lut_off + s.lut_base;
-        const int64_t lit = lf.lit_i64;
-        const int64_t litk = f64_order_key((uint64_t)lf.lit_i64);
-        const uint32_t op = lf.cmp;
-        for (uint32_t r0 = warp_id() * 32; r0 < R; r0 += kScanThreads) {
-          uint32_t r = r0 + lane_id();
-          bool t = false;
-          if (r < R) {
-            RowVal rv = row_rank(s, vbm, rk, r);
-            if (rv.valid) {
-              if (s.enc == DE_DICT) t = lut[idx[rv.j]] != 0;
-              else if (kind == DK_BOOL) t = cmp_i64((int64_t)value_bool(s, a.arena, idx, rv.j), lit, op);
-              else if (kind == DK_I64) t = cmp_i64((int64_t)value_u64(s, a.arena, idx, rv.j), lit, op);
-              else if (kind == DK_F64) t = cmp_i64(f64_order_key(value_u64(s, a.arena, idx, rv.j)), litk, op);
-            }
-          }
-          uint32_t tw = __ballot_sync(0xffffffffu, t);
-          if (lane_id() == 0) Tw[r0 >> 5] = tw;
-        }
-      }
-      __syncthreads();
-
-      // ---- 6. Kleene combine on words -> selection; filter mode consumes right here ----
-      for (uint32_t w = tid; w < nwords; w += kScanThreads) {
-        uint32_t st_t[kPredStack], st_n[kPredStack];
-        int sp = 0;
-        const uint32_t rm = row_mask(w, R);
-#pragma unroll 1
-        for (uint32_t i = 0; i < plan.npred; i++) {
-          const DevPredOp op = plan.pred[i];
-          if (op.kind == PK_LEAF) {
-            const DevLeaf& lf = plan.leaves[op.arg];
-            const SlabCol& s = ctl.slab[lf.col];
-            uint32_t V = !s.present ? 0u : (s.all_valid ? 0xffffffffu : smem_at<uint32_t>(smem, L.valid[lf.col])[w]);
-            uint32_t t, n;
-            if (lf.kind == LK_IS_NULL) { t = ~V; n = 0; }
-            else if (lf.kind == LK_IS_NOT_NULL) { t = V; n = 0; }
-            else { t = leafT[op.arg * kLeafWords + w] & V; n = ~V; }
-            st_t[sp] = t;
-            st_n[sp] = n;
-            sp++;
-          } else if (op.kind == PK_CONST) {
-            st_t[sp] = op.arg == 1 ? 0xffffffffu : 0u;
-            st_n[sp] = op.arg == 2 ? 0xffffffffu : 0u;
-            sp++;
-          } else if (op.kind == PK_NOT) {
-            st_t[sp - 1] = ~(st_t[sp - 1] | st_n[sp - 1]);
-          } else {
-            uint32_t tb = st_t[sp - 1], nb = st_n[sp - 1], ta = st_t[sp - 2], na = st_n[sp - 2];
-            sp--;
-            if (op.kind == PK_AND) {
-              uint32_t fa = ~(ta | na), fb = ~(tb | nb);
-              st_t[sp - 1] = ta & tb;
-              st_n[sp - 1] = (na | nb) & ~fa & ~fb;
-            } else {
-              uint32_t t = ta | tb;
-              st_t[sp - 1] = t;
-              st_n[sp - 1] = (na | nb) & ~t;
-            }
-          }
-        }
-        uint32_t sel = (plan.npred ? st_t[0] : 0xffffffffu) & rm;
-        if (agg_mode) selw[w] = sel;
-        else {
-          cnt += __popc(sel);
-          if (plan.write_bitmap && sel) {
-            uint32_t pos = r_item + w * 32;
-            uint32_t* dst = a.bitmap + item.bitmap_word0 + (pos >> 5);
-            uint32_t sh = pos & 31;
-            if (sh == 0) *dst = sel;  // slabs are word aligned except after a pathological shrink
-            else {
-              atomicOr(dst, sel << sh);
-              uint32_t hi = sel >> (32 - sh);
-              if (hi) atomicOr(dst + 1, hi);
-            }
-          }
-        }
-      }
-      if (agg_mode) {
-        __syncthreads();
-        for (uint32_t r = tid; r < R; r += kScanThreads) {
-          if (!((selw[r >> 5] >> (r & 31)) & 1)) continue;
-          cnt++;
-          uint32_t slot = 0;
-          for (uint32_t k = 0; k < plan.nkeys; k++) {
-            const DevKey& key = plan.keys[k];
-            const SlabCol& s = ctl.slab[key.col];
-            RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
-            uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
-            if (rv.valid) {
-              if (key.kind == KK_BOOL) gid = value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[key.col]), rv.j);
-              else gid = a.gid_luts[key.gid_off + s.lut_base + smem_at<uint32_t>(smem, L.idx[key.col])[rv.j]];
-            }
-            slot += gid * key.stride;
-          }
-          atomicAdd(&acc[slot], 1ull);
-          for (uint32_t g = 0; g < plan.naggs; g++) {
-            const DevAgg& ag = plan.aggs[g];
-            if (ag.fn == AG_COUNT_STAR) continue;
-            const SlabCol& s = ctl.slab[ag.col];
-            RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
-            if (!rv.valid) continue;
-            if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
-            if (ag.fn == AG_COUNT) continue;
-            uint64_t bits = ag.kind == DK_BOOL ? value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j)
-                                               : value_u64(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j);
-            acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
-          }
-        }
-      }
-      }  // general row phase
-      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      if (lane_id() == 0 && cnt) atomicAdd(&ctl.sel_count, cnt);
+      row_phase(plan, ctl, L, smem, a, item, mode, has_delta, buf, R, r_item, acc, agg_mode);
 
       rows_left -= R;
       r_item += R;
