@@ -18,7 +18,7 @@ constexpr int kDirEntryMaxValues = 512;
 constexpr int kMaxDeltaEntries = 80;  // DELTA_BINARY_PACKED miniblock directory entries per slab
 constexpr int kDeltaWindowBytes = 8192 + 64;
 constexpr int kPredStack = 8;
-constexpr int kFastDirEntries = 32;   // prebuilt run directory: entries per (slab, column) incl. 2 sentinels
+constexpr int kFastDirEntries = 16;   // slab index: run-directory entry budget per slab (a page's slabs share the page's budget)
 constexpr int kRecBatch = 16;         // slab records a CTA keeps in shared memory at a time
 
 // page value encodings as the kernels see them
@@ -39,8 +39,10 @@ struct DevPage {               // one data page
   uint32_t val_off;            // values section inside the payload
   uint8_t enc;                 // DevEnc
   uint8_t bit_width;           // DE_DICT: index bit width
-  uint16_t chunk_slot;         // which DevChunk of the row group (== column slot)
+  uint16_t chunk_slot;         // table column of this page
   uint32_t chunk;              // index into chunks[]
+  uint32_t slab0;              // first record of this page in the table's slab index
+  uint32_t flags;              // host copy only: bit 0 = every slab of the page is in the slab index
 };
 
 struct DevChunk {              // one column chunk (row group x referenced column)
@@ -60,12 +62,13 @@ struct DevItem {               // unit of CTA work: rows between two page bounda
   uint32_t bitmap_word0;       // first word of this item's region in the selection bitmap
   uint64_t global_row0;        // ordinal of row0 in the scanned table (row-id output)
   uint32_t page[kMaxCols];     // page index (into pages[]) holding row0, per column slot
-  uint32_t slab0;              // first slab of this item in the prebuilt slab directory
+  uint32_t fast;               // 1: every referenced column has exactly one, slab-indexed page over this item
   uint32_t _pad;
 };
 
-// One (slab, column) of the prebuilt slab directory (k_slab_dirs): what the per-slab control of
-// k_scan would have derived by walking the run headers, computed for every slab at once.
+// One slab (kSlabRows rows from the page start) of one page in the table's slab index
+// (k_slab_index, built when the table is opened): what the per-slab control of k_scan would derive
+// by walking the run headers, computed for every page at once.
 struct DevSlabRec {
   uint64_t win_off;            // arena offset the value window is staged from (16-byte aligned)
   uint64_t val_base;           // arena offset of the page's values section
@@ -73,7 +76,8 @@ struct DevSlabRec {
   uint16_t nent;               // run-directory entries (two sentinels follow)
   uint8_t enc;                 // DevEnc
   uint8_t bw;                  // index bit width
-  uint32_t _pad[2];
+  uint32_t ent0;               // first run-directory entry of this slab in the index (entries are 16 bytes)
+  uint32_t _pad;
 };
 
 struct DevColumn {
@@ -171,10 +175,9 @@ struct DevScanArgs {
   uint32_t* item_counts;       // selected rows per item
   unsigned long long* acc;     // accumulator table (global)
   unsigned long long* counters;  // [0] rows selected, [1] error flag, [2] work-queue head
-  // prebuilt slab directory (fast items): flags[item] != 0 -> every slab of the item has records
-  uint32_t* item_flags;
-  DevSlabRec* slab_recs;       // [(item.slab0 + k) * ncols + col]
-  struct DirEntry* slab_dirs;  // [((item.slab0 + k) * ncols + col) * kFastDirEntries + e]
+  // the table's slab index (fast items)
+  const DevSlabRec* slab_recs;       // [page.slab0 + k]
+  const struct DirEntry* slab_dirs;  // [rec.ent0 + e]
 };
 
 // run-directory entry produced by the stream walker

@@ -116,11 +116,23 @@ class Table {
   uint8_t* d_arena = nullptr;
   uint64_t arena_bytes = 0;
   DevPage* d_pages = nullptr;
+  // slab index (k_slab_index): per page, per kSlabRows rows, the run directory and window start the
+  // scan kernel would otherwise derive by walking the run headers; see DESIGN.md
+  DevSlabRec* d_slab_recs = nullptr;
+  DirEntry* d_slab_dirs = nullptr;
+  uint64_t total_slabs = 0;
+  std::vector<uint32_t> col_valwin_cap;   // per table column: staged window bytes the index was built for
   uint64_t total_rows = 0;
   uint64_t h2d_bytes = 0;
   uint64_t chunk_bytes = 0;
   int find_column(const std::string& name) const;
 };
+
+// staged window bytes for one slab of a dictionary-index stream of the given bit width
+inline uint32_t valwin_cap_for_bw(uint32_t max_bw) { return ((kSlabRows * max_bw / 8 + kSlabRows / 8 + 64) + 15u) & ~15u; }
+// launches k_slab_index (defined next to k_scan, query.cu)
+void launch_slab_index(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, const uint32_t* col_caps, DevSlabRec* recs,
+                       DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream);
 
 // page-locked host block that result batches can alias (zero copy); returns to the pool when
 // the last batch that references it is released by the consumer

@@ -189,8 +189,20 @@ Query::Query(const PqQueryDesc& d) {
 }
 Query::~Query() = default;
 
+void launch_slab_index(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, const uint32_t* col_caps, DevSlabRec* recs,
+                       DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream) {
+  if (!n_pages) return;
+  k_slab_index<<<(n_pages + 63) / 64, 64, 0, stream>>>(arena, pages, n_pages, col_caps, recs, dirs, page_fast);
+  PQB_CUDA(cudaGetLastError());
+}
+
 void Query::run(const PqQueryDesc& d) {
   const auto t_begin = std::chrono::steady_clock::now();
+  const bool verbose = getenv("PQB_VERBOSE") != nullptr;
+  auto mark = [&](const char* what) {   // PQB_VERBOSE: host timeline of this query
+    if (verbose)
+      fprintf(stderr, "[pqb] +%.3f ms %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what);
+  };
   struct HostTimer {
     std::chrono::steady_clock::time_point t0;
     PqMetrics* m;
@@ -483,13 +495,13 @@ void Query::run(const PqQueryDesc& d) {
     plan.n_nn = uint32_t(nn_of_col.size());
   }
 
+  mark("plan compiled");
   // ---- per query chunk table, work items ----
   const uint32_t nrg = uint32_t(rgs.size());
   std::vector<DevChunk> chunks(size_t(nrg) * std::max<uint32_t>(ncols, 1));
   std::vector<DevItem> items;
-  std::vector<uint32_t> item_flags;   // 1: every referenced column has exactly one page over the item -> slab directory pre-pass
-  uint32_t total_slabs = 0, n_fast_items = 0;
-  const bool use_slab_dirs = ncols > 0 && !(getenv("PQB_SLAB_DIRS") && getenv("PQB_SLAB_DIRS")[0] == '0');   // A/B switch
+  uint32_t n_fast_items = 0;   // items the table's slab index covers: no in-kernel run-header walk
+  const bool use_slab_index = ncols > 0 && table->d_slab_recs != nullptr;
   std::vector<uint8_t> col_needs_ent(ncols, 0);  // entry offsets (string leaf / any key column)
   std::vector<uint8_t> col_has_lut(ncols, 0);
   for (uint32_t l = 0; l < nleaves; l++) {
@@ -560,7 +572,7 @@ void Query::run(const PqQueryDesc& d) {
       it.global_row0 = rg.global_row0 + common[i];
       it.bitmap_word0 = bitmap_words;
       bitmap_words += (it.nrows + 31) / 32 + 1;
-      bool fast = use_slab_dirs;
+      bool fast = use_slab_index;
       for (uint32_t s = 0; s < ncols; s++) {
         const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
         if (!tc.present) continue;
@@ -572,11 +584,10 @@ void Query::run(const PqQueryDesc& d) {
         }
         it.page[s] = tc.pages.first_page + lo;
         const DevPage& pg = table->pages[it.page[s]];
-        if (pg.first_row != it.row0 || pg.num_rows != it.nrows || pg.enc == DE_DELTA) fast = false;
+        if (pg.first_row != it.row0 || pg.num_rows != it.nrows || !(pg.flags & 1u)) fast = false;
       }
-      it.slab0 = total_slabs;
-      if (fast && it.nrows) { total_slabs += (it.nrows + kSlabRows - 1) / kSlabRows; n_fast_items++; }
-      item_flags.push_back(fast && it.nrows ? 1u : 0u);
+      it.fast = fast && it.nrows ? 1u : 0u;
+      n_fast_items += it.fast;
       items.push_back(it);
     }
   }
@@ -599,6 +610,7 @@ void Query::run(const PqQueryDesc& d) {
       throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has PLAIN (dictionary-fallback) pages; only dictionary-encoded keys are on the GPU path");
   }
 
+  mark("chunks + items built");
   // ---- shared-memory layout ----
   SmemLayout L{};
   uint32_t off = align_up(uint32_t(sizeof(ScanCtl)), 128);
@@ -606,7 +618,9 @@ void Query::run(const PqQueryDesc& d) {
     // window = bytes of one slab at the widest index + one header per 8 values + alignment slop;
     // anything denser makes the kernel shrink the slab (always correct, only slower)
     L.defwin_cap[s] = plan.cols[s].max_def ? align_up(kSlabRows / 8 + kSlabRows / 16 + 64, 16) : 0;
-    L.valwin_cap[s] = plan.cols[s].has_dict ? align_up(kSlabRows * plan.cols[s].max_bw / 8 + kSlabRows / 8 + 64, 16) : 0;
+    L.valwin_cap[s] = plan.cols[s].has_dict ? valwin_cap_for_bw(plan.cols[s].max_bw) : 0;
+    // the slab index holds window-relative bit offsets: stage at least the window it was built for
+    if (n_fast_items && plan.cols[s].has_dict) L.valwin_cap[s] = std::max(L.valwin_cap[s], table->col_valwin_cap[tcol[qcol_of_slot[s]]]);
     if (plan.cols[s].has_delta) L.valwin_cap[s] = std::max<uint32_t>(L.valwin_cap[s], align_up(kDeltaWindowBytes, 16));
     for (int b = 0; b < 2; b++) { L.defwin[s][b] = off; off += align_up(L.defwin_cap[s] + 16, 128); }
     for (int b = 0; b < 2; b++) { L.valwin[s][b] = off; off += align_up(L.valwin_cap[s] + 16, 128); }
@@ -855,31 +869,7 @@ void Query::run(const PqQueryDesc& d) {
   if (want_rows) algo_bytes += metrics.rows_scanned / 8;
   metrics.algorithmic_bytes = algo_bytes;
 
-  // ---- slab directory pre-pass: every (item, column) run-header walk at once ----
-  DevBuf<uint32_t> d_item_flags;
-  DevBuf<DevSlabRec> d_slab_recs;
-  DevBuf<DirEntry> d_slab_dirs;
-  if (n_fast_items) {
-    d_item_flags.upload(item_flags, stream);
-    d_slab_recs.alloc(size_t(total_slabs) * ncols, stream);
-    d_slab_dirs.alloc(size_t(total_slabs) * ncols * kFastDirEntries, stream);
-    SlabDirArgs sd{};
-    sd.arena = table->d_arena;
-    sd.pages = table->d_pages;
-    sd.chunks = d_chunks.p;
-    sd.items = d_items.p;
-    sd.n_items = uint32_t(items.size());
-    sd.ncols = ncols;
-    for (uint32_t s = 0; s < ncols; s++) sd.valwin_cap[s] = L.valwin_cap[s];
-    sd.item_flags = d_item_flags.p;
-    sd.slab_recs = d_slab_recs.p;
-    sd.slab_dirs = d_slab_dirs.p;
-    const uint32_t nthreads = uint32_t(items.size()) * ncols;
-    k_slab_dirs<<<(nthreads + 63) / 64, 64, 0, stream>>>(sd);
-    PQB_CUDA(cudaGetLastError());
-    launches++;
-  }
-
+  mark("prep kernels queued");
   // ---- the fused scan ----
   DevScanArgs sa{};
   sa.arena = table->d_arena;
@@ -893,9 +883,8 @@ void Query::run(const PqQueryDesc& d) {
   sa.item_counts = d_item_counts.p;
   sa.acc = d_acc.p;
   sa.counters = d_counters.p;
-  sa.item_flags = d_item_flags.p;
-  sa.slab_recs = d_slab_recs.p;
-  sa.slab_dirs = d_slab_dirs.p;
+  sa.slab_recs = table->d_slab_recs;
+  sa.slab_dirs = table->d_slab_dirs;
   if (!items.empty()) {
     PQB_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
     int occ = 1;
@@ -906,6 +895,7 @@ void Query::run(const PqQueryDesc& d) {
     if (getenv("PQB_VERBOSE"))
       fprintf(stderr, "[pqb] k_scan: %u CTAs x %d threads, %zu B smem/CTA, %d CTAs/SM, %zu items\n", grid, kScanThreads,
               size_t(smem_total), occ, items.size());
+    if (verbose) fprintf(stderr, "[pqb] %u of %zu items covered by the slab index\n", n_fast_items, items.size());
     PQB_CUDA(cudaEventRecord(t_scan.a, stream));
     k_scan<<<grid, kScanThreads, smem_total, stream>>>(plan, L, sa);
     PQB_CUDA(cudaEventRecord(t_scan.b, stream));
@@ -921,6 +911,7 @@ void Query::run(const PqQueryDesc& d) {
       fprintf(stderr, "item %zu rg %u row0 %u nrows %u g0 %llu count %u\n", i, items[i].rg, items[i].row0, items[i].nrows,
               (unsigned long long)items[i].global_row0, ic[i]);
   }
+  mark("scan queued");
   unsigned long long h_counters[4] = {0, 0, 0, 0};
   PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
   metrics.d2h_bytes += sizeof(h_counters);
@@ -1055,6 +1046,7 @@ void Query::run(const PqQueryDesc& d) {
       unsigned long long total = 0;
       PQB_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
+      mark("scan done, selected-row total on host");
       metrics.d2h_bytes += 8;
       unsigned long long keep = total;
       if (d.limit >= 0 && (unsigned long long)d.limit < keep) keep = (unsigned long long)d.limit;
@@ -1073,6 +1065,7 @@ void Query::run(const PqQueryDesc& d) {
     }
     PQB_CUDA(cudaEventRecord(t_all.b, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
+    mark("results on host");
     if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
     metrics.rows_selected = h_counters[0];
     if (has_aggs) {  // SELECT COUNT(*) [, COUNT(*)...] WHERE ...

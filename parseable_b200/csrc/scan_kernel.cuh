@@ -860,10 +860,10 @@ __device__ __forceinline__ void fill_lut_cache(const DevPlan& plan, ScanCtl& ctl
   }
 }
 
-// thread 0: stage slab k (of the record batch in shared memory) of a fast item into buffer `buf`:
-// the value windows and the prebuilt run directories, one mbarrier transaction
+// thread 0: stage slab k0 + k of a fast item (its records sit in shared memory) into buffer `buf`:
+// the value windows and the indexed run directories, one mbarrier transaction
 __device__ __forceinline__ void fast_issue(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const DevScanArgs& a,
-                                           const DevSlabRec* recs, uint32_t slab_global, uint32_t k, uint32_t ncols, uint32_t buf) {
+                                           const DevSlabRec* recs, uint32_t k0, uint32_t k, uint32_t ncols, uint32_t buf) {
   uint32_t bytes = 0;
   for (uint32_t c = 0; c < ncols; c++) {
     const DevSlabRec& rc = recs[k * ncols + c];
@@ -874,55 +874,43 @@ __device__ __forceinline__ void fast_issue(ScanCtl& ctl, const SmemLayout& L, ui
     const DevSlabRec& rc = recs[k * ncols + c];
     if (!(PQB_ENC_HAS_STREAM(rc.enc) && rc.nent)) continue;
     tma_load_1d(smem + L.valwin[c][buf], a.arena + rc.win_off, L.valwin_cap[c], &ctl.mbar[buf]);
-    tma_load_1d(smem + L.valdir[c][buf], a.slab_dirs + (size_t(slab_global + k) * ncols + c) * kFastDirEntries,
+    tma_load_1d(smem + L.valdir[c][buf], a.slab_dirs + rc.ent0,
                 (uint32_t(rc.nent) + 2u) * uint32_t(sizeof(DirEntry)), &ctl.mbar[buf]);
   }
 }
 
-// ---- slab directory pre-pass -------------------------------------------------------------------
+// ---- slab index ----------------------------------------------------------------------------------
 // The run headers of an RLE / bit-packed hybrid stream can only be walked sequentially, and inside
 // k_scan that walk sat on the critical path of every slab (one lane busy, 255 waiting: 40 % of all
-// stall samples in profiles/k_scan_r1c).  But every (item, column) stream is independent of every
-// other, so this kernel walks them all at once, one thread each, reading the few header bytes
-// straight from HBM/L2, and leaves per slab exactly what the in-kernel control would have built:
-// the window start, the run directory (window-relative bit offsets) and the page cursor.  Items it
-// cannot cover (NULLs in the definition levels, DELTA pages, more runs than kFastDirEntries, a
-// window that does not hold a whole slab) are flagged back to the in-kernel path.
-struct SlabDirArgs {
-  const uint8_t* arena;
-  const DevPage* pages;
-  const DevChunk* chunks;
-  const DevItem* items;
-  uint32_t n_items, ncols;
-  uint32_t valwin_cap[kMaxCols];
-  uint32_t* item_flags;
-  DevSlabRec* slab_recs;
-  DirEntry* slab_dirs;
-};
-
-__global__ void k_slab_dirs(const __grid_constant__ SlabDirArgs p) {
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.n_items * p.ncols) return;
-  const uint32_t it = idx / p.ncols, c = idx % p.ncols;
-  if (!p.item_flags[it]) return;
-  const DevItem& item = p.items[it];
-  const DevChunk ch = p.chunks[item.rg * p.ncols + c];
-  const uint32_t nslabs = (item.nrows + kSlabRows - 1) / kSlabRows;
-  DevSlabRec rec{};
-  if (!ch.present) {
-    rec.enc = DE_PLAIN;
-    for (uint32_t k = 0; k < nslabs; k++) p.slab_recs[size_t(item.slab0 + k) * p.ncols + c] = rec;
-    return;
-  }
+// stall samples in profiles/k_scan_r1c).  But every page's stream is independent of every other, so
+// this kernel — run once, when the table is opened — walks them all at the same time, one thread
+// per page, reading the few header bytes straight from HBM/L2, and leaves for every slab of
+// kSlabRows rows exactly what the in-kernel control would have built: the window start, the run
+// directory (window-relative bit offsets) and the page cursor.  Pages it cannot cover (NULLs in the
+// definition levels, DELTA pages, more runs per slab than kFastDirEntries, a window that does not
+// hold a whole slab) stay on the in-kernel path (page_fast = 0).
+__global__ void k_slab_index(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages, uint32_t n_pages,
+                             const uint32_t* __restrict__ col_caps, DevSlabRec* __restrict__ slab_recs,
+                             DirEntry* __restrict__ slab_dirs, uint8_t* __restrict__ page_fast) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pages) return;
   ColCursor cur;
-  page_enter(cur, p.pages, item.page[c]);
-  if (cur.enc == DE_DELTA) { p.item_flags[it] = 0; return; }
-  uint32_t rows_left = item.nrows;
+  page_enter(cur, pages, i);
+  const DevPage& pg = pages[i];
+  const uint32_t cap = col_caps[pg.chunk_slot];
+  page_fast[i] = 2;   // 1: indexed; otherwise why not (2 DELTA page, 3 NULLs / bit-packed definition levels, 4 runs or window overflow)
+  if (cur.enc == DE_DELTA) return;
+  uint32_t rows_left = pg.num_rows;
+  const uint32_t nslabs = (pg.num_rows + kSlabRows - 1) / kSlabRows;
+  DevSlabRec rec{};
+  // the page's slabs share one entry budget: a slab with many short runs borrows from its neighbours
+  const uint32_t ent_base = pg.slab0 * kFastDirEntries, budget = nslabs * kFastDirEntries;
+  uint32_t used = 0;
   for (uint32_t k = 0; k < nslabs; k++) {
     const uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
     if (cur.has_def) {  // every definition level of the slab must be 1 (RLE runs of 1s)
       const uint64_t base = stream_window_start(cur.def) & ~15ull;
-      const Window w{p.arena + base, base, uint32_t(cur.def.end - base)};
+      const Window w{arena + base, base, uint32_t(cur.def.end - base)};
       uint32_t covered = 0;
       bool ok = true;
       while (covered < R && ok) {
@@ -933,19 +921,23 @@ __global__ void k_slab_dirs(const __grid_constant__ SlabDirArgs p) {
         ok = ok && got != 0;
         covered += got;
       }
-      if (!ok) { p.item_flags[it] = 0; return; }
+      if (!ok) { page_fast[i] = 3; return; }
     }
     rec.win_off = 0;
     rec.nent = 0;
     rec.bw = 0;
     if (PQB_ENC_HAS_STREAM(cur.enc)) {
       const uint64_t base = stream_window_start(cur.val) & ~15ull;
-      const Window w{p.arena + base, base, p.valwin_cap[c]};
-      DirEntry* out = p.slab_dirs + (size_t(item.slab0 + k) * p.ncols + c) * kFastDirEntries;
+      const Window w{arena + base, base, cap};
+      if (used + 3 > budget) { page_fast[i] = 4; return; }
+      DirEntry* out = slab_dirs + ent_base + used;
+      const uint32_t room = budget - used - 2;
       uint32_t n = 0;
-      const uint32_t got = walk_stream(cur.val, w, R, out, n, kFastDirEntries - 2);
-      if (got < R || n == 0) { p.item_flags[it] = 0; return; }
+      const uint32_t got = walk_stream(cur.val, w, R, out, n, room < uint32_t(kMaxDirEntries - 2) ? room : uint32_t(kMaxDirEntries - 2));
+      if (got < R || n == 0) { page_fast[i] = 4; return; }
       dir_sentinels(out, n);
+      rec.ent0 = ent_base + used;
+      used += n + 2;
       rec.win_off = base;
       rec.nent = uint16_t(n);
       rec.bw = cur.val.bw;
@@ -953,10 +945,11 @@ __global__ void k_slab_dirs(const __grid_constant__ SlabDirArgs p) {
     rec.val_base = cur.val_base;
     rec.vals_done = cur.vals_done;
     rec.enc = uint8_t(cur.enc);
-    p.slab_recs[size_t(item.slab0 + k) * p.ncols + c] = rec;
+    slab_recs[pg.slab0 + k] = rec;
     cur.vals_done += R;
     rows_left -= R;
   }
+  page_fast[i] = 1;
 }
 
 // ---- the row phase of one slab: DELTA decode, then the row pass the slab qualifies for; adds the
@@ -1180,8 +1173,8 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     if (item_id >= plan.n_items) break;
     const DevItem& item = a.items[item_id];
 
-    if (a.item_flags && a.item_flags[item_id]) {
-      // ---------------- fast item: k_slab_dirs prebuilt every slab's run directory ----------------
+    if (item.fast) {
+      // ---------------- fast item: the table's slab index holds every slab's run directory ----------------
       // no header walk, no cursor: per slab one wait for the staged bytes, the row phase, and the
       // bulk copies of the slab after next
       if (tid < ncols) {
@@ -1200,15 +1193,19 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       uint32_t r_item = 0;
       for (uint32_t k0 = 0; k0 < nslabs; k0 += kRecBatch) {
         const uint32_t nb = nslabs - k0 < (uint32_t)kRecBatch ? nslabs - k0 : (uint32_t)kRecBatch;
-        {  // this batch's slab records -> shared memory
-          const uint4* src = reinterpret_cast<const uint4*>(a.slab_recs + size_t(item.slab0 + k0) * ncols);
-          uint4* dst = reinterpret_cast<uint4*>(recs);
-          for (uint32_t i = tid; i < nb * ncols * uint32_t(sizeof(DevSlabRec) / 16); i += kScanThreads) dst[i] = src[i];
+        // this batch's slab records -> shared memory, one thread per (slab, column); the first batch
+        // runs in the same phase as the item setup above, so every thread looks up its page itself
+        for (uint32_t i = tid; i < nb * ncols; i += kScanThreads) {
+          const uint32_t k = i / ncols, c = i % ncols;
+          DevSlabRec rc{};
+          rc.enc = DE_PLAIN;
+          if (a.chunks[item.rg * ncols + c].present) rc = a.slab_recs[a.pages[item.page[c]].slab0 + k0 + k];
+          recs[i] = rc;
         }
         __syncthreads();
         if (tid == 0) {
-          fast_issue(ctl, L, smem, a, recs, item.slab0 + k0, 0, ncols, 0);
-          if (nb > 1) fast_issue(ctl, L, smem, a, recs, item.slab0 + k0, 1, ncols, 1);
+          fast_issue(ctl, L, smem, a, recs, k0, 0, ncols, 0);
+          if (nb > 1) fast_issue(ctl, L, smem, a, recs, k0, 1, ncols, 1);
         }
         for (uint32_t k = 0; k < nb; k++) {
           const uint32_t buf = k & 1u;
@@ -1241,7 +1238,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           row_phase(plan, ctl, L, smem, a, item, ctl.mode, 0, buf, R, r_item, acc, agg_mode);
           r_item += R;
           __syncthreads();
-          if (tid == 0 && k + 2 < nb) fast_issue(ctl, L, smem, a, recs, item.slab0 + k0, k + 2, ncols, buf);
+          if (tid == 0 && k + 2 < nb) fast_issue(ctl, L, smem, a, recs, k0, k + 2, ncols, buf);
         }
       }
       if (tid == 0) {

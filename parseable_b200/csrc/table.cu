@@ -212,6 +212,8 @@ Table::~Table() {
   // stream-ordered frees into the pool: a per-query table costs no device-wide synchronisation
   if (d_arena) cudaFreeAsync(d_arena, cudaStreamPerThread);
   if (d_pages) cudaFreeAsync(d_pages, cudaStreamPerThread);
+  if (d_slab_recs) cudaFreeAsync(d_slab_recs, cudaStreamPerThread);
+  if (d_slab_dirs) cudaFreeAsync(d_slab_dirs, cudaStreamPerThread);
 }
 
 int Table::find_column(const std::string& name) const {
@@ -641,8 +643,15 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       TableChunk& tc = row_groups[jobs[j].rg].chunks[jobs[j].col];
       tc.pages.first_page = uint32_t(pages.size());
       tc.pages.n_pages = uint32_t(out[j].size());
+      for (DevPage& dp : out[j]) {
+        dp.chunk_slot = uint16_t(jobs[j].col);
+        dp.slab0 = uint32_t(total_slabs);
+        dp.flags = 0;
+        total_slabs += (dp.num_rows + kSlabRows - 1) / kSlabRows;
+      }
       pages.insert(pages.end(), out[j].begin(), out[j].end());
     }
+    if (total_slabs > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "too many slabs for one table");
   }
   if (!pages.empty()) {
     PQB_CUDA(cudaMallocAsync((void**)&d_pages, pages.size() * sizeof(DevPage), stream));
@@ -683,6 +692,35 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
           }
         }
       }
+  }
+  // ---- slab index: every page's run headers walked once, all pages at the same time ----
+  col_valwin_cap.assign(columns.size(), 0);
+  for (const TableRowGroup& rg : row_groups)
+    for (size_t c = 0; c < rg.chunks.size(); c++)
+      if (rg.chunks[c].present && rg.chunks[c].has_dict_pages)
+        col_valwin_cap[c] = std::max(col_valwin_cap[c], valwin_cap_for_bw(rg.chunks[c].max_bw));
+  const bool want_index = !(getenv("PQB_SLAB_INDEX") && getenv("PQB_SLAB_INDEX")[0] == '0');   // A/B switch
+  if (want_index && !pages.empty() && !columns.empty()) {
+    uint32_t* d_caps = nullptr;
+    uint8_t* d_fast = nullptr;
+    PQB_CUDA(cudaMallocAsync((void**)&d_caps, col_valwin_cap.size() * 4, stream));
+    PQB_CUDA(cudaMemcpyAsync(d_caps, col_valwin_cap.data(), col_valwin_cap.size() * 4, cudaMemcpyHostToDevice, stream));
+    PQB_CUDA(cudaMallocAsync((void**)&d_fast, pages.size(), stream));
+    PQB_CUDA(cudaMallocAsync((void**)&d_slab_recs, std::max<uint64_t>(total_slabs, 1) * sizeof(DevSlabRec), stream));
+    PQB_CUDA(cudaMallocAsync((void**)&d_slab_dirs, std::max<uint64_t>(total_slabs, 1) * kFastDirEntries * sizeof(DirEntry), stream));
+    launch_slab_index(d_arena, d_pages, uint32_t(pages.size()), d_caps, d_slab_recs, d_slab_dirs, d_fast, stream);
+    std::vector<uint8_t> fast(pages.size());
+    PQB_CUDA(cudaMemcpyAsync(fast.data(), d_fast, fast.size(), cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    PQB_CUDA(cudaFreeAsync(d_caps, stream));
+    PQB_CUDA(cudaFreeAsync(d_fast, stream));
+    for (size_t i = 0; i < pages.size(); i++) pages[i].flags = fast[i] == 1 ? 1u : 0u;
+    if (getenv("PQB_VERBOSE")) {
+      size_t h[5] = {0, 0, 0, 0, 0};
+      for (uint8_t f : fast) h[f < 5 ? f : 0]++;
+      fprintf(stderr, "[pqb] slab index: %zu pages indexed, not indexed: %zu DELTA, %zu NULLs, %zu run/window overflow; %llu slabs\n", h[1], h[2],
+              h[3], h[4], (unsigned long long)total_slabs);
+    }
   }
   PQB_CUDA(cudaStreamSynchronize(stream));
 }
