@@ -518,9 +518,14 @@ void Query::run(const PqQueryDesc& d) {
   uint64_t total_entries = 0;
   uint32_t bitmap_words = 0;
   uint64_t algo_bytes = 0, scanned_bytes = 0;
+  std::vector<std::vector<uint32_t>> bounds;   // reused across row groups
+  std::vector<uint32_t> common;
+  size_t bounds_n = 0;
+  items.reserve(size_t(nrg) * 16);
   for (uint32_t gi = 0; gi < nrg; gi++) {
     const TableRowGroup& rg = table->row_groups[rgs[gi]];
-    std::vector<std::vector<uint32_t>> bounds;
+    bounds_n = 0;
+    int first_present = -1;
     for (uint32_t s = 0; s < ncols; s++) {
       const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
       DevChunk& dc = chunks[size_t(gi) * ncols + s];
@@ -548,16 +553,24 @@ void Query::run(const PqQueryDesc& d) {
       plan.cols[s].has_plain |= tc.has_plain_pages;
       scanned_bytes += tc.bytes;
       algo_bytes += uint64_t(tc.meta->total_uncompressed_size);
-      std::vector<uint32_t> b;
-      for (uint32_t p = 0; p < tc.pages.n_pages; p++) b.push_back(table->pages[tc.pages.first_page + p].first_row);
-      bounds.push_back(std::move(b));
+      if (first_present < 0) first_present = int(s);
+      if (!rg.pages_aligned) {
+        if (bounds.size() <= bounds_n) bounds.emplace_back();
+        std::vector<uint32_t>& b = bounds[bounds_n++];
+        b.clear();
+        for (uint32_t p = 0; p < tc.pages.n_pages; p++) b.push_back(table->pages[tc.pages.first_page + p].first_row);
+      }
     }
     // boundaries common to every present column
-    std::vector<uint32_t> common;
-    if (bounds.empty()) common.push_back(0);
+    common.clear();
+    const bool aligned = rg.pages_aligned && first_present >= 0;
+    if (aligned) {   // the pages ARE the items
+      const TableChunk& tc0 = rg.chunks[tcol[qcol_of_slot[first_present]]];
+      for (uint32_t p = 0; p < tc0.pages.n_pages; p++) common.push_back(table->pages[tc0.pages.first_page + p].first_row);
+    } else if (bounds_n == 0) common.push_back(0);
     else {
       common = bounds[0];
-      for (size_t i = 1; i < bounds.size(); i++) {
+      for (size_t i = 1; i < bounds_n; i++) {
         std::vector<uint32_t> t;
         std::set_intersection(common.begin(), common.end(), bounds[i].begin(), bounds[i].end(), std::back_inserter(t));
         common.swap(t);
@@ -577,7 +590,7 @@ void Query::run(const PqQueryDesc& d) {
         const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
         if (!tc.present) continue;
         // page whose first_row == row0
-        uint32_t lo = 0, hi = tc.pages.n_pages;
+        uint32_t lo = aligned ? uint32_t(i) : 0, hi = aligned ? uint32_t(i) + 1 : tc.pages.n_pages;
         while (hi - lo > 1) {
           uint32_t mid = (lo + hi) / 2;
           if (table->pages[tc.pages.first_page + mid].first_row <= it.row0) lo = mid; else hi = mid;

@@ -92,7 +92,7 @@ struct SlabCol {
   uint32_t ndef, nval;
   uint32_t lut_base;
   uint32_t _pad;
-  int64_t dl_last;          // DELTA pages: value of the last row decoded so far in this page
+  int64_t _pad2;
 };
 
 enum SlabMode : uint32_t { MODE_GENERIC = 0, MODE_FAST_AND = 1, MODE_ROW_MAJOR = 2, MODE_GENERAL_WALK = 3 };
@@ -114,7 +114,9 @@ struct ScanCtl {
   uint32_t stk[kScanWarps][2 * kPredStack]; // fast row pass: per warp Kleene stack (t, n) words
   uint32_t lut_smem[kMaxLeaves];            // fast AND path: leaf LUT of this item's row group is cached in smem
   ColCursor cur[kMaxCols];
-  SlabCol slab[kMaxCols];
+  SlabCol slab[2][kMaxCols];                // per staging buffer: warps of a barrier-free item may be one slab apart
+  uint64_t empty[2];                        // rows -> producer: every warp is done with the buffer
+  int64_t dl_last[kMaxCols];                // DELTA pages: value of the last row decoded so far in the page (carried across slabs)
 };
 
 __device__ __forceinline__ void page_enter(ColCursor& c, const DevPage* pages, uint32_t pg) {
@@ -319,7 +321,7 @@ __device__ __forceinline__ bool walker_of(uint32_t ncols, uint32_t& col) {
 
 // ---- DELTA_BINARY_PACKED: miniblock directory -> deltas -> block-wide inclusive scan -> values ----
 __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf) {
-  SlabCol& s = ctl.slab[c];
+  SlabCol& s = ctl.slab[buf][c];
   const uint32_t nv = s.nv;
   int64_t* vals = smem_at<int64_t>(smem, L.idx[c]);
   const DeltaEntry* dir = smem_at<DeltaEntry>(smem, L.valdir[c][buf]);
@@ -331,7 +333,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout
   }
   __syncthreads();
   // a slab that starts a page begins with the page's first value (absolute): no carry
-  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : s.dl_last;
+  const int64_t carry = (s.nval && dir[0].kind == 1) ? 0 : ctl.dl_last[c];
   constexpr uint32_t kPer = kSlabRows / kScanThreads;
   const uint32_t b = threadIdx.x * kPer;
   int64_t loc[kPer];
@@ -356,7 +358,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout
   for (uint32_t i = 0; i < kPer; i++)
     if (b + i < nv) vals[b + i] = int64_t(uint64_t(base) + uint64_t(loc[i]));
   __syncthreads();
-  if (threadIdx.x == 0 && nv) s.dl_last = vals[nv - 1];
+  if (threadIdx.x == 0 && nv) ctl.dl_last[c] = vals[nv - 1];
   __syncthreads();
 }
 
@@ -366,7 +368,7 @@ __device__ __forceinline__ void delta_decode_scan(ScanCtl& ctl, const SmemLayout
 // across directory entries inside one 32-row word.
 __device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, uint32_t c, uint32_t buf,
                                              uint32_t base_row, uint32_t r, bool in) {
-  const SlabCol& s = ctl.slab[c];
+  const SlabCol& s = ctl.slab[buf][c];
   const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
   const uint32_t n = s.nval;
   uint32_t e = ctl.wcur[warp_id()][c];
@@ -380,7 +382,7 @@ __device__ __forceinline__ uint32_t fast_idx(ScanCtl& ctl, const SmemLayout& L, 
 
 __device__ __forceinline__ uint64_t fast_value_u64(ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const uint8_t* arena,
                                                    uint32_t c, uint32_t buf, uint32_t base_row, uint32_t r, bool in, bool want) {
-  const SlabCol& s = ctl.slab[c];
+  const SlabCol& s = ctl.slab[buf][c];
   if (PQB_ENC_HAS_STREAM(s.enc)) {
     uint32_t v = fast_idx(ctl, L, smem, c, buf, base_row, r, in);
     if (s.enc == DE_RLE_BOOL) return v & 1;
@@ -396,7 +398,7 @@ __device__ __forceinline__ uint32_t fast_leaf_word(const DevPlan& plan, ScanCtl&
                                                    uint32_t r, bool in, uint32_t* nw) {
   const DevLeaf& lf = plan.leaves[l];
   const uint32_t c = lf.col;
-  const SlabCol& s = ctl.slab[c];
+  const SlabCol& s = ctl.slab[buf][c];
   *nw = 0;
   if (!s.present) {  // column missing from this file: every row NULL
     if (lf.kind == LK_IS_NULL) return 0xffffffffu;
@@ -495,7 +497,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
     uint32_t slot = 0;
     for (uint32_t k = 0; k < plan.nkeys; k++) {
       const DevKey& key = plan.keys[k];
-      const SlabCol& s = ctl.slab[key.col];
+      const SlabCol& s = ctl.slab[buf][key.col];
       uint32_t gid = key.card;  // column missing: NULL group
       if (s.present) {
         if (key.kind == KK_BOOL) {
@@ -515,7 +517,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = ctl.slab[ag.col];
+      const SlabCol& s = ctl.slab[buf][ag.col];
       if (!s.present) continue;  // all NULL: contributes nothing
       uint64_t bits;
       if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
@@ -609,20 +611,31 @@ __device__ __forceinline__ uint32_t octet_leaf(const uint32_t* __restrict__ dirw
     }
     return m;
   }
-  // the octet straddles directory entries (short runs): row by row
-  for (uint32_t k = 0; k < 8; k++) {
-    if (!((need >> k) & 1)) continue;
-    const uint32_t rr = r + k;
-    while (dirw[(e + 1) * kDirWords] <= rr) e++;
+  // the octet straddles directory entries (short runs, e.g. a skewed `level` column): entry by entry,
+  // an RLE run answers all its rows of the octet with one LUT probe
+  uint32_t k = 0;
+  while (k < 8) {
+    while (dirw[(e + 1) * kDirWords] <= r + k) e++;
     const uint32_t* B = dirw + e * kDirWords;
-    uint32_t v = B[2];
-    if (B[1] & 0x10000u) {
-      const uint32_t bit = B[2] + (rr - B[0]) * bw;
-      const uint32_t wi = bit >> 5;
-      v = __funnelshift_r(win[wi], win[wi + 1], bit & 31) & vmask;
+    const uint32_t nx = B[kDirWords];
+    const uint32_t kend = nx - r < 8u ? nx - r : 8u;      // first row of the octet past this entry
+    const uint32_t seg = ((1u << kend) - 1u) & ~((1u << k) - 1u);
+    if (need & seg) {
+      if (!(B[1] & 0x10000u)) {
+        const uint32_t t = smem_lut ? lut_s[B[2] & (kLutCacheBytes - 1)] : lut_g[B[2]];
+        if (t) m |= seg;
+      } else {
+        uint32_t bit = B[2] + (r + k - B[0]) * bw;
+        for (uint32_t j = k; j < kend; j++, bit += bw) {
+          if (!((need >> j) & 1)) continue;
+          const uint32_t wi = bit >> 5;
+          const uint32_t v = __funnelshift_r(win[wi], win[wi + 1], bit & 31) & vmask;
+          const uint32_t t = smem_lut ? lut_s[v & (kLutCacheBytes - 1)] : lut_g[v];
+          m |= (t ? 1u : 0u) << j;
+        }
+      }
     }
-    const uint32_t t = smem_lut ? lut_s[v & (kLutCacheBytes - 1)] : lut_g[v];
-    m |= (t ? 1u : 0u) << k;
+    k = kend;
   }
   return m;
 }
@@ -639,7 +652,7 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
   for (uint32_t l = 0; l < plan.nleaves; l++) {
     if (sel8 == 0) break;  // per thread: nothing left in its octet (most octets once a selective leaf ran)
     const DevLeaf& lf = plan.leaves[l];
-    const SlabCol& s = ctl.slab[lf.col];
+    const SlabCol& s = ctl.slab[buf][lf.col];
     sel8 &= octet_leaf(smem_at<uint32_t>(smem, L.valdir[lf.col][buf]), s.nval, smem_at<uint32_t>(smem, L.valwin[lf.col][buf]), s.bw, r8,
                        sel8, ctl.lut_smem[l] != 0, smem + L.lutc + l * kLutCacheBytes, a.luts + lf.lut_off + s.lut_base);
   }
@@ -691,7 +704,7 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     uint32_t slot = 0;
     for (uint32_t k = 0; k < plan.nkeys; k++) {
       const DevKey& key = plan.keys[k];
-      const SlabCol& s = ctl.slab[key.col];
+      const SlabCol& s = ctl.slab[buf][key.col];
       uint32_t gid = key.card;
       if (s.present) {
         if (key.kind == KK_BOOL) {
@@ -711,7 +724,7 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = ctl.slab[ag.col];
+      const SlabCol& s = ctl.slab[buf][ag.col];
       if (!s.present) continue;
       uint64_t bits;
       if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
@@ -741,7 +754,7 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
   for (int attempt = 0; attempt < 4 && R > 0; attempt++) {
     if (walker) {  // definition levels
       ColCursor& c = ctl.cur[mycol];
-      SlabCol& s = ctl.slab[mycol];
+      SlabCol& s = ctl.slab[buf][mycol];
       uint32_t got = R;
       s.ndef = 0;
       s.all_valid = 1;
@@ -771,14 +784,14 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
       continue;
     }
     for (uint32_t c = 0; c < ncols; c++) {
-      const SlabCol& s = ctl.slab[c];
+      const SlabCol& s = ctl.slab[buf][c];
       if (s.present && !s.all_valid)
         dir_to_bitmap(smem_at<DirEntry>(smem, L.defdir[c]), s.ndef, smem_at<uint32_t>(smem, L.defwin[c][buf]),
                       smem_at<uint32_t>(smem, L.valid[c]));
     }
     __syncthreads();
     for (uint32_t c = warp_id(); c < ncols; c += kScanWarps) {
-      SlabCol& s = ctl.slab[c];
+      SlabCol& s = ctl.slab[buf][c];
       if (!s.present) { if (lane_id() == 0) s.nv = 0; continue; }
       if (s.all_valid) { if (lane_id() == 0) s.nv = R; continue; }
       uint32_t* bm = smem_at<uint32_t>(smem, L.valid[c]);
@@ -801,7 +814,7 @@ __device__ __noinline__ uint32_t general_walk(ScanCtl& ctl, const SmemLayout& L,
     __syncthreads();
     if (walker) {  // dictionary-index streams
       ColCursor& c = ctl.cur[mycol];
-      SlabCol& s = ctl.slab[mycol];
+      SlabCol& s = ctl.slab[buf][mycol];
       uint32_t rc = R;
       s.nval = 0;
       if (c.present && PQB_ENC_HAS_WINDOW(c.enc) && s.nv > 0) {
@@ -857,6 +870,23 @@ __device__ __forceinline__ void fill_lut_cache(const DevPlan& plan, ScanCtl& ctl
       uint8_t* dst = smem + L.lutc + l * kLutCacheBytes;
       for (uint32_t i = threadIdx.x; i < ch.dict_n; i += kScanThreads) dst[i] = src[i];
     }
+  }
+}
+
+// one thread: publish the per-slab view of batch slab k in buffer `buf` (rows_left = rows of the
+// item from this slab on)
+__device__ __forceinline__ void fast_view(ScanCtl& ctl, const DevSlabRec* recs, uint32_t k, uint32_t ncols, uint32_t buf,
+                                          uint32_t rows_left) {
+  const uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
+  for (uint32_t c = 0; c < ncols; c++) {
+    const DevSlabRec& rc = recs[k * ncols + c];
+    SlabCol& s = ctl.slab[buf][c];
+    s.val_base = rc.val_base;
+    s.vals_done = rc.vals_done;
+    s.enc = rc.enc;
+    s.bw = rc.bw;
+    s.nval = rc.nent;
+    s.nv = s.present ? R : 0;
   }
 }
 
@@ -965,7 +995,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
   // ---- 3b. DELTA_BINARY_PACKED columns: deltas + block scan into their staging array ----
   if (has_delta)
     for (uint32_t c = 0; c < ncols; c++)
-      if (ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv) delta_decode_scan(ctl, L, smem, c, buf);
+      if (ctl.slab[buf][c].present && ctl.slab[buf][c].enc == DE_DELTA && ctl.slab[buf][c].nv) delta_decode_scan(ctl, L, smem, c, buf);
   const uint32_t nwords = (R + 31) >> 5;
   uint32_t cnt = 0;
   const bool fast_and = mode == MODE_FAST_AND;
@@ -980,7 +1010,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
   for (uint32_t w = tid; w < plan.nleaves * kLeafWords; w += kScanThreads) leafT[w] = 0;
   __syncthreads();
   for (uint32_t c = 0; c < ncols; c++) {
-    const SlabCol& s = ctl.slab[c];
+    const SlabCol& s = ctl.slab[buf][c];
     if (!s.present || !PQB_ENC_HAS_STREAM(s.enc) || s.nv == 0) continue;
     uint32_t* idx = L.idx[c] ? smem_at<uint32_t>(smem, L.idx[c]) : nullptr;
     const DirEntry* dir = smem_at<DirEntry>(smem, L.valdir[c][buf]);
@@ -1006,7 +1036,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
   for (uint32_t l = 0; l < plan.nleaves; l++) {
     const DevLeaf& lf = plan.leaves[l];
     if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;   // IS [NOT] NULL comes from the validity words
-    const SlabCol& s = ctl.slab[lf.col];
+    const SlabCol& s = ctl.slab[buf][lf.col];
     if (!s.present) continue;                                 // all NULL: T stays 0
     if (s.enc == DE_DICT && s.all_valid && plan.col_nlut[lf.col] <= 2) continue;  // answered by the fused pass
     const uint32_t* vbm = smem_at<uint32_t>(smem, L.valid[lf.col]);
@@ -1046,7 +1076,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
       const DevPredOp op = plan.pred[i];
       if (op.kind == PK_LEAF) {
         const DevLeaf& lf = plan.leaves[op.arg];
-        const SlabCol& s = ctl.slab[lf.col];
+        const SlabCol& s = ctl.slab[buf][lf.col];
         uint32_t V = !s.present ? 0u : (s.all_valid ? 0xffffffffu : smem_at<uint32_t>(smem, L.valid[lf.col])[w]);
         uint32_t t, n;
         if (lf.kind == LK_IS_NULL) { t = ~V; n = 0; }
@@ -1100,7 +1130,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
       uint32_t slot = 0;
       for (uint32_t k = 0; k < plan.nkeys; k++) {
         const DevKey& key = plan.keys[k];
-        const SlabCol& s = ctl.slab[key.col];
+        const SlabCol& s = ctl.slab[buf][key.col];
         RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[key.col]), smem_at<uint32_t>(smem, L.rank[key.col]), r);
         uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
         if (rv.valid) {
@@ -1113,7 +1143,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
       for (uint32_t g = 0; g < plan.naggs; g++) {
         const DevAgg& ag = plan.aggs[g];
         if (ag.fn == AG_COUNT_STAR) continue;
-        const SlabCol& s = ctl.slab[ag.col];
+        const SlabCol& s = ctl.slab[buf][ag.col];
         RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
         if (!rv.valid) continue;
         if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
@@ -1144,6 +1174,8 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
   if (tid == 0) {
     mbar_init(&ctl.mbar[0], 1);
     mbar_init(&ctl.mbar[1], 1);
+    mbar_init(&ctl.empty[0], kScanWarps);
+    mbar_init(&ctl.empty[1], kScanWarps);
     mbar_fence_init();
     ctl.error = 0;
   }
@@ -1163,7 +1195,8 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
   unsigned long long* acc = (agg_mode && plan.smem_acc) ? sacc : a.acc;
   const uint32_t nslots = plan.nslots;
 
-  uint32_t phases = 0;  // bit b: parity to wait for on mbar[b]
+  uint32_t phases = 0;   // bit b: parity to wait for on mbar[b]
+  uint32_t ephases = 0;  // bit b: parity of the next completion of empty[b]
 
   for (;;) {
     __syncthreads();
@@ -1179,12 +1212,14 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
       // bulk copies of the slab after next
       if (tid < ncols) {
         const DevChunk ch = a.chunks[item.rg * ncols + tid];
-        SlabCol& s = ctl.slab[tid];
-        s.lut_base = ch.lut_base;
-        s.dict_off = ch.dict_off;
-        s.present = ch.present;
-        s.ndef = 0;
-        s.all_valid = 1;
+        for (uint32_t b = 0; b < 2; b++) {
+          SlabCol& s = ctl.slab[b][tid];
+          s.lut_base = ch.lut_base;
+          s.dict_off = ch.dict_off;
+          s.present = ch.present;
+          s.ndef = 0;
+          s.all_valid = 1;
+        }
       }
       if (tid == 0) ctl.sel_count = 0;
       fill_lut_cache(plan, ctl, L, smem, a, item.rg);
@@ -1203,6 +1238,49 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           recs[i] = rc;
         }
         __syncthreads();
+        // can every slab of the batch take the conjunction pass?  Then the warps need no block
+        // barrier at all: each waits for the staged bytes itself and hands the buffer back through
+        // an mbarrier, so a slow warp (short runs, many survivors) no longer stalls the other seven
+        bool conj = plan.fast_and != 0;
+        if (conj && tid < nb)
+          for (uint32_t l = 0; conj && l < plan.nleaves; l++) {
+            const uint32_t c = plan.leaves[l].col;
+            const DevSlabRec& rc = recs[tid * ncols + c];
+            conj = ctl.slab[0][c].present && rc.enc == DE_DICT && rc.nent > 0;
+          }
+        if (__syncthreads_and(conj)) {
+          const uint32_t row00 = r_item;
+          if (tid == 0) {
+            for (uint32_t k = 0; k < 2 && k < nb; k++) {
+              fast_view(ctl, recs, k, ncols, k, item.nrows - row00 - k * kSlabRows);
+              fast_issue(ctl, L, smem, a, recs, k0, k, ncols, k);
+            }
+          }
+          for (uint32_t k = 0; k < nb; k++) {
+            const uint32_t buf = k & 1u;
+            const uint32_t R = item.nrows - r_item < (uint32_t)kSlabRows ? item.nrows - r_item : (uint32_t)kSlabRows;
+            if (lane_id() == 0) mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
+            __syncwarp();
+            phases ^= 1u << buf;
+            uint32_t cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+            for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane_id() == 0) {
+              if (cnt) atomicAdd(&ctl.sel_count, cnt);
+              mbar_arrive(&ctl.empty[buf]);   // this warp is done with buffer `buf`
+            }
+            const uint32_t epar = (ephases >> buf) & 1u;
+            ephases ^= 1u << buf;
+            r_item += R;
+            if (tid == 0 && k + 2 < nb) {   // refill the buffer once all eight warps let go of it
+              mbar_wait(&ctl.empty[buf], epar);
+              fast_view(ctl, recs, k + 2, ncols, buf, item.nrows - row00 - (k + 2) * kSlabRows);
+              fast_issue(ctl, L, smem, a, recs, k0, k + 2, ncols, buf);
+            }
+            __syncwarp();
+          }
+          __syncthreads();
+          continue;
+        }
         if (tid == 0) {
           fast_issue(ctl, L, smem, a, recs, k0, 0, ncols, 0);
           if (nb > 1) fast_issue(ctl, L, smem, a, recs, k0, 1, ncols, 1);
@@ -1212,7 +1290,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           const uint32_t R = item.nrows - r_item < (uint32_t)kSlabRows ? item.nrows - r_item : (uint32_t)kSlabRows;
           if (tid < ncols) {
             const DevSlabRec& rc = recs[k * ncols + tid];
-            SlabCol& s = ctl.slab[tid];
+            SlabCol& s = ctl.slab[buf][tid];
             s.val_base = rc.val_base;
             s.vals_done = rc.vals_done;
             s.enc = rc.enc;
@@ -1226,7 +1304,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
               const uint32_t c = plan.leaves[l].col;
               const DevSlabRec& rc = recs[k * ncols + c];
-              fa = ctl.slab[c].present && rc.enc == DE_DICT && rc.nent > 0;
+              fa = ctl.slab[buf][c].present && rc.enc == DE_DICT && rc.nent > 0;
             }
             if (fa) mode = MODE_FAST_AND;
             else if (plan.row_major) mode = MODE_ROW_MAJOR;
@@ -1251,10 +1329,12 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     if (tid < ncols) {
       ColCursor& c = ctl.cur[tid];
       const DevChunk ch = a.chunks[item.rg * ncols + tid];
-      SlabCol& s = ctl.slab[tid];
-      s.lut_base = ch.lut_base;
-      s.dict_off = ch.dict_off;
-      s.present = ch.present;
+      for (uint32_t b = 0; b < 2; b++) {
+        SlabCol& s = ctl.slab[b][tid];
+        s.lut_base = ch.lut_base;
+        s.dict_off = ch.dict_off;
+        s.present = ch.present;
+      }
       c.present = ch.present;
       c.page_end = ch.first_page + ch.n_pages;
       if (ch.present) page_enter(c, a.pages, item.page[tid]);
@@ -1282,7 +1362,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         const uint32_t R0w = ctl.target;
         if (walker) {
           ColCursor& c = ctl.cur[mycol];
-          SlabCol& s = ctl.slab[mycol];
+          SlabCol& s = ctl.slab[buf][mycol];
           snap_def = c.def;
           snap_val = c.val;
           snap_dl = c.dl;
@@ -1321,7 +1401,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         if (!general) {
           if (walker) {  // freeze this slab's view, advance the cursor
             ColCursor& c = ctl.cur[mycol];
-            SlabCol& s = ctl.slab[mycol];
+            SlabCol& s = ctl.slab[buf][mycol];
             s.val_base = c.val_base;
             s.vals_done = c.vals_done;
             s.enc = c.enc;
@@ -1339,9 +1419,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           if (lane_id() == 0) {
             uint32_t mode = MODE_GENERIC, has_delta = 0;
             bool fa = plan.fast_and != 0;
-            for (uint32_t c = 0; c < ncols; c++) has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
+            for (uint32_t c = 0; c < ncols; c++) has_delta |= ctl.slab[buf][c].present && ctl.slab[buf][c].enc == DE_DELTA && ctl.slab[buf][c].nv;
             for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
-              const SlabCol& s = ctl.slab[plan.leaves[l].col];
+              const SlabCol& s = ctl.slab[buf][plan.leaves[l].col];
               fa = s.present && s.enc == DE_DICT && s.nval > 0;
             }
             if (fa) mode = MODE_FAST_AND;
@@ -1372,7 +1452,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         }
         if (walker) {
           ColCursor& c = ctl.cur[mycol];
-          SlabCol& s = ctl.slab[mycol];
+          SlabCol& s = ctl.slab[buf][mycol];
           s.val_base = c.val_base;
           s.vals_done = c.vals_done;
           s.enc = c.enc;
@@ -1390,14 +1470,14 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
         if (!ctl.error && tid == 0 && rows_left > R) issue_windows(ctl, L, smem, a.arena, ncols, buf ^ 1, rows_left - R);
         has_delta = 0;
         for (uint32_t c = 0; c < ncols; c++) {
-          has_nulls |= ctl.slab[c].present && !ctl.slab[c].all_valid;
-          has_delta |= ctl.slab[c].present && ctl.slab[c].enc == DE_DELTA && ctl.slab[c].nv;
+          has_nulls |= ctl.slab[buf][c].present && !ctl.slab[buf][c].all_valid;
+          has_delta |= ctl.slab[buf][c].present && ctl.slab[buf][c].enc == DE_DELTA && ctl.slab[buf][c].nv;
         }
         mode = MODE_GENERIC;
         if (!has_nulls) {
           bool fa = plan.fast_and != 0;
           for (uint32_t l = 0; fa && l < plan.nleaves; l++) {
-            const SlabCol& s = ctl.slab[plan.leaves[l].col];
+            const SlabCol& s = ctl.slab[buf][plan.leaves[l].col];
             fa = s.present && s.enc == DE_DICT && s.nval > 0;
           }
           if (fa) mode = MODE_FAST_AND;

@@ -693,6 +693,20 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         }
       }
   }
+  // row groups whose columns all share their page boundaries: work items are simply the pages
+  for (TableRowGroup& rg : row_groups) {
+    const TableChunk* first = nullptr;
+    bool same = true;
+    for (const TableChunk& tc : rg.chunks) {
+      if (!tc.present) continue;
+      if (!first) { first = &tc; continue; }
+      if (tc.pages.n_pages != first->pages.n_pages) { same = false; break; }
+      for (uint32_t k = 0; k < tc.pages.n_pages && same; k++)
+        same = pages[tc.pages.first_page + k].first_row == pages[first->pages.first_page + k].first_row;
+      if (!same) break;
+    }
+    rg.pages_aligned = same && first != nullptr;
+  }
   // ---- slab index: every page's run headers walked once, all pages at the same time ----
   col_valwin_cap.assign(columns.size(), 0);
   for (const TableRowGroup& rg : row_groups)
