@@ -36,7 +36,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // back off between polls: a spinning warp competes for issue slots with the warps it waits for
+  // (profiles/k_scan_r1g: a third of all executed instructions were this loop)
+  uint32_t ns = 32;
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;
   }
 }
 // global -> shared bulk copy; src, dst and bytes are multiples of 16

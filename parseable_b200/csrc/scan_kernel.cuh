@@ -1250,6 +1250,7 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
           }
         if (__syncthreads_and(conj)) {
           const uint32_t row00 = r_item;
+          uint32_t cnt_batch = 0;   // selected rows of this thread's octets over the whole batch
           if (tid == 0) {
             for (uint32_t k = 0; k < 2 && k < nb; k++) {
               fast_view(ctl, recs, k, ncols, k, item.nrows - row00 - k * kSlabRows);
@@ -1262,12 +1263,9 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             if (lane_id() == 0) mbar_wait(&ctl.mbar[buf], (phases >> buf) & 1u);
             __syncwarp();
             phases ^= 1u << buf;
-            uint32_t cnt = fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
-            for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            if (lane_id() == 0) {
-              if (cnt) atomicAdd(&ctl.sel_count, cnt);
-              mbar_arrive(&ctl.empty[buf]);   // this warp is done with buffer `buf`
-            }
+            cnt_batch += fast_and_rows(plan, ctl, L, smem, a, item, buf, R, r_item, acc, agg_mode);
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&ctl.empty[buf]);   // this warp is done with buffer `buf`
             const uint32_t epar = (ephases >> buf) & 1u;
             ephases ^= 1u << buf;
             r_item += R;
@@ -1278,6 +1276,8 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
             }
             __syncwarp();
           }
+          for (int o = 16; o; o >>= 1) cnt_batch += __shfl_xor_sync(0xffffffffu, cnt_batch, o);
+          if (lane_id() == 0 && cnt_batch) atomicAdd(&ctl.sel_count, cnt_batch);
           __syncthreads();
           continue;
         }
