@@ -121,6 +121,8 @@ class Table {
   // scan kernel would otherwise derive by walking the run headers; see DESIGN.md
   DevSlabRec* d_slab_recs = nullptr;
   DirEntry* d_slab_dirs = nullptr;
+  uint8_t* d_slab_flat = nullptr;         // flat bit-packed copies of run-heavy pages (k_flatten_pages)
+  uint64_t slab_flat_bytes = 0;
   uint64_t total_slabs = 0;
   std::vector<uint32_t> col_valwin_cap;   // per table column: staged window bytes the index was built for
   uint64_t total_rows = 0;
@@ -134,6 +136,8 @@ inline uint32_t valwin_cap_for_bw(uint32_t max_bw) { return ((kSlabRows * max_bw
 // launches k_slab_index (defined next to k_scan, query.cu)
 void launch_slab_index(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, const uint32_t* col_caps, DevSlabRec* recs,
                        DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream);
+void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* side,
+                          DevSlabRec* recs, DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream);
 
 // page-locked host block that result batches can alias (zero copy); returns to the pool when
 // the last batch that references it is released by the consumer

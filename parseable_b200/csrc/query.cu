@@ -196,6 +196,13 @@ void launch_slab_index(const uint8_t* arena, const DevPage* pages, uint32_t n_pa
   PQB_CUDA(cudaGetLastError());
 }
 
+void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* side,
+                          DevSlabRec* recs, DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream) {
+  if (!n_jobs) return;
+  k_flatten_pages<<<(n_jobs + 31) / 32, 32, 0, stream>>>(arena, pages, static_cast<const FlatJob*>(jobs), n_jobs, side, recs, dirs, page_fast);
+  PQB_CUDA(cudaGetLastError());
+}
+
 void Query::run(const PqQueryDesc& d) {
   const auto t_begin = std::chrono::steady_clock::now();
   const bool verbose = getenv("PQB_VERBOSE") != nullptr;

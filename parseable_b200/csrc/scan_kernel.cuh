@@ -281,15 +281,43 @@ __device__ __forceinline__ T* smem_at(uint8_t* base, uint32_t off) {
   return reinterpret_cast<T*>(base + off);
 }
 
+// 64-bit integer add into an accumulator cell.  Global memory has a native 64-bit reduction; shared
+// memory does not (the compiler emits a compare-and-swap spin loop, ATOMS.CAST.SPIN.64, which
+// collapses under the contention of a 25-group table), so there the add is two native 32-bit
+// atomics: the low word, and the high word plus the carry this very add produced.  Addition
+// commutes per word and every wrap of the low word is seen by exactly one thread, so the cell is
+// exact once the CTA has synchronised (it is only read at the flush).
+__device__ __forceinline__ void acc_add(unsigned long long* cell, unsigned long long v) {
+  if (__isShared(cell)) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(cell);
+    const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+    uint32_t carry = 0;
+    if (lo) {
+      const uint32_t old = atomicAdd(&w[0], lo);
+      carry = uint32_t(old + lo) < lo ? 1u : 0u;
+    }
+    if (hi + carry) atomicAdd(&w[1], hi + carry);
+  } else {
+    atomicAdd(cell, v);
+  }
+}
+
 __device__ __forceinline__ void acc_apply(unsigned long long* cell, uint32_t fn, uint32_t kind, uint64_t bits) {
   if (fn == AG_SUM) {
     if (kind == DK_F64) atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double((long long)bits));
-    else atomicAdd(cell, (unsigned long long)bits);  // wrapping, like DataFusion's SUM(Int64)
+    else acc_add(cell, (unsigned long long)bits);  // wrapping, like DataFusion's SUM(Int64)
   } else if (fn == AG_AVG) {
     double v = kind == DK_F64 ? __longlong_as_double((long long)bits) : double((long long)bits);
     atomicAdd(reinterpret_cast<double*>(cell), v);
   } else {
     long long k = kind == DK_F64 ? (long long)f64_order_key(bits) : (long long)bits;
+    // shared memory: 64-bit min / max are compare-and-swap loops; the cell only ever moves one way,
+    // so a row that cannot improve the value it reads (one aligned 8-byte load) skips the atomic —
+    // after the first few rows of a group that is nearly every row
+    if (__isShared(cell)) {
+      const long long cur = *reinterpret_cast<volatile long long*>(cell);
+      if (fn == AG_MIN ? k >= cur : k <= cur) return;
+    }
     if (fn == AG_MIN) atomicMin(reinterpret_cast<long long*>(cell), k);
     else atomicMax(reinterpret_cast<long long*>(cell), k);
   }
@@ -513,7 +541,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
       }
       slot += gid * key.stride;
     }
-    if (mine) atomicAdd(&acc[slot], 1ull);
+    if (mine) acc_add(&acc[slot], 1ull);
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
@@ -527,7 +555,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
         bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
       }
       if (!mine) continue;
-      if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+      if (ag.update_nn) acc_add(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
       if (ag.fn == AG_COUNT) continue;
       acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
     }
@@ -720,7 +748,7 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
       }
       slot += gid * key.stride;
     }
-    if (mine) atomicAdd(&acc[slot], 1ull);
+    if (mine) acc_add(&acc[slot], 1ull);
     for (uint32_t g = 0; g < plan.naggs; g++) {
       const DevAgg& ag = plan.aggs[g];
       if (ag.fn == AG_COUNT_STAR) continue;
@@ -734,7 +762,7 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
         bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
       }
       if (!mine) continue;
-      if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+      if (ag.update_nn) acc_add(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
       if (ag.fn == AG_COUNT) continue;
       acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
     }
@@ -936,6 +964,7 @@ __global__ void k_slab_index(const uint8_t* __restrict__ arena, const DevPage* _
   // the page's slabs share one entry budget: a slab with many short runs borrows from its neighbours
   const uint32_t ent_base = pg.slab0 * kFastDirEntries, budget = nslabs * kFastDirEntries;
   uint32_t used = 0;
+  bool flat = false;
   for (uint32_t k = 0; k < nslabs; k++) {
     const uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
     if (cur.has_def) {  // every definition level of the slab must be 1 (RLE runs of 1s)
@@ -956,21 +985,27 @@ __global__ void k_slab_index(const uint8_t* __restrict__ arena, const DevPage* _
     rec.win_off = 0;
     rec.nent = 0;
     rec.bw = 0;
-    if (PQB_ENC_HAS_STREAM(cur.enc)) {
+    if (PQB_ENC_HAS_STREAM(cur.enc) && !flat) {
       const uint64_t base = stream_window_start(cur.val) & ~15ull;
       const Window w{arena + base, base, cap};
-      if (used + 3 > budget) { page_fast[i] = 4; return; }
-      DirEntry* out = slab_dirs + ent_base + used;
-      const uint32_t room = budget - used - 2;
-      uint32_t n = 0;
-      const uint32_t got = walk_stream(cur.val, w, R, out, n, room < uint32_t(kMaxDirEntries - 2) ? room : uint32_t(kMaxDirEntries - 2));
-      if (got < R || n == 0) { page_fast[i] = 4; return; }
-      dir_sentinels(out, n);
-      rec.ent0 = ent_base + used;
-      used += n + 2;
-      rec.win_off = base;
-      rec.nent = uint16_t(n);
-      rec.bw = cur.val.bw;
+      uint32_t n = 0, got = 0;
+      if (used + 3 <= budget) {
+        DirEntry* out = slab_dirs + ent_base + used;
+        const uint32_t room = budget - used - 2;
+        got = walk_stream(cur.val, w, R, out, n, room < uint32_t(kMaxDirEntries - 2) ? room : uint32_t(kMaxDirEntries - 2));
+        if (got == R && n) dir_sentinels(out, n);
+      }
+      if (got < R || n == 0) {
+        // too many runs for the page's entry budget (or for one staged window): the page gets a
+        // flat bit-packed copy instead (k_flatten_pages); keep checking the definition levels only
+        flat = true;
+      } else {
+        rec.ent0 = ent_base + used;
+        used += n + 2;
+        rec.win_off = base;
+        rec.nent = uint16_t(n);
+        rec.bw = cur.val.bw;
+      }
     }
     rec.val_base = cur.val_base;
     rec.vals_done = cur.vals_done;
@@ -979,7 +1014,51 @@ __global__ void k_slab_index(const uint8_t* __restrict__ arena, const DevPage* _
     cur.vals_done += R;
     rows_left -= R;
   }
-  page_fast[i] = 1;
+  page_fast[i] = flat ? 5 : 1;
+}
+
+// Second pass of the slab index: pages whose run structure does not fit a directory get a flat
+// bit-packed copy of their index stream (decode_core.cuh transcode_values) in a side buffer; every
+// slab of such a page is then a single bit-packed directory entry at a 256 * bw byte stride.
+struct FlatJob { uint32_t page; uint32_t _pad; uint64_t side_off; };
+__global__ void k_flatten_pages(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages, const FlatJob* __restrict__ jobs,
+                                uint32_t n_jobs, uint8_t* __restrict__ side, DevSlabRec* __restrict__ slab_recs,
+                                DirEntry* __restrict__ slab_dirs, uint8_t* __restrict__ page_fast) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_jobs) return;
+  const uint32_t pi = jobs[i].page;
+  ColCursor cur;
+  page_enter(cur, pages, pi);
+  const DevPage& pg = pages[pi];
+  const uint32_t bw = cur.val.bw;
+  uint8_t* dst = side + jobs[i].side_off;
+  BitWriter b{reinterpret_cast<uint32_t*>(dst), 0, 0};
+  uint32_t rows_left = pg.num_rows;
+  const uint32_t nslabs = (pg.num_rows + kSlabRows - 1) / kSlabRows;
+  DevSlabRec rec{};
+  for (uint32_t k = 0; k < nslabs; k++) {
+    const uint32_t R = rows_left < (uint32_t)kSlabRows ? rows_left : (uint32_t)kSlabRows;
+    if (transcode_values(cur.val, arena, R, b) < R) { page_fast[pi] = 4; return; }
+    DirEntry* out = slab_dirs + size_t(pg.slab0) * kFastDirEntries + 3 * k;
+    out[0].start = 0;
+    out[0].count = uint16_t(R);
+    out[0].kind = bw ? 1 : 0;   // a one-entry dictionary has no bits at all: one RLE run of index 0
+    out[0].chunk0 = 0;
+    out[0].payload = 0;
+    out[0]._pad = 0;
+    dir_sentinels(out, 1);
+    rec.win_off = uint64_t(dst + size_t(k) * (kSlabRows / 8) * bw) - uint64_t(arena);   // relative to the arena, may wrap
+    rec.val_base = cur.val_base;
+    rec.vals_done = k * kSlabRows;
+    rec.nent = 1;
+    rec.enc = uint8_t(cur.enc);
+    rec.bw = uint8_t(bw);
+    rec.ent0 = pg.slab0 * kFastDirEntries + 3 * k;
+    slab_recs[pg.slab0 + k] = rec;
+    rows_left -= R;
+  }
+  bitwriter_flush(b);
+  page_fast[pi] = 1;
 }
 
 // ---- the row phase of one slab: DELTA decode, then the row pass the slab qualifies for; adds the
@@ -1139,14 +1218,14 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
         }
         slot += gid * key.stride;
       }
-      atomicAdd(&acc[slot], 1ull);
+      acc_add(&acc[slot], 1ull);
       for (uint32_t g = 0; g < plan.naggs; g++) {
         const DevAgg& ag = plan.aggs[g];
         if (ag.fn == AG_COUNT_STAR) continue;
         const SlabCol& s = ctl.slab[buf][ag.col];
         RowVal rv = row_rank(s, smem_at<uint32_t>(smem, L.valid[ag.col]), smem_at<uint32_t>(smem, L.rank[ag.col]), r);
         if (!rv.valid) continue;
-        if (ag.update_nn) atomicAdd(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+        if (ag.update_nn) acc_add(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
         if (ag.fn == AG_COUNT) continue;
         uint64_t bits = ag.kind == DK_BOOL ? value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j)
                                            : value_u64(s, a.arena, smem_at<uint32_t>(smem, L.idx[ag.col]), rv.j);

@@ -214,6 +214,7 @@ Table::~Table() {
   if (d_pages) cudaFreeAsync(d_pages, cudaStreamPerThread);
   if (d_slab_recs) cudaFreeAsync(d_slab_recs, cudaStreamPerThread);
   if (d_slab_dirs) cudaFreeAsync(d_slab_dirs, cudaStreamPerThread);
+  if (d_slab_flat) cudaFreeAsync(d_slab_flat, cudaStreamPerThread);
 }
 
 int Table::find_column(const std::string& name) const {
@@ -726,14 +727,37 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     std::vector<uint8_t> fast(pages.size());
     PQB_CUDA(cudaMemcpyAsync(fast.data(), d_fast, fast.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
+    // run-heavy pages (skewed low-cardinality columns): a flat bit-packed copy replaces the directory
+    struct FlatJobH { uint32_t page; uint32_t pad; uint64_t side_off; };
+    std::vector<FlatJobH> fjobs;
+    uint64_t side = 0;
+    for (size_t i = 0; i < pages.size(); i++)
+      if (fast[i] == 5) {
+        fjobs.push_back({uint32_t(i), 0, side});
+        side += ((uint64_t(pages[i].num_rows) * pages[i].bit_width + 31) / 32 * 4 + 255 + 256) & ~255ull;
+      }
+    if (!fjobs.empty()) {
+      uint32_t max_cap = 0;
+      for (uint32_t c : col_valwin_cap) max_cap = std::max(max_cap, c);
+      slab_flat_bytes = side + max_cap + 256;   // staged windows over-read past the last slab
+      void* d_jobs = nullptr;
+      PQB_CUDA(cudaMallocAsync((void**)&d_slab_flat, slab_flat_bytes, stream));
+      PQB_CUDA(cudaMemsetAsync(d_slab_flat + side, 0, slab_flat_bytes - side, stream));
+      PQB_CUDA(cudaMallocAsync(&d_jobs, fjobs.size() * sizeof(FlatJobH), stream));
+      PQB_CUDA(cudaMemcpyAsync(d_jobs, fjobs.data(), fjobs.size() * sizeof(FlatJobH), cudaMemcpyHostToDevice, stream));
+      launch_flatten_pages(d_arena, d_pages, d_jobs, uint32_t(fjobs.size()), d_slab_flat, d_slab_recs, d_slab_dirs, d_fast, stream);
+      PQB_CUDA(cudaMemcpyAsync(fast.data(), d_fast, fast.size(), cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      PQB_CUDA(cudaFreeAsync(d_jobs, stream));
+    }
     PQB_CUDA(cudaFreeAsync(d_caps, stream));
     PQB_CUDA(cudaFreeAsync(d_fast, stream));
     for (size_t i = 0; i < pages.size(); i++) pages[i].flags = fast[i] == 1 ? 1u : 0u;
     if (getenv("PQB_VERBOSE")) {
       size_t h[5] = {0, 0, 0, 0, 0};
       for (uint8_t f : fast) h[f < 5 ? f : 0]++;
-      fprintf(stderr, "[pqb] slab index: %zu pages indexed, not indexed: %zu DELTA, %zu NULLs, %zu run/window overflow; %llu slabs\n", h[1], h[2],
-              h[3], h[4], (unsigned long long)total_slabs);
+      fprintf(stderr, "[pqb] slab index: %zu pages indexed (%zu of them as flat bit-packed copies, %llu bytes), not indexed: %zu DELTA, %zu NULLs, %zu corrupt; %llu slabs\n",
+              h[1], fjobs.size(), (unsigned long long)slab_flat_bytes, h[2], h[3], h[4], (unsigned long long)total_slabs);
     }
   }
   PQB_CUDA(cudaStreamSynchronize(stream));

@@ -104,6 +104,25 @@ def test_hybrid_tiny_windows_force_slab_shrink(dc, bw, cap, max_ent):
     assert np.array_equal(out.astype(np.uint64), vals)
 
 
+@pytest.mark.parametrize("bw", [0, 1, 3, 5, 8, 13, 17, 32])
+def test_transcode_to_flat_bitpacked(dc, bw):
+    """Run-heavy pages are kept in the slab index as a flat bit-packed copy (transcode_values)."""
+    rng = np.random.default_rng(1234 + bw)
+    n = 20000
+    hi = (1 << bw) if bw else 1
+    vals = np.repeat(rng.integers(0, hi, n, dtype=np.uint64), rng.integers(1, 25, n))[:n].astype(np.uint64)
+    enc = encode_hybrid(vals, bw, rng, rle_bias=0.6)
+    words = np.zeros(n * max(bw, 1) // 32 + 8, np.uint32)
+    dc.dc_transcode.restype = C.c_int64
+    got = dc.dc_transcode(enc, C.c_uint64(len(enc)), bw, n, 2048, words.ctypes.data_as(C.c_void_p))
+    assert got == n
+    if bw == 0:
+        return
+    bits = np.unpackbits(words.view(np.uint8), bitorder="little")[: n * bw].reshape(n, bw).astype(np.uint64)
+    back = (bits << np.arange(bw, dtype=np.uint64)).sum(axis=1)
+    assert np.array_equal(back, vals)
+
+
 def test_f64_order_key_is_total_order(dc):
     vals = [float("-inf"), -1e300, -1.5, -0.0, 0.0, 5e-324, 1.5, 1e300, float("inf")]
     nan_pos = struct.unpack("<d", struct.pack("<Q", 0x7FF8000000000001))[0]

@@ -40,6 +40,23 @@ int64_t dc_decode_hybrid(const uint8_t* stream, uint64_t len, uint32_t bw, uint3
   }
   return done;
 }
+// hybrid stream -> flat bit-packed words (the slab index's copy of run-heavy pages), `slab` values per call
+int64_t dc_transcode(const uint8_t* stream, uint64_t len, uint32_t bw, uint32_t n, uint32_t slab, uint32_t* out_words) {
+  std::vector<uint8_t> padded(len + 64 + 16, 0);
+  std::memcpy(padded.data() + 16, stream, len);
+  StreamState st;
+  stream_init(st, 16, 16 + len, bw);
+  BitWriter b{out_words, 0, 0};
+  uint32_t done = 0;
+  while (done < n) {
+    uint32_t need = n - done < slab ? n - done : slab;
+    uint32_t got = transcode_values(st, padded.data(), need, b);
+    done += got;
+    if (got < need) return -int64_t(done) - 1;
+  }
+  bitwriter_flush(b);
+  return done;
+}
 // DELTA_BINARY_PACKED page payload -> int64 values, through the kernel's window / directory geometry
 int64_t dc_decode_delta(const uint8_t* stream, uint64_t len, uint32_t n, uint32_t slab, uint32_t win_cap,
                         uint32_t max_ent, int64_t* out) {
