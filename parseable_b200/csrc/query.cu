@@ -525,6 +525,7 @@ void Query::run(const PqQueryDesc& d) {
   uint64_t total_entries = 0;
   uint32_t bitmap_words = 0;
   uint64_t algo_bytes = 0, scanned_bytes = 0;
+  std::vector<uint8_t> col_has_nulls(std::max<uint32_t>(ncols, 1), 0);   // statistics cannot rule NULLs out
   std::vector<std::vector<uint32_t>> bounds;   // reused across row groups
   std::vector<uint32_t> common;
   size_t bounds_n = 0;
@@ -537,6 +538,7 @@ void Query::run(const PqQueryDesc& d) {
       const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
       DevChunk& dc = chunks[size_t(gi) * ncols + s];
       dc.present = tc.present ? 1 : 0;
+      if (!tc.present || tc.meta->stats.null_count != 0) col_has_nulls[s] = 1;   // absent column: every row NULL
       if (!tc.present) continue;
       const uint8_t kind = plan.cols[s].kind;
       dc.dict_off = tc.dict_off;
@@ -613,6 +615,15 @@ void Query::run(const PqQueryDesc& d) {
   }
   plan.n_items = uint32_t(items.size());
   metrics.bytes_scanned = scanned_bytes;
+  // an aggregated column whose footers promise null_count == 0 in every row group read: its
+  // non-null counter equals the group's row count, so the scan skips that atomic
+  std::vector<uint8_t> nn_is_rows(kMaxAggs, 0);
+  for (uint32_t a = 0; a < d.n_aggs; a++) {
+    DevAgg& ag = plan.aggs[a];
+    if (ag.fn == AG_COUNT_STAR || col_has_nulls[ag.col]) continue;
+    ag.update_nn = 0;
+    nn_is_rows[a] = 1;
+  }
 
   // columns whose dictionary indices the row phase needs (GROUP BY keys, aggregate inputs)
   for (uint32_t k = 0; k < d.n_group_by; k++) plan.cols[slot_of[d.group_by[k]]].need_idx = 1;
@@ -1028,7 +1039,7 @@ void Query::run(const PqQueryDesc& d) {
           if (!synth_empty) {
             uint32_t o = order[r0 + i];
             rows = out_cells[o];
-            if (ag.fn != AG_COUNT_STAR) nn = out_cells[size_t(1 + plan.n_acc + ag.nn_slot) * n_out + o];
+            if (ag.fn != AG_COUNT_STAR) nn = nn_is_rows[a] ? rows : out_cells[size_t(1 + plan.n_acc + ag.nn_slot) * n_out + o];
             if (ag.fn >= AG_SUM) cell = out_cells[size_t(1 + ag.acc_slot) * n_out + o];
           }
           bool valid = true;

@@ -569,6 +569,56 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
 // run-directory entry, unpacks its 8 indices from the staged window into registers, probes the
 // leaf's LUT and ANDs the byte.  No leaf bitmaps, no atomics, no block barrier inside the slab.
 // The aggregate consume pass still walks 32-row words (a warp owns kWordsPerWarp consecutive ones).
+// Aggregate consume of one 32-row selection word (conjunction pass): group slot from the key
+// columns, then every aggregate.  Deliberately NOT inlined: the caller's loop over the warp's eight
+// words is unrolled, and eight inlined copies of this body made the kernel miss the instruction
+// cache (ncu: no_instruction was the top stall of a filtered group-by, issue slots 15 % busy).
+__device__ __noinline__ void consume_word_agg(const DevPlan& plan, ScanCtl& ctl, const SmemLayout& L, uint8_t* smem, const DevScanArgs& a,
+                                              uint32_t buf, uint32_t base_row, uint32_t sel, uint32_t R, unsigned long long* acc) {
+  const uint32_t lane = lane_id();
+  const uint32_t nslots = plan.nslots;
+  const uint32_t r = base_row + lane;
+  const bool in = r < R;
+  const bool mine = (sel >> lane) & 1;
+  uint32_t slot = 0;
+  for (uint32_t k = 0; k < plan.nkeys; k++) {
+    const DevKey& key = plan.keys[k];
+    const SlabCol& s = ctl.slab[buf][key.col];
+    uint32_t gid = key.card;
+    if (s.present) {
+      if (key.kind == KK_BOOL) {
+        gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
+        if (!PQB_ENC_HAS_STREAM(s.enc)) {
+          uint32_t kk = s.vals_done + r;
+          gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
+        }
+      } else {
+        uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
+        gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
+      }
+    }
+    slot += gid * key.stride;
+  }
+  if (mine) acc_add(&acc[slot], 1ull);
+  for (uint32_t g = 0; g < plan.naggs; g++) {
+    const DevAgg& ag = plan.aggs[g];
+    if (ag.fn == AG_COUNT_STAR) continue;
+    const SlabCol& s = ctl.slab[buf][ag.col];
+    if (!s.present) continue;
+    uint64_t bits;
+    if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
+      uint32_t kk = s.vals_done + r;
+      bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
+    } else {
+      bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
+    }
+    if (!mine) continue;
+    if (ag.update_nn) acc_add(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
+    if (ag.fn == AG_COUNT) continue;
+    acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
+  }
+}
+
 constexpr int kWordsPerWarp = kSlabWords / kScanWarps;
 constexpr int kRowsPerThread = kSlabRows / kScanThreads;
 static_assert(kRowsPerThread == 8, "the octet pass gives every thread 8 consecutive rows (one selection byte)");
@@ -727,45 +777,8 @@ __device__ __forceinline__ uint32_t fast_and_rows(const DevPlan& plan, ScanCtl& 
       }
       continue;
     }
-    const bool mine = (sel >> lane) & 1;
     if (lane == 0) cnt += __popc(sel);
-    uint32_t slot = 0;
-    for (uint32_t k = 0; k < plan.nkeys; k++) {
-      const DevKey& key = plan.keys[k];
-      const SlabCol& s = ctl.slab[buf][key.col];
-      uint32_t gid = key.card;
-      if (s.present) {
-        if (key.kind == KK_BOOL) {
-          gid = (uint32_t)fast_value_u64(ctl, L, smem, a.arena, key.col, buf, base_row, r, in, false);
-          if (!PQB_ENC_HAS_STREAM(s.enc)) {
-            uint32_t kk = s.vals_done + r;
-            gid = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
-          }
-        } else {
-          uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
-          gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
-        }
-      }
-      slot += gid * key.stride;
-    }
-    if (mine) acc_add(&acc[slot], 1ull);
-    for (uint32_t g = 0; g < plan.naggs; g++) {
-      const DevAgg& ag = plan.aggs[g];
-      if (ag.fn == AG_COUNT_STAR) continue;
-      const SlabCol& s = ctl.slab[buf][ag.col];
-      if (!s.present) continue;
-      uint64_t bits;
-      if (ag.kind == DK_BOOL && !PQB_ENC_HAS_STREAM(s.enc)) {
-        uint32_t kk = s.vals_done + r;
-        bits = in ? (a.arena[s.val_base + (kk >> 3)] >> (kk & 7)) & 1 : 0;
-      } else {
-        bits = fast_value_u64(ctl, L, smem, a.arena, ag.col, buf, base_row, r, in, mine && ag.fn != AG_COUNT);
-      }
-      if (!mine) continue;
-      if (ag.update_nn) acc_add(&acc[(1 + plan.n_acc + ag.nn_slot) * nslots + slot], 1ull);
-      if (ag.fn == AG_COUNT) continue;
-      acc_apply(&acc[(1 + ag.acc_slot) * nslots + slot], ag.fn, ag.kind, bits);
-    }
+    consume_word_agg(plan, ctl, L, smem, a, buf, base_row, sel, R, acc);
   }
   return cnt;
 }

@@ -16,7 +16,8 @@ def main():
     table = DeviceTable(files, cols)
     prov = StandardTableProvider(table, schema=schema)
     q = {"small": (["level", "status"], [count_star(), sum_("bytes"), min_("bytes"), max_("bytes")], []),
-         "c3": (["host"], [count_star(), sum_("bytes")], [])}[which]
+         "c3": (["host"], [count_star(), sum_("bytes")], []),
+         "filtered": (["host"], [count_star(), sum_("bytes")], [col("level") == "ERROR"])}[which]
     for _ in range(4):
         r = prov.aggregate(*q)
     print(which, "k_scan ms", r.metrics["scan_kernel_ms"], "groups", r.metrics["groups"])
