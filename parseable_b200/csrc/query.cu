@@ -714,7 +714,7 @@ void Query::run(const PqQueryDesc& d) {
   uint32_t max_dict_n = 1;
   for (const DevChunk& c : chunks) max_dict_n = std::max(max_dict_n, c.dict_n);
   if (nrg && ncols && any_ent) {
-    k_dict_entry_offsets<<<(pa.n_chunks + 63) / 64, 64, 0, stream>>>(pa, d_colkind.p, d_colneeds.p);
+    k_dict_entry_offsets<<<(pa.n_chunks + 3) / 4, 128, 0, stream>>>(pa, d_colkind.p, d_colneeds.p);
     launches++;
   }
   if (nrg && ncols && nleaves) {
