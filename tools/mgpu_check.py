@@ -47,6 +47,7 @@ def main():
         (["region"], [count_star()], [col("level") == "NOPE"]),
     ]
     for keys, aggs, flt in cases:
+        print(f"rank {rank}: case {keys} {len(aggs)} aggs", flush=True)
         got = prov.aggregate(keys, aggs, flt, flags=L.PQ_QUERY_ALLREDUCE)
         exp = ora.group_by(keys, aggs, flt)
         res = got.table() if got.batches else exp.slice(0, 0)
