@@ -169,6 +169,39 @@ def acero_throughput(files: list[str]):
     return rows / dt, rows, tb.num_rows, dt
 
 
+def groupby_section(files, steps: int = 8, warmup: int = 3):
+    """Secondary numbers, N=1 only (not the headline): BASELINE.json configs[2] and two log-analytics
+    group-bys over the same 100 M-row files, table resident.  Parity of exactly these queries against
+    the oracle: tools/c3_groupby.py and tests/test_gpu_parity.py."""
+    import pyarrow as pa
+    from parseable_b200.query import (DeviceTable, StandardTableProvider, col, count_star, max_, min_, sum_)
+    cols = ["host", "bytes", "level", "status"]
+    schema = {"host": pa.string(), "bytes": pa.int64(), "level": pa.string(), "status": pa.int64()}
+    table = DeviceTable(files, cols)
+    prov = StandardTableProvider(table, schema=schema)
+    queries = [
+        ("C3: SELECT host, COUNT(*), SUM(bytes) GROUP BY host (10k groups)", ["host"], [count_star(), sum_("bytes")], []),
+        ("SELECT level, status, COUNT(*), SUM/MIN/MAX(bytes) GROUP BY level, status (25 groups)", ["level", "status"],
+         [count_star(), sum_("bytes"), min_("bytes"), max_("bytes")], []),
+        ("SELECT host, COUNT(*), SUM(bytes) WHERE level='ERROR' GROUP BY host", ["host"], [count_star(), sum_("bytes")],
+         [col("level") == "ERROR"]),
+    ]
+    out = []
+    for name, keys, aggs, flt in queries:
+        for _ in range(warmup):
+            r = prov.aggregate(keys, aggs, flt)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = prov.aggregate(keys, aggs, flt)
+        dt = (time.perf_counter() - t0) / steps
+        out.append({"query": name, "value": table.rows / dt, "unit": "rows/s", "ms_per_step": dt * 1e3,
+                    "k_scan_ms": r.metrics["scan_kernel_ms"], "device_ms": r.metrics["device_ms"], "groups": r.metrics["groups"]})
+        print(f"[bench] group-by: {name}: {table.rows / dt / 1e9:.1f} G rows/s ({dt * 1e3:.2f} ms/step, k_scan {r.metrics['scan_kernel_ms']:.2f} ms)",
+              file=sys.stderr)
+    table.close()
+    return out
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -205,6 +238,7 @@ def main():
     ap.add_argument("--row-groups", type=int, default=N_ROW_GROUPS, help="smaller tables for development runs")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-groupby", action="store_true", help="skip the secondary group-by measurements (N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -350,6 +384,13 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_scan_dram_bytes_per_launch")
     except Exception:
         pass
+    groupby = None
+    if world == 1 and not args.skip_groupby:
+        try:
+            table.close()   # the C2 table: make room and keep the pool small
+            groupby = groupby_section(files)
+        except Exception as e:  # secondary numbers must never cost the headline line
+            groupby = [{"error": repr(e)}]
     cpu_baseline = None
     if not args.skip_cpu:
         cores = os.cpu_count() or 1
@@ -377,6 +418,8 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "cpu_baseline": cpu_baseline,
         "d2h_bytes_per_step_resident": d2h_res,
     }
+    if groupby is not None:
+        line["groupby"] = groupby
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
