@@ -262,6 +262,12 @@ def test_arrow_default_pages_and_v2(data_dir, built):
         for flt in ([col("k") == 7], [(col("v") > 0) & (col("s") == "ccc")], [col("f") < -1.0], [col("b") == True],  # noqa: E712
                     [~(col("b") == True) | col("f").is_null()]):                                                       # noqa: E712
             assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt), (ver, kw, flt)
+        # one 120 000-row page per row group: a slab-indexed item of 59 slabs (several record batches),
+        # long RLE runs kept as a flat copy; the row ids must come out exactly
+        for flt in ([col("k") == 7], [(col("k") == 7) & (col("s") == "ccc")]):
+            res = prov.scan(filters=flt)
+            ids = np.concatenate([b.column(0).to_numpy() for b in res.batches]) if res.batches else np.array([], np.int64)
+            assert np.array_equal(ids, ora.row_ids(flt)), (ver, kw, flt)
         keys, aggs = ["k"], [count_star(), sum_("v"), min_("f"), max_("f"), count("f")]
         assert_tables_equal(prov.aggregate(keys, aggs, [col("s") != "a"]).table(), ora.group_by(keys, aggs, [col("s") != "a"]), keys)
         keys, aggs = ["b", "s"], [count_star(), avg("f")]
