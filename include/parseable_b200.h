@@ -10,6 +10,10 @@
  *                             AggregateExec DataFusion stacks on top)         src/query/stream_schema_provider.rs:114-189, 526-659
  *   pq_query_next             SendableRecordBatchStream::poll_next driven by
  *                             collect_partitioned / execute_stream_partitioned src/query/mod.rs:287, 310-334
+ *   pq_query_stream           the same stream as ONE Arrow C stream object:
+ *                             execute_stream_partitioned's merged
+ *                             SendableRecordBatchStream (arrow-rs imports it
+ *                             with ArrowArrayStreamReader)                     src/query/mod.rs:310-343
  *   pq_query_metrics          get_total_bytes_scanned ("bytes_scanned")        src/query/mod.rs:437-452
  *   pq_last_error             ExecuteError / DataFusionError::External         src/query/mod.rs:904-917
  *   pq_query_close            dropping the stream (cancellation)               src/query/mod.rs:300-340
@@ -61,6 +65,17 @@ struct ArrowArray {
   struct ArrowArray** children;
   struct ArrowArray* dictionary;
   void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif
+/* ---- Arrow C Stream Interface (https://arrow.apache.org/docs/format/CStreamInterface.html) ---- */
+#ifndef ARROW_C_STREAM_INTERFACE
+#define ARROW_C_STREAM_INTERFACE
+struct ArrowArrayStream {
+  int (*get_schema)(struct ArrowArrayStream*, struct ArrowSchema* out);
+  int (*get_next)(struct ArrowArrayStream*, struct ArrowArray* out); /* out->release == NULL: end of stream */
+  const char* (*get_last_error)(struct ArrowArrayStream*);
+  void (*release)(struct ArrowArrayStream*);
   void* private_data;
 };
 #endif
@@ -223,6 +238,9 @@ void pq_table_close(PqTable*);
 /* ---- query ---- */
 int pq_query_open(const PqQueryDesc* desc, PqQuery** out);
 int pq_query_next(PqQuery* q, int partition, struct ArrowArray* out, struct ArrowSchema* out_schema);
+/* All remaining batches of a partition as one Arrow C stream.  The stream borrows the query: release
+ * it (or drain it) before pq_query_close; the batches it produced stay valid on their own. */
+int pq_query_stream(PqQuery* q, int partition, struct ArrowArrayStream* out);
 int pq_query_metrics(PqQuery* q, PqMetrics* out);
 const char* pq_last_error(PqQuery* q); /* q == NULL: last error of the calling thread */
 void pq_query_close(PqQuery* q);

@@ -93,11 +93,16 @@ ArrowArray._fields_ = [
     ("n_children", C.c_int64), ("buffers", C.POINTER(C.c_void_p)), ("children", C.POINTER(C.POINTER(ArrowArray))),
     ("dictionary", C.POINTER(ArrowArray)), ("release", C.c_void_p), ("private_data", C.c_void_p)]
 
+class ArrowArrayStream(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p),
+                ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
 # every symbol include/parseable_b200.h declares (tests check the export list against this)
 EXPORTS = [
     "pq_init", "pq_shutdown", "pq_version", "pq_device_count",
     "pq_table_open", "pq_table_rows", "pq_table_device_bytes", "pq_table_close",
-    "pq_query_open", "pq_query_next", "pq_query_metrics", "pq_last_error", "pq_query_close",
+    "pq_query_open", "pq_query_next", "pq_query_stream", "pq_query_metrics", "pq_last_error", "pq_query_close",
     "pq_comm_unique_id", "pq_comm_init_rank", "pq_comm_destroy",
     "pq_host_alloc", "pq_host_free", "pq_file_describe",
 ]
@@ -137,6 +142,8 @@ def load() -> C.CDLL:
     lib.pq_query_open.restype = C.c_int
     lib.pq_query_next.argtypes = [C.c_void_p, C.c_int, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     lib.pq_query_next.restype = C.c_int
+    lib.pq_query_stream.argtypes = [C.c_void_p, C.c_int, C.POINTER(ArrowArrayStream)]
+    lib.pq_query_stream.restype = C.c_int
     lib.pq_query_metrics.argtypes = [C.c_void_p, C.POINTER(PqMetrics)]
     lib.pq_query_metrics.restype = C.c_int
     lib.pq_last_error.argtypes = [C.c_void_p]

@@ -113,6 +113,51 @@ int pq_query_next(PqQuery* q, int partition, struct ArrowArray* out, struct Arro
   return guard([&] { return q->q->next(partition, out, out_schema); }, &q->error);
 }
 
+namespace {
+struct StreamPriv {
+  PqQuery* q;
+  int partition;
+  std::string err;
+};
+int stream_get_schema(struct ArrowArrayStream* s, struct ArrowSchema* out) {
+  auto* p = static_cast<StreamPriv*>(s->private_data);
+  try {
+    p->q->q->schema(out);
+    return 0;
+  } catch (const std::exception& e) {
+    p->err = e.what();
+    return 5;  // EIO
+  }
+}
+int stream_get_next(struct ArrowArrayStream* s, struct ArrowArray* out) {
+  auto* p = static_cast<StreamPriv*>(s->private_data);
+  const int rc = pq_query_next(p->q, p->partition, out, nullptr);
+  if (rc == PQ_OK) return 0;
+  if (rc == PQ_END_OF_STREAM) {
+    std::memset(out, 0, sizeof(*out));  // release == NULL marks the end
+    return 0;
+  }
+  p->err = pq_last_error(p->q);
+  return 5;
+}
+const char* stream_last_error(struct ArrowArrayStream* s) { return static_cast<StreamPriv*>(s->private_data)->err.c_str(); }
+void stream_release(struct ArrowArrayStream* s) {
+  delete static_cast<StreamPriv*>(s->private_data);
+  s->private_data = nullptr;
+  s->release = nullptr;
+}
+}  // namespace
+
+int pq_query_stream(PqQuery* q, int partition, struct ArrowArrayStream* out) {
+  if (!q || !q->q || !out) return PQ_ERR_INVALID_ARG;
+  out->get_schema = stream_get_schema;
+  out->get_next = stream_get_next;
+  out->get_last_error = stream_last_error;
+  out->release = stream_release;
+  out->private_data = new StreamPriv{q, partition, {}};
+  return PQ_OK;
+}
+
 int pq_query_metrics(PqQuery* q, PqMetrics* out) {
   if (!q || !q->q || !out) return PQ_ERR_INVALID_ARG;
   *out = q->q->metrics;

@@ -168,6 +168,7 @@ class Query {
   explicit Query(const PqQueryDesc& d);
   ~Query();
   int next(int partition, ArrowArray* out, ArrowSchema* schema);
+  void schema(ArrowSchema* out) const;   // of the result batches (an empty struct when the query produced none)
   PqMetrics metrics{};
   std::string error;
 

@@ -1142,6 +1142,12 @@ void Query::run(const PqQueryDesc& d) {
   metrics.kernel_launches = launches;
 }
 
+void Query::schema(ArrowSchema* out) const {
+  if (!batches_.empty()) { export_batch(batches_[0], nullptr, out); return; }
+  OutBatch none;
+  export_batch(none, nullptr, out);
+}
+
 int Query::next(int partition, ArrowArray* out, ArrowSchema* schema) {
   (void)partition;
   if (next_batch_ >= batches_.size()) return PQ_END_OF_STREAM;

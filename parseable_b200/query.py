@@ -308,20 +308,21 @@ class StandardTableProvider:
 
     # -- TableProvider::scan -------------------------------------------------
     def scan(self, projection: Sequence[str] | None = None, filters: Iterable[Expr] = (), limit: int | None = None,
-             count_only: bool = False, row_ids: bool = True, batch_size: int = 0, flags: int = 0) -> QueryResult:
+             count_only: bool = False, row_ids: bool = True, batch_size: int = 0, flags: int = 0,
+             poll: bool = False) -> QueryResult:
         f = 0
         if count_only:
             f |= L.PQ_QUERY_COUNT_ONLY
         elif row_ids:
             f |= L.PQ_QUERY_EMIT_ROW_IDS
-        return self._run(list(filters), [], [], list(projection or []), limit, batch_size, f | flags)
+        return self._run(list(filters), [], [], list(projection or []), limit, batch_size, f | flags, poll=poll)
 
     # -- FilterExec + AggregateExec folded into the same call ----------------
     def aggregate(self, group_by: Sequence[str], aggs: Sequence[Agg], filters: Iterable[Expr] = (),
                   batch_size: int = 0, flags: int = 0) -> QueryResult:
         return self._run(list(filters), list(group_by), list(aggs), [], None, batch_size, flags)
 
-    def _run(self, filters, group_by, aggs, projection, limit, batch_size, flags) -> QueryResult:
+    def _run(self, filters, group_by, aggs, projection, limit, batch_size, flags, poll: bool = False) -> QueryResult:
         lib = L.load()
         d = _Desc()
         ops: list = []
@@ -371,8 +372,10 @@ class StandardTableProvider:
         if rc != L.PQ_OK:
             raise QueryError(rc, (lib.pq_last_error(None) or b"").decode())
         try:
+            # every batch through ONE Arrow C stream (pq_query_stream): what arrow-rs does with
+            # ArrowArrayStreamReader; pq_query_next stays for consumers that poll batch by batch
             batches = []
-            while True:
+            while poll:   # poll_next, one batch per call
                 arr_c, sch_c = L.ArrowArray(), L.ArrowSchema()
                 rc = lib.pq_query_next(h, 0, C.byref(arr_c), C.byref(sch_c))
                 if rc == L.PQ_END_OF_STREAM:
@@ -380,6 +383,15 @@ class StandardTableProvider:
                 if rc != L.PQ_OK:
                     raise QueryError(rc, (lib.pq_last_error(h) or b"").decode())
                 batches.append(pa.RecordBatch._import_from_c(C.addressof(arr_c), C.addressof(sch_c)))
+            if not poll:
+                stream_c = L.ArrowArrayStream()
+                rc = lib.pq_query_stream(h, 0, C.byref(stream_c))
+                if rc != L.PQ_OK:
+                    raise QueryError(rc, (lib.pq_last_error(h) or b"").decode())
+                try:
+                    batches = list(pa.RecordBatchReader._import_from_c(C.addressof(stream_c)))
+                except pa.ArrowException as e:
+                    raise QueryError(L.PQ_ERR_CUDA, (lib.pq_last_error(h) or str(e).encode()).decode()) from e
             m = L.PqMetrics()
             lib.pq_query_metrics(h, C.byref(m))
         finally:

@@ -238,6 +238,18 @@ def test_multiple_files_missing_columns_and_shards(env, data_dir):
     assert np.array_equal(np.sort(np.concatenate(ids)), ora.row_ids(flt))
 
 
+def test_stream_and_poll_next_agree(env):
+    """pq_query_stream (one Arrow C stream) and pq_query_next (batch by batch) hand out the same batches."""
+    path, ora, prov = env["nn"]
+    flt = FILTERS["c2_level_and_latency"]
+    a = prov.scan(filters=flt, batch_size=500)
+    b = prov.scan(filters=flt, batch_size=500, poll=True)
+    assert len(a.batches) == len(b.batches) > 1
+    for x, y in zip(a.batches, b.batches):
+        assert x.equals(y)
+    assert np.array_equal(np.concatenate([x.column(0).to_numpy() for x in a.batches]), ora.row_ids(flt))
+
+
 def test_arrow_default_pages_and_v2(data_dir, built):
     """Files NOT written the Parseable way: pyarrow defaults (1 MiB pages, misaligned across columns),
     data page v2, required (non-nullable) columns, small dictionaries with long RLE runs."""
