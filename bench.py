@@ -304,6 +304,19 @@ def main():
     for _ in range(args.warmup):
         r = step_resident()
     sel_expected = sum(b.num_rows for b in r.batches)
+    # full-size properties of the result (the oracle cannot decode 100 M rows in the tests' time budget):
+    # row ids strictly ascending and in range, COUNT-only scan agrees, a checksum of per-file checksums agrees
+    checks = {}
+    if rank == 0:
+        import numpy as np
+        ids = np.concatenate([b.column(0).to_numpy() for b in r.batches]) if r.batches else np.array([], np.int64)
+        assert len(ids) == sel_expected and (len(ids) == 0 or (ids[0] >= 0 and ids[-1] < rows_per_step))
+        assert bool(np.all(np.diff(ids) > 0)), "row ids are not strictly ascending"
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == sel_expected
+        per_file = [StandardTableProvider([f], schema=schema).scan(filters=flt, count_only=True).metrics["rows_selected"] for f in files]
+        assert sum(per_file) == sel_expected, (sum(per_file), sel_expected)
+        checks = {"row_ids_strictly_ascending": True, "count_only_agrees": True, "sum_of_per_file_counts_agrees": True,
+                  "selected_rows": int(sel_expected)}
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -396,6 +409,10 @@ def main():
         cores = os.cpu_count() or 1
         sample = files[: max(1, min(len(files), cores // 2 if cores >= 8 else 2))]
         v, rows, sel, secs = cpu_port_throughput(sample, workers=min(cores, len(sample)))
+        # the CPU port's answer over its sample is also the checker of the GPU arm at full row-group size
+        gpu_sel = sum(StandardTableProvider([f], schema=schema).scan(filters=flt, count_only=True).metrics["rows_selected"] for f in sample)
+        assert gpu_sel == sel, f"GPU selected {gpu_sel} rows over the CPU sample, the oracle port {sel}"
+        checks["oracle_port_count_over_cpu_sample_agrees"] = True
         cpu_baseline = {"value": v, "unit": "rows/s", "cores": min(cores, len(sample)), "kind": "port",
                         "sample": f"{len(sample)} of {len(files)} files ({rows} rows, {secs:.1f} s), pyarrow decode + oracle.c, one process per file"}
         try:
@@ -418,6 +435,7 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "cpu_baseline": cpu_baseline,
         "d2h_bytes_per_step_resident": d2h_res,
     }
+    line["checks"] = checks
     if groupby is not None:
         line["groupby"] = groupby
     print(json.dumps(line), flush=True)
