@@ -326,8 +326,11 @@ def main():
     host_ms = []
     algo_bytes = r.metrics["algorithmic_bytes"]
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         r = step_resident()
+        step_ms.append(1000.0 * (time.perf_counter() - ts))
         launches += r.metrics["kernel_launches"]
         scan_ms.append(r.metrics["scan_kernel_ms"])
         dev_ms.append(r.metrics["device_ms"])
@@ -435,6 +438,11 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "cpu_baseline": cpu_baseline,
         "d2h_bytes_per_step_resident": d2h_res,
     }
+    try:   # spread of the timed steps (median + p10 / p90)
+        q = sorted(step_ms)
+        line["step_ms_quantiles"] = {"p10": q[len(q) // 10], "p50": q[len(q) // 2], "p90": q[(len(q) * 9) // 10]}
+    except Exception:
+        pass
     line["checks"] = checks
     if groupby is not None:
         line["groupby"] = groupby
