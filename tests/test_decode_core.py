@@ -123,6 +123,40 @@ def test_transcode_to_flat_bitpacked(dc, bw):
     assert np.array_equal(back, vals)
 
 
+@pytest.mark.parametrize("pattern", ["random", "skewed", "long_runs", "mixed"])
+@pytest.mark.parametrize("bw", [0, 1, 3, 6, 8, 9, 11, 14, 17])
+def test_slab_index_and_octet_pass_replica(dc, bw, pattern):
+    """CPU replica of k_slab_index / k_flatten_pages / the octet pass (tools/decode_core_host.cpp): the
+    selection bytes of a dictionary-LUT leaf over one 20 000-row page must equal LUT[value] for every
+    run structure — bit-packed only, a skewed column (hundreds of tiny runs: flat copy), long RLE runs,
+    and a mix whose octets straddle directory entries."""
+    rng = np.random.default_rng(100 * bw + len(pattern))
+    n = 20000
+    hi = (1 << bw) if bw else 1
+    if pattern == "random":
+        vals = rng.integers(0, hi, n, dtype=np.uint64)
+    elif pattern == "skewed":
+        vals = np.where(rng.random(n) < 0.8, 0, rng.integers(0, hi, n)).astype(np.uint64)
+    elif pattern == "long_runs":
+        vals = np.repeat(rng.integers(0, hi, n // 150 + 2, dtype=np.uint64), rng.integers(100, 400, n // 150 + 2))[:n]
+    else:
+        vals = np.repeat(rng.integers(0, hi, n // 5 + 2, dtype=np.uint64), rng.integers(1, 30, n // 5 + 2))[:n]
+    vals = vals.astype(np.uint64)
+    enc = encode_hybrid(vals, bw, rng, rle_bias=0.5)
+    smem = 1 if hi <= 2048 else 0
+    lut = (rng.random(max(hi, 2048)) < 0.3).astype(np.uint8)
+    out = np.zeros((n + 7) // 8 + 256, np.uint8)
+    flat = C.c_int32(0)
+    dc.dc_index_octet_scan.restype = C.c_int64
+    got = dc.dc_index_octet_scan(enc, C.c_uint64(len(enc)), bw, n, lut.ctypes.data_as(C.c_void_p), smem, 16,
+                                 out.ctypes.data_as(C.c_void_p), C.byref(flat))
+    assert got == n
+    exp = np.packbits(lut[vals.astype(np.int64)].astype(bool), bitorder="little")
+    assert np.array_equal(out[: len(exp)], exp), (bw, pattern, flat.value)
+    if pattern == "long_runs" and bw >= 1:
+        assert flat.value == 0      # a handful of long runs per slab fits the directory budget
+
+
 def test_f64_order_key_is_total_order(dc):
     vals = [float("-inf"), -1e300, -1.5, -0.0, 0.0, 5e-324, 1.5, 1e300, float("inf")]
     nan_pos = struct.unpack("<d", struct.pack("<Q", 0x7FF8000000000001))[0]
