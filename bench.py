@@ -173,7 +173,7 @@ def acero_throughput(files: list[str]):
 def groupby_section(files, steps: int = 8, warmup: int = 3):
     """Secondary numbers, N=1 only (not the headline): BASELINE.json configs[2] and two log-analytics
     group-bys over the same 100 M-row files, table resident.  Parity of exactly these queries against
-    the oracle: tools/c3_groupby.py and tests/test_gpu_parity.py."""
+    the oracle: tests/scripts/c3_groupby.py and tests/test_gpu_parity.py."""
     import pyarrow as pa
     from parseable_b200.query import (DeviceTable, StandardTableProvider, col, count_star, max_, min_, sum_)
     cols = ["host", "bytes", "level", "status"]

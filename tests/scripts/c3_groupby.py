@@ -2,7 +2,7 @@
 (100 M rows, 10 000 distinct hosts), table resident in HBM; plus configs-style filtered group-by.
 Checks one file against the oracle, then times the whole table."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests/scripts/ -> repo root
 sys.path.insert(0, ROOT)
 import pyarrow as pa
 import bench

@@ -1,7 +1,7 @@
 """Race / work-distribution stress for k_scan: same queries under forced grid sizes
 (PQB_GRID) so that CTAs take several items each in every order, compared with the oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # tests/scripts/ -> repo root
 sys.path.insert(0, ROOT)
 from oracle.oracle import Oracle
 from parseable_b200 import synth

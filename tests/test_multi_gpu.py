@@ -19,7 +19,7 @@ def test_two_rank_allreduce_matches_oracle(small_files, tmp_path, built):
         pytest.skip("needs 2 GPUs")
     n = 2
     idfile = str(tmp_path / "nccl_id")
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "mgpu_check.py"), str(r), str(n), idfile,
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "scripts", "mgpu_check.py"), str(r), str(n), idfile,
                                small_files["nulls"], small_files["nn"]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(n)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
