@@ -180,6 +180,9 @@ struct DevScanArgs {
   const struct DirEntry* slab_dirs;  // [rec.ent0 + e]
 };
 
+// one page the second pass of the slab index re-packs flat (k_flatten_pages)
+struct FlatJob { uint32_t page; uint32_t _pad; uint64_t side_off; };
+
 // run-directory entry produced by the stream walker
 struct DirEntry {     // 16 bytes: bulk-copyable (TMA) from the prebuilt slab directory
   uint32_t start;    // first value (slab relative)

@@ -1033,7 +1033,6 @@ __global__ void k_slab_index(const uint8_t* __restrict__ arena, const DevPage* _
 // Second pass of the slab index: pages whose run structure does not fit a directory get a flat
 // bit-packed copy of their index stream (decode_core.cuh transcode_values) in a side buffer; every
 // slab of such a page is then a single bit-packed directory entry at a 256 * bw byte stride.
-struct FlatJob { uint32_t page; uint32_t _pad; uint64_t side_off; };
 __global__ void k_flatten_pages(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages, const FlatJob* __restrict__ jobs,
                                 uint32_t n_jobs, uint8_t* __restrict__ side, DevSlabRec* __restrict__ slab_recs,
                                 DirEntry* __restrict__ slab_dirs, uint8_t* __restrict__ page_fast) {

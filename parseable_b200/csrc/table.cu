@@ -728,8 +728,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     PQB_CUDA(cudaMemcpyAsync(fast.data(), d_fast, fast.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     // run-heavy pages (skewed low-cardinality columns): a flat bit-packed copy replaces the directory
-    struct FlatJobH { uint32_t page; uint32_t pad; uint64_t side_off; };
-    std::vector<FlatJobH> fjobs;
+    std::vector<FlatJob> fjobs;
     uint64_t side = 0;
     for (size_t i = 0; i < pages.size(); i++)
       if (fast[i] == 5) {
@@ -743,8 +742,8 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       void* d_jobs = nullptr;
       PQB_CUDA(cudaMallocAsync((void**)&d_slab_flat, slab_flat_bytes, stream));
       PQB_CUDA(cudaMemsetAsync(d_slab_flat + side, 0, slab_flat_bytes - side, stream));
-      PQB_CUDA(cudaMallocAsync(&d_jobs, fjobs.size() * sizeof(FlatJobH), stream));
-      PQB_CUDA(cudaMemcpyAsync(d_jobs, fjobs.data(), fjobs.size() * sizeof(FlatJobH), cudaMemcpyHostToDevice, stream));
+      PQB_CUDA(cudaMallocAsync(&d_jobs, fjobs.size() * sizeof(FlatJob), stream));
+      PQB_CUDA(cudaMemcpyAsync(d_jobs, fjobs.data(), fjobs.size() * sizeof(FlatJob), cudaMemcpyHostToDevice, stream));
       launch_flatten_pages(d_arena, d_pages, d_jobs, uint32_t(fjobs.size()), d_slab_flat, d_slab_recs, d_slab_dirs, d_fast, stream);
       PQB_CUDA(cudaMemcpyAsync(fast.data(), d_fast, fast.size(), cudaMemcpyDeviceToHost, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
