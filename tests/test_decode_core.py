@@ -196,6 +196,30 @@ def test_like_match(dc, s, p, kind, ci, want):
     assert bool(dc.dc_like(s, len(s), p, len(p), kind, int(ci))) == want
 
 
+def test_device_like_matcher_agrees_with_acero(dc):
+    """like_general is the very function k_leaf_luts runs per dictionary entry (host/device code): every
+    (value, pattern) pair of a grid with wildcards, escapes, empty strings and multi-byte characters
+    must agree with Acero's match_like; ILIKE is compared on ASCII patterns (the matcher folds ASCII only)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    vals = ["", "a", "ab", "abc", "a%c", "a_c", "A_C", "abcabc", "xxabcxx", "ABC", "aXc", "%", "_", "a\\c", "timeout", "Timeout after 30s",
+            "GET /api/v1/users/42", "get /api/v1/users/42", "ééé", "aéc", "日本語ログ", "a\nb"]
+    pats = ["%", "", "a", "a%", "%c", "%b%", "a_c", "a\\_c", "a\\%c", "%\\%%", "_", "__", "___", "%abc%abc%", "abc%abc", "%a%b%c%", "A_C", "%timeout%",
+            "Timeout%30s", "GET /api/%/users/__", "a%c", "%é%", "a_c%", "%_", "_%_", "日_語%", "%\\\\%"]
+    arr = pa.array(vals, pa.string())
+    for p in pats:
+        pb = p.encode()
+        for ci in (False, True):
+            if ci and any(ord(ch) > 127 for ch in p):
+                continue
+            want = pc.match_like(arr, p, ignore_case=ci).to_pylist()
+            for v, w in zip(vals, want):
+                if ci and any(ord(ch) > 127 for ch in v):
+                    continue
+                vb = v.encode()
+                assert bool(dc.dc_like(vb, len(vb), pb, len(pb), 4, int(ci))) == w, (v, p, ci)
+
+
 def _page_payloads(path, col):
     """Raw data-page payloads of column `col` (row group 0) located with the library's own page walk."""
     import ctypes as C
