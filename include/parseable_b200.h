@@ -220,6 +220,7 @@ typedef struct {
   uint64_t groups;          /* output groups (aggregate queries) */
   double host_ms;           /* wall time of pq_query_open (planning + uploads + device work + result copy) */
   double upload_ms;         /* of which: footer parse, page walk and H2D of the column chunks (file-list queries) */
+  double allreduce_ms;      /* CUDA-event time of the NCCL all-reduce of the partial tables (PQ_QUERY_ALLREDUCE) */
 } PqMetrics;
 
 /* ---- lifecycle ---- */

@@ -69,7 +69,7 @@ class PqMetrics(C.Structure):
         ("row_groups_total", C.c_uint64), ("row_groups_pruned", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
         ("device_ms", C.c_double), ("scan_kernel_ms", C.c_double), ("groups", C.c_uint64),
-        ("host_ms", C.c_double), ("upload_ms", C.c_double),
+        ("host_ms", C.c_double), ("upload_ms", C.c_double), ("allreduce_ms", C.c_double),
     ]
 
     def as_dict(self) -> dict:

@@ -15,6 +15,7 @@ namespace {
 std::mutex g_mu;
 ncclComm_t g_comm = nullptr;
 int g_nranks = 0, g_rank = 0;
+uint64_t g_epoch = 0;   // bumped by every comm_init_rank: caches of cross-rank agreements are tagged with it
 
 void check(ncclResult_t r, const char* what) {
   if (r != ncclSuccess) throw Error(PQ_ERR_CUDA, std::string(what) + ": " + ncclGetErrorString(r));
@@ -40,6 +41,7 @@ int comm_init_rank(const uint8_t* id, int nranks, int rank) {
   check(ncclCommInitRank(&g_comm, nranks, u, rank), "ncclCommInitRank");
   g_nranks = nranks;
   g_rank = rank;
+  g_epoch++;
   return PQ_OK;
 }
 
@@ -54,6 +56,9 @@ int comm_destroy() {
 }
 
 bool comm_active() { return g_comm != nullptr; }
+uint64_t comm_epoch() { return g_epoch; }
+void comm_group_begin() { check(ncclGroupStart(), "ncclGroupStart"); }
+void comm_group_end() { check(ncclGroupEnd(), "ncclGroupEnd"); }
 int comm_nranks() { return g_nranks; }
 int comm_rank() { return g_rank; }
 

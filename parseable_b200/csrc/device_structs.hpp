@@ -51,8 +51,20 @@ struct DevChunk {              // one column chunk (row group x referenced colum
   uint32_t dict_n;             // dictionary entries (0: no dictionary page)
   uint32_t first_page;         // into pages[]
   uint32_t n_pages;
-  uint32_t lut_base;           // base into per-entry side tables (str offsets / leaf LUTs / gid LUTs)
+  uint32_t lut_base;           // base into the COLUMN's per-entry side tables (str offsets / leaf LUTs / gid LUTs):
+                               // entries of this column in the row groups before this one (table level, query independent)
   uint32_t present;            // 0: column missing from this file -> all NULL
+  uint64_t dict8_off;          // flat-store offset of the 8-byte aligned copy of a numeric dictionary (~0: none)
+};
+
+// Flat store (flat_store.cuh): the scan-ready copy of one data page.
+enum FlatKind : uint8_t { FK_NONE = 0, FK_INDEX = 1, FK_PLAIN8 = 2, FK_BITS = 3 };
+struct FlatPageRec {           // parallel to pages[]
+  uint64_t off;                // byte offset in the flat buffer, 16-byte aligned
+  uint32_t rows;
+  uint8_t bw;                  // FK_INDEX: bits per dictionary index; FK_BITS: 1
+  uint8_t fkind;               // FlatKind: FK_INDEX dictionary indices, FK_PLAIN8 8-byte values, FK_BITS boolean values
+  uint16_t _pad;
 };
 
 struct DevItem {               // unit of CTA work: rows between two page boundaries common to all columns
@@ -62,9 +74,12 @@ struct DevItem {               // unit of CTA work: rows between two page bounda
   uint32_t bitmap_word0;       // first word of this item's region in the selection bitmap
   uint64_t global_row0;        // ordinal of row0 in the scanned table (row-id output)
   uint32_t page[kMaxCols];     // page index (into pages[]) holding row0, per column slot
-  uint32_t fast;               // 1: every referenced column has exactly one, slab-indexed page over this item
+  uint32_t poff[kMaxCols];     // flat items: row0 minus the page's first row (a piece may start inside a page)
+  uint32_t fast;               // bit 0: every referenced column has exactly one, slab-indexed page over this item (k_scan);
+                               // bit 1: ... exactly one page with a flat-store copy (k_flat_*)
   uint32_t _pad;
 };
+constexpr uint32_t kItemSlabIndexed = 1u, kItemFlat = 2u;
 
 // One slab (kSlabRows rows from the page start) of one page in the table's slab index
 // (k_slab_index, built when the table is opened): what the per-slab control of k_scan would derive
@@ -124,7 +139,8 @@ struct DevKey {
   uint16_t _pad;
   uint32_t card;      // global distinct values; NULL takes id == card
   uint32_t stride;    // mixed-radix stride of this key in the dense group slot
-  uint32_t gid_off;   // gid LUT base (u32 per dictionary entry, entry = chunk.lut_base+idx)
+  uint32_t _pad2;
+  const uint32_t* gid;  // gid LUT of the key column (u32 per dictionary entry, entry = chunk.lut_base + idx)
 };
 
 enum ScanMode : uint32_t { SM_FILTER = 0, SM_AGG = 1 };
@@ -156,6 +172,14 @@ struct DevPlan {
   int8_t col_l1[kMaxCols];
   uint32_t row_major;          // 1: no-NULL slabs use the register-only row-major pass
   uint32_t fast_and;           // 1: the predicate is leaf AND leaf AND ... (1-4 CMP/LIKE leaves): specialised pass
+  uint32_t conj;               // 1: the predicate is a pure conjunction of leaves (flat kernels: survivors-only evaluation)
+  uint32_t hot_slots;          // flat aggregate kernel: group slots < hot_slots accumulate in shared memory
+  uint32_t flat_krows;         // flat aggregate kernel: rows per consumer thread per slab
+  uint32_t flat_slab_rows;     // rows per slab of the flat kernels
+  uint32_t no_flat;            // 1: the flat kernels do not run (NULL literal in the predicate, PQB_FLAT_SCAN=0): k_scan takes every item
+  uint32_t replicas;           // accumulator table copies in global memory; CTA b adds into copy b % replicas (merged by k_acc_reduce)
+  uint32_t smem_share;         // of every 8 consumer warps of k_flat_agg, how many keep hot slots in shared memory (the rest use L2)
+  uint32_t f64_global;         // 1: f64 SUM / AVG cells always go to L2 (no native shared-memory f64 atomic)
 };
 
 // Accumulator table layout (device, 8-byte cells, struct of arrays over nslots):
@@ -169,8 +193,10 @@ struct DevScanArgs {
   const DevChunk* chunks;      // [rg_slot * ncols + col]
   const DevItem* items;
   const uint8_t* luts;         // leaf LUT bytes (0 false, 1 true) per dictionary entry
-  const uint32_t* gid_luts;    // group ids per dictionary entry
   const uint8_t* lit_pool;
+  const uint8_t* rg_live;      // per row group: 0 = pruned by statistics for this query (nullptr: all live)
+  const uint8_t* flat;         // flat store (flat_store.cuh)
+  const FlatPageRec* fpages;   // parallel to pages[]
   uint32_t* bitmap;            // selection bitmap, per-item word regions
   uint32_t* item_counts;       // selected rows per item
   unsigned long long* acc;     // accumulator table (global)

@@ -6,7 +6,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -84,6 +86,7 @@ struct TableChunk {
   TablePageRef pages;
   bool has_dict_pages = false, has_plain_pages = false, has_delta_pages = false;
   uint32_t max_bw = 0;
+  uint64_t dict8_off = ~0ull;   // flat store: 8-byte aligned copy of a numeric dictionary
 };
 
 struct TableColumn {
@@ -99,6 +102,39 @@ struct TableRowGroup {
   uint64_t global_row0 = 0;         // ordinal over ALL row groups of the file list (before sharding)
   std::vector<TableChunk> chunks;   // per table column
   bool pages_aligned = false;       // every present column has the same page boundaries (Parseable's writer: 20 000-row pages)
+};
+
+// Query-independent side tables of one table column, built on first use and kept with the table:
+// string dictionary entry offsets, and (GROUP BY) the interned group ids of every dictionary entry.
+struct KeyDict { std::vector<uint32_t> offs; std::vector<uint8_t> bytes; };
+struct ColSide {
+  std::vector<uint32_t> base_per_rg;   // dictionary entries of this column in the row groups before g
+  uint32_t total_entries = 0;
+  uint32_t max_dict_n = 0;
+  uint64_t* d_ent_off = nullptr;       // arena offset of every dictionary entry (strings: behind the length prefix)
+  bool ent_ready = false;
+  // group-key interning (local numbering, hot-first)
+  bool key_ready = false;
+  uint32_t* d_gid = nullptr;           // group id per dictionary entry
+  uint32_t card = 0;
+  KeyDict kd;                          // distinct values in group-id order
+  uint64_t* d_key_hash = nullptr;      // 64-bit hash of every distinct value, group-id order (multi-GPU unification)
+};
+
+// What a query needs per SET of referenced columns, built once per (table, column set): the chunk
+// table, the work items (row ranges between page boundaries common to the columns) and what the
+// kernels' shared-memory layouts depend on.
+struct Shape {
+  std::vector<int> tcols;
+  std::vector<DevItem> items;
+  DevChunk* d_chunks = nullptr;        // [table row group * ncols + slot]
+  DevItem* d_items = nullptr;
+  uint32_t n_flat = 0, n_general = 0, n_slab_fast = 0;
+  uint32_t bitmap_words = 0;
+  std::vector<uint32_t> max_bw, flat_max_bw;          // per slot
+  std::vector<uint8_t> has_dict, has_plain, has_delta, flat_plain8;
+  std::atomic<unsigned long long> last_total{~0ull};   // rows the last filter scan of this shape selected (sizes the next result)
+  ~Shape();
 };
 
 // Encoded column chunks of a set of files, resident in HBM ("hot tier in HBM").
@@ -129,6 +165,25 @@ class Table {
   uint64_t h2d_bytes = 0;
   uint64_t chunk_bytes = 0;
   int find_column(const std::string& name) const;
+
+  // flat store (flat_store.cuh): header-less bit-packed copies of the NULL-free dictionary-index pages,
+  // aligned copies of PLAIN 8-byte pages and of numeric dictionaries
+  uint8_t* d_flat = nullptr;
+  uint64_t flat_bytes = 0;
+  std::vector<FlatPageRec> flat_pages;   // host copy, parallel to pages
+  FlatPageRec* d_flat_pages = nullptr;
+  uint64_t flat_page_count = 0;
+
+  // lazily built, query independent (the table is immutable once opened); guarded by side_mu
+  mutable std::mutex side_mu;
+  mutable std::vector<ColSide> sides;
+  mutable std::map<std::vector<int>, std::shared_ptr<Shape>> shapes;
+  std::shared_ptr<Shape> shape_for(const std::vector<int>& tcols, cudaStream_t stream) const;
+  void ensure_ent_off(int tcol, cudaStream_t stream) const;
+  void ensure_key(int tcol, cudaStream_t stream) const;
+
+ private:
+  void build_flat_store(cudaStream_t stream);
 };
 
 // staged window bytes for one slab of a dictionary-index stream of the given bit width
@@ -138,6 +193,12 @@ void launch_slab_index(const uint8_t* arena, const DevPage* pages, uint32_t n_pa
                        DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream);
 void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* side,
                           DevSlabRec* recs, DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream);
+// launches k_flat_store (flat_store.cuh); jobs are FlatStoreJob records on the device
+void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat, uint8_t* ok,
+                       cudaStream_t stream);
+// side-table builders (prep_kernels.cuh), defined in query.cu
+void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, cudaStream_t stream);
+void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream);
 
 // page-locked host block that result batches can alias (zero copy); returns to the pool when
 // the last batch that references it is released by the consumer
@@ -188,6 +249,9 @@ int comm_unique_id(uint8_t* id);
 int comm_init_rank(const uint8_t* id, int nranks, int rank);
 int comm_destroy();
 bool comm_active();
+uint64_t comm_epoch();        // changes with every communicator
+void comm_group_begin();      // ncclGroupStart / End: the collectives in between launch as one
+void comm_group_end();
 int comm_nranks();
 int comm_rank();
 void comm_allreduce_u64(void* buf, size_t count, int op /*0 sum,1 min(s64),2 max(s64),3 sum f64*/, cudaStream_t s);

@@ -1,0 +1,656 @@
+// The flat scan kernels: decode -> predicate -> (selection bitmap | group-by accumulation) over the
+// flat store (flat_store.cuh).  Same operator chain of the reference as k_scan
+//   DataSourceExec(Parquet) -> FilterExec -> AggregateExec(Partial)
+// (/root/reference/src/query/mod.rs:287), for the common case: every
+// referenced column of a work item has one NULL-free page with a flat copy.  Items that do not
+// qualify (NULLs, DELTA pages the time range cuts, PLAIN strings) stay with k_scan.
+//
+// Shape (both kernels): persistent CTAs, one PRODUCER warp and N consumer warps.  The producer's
+// elected lane pulls work items from the queue, and for every slab of an item stages the slab's
+// bytes of every referenced column with one TMA bulk copy per column (cp.async.bulk -> mbarrier
+// complete_tx) into a ring of shared-memory stages; it runs up to `nstages` slabs ahead, across item
+// boundaries.  Consumers wait on the stage's `full` mbarrier, work out of shared memory and hand the
+// stage back through its `empty` mbarrier.  No block barrier inside the loop, no run directory, no
+// header walk: value i of a page is bits [i*bw, (i+1)*bw).
+//
+// k_flat_filter: 8 consumer warps, a thread owns 32 consecutive rows = one word of the selection
+//   bitmap.  First leaf: all 32 indices unpacked with compile-time shifts; a dictionary of <= 32
+//   entries keeps its whole LUT in ONE REGISTER (3 instructions per row: extract, rotate, funnel).
+//   Later leaves of a conjunction run only on the surviving rows.  HBM traffic = encoded bytes once
+//   + 1 bit per row.
+// k_flat_agg: 31 consumer warps, one CTA per SM so that the hot part of the accumulator table
+//   (group slots < plan.hot_slots; group ids are numbered hot-first) lives in shared memory
+//   next to the stages; cold slots go to L2 with fire-and-forget reductions.  Rows are dealt to
+//   threads interleaved (lane L of a warp takes row base + L): PLAIN 8-byte values are read without
+//   bank conflicts and neighbouring lanes share their index words.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "decode_core.cuh"
+#include "device_structs.hpp"
+#include "flat_store.cuh"
+#include "ptx_utils.cuh"
+#include "scan_kernel.cuh"   // acc_add / acc_apply / acc_merge
+
+namespace pqb {
+
+constexpr int kFlatStagesMax = 4;
+constexpr int kFilterConsumerWarps = 8;
+constexpr int kFilterThreads = 32 * (kFilterConsumerWarps + 1);
+constexpr int kFilterSlabRows = 32 * 32 * kFilterConsumerWarps;   // 8192: one 32-row word per consumer thread
+constexpr int kAggThreads = 1024;
+constexpr int kAggConsumers = kAggThreads - 32;
+
+struct FlatLayout {              // dynamic shared memory of the flat kernels (byte offsets), computed on the host
+  uint32_t nstages;
+  uint32_t stage_bytes;
+  uint32_t stage0;               // first stage buffer
+  uint32_t col_off[kMaxCols];    // column c inside a stage (16-byte aligned)
+  uint32_t acc;                  // hot accumulator table (k_flat_agg)
+  uint32_t total;
+};
+
+struct FlatStageCol {
+  uint64_t dict8;                // flat-store offset of the aligned numeric dictionary (~0: none)
+  uint32_t bw;                   // bits per value (FK_PLAIN8: 64, FK_BITS: 1)
+  uint32_t fkind;                // FlatKind
+  uint32_t lut_base;
+  uint32_t dict_n;
+  uint32_t phase;                // bit of the staged bytes where row 0 of the slab starts (a piece may start inside a
+  uint32_t _pad;                 // page at a row that is not a multiple of 128: the copy starts at the 16 bytes below)
+};
+struct FlatStage {
+  uint32_t item;                 // 0xffffffff: the queue is empty, consumers leave
+  uint32_t R;                    // rows of this slab
+  uint32_t r0;                   // first row of the slab inside the item
+  uint32_t bitmap_word0;
+  uint32_t regmask;              // bit l: leaf l's whole LUT is lutreg[l] (dictionary of <= 32 entries, index width <= 5)
+  uint32_t lutreg[kMaxLeaves];   // periodic with 2^bw, so the bits above the index never matter
+  FlatStageCol col[kMaxCols];
+};
+struct FlatCtl {
+  uint64_t full[kFlatStagesMax];
+  uint64_t empty[kFlatStagesMax];
+  FlatStage st[kFlatStagesMax];
+};
+
+__device__ __forceinline__ uint32_t flat_col_bytes(uint32_t phase, uint32_t bw, uint32_t rows) {
+  const uint32_t nb = (phase + rows * bw + 7u) >> 3;
+  return (nb + 15u) & ~15u;
+}
+
+// ---- producer: one warp; lane 0 owns the queue, the barriers and the TMA copies ------------------
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  // mbarrier.try_wait suspends the thread in hardware for a bounded time: no sleep / back-off code around it
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout& L, const DevScanArgs& a, FlatCtl& ctl,
+                                           uint8_t* smem, uint32_t S) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t stage = 0, par = 1;   // parity the next wait on empty[stage] needs; a fresh barrier counts as released
+  const uint32_t ncols = plan.ncols;
+  for (;;) {
+    uint32_t id = 0;
+    if (lane == 0) id = (uint32_t)atomicAdd(&a.counters[2], 1ull);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (id >= plan.n_items) break;
+    const DevItem& item = a.items[id];
+    if (!(item.fast & kItemFlat)) continue;
+    const uint32_t rg = item.rg;
+    if (a.rg_live && !a.rg_live[rg]) continue;
+    // lane c looks after column slot c
+    FlatStageCol mycol{};
+    uint64_t mysrc = 0;
+    uint32_t mypoff = 0;
+    if (lane < ncols) {
+      const DevChunk& ch = a.chunks[rg * ncols + lane];
+      const FlatPageRec fp = a.fpages[item.page[lane]];
+      mycol.dict8 = ch.dict8_off;
+      mycol.bw = fp.bw;
+      mycol.fkind = fp.fkind;
+      mycol.lut_base = ch.lut_base;
+      mycol.dict_n = ch.dict_n;
+      mysrc = fp.off;
+      mypoff = item.poff[lane];
+    }
+    // register LUTs of this item's row group: every lane fetches one LUT byte, one ballot per leaf
+    uint32_t regmask = 0, mylut = 0;
+    for (uint32_t l = 0; l < plan.nleaves; l++) {
+      const DevLeaf& lf = plan.leaves[l];
+      const uint32_t bw = __shfl_sync(0xffffffffu, mycol.bw, lf.col), fk = __shfl_sync(0xffffffffu, mycol.fkind, lf.col);
+      const uint32_t dn = __shfl_sync(0xffffffffu, mycol.dict_n, lf.col), lb = __shfl_sync(0xffffffffu, mycol.lut_base, lf.col);
+      if (!((lf.kind == LK_CMP || lf.kind == LK_LIKE) && fk == FK_INDEX && bw <= 5 && dn <= 32)) continue;
+      const uint8_t* lut = a.luts + lf.lut_off + lb;
+      uint32_t r = __ballot_sync(0xffffffffu, lane < dn && lut[lane] != 0);
+      for (uint32_t p = 1u << bw; p < 32; p <<= 1) r |= r << p;
+      if (lane == l) mylut = r;
+      regmask |= 1u << l;
+    }
+    const uint32_t nrows = item.nrows, bm0 = item.bitmap_word0;
+    for (uint32_t r0 = 0; r0 < nrows; r0 += S) {
+      const uint32_t R = nrows - r0 < S ? nrows - r0 : S;
+      if (lane == 0) mbar_wait_spin(&ctl.empty[stage], par);
+      __syncwarp();
+      FlatStage& st = ctl.st[stage];
+      // first bit of the slab in the page's flat copy; the copy starts at the 16-byte boundary below it
+      const uint64_t bit0 = uint64_t(mypoff + r0) * mycol.bw;
+      mycol.phase = uint32_t(bit0 & 127u);
+      uint32_t nb = lane < ncols ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
+      if (lane < ncols) st.col[lane] = mycol;
+      if (lane < plan.nleaves) st.lutreg[lane] = mylut;
+      uint32_t bytes = nb;
+      for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+      if (lane == 0) {
+        st.item = id;
+        st.R = R;
+        st.r0 = r0;
+        st.bitmap_word0 = bm0;
+        st.regmask = regmask;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&ctl.full[stage], bytes);
+      __syncwarp();
+      if (nb) tma_load_1d(smem + L.stage0 + stage * L.stage_bytes + L.col_off[lane], a.flat + mysrc + ((bit0 >> 7) << 4), nb, &ctl.full[stage]);
+      if (++stage == L.nstages) { stage = 0; par ^= 1u; }
+    }
+  }
+  if (lane == 0) {
+    mbar_wait_spin(&ctl.empty[stage], par);
+    ctl.st[stage].item = 0xffffffffu;
+    mbar_arrive(&ctl.full[stage]);
+  }
+}
+
+__device__ __forceinline__ void flat_ctl_init(FlatCtl& ctl, uint32_t nstages, uint32_t consumer_warps) {
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < nstages; s++) {
+      mbar_init(&ctl.full[s], 1);
+      mbar_init(&ctl.empty[s], consumer_warps);
+    }
+    mbar_fence_init();
+  }
+}
+
+// ---- leaves -------------------------------------------------------------------------------------
+// Everything a consumer needs about one leaf for the CURRENT slab; built once per slab (warp uniform)
+// so that the row loops below carry no interpretation: the switch on the page kind sits outside them.
+struct LeafCtx {
+  const uint32_t* colw;      // the column's staged slab (flat bits / 8-byte values), whole words of the phase folded in
+  const uint8_t* lut;        // this leaf's LUT bytes for the chunk (global)
+  uint32_t phase;            // remaining bit phase (0..31) of row 0
+  uint32_t bw, fkind, dict_max;   // dict_max = entries - 1: a corrupt index must not leave the LUT (the reference's reader errors out)
+  uint32_t lutreg;           // reglut: the whole LUT, periodic with 2^bw
+  uint32_t mode;             // LeafMode
+  uint32_t cmp;
+  int64_t lit;               // literal (i64, bool 0/1, or f64 order key for DK_F64)
+  bool f64;
+};
+enum LeafMode : uint32_t { LM_FALSE = 0, LM_TRUE = 1, LM_REGLUT = 2, LM_MEMLUT = 3, LM_PLAIN8 = 4, LM_BITS = 5 };
+
+__device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const DevScanArgs& a, const FlatStage& st,
+                                         const uint8_t* stage_base, const FlatLayout& L, uint32_t l) {
+  const DevLeaf& lf = plan.leaves[l];
+  const uint32_t c = lf.col;
+  const FlatStageCol& sc = st.col[c];
+  x.colw = reinterpret_cast<const uint32_t*>(stage_base + L.col_off[c]) + (sc.phase >> 5);
+  x.phase = sc.phase & 31u;
+  x.bw = sc.bw;
+  x.fkind = sc.fkind;
+  x.dict_max = sc.dict_n ? sc.dict_n - 1 : 0u;
+  x.cmp = lf.cmp;
+  x.f64 = plan.cols[c].kind == DK_F64;
+  x.lit = (x.f64 && lf.kind == LK_CMP) ? f64_order_key(uint64_t(lf.lit_i64)) : lf.lit_i64;
+  x.lut = a.luts + lf.lut_off + sc.lut_base;
+  x.lutreg = st.lutreg[l];
+  if (lf.kind == LK_IS_NULL) x.mode = LM_FALSE;            // flat pages hold no NULLs
+  else if (lf.kind == LK_IS_NOT_NULL) x.mode = LM_TRUE;
+  else if (sc.fkind == FK_INDEX) {
+    if ((st.regmask >> l) & 1u) x.mode = LM_REGLUT;
+    else if (sc.bw == 0) x.mode = x.lut[0] ? LM_TRUE : LM_FALSE;   // one-entry dictionary: no bits at all
+    else x.mode = LM_MEMLUT;
+  } else x.mode = sc.fkind == FK_PLAIN8 ? LM_PLAIN8 : LM_BITS;
+}
+
+__device__ __forceinline__ bool plain_cmp(uint64_t bits, const LeafCtx& x) {
+  const int64_t v = x.f64 ? f64_order_key(bits) : int64_t(bits);
+  return cmp_i64(v, x.lit, x.cmp);
+}
+
+// the answer for ONE row; x.mode is warp uniform, so the switch costs one predictable branch
+__device__ __forceinline__ bool leaf_row(const LeafCtx& x, uint32_t row) {
+  switch (x.mode) {
+    case LM_FALSE: return false;
+    case LM_TRUE: return true;
+    case LM_REGLUT: return (__funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.colw, x.phase + row * x.bw)) & 1u) != 0;
+    case LM_MEMLUT: {
+      uint32_t v = bits32_at(x.colw, x.phase + row * x.bw) & (x.bw >= 32 ? 0xffffffffu : ((1u << x.bw) - 1u));
+      v = v < x.dict_max ? v : x.dict_max;
+      return x.lut[v] != 0;
+    }
+    case LM_PLAIN8: return plain_cmp(reinterpret_cast<const uint64_t*>(x.colw)[row], x);
+    default: {
+      const uint32_t pb = x.phase + row;
+      return cmp_i64(int64_t((x.colw[pb >> 5] >> (pb & 31)) & 1u), x.lit, x.cmp);
+    }
+  }
+}
+
+// knock the rows of `m` (bit k = row row0 + k) out that fail the leaf: one trip per surviving row
+__device__ __forceinline__ uint32_t leaf_survivors(const LeafCtx& x, uint32_t row0, uint32_t m) {
+  uint32_t mm = m;
+  if (x.mode == LM_MEMLUT) {
+    const uint32_t mask = x.bw >= 32 ? 0xffffffffu : ((1u << x.bw) - 1u);
+    const uint32_t bit0 = x.phase + row0 * x.bw;
+    while (mm) {
+      const uint32_t k = __ffs(mm) - 1;
+      mm &= mm - 1;
+      uint32_t v = bits32_at(x.colw, bit0 + k * x.bw) & mask;
+      v = v < x.dict_max ? v : x.dict_max;
+      if (!x.lut[v]) m ^= 1u << k;
+    }
+    return m;
+  }
+  if (x.mode == LM_TRUE) return m;
+  if (x.mode == LM_FALSE) return 0u;
+  while (mm) {
+    const uint32_t k = __ffs(mm) - 1;
+    mm &= mm - 1;
+    if (!leaf_row(x, row0 + k)) m ^= 1u << k;
+  }
+  return m;
+}
+
+// 32 consecutive indices of BW bits starting at word w[0] -> 32 LUT answers, bit k = value k
+template <int BW, bool REGLUT>
+__device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w, uint32_t lutreg, const uint8_t* __restrict__ lut,
+                                                  uint32_t dict_max) {
+  uint32_t x[BW + 1];
+#pragma unroll
+  for (int i = 0; i < BW; i++) x[i] = w[i];
+  x[BW] = 0;
+  uint32_t m = 0;
+  constexpr uint32_t mask = BW >= 32 ? 0xffffffffu : ((1u << BW) - 1u);
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    const int bit = k * BW, wi = bit >> 5, sh = bit & 31;
+    uint32_t v = (sh + BW <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
+    uint32_t t;
+    if (REGLUT) t = __funnelshift_r(lutreg, lutreg, v);   // rotate: bit 0 = LUT[v mod 32], the LUT is periodic with 2^BW
+    else {
+      v &= mask;
+      v = v < dict_max ? v : dict_max;
+      t = lut[v];
+    }
+    m = __funnelshift_r(m, t, 1);                          // shift the answer in from the top: after 32 steps bit k = value k
+  }
+  return m;
+}
+
+// dense evaluation of one leaf over the thread's 32 rows [32*tc, 32*tc + 32) (blocked mapping)
+__device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, uint32_t R) {
+  switch (x.mode) {
+    case LM_FALSE: return 0u;
+    case LM_TRUE: return 0xffffffffu;
+    case LM_REGLUT:
+    case LM_MEMLUT: {
+      if (tc * 32 >= R) return 0u;   // a short slab (or a reduced slab size): nothing staged for this thread
+      const uint32_t* w = x.colw + tc * x.bw;
+      if (x.phase == 0) {
+        if (x.mode == LM_REGLUT) {
+          switch (x.bw) {
+            case 0: return (x.lutreg & 1u) ? 0xffffffffu : 0u;
+            case 1: return leaf_dense_bw<1, true>(w, x.lutreg, nullptr, 0);
+            case 2: return leaf_dense_bw<2, true>(w, x.lutreg, nullptr, 0);
+            case 3: return leaf_dense_bw<3, true>(w, x.lutreg, nullptr, 0);
+            case 4: return leaf_dense_bw<4, true>(w, x.lutreg, nullptr, 0);
+            default: return leaf_dense_bw<5, true>(w, x.lutreg, nullptr, 0);
+          }
+        }
+        switch (x.bw) {
+          case 1: return leaf_dense_bw<1, false>(w, 0, x.lut, x.dict_max);
+          case 2: return leaf_dense_bw<2, false>(w, 0, x.lut, x.dict_max);
+          case 3: return leaf_dense_bw<3, false>(w, 0, x.lut, x.dict_max);
+          case 4: return leaf_dense_bw<4, false>(w, 0, x.lut, x.dict_max);
+          case 5: return leaf_dense_bw<5, false>(w, 0, x.lut, x.dict_max);
+          case 6: return leaf_dense_bw<6, false>(w, 0, x.lut, x.dict_max);
+          case 7: return leaf_dense_bw<7, false>(w, 0, x.lut, x.dict_max);
+          case 8: return leaf_dense_bw<8, false>(w, 0, x.lut, x.dict_max);
+          case 9: return leaf_dense_bw<9, false>(w, 0, x.lut, x.dict_max);
+          case 10: return leaf_dense_bw<10, false>(w, 0, x.lut, x.dict_max);
+          case 11: return leaf_dense_bw<11, false>(w, 0, x.lut, x.dict_max);
+          case 12: return leaf_dense_bw<12, false>(w, 0, x.lut, x.dict_max);
+          default: break;
+        }
+      }
+      // wide indices, or a piece that starts inside a page off the 32-bit grid: value by value
+      const uint32_t mask = x.bw >= 32 ? 0xffffffffu : ((1u << x.bw) - 1u);
+      uint32_t m = 0, bit = x.phase + tc * 32 * x.bw;
+      if (x.mode == LM_REGLUT) {
+#pragma unroll 4
+        for (int k = 0; k < 32; k++, bit += x.bw) m = __funnelshift_r(m, __funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.colw, bit)), 1);
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < 32; k++, bit += x.bw) {
+          uint32_t v = bits32_at(x.colw, bit) & mask;
+          v = v < x.dict_max ? v : x.dict_max;
+          m = __funnelshift_r(m, uint32_t(x.lut[v]), 1);
+        }
+      }
+      return m;
+    }
+    case LM_BITS: {
+      if (tc * 32 >= R) return 0u;
+      const uint32_t word = bits32_at(x.colw, x.phase + tc * 32);
+      const uint32_t r1 = cmp_i64(1, x.lit, x.cmp) ? word : 0u, r0 = cmp_i64(0, x.lit, x.cmp) ? ~word : 0u;
+      return r1 | r0;
+    }
+    default: {
+      // LM_PLAIN8: transposed over the warp (lane L reads row base + 32 j + L: conflict free), lane j keeps word j
+      const uint32_t lane = threadIdx.x & 31, wbase = (tc & ~31u) * 32;
+      const uint64_t* v8 = reinterpret_cast<const uint64_t*>(x.colw);
+      uint32_t mine = 0;
+#pragma unroll 4
+      for (uint32_t j = 0; j < 32; j++) {
+        const uint32_t r = wbase + j * 32 + lane;
+        const bool t = r < R && plain_cmp(v8[r], x);
+        const uint32_t wj = __ballot_sync(0xffffffffu, t);
+        if (lane == j) mine = wj;
+      }
+      return mine;
+    }
+  }
+}
+
+// ---- k_flat_filter ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFilterThreads, 3)
+k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const DevScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  FlatCtl& ctl = *reinterpret_cast<FlatCtl*>(smem);
+  flat_ctl_init(ctl, L.nstages, kFilterConsumerWarps);
+  __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == kFilterConsumerWarps) {   // the last warp produces
+    flat_producer(plan, L, a, ctl, smem, plan.flat_slab_rows);
+    return;
+  }
+  const uint32_t tc = threadIdx.x;      // consumer thread: rows [32 tc, 32 tc + 32) of every slab
+  const uint32_t row0 = tc * 32;
+  uint32_t stage = 0, par = 0;
+  for (;;) {
+    mbar_wait_spin(&ctl.full[stage], par);
+    const FlatStage& st = ctl.st[stage];
+    if (st.item == 0xffffffffu) break;
+    const uint32_t R = st.R;
+    const uint8_t* base = smem + L.stage0 + stage * L.stage_bytes;
+    const uint32_t inr = row0 >= R ? 0u : (R - row0 >= 32 ? 0xffffffffu : ((1u << (R - row0)) - 1u));
+    uint32_t m = inr;
+    if (plan.npred) {
+      if (plan.conj) {
+        // conjunction: first leaf on every row, the others on the survivors only (or dense when many survive)
+        for (uint32_t l = 0; l < plan.nleaves; l++) {
+          const uint32_t mx = l ? __reduce_max_sync(0xffffffffu, __popc(m)) : 32u;
+          if (mx == 0) break;
+          LeafCtx x;
+          leaf_ctx(x, plan, a, st, base, L, l);
+          if (mx > 10) m &= leaf_dense(x, tc, R);
+          else m = leaf_survivors(x, row0, m);
+        }
+      } else {
+        // general boolean program (no NULLs on flat pages: two-valued logic)
+        uint32_t stk[kPredStack];
+        int sp = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < plan.npred; i++) {
+          const DevPredOp op = plan.pred[i];
+          if (op.kind == PK_LEAF) {
+            LeafCtx x;
+            leaf_ctx(x, plan, a, st, base, L, op.arg);
+            stk[sp++] = leaf_dense(x, tc, R);
+          } else if (op.kind == PK_CONST) stk[sp++] = op.arg == 1 ? 0xffffffffu : 0u;
+          else if (op.kind == PK_NOT) stk[sp - 1] = ~stk[sp - 1];
+          else { sp--; stk[sp - 1] = op.kind == PK_AND ? (stk[sp - 1] & stk[sp]) : (stk[sp - 1] | stk[sp]); }
+        }
+        m = stk[0] & inr;
+      }
+    }
+    if (plan.write_bitmap && row0 < R) a.bitmap[st.bitmap_word0 + (st.r0 >> 5) + tc] = m;
+    const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(m));
+    const uint32_t item = st.item;
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&ctl.empty[stage]);
+      if (cnt) atomicAdd(&a.item_counts[item], cnt);
+    }
+    if (++stage == L.nstages) { stage = 0; par ^= 1u; }
+  }
+}
+
+// ---- k_flat_agg ---------------------------------------------------------------------------------
+// A consumer thread owns up to kAggRowsMax rows of a slab, interleaved: row i of thread tc is
+// tc + i * kAggConsumers.  The slab is processed operator by operator ("vectorised interpreter"):
+// selection mask, then one pass per GROUP BY key into slot[], then one pass per aggregate.  Every
+// decision that does not depend on the row (page kind, bit width, aggregate function, pointers) is
+// made once per pass, outside the row loop.
+constexpr int kAggRowsMax = 8;
+
+struct ColCtx {              // one staged column of the current slab
+  const uint32_t* colw;
+  uint32_t phase, bw, mask, dict_max, fkind;
+};
+__device__ __forceinline__ void col_ctx(ColCtx& c, const FlatStage& st, const uint8_t* base, const FlatLayout& L, uint32_t col) {
+  const FlatStageCol& sc = st.col[col];
+  c.colw = reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
+  c.phase = sc.phase & 31u;
+  c.bw = sc.bw;
+  c.mask = sc.bw >= 32 ? 0xffffffffu : ((1u << sc.bw) - 1u);
+  c.dict_max = sc.dict_n ? sc.dict_n - 1 : 0u;
+  c.fkind = sc.fkind;
+}
+__device__ __forceinline__ uint32_t col_index(const ColCtx& c, uint32_t row) {
+  uint32_t v = bits32_at(c.colw, c.phase + row * c.bw) & c.mask;   // bw == 0: mask == 0
+  return v < c.dict_max ? v : c.dict_max;
+}
+
+// shared-memory cells are 8 bytes like the global ones; per-CTA partial counts and the low words of
+// partial sums are updated with native 32-bit atomics
+__device__ __forceinline__ void cell_add_u64(unsigned long long* cell, bool hot, unsigned long long v) {
+  if (hot) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(cell);
+    const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+    uint32_t carry = 0;
+    if (lo) carry = uint32_t(atomicAdd(&w[0], lo) + lo) < lo ? 1u : 0u;
+    if (hi + carry) atomicAdd(&w[1], hi + carry);
+  } else atomicAdd(cell, v);
+}
+__device__ __forceinline__ void cell_min_max(unsigned long long* cell, bool hot, bool is_min, long long k) {
+  if (hot) {   // 64-bit min / max in shared memory are CAS loops: skip when the row cannot improve the cell
+    const long long cur = *reinterpret_cast<volatile long long*>(cell);
+    if (is_min ? k >= cur : k <= cur) return;
+  }
+  if (is_min) atomicMin(reinterpret_cast<long long*>(cell), k);
+  else atomicMax(reinterpret_cast<long long*>(cell), k);
+}
+
+__global__ void __launch_bounds__(kAggThreads, 1)
+k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const DevScanArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  FlatCtl& ctl = *reinterpret_cast<FlatCtl*>(smem);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t H = plan.hot_slots, nslots = plan.nslots;
+  const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
+  unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem + L.acc);
+  // this CTA's copy of the global table (plan.replicas copies spread same-address traffic over L2; k_acc_reduce merges them)
+  unsigned long long* gacc = a.acc + size_t(blockIdx.x % plan.replicas) * cells * nslots;
+  flat_ctl_init(ctl, L.nstages, kAggConsumers / 32);
+  for (uint32_t i = threadIdx.x; i < cells * H; i += kAggThreads) {
+    const uint32_t arr = i / H;
+    unsigned long long init = 0;
+    if (arr >= 1 && arr < 1 + plan.n_acc) {
+      const uint8_t k = plan.acc_init[arr - 1];
+      init = k == 2 ? 0x7fffffffffffffffull : (k == 3 ? 0x8000000000000000ull : 0ull);
+    }
+    sacc[i] = init;
+  }
+  __syncthreads();
+  const uint32_t S = plan.flat_slab_rows;
+  // the shared-memory atomic unit retires ~1 lane-operation per 2 cycles; L2 reductions go down another path.
+  // Warps with (warp & 7) >= smem_share send even their hot slots to L2 (plan.smem_share of 8 warps use shared memory).
+  const uint32_t Hw = (warp & 7u) < plan.smem_share ? H : 0u;
+  if (warp == kAggConsumers / 32) {
+    flat_producer(plan, L, a, ctl, smem, S);
+  } else {
+    const uint32_t tc = threadIdx.x;
+    uint32_t stage = 0, par = 0;
+    for (;;) {
+      mbar_wait_spin(&ctl.full[stage], par);
+      const FlatStage& st = ctl.st[stage];
+      if (st.item == 0xffffffffu) break;
+      const uint32_t R = st.R;
+      const uint8_t* base = smem + L.stage0 + stage * L.stage_bytes;
+      // ---- rows of this thread, selection ----
+      uint32_t sel = 0;
+#pragma unroll
+      for (int i = 0; i < kAggRowsMax; i++) sel |= (tc + i * kAggConsumers < R ? 1u : 0u) << i;
+      if (plan.npred && sel) {
+        if (plan.conj) {
+          for (uint32_t l = 0; l < plan.nleaves; l++) {
+            LeafCtx x;
+            leaf_ctx(x, plan, a, st, base, L, l);
+            uint32_t m = 0;
+#pragma unroll
+            for (int i = 0; i < kAggRowsMax; i++)
+              if ((sel >> i) & 1u) m |= (leaf_row(x, tc + i * kAggConsumers) ? 1u : 0u) << i;
+            sel = m;
+          }
+        } else {
+          uint32_t stk[kPredStack];
+          int sp = 0;
+#pragma unroll 1
+          for (uint32_t i = 0; i < plan.npred; i++) {
+            const DevPredOp op = plan.pred[i];
+            if (op.kind == PK_LEAF) {
+              LeafCtx x;
+              leaf_ctx(x, plan, a, st, base, L, op.arg);
+              uint32_t m = 0;
+#pragma unroll
+              for (int j = 0; j < kAggRowsMax; j++)
+                if ((sel >> j) & 1u) m |= (leaf_row(x, tc + j * kAggConsumers) ? 1u : 0u) << j;
+              stk[sp++] = m;
+            } else if (op.kind == PK_CONST) stk[sp++] = op.arg == 1 ? 0xffu : 0u;
+            else if (op.kind == PK_NOT) stk[sp - 1] = ~stk[sp - 1];
+            else { sp--; stk[sp - 1] = op.kind == PK_AND ? (stk[sp - 1] & stk[sp]) : (stk[sp - 1] | stk[sp]); }
+          }
+          sel &= stk[0];
+        }
+      }
+      // ---- group slot of every selected row: one pass per key ----
+      uint32_t slot[kAggRowsMax];
+#pragma unroll
+      for (int i = 0; i < kAggRowsMax; i++) slot[i] = 0;
+      for (uint32_t k = 0; k < plan.nkeys; k++) {
+        const DevKey& key = plan.keys[k];
+        ColCtx c;
+        col_ctx(c, st, base, L, key.col);
+        const uint32_t stride = key.stride;
+        if (key.kind == KK_BOOL) {
+#pragma unroll
+          for (int i = 0; i < kAggRowsMax; i++)
+            if ((sel >> i) & 1u) { const uint32_t pb = c.phase + tc + i * kAggConsumers; slot[i] += ((c.colw[pb >> 5] >> (pb & 31)) & 1u) * stride; }
+        } else {
+          const uint32_t* __restrict__ gid = key.gid + st.col[key.col].lut_base;
+#pragma unroll
+          for (int i = 0; i < kAggRowsMax; i++)
+            if ((sel >> i) & 1u) slot[i] += gid[col_index(c, tc + i * kAggConsumers)] * stride;
+        }
+      }
+      // ---- COUNT(*) cell ----
+#pragma unroll
+      for (int i = 0; i < kAggRowsMax; i++)
+        if ((sel >> i) & 1u) {
+          if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[slot[i]]), 1u);   // a CTA sees < 2^32 rows: the low word never wraps
+          else atomicAdd(&gacc[slot[i]], 1ull);
+        }
+      // ---- one pass per aggregate ----
+      for (uint32_t g = 0; g < plan.naggs; g++) {
+        const DevAgg& ag = plan.aggs[g];
+        if (ag.fn == AG_COUNT_STAR) continue;
+        if (ag.update_nn) {
+          const uint32_t arr = 1 + plan.n_acc + ag.nn_slot;
+#pragma unroll
+          for (int i = 0; i < kAggRowsMax; i++)
+            if ((sel >> i) & 1u) {
+              if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[arr * H + slot[i]]), 1u);
+              else atomicAdd(&gacc[size_t(arr) * nslots + slot[i]], 1ull);
+            }
+        }
+        if (ag.fn == AG_COUNT) continue;
+        ColCtx c;
+        col_ctx(c, st, base, L, ag.col);
+        const bool plain = c.fkind == FK_PLAIN8;
+        const uint64_t* __restrict__ dict = reinterpret_cast<const uint64_t*>(a.flat + st.col[ag.col].dict8);
+        const uint64_t* v8 = reinterpret_cast<const uint64_t*>(c.colw);
+        unsigned long long* scell = sacc + size_t(1 + ag.acc_slot) * H;
+        unsigned long long* gcell = gacc + size_t(1 + ag.acc_slot) * nslots;
+        const bool f64 = ag.kind == DK_F64;
+        const uint32_t fn = ag.fn;
+        // f64 sums have no native shared-memory atomic (a CAS loop): plan.f64_global sends them to L2
+        const uint32_t Hc = (plan.f64_global && (fn == AG_AVG || (fn == AG_SUM && f64))) ? 0u : Hw;
+#pragma unroll
+        for (int i = 0; i < kAggRowsMax; i++) {
+          if (!((sel >> i) & 1u)) continue;
+          const uint32_t r = tc + i * kAggConsumers;
+          const uint64_t bits = plain ? v8[r] : dict[col_index(c, r)];
+          const bool hot = slot[i] < Hc;
+          unsigned long long* cell = hot ? scell + slot[i] : gcell + slot[i];
+          if (fn == AG_SUM && !f64) cell_add_u64(cell, hot, bits);                      // wrapping, like DataFusion's SUM(Int64)
+          else if (fn == AG_SUM) atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double((long long)bits));
+          else if (fn == AG_AVG) atomicAdd(reinterpret_cast<double*>(cell), f64 ? __longlong_as_double((long long)bits) : double((long long)bits));
+          else cell_min_max(cell, hot, fn == AG_MIN, f64 ? (long long)f64_order_key(bits) : (long long)bits);
+        }
+      }
+      const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(sel));
+      const uint32_t item = st.item;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ctl.empty[stage]);
+        if (cnt) atomicAdd(&a.item_counts[item], cnt);
+      }
+      if (++stage == L.nstages) { stage = 0; par ^= 1u; }
+    }
+  }
+  // ---- flush the hot table ----
+  __syncthreads();
+  for (uint32_t slot = threadIdx.x; slot < H; slot += kAggThreads) {
+    const unsigned long long rows = sacc[slot];
+    if (rows == 0) continue;
+    atomicAdd(&gacc[slot], rows);
+    for (uint32_t arr = 0; arr < plan.n_acc; arr++)
+      acc_merge(&gacc[(1 + arr) * nslots + slot], plan.acc_init[arr], sacc[(1 + arr) * H + slot]);
+    for (uint32_t k = 0; k < plan.n_nn; k++) {
+      const unsigned long long v = sacc[(1 + plan.n_acc + k) * H + slot];
+      if (v) atomicAdd(&gacc[(1 + plan.n_acc + k) * nslots + slot], v);
+    }
+  }
+}
+
+// merge the copies 1 .. replicas-1 of the accumulator table into copy 0
+__global__ void k_acc_reduce(unsigned long long* __restrict__ acc, uint32_t nslots, uint32_t cells, uint32_t replicas,
+                             const __grid_constant__ DevPlan plan) {
+  const uint64_t n = uint64_t(nslots) * cells;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t arr = uint32_t(i / nslots);
+    const uint8_t how = (arr >= 1 && arr < 1 + plan.n_acc) ? plan.acc_init[arr - 1] : 0;
+    unsigned long long v = acc[i];
+    for (uint32_t r = 1; r < replicas; r++) {
+      const unsigned long long o = acc[uint64_t(r) * n + i];
+      if (how == 0) v += o;
+      else if (how == 1) v = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)v) + __longlong_as_double((long long)o));
+      else if (how == 2) v = (long long)o < (long long)v ? o : v;
+      else v = (long long)o > (long long)v ? o : v;
+    }
+    acc[i] = v;
+  }
+}
+
+}  // namespace pqb

@@ -16,34 +16,37 @@ namespace pqb {
 
 struct DevPrepArgs {
   const uint8_t* arena;
-  const DevChunk* chunks;   // [rg_slot * ncols + col]
-  uint32_t n_chunks;        // rg_slots * ncols
+  const DevChunk* chunks;        // [table row group * ncols + slot]
+  uint32_t n_chunks;             // row groups * ncols
   uint32_t ncols;
-  uint64_t* ent_off;        // per dictionary entry: arena offset of its bytes (strings: after the length prefix)
+  const uint8_t* rg_live;        // per row group: 0 = pruned for this query (nullptr: all live)
+  const uint64_t* ent[kMaxCols]; // per slot: arena offset of every dictionary entry of the column (string leaves only)
   uint8_t* luts;
-  uint32_t* gid_luts;
   const uint8_t* lit_pool;
   unsigned long long* counters;  // [1] error flag
 };
 
-// needs[col] bit 0: entry offsets wanted for this column.
+// one column chunk as the table-level side-table builders see it
+struct EntChunk { uint64_t dict_off; uint32_t dict_len; uint32_t dict_n; uint32_t base; uint32_t present; };
+
+// Arena offset of every dictionary entry of ONE column (all row groups): query independent, built on
+// first use and kept with the table.
 // One WARP per column chunk.  A PLAIN byte-array dictionary is a chain (each length prefix says where
 // the next entry starts), so the walk is serial — but not at HBM/L2 latency: the warp stages the
 // dictionary through shared memory in 4 KiB tiles (coalesced 16-byte loads) and lane 0 follows the
-// chain there (tens of cycles per entry instead of ~600).  A 10 000-entry `host` dictionary per row
-// group used to make this kernel 3.8 ms of a group-by query.
+// chain there (tens of cycles per entry instead of ~600).
 constexpr int kEntTile = 4096;
-__global__ void __launch_bounds__(128) k_dict_entry_offsets(DevPrepArgs a, const uint8_t* __restrict__ col_kind,
-                                                            const uint8_t* __restrict__ col_needs) {
+__global__ void __launch_bounds__(128) k_dict_entry_offsets(const uint8_t* __restrict__ arena, const EntChunk* __restrict__ chunks,
+                                                            uint32_t n_chunks, uint32_t kind, uint64_t* __restrict__ ent_off,
+                                                            unsigned int* __restrict__ err) {
   __shared__ __align__(16) uint8_t tiles[4][kEntTile + 16];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ci = blockIdx.x * 4 + warp;
-  if (ci >= a.n_chunks) return;
-  const DevChunk ch = a.chunks[ci];
-  const uint32_t col = ci % a.ncols;
-  if (!ch.present || ch.dict_n == 0 || !col_needs[col]) return;
-  uint64_t* out = a.ent_off + ch.lut_base;
-  if (col_kind[col] != DK_STR) {
+  if (ci >= n_chunks) return;
+  const EntChunk ch = chunks[ci];
+  if (!ch.present || ch.dict_n == 0) return;
+  uint64_t* out = ent_off + ch.base;
+  if (kind != DK_STR) {
     for (uint32_t i = lane; i < ch.dict_n; i += 32) out[i] = ch.dict_off + uint64_t(i) * 8;
     return;
   }
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(128) k_dict_entry_offsets(DevPrepArgs a, const
     // stage [t0, t0 + kEntTile) with t0 = p rounded down to 16 (the arena is padded past every chunk)
     const uint64_t t0 = p & ~15ull;
     for (uint32_t o = lane * 16; o < (uint32_t)kEntTile; o += 32 * 16)
-      *reinterpret_cast<uint4*>(tile + o) = *reinterpret_cast<const uint4*>(a.arena + t0 + o);
+      *reinterpret_cast<uint4*>(tile + o) = *reinterpret_cast<const uint4*>(arena + t0 + o);
     __syncwarp();
     if (lane == 0) {
       while (i < ch.dict_n) {
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(128) k_dict_entry_offsets(DevPrepArgs a, const
         if (rel + 4 > (uint32_t)kEntTile) break;   // next length prefix is outside this tile
         const uint32_t len = uint32_t(tile[rel]) | (uint32_t(tile[rel + 1]) << 8) | (uint32_t(tile[rel + 2]) << 16) |
                              (uint32_t(tile[rel + 3]) << 24);
+        if (p + 4 + uint64_t(len) > end) { bad = true; break; }
         out[i++] = p + 4;
         p += 4 + uint64_t(len);
       }
@@ -74,19 +78,25 @@ __global__ void __launch_bounds__(128) k_dict_entry_offsets(DevPrepArgs a, const
     bad = __shfl_sync(0xffffffffu, bad ? 1 : 0, 0) != 0;
     __syncwarp();
   }
-  if (lane == 0 && (bad || p > end)) atomicExch(&a.counters[1], 3ull);
+  if (bad) {
+    // a corrupt dictionary: the remaining entries read as empty strings at the dictionary start (never
+    // out of bounds); the query that asked for this table fails with PQ_ERR_CORRUPT
+    for (uint32_t k = i + lane; k < ch.dict_n; k += 32) out[k] = ch.dict_off + 4;
+    if (lane == 0) atomicExch(err, 3u);
+  }
 }
 
 __device__ __forceinline__ uint32_t entry_len(const uint8_t* arena, uint64_t off, uint8_t kind) {
   return kind == DK_STR ? load_u32_unaligned(arena + off - 4) : 8u;
 }
 
-// grid.x = chunk, grid.y = blocks over entries
+// grid.x = chunk (row group x slot), grid.y = blocks over entries
 __global__ void k_leaf_luts(DevPrepArgs a, const __grid_constant__ DevPlan plan) {
   uint32_t ci = blockIdx.x;
   const DevChunk ch = a.chunks[ci];
   uint32_t col = ci % a.ncols;
   if (!ch.present || ch.dict_n == 0) return;
+  if (a.rg_live && !a.rg_live[ci / a.ncols]) return;
   const uint8_t kind = plan.cols[col].kind;
   for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
     for (uint32_t l = 0; l < plan.nleaves; l++) {
@@ -94,7 +104,7 @@ __global__ void k_leaf_luts(DevPrepArgs a, const __grid_constant__ DevPlan plan)
       if (lf.col != col || (lf.kind != LK_CMP && lf.kind != LK_LIKE)) continue;
       bool t;
       if (kind == DK_STR) {
-        uint64_t off = a.ent_off[ch.lut_base + e];
+        uint64_t off = a.ent[col][ch.lut_base + e];
         uint32_t len = load_u32_unaligned(a.arena + off - 4);
         const uint8_t* s = a.arena + off;
         const uint8_t* lit = a.lit_pool + lf.str_off;
@@ -116,16 +126,16 @@ __global__ void k_leaf_luts(DevPrepArgs a, const __grid_constant__ DevPlan plan)
   }
 }
 
-// ---- GROUP BY key interning ----
+// ---- GROUP BY key interning (per table column, query independent) ----
 struct DevKeyTable {
-  unsigned long long* slots;  // 0 empty, else (hash32 << 32) | (global entry index + 1)
+  unsigned long long* slots;  // 0 empty, else (hash32 << 32) | (column entry index + 1)
   uint32_t* gid_of_slot;
-  uint32_t* rep_of_gid;       // representative global entry index per group id
+  uint32_t* rep_of_gid;       // representative column entry index per group id
   uint32_t* counter;          // [0] distinct count, [1] overflow flag
   uint32_t cap_mask;
-  uint32_t col;
-  uint32_t gid_off;           // into gid_luts
   uint32_t kind;              // DevKind
+  const uint64_t* ent;        // entry offsets of the column
+  uint32_t* gid;              // out: group id per column entry
 };
 
 __device__ __forceinline__ bool entry_equal(const uint8_t* arena, uint64_t oa, uint64_t ob, uint32_t len, uint8_t kind) {
@@ -136,16 +146,15 @@ __device__ __forceinline__ bool entry_equal(const uint8_t* arena, uint64_t oa, u
   return true;
 }
 
-// mode 0: insert + number; mode 1: lookup -> gid_luts
-__global__ void k_key_intern(DevPrepArgs a, DevKeyTable t, int mode) {
-  uint32_t ci = blockIdx.x * a.ncols + t.col;  // grid.x = row-group slots
-  const DevChunk ch = a.chunks[ci];
+// mode 0: insert + number; mode 1: lookup -> gid[].  grid.x = column chunks in [c0, c0 + gridDim.x)
+__global__ void k_key_intern(const uint8_t* __restrict__ arena, const EntChunk* __restrict__ chunks, uint32_t c0, DevKeyTable t, int mode) {
+  const EntChunk ch = chunks[c0 + blockIdx.x];
   if (!ch.present || ch.dict_n == 0) return;
   for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
-    uint32_t ge = ch.lut_base + e;
-    uint64_t off = a.ent_off[ge];
-    uint32_t len = entry_len(a.arena, off, (uint8_t)t.kind);
-    uint64_t h = t.kind == DK_STR ? hash_bytes(a.arena + off, len) : mix64(load_u64_unaligned(a.arena + off));
+    uint32_t ge = ch.base + e;
+    uint64_t off = t.ent[ge];
+    uint32_t len = entry_len(arena, off, (uint8_t)t.kind);
+    uint64_t h = t.kind == DK_STR ? hash_bytes(arena + off, len) : mix64(load_u64_unaligned(arena + off));
     uint32_t h32 = uint32_t(h >> 32);
     unsigned long long word = ((unsigned long long)h32 << 32) | (unsigned long long)(ge + 1);
     uint32_t slot = uint32_t(h) & t.cap_mask;
@@ -165,8 +174,8 @@ __global__ void k_key_intern(DevPrepArgs a, DevKeyTable t, int mode) {
       if (cur == 0) { atomicExch(&t.counter[1], 2u); break; }  // lookup miss: cannot happen
       if (uint32_t(cur >> 32) == h32) {
         uint32_t other = uint32_t(cur & 0xffffffffull) - 1;
-        if (other == ge || entry_equal(a.arena, off, a.ent_off[other], len, (uint8_t)t.kind)) {
-          if (mode == 1) a.gid_luts[t.gid_off + ge] = t.gid_of_slot[slot];
+        if (other == ge || entry_equal(arena, off, t.ent[other], len, (uint8_t)t.kind)) {
+          if (mode == 1) t.gid[ge] = t.gid_of_slot[slot];
           break;
         }
       }
@@ -176,14 +185,31 @@ __global__ void k_key_intern(DevPrepArgs a, DevKeyTable t, int mode) {
   }
 }
 
-// multi-GPU: rewrite local group ids into the numbering every rank agreed on
-__global__ void k_gid_remap(DevPrepArgs a, uint32_t col, uint32_t gid_off, const uint32_t* __restrict__ remap, uint32_t card_local) {
-  uint32_t ci = blockIdx.x * a.ncols + col;
-  const DevChunk ch = a.chunks[ci];
-  if (!ch.present || ch.dict_n == 0) return;
-  for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
-    uint32_t g = a.gid_luts[gid_off + ch.lut_base + e];
-    if (g < card_local) a.gid_luts[gid_off + ch.lut_base + e] = remap[g];
+// renumber group ids: gid[e] = remap[gid[e]] for every entry of the column
+__global__ void k_gid_remap(const uint32_t* __restrict__ gid_in, uint32_t* __restrict__ gid_out, uint32_t n_entries,
+                            const uint32_t* __restrict__ remap, uint32_t card) {
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += gridDim.x * blockDim.x) {
+    const uint32_t g = gid_in[e];
+    gid_out[e] = g < card ? remap[g] : g;
+  }
+}
+
+// Occurrences of every group id over a sample of the key column's flat pages: the hot-first
+// numbering of group ids (the flat aggregate kernel keeps slots < hot_slots in shared memory).
+struct KeySamplePage { uint64_t off; uint32_t rows; uint32_t bw; uint32_t base; uint32_t dict_n; };
+__global__ void k_key_sample(const uint8_t* __restrict__ flat, const KeySamplePage* __restrict__ sp, uint32_t n_pages,
+                             const uint32_t* __restrict__ gid, uint32_t* __restrict__ counts) {
+  const KeySamplePage p = sp[blockIdx.x];
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(flat + p.off);
+  const uint32_t mask = p.bw >= 32 ? 0xffffffffu : ((1u << p.bw) - 1u);
+  for (uint32_t r = threadIdx.x; r < p.rows; r += blockDim.x) {
+    uint32_t v = 0;
+    if (p.bw) {
+      const uint32_t bit = r * p.bw, i = bit >> 5, sh = bit & 31;
+      v = __funnelshift_r(w[i], w[i + 1], sh) & mask;
+    }
+    if (v >= p.dict_n) continue;
+    atomicAdd(&counts[gid[p.base + v]], 1u);
   }
 }
 

@@ -1,6 +1,7 @@
-// Query planning and execution: the C-ABI PqQueryDesc becomes a DevPlan, work
-// items and side tables; then  k_dict_entry_offsets -> k_leaf_luts ->
-// k_key_intern x2 -> k_scan -> k_agg_compact  run on one stream.
+// Query planning and execution: the C-ABI PqQueryDesc becomes a DevPlan; work items, chunk tables
+// and the per-column side tables (string entry offsets, interned GROUP BY ids) come from the
+// table's caches; then  k_leaf_luts -> k_flat_filter | k_flat_agg (+ k_scan for the items the flat
+// store does not cover) -> k_item_prefix / k_compact_row_ids | k_agg_compact  run on one stream.
 //
 // Reference behaviour restated here (all /root/reference paths):
 //   * predicate pushed into the scan AND re-applied (Inexact pushdown,
@@ -21,6 +22,7 @@
 #include "engine.hpp"
 #include "prep_kernels.cuh"
 #include "scan_kernel.cuh"
+#include "flat_scan.cuh"
 
 namespace pqb {
 
@@ -203,9 +205,150 @@ void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void
   PQB_CUDA(cudaGetLastError());
 }
 
+void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat, uint8_t* ok,
+                       cudaStream_t stream) {
+  if (!n_jobs) return;
+  k_flat_store<<<(n_jobs + 3) / 4, 128, 0, stream>>>(arena, pages, static_cast<const FlatStoreJob*>(jobs), n_jobs, flat, ok);
+  PQB_CUDA(cudaGetLastError());
+}
+
+// ---- table-level side tables (called under Table::side_mu) -----------------------------------------
+static std::vector<EntChunk> column_chunks(const Table& t, int tcol) {
+  std::vector<EntChunk> v(t.row_groups.size());
+  for (size_t g = 0; g < t.row_groups.size(); g++) {
+    const TableChunk& tc = t.row_groups[g].chunks[tcol];
+    v[g] = EntChunk{tc.dict_off, tc.dict_len, tc.dict_n, t.sides[tcol].base_per_rg[g], tc.present ? 1u : 0u};
+  }
+  return v;
+}
+
+void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, cudaStream_t stream) {
+  std::vector<EntChunk> ch = column_chunks(t, tcol);
+  if (ch.empty()) return;
+  DevBuf<EntChunk> d_ch; d_ch.upload(ch, stream);
+  DevBuf<unsigned int> d_err; d_err.alloc(1, stream); d_err.zero();
+  k_dict_entry_offsets<<<uint32_t((ch.size() + 3) / 4), 128, 0, stream>>>(t.d_arena, d_ch.p, uint32_t(ch.size()), t.columns[tcol].kind, d_out, d_err.p);
+  PQB_CUDA(cudaGetLastError());
+  unsigned int err = 0;
+  PQB_CUDA(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, stream));
+  PQB_CUDA(cudaStreamSynchronize(stream));
+  if (err) throw Error(PQ_ERR_CORRUPT, "column '" + t.columns[tcol].name + "': a string dictionary page runs past its end");
+}
+
+// GROUP BY key interning of one table column: every dictionary entry of every row group gets the
+// dense id of its VALUE (DataFusion's GroupValues), ids numbered hot-first from a
+// sample of the column, and the distinct values are packed for the result batches.
+void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream) {
+  const uint8_t kkind = t.columns[tcol].kind;
+  std::vector<EntChunk> ch = column_chunks(t, tcol);
+  const uint32_t nrg = uint32_t(ch.size());
+  const uint32_t n = side.total_entries;
+  PQB_CUDA(cudaMallocAsync((void**)&side.d_gid, std::max<uint64_t>(n, 1) * 4, stream));
+  side.card = 0;
+  side.kd = KeyDict{};
+  side.kd.offs.assign(1, 0);
+  if (!n || !nrg) { PQB_CUDA(cudaStreamSynchronize(stream)); return; }
+  DevBuf<EntChunk> d_ch; d_ch.upload(ch, stream);
+  const uint32_t maxn = std::max<uint32_t>(side.max_dict_n, 1);
+  uint64_t cap = 64;
+  while (cap < 4ull * maxn) cap <<= 1;
+  DevBuf<uint32_t> rep;
+  uint32_t card = 0;
+  for (;;) {
+    DevBuf<unsigned long long> slots; slots.alloc(cap, stream); slots.zero();
+    DevBuf<uint32_t> gid_of_slot; gid_of_slot.alloc(cap, stream);
+    DevBuf<uint32_t> rep_try; rep_try.alloc(cap, stream);
+    DevBuf<uint32_t> counter; counter.alloc(2, stream); counter.zero();
+    DevKeyTable kt{slots.p, gid_of_slot.p, rep_try.p, counter.p, uint32_t(cap - 1), kkind, side.d_ent_off, side.d_gid};
+    const uint32_t gy = std::min<uint32_t>((maxn + 255) / 256, 64);
+    for (int mode = 0; mode < 2; mode++)
+      for (uint32_t c0 = 0; c0 < nrg; c0 += 32768) {
+        dim3 grid(std::min<uint32_t>(32768, nrg - c0), gy);
+        k_key_intern<<<grid, 256, 0, stream>>>(t.d_arena, d_ch.p, c0, kt, mode);
+      }
+    PQB_CUDA(cudaGetLastError());
+    uint32_t cnt[2];
+    PQB_CUDA(cudaMemcpyAsync(cnt, counter.p, 8, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    if (cnt[1] == 1 || cnt[0] * 2ull > cap) {  // table too full: grow and redo
+      if (cap > (1ull << 30)) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key table overflow");
+      cap <<= 2;
+      continue;
+    }
+    if (cnt[1]) throw Error(PQ_ERR_CUDA, "group key lookup failed");
+    card = cnt[0];
+    rep.alloc(std::max<uint32_t>(card, 1), stream);
+    PQB_CUDA(cudaMemcpyAsync(rep.p, rep_try.p, size_t(card) * 4, cudaMemcpyDeviceToDevice, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    break;
+  }
+  side.card = card;
+  // ---- hot-first numbering: occurrences of every id over a sample of the column's flat pages ----
+  if (card > 1 && t.d_flat_pages) {
+    std::vector<KeySamplePage> sp;
+    std::vector<uint32_t> cand;
+    for (uint32_t g = 0; g < nrg; g++) {
+      const TableChunk& tc = t.row_groups[g].chunks[tcol];
+      if (!tc.present) continue;
+      for (uint32_t k = 0; k < tc.pages.n_pages; k++)
+        if (t.flat_pages[tc.pages.first_page + k].fkind == FK_INDEX) { cand.push_back(g); cand.push_back(tc.pages.first_page + k); }
+    }
+    const size_t npg = cand.size() / 2, want = std::min<size_t>(npg, 512);
+    for (size_t i = 0; i < want; i++) {
+      const size_t j = i * npg / want;
+      const uint32_t g = cand[2 * j], pi = cand[2 * j + 1];
+      const FlatPageRec& fr = t.flat_pages[pi];
+      sp.push_back({fr.off, std::min<uint32_t>(fr.rows, 4096), fr.bw, side.base_per_rg[g], t.row_groups[g].chunks[tcol].dict_n});
+    }
+    if (!sp.empty()) {
+      DevBuf<KeySamplePage> d_sp; d_sp.upload(sp, stream);
+      DevBuf<uint32_t> d_cnt; d_cnt.alloc(card, stream); d_cnt.zero();
+      k_key_sample<<<uint32_t(sp.size()), 256, 0, stream>>>(t.d_flat, d_sp.p, uint32_t(sp.size()), side.d_gid, d_cnt.p);
+      PQB_CUDA(cudaGetLastError());
+      std::vector<uint32_t> cnt(card), hrep(card);
+      PQB_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.p, size_t(card) * 4, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaMemcpyAsync(hrep.data(), rep.p, size_t(card) * 4, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      std::vector<uint32_t> order(card);
+      for (uint32_t i = 0; i < card; i++) order[i] = i;
+      // hot first; ties by the representative entry (deterministic for a given table)
+      std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cnt[a] != cnt[b] ? cnt[a] > cnt[b] : hrep[a] < hrep[b]; });
+      std::vector<uint32_t> remap(card), nrep(card);
+      for (uint32_t i = 0; i < card; i++) { remap[order[i]] = i; nrep[i] = hrep[order[i]]; }
+      DevBuf<uint32_t> d_remap; d_remap.upload(remap, stream);
+      k_gid_remap<<<std::min<uint32_t>(1024, (n + 255) / 256), 256, 0, stream>>>(side.d_gid, side.d_gid, n, d_remap.p, card);
+      PQB_CUDA(cudaMemcpyAsync(rep.p, nrep.data(), size_t(card) * 4, cudaMemcpyHostToDevice, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+    }
+  }
+  // ---- pack the distinct values: lengths -> offsets (host) -> bytes ----
+  KeyDict& loc = side.kd;
+  loc.offs.assign(size_t(card) + 1, 0);
+  if (card) {
+    DevBuf<uint32_t> lens;
+    lens.alloc(card, stream);
+    k_key_lens<<<(card + 255) / 256, 256, 0, stream>>>(t.d_arena, side.d_ent_off, rep.p, card, kkind, lens.p);
+    std::vector<uint32_t> hl(card);
+    PQB_CUDA(cudaMemcpyAsync(hl.data(), lens.p, card * 4ull, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    uint64_t tot = 0;
+    for (uint32_t g = 0; g < card; g++) { loc.offs[g] = uint32_t(tot); tot += hl[g]; }
+    loc.offs[card] = uint32_t(tot);
+    if (tot > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "group key strings exceed 2 GiB");
+    DevBuf<uint32_t> doffs;
+    doffs.upload(loc.offs, stream);
+    DevBuf<uint8_t> dbytes;
+    dbytes.alloc(std::max<uint64_t>(tot, 1), stream);
+    k_key_bytes<<<card, 64, 0, stream>>>(t.d_arena, side.d_ent_off, rep.p, card, kkind, doffs.p, dbytes.p);
+    loc.bytes.resize(tot);
+    if (tot) PQB_CUDA(cudaMemcpyAsync(loc.bytes.data(), dbytes.p, tot, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+  }
+}
+
 void Query::run(const PqQueryDesc& d) {
   const auto t_begin = std::chrono::steady_clock::now();
-  const bool verbose = getenv("PQB_VERBOSE") != nullptr;
+  const char* vb = getenv("PQB_VERBOSE"); const bool verbose = vb && vb[0] && vb[0] != '0';
   auto mark = [&](const char* what) {   // PQB_VERBOSE: host timeline of this query
     if (verbose)
       fprintf(stderr, "[pqb] +%.3f ms %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what);
@@ -249,13 +392,11 @@ void Query::run(const PqQueryDesc& d) {
   // ---- column kinds vs the plan's expectation ----
   DevPlan plan{};
   plan.ncols = d.n_columns;
-  std::vector<bool> col_all_null(d.n_columns, false);
   for (uint32_t c = 0; c < d.n_columns; c++) {
     const TableColumn& tc = table->columns[tcol[c]];
     uint8_t kind = tc.kind;
     int want = d.columns[c].type;
     if (kind == 0xfe) {  // in no file: all NULL, take the plan's type
-      col_all_null[c] = true;
       kind = want == PQ_T_F64 ? DK_F64 : want == PQ_T_UTF8 ? DK_STR : want == PQ_T_BOOL ? DK_BOOL : DK_I64;
     } else {
       bool ok = (want == PQ_T_I64 && kind == DK_I64 && !tc.is_ts) || (want == PQ_T_TS_MS && kind == DK_I64 && tc.is_ts) ||
@@ -279,6 +420,7 @@ void Query::run(const PqQueryDesc& d) {
   std::vector<HostLeaf> leaves;
   std::vector<DevPredOp> prog;
   std::vector<uint8_t> lit_pool(16, 0);
+  bool has_null_const = false;
   {
     int depth = 0;
     for (uint32_t i = 0; i < d.n_pred; i++) {
@@ -351,6 +493,7 @@ void Query::run(const PqQueryDesc& d) {
           break;
         case PQ_OP_CONST:
           prog.push_back({PK_CONST, uint8_t(op.lit.type == PQ_T_NULL ? 2 : (op.lit.i64 ? 1 : 0))});
+          has_null_const |= op.lit.type == PQ_T_NULL;
           depth++;
           break;
         default: throw Error(PQ_ERR_INVALID_ARG, "unknown predicate op");
@@ -361,34 +504,39 @@ void Query::run(const PqQueryDesc& d) {
   }
 
   // ---- row-group pruning + constant folding of leaves that statistics decide everywhere ----
-  std::vector<uint32_t> rgs;  // surviving table row groups
+  const uint32_t nrg_table = uint32_t(table->row_groups.size());
+  std::vector<uint8_t> rg_live(std::max<uint32_t>(nrg_table, 1), 0);
+  uint32_t nrg = 0;   // surviving row groups
   std::vector<int> leaf_const(leaves.size(), -1);  // -1 unknown; else Tri over all survivors
-  metrics.row_groups_total = table->row_groups.size();
-  for (uint32_t g = 0; g < table->row_groups.size(); g++) {
-    const TableRowGroup& rg = table->row_groups[g];
-    std::vector<Tri> lt(leaves.size());
-    for (size_t l = 0; l < leaves.size(); l++) {
-      const TableChunk& ch = rg.chunks[tcol[leaves[l].qcol]];
-      lt[l] = leaf_from_stats(leaves[l], plan.cols[leaves[l].qcol].kind, ch, rg.num_rows);
-    }
-    Tri root = TRI_TRUE;
-    if (!prog.empty()) {
-      std::vector<Tri> st;
-      for (const DevPredOp& op : prog) {
-        if (op.kind == PK_LEAF) st.push_back(lt[op.arg]);
-        else if (op.kind == PK_CONST) st.push_back(op.arg == 1 ? TRI_TRUE : TRI_FALSE);
-        else if (op.kind == PK_NOT) st.back() = tri_not(st.back());
-        else { Tri b = st.back(); st.pop_back(); st.back() = op.kind == PK_AND ? tri_and(st.back(), b) : tri_or(st.back(), b); }
+  metrics.row_groups_total = nrg_table;
+  {
+    std::vector<Tri> lt(leaves.size()), st;
+    for (uint32_t g = 0; g < nrg_table; g++) {
+      const TableRowGroup& rg = table->row_groups[g];
+      for (size_t l = 0; l < leaves.size(); l++) {
+        const TableChunk& ch = rg.chunks[tcol[leaves[l].qcol]];
+        lt[l] = leaf_from_stats(leaves[l], plan.cols[leaves[l].qcol].kind, ch, rg.num_rows);
       }
-      root = st[0];
+      Tri root = TRI_TRUE;
+      if (!prog.empty()) {
+        st.clear();
+        for (const DevPredOp& op : prog) {
+          if (op.kind == PK_LEAF) st.push_back(lt[op.arg]);
+          else if (op.kind == PK_CONST) st.push_back(op.arg == 1 ? TRI_TRUE : TRI_FALSE);
+          else if (op.kind == PK_NOT) st.back() = tri_not(st.back());
+          else { Tri b = st.back(); st.pop_back(); st.back() = op.kind == PK_AND ? tri_and(st.back(), b) : tri_or(st.back(), b); }
+        }
+        root = st[0];
+      }
+      if (root == TRI_FALSE) { metrics.row_groups_pruned++; continue; }
+      for (size_t l = 0; l < leaves.size(); l++) {
+        if (leaf_const[l] == -1) leaf_const[l] = lt[l];
+        else if (leaf_const[l] != lt[l]) leaf_const[l] = TRI_MAYBE;
+      }
+      rg_live[g] = 1;
+      nrg++;
+      metrics.rows_scanned += rg.num_rows;
     }
-    if (root == TRI_FALSE) { metrics.row_groups_pruned++; continue; }
-    for (size_t l = 0; l < leaves.size(); l++) {
-      if (leaf_const[l] == -1) leaf_const[l] = lt[l];
-      else if (leaf_const[l] != lt[l]) leaf_const[l] = TRI_MAYBE;
-    }
-    rgs.push_back(g);
-    metrics.rows_scanned += rg.num_rows;
   }
   // a leaf that is TRUE in every surviving row group is replaced by a constant: the injected
   // p_timestamp range filter (src/query/mod.rs:774-833) usually disappears here and its column
@@ -421,18 +569,41 @@ void Query::run(const PqQueryDesc& d) {
     plan = p2;
     plan.ncols = ncols;
   }
-  // renumber live leaves
+  std::vector<int> shape_cols(ncols);
+  for (uint32_t s = 0; s < ncols; s++) shape_cols[s] = tcol[qcol_of_slot[s]];
+  std::shared_ptr<Shape> shape = table->shape_for(shape_cols, stream);
+  const std::vector<DevItem>& items = shape->items;
+
+  // is the predicate a pure conjunction of leaves (folded TRUE constants are neutral)?
+  bool conj = true;
+  for (const DevPredOp& op : prog)
+    if (!(op.kind == PK_LEAF || op.kind == PK_AND || (op.kind == PK_CONST && op.arg == 1))) conj = false;
+  // renumber live leaves; a conjunction evaluates its cheapest leaves first (narrow dictionary indices:
+  // the whole LUT in a register), the later ones only see the survivors
   std::vector<int> leaf_slot(leaves.size(), -1);
   uint32_t nleaves = 0;
-  for (size_t l = 0; l < leaves.size(); l++) {
-    if (!leaf_live[l]) continue;
-    leaf_slot[l] = int(nleaves);
-    plan.leaves[nleaves] = leaves[l].d;
-    plan.leaves[nleaves].col = uint8_t(slot_of[leaves[l].qcol]);
-    nleaves++;
+  {
+    std::vector<size_t> order;
+    for (size_t l = 0; l < leaves.size(); l++) if (leaf_live[l]) order.push_back(l);
+    if (conj)
+      std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        auto cost = [&](size_t l) {
+          const uint32_t s = uint32_t(slot_of[leaves[l].qcol]);
+          if (leaves[l].d.kind == LK_IS_NULL || leaves[l].d.kind == LK_IS_NOT_NULL) return 0u;
+          return shape->flat_plain8[s] ? 64u : std::max<uint32_t>(shape->flat_max_bw[s], shape->max_bw[s]);
+        };
+        return cost(a) < cost(b);
+      });
+    for (size_t l : order) {
+      leaf_slot[l] = int(nleaves);
+      plan.leaves[nleaves] = leaves[l].d;
+      plan.leaves[nleaves].col = uint8_t(slot_of[leaves[l].qcol]);
+      nleaves++;
+    }
   }
   plan.nleaves = nleaves;
-  // per column: the leaves a dictionary LUT answers (the kernel fuses up to two into the unpack)
+  plan.conj = conj ? 1 : 0;
+  // per column: the leaves a dictionary LUT answers (k_scan fuses up to two into the unpack)
   for (uint32_t c = 0; c < (uint32_t)kMaxCols; c++) { plan.col_nlut[c] = 0; plan.col_l0[c] = -1; plan.col_l1[c] = -1; }
   for (uint32_t l = 0; l < nleaves; l++) {
     const DevLeaf& lf = plan.leaves[l];
@@ -446,17 +617,11 @@ void Query::run(const PqQueryDesc& d) {
     plan.row_major = rm && rm[0] == '1';
   }
   {
-    // conjunction of 1-4 CMP/LIKE leaves (folded TRUE constants are neutral): specialised row pass
-    bool conj = nleaves >= 1 && nleaves <= 4;
-    uint32_t leaves_seen = 0;
-    for (const DevPredOp& op : prog) {
-      if (op.kind == PK_LEAF) { leaves_seen++; conj &= plan.leaves[leaf_slot[op.arg]].kind == LK_CMP || plan.leaves[leaf_slot[op.arg]].kind == LK_LIKE; }
-      else if (op.kind == PK_AND) {}
-      else if (op.kind == PK_CONST && op.arg == 1) {}
-      else conj = false;
-    }
+    // k_scan: conjunction of 1-4 CMP/LIKE leaves: specialised octet pass over slab-indexed pages
+    bool c4 = conj && nleaves >= 1 && nleaves <= 4;
+    for (uint32_t l = 0; l < nleaves; l++) c4 &= plan.leaves[l].kind == LK_CMP || plan.leaves[l].kind == LK_LIKE;
     const char* fa = getenv("PQB_FAST_AND");
-    plan.fast_and = conj && leaves_seen == nleaves && !(fa && fa[0] == '0');
+    plan.fast_and = c4 && !(fa && fa[0] == '0');
   }
   plan.npred = uint32_t(prog.size());
   for (size_t i = 0; i < prog.size(); i++) {
@@ -472,7 +637,6 @@ void Query::run(const PqQueryDesc& d) {
   plan.mode = agg_kernel ? SM_AGG : SM_FILTER;
   std::vector<int> agg_out_type(d.n_aggs, PQ_T_I64);
   if (has_aggs) {
-    std::map<int, int> nn_of_col;
     uint32_t n_acc = 0;
     plan.naggs = d.n_aggs;
     for (uint32_t a = 0; a < d.n_aggs; a++) {
@@ -486,9 +650,6 @@ void Query::run(const PqQueryDesc& d) {
       ag.kind = plan.cols[ag.col].kind;
       if (ag.fn != AG_COUNT && ag.kind != DK_I64 && ag.kind != DK_F64)
         throw Error(PQ_ERR_UNSUPPORTED, std::string("SUM/MIN/MAX/AVG over ") + type_name(out_type_of(qc)) + " is not on the GPU path");
-      auto it = nn_of_col.find(int(qc));
-      if (it == nn_of_col.end()) { it = nn_of_col.emplace(int(qc), int(nn_of_col.size())).first; ag.update_nn = 1; }
-      ag.nn_slot = uint8_t(it->second);
       if (ag.fn == AG_COUNT) { agg_out_type[a] = PQ_T_I64; continue; }
       ag.acc_slot = uint8_t(n_acc);
       uint8_t how = 0;
@@ -499,317 +660,112 @@ void Query::run(const PqQueryDesc& d) {
       agg_out_type[a] = ag.fn == AG_AVG ? PQ_T_F64 : out_type_of(qc);
     }
     plan.n_acc = n_acc;
-    plan.n_nn = uint32_t(nn_of_col.size());
   }
 
   mark("plan compiled");
-  // ---- per query chunk table, work items ----
-  const uint32_t nrg = uint32_t(rgs.size());
-  std::vector<DevChunk> chunks(size_t(nrg) * std::max<uint32_t>(ncols, 1));
-  std::vector<DevItem> items;
-  uint32_t n_fast_items = 0;   // items the table's slab index covers: no in-kernel run-header walk
-  const bool use_slab_index = ncols > 0 && table->d_slab_recs != nullptr;
-  std::vector<uint8_t> col_needs_ent(ncols, 0);  // entry offsets (string leaf / any key column)
-  std::vector<uint8_t> col_has_lut(ncols, 0);
+  // ---- what this query reads: bytes, NULL presence, encodings the kernels cannot take ----
+  std::vector<uint8_t> col_needs_ent(ncols, 0);  // entry offsets (string leaf)
   for (uint32_t l = 0; l < nleaves; l++) {
     const DevLeaf& lf = plan.leaves[l];
-    if (lf.kind == LK_CMP || lf.kind == LK_LIKE) {
-      col_has_lut[lf.col] = 1;
-      if (plan.cols[lf.col].kind == DK_STR) col_needs_ent[lf.col] = 1;
-    }
+    if ((lf.kind == LK_CMP || lf.kind == LK_LIKE) && plan.cols[lf.col].kind == DK_STR) col_needs_ent[lf.col] = 1;
   }
-  for (uint32_t k = 0; k < d.n_group_by; k++) {
-    uint32_t s = uint32_t(slot_of[d.group_by[k]]);
-    if (plan.cols[s].kind != DK_BOOL) { col_needs_ent[s] = 1; col_has_lut[s] = 1; }
-  }
-  uint64_t total_entries = 0;
-  uint32_t bitmap_words = 0;
   uint64_t algo_bytes = 0, scanned_bytes = 0;
   std::vector<uint8_t> col_has_nulls(std::max<uint32_t>(ncols, 1), 0);   // statistics cannot rule NULLs out
-  std::vector<std::vector<uint32_t>> bounds;   // reused across row groups
-  std::vector<uint32_t> common;
-  size_t bounds_n = 0;
-  items.reserve(size_t(nrg) * 16);
-  for (uint32_t gi = 0; gi < nrg; gi++) {
-    const TableRowGroup& rg = table->row_groups[rgs[gi]];
-    bounds_n = 0;
-    int first_present = -1;
+  for (uint32_t g = 0; g < nrg_table; g++) {
+    if (!rg_live[g]) continue;
+    const TableRowGroup& rg = table->row_groups[g];
     for (uint32_t s = 0; s < ncols; s++) {
-      const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
-      DevChunk& dc = chunks[size_t(gi) * ncols + s];
-      dc.present = tc.present ? 1 : 0;
+      const TableChunk& tc = rg.chunks[shape_cols[s]];
       if (!tc.present || tc.meta->stats.null_count != 0) col_has_nulls[s] = 1;   // absent column: every row NULL
       if (!tc.present) continue;
-      const uint8_t kind = plan.cols[s].kind;
-      dc.dict_off = tc.dict_off;
-      dc.dict_len = tc.dict_len;
-      dc.dict_n = tc.dict_n;
-      dc.first_page = tc.pages.first_page;
-      dc.n_pages = tc.pages.n_pages;
-      if (col_has_lut[s] || col_needs_ent[s]) {
-        dc.lut_base = uint32_t(total_entries);
-        total_entries += tc.dict_n;
-        if (total_entries > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "too many dictionary entries for one query");
-      }
-      if (tc.has_delta_pages && kind != DK_I64)
-        throw Error(PQ_ERR_UNSUPPORTED, "column '" + table->columns[tcol[qcol_of_slot[s]]].name + "': DELTA_BINARY_PACKED is decoded for INT64 columns only");
-      plan.cols[s].has_delta |= tc.has_delta_pages;
-      if (tc.has_plain_pages && kind == DK_STR)
-        throw Error(PQ_ERR_UNSUPPORTED, "column '" + table->columns[tcol[qcol_of_slot[s]]].name + "': PLAIN (dictionary-fallback) string pages are not decoded on the GPU yet");
-      if (kind == DK_STR && tc.dict_n == 0 && tc.has_dict_pages && false) {}
-      plan.cols[s].max_bw = std::max(plan.cols[s].max_bw, tc.max_bw);
-      plan.cols[s].has_dict |= tc.has_dict_pages;
-      plan.cols[s].has_plain |= tc.has_plain_pages;
       scanned_bytes += tc.bytes;
       algo_bytes += uint64_t(tc.meta->total_uncompressed_size);
-      if (first_present < 0) first_present = int(s);
-      if (!rg.pages_aligned) {
-        if (bounds.size() <= bounds_n) bounds.emplace_back();
-        std::vector<uint32_t>& b = bounds[bounds_n++];
-        b.clear();
-        for (uint32_t p = 0; p < tc.pages.n_pages; p++) b.push_back(table->pages[tc.pages.first_page + p].first_row);
-      }
     }
-    // boundaries common to every present column
-    common.clear();
-    const bool aligned = rg.pages_aligned && first_present >= 0;
-    if (aligned) {   // the pages ARE the items
-      const TableChunk& tc0 = rg.chunks[tcol[qcol_of_slot[first_present]]];
-      for (uint32_t p = 0; p < tc0.pages.n_pages; p++) common.push_back(table->pages[tc0.pages.first_page + p].first_row);
-    } else if (bounds_n == 0) common.push_back(0);
-    else {
-      common = bounds[0];
-      for (size_t i = 1; i < bounds_n; i++) {
-        std::vector<uint32_t> t;
-        std::set_intersection(common.begin(), common.end(), bounds[i].begin(), bounds[i].end(), std::back_inserter(t));
-        common.swap(t);
-      }
-    }
-    if (common.empty() || common[0] != 0) throw Error(PQ_ERR_CORRUPT, "row group pages do not start at row 0");
-    for (size_t i = 0; i < common.size(); i++) {
-      DevItem it{};
-      it.rg = gi;
-      it.row0 = common[i];
-      it.nrows = (i + 1 < common.size() ? common[i + 1] : rg.num_rows) - common[i];
-      it.global_row0 = rg.global_row0 + common[i];
-      it.bitmap_word0 = bitmap_words;
-      bitmap_words += (it.nrows + 31) / 32 + 1;
-      bool fast = use_slab_index;
-      for (uint32_t s = 0; s < ncols; s++) {
-        const TableChunk& tc = rg.chunks[tcol[qcol_of_slot[s]]];
-        if (!tc.present) continue;
-        // page whose first_row == row0
-        uint32_t lo = aligned ? uint32_t(i) : 0, hi = aligned ? uint32_t(i) + 1 : tc.pages.n_pages;
-        while (hi - lo > 1) {
-          uint32_t mid = (lo + hi) / 2;
-          if (table->pages[tc.pages.first_page + mid].first_row <= it.row0) lo = mid; else hi = mid;
-        }
-        it.page[s] = tc.pages.first_page + lo;
-        const DevPage& pg = table->pages[it.page[s]];
-        if (pg.first_row != it.row0 || pg.num_rows != it.nrows || !(pg.flags & 1u)) fast = false;
-      }
-      it.fast = fast && it.nrows ? 1u : 0u;
-      n_fast_items += it.fast;
-      items.push_back(it);
-    }
+  }
+  for (uint32_t s = 0; s < ncols; s++) {
+    const std::string& cname = table->columns[shape_cols[s]].name;
+    plan.cols[s].has_delta = shape->has_delta[s];
+    plan.cols[s].has_dict = shape->has_dict[s];
+    plan.cols[s].has_plain = shape->has_plain[s];
+    plan.cols[s].max_bw = shape->max_bw[s];
+    if (shape->has_delta[s] && plan.cols[s].kind != DK_I64)
+      throw Error(PQ_ERR_UNSUPPORTED, "column '" + cname + "': DELTA_BINARY_PACKED is decoded for INT64 columns only");
+    if (shape->has_plain[s] && plan.cols[s].kind == DK_STR)
+      throw Error(PQ_ERR_UNSUPPORTED, "column '" + cname + "': PLAIN (dictionary-fallback) string pages are not decoded on the GPU yet");
   }
   plan.n_items = uint32_t(items.size());
   metrics.bytes_scanned = scanned_bytes;
-  // an aggregated column whose footers promise null_count == 0 in every row group read: its
-  // non-null counter equals the group's row count, so the scan skips that atomic
+  const bool allreduce = (d.flags & PQ_QUERY_ALLREDUCE) != 0;
+  if (allreduce && !comm_active()) throw Error(PQ_ERR_INVALID_ARG, "PQ_QUERY_ALLREDUCE without pq_comm_init_rank");
+  const bool multi = agg_kernel && allreduce && comm_nranks() > 1;
+  // an aggregated column whose footers promise null_count == 0 in every row group read: its non-null
+  // counter equals the group's row count, so the scan skips that atomic.  Decided per rank from local
+  // footers: under PQ_QUERY_ALLREDUCE the cells are summed across ranks and every rank must make the
+  // same choice, so the shortcut is off there.
   std::vector<uint8_t> nn_is_rows(kMaxAggs, 0);
-  for (uint32_t a = 0; a < d.n_aggs; a++) {
-    DevAgg& ag = plan.aggs[a];
-    if (ag.fn == AG_COUNT_STAR || col_has_nulls[ag.col]) continue;
-    ag.update_nn = 0;
-    nn_is_rows[a] = 1;
+  {
+    std::map<int, int> nn_of_col;   // one non-null counter array per aggregated column that may hold NULLs
+    for (uint32_t a = 0; a < d.n_aggs; a++) {
+      DevAgg& ag = plan.aggs[a];
+      if (ag.fn == AG_COUNT_STAR) continue;
+      ag.update_nn = 0;
+      if (!col_has_nulls[ag.col] && !allreduce) { nn_is_rows[a] = 1; continue; }
+      auto it = nn_of_col.find(int(ag.col));
+      if (it == nn_of_col.end()) { it = nn_of_col.emplace(int(ag.col), int(nn_of_col.size())).first; ag.update_nn = 1; }
+      ag.nn_slot = uint8_t(it->second);
+    }
+    plan.n_nn = uint32_t(nn_of_col.size());
   }
-
-  // columns whose dictionary indices the row phase needs (GROUP BY keys, aggregate inputs)
+  // columns whose dictionary indices the row phase of k_scan needs (GROUP BY keys, aggregate inputs)
   for (uint32_t k = 0; k < d.n_group_by; k++) plan.cols[slot_of[d.group_by[k]]].need_idx = 1;
   for (uint32_t a = 0; a < d.n_aggs; a++)
     if (d.aggs[a].fn != PQ_AGG_COUNT_STAR) plan.cols[slot_of[d.aggs[a].col]].need_idx = 1;
 
-  // GROUP BY keys
-  plan.nkeys = d.n_group_by;
-  for (uint32_t k = 0; k < d.n_group_by; k++) {
-    DevKey& key = plan.keys[k];
-    key.col = uint8_t(slot_of[d.group_by[k]]);
-    uint8_t kind = plan.cols[key.col].kind;
-    key.kind = kind == DK_BOOL ? KK_BOOL : KK_DICT_LUT;
-    if (key.kind == KK_DICT_LUT && (plan.cols[key.col].has_plain || plan.cols[key.col].has_delta))
-      throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has PLAIN (dictionary-fallback) pages; only dictionary-encoded keys are on the GPU path");
-  }
-
-  mark("chunks + items built");
-  // ---- shared-memory layout ----
-  SmemLayout L{};
-  uint32_t off = align_up(uint32_t(sizeof(ScanCtl)), 128);
-  for (uint32_t s = 0; s < ncols; s++) {
-    // window = bytes of one slab at the widest index + one header per 8 values + alignment slop;
-    // anything denser makes the kernel shrink the slab (always correct, only slower)
-    L.defwin_cap[s] = plan.cols[s].max_def ? align_up(kSlabRows / 8 + kSlabRows / 16 + 64, 16) : 0;
-    L.valwin_cap[s] = plan.cols[s].has_dict ? valwin_cap_for_bw(plan.cols[s].max_bw) : 0;
-    // the slab index holds window-relative bit offsets: stage at least the window it was built for
-    if (n_fast_items && plan.cols[s].has_dict) L.valwin_cap[s] = std::max(L.valwin_cap[s], table->col_valwin_cap[tcol[qcol_of_slot[s]]]);
-    if (plan.cols[s].has_delta) L.valwin_cap[s] = std::max<uint32_t>(L.valwin_cap[s], align_up(kDeltaWindowBytes, 16));
-    for (int b = 0; b < 2; b++) { L.defwin[s][b] = off; off += align_up(L.defwin_cap[s] + 16, 128); }
-    for (int b = 0; b < 2; b++) { L.valwin[s][b] = off; off += align_up(L.valwin_cap[s] + 16, 128); }
-    L.valid[s] = off; off += align_up((kSlabWords + 2) * 4, 16);
-    L.rank[s] = off; off += kSlabWords * 4;
-    // staging: u32 dictionary indices, or i64 values of DELTA_BINARY_PACKED pages
-    L.idx[s] = (plan.cols[s].has_dict || plan.cols[s].has_delta) ? off : 0;
-    off += plan.cols[s].has_delta ? kSlabRows * 8 : (plan.cols[s].has_dict ? kSlabRows * 4 : 0);
-    L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
-    for (int b = 0; b < 2; b++) {   // bulk-copy destination for prebuilt directories: 16-byte aligned
-      off = align_up(off, 16);
-      L.valdir[s][b] = off;
-      off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
-    }
-  }
-  off = align_up(off, 16);
-  L.recs = off; off += uint32_t(kRecBatch * std::max<uint32_t>(ncols, 1) * sizeof(DevSlabRec));
-  L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
-  L.sel = off; off += kSlabWords * 4;
-  L.lutc = off; if (plan.fast_and) off += nleaves * kLutCacheBytes;
-  off = align_up(off, 128);
-  L.acc = off;
-  const uint32_t smem_fixed = off;
-
-  // ---- device side tables ----
-  Timer t_all, t_scan;
-  PQB_CUDA(cudaEventRecord(t_all.a, stream));
-  DevBuf<DevChunk> d_chunks; d_chunks.upload(chunks, stream);
-  DevBuf<DevItem> d_items; d_items.upload(items, stream);
-  DevBuf<uint8_t> d_lit; d_lit.upload(lit_pool, stream);
-  DevBuf<uint64_t> d_ent; d_ent.alloc(std::max<uint64_t>(total_entries, 1), stream);
-  for (uint32_t l = 0; l < nleaves; l++) plan.leaves[l].lut_off = uint32_t(uint64_t(l) * total_entries);
-  if (uint64_t(nleaves) * total_entries > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "leaf LUTs too large");
-  DevBuf<uint8_t> d_luts; d_luts.alloc(std::max<uint64_t>(uint64_t(nleaves) * total_entries, 16), stream);
-  DevBuf<uint32_t> d_gid; d_gid.alloc(std::max<uint64_t>(uint64_t(d.n_group_by) * total_entries, 4), stream);
-  DevBuf<unsigned long long> d_counters; d_counters.alloc(8, stream); d_counters.zero();
-  DevBuf<uint8_t> d_colkind, d_colneeds;
-  {
-    std::vector<uint8_t> ck(std::max<uint32_t>(ncols, 1)), cn(std::max<uint32_t>(ncols, 1));
-    for (uint32_t s = 0; s < ncols; s++) { ck[s] = plan.cols[s].kind; cn[s] = col_needs_ent[s]; }
-    d_colkind.upload(ck, stream);
-    d_colneeds.upload(cn, stream);
-  }
-  metrics.h2d_bytes += chunks.size() * sizeof(DevChunk) + items.size() * sizeof(DevItem) + lit_pool.size();
-
+  // ---- side tables: string entry offsets, per-leaf LUT regions ----
   DevPrepArgs pa{};
-  pa.arena = table->d_arena;
-  pa.chunks = d_chunks.p;
-  pa.n_chunks = nrg * ncols;
-  pa.ncols = ncols;
-  pa.ent_off = d_ent.p;
-  pa.luts = d_luts.p;
-  pa.gid_luts = d_gid.p;
-  pa.lit_pool = d_lit.p;
-  pa.counters = d_counters.p;
-
-  uint64_t launches = 0;
-  bool any_ent = false;
-  for (uint32_t s = 0; s < ncols; s++) any_ent |= col_needs_ent[s] != 0;
+  uint64_t lut_total = 0;
+  for (uint32_t s = 0; s < ncols; s++)
+    if (col_needs_ent[s]) { table->ensure_ent_off(shape_cols[s], stream); pa.ent[s] = table->sides[shape_cols[s]].d_ent_off; }
+  bool any_lut = false;
   uint32_t max_dict_n = 1;
-  for (const DevChunk& c : chunks) max_dict_n = std::max(max_dict_n, c.dict_n);
-  if (nrg && ncols && any_ent) {
-    k_dict_entry_offsets<<<(pa.n_chunks + 3) / 4, 128, 0, stream>>>(pa, d_colkind.p, d_colneeds.p);
-    launches++;
-  }
-  if (nrg && ncols && nleaves) {
-    bool any_lut = false;
-    for (uint32_t l = 0; l < nleaves; l++) any_lut |= plan.leaves[l].kind == LK_CMP || plan.leaves[l].kind == LK_LIKE;
-    if (any_lut) {
-      dim3 grid(pa.n_chunks, std::min<uint32_t>((max_dict_n + 255) / 256, 64));
-      k_leaf_luts<<<grid, 256, 0, stream>>>(pa, plan);
-      launches++;
-    }
+  for (uint32_t l = 0; l < nleaves; l++) {
+    DevLeaf& lf = plan.leaves[l];
+    lf.lut_off = 0;
+    if (lf.kind != LK_CMP && lf.kind != LK_LIKE) continue;
+    const ColSide& cs = table->sides[shape_cols[lf.col]];
+    if (lut_total + cs.total_entries > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "leaf LUTs too large");
+    lf.lut_off = uint32_t(lut_total);
+    lut_total += cs.total_entries;
+    any_lut |= cs.total_entries != 0;
+    max_dict_n = std::max(max_dict_n, cs.max_dict_n);
   }
 
-  // ---- GROUP BY key interning ----
-  // Local: every dictionary entry of a key column is interned into a device hash table and gets a
-  // dense id.  The distinct values are then packed to the host (they are also the output key
-  // dictionary).  Multi-GPU: the packed sets are all-gathered and numbered identically on every
-  // rank (rank order, first occurrence), local ids are remapped, so partial tables are slot-aligned
-  // for one ncclAllReduce.
-  struct KeyBufs { DevBuf<unsigned long long> slots; DevBuf<uint32_t> gid_of_slot, rep, counter; uint32_t cap = 0; };
-  struct KeyDict { std::vector<uint32_t> offs; std::vector<uint8_t> bytes; };
-  std::vector<std::unique_ptr<KeyBufs>> keybufs(d.n_group_by);
-  std::vector<uint32_t> key_card(d.n_group_by, 0);
-  std::vector<KeyDict> kd(d.n_group_by);
-  const bool multi = agg_kernel && (d.flags & PQ_QUERY_ALLREDUCE) && comm_active() && comm_nranks() > 1;
-  if ((d.flags & PQ_QUERY_ALLREDUCE) && !comm_active()) throw Error(PQ_ERR_INVALID_ARG, "PQ_QUERY_ALLREDUCE without pq_comm_init_rank");
+  // ---- GROUP BY keys: interned per table column (cached with the table) ----
+  struct QKey { const KeyDict* kd = nullptr; uint32_t card = 0; };
+  std::vector<QKey> qk(d.n_group_by);
+  std::vector<std::unique_ptr<DevBuf<uint32_t>>> gid_q(d.n_group_by);   // multi-GPU: per-query globally numbered ids
+  std::vector<KeyDict> glob_kd(d.n_group_by);
+  plan.nkeys = d.n_group_by;
+  uint64_t launches = 0;
   for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++) {
     DevKey& key = plan.keys[k];
-    key.gid_off = uint32_t(uint64_t(k) * total_entries);
-    if (key.kind == KK_BOOL) { key_card[k] = 2; continue; }
-    const uint8_t kkind = plan.cols[key.col].kind;
-    uint32_t card_l = 0;
-    uint32_t maxn = 1;
-    if (nrg) {
-      uint64_t sumn = 0;
-      for (uint32_t gi = 0; gi < nrg; gi++) { uint32_t n = chunks[size_t(gi) * ncols + key.col].dict_n; maxn = std::max(maxn, n); sumn += n; }
-      uint64_t cap = 64;
-      while (cap < 4ull * maxn) cap <<= 1;
-      for (;;) {
-        auto kb = std::make_unique<KeyBufs>();
-        kb->cap = uint32_t(cap);
-        kb->slots.alloc(cap, stream); kb->slots.zero();
-        kb->gid_of_slot.alloc(cap, stream);
-        kb->rep.alloc(cap, stream);
-        kb->counter.alloc(2, stream); kb->counter.zero();
-        DevKeyTable t{kb->slots.p, kb->gid_of_slot.p, kb->rep.p, kb->counter.p, uint32_t(cap - 1), key.col, key.gid_off, kkind};
-        dim3 grid(nrg, std::min<uint32_t>((maxn + 255) / 256, 64));
-        k_key_intern<<<grid, 256, 0, stream>>>(pa, t, 0);
-        k_key_intern<<<grid, 256, 0, stream>>>(pa, t, 1);
-        launches += 2;
-        uint32_t cnt[2];
-        PQB_CUDA(cudaMemcpyAsync(cnt, kb->counter.p, 8, cudaMemcpyDeviceToHost, stream));
-        PQB_CUDA(cudaStreamSynchronize(stream));
-        metrics.d2h_bytes += 8;
-        if (cnt[1] == 1 || cnt[0] * 2ull > cap) {  // table too full: grow and redo
-          if (cap > (1ull << 28) || cap > 4 * sumn + 64) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key table overflow");
-          cap <<= 2;
-          continue;
-        }
-        if (cnt[1]) throw Error(PQ_ERR_CUDA, "group key lookup failed");
-        card_l = cnt[0];
-        keybufs[k] = std::move(kb);
-        break;
-      }
-    }
-    // pack the local distinct values: lengths -> offsets (host) -> bytes
-    KeyDict loc;
-    loc.offs.assign(size_t(card_l) + 1, 0);
-    if (card_l) {
-      DevBuf<uint32_t> lens;
-      lens.alloc(card_l, stream);
-      k_key_lens<<<(card_l + 255) / 256, 256, 0, stream>>>(table->d_arena, d_ent.p, keybufs[k]->rep.p, card_l, kkind, lens.p);
-      std::vector<uint32_t> hl(card_l);
-      PQB_CUDA(cudaMemcpyAsync(hl.data(), lens.p, card_l * 4ull, cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaStreamSynchronize(stream));
-      uint64_t tot = 0;
-      for (uint32_t g = 0; g < card_l; g++) { loc.offs[g] = uint32_t(tot); tot += hl[g]; }
-      loc.offs[card_l] = uint32_t(tot);
-      if (tot > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "group key strings exceed 2 GiB");
-      DevBuf<uint32_t> doffs;
-      doffs.upload(loc.offs, stream);
-      DevBuf<uint8_t> dbytes;
-      dbytes.alloc(std::max<uint64_t>(tot, 1), stream);
-      k_key_bytes<<<card_l, 64, 0, stream>>>(table->d_arena, d_ent.p, keybufs[k]->rep.p, card_l, kkind, doffs.p, dbytes.p);
-      launches += 2;
-      loc.bytes.resize(tot);
-      if (tot) PQB_CUDA(cudaMemcpyAsync(loc.bytes.data(), dbytes.p, tot, cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaStreamSynchronize(stream));
-      metrics.d2h_bytes += card_l * 4ull + tot;
-    }
-    if (!multi) {
-      key_card[k] = card_l;
-      kd[k] = std::move(loc);
-      continue;
-    }
-    // ---- multi-GPU: agree on one numbering ----
+    key.col = uint8_t(slot_of[d.group_by[k]]);
+    const uint8_t kind = plan.cols[key.col].kind;
+    key.kind = kind == DK_BOOL ? KK_BOOL : KK_DICT_LUT;
+    if (key.kind == KK_BOOL) { qk[k].card = 2; continue; }
+    if (plan.cols[key.col].has_plain || plan.cols[key.col].has_delta)
+      throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has PLAIN (dictionary-fallback) pages; only dictionary-encoded keys are on the GPU path");
+    const int tc_i = shape_cols[key.col];
+    table->ensure_key(tc_i, stream);
+    const ColSide& cs = table->sides[tc_i];
+    key.gid = cs.d_gid;
+    qk[k].kd = &cs.kd;
+    qk[k].card = cs.card;
+    if (!multi) continue;
+    // ---- multi-GPU: agree on one numbering: all-gather the packed distinct values, number them by
+    // first occurrence in rank order (identical on every rank), remap the local ids ----
+    const KeyDict& loc = cs.kd;
+    const uint32_t card_l = cs.card;
     const int nr = comm_nranks(), me = comm_rank();
     std::vector<unsigned long long> sizes(size_t(nr) * 2);
     {
@@ -840,8 +796,8 @@ void Query::run(const PqQueryDesc& d) {
     }
     std::map<std::string, uint32_t> ids;  // identical content + identical insertion order on every rank
     std::vector<uint32_t> remap(std::max<uint32_t>(card_l, 1), 0);
-    KeyDict glob;
-    glob.offs.push_back(0);
+    KeyDict& glob = glob_kd[k];
+    glob.offs.assign(1, 0);
     for (int r = 0; r < nr; r++) {
       const uint8_t* base = recvbuf.data() + per_rank * r;
       const uint32_t* offs = reinterpret_cast<const uint32_t*>(base);
@@ -857,98 +813,269 @@ void Query::run(const PqQueryDesc& d) {
         if (r == me) remap[i] = it->second;
       }
     }
-    if (card_l) {
+    gid_q[k] = std::make_unique<DevBuf<uint32_t>>();
+    gid_q[k]->alloc(std::max<uint32_t>(cs.total_entries, 1), stream);
+    if (card_l && cs.total_entries) {
       DevBuf<uint32_t> dremap;
       dremap.upload(remap, stream);
-      dim3 grid(nrg, std::min<uint32_t>((maxn + 255) / 256, 64));
-      k_gid_remap<<<grid, 256, 0, stream>>>(pa, key.col, key.gid_off, dremap.p, card_l);
+      k_gid_remap<<<std::min<uint32_t>(1024, (cs.total_entries + 255) / 256), 256, 0, stream>>>(cs.d_gid, gid_q[k]->p, cs.total_entries, dremap.p, card_l);
       launches++;
       PQB_CUDA(cudaStreamSynchronize(stream));
     }
-    key_card[k] = uint32_t(ids.size());
-    kd[k] = std::move(glob);
+    key.gid = gid_q[k]->p;
+    qk[k].kd = &glob;
+    qk[k].card = uint32_t(ids.size());
   }
+  // mixed-radix group slot: the smallest key varies fastest, so that with hot-first ids of the largest key
+  // "slot < hot_slots" is "one of the hottest values of the largest key" (flat aggregate kernel)
   uint64_t nslots64 = 1;
-  for (uint32_t k = 0; k < d.n_group_by; k++) {
-    plan.keys[k].card = key_card[k];
-    plan.keys[k].stride = uint32_t(nslots64);
-    nslots64 *= uint64_t(key_card[k]) + 1;
-    if (nslots64 > (1ull << 26)) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key space too large for the dense accumulator table");
+  {
+    std::vector<uint32_t> korder(d.n_group_by);
+    for (uint32_t k = 0; k < d.n_group_by; k++) korder[k] = k;
+    std::stable_sort(korder.begin(), korder.end(), [&](uint32_t a, uint32_t b) { return qk[a].card < qk[b].card; });
+    for (uint32_t k : korder) {
+      plan.keys[k].card = qk[k].card;
+      plan.keys[k].stride = uint32_t(nslots64);
+      nslots64 *= uint64_t(qk[k].card) + 1;
+      if (nslots64 > (1ull << 26)) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key space too large for the dense accumulator table");
+    }
   }
   plan.nslots = uint32_t(nslots64);
   const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
 
+  // ---- which kernels run ----
+  const bool flat_ok = !has_null_const && !(getenv("PQB_FLAT_SCAN") && getenv("PQB_FLAT_SCAN")[0] == '0');
+  plan.no_flat = flat_ok ? 0 : 1;
+  const uint32_t n_flat = flat_ok ? shape->n_flat : 0;
+  const uint32_t n_general = flat_ok ? shape->n_general : uint32_t(items.size());
+  const uint32_t n_fast_items = shape->n_slab_fast;
+
+  mark("side tables ready");
+  // ---- shared-memory layout of k_scan (items the flat kernels do not take) ----
+  SmemLayout L{};
+  size_t smem_fixed = 0;
+  if (n_general) {
+    uint32_t off = align_up(uint32_t(sizeof(ScanCtl)), 128);
+    for (uint32_t s = 0; s < ncols; s++) {
+      // window = bytes of one slab at the widest index + one header per 8 values + alignment slop;
+      // anything denser makes the kernel shrink the slab (always correct, only slower)
+      L.defwin_cap[s] = plan.cols[s].max_def ? align_up(kSlabRows / 8 + kSlabRows / 16 + 64, 16) : 0;
+      L.valwin_cap[s] = plan.cols[s].has_dict ? valwin_cap_for_bw(plan.cols[s].max_bw) : 0;
+      // the slab index holds window-relative bit offsets: stage at least the window it was built for
+      if (n_fast_items && plan.cols[s].has_dict) L.valwin_cap[s] = std::max(L.valwin_cap[s], table->col_valwin_cap[shape_cols[s]]);
+      if (plan.cols[s].has_delta) L.valwin_cap[s] = std::max<uint32_t>(L.valwin_cap[s], align_up(kDeltaWindowBytes, 16));
+      for (int b = 0; b < 2; b++) { L.defwin[s][b] = off; off += align_up(L.defwin_cap[s] + 16, 128); }
+      for (int b = 0; b < 2; b++) { L.valwin[s][b] = off; off += align_up(L.valwin_cap[s] + 16, 128); }
+      L.valid[s] = off; off += align_up((kSlabWords + 2) * 4, 16);
+      L.rank[s] = off; off += kSlabWords * 4;
+      // staging: u32 dictionary indices, or i64 values of DELTA_BINARY_PACKED pages
+      L.idx[s] = (plan.cols[s].has_dict || plan.cols[s].has_delta) ? off : 0;
+      off += plan.cols[s].has_delta ? kSlabRows * 8 : (plan.cols[s].has_dict ? kSlabRows * 4 : 0);
+      L.defdir[s] = off; off += kMaxDirEntries * sizeof(DirEntry);
+      for (int b = 0; b < 2; b++) {   // bulk-copy destination for prebuilt directories: 16-byte aligned
+        off = align_up(off, 16);
+        L.valdir[s][b] = off;
+        off += std::max<uint32_t>(kMaxDirEntries * sizeof(DirEntry), plan.cols[s].has_delta ? kMaxDeltaEntries * sizeof(DeltaEntry) : 0);
+      }
+    }
+    off = align_up(off, 16);
+    L.recs = off; off += uint32_t(kRecBatch * std::max<uint32_t>(ncols, 1) * sizeof(DevSlabRec));
+    L.leafT = off; off += std::max<uint32_t>(nleaves, 1) * kLeafWords * 4;
+    L.sel = off; off += kSlabWords * 4;
+    L.lutc = off; if (plan.fast_and) off += nleaves * kLutCacheBytes;
+    off = align_up(off, 128);
+    L.acc = off;
+    smem_fixed = off;
+  }
+
+  // ---- shared-memory layout of the flat kernels ----
+  FlatLayout FL{};
+  if (n_flat) {
+    const uint32_t ctl_bytes = align_up(uint32_t(sizeof(FlatCtl)), 128);
+    auto stage_bytes_for = [&](uint32_t S) {
+      uint32_t off = 0;
+      for (uint32_t s = 0; s < ncols; s++) {
+        FL.col_off[s] = off;
+        const uint32_t cap = std::max<uint32_t>(shape->flat_plain8[s] ? S * 8 : 0, (S * shape->flat_max_bw[s] + 7) / 8);
+        off += align_up(cap + 48, 128);   // + the bit phase of a piece that starts inside a page, + over-read slack
+      }
+      return std::max<uint32_t>(off, 128);
+    };
+    const uint32_t avail = uint32_t(ctx.smem_optin()) - ctl_bytes - 256;
+    if (!agg_kernel) {
+      // three CTAs per SM: a CTA may use a third of the SM's shared memory
+      const uint32_t budget = (228u * 1024 - 3 * 1024) / 3 - ctl_bytes;
+      uint32_t S = kFilterSlabRows;
+      while (S > 1024 && 2 * stage_bytes_for(S) > budget) S >>= 1;
+      FL.stage_bytes = stage_bytes_for(S);
+      if (2 * FL.stage_bytes > avail) throw Error(PQ_ERR_UNSUPPORTED, "query needs more shared memory than one SM has");
+      FL.nstages = std::max<uint32_t>(2, std::min<uint32_t>(kFlatStagesMax, std::max<uint32_t>(budget, 2 * FL.stage_bytes) / FL.stage_bytes));
+      plan.flat_slab_rows = S;
+      plan.hot_slots = 0;
+    } else {
+      // one CTA per SM: the hot part of the accumulator table next to the stages
+      const uint64_t full = uint64_t(plan.nslots) * cells * 8;
+      uint32_t krows = 8;
+      while (krows > 1 && 2 * stage_bytes_for(kAggConsumers * krows) + std::min<uint64_t>(full, 96 * 1024) > avail) krows >>= 1;
+      const uint32_t S = kAggConsumers * krows;
+      FL.stage_bytes = stage_bytes_for(S);
+      if (2 * FL.stage_bytes + cells * 8 > avail) throw Error(PQ_ERR_UNSUPPORTED, "query needs more shared memory than one SM has");
+      FL.nstages = 2;
+      uint32_t left = avail - 2 * FL.stage_bytes;
+      if (full + FL.stage_bytes <= left && FL.nstages < (uint32_t)kFlatStagesMax) { FL.nstages = 3; left -= FL.stage_bytes; }
+      plan.hot_slots = uint32_t(std::min<uint64_t>(plan.nslots, left / (cells * 8)));
+      if (const char* hs = getenv("PQB_HOT_SLOTS")) plan.hot_slots = std::min<uint32_t>(plan.hot_slots, uint32_t(atoi(hs)));   // experiment switch
+      plan.flat_slab_rows = S;
+      plan.flat_krows = krows;
+    }
+    FL.stage0 = ctl_bytes;
+    FL.acc = align_up(FL.stage0 + FL.nstages * FL.stage_bytes, 128);
+    FL.total = FL.acc + (agg_kernel ? plan.hot_slots * cells * 8 : 0);
+    if (FL.total > ctx.smem_optin()) throw Error(PQ_ERR_UNSUPPORTED, "query needs more shared memory than one SM has");
+  }
+
+  // ---- per-query device state ----
+  Timer t_all, t_scan;
+  PQB_CUDA(cudaEventRecord(t_all.a, stream));
+  DevBuf<uint8_t> d_lit; d_lit.upload(lit_pool, stream);
+  DevBuf<uint8_t> d_live;
+  const bool pruned = nrg < nrg_table;
+  if (pruned) d_live.upload(rg_live, stream);
+  DevBuf<uint8_t> d_luts; d_luts.alloc(std::max<uint64_t>(lut_total, 16), stream);
+  DevBuf<unsigned long long> d_counters; d_counters.alloc(8, stream); d_counters.zero();
+  metrics.h2d_bytes += lit_pool.size() + (pruned ? rg_live.size() : 0);
+
+  pa.arena = table->d_arena;
+  pa.chunks = shape->d_chunks;
+  pa.n_chunks = nrg_table * ncols;
+  pa.ncols = ncols;
+  pa.rg_live = pruned ? d_live.p : nullptr;
+  pa.luts = d_luts.p;
+  pa.lit_pool = d_lit.p;
+  pa.counters = d_counters.p;
+  if (nrg && ncols && any_lut) {
+    dim3 grid(pa.n_chunks, std::min<uint32_t>((max_dict_n + 255) / 256, 64));
+    k_leaf_luts<<<grid, 256, 0, stream>>>(pa, plan);
+    launches++;
+  }
+
   // ---- accumulators ----
   DevBuf<unsigned long long> d_acc;
   size_t smem_total = smem_fixed;
+  plan.replicas = 1;
+  plan.smem_share = 8;
+  plan.f64_global = 0;
+  if (const char* e = getenv("PQB_SMEM_SHARE")) plan.smem_share = uint32_t(atoi(e));
+  if (const char* e = getenv("PQB_F64_GLOBAL")) plan.f64_global = uint32_t(atoi(e));
   if (agg_kernel) {
-    d_acc.alloc(size_t(plan.nslots) * cells, stream);
-    k_acc_init<<<std::min<uint32_t>(1024, (plan.nslots * cells + 255) / 256), 256, 0, stream>>>(d_acc.p, plan.nslots, plan.n_acc, cells, plan);
-    launches++;
+    // Cold group slots go to L2 with fire-and-forget reductions; L2 serialises same-address atomics, so the
+    // table is kept in a few copies (CTA b adds into copy b mod replicas) as long as all copies stay L2 resident.
+    if (n_flat && (plan.hot_slots < plan.nslots || plan.smem_share < 8 || plan.f64_global)) {
+      const uint64_t tbytes = uint64_t(plan.nslots) * cells * 8;
+      uint32_t r = uint32_t(std::min<uint64_t>(32, (48ull << 20) / std::max<uint64_t>(tbytes, 1)));
+      if (const char* e = getenv("PQB_REPLICAS")) r = uint32_t(atoi(e));
+      plan.replicas = std::max<uint32_t>(1, std::min<uint32_t>(r, uint32_t(ctx.sm_count())));
+    }
+    d_acc.alloc(size_t(plan.nslots) * cells * plan.replicas, stream);
+    for (uint32_t r = 0; r < plan.replicas; r++)
+      k_acc_init<<<std::min<uint32_t>(1024, (plan.nslots * cells + 255) / 256), 256, 0, stream>>>(d_acc.p + size_t(r) * plan.nslots * cells, plan.nslots, plan.n_acc, cells, plan);
+    launches += plan.replicas;
     size_t acc_bytes = size_t(plan.nslots) * cells * 8;
-    if (smem_fixed + acc_bytes + 1024 <= ctx.smem_optin()) { plan.smem_acc = 1; smem_total = smem_fixed + acc_bytes; }
+    if (n_general && smem_fixed + acc_bytes + 1024 <= ctx.smem_optin()) { plan.smem_acc = 1; smem_total = smem_fixed + acc_bytes; }
   }
   L.total = uint32_t(smem_total);
   if (smem_total > ctx.smem_optin()) throw Error(PQ_ERR_UNSUPPORTED, "query needs more shared memory than one SM has");
 
   // ---- selection bitmap / counts ----
   const bool want_rows = !has_aggs && !(d.flags & PQ_QUERY_COUNT_ONLY);
+  if (want_rows && d.n_projection && !(d.flags & PQ_QUERY_EMIT_ROW_IDS))
+    throw Error(PQ_ERR_UNSUPPORTED, "projection of column values is not on the GPU path yet: ask for PQ_QUERY_EMIT_ROW_IDS or PQ_QUERY_COUNT_ONLY");
   plan.write_bitmap = want_rows ? 1 : 0;
   DevBuf<uint32_t> d_bitmap, d_item_counts;
-  if (want_rows) { d_bitmap.alloc(std::max<uint32_t>(bitmap_words, 1), stream); d_bitmap.zero(); }
+  // k_scan ORs partial words into its bitmap regions: they start zeroed.  The flat filter kernel stores
+  // every word of its items, no memset needed.
+  if (want_rows) { d_bitmap.alloc(std::max<uint32_t>(shape->bitmap_words, 1), stream); if (n_general) d_bitmap.zero(); }
   d_item_counts.alloc(std::max<size_t>(items.size(), 1), stream);
+  d_item_counts.zero();
   if (want_rows) algo_bytes += metrics.rows_scanned / 8;
   metrics.algorithmic_bytes = algo_bytes;
 
   mark("prep kernels queued");
-  // ---- the fused scan ----
+  // ---- the fused scans ----
   DevScanArgs sa{};
   sa.arena = table->d_arena;
   sa.pages = table->d_pages;
-  sa.chunks = d_chunks.p;
-  sa.items = d_items.p;
+  sa.chunks = shape->d_chunks;
+  sa.items = shape->d_items;
   sa.luts = d_luts.p;
-  sa.gid_luts = d_gid.p;
   sa.lit_pool = d_lit.p;
+  sa.rg_live = pruned ? d_live.p : nullptr;
+  sa.flat = table->d_flat;
+  sa.fpages = table->d_flat_pages;
   sa.bitmap = d_bitmap.p;
   sa.item_counts = d_item_counts.p;
   sa.acc = d_acc.p;
   sa.counters = d_counters.p;
   sa.slab_recs = table->d_slab_recs;
   sa.slab_dirs = table->d_slab_dirs;
-  if (!items.empty()) {
+  PQB_CUDA(cudaEventRecord(t_scan.a, stream));
+  if (n_flat && nrg) {
+    uint32_t grid;
+    if (agg_kernel) {
+      PQB_CUDA(cudaFuncSetAttribute(k_flat_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
+      grid = std::min<uint32_t>(n_flat, uint32_t(ctx.sm_count()));
+      if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));
+      k_flat_agg<<<grid, kAggThreads, FL.total, stream>>>(plan, FL, sa);
+    } else {
+      PQB_CUDA(cudaFuncSetAttribute(k_flat_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
+      int occ = 1;
+      PQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_flat_filter, kFilterThreads, FL.total));
+      if (occ < 1) occ = 1;
+      grid = std::min<uint32_t>(n_flat, uint32_t(ctx.sm_count() * occ));
+      if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));
+      k_flat_filter<<<grid, kFilterThreads, FL.total, stream>>>(plan, FL, sa);
+    }
+    PQB_CUDA(cudaGetLastError());
+    launches++;
+    if (verbose)
+      fprintf(stderr, "[pqb] %s: %u CTAs, %u B smem/CTA, %u stages x %u B, slab %u rows, hot slots %u of %u, %u copies, %u flat items\n",
+              agg_kernel ? "k_flat_agg" : "k_flat_filter", grid, FL.total, FL.nstages, FL.stage_bytes, plan.flat_slab_rows, plan.hot_slots,
+              plan.nslots, plan.replicas, n_flat);
+  }
+  if (n_general && nrg) {
+    if (n_flat) { PQB_CUDA(cudaMemsetAsync(d_counters.p + 2, 0, 8, stream)); }   // the work-queue head
     PQB_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
     int occ = 1;
     PQB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, kScanThreads, smem_total));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * occ));
     if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));   // debugging aid: forces several items per CTA
-    if (getenv("PQB_VERBOSE"))
-      fprintf(stderr, "[pqb] k_scan: %u CTAs x %d threads, %zu B smem/CTA, %d CTAs/SM, %zu items\n", grid, kScanThreads,
-              size_t(smem_total), occ, items.size());
-    if (verbose) fprintf(stderr, "[pqb] %u of %zu items covered by the slab index\n", n_fast_items, items.size());
-    PQB_CUDA(cudaEventRecord(t_scan.a, stream));
+    if (verbose)
+      fprintf(stderr, "[pqb] k_scan: %u CTAs x %d threads, %zu B smem/CTA, %d CTAs/SM, %u of %zu items (%u slab-indexed)\n", grid,
+              kScanThreads, size_t(smem_total), occ, n_general, items.size(), n_fast_items);
     k_scan<<<grid, kScanThreads, smem_total, stream>>>(plan, L, sa);
-    PQB_CUDA(cudaEventRecord(t_scan.b, stream));
     PQB_CUDA(cudaGetLastError());
     launches++;
   }
+  if (agg_kernel && plan.replicas > 1) {
+    k_acc_reduce<<<std::min<uint32_t>(1024, (plan.nslots * cells + 255) / 256), 256, 0, stream>>>(d_acc.p, plan.nslots, cells, plan.replicas, plan);
+    launches++;
+  }
+  PQB_CUDA(cudaEventRecord(t_scan.b, stream));
 
   if (getenv("PQB_DEBUG_ITEMS")) {
     std::vector<uint32_t> ic(items.size());
     PQB_CUDA(cudaMemcpyAsync(ic.data(), d_item_counts.p, ic.size() * 4, cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     for (size_t i = 0; i < ic.size(); i++)
-      fprintf(stderr, "item %zu rg %u row0 %u nrows %u g0 %llu count %u\n", i, items[i].rg, items[i].row0, items[i].nrows,
-              (unsigned long long)items[i].global_row0, ic[i]);
+      fprintf(stderr, "item %zu rg %u row0 %u nrows %u g0 %llu flags %u count %u\n", i, items[i].rg, items[i].row0, items[i].nrows,
+              (unsigned long long)items[i].global_row0, items[i].fast, ic[i]);
   }
   mark("scan queued");
-  unsigned long long h_counters[4] = {0, 0, 0, 0};
-  PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
-  metrics.d2h_bytes += sizeof(h_counters);
 
   // ---- results ----
   const uint32_t batch_rows = d.batch_size ? d.batch_size : 20000;
+  unsigned long long h_counters[4] = {0, 0, 0, 0};
   if (agg_kernel) {
     DevBuf<uint32_t> d_out_count, d_out_slot;
     DevBuf<unsigned long long> d_out_cells;
@@ -956,20 +1083,28 @@ void Query::run(const PqQueryDesc& d) {
     d_out_count.alloc(1, stream); d_out_count.zero();
     d_out_slot.alloc(out_cap, stream);
     d_out_cells.alloc(size_t(out_cap) * cells, stream);
-    // multi-GPU: one all-reduce of the partial tables
-    if (d.flags & PQ_QUERY_ALLREDUCE) {
+    // multi-GPU: the partial tables meet in ONE grouped all-reduce: one NCCL launch,
+    // per array the reduction its aggregate needs
+    Timer t_ar;
+    if (allreduce) {
+      PQB_CUDA(cudaEventRecord(t_ar.a, stream));
+      comm_group_begin();
       comm_allreduce_u64(d_acc.p, plan.nslots, 0, stream);
       for (uint32_t a = 0; a < plan.n_acc; a++) {
         uint8_t how = plan.acc_init[a];
         comm_allreduce_u64(d_acc.p + size_t(1 + a) * plan.nslots, plan.nslots, how == 0 ? 0 : how == 1 ? 3 : how == 2 ? 1 : 2, stream);
       }
-      for (uint32_t k = 0; k < plan.n_nn; k++) comm_allreduce_u64(d_acc.p + size_t(1 + plan.n_acc + k) * plan.nslots, plan.nslots, 0, stream);
+      if (plan.n_nn) comm_allreduce_u64(d_acc.p + size_t(1 + plan.n_acc) * plan.nslots, size_t(plan.n_nn) * plan.nslots, 0, stream);
+      comm_group_end();
+      PQB_CUDA(cudaEventRecord(t_ar.b, stream));
     }
     k_agg_compact<<<std::min<uint32_t>(512, (plan.nslots + 255) / 256), 256, 0, stream>>>(d_acc.p, plan.nslots, cells, d_out_count.p, d_out_slot.p, d_out_cells.p, out_cap);
     launches++;
     uint32_t n_out = 0;
     PQB_CUDA(cudaMemcpyAsync(&n_out, d_out_count.p, 4, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
+    metrics.d2h_bytes += 4 + sizeof(h_counters);
     if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
     std::vector<uint32_t> out_slot(n_out);
     std::vector<unsigned long long> out_cells(size_t(n_out) * cells);
@@ -981,6 +1116,7 @@ void Query::run(const PqQueryDesc& d) {
     PQB_CUDA(cudaEventRecord(t_all.b, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     metrics.d2h_bytes += uint64_t(n_out) * (4 + 8ull * cells);
+    if (allreduce) { float ms = 0; cudaEventElapsedTime(&ms, t_ar.a, t_ar.b); metrics.allreduce_ms = ms; }
 
     // SQL: a global aggregate over zero rows still yields one row
     bool synth_empty = d.n_group_by == 0 && n_out == 0;
@@ -1005,22 +1141,24 @@ void Query::run(const PqQueryDesc& d) {
         oc.name = d.columns[qc].name;
         oc.type = out_type_of(qc);
         uint8_t kind = plan.cols[plan.keys[k].col].kind;
+        const uint32_t card = qk[k].card;
+        const KeyDict* kd = qk[k].kd;
         oc.validity.assign((nb + 7) / 8, 0);
         if (kind == DK_STR) oc.offsets.push_back(0);
         else if (kind == DK_BOOL) oc.values.assign((nb + 7) / 8, 0);
         else oc.values.resize(size_t(nb) * 8);
         for (uint32_t i = 0; i < nb; i++) {
           uint32_t slot = out_slot[order[r0 + i]];
-          uint32_t gid = (slot / plan.keys[k].stride) % (key_card[k] + 1);
-          bool valid = gid != key_card[k];
+          uint32_t gid = (slot / plan.keys[k].stride) % (card + 1);
+          bool valid = gid != card;
           if (valid) oc.validity[i >> 3] |= uint8_t(1u << (i & 7)); else oc.null_count++;
           if (kind == DK_STR) {
-            if (valid) oc.values.insert(oc.values.end(), kd[k].bytes.begin() + kd[k].offs[gid], kd[k].bytes.begin() + kd[k].offs[gid + 1]);
+            if (valid) oc.values.insert(oc.values.end(), kd->bytes.begin() + kd->offs[gid], kd->bytes.begin() + kd->offs[gid + 1]);
             oc.offsets.push_back(int32_t(oc.values.size()));
           } else if (kind == DK_BOOL) {
             if (valid && gid) oc.values[i >> 3] |= uint8_t(1u << (i & 7));
           } else if (valid) {
-            std::memcpy(oc.values.data() + size_t(i) * 8, kd[k].bytes.data() + kd[k].offs[gid], 8);
+            std::memcpy(oc.values.data() + size_t(i) * 8, kd->bytes.data() + kd->offs[gid], 8);
           }
         }
         if (!oc.null_count) oc.validity.clear();
@@ -1063,48 +1201,76 @@ void Query::run(const PqQueryDesc& d) {
     }
   } else {
     // ---- filter / COUNT(*) ----
-    // bitmap-driven stream compaction on the device: per-item prefix, then one CTA per item
+    // bitmap-driven stream compaction on the device: per-item prefix, then one CTA per item.  The
+    // selected-row total is needed on the host to size the result; a repeat of the same query shape
+    // sizes it from the previous answer and skips that round trip.
     DevBuf<unsigned long long> d_item_base, d_total, d_ids;
     std::shared_ptr<PinnedBlock> ids_block;   // selected row ordinals land in page-locked memory, batches alias it
-    unsigned long long n_ids = 0;
-    if (want_rows && !items.empty()) {
-      if (d.n_projection && !(d.flags & PQ_QUERY_EMIT_ROW_IDS))
-        throw Error(PQ_ERR_UNSUPPORTED, "projection of column values is not on the GPU path yet: ask for PQ_QUERY_EMIT_ROW_IDS or PQ_QUERY_COUNT_ONLY");
-      d_item_base.alloc(items.size(), stream);
-      d_total.alloc(1, stream);
+    unsigned long long n_ids = 0, total = 0;
+    d_total.alloc(1, stream);
+    d_item_base.alloc(std::max<size_t>(items.size(), 1), stream);
+    if (!items.empty()) {
       k_item_prefix<<<1, 1024, 0, stream>>>(d_item_counts.p, uint32_t(items.size()), d_item_base.p, d_total.p);
       launches++;
-      unsigned long long total = 0;
-      PQB_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaStreamSynchronize(stream));
-      mark("scan done, selected-row total on host");
-      metrics.d2h_bytes += 8;
-      unsigned long long keep = total;
-      if (d.limit >= 0 && (unsigned long long)d.limit < keep) keep = (unsigned long long)d.limit;
-      if (keep) {
-        d_ids.alloc(keep, stream);
-        uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * 8));
-        k_compact_row_ids<<<grid, 256, 0, stream>>>(d_bitmap.p, d_items.p, d_item_counts.p, d_item_base.p, uint32_t(items.size()), d_ids.p, keep);
-        launches++;
-        ids_block = std::make_shared<PinnedBlock>();
-        ids_block->p = ctx.pinned_acquire(keep * 8);
-        ids_block->bytes = keep * 8;
-        n_ids = keep;
-        PQB_CUDA(cudaMemcpyAsync(ids_block->p, d_ids.p, keep * 8, cudaMemcpyDeviceToHost, stream));
-        metrics.d2h_bytes += keep * 8;
+    } else {
+      PQB_CUDA(cudaMemsetAsync(d_total.p, 0, 8, stream));
+    }
+    PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
+    metrics.d2h_bytes += 8 + sizeof(h_counters);
+    const unsigned long long lim = d.limit >= 0 ? (unsigned long long)d.limit : ~0ull;
+    if (want_rows && !items.empty()) {
+      unsigned long long hint = shape->last_total.load();
+      bool done = false;
+      if (hint != ~0ull) {
+        // optimistic pass: room for the previous answer plus a margin
+        unsigned long long cap = std::min(lim, hint + hint / 8 + 1024);
+        if (cap) {
+          d_ids.alloc(cap, stream);
+          uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * 8));
+          k_compact_row_ids<<<grid, 256, 0, stream>>>(d_bitmap.p, shape->d_items, d_item_counts.p, d_item_base.p, uint32_t(items.size()), d_ids.p, cap);
+          launches++;
+          ids_block = std::make_shared<PinnedBlock>();
+          ids_block->p = ctx.pinned_acquire(cap * 8);
+          ids_block->bytes = cap * 8;
+          PQB_CUDA(cudaMemcpyAsync(ids_block->p, d_ids.p, cap * 8, cudaMemcpyDeviceToHost, stream));
+        }
+        PQB_CUDA(cudaStreamSynchronize(stream));
+        const unsigned long long keep = std::min(total, lim);
+        if (keep <= cap) { done = true; n_ids = keep; metrics.d2h_bytes += cap * 8; }
+        else ids_block.reset();
+      } else {
+        PQB_CUDA(cudaStreamSynchronize(stream));
       }
+      mark("scan done, selected-row total on host");
+      if (!done) {
+        const unsigned long long keep = std::min(total, lim);
+        if (keep) {
+          DevBuf<unsigned long long> d_ids2;
+          d_ids2.alloc(keep, stream);
+          uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * 8));
+          k_compact_row_ids<<<grid, 256, 0, stream>>>(d_bitmap.p, shape->d_items, d_item_counts.p, d_item_base.p, uint32_t(items.size()), d_ids2.p, keep);
+          launches++;
+          ids_block = std::make_shared<PinnedBlock>();
+          ids_block->p = ctx.pinned_acquire(keep * 8);
+          ids_block->bytes = keep * 8;
+          n_ids = keep;
+          PQB_CUDA(cudaMemcpyAsync(ids_block->p, d_ids2.p, keep * 8, cudaMemcpyDeviceToHost, stream));
+          PQB_CUDA(cudaStreamSynchronize(stream));
+          metrics.d2h_bytes += keep * 8;
+        }
+      }
+      shape->last_total.store(total);
     }
     PQB_CUDA(cudaEventRecord(t_all.b, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     mark("results on host");
     if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
-    metrics.rows_selected = h_counters[0];
+    metrics.rows_selected = total;
     if (has_aggs) {  // SELECT COUNT(*) [, COUNT(*)...] WHERE ...
-      unsigned long long total = h_counters[0];
-      if (d.flags & PQ_QUERY_ALLREDUCE) {
-        if (!comm_active()) throw Error(PQ_ERR_INVALID_ARG, "PQ_QUERY_ALLREDUCE without pq_comm_init_rank");
-        comm_allreduce_u64(d_counters.p, 1, 0, stream);
-        PQB_CUDA(cudaMemcpyAsync(&total, d_counters.p, 8, cudaMemcpyDeviceToHost, stream));
+      if (allreduce) {
+        comm_allreduce_u64(d_total.p, 1, 0, stream);
+        PQB_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
         PQB_CUDA(cudaStreamSynchronize(stream));
       }
       OutBatch ob;
@@ -1120,7 +1286,7 @@ void Query::run(const PqQueryDesc& d) {
       metrics.groups = 1;
       batches_.push_back(std::move(ob));
     } else if (want_rows) {
-      // selected row ordinals, ascending (projection of column VALUES is the next widening step)
+      // selected row ordinals, ascending
       for (size_t r0 = 0; r0 < n_ids || (r0 == 0 && n_ids == 0); r0 += batch_rows) {
         size_t nb = std::min<size_t>(batch_rows, n_ids - r0);
         OutBatch ob;
@@ -1138,7 +1304,7 @@ void Query::run(const PqQueryDesc& d) {
   float ms = 0;
   cudaEventElapsedTime(&ms, t_all.a, t_all.b);
   metrics.device_ms = ms;
-  if (!items.empty()) { cudaEventElapsedTime(&ms, t_scan.a, t_scan.b); metrics.scan_kernel_ms = ms; }
+  if (!items.empty() && nrg) { cudaEventElapsedTime(&ms, t_scan.a, t_scan.b); metrics.scan_kernel_ms = ms; }
   metrics.kernel_launches = launches;
 }
 

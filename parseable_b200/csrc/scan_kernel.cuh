@@ -536,7 +536,7 @@ __device__ __forceinline__ uint32_t fast_rows(const DevPlan& plan, ScanCtl& ctl,
           }
         } else {
           uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
-          gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
+          gid = mine ? key.gid[s.lut_base + v] : 0;
         }
       }
       slot += gid * key.stride;
@@ -594,7 +594,7 @@ __device__ __noinline__ void consume_word_agg(const DevPlan& plan, ScanCtl& ctl,
         }
       } else {
         uint32_t v = fast_idx(ctl, L, smem, key.col, buf, base_row, r, in);
-        gid = mine ? a.gid_luts[key.gid_off + s.lut_base + v] : 0;
+        gid = mine ? key.gid[s.lut_base + v] : 0;
       }
     }
     slot += gid * key.stride;
@@ -1226,7 +1226,7 @@ __device__ __forceinline__ void row_phase(const DevPlan& plan, ScanCtl& ctl, con
         uint32_t gid = key.card;  // NULL is its own group (field_stats.rs:1009-1037)
         if (rv.valid) {
           if (key.kind == KK_BOOL) gid = value_bool(s, a.arena, smem_at<uint32_t>(smem, L.idx[key.col]), rv.j);
-          else gid = a.gid_luts[key.gid_off + s.lut_base + smem_at<uint32_t>(smem, L.idx[key.col])[rv.j]];
+          else gid = key.gid[s.lut_base + smem_at<uint32_t>(smem, L.idx[key.col])[rv.j]];
         }
         slot += gid * key.stride;
       }
@@ -1296,8 +1296,10 @@ k_scan(const __grid_constant__ DevPlan plan, const __grid_constant__ SmemLayout 
     const uint32_t item_id = ctl.item;
     if (item_id >= plan.n_items) break;
     const DevItem& item = a.items[item_id];
+    if ((item.fast & kItemFlat) && !plan.no_flat) continue;   // the flat kernels own this item
+    if (a.rg_live && !a.rg_live[item.rg]) continue;            // row group pruned by statistics (counts stay 0)
 
-    if (item.fast) {
+    if (item.fast & kItemSlabIndexed) {
       // ---------------- fast item: the table's slab index holds every slab's run directory ----------------
       // no header walk, no cursor: per slab one wait for the staged bytes, the row phase, and the
       // bulk copies of the slab after next

@@ -215,6 +215,18 @@ Table::~Table() {
   if (d_slab_recs) cudaFreeAsync(d_slab_recs, cudaStreamPerThread);
   if (d_slab_dirs) cudaFreeAsync(d_slab_dirs, cudaStreamPerThread);
   if (d_slab_flat) cudaFreeAsync(d_slab_flat, cudaStreamPerThread);
+  if (d_flat) cudaFreeAsync(d_flat, cudaStreamPerThread);
+  if (d_flat_pages) cudaFreeAsync(d_flat_pages, cudaStreamPerThread);
+  for (ColSide& cs : sides) {
+    if (cs.d_ent_off) cudaFreeAsync(cs.d_ent_off, cudaStreamPerThread);
+    if (cs.d_gid) cudaFreeAsync(cs.d_gid, cudaStreamPerThread);
+    if (cs.d_key_hash) cudaFreeAsync(cs.d_key_hash, cudaStreamPerThread);
+  }
+}
+
+Shape::~Shape() {
+  if (d_chunks) cudaFreeAsync(d_chunks, cudaStreamPerThread);
+  if (d_items) cudaFreeAsync(d_items, cudaStreamPerThread);
 }
 
 int Table::find_column(const std::string& name) const {
@@ -714,7 +726,10 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     for (size_t c = 0; c < rg.chunks.size(); c++)
       if (rg.chunks[c].present && rg.chunks[c].has_dict_pages)
         col_valwin_cap[c] = std::max(col_valwin_cap[c], valwin_cap_for_bw(rg.chunks[c].max_bw));
-  const bool want_index = !(getenv("PQB_SLAB_INDEX") && getenv("PQB_SLAB_INDEX")[0] == '0');   // A/B switch
+  // The slab index was round 1's fast path (run directories per 2048 rows for k_scan).  Every page it
+  // can cover now has a flat-store copy and goes to the flat kernels, so it is only built on request
+  // (PQB_SLAB_INDEX=1: the A/B of DESIGN.md §4).
+  const bool want_index = getenv("PQB_SLAB_INDEX") && getenv("PQB_SLAB_INDEX")[0] == '1';
   if (want_index && !pages.empty() && !columns.empty()) {
     uint32_t* d_caps = nullptr;
     uint8_t* d_fast = nullptr;
@@ -759,7 +774,264 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
               h[1], fjobs.size(), (unsigned long long)slab_flat_bytes, h[2], h[3], h[4], (unsigned long long)total_slabs);
     }
   }
+  // ---- per-column entry numbering (query independent): entries of the column in earlier row groups ----
+  sides.assign(columns.size(), ColSide{});
+  for (size_t c = 0; c < columns.size(); c++) {
+    ColSide& cs = sides[c];
+    cs.base_per_rg.resize(row_groups.size());
+    uint64_t tot = 0;
+    for (size_t g = 0; g < row_groups.size(); g++) {
+      cs.base_per_rg[g] = uint32_t(tot);
+      const TableChunk& tc = row_groups[g].chunks[c];
+      if (tc.present) { tot += tc.dict_n; cs.max_dict_n = std::max(cs.max_dict_n, tc.dict_n); }
+      if (tot > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "too many dictionary entries in column '" + columns[c].name + "'");
+    }
+    cs.total_entries = uint32_t(tot);
+  }
+  build_flat_store(stream);
   PQB_CUDA(cudaStreamSynchronize(stream));
+}
+
+// ---- flat store ----------------------------------------------------------------------------------
+void Table::build_flat_store(cudaStream_t stream) {
+  flat_pages.assign(pages.size(), FlatPageRec{});
+  const char* sw = getenv("PQB_FLAT");
+  if ((sw && sw[0] == '0') || pages.empty()) return;   // A/B switch: everything through k_scan
+  struct J { uint64_t src, off; uint32_t page, kind, rows, zone; };
+  std::vector<J> js;
+  uint64_t zoff[2] = {0, 0};   // zone 0: hybrid outputs (zeroed, merged with atomicOr); zone 1: plain copies
+  auto take = [&](int zone, uint64_t bytes) { uint64_t o = zoff[zone]; zoff[zone] = (zoff[zone] + bytes + 16 + 15) & ~15ull; return o; };
+  for (TableRowGroup& rg : row_groups)
+    for (size_t c = 0; c < rg.chunks.size(); c++) {
+      TableChunk& tc = rg.chunks[c];
+      if (!tc.present) continue;
+      const uint8_t kind = columns[c].kind;
+      if (tc.dict_n && (kind == DK_I64 || kind == DK_F64)) {
+        if (uint64_t(tc.dict_n) * 8 > tc.dict_len)
+          throw Error(PQ_ERR_CORRUPT, "column '" + columns[c].name + "': dictionary page shorter than its entry count");
+        js.push_back({tc.dict_off, take(1, uint64_t(tc.dict_n) * 8), 0u, 4u /*FJ_DICT8*/, tc.dict_n, 1u});
+        tc.dict8_off = js.size() - 1;   // job index for now, resolved below
+      }
+      for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
+        const uint32_t pi = tc.pages.first_page + k;
+        const DevPage& pg = pages[pi];
+        FlatPageRec& fr = flat_pages[pi];
+        fr.rows = pg.num_rows;
+        if (pg.enc == DE_DICT || pg.enc == DE_RLE_BOOL) {
+          fr.fkind = pg.enc == DE_DICT ? FK_INDEX : FK_BITS;
+          fr.bw = pg.bit_width;
+          js.push_back({0, take(0, (uint64_t(pg.num_rows) * pg.bit_width + 7) / 8), pi, 1u /*FJ_HYBRID*/, pg.num_rows, 0u});
+        } else if (pg.enc == DE_PLAIN && (kind == DK_I64 || kind == DK_F64)) {
+          fr.fkind = FK_PLAIN8;
+          fr.bw = 64;
+          js.push_back({0, take(1, uint64_t(pg.num_rows) * 8), pi, 2u /*FJ_COPY8*/, pg.num_rows, 1u});
+        } else if (pg.enc == DE_PLAIN && kind == DK_BOOL) {
+          fr.fkind = FK_BITS;
+          fr.bw = 1;
+          js.push_back({0, take(1, (uint64_t(pg.num_rows) + 31) / 32 * 4), pi, 3u /*FJ_BITS*/, pg.num_rows, 1u});
+        } else {
+          continue;   // DELTA pages, PLAIN strings: k_scan
+        }
+      }
+    }
+  if (js.empty()) return;
+  const uint64_t zone1 = (zoff[0] + 255) & ~255ull;
+  flat_bytes = zone1 + zoff[1] + 256;
+  PQB_CUDA(cudaMallocAsync((void**)&d_flat, flat_bytes, stream));
+  PQB_CUDA(cudaMemsetAsync(d_flat, 0, zone1, stream));
+  PQB_CUDA(cudaMemsetAsync(d_flat + zone1 + zoff[1], 0, 256, stream));
+  struct DevJob { uint64_t src, dst; uint32_t page, kind, rows, pad; };   // == FlatStoreJob
+  std::vector<DevJob> dj(js.size());
+  for (size_t i = 0; i < js.size(); i++) {
+    const uint64_t dst = js[i].zone ? zone1 + js[i].off : js[i].off;
+    dj[i] = {js[i].src, dst, js[i].page, js[i].kind, js[i].rows, 0u};
+    if (js[i].kind != 4u) flat_pages[js[i].page].off = dst;
+  }
+  for (TableRowGroup& rg : row_groups)
+    for (TableChunk& tc : rg.chunks)
+      if (tc.present && tc.dict8_off != ~0ull) tc.dict8_off = dj[tc.dict8_off].dst;
+  void* d_jobs = nullptr;
+  uint8_t* d_ok = nullptr;
+  PQB_CUDA(cudaMallocAsync(&d_jobs, dj.size() * sizeof(DevJob), stream));
+  PQB_CUDA(cudaMallocAsync((void**)&d_ok, dj.size(), stream));
+  PQB_CUDA(cudaMemcpyAsync(d_jobs, dj.data(), dj.size() * sizeof(DevJob), cudaMemcpyHostToDevice, stream));
+  launch_flat_store(d_arena, d_pages, d_jobs, uint32_t(dj.size()), d_flat, d_ok, stream);
+  std::vector<uint8_t> ok(dj.size());
+  PQB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, ok.size(), cudaMemcpyDeviceToHost, stream));
+  PQB_CUDA(cudaStreamSynchronize(stream));
+  PQB_CUDA(cudaFreeAsync(d_jobs, stream));
+  PQB_CUDA(cudaFreeAsync(d_ok, stream));
+  size_t n_ok = 0;
+  for (size_t i = 0; i < dj.size(); i++) {
+    if (dj[i].kind == 4u) continue;
+    if (ok[i]) n_ok++;
+    else flat_pages[dj[i].page].fkind = FK_NONE;   // NULLs in the page (or a stream the walker refused): k_scan reads the original
+  }
+  flat_page_count = n_ok;
+  PQB_CUDA(cudaMallocAsync((void**)&d_flat_pages, flat_pages.size() * sizeof(FlatPageRec), stream));
+  PQB_CUDA(cudaMemcpyAsync(d_flat_pages, flat_pages.data(), flat_pages.size() * sizeof(FlatPageRec), cudaMemcpyHostToDevice, stream));
+  if (getenv("PQB_VERBOSE"))
+    fprintf(stderr, "[pqb] flat store: %zu of %zu pages, %llu bytes (arena %llu)\n", n_ok, pages.size(),
+            (unsigned long long)flat_bytes, (unsigned long long)arena_bytes);
+}
+
+// ---- per column-set shape: chunk table + work items (built once, reused by every query) ----------
+std::shared_ptr<Shape> Table::shape_for(const std::vector<int>& tcols, cudaStream_t stream) const {
+  std::lock_guard<std::mutex> lk(side_mu);
+  auto it = shapes.find(tcols);
+  if (it != shapes.end()) return it->second;
+  auto sh = std::make_shared<Shape>();
+  sh->tcols = tcols;
+  const uint32_t ncols = uint32_t(tcols.size());
+  const uint32_t nrg = uint32_t(row_groups.size());
+  sh->max_bw.assign(ncols, 0); sh->flat_max_bw.assign(ncols, 0);
+  sh->has_dict.assign(ncols, 0); sh->has_plain.assign(ncols, 0); sh->has_delta.assign(ncols, 0); sh->flat_plain8.assign(ncols, 0);
+  std::vector<DevChunk> chunks(size_t(nrg) * std::max<uint32_t>(ncols, 1));
+  std::vector<std::vector<uint32_t>> bounds;
+  std::vector<uint32_t> common;
+  const bool use_slab_index = ncols > 0 && d_slab_recs != nullptr;
+  const bool use_flat = d_flat_pages != nullptr || ncols == 0;
+  sh->items.reserve(size_t(nrg) * 16);
+  for (uint32_t g = 0; g < nrg; g++) {
+    const TableRowGroup& rg = row_groups[g];
+    size_t bounds_n = 0;
+    int first_present = -1;
+    for (uint32_t s = 0; s < ncols; s++) {
+      const TableChunk& tc = rg.chunks[tcols[s]];
+      DevChunk& dc = chunks[size_t(g) * ncols + s];
+      dc.present = tc.present ? 1 : 0;
+      dc.dict8_off = ~0ull;
+      if (!tc.present) continue;
+      dc.dict_off = tc.dict_off;
+      dc.dict_len = tc.dict_len;
+      dc.dict_n = tc.dict_n;
+      dc.first_page = tc.pages.first_page;
+      dc.n_pages = tc.pages.n_pages;
+      dc.lut_base = sides[tcols[s]].base_per_rg[g];
+      dc.dict8_off = tc.dict8_off;
+      sh->max_bw[s] = std::max(sh->max_bw[s], tc.max_bw);
+      sh->has_dict[s] |= tc.has_dict_pages;
+      sh->has_plain[s] |= tc.has_plain_pages;
+      sh->has_delta[s] |= tc.has_delta_pages;
+      if (first_present < 0) first_present = int(s);
+      if (!rg.pages_aligned) {
+        if (bounds.size() <= bounds_n) bounds.emplace_back();
+        std::vector<uint32_t>& b = bounds[bounds_n++];
+        b.clear();
+        for (uint32_t p = 0; p < tc.pages.n_pages; p++) b.push_back(pages[tc.pages.first_page + p].first_row);
+      }
+    }
+    common.clear();
+    const bool aligned = rg.pages_aligned && first_present >= 0;
+    if (aligned) {   // the pages ARE the items
+      const TableChunk& tc0 = rg.chunks[tcols[first_present]];
+      for (uint32_t p = 0; p < tc0.pages.n_pages; p++) common.push_back(pages[tc0.pages.first_page + p].first_row);
+    } else if (bounds_n == 0) common.push_back(0);
+    else {
+      common = bounds[0];
+      for (size_t i = 1; i < bounds_n; i++) {
+        std::vector<uint32_t> t;
+        std::set_intersection(common.begin(), common.end(), bounds[i].begin(), bounds[i].end(), std::back_inserter(t));
+        common.swap(t);
+      }
+    }
+    if (common.empty() || common[0] != 0) throw Error(PQ_ERR_CORRUPT, "row group pages do not start at row 0");
+    // page of column slot s that holds row r of this row group
+    auto page_of = [&](uint32_t s, uint32_t r, uint32_t hint) {
+      const TableChunk& tc = rg.chunks[tcols[s]];
+      uint32_t lo = aligned ? hint : 0, hi = aligned ? hint + 1 : tc.pages.n_pages;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) / 2;
+        if (pages[tc.pages.first_page + mid].first_row <= r) lo = mid; else hi = mid;
+      }
+      return tc.pages.first_page + lo;
+    };
+    auto push_item = [&](DevItem& it, bool flat, bool fast) {
+      it.bitmap_word0 = sh->bitmap_words;
+      sh->bitmap_words += (it.nrows + 31) / 32 + 1;
+      if (flat)
+        for (uint32_t s = 0; s < ncols; s++) {
+          const FlatPageRec& fr = flat_pages[it.page[s]];
+          if (fr.fkind == FK_PLAIN8) sh->flat_plain8[s] = 1;
+          else sh->flat_max_bw[s] = std::max<uint32_t>(sh->flat_max_bw[s], fr.bw);
+        }
+      it.fast = (flat ? kItemFlat : (fast ? kItemSlabIndexed : 0u));
+      sh->n_flat += flat ? 1 : 0;
+      sh->n_slab_fast += (!flat && fast) ? 1 : 0;
+      sh->n_general += flat ? 0 : 1;
+      sh->items.push_back(it);
+    };
+    std::vector<uint32_t> cuts;
+    for (size_t i = 0; i < common.size(); i++) {
+      DevItem it{};
+      it.rg = g;
+      it.row0 = common[i];
+      it.nrows = (i + 1 < common.size() ? common[i + 1] : rg.num_rows) - common[i];
+      it.global_row0 = rg.global_row0 + common[i];
+      const uint32_t row_end = it.row0 + it.nrows;
+      bool fast = use_slab_index, flat = use_flat && it.nrows != 0;
+      cuts.clear();
+      for (uint32_t s = 0; s < ncols; s++) {
+        const TableChunk& tc = rg.chunks[tcols[s]];
+        if (!tc.present) { flat = false; continue; }
+        it.page[s] = page_of(s, it.row0, uint32_t(i));
+        const DevPage& pg = pages[it.page[s]];
+        const bool whole = pg.first_row == it.row0 && pg.num_rows == it.nrows;
+        if (!whole || !(pg.flags & 1u)) fast = false;
+        // every page of this column under the item needs a flat copy; their starts cut the item into pieces
+        for (uint32_t pi = it.page[s]; pi < tc.pages.first_page + tc.pages.n_pages && pages[pi].first_row < row_end; pi++) {
+          if (flat_pages.empty() || flat_pages[pi].fkind == FK_NONE) flat = false;
+          if (pages[pi].first_row > it.row0) cuts.push_back(pages[pi].first_row);
+        }
+      }
+      if (!it.nrows) fast = false;
+      if (!flat) { push_item(it, false, fast); continue; }
+      // flat: one piece per stretch between page starts of ANY column (a piece lies in one page of every column)
+      std::sort(cuts.begin(), cuts.end());
+      cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+      cuts.push_back(row_end);
+      uint32_t r = it.row0;
+      for (uint32_t cut : cuts) {
+        DevItem pc{};
+        pc.rg = g;
+        pc.row0 = r;
+        pc.nrows = cut - r;
+        pc.global_row0 = rg.global_row0 + r;
+        for (uint32_t s = 0; s < ncols; s++) {
+          pc.page[s] = page_of(s, r, uint32_t(i));
+          pc.poff[s] = r - pages[pc.page[s]].first_row;
+        }
+        push_item(pc, true, false);
+        r = cut;
+      }
+    }
+  }
+  PQB_CUDA(cudaMallocAsync((void**)&sh->d_chunks, std::max<size_t>(chunks.size(), 1) * sizeof(DevChunk), stream));
+  if (!chunks.empty()) PQB_CUDA(cudaMemcpyAsync(sh->d_chunks, chunks.data(), chunks.size() * sizeof(DevChunk), cudaMemcpyHostToDevice, stream));
+  PQB_CUDA(cudaMallocAsync((void**)&sh->d_items, std::max<size_t>(sh->items.size(), 1) * sizeof(DevItem), stream));
+  if (!sh->items.empty())
+    PQB_CUDA(cudaMemcpyAsync(sh->d_items, sh->items.data(), sh->items.size() * sizeof(DevItem), cudaMemcpyHostToDevice, stream));
+  PQB_CUDA(cudaStreamSynchronize(stream));
+  shapes.emplace(tcols, sh);
+  return sh;
+}
+
+void Table::ensure_ent_off(int tcol, cudaStream_t stream) const {
+  std::lock_guard<std::mutex> lk(side_mu);
+  ColSide& cs = sides[tcol];
+  if (cs.ent_ready) return;
+  PQB_CUDA(cudaMallocAsync((void**)&cs.d_ent_off, std::max<uint64_t>(cs.total_entries, 1) * 8, stream));
+  launch_entry_offsets(*this, tcol, cs.d_ent_off, stream);
+  cs.ent_ready = true;
+}
+
+void Table::ensure_key(int tcol, cudaStream_t stream) const {
+  ensure_ent_off(tcol, stream);
+  std::lock_guard<std::mutex> lk(side_mu);
+  ColSide& cs = sides[tcol];
+  if (cs.key_ready) return;
+  build_key_side(*this, tcol, cs, stream);
+  cs.key_ready = true;
 }
 
 }  // namespace pqb
