@@ -93,6 +93,20 @@ void export_batch(const OutBatch& b, ArrowArray* out, ArrowSchema* schema) {
     std::memset(&a, 0, sizeof(a));
     a.length = b.rows;
     a.null_count = c.null_count;
+    if (c.ext_all) {
+      // device-assembled column: validity, [offsets], data all alias the page-locked block
+      p->keep = c.ext;
+      const uint8_t* base = c.ext->p;
+      p->buffers.push_back(c.null_count ? static_cast<const void*>(base + c.ext_validity_off) : nullptr);
+      if (c.type == PQ_T_UTF8) p->buffers.push_back(base + c.ext_offsets_off);
+      p->buffers.push_back(base + c.ext_off);
+      a.n_buffers = int64_t(p->buffers.size());
+      a.buffers = p->buffers.data();
+      a.release = release_array;
+      a.private_data = p;
+      top->child_ptrs.push_back(&a);
+      continue;
+    }
     // buffers: validity, [offsets], data
     if (c.null_count) { p->owned.push_back(c.validity); } else { p->owned.emplace_back(); }
     if (c.type == PQ_T_UTF8) {

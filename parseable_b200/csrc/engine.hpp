@@ -118,6 +118,9 @@ struct ColSide {
   uint32_t* d_gid = nullptr;           // group id per dictionary entry
   uint32_t card = 0;
   KeyDict kd;                          // distinct values in group-id order
+  uint32_t* d_kd_offs = nullptr;       // the same on the device (result assembly)
+  uint8_t* d_kd_bytes = nullptr;
+  uint32_t kd_max_len = 0;
   uint64_t* d_key_hash = nullptr;      // 64-bit hash of every distinct value, group-id order (multi-GPU unification)
 };
 
@@ -217,6 +220,10 @@ struct OutColumn {
   std::vector<int32_t> offsets;      // utf8
   std::vector<uint8_t> validity;     // empty when null_count == 0
   int64_t null_count = 0;
+  // device-assembled results: every buffer of the column lives in `ext`
+  bool ext_all = false;
+  size_t ext_validity_off = 0;       // validity bitmap (used when null_count != 0)
+  size_t ext_offsets_off = 0;        // utf8: int32 offsets of this batch's first row (n + 1 entries follow)
 };
 
 struct OutBatch {

@@ -214,11 +214,11 @@ __global__ void k_key_sample(const uint8_t* __restrict__ flat, const KeySamplePa
 }
 
 // accumulator table initialisation: rows / sums / nn = 0, MIN = INT64_MAX, MAX = INT64_MIN
-__global__ void k_acc_init(unsigned long long* acc, uint32_t nslots, uint32_t n_acc, uint32_t cells,
+__global__ void k_acc_init(unsigned long long* acc, uint32_t nslots, uint32_t n_acc, uint32_t cells, uint32_t replicas,
                            const __grid_constant__ DevPlan plan) {
-  uint64_t n = uint64_t(nslots) * cells;
+  uint64_t n = uint64_t(nslots) * cells * replicas;
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
-    uint32_t arr = uint32_t(i / nslots);
+    uint32_t arr = uint32_t((i / nslots) % cells);
     unsigned long long init = 0;
     if (arr >= 1 && arr < 1 + n_acc) {
       uint8_t k = plan.acc_init[arr - 1];

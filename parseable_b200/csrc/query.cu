@@ -23,6 +23,7 @@
 #include "prep_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "flat_scan.cuh"
+#include "egress_kernels.cuh"
 
 namespace pqb {
 
@@ -342,7 +343,13 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
     k_key_bytes<<<card, 64, 0, stream>>>(t.d_arena, side.d_ent_off, rep.p, card, kkind, doffs.p, dbytes.p);
     loc.bytes.resize(tot);
     if (tot) PQB_CUDA(cudaMemcpyAsync(loc.bytes.data(), dbytes.p, tot, cudaMemcpyDeviceToHost, stream));
+    // the result assembly reads the dictionary on the device
+    PQB_CUDA(cudaMallocAsync((void**)&side.d_kd_offs, (size_t(card) + 1) * 4, stream));
+    PQB_CUDA(cudaMallocAsync((void**)&side.d_kd_bytes, std::max<uint64_t>(tot, 1), stream));
+    PQB_CUDA(cudaMemcpyAsync(side.d_kd_offs, doffs.p, (size_t(card) + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+    if (tot) PQB_CUDA(cudaMemcpyAsync(side.d_kd_bytes, dbytes.p, tot, cudaMemcpyDeviceToDevice, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
+    for (uint32_t g = 0; g < card; g++) side.kd_max_len = std::max(side.kd_max_len, hl[g]);
   }
 }
 
@@ -977,9 +984,11 @@ void Query::run(const PqQueryDesc& d) {
       plan.replicas = std::max<uint32_t>(1, std::min<uint32_t>(r, uint32_t(ctx.sm_count())));
     }
     d_acc.alloc(size_t(plan.nslots) * cells * plan.replicas, stream);
-    for (uint32_t r = 0; r < plan.replicas; r++)
-      k_acc_init<<<std::min<uint32_t>(1024, (plan.nslots * cells + 255) / 256), 256, 0, stream>>>(d_acc.p + size_t(r) * plan.nslots * cells, plan.nslots, plan.n_acc, cells, plan);
-    launches += plan.replicas;
+    {
+      const uint64_t ncell = uint64_t(plan.nslots) * cells * plan.replicas;
+      k_acc_init<<<uint32_t(std::min<uint64_t>(2048, (ncell + 255) / 256)), 256, 0, stream>>>(d_acc.p, plan.nslots, plan.n_acc, cells, plan.replicas, plan);
+    }
+    launches++;
     size_t acc_bytes = size_t(plan.nslots) * cells * 8;
     if (n_general && smem_fixed + acc_bytes + 1024 <= ctx.smem_optin()) { plan.smem_acc = 1; smem_total = smem_fixed + acc_bytes; }
   }
@@ -1077,12 +1086,6 @@ void Query::run(const PqQueryDesc& d) {
   const uint32_t batch_rows = d.batch_size ? d.batch_size : 20000;
   unsigned long long h_counters[4] = {0, 0, 0, 0};
   if (agg_kernel) {
-    DevBuf<uint32_t> d_out_count, d_out_slot;
-    DevBuf<unsigned long long> d_out_cells;
-    uint32_t out_cap = plan.nslots;
-    d_out_count.alloc(1, stream); d_out_count.zero();
-    d_out_slot.alloc(out_cap, stream);
-    d_out_cells.alloc(size_t(out_cap) * cells, stream);
     // multi-GPU: the partial tables meet in ONE grouped all-reduce: one NCCL launch,
     // per array the reduction its aggregate needs
     Timer t_ar;
@@ -1098,106 +1101,179 @@ void Query::run(const PqQueryDesc& d) {
       comm_group_end();
       PQB_CUDA(cudaEventRecord(t_ar.b, stream));
     }
-    k_agg_compact<<<std::min<uint32_t>(512, (plan.nslots + 255) / 256), 256, 0, stream>>>(d_acc.p, plan.nslots, cells, d_out_count.p, d_out_slot.p, d_out_cells.p, out_cap);
-    launches++;
-    uint32_t n_out = 0;
-    PQB_CUDA(cudaMemcpyAsync(&n_out, d_out_count.p, 4, cudaMemcpyDeviceToHost, stream));
+    // ---- non-empty groups in ascending slot order (deterministic: the mixed radix of the group ids) ----
+    const uint32_t ntiles = (plan.nslots + kSlotTile - 1) / kSlotTile;
+    const uint64_t out_cap = std::min<uint64_t>(plan.nslots, std::max<uint64_t>(allreduce ? plan.nslots : metrics.rows_scanned, 1));
+    DevBuf<uint32_t> d_tile_counts, d_out_slot;
+    DevBuf<unsigned long long> d_tile_base, d_totals;
+    d_tile_counts.alloc(ntiles, stream);
+    d_tile_base.alloc(ntiles, stream);
+    d_totals.alloc(2, stream);
+    d_out_slot.alloc(out_cap, stream);
+    k_slot_tile_counts<<<ntiles, 256, 0, stream>>>(d_acc.p, plan.nslots, d_tile_counts.p);
+    k_item_prefix<<<1, 1024, 0, stream>>>(d_tile_counts.p, ntiles, d_tile_base.p, d_totals.p);
+    k_slot_compact<<<ntiles, 256, 0, stream>>>(d_acc.p, plan.nslots, d_tile_base.p, d_out_slot.p);
+    // rows this rank selected (its own items)
+    DevBuf<unsigned long long> d_item_base;
+    d_item_base.alloc(std::max<size_t>(items.size(), 1), stream);
+    if (!items.empty()) k_item_prefix<<<1, 1024, 0, stream>>>(d_item_counts.p, uint32_t(items.size()), d_item_base.p, d_totals.p + 1);
+    else PQB_CUDA(cudaMemsetAsync(d_totals.p + 1, 0, 8, stream));
+    launches += 4;
+    unsigned long long totals[2] = {0, 0};
+    PQB_CUDA(cudaMemcpyAsync(totals, d_totals.p, 16, cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
-    metrics.d2h_bytes += 4 + sizeof(h_counters);
+    metrics.d2h_bytes += 16 + sizeof(h_counters);
     if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
-    std::vector<uint32_t> out_slot(n_out);
-    std::vector<unsigned long long> out_cells(size_t(n_out) * cells);
-    if (n_out) {
-      PQB_CUDA(cudaMemcpyAsync(out_slot.data(), d_out_slot.p, n_out * 4, cudaMemcpyDeviceToHost, stream));
-      for (uint32_t c = 0; c < cells; c++)
-        PQB_CUDA(cudaMemcpyAsync(out_cells.data() + size_t(c) * n_out, d_out_cells.p + size_t(c) * out_cap, n_out * 8ull, cudaMemcpyDeviceToHost, stream));
-    }
-    PQB_CUDA(cudaEventRecord(t_all.b, stream));
-    PQB_CUDA(cudaStreamSynchronize(stream));
-    metrics.d2h_bytes += uint64_t(n_out) * (4 + 8ull * cells);
+    const uint32_t n_out = uint32_t(totals[0]);
+    metrics.rows_selected = totals[1];
     if (allreduce) { float ms = 0; cudaEventElapsedTime(&ms, t_ar.a, t_ar.b); metrics.allreduce_ms = ms; }
-
-    // SQL: a global aggregate over zero rows still yields one row
-    bool synth_empty = d.n_group_by == 0 && n_out == 0;
-    uint32_t n_rows = synth_empty ? 1 : n_out;
-    metrics.groups = n_rows;
-    unsigned long long rows_sel = 0;
-    for (uint32_t i = 0; i < n_out; i++) rows_sel += out_cells[i];
-    metrics.rows_selected = rows_sel;
-
-    // deterministic order: ascending dense slot (= mixed radix of group ids)
-    std::vector<uint32_t> order(n_out);
-    for (uint32_t i = 0; i < n_out; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return out_slot[a] < out_slot[b]; });
-
-    for (uint32_t r0 = 0; r0 < n_rows; r0 += batch_rows) {
-      uint32_t nb = std::min(batch_rows, n_rows - r0);
+    static const char* fn_names[] = {"count(*)", "count", "sum", "min", "max", "avg"};
+    auto agg_name = [&](uint32_t a) {
+      const DevAgg& ag = plan.aggs[a];
+      return ag.fn == AG_COUNT_STAR ? std::string("count(*)") : std::string(fn_names[ag.fn]) + "(" + d.columns[d.aggs[a].col].name + ")";
+    };
+    if (d.n_group_by == 0 && n_out == 0) {
+      // SQL: a global aggregate over zero rows still yields one row: COUNT = 0, everything else NULL
       OutBatch ob;
-      ob.rows = nb;
-      for (uint32_t k = 0; k < d.n_group_by; k++) {
+      ob.rows = 1;
+      for (uint32_t a = 0; a < d.n_aggs; a++) {
         OutColumn oc;
-        uint32_t qc = uint32_t(d.group_by[k]);
-        oc.name = d.columns[qc].name;
-        oc.type = out_type_of(qc);
-        uint8_t kind = plan.cols[plan.keys[k].col].kind;
-        const uint32_t card = qk[k].card;
-        const KeyDict* kd = qk[k].kd;
-        oc.validity.assign((nb + 7) / 8, 0);
-        if (kind == DK_STR) oc.offsets.push_back(0);
-        else if (kind == DK_BOOL) oc.values.assign((nb + 7) / 8, 0);
-        else oc.values.resize(size_t(nb) * 8);
-        for (uint32_t i = 0; i < nb; i++) {
-          uint32_t slot = out_slot[order[r0 + i]];
-          uint32_t gid = (slot / plan.keys[k].stride) % (card + 1);
-          bool valid = gid != card;
-          if (valid) oc.validity[i >> 3] |= uint8_t(1u << (i & 7)); else oc.null_count++;
-          if (kind == DK_STR) {
-            if (valid) oc.values.insert(oc.values.end(), kd->bytes.begin() + kd->offs[gid], kd->bytes.begin() + kd->offs[gid + 1]);
-            oc.offsets.push_back(int32_t(oc.values.size()));
-          } else if (kind == DK_BOOL) {
-            if (valid && gid) oc.values[i >> 3] |= uint8_t(1u << (i & 7));
-          } else if (valid) {
-            std::memcpy(oc.values.data() + size_t(i) * 8, kd->bytes.data() + kd->offs[gid], 8);
+        oc.name = agg_name(a);
+        oc.type = agg_out_type[a];
+        oc.values.assign(8, 0);
+        const bool is_count = plan.aggs[a].fn == AG_COUNT_STAR || plan.aggs[a].fn == AG_COUNT;
+        if (!is_count) { oc.validity.assign(1, 0); oc.null_count = 1; }
+        ob.cols.push_back(std::move(oc));
+      }
+      metrics.groups = 1;
+      batches_.push_back(std::move(ob));
+      PQB_CUDA(cudaEventRecord(t_all.b, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+    } else if (n_out == 0) {
+      metrics.groups = 0;
+      PQB_CUDA(cudaEventRecord(t_all.b, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      // ---- the result block: every buffer of every batch, assembled on the device ----
+      FinishArgs fa{};
+      const uint32_t nbatches = (n_out + batch_rows - 1) / batch_rows;
+      const uint32_t wpb = (batch_rows + 31) / 32;
+      const uint32_t ncolumns = d.n_group_by + d.n_aggs;
+      uint64_t off = 0;
+      auto take = [&](uint64_t bytes) { uint64_t o = off; off = (off + bytes + 63) & ~63ull; return o; };
+      const uint64_t nulls_off = take(uint64_t(ncolumns) * nbatches * 4);
+      std::vector<DevBuf<uint32_t>> kd_offs_q(d.n_group_by);
+      std::vector<DevBuf<uint8_t>> kd_bytes_q(d.n_group_by);
+      for (uint32_t k = 0; k < d.n_group_by; k++) {
+        FinishKey& fk = fa.keys[k];
+        const uint8_t kind = plan.cols[plan.keys[k].col].kind;
+        fk.kind = kind;
+        fk.stride = plan.keys[k].stride;
+        fk.card = qk[k].card;
+        fk.valid_off = take(uint64_t(nbatches) * wpb * 4);
+        if (kind == DK_BOOL) fk.val_off = take(uint64_t(nbatches) * wpb * 4);
+        else if (kind == DK_STR) fk.val_off = take((uint64_t(n_out) + 1) * 4);
+        else fk.val_off = take(uint64_t(n_out) * 8);
+        if (kind != DK_BOOL) {
+          const ColSide& cs = table->sides[shape_cols[plan.keys[k].col]];
+          if (multi) {   // the globally agreed dictionary of this query
+            kd_offs_q[k].upload(qk[k].kd->offs, stream);
+            kd_bytes_q[k].alloc(std::max<size_t>(qk[k].kd->bytes.size(), 1), stream);
+            if (!qk[k].kd->bytes.empty())
+              PQB_CUDA(cudaMemcpyAsync(kd_bytes_q[k].p, qk[k].kd->bytes.data(), qk[k].kd->bytes.size(), cudaMemcpyHostToDevice, stream));
+            fk.kd_offs = kd_offs_q[k].p;
+            fk.kd_bytes = kd_bytes_q[k].p;
+          } else {
+            fk.kd_offs = cs.d_kd_offs;
+            fk.kd_bytes = cs.d_kd_bytes;
           }
         }
-        if (!oc.null_count) oc.validity.clear();
-        ob.cols.push_back(std::move(oc));
       }
       for (uint32_t a = 0; a < d.n_aggs; a++) {
-        const DevAgg& ag = plan.aggs[a];
-        OutColumn oc;
-        static const char* fn_names[] = {"count(*)", "count", "sum", "min", "max", "avg"};
-        oc.name = ag.fn == AG_COUNT_STAR ? "count(*)" : std::string(fn_names[ag.fn]) + "(" + d.columns[d.aggs[a].col].name + ")";
-        oc.type = agg_out_type[a];
-        oc.values.resize(size_t(nb) * 8);
-        oc.validity.assign((nb + 7) / 8, 0);
-        for (uint32_t i = 0; i < nb; i++) {
-          unsigned long long rows = 0, nn = 0, cell = 0;
-          if (!synth_empty) {
-            uint32_t o = order[r0 + i];
-            rows = out_cells[o];
-            if (ag.fn != AG_COUNT_STAR) nn = nn_is_rows[a] ? rows : out_cells[size_t(1 + plan.n_acc + ag.nn_slot) * n_out + o];
-            if (ag.fn >= AG_SUM) cell = out_cells[size_t(1 + ag.acc_slot) * n_out + o];
-          }
-          bool valid = true;
-          uint64_t v = 0;
-          switch (ag.fn) {
-            case AG_COUNT_STAR: v = rows; break;
-            case AG_COUNT: v = nn; break;
-            case AG_SUM: valid = nn > 0; v = cell; break;
-            case AG_AVG: valid = nn > 0; if (valid) v = f64_bits(bits_f64(cell) / double(nn)); break;
-            default:  // MIN / MAX
-              valid = nn > 0;
-              v = ag.kind == DK_F64 ? f64_from_order_key((int64_t)cell) : cell;
-          }
-          if (valid) { oc.validity[i >> 3] |= uint8_t(1u << (i & 7)); std::memcpy(oc.values.data() + size_t(i) * 8, &v, 8); }
-          else oc.null_count++;
-        }
-        if (!oc.null_count) oc.validity.clear();
-        ob.cols.push_back(std::move(oc));
+        fa.aggs[a] = plan.aggs[a];
+        fa.nn_is_rows[a] = nn_is_rows[a];
+        fa.valid_off[a] = take(uint64_t(nbatches) * wpb * 4);
+        fa.val_off[a] = take(uint64_t(n_out) * 8);
       }
-      batches_.push_back(std::move(ob));
+      // string key bytes: an upper bound (rows x the longest distinct value) keeps the copy to one round trip
+      for (uint32_t k = 0; k < d.n_group_by; k++) {
+        FinishKey& fk = fa.keys[k];
+        if (fk.kind != DK_STR) continue;
+        uint64_t max_len = 0;
+        const KeyDict* kd = qk[k].kd;
+        if (multi) { for (size_t g = 0; g + 1 < kd->offs.size(); g++) max_len = std::max<uint64_t>(max_len, kd->offs[g + 1] - kd->offs[g]); }
+        else max_len = table->sides[shape_cols[plan.keys[k].col]].kd_max_len;
+        const uint64_t bound = std::min<uint64_t>(uint64_t(n_out) * max_len, uint64_t(n_out / std::max<uint32_t>(fk.card, 1) + 1) * kd->bytes.size());
+        if (bound > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "group key strings of one result exceed 2 GiB");
+        fk.data_off = take(bound);
+      }
+      const uint64_t copy_bytes = off;
+      for (uint32_t k = 0; k < d.n_group_by; k++)
+        if (fa.keys[k].kind == DK_STR) fa.keys[k].len_off = take(uint64_t(n_out) * 4);   // device-only scratch behind the copied part
+      DevBuf<uint8_t> d_block;
+      d_block.alloc(off, stream);
+      PQB_CUDA(cudaMemsetAsync(d_block.p, 0, copy_bytes, stream));
+      fa.acc = d_acc.p;
+      fa.out_slot = d_out_slot.p;
+      fa.out = d_block.p;
+      fa.nulls = reinterpret_cast<uint32_t*>(d_block.p + nulls_off);
+      fa.n_out = n_out;
+      fa.nslots = plan.nslots;
+      fa.n_acc = plan.n_acc;
+      fa.naggs = d.n_aggs;
+      fa.nkeys = d.n_group_by;
+      fa.batch_rows = batch_rows;
+      fa.words_per_batch = wpb;
+      fa.nbatches = nbatches;
+      k_agg_finish<<<(n_out + 255) / 256, 256, 0, stream>>>(fa);
+      launches++;
+      for (uint32_t k = 0; k < d.n_group_by; k++) {
+        if (fa.keys[k].kind != DK_STR) continue;
+        k_offsets_scan<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_block.p + fa.keys[k].len_off), n_out,
+                                               reinterpret_cast<int32_t*>(d_block.p + fa.keys[k].val_off));
+        k_key_gather<<<uint32_t((uint64_t(n_out) * 32 + 255) / 256), 256, 0, stream>>>(fa, k);
+        launches += 2;
+      }
+      PQB_CUDA(cudaGetLastError());
+      auto block = std::make_shared<PinnedBlock>();
+      block->p = ctx.pinned_acquire(copy_bytes);
+      block->bytes = copy_bytes;
+      PQB_CUDA(cudaMemcpyAsync(block->p, d_block.p, copy_bytes, cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaEventRecord(t_all.b, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      metrics.d2h_bytes += copy_bytes;
+      metrics.groups = n_out;
+      const uint32_t* nulls = reinterpret_cast<const uint32_t*>(block->p + nulls_off);
+      for (uint32_t b = 0; b < nbatches; b++) {
+        const uint32_t r0 = b * batch_rows, nb = std::min(batch_rows, n_out - r0);
+        OutBatch ob;
+        ob.rows = nb;
+        for (uint32_t c = 0; c < ncolumns; c++) {
+          OutColumn oc;
+          oc.ext = block;
+          oc.ext_all = true;
+          oc.null_count = nulls[c * nbatches + b];
+          if (c < d.n_group_by) {
+            const FinishKey& fk = fa.keys[c];
+            const uint32_t qc = uint32_t(d.group_by[c]);
+            oc.name = d.columns[qc].name;
+            oc.type = out_type_of(qc);
+            oc.ext_validity_off = fk.valid_off + uint64_t(b) * wpb * 4;
+            if (fk.kind == DK_STR) { oc.ext_offsets_off = fk.val_off + uint64_t(r0) * 4; oc.ext_off = fk.data_off; }
+            else if (fk.kind == DK_BOOL) oc.ext_off = fk.val_off + uint64_t(b) * wpb * 4;
+            else oc.ext_off = fk.val_off + uint64_t(r0) * 8;
+          } else {
+            const uint32_t a = c - d.n_group_by;
+            oc.name = agg_name(a);
+            oc.type = agg_out_type[a];
+            oc.ext_validity_off = fa.valid_off[a] + uint64_t(b) * wpb * 4;
+            oc.ext_off = fa.val_off[a] + uint64_t(r0) * 8;
+          }
+          ob.cols.push_back(std::move(oc));
+        }
+        batches_.push_back(std::move(ob));
+      }
     }
   } else {
     // ---- filter / COUNT(*) ----

@@ -221,6 +221,8 @@ Table::~Table() {
     if (cs.d_ent_off) cudaFreeAsync(cs.d_ent_off, cudaStreamPerThread);
     if (cs.d_gid) cudaFreeAsync(cs.d_gid, cudaStreamPerThread);
     if (cs.d_key_hash) cudaFreeAsync(cs.d_key_hash, cudaStreamPerThread);
+    if (cs.d_kd_offs) cudaFreeAsync(cs.d_kd_offs, cudaStreamPerThread);
+    if (cs.d_kd_bytes) cudaFreeAsync(cs.d_kd_bytes, cudaStreamPerThread);
   }
 }
 
@@ -1021,7 +1023,7 @@ void Table::ensure_ent_off(int tcol, cudaStream_t stream) const {
   ColSide& cs = sides[tcol];
   if (cs.ent_ready) return;
   PQB_CUDA(cudaMallocAsync((void**)&cs.d_ent_off, std::max<uint64_t>(cs.total_entries, 1) * 8, stream));
-  launch_entry_offsets(*this, tcol, cs.d_ent_off, stream);
+  launch_entry_offsets(*this, tcol, cs.d_ent_off, stream);   // synchronises: later queries run on other streams
   cs.ent_ready = true;
 }
 
