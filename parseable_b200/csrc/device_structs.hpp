@@ -99,7 +99,7 @@ struct DevColumn {
   uint8_t kind;                // DevKind
   uint8_t max_def;             // 0: REQUIRED
   uint8_t need_idx;            // stage dictionary indices in the row phase
-  uint8_t is_key;
+  uint8_t staged;              // flat kernels: 1 = predicate / key / aggregate input (TMA-staged per slab); 0 = only projected
   uint32_t max_bw;             // widest dictionary index over all pages read
   uint32_t has_delta, has_plain, has_dict;
 };

@@ -175,4 +175,133 @@ __global__ void k_key_gather(const __grid_constant__ FinishArgs f, uint32_t k) {
   for (uint32_t b = lane; b < n; b += 32) dst[b] = key.kd_bytes[a + b];
 }
 
+
+// ---- projection: TableProvider::scan(projection, ...) (stream_schema_provider.rs:526-659, :114-189) ----
+// Late materialisation: the filter kernels leave a selection bitmap; only the selected rows of the
+// projected columns are decoded, straight out of the flat store (row r of a page is bits
+// [r*bw, (r+1)*bw) / 8-byte slot r), dictionary values through the chunk's dictionary.  The buffers
+// of every result batch are assembled in one device block, like the aggregate results above.
+struct ProjCol {
+  const uint64_t* ent;   // strings: arena offset of every dictionary entry of the column
+  uint64_t val_off;      // 8-byte values | per-batch bit words (bool) | int32 offsets (n + 1) (strings)
+  uint64_t valid_off;    // per-batch validity words
+  uint64_t src_off;      // strings: u64 arena offset of the bytes per output row (device-only scratch)
+  uint64_t len_off;      // strings: u32 length per output row (device-only scratch)
+  uint64_t data_off;     // strings: bytes
+  uint32_t slot;         // column slot of the plan (chunk table, item.page, item.poff); 0xffffffff: the __row_id column
+  uint32_t kind;         // DevKind
+};
+struct ProjArgs {
+  const uint8_t* arena;
+  const uint8_t* flat;
+  const FlatPageRec* fpages;
+  const DevChunk* chunks;
+  const DevItem* items;
+  const uint32_t* bitmap;
+  const uint32_t* item_counts;
+  const unsigned long long* item_base;
+  uint8_t* out;
+  uint32_t* nulls;       // [ncols * nbatches]
+  unsigned long long n_out;   // output rows kept (LIMIT)
+  uint32_t n_items, plan_ncols, ncols;
+  uint32_t batch_rows, words_per_batch, nbatches;
+  ProjCol cols[kMaxCols + 1];
+};
+
+__device__ __forceinline__ uint32_t flat_bits_at(const uint8_t* flat, uint64_t off, uint64_t bit, uint32_t bw) {
+  if (bw == 0) return 0;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(flat + off) + (bit >> 5);
+  const uint32_t sh = uint32_t(bit & 31);
+  const uint32_t v = __funnelshift_r(w[0], w[1], sh);
+  return bw >= 32 ? v : (v & ((1u << bw) - 1u));
+}
+
+// one CTA per work item (grid-strided): bitmap words -> output positions -> values of every projected column
+__global__ void __launch_bounds__(256) k_project(const __grid_constant__ ProjArgs f) {
+  __shared__ uint32_t warp_sums[8];
+  __shared__ uint32_t carry;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (uint32_t it = blockIdx.x; it < f.n_items; it += gridDim.x) {
+    if (f.item_counts[it] == 0) continue;   // uniform per block
+    const DevItem& item = f.items[it];
+    const uint32_t nwords = (item.nrows + 31) >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t w0 = 0; w0 < nwords; w0 += blockDim.x) {
+      const uint32_t w = w0 + threadIdx.x;
+      uint32_t word = w < nwords ? f.bitmap[item.bitmap_word0 + w] : 0;
+      const uint32_t c = __popc(word);
+      uint32_t incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      if (lane == 31) warp_sums[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t s = lane < nwarps ? warp_sums[lane] : 0, si = s;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+          if ((int)lane >= o) si += t;
+        }
+        if (lane < nwarps) warp_sums[lane] = si - s;
+      }
+      __syncthreads();
+      unsigned long long pos = f.item_base[it] + carry + warp_sums[warp] + incl - c;
+      while (word) {
+        const uint32_t b = __ffs(word) - 1;
+        word &= word - 1;
+        if (pos < f.n_out) {
+          const uint32_t r = w * 32 + b;   // row inside the item
+          const uint32_t batch = uint32_t(pos / f.batch_rows), bp = uint32_t(pos - uint64_t(batch) * f.batch_rows);
+          const uint32_t vword = batch * f.words_per_batch + (bp >> 5), vbit = 1u << (bp & 31);
+          for (uint32_t ci = 0; ci < f.ncols; ci++) {
+            const ProjCol& pc = f.cols[ci];
+            if (pc.slot == 0xffffffffu) {   // __row_id: ordinal of the row in the scanned table
+              reinterpret_cast<unsigned long long*>(f.out + pc.val_off)[pos] = item.global_row0 + r;
+              continue;
+            }
+            const FlatPageRec fp = f.fpages[item.page[pc.slot]];
+            const uint64_t row = uint64_t(item.poff[pc.slot]) + r;
+            atomicOr(reinterpret_cast<uint32_t*>(f.out + pc.valid_off) + vword, vbit);   // flat pages hold no NULLs
+            if (fp.fkind == FK_PLAIN8) {
+              reinterpret_cast<unsigned long long*>(f.out + pc.val_off)[pos] = reinterpret_cast<const unsigned long long*>(f.flat + fp.off)[row];
+            } else if (fp.fkind == FK_BITS) {
+              const uint32_t v = (reinterpret_cast<const uint32_t*>(f.flat + fp.off)[row >> 5] >> (row & 31)) & 1u;
+              if (v) atomicOr(reinterpret_cast<uint32_t*>(f.out + pc.val_off) + vword, vbit);
+            } else {
+              const DevChunk& ch = f.chunks[item.rg * f.plan_ncols + pc.slot];
+              uint32_t idx = flat_bits_at(f.flat, fp.off, row * fp.bw, fp.bw);
+              idx = idx < ch.dict_n ? idx : (ch.dict_n ? ch.dict_n - 1 : 0);
+              if (pc.kind == DK_STR) {
+                const uint64_t e = pc.ent[ch.lut_base + idx];
+                reinterpret_cast<unsigned long long*>(f.out + pc.src_off)[pos] = e;
+                reinterpret_cast<uint32_t*>(f.out + pc.len_off)[pos] = load_u32_unaligned(f.arena + e - 4);
+              } else {
+                reinterpret_cast<unsigned long long*>(f.out + pc.val_off)[pos] = reinterpret_cast<const unsigned long long*>(f.flat + ch.dict8_off)[idx];
+              }
+            }
+          }
+        }
+        pos++;
+      }
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) carry += warp_sums[warp] + incl;
+      __syncthreads();
+    }
+  }
+}
+
+// string bytes of one projected column: one warp per output row
+__global__ void k_project_bytes(const __grid_constant__ ProjArgs f, uint32_t ci, unsigned long long n_rows) {
+  const unsigned long long i = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (i >= n_rows) return;
+  const ProjCol& pc = f.cols[ci];
+  const uint32_t n = reinterpret_cast<const uint32_t*>(f.out + pc.len_off)[i];
+  const uint8_t* src = f.arena + reinterpret_cast<const unsigned long long*>(f.out + pc.src_off)[i];
+  uint8_t* dst = f.out + pc.data_off + reinterpret_cast<const int32_t*>(f.out + pc.val_off)[i];
+  for (uint32_t b = lane; b < n; b += 32) dst[b] = src[b];
+}
+
 }  // namespace pqb

@@ -118,6 +118,10 @@ struct ColSide {
   uint32_t* d_gid = nullptr;           // group id per dictionary entry
   uint32_t card = 0;
   KeyDict kd;                          // distinct values in group-id order
+  uint32_t max_ent_len = 0;            // longest dictionary entry (sizes projected string buffers)
+  bool has_delta = false;              // some page of the column is DELTA_BINARY_PACKED
+  bool delta_ready = false;            // ... and its pages have aligned 8-byte copies in d_delta_flat (ensure_plain8)
+  uint8_t* d_delta_flat = nullptr;
   uint32_t* d_kd_offs = nullptr;       // the same on the device (result assembly)
   uint8_t* d_kd_bytes = nullptr;
   uint32_t kd_max_len = 0;
@@ -173,8 +177,8 @@ class Table {
   // aligned copies of PLAIN 8-byte pages and of numeric dictionaries
   uint8_t* d_flat = nullptr;
   uint64_t flat_bytes = 0;
-  std::vector<FlatPageRec> flat_pages;   // host copy, parallel to pages
-  FlatPageRec* d_flat_pages = nullptr;
+  mutable std::vector<FlatPageRec> flat_pages;   // host copy, parallel to pages (ensure_plain8 adds entries later)
+  mutable FlatPageRec* d_flat_pages = nullptr;
   uint64_t flat_page_count = 0;
 
   // lazily built, query independent (the table is immutable once opened); guarded by side_mu
@@ -184,6 +188,7 @@ class Table {
   std::shared_ptr<Shape> shape_for(const std::vector<int>& tcols, cudaStream_t stream) const;
   void ensure_ent_off(int tcol, cudaStream_t stream) const;
   void ensure_key(int tcol, cudaStream_t stream) const;
+  void ensure_plain8(int tcol, cudaStream_t stream) const;   // DELTA_BINARY_PACKED pages -> row-addressable 8-byte values
 
  private:
   void build_flat_store(cudaStream_t stream);
@@ -200,7 +205,9 @@ void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void
 void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat, uint8_t* ok,
                        cudaStream_t stream);
 // side-table builders (prep_kernels.cuh), defined in query.cu
-void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, cudaStream_t stream);
+void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, uint32_t* max_len, cudaStream_t stream);
+void launch_delta_to_plain8(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat_base, uint8_t* ok,
+                            cudaStream_t stream);
 void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream);
 
 // page-locked host block that result batches can alias (zero copy); returns to the pool when

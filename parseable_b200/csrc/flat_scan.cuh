@@ -136,7 +136,8 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
       // first bit of the slab in the page's flat copy; the copy starts at the 16-byte boundary below it
       const uint64_t bit0 = uint64_t(mypoff + r0) * mycol.bw;
       mycol.phase = uint32_t(bit0 & 127u);
-      uint32_t nb = lane < ncols ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
+      // a column that is only projected is not staged: the gather after the scan reads its selected rows
+      uint32_t nb = (lane < ncols && plan.cols[lane].staged) ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
       if (lane < ncols) st.col[lane] = mycol;
       if (lane < plan.nleaves) st.lutreg[lane] = mylut;
       uint32_t bytes = nb;

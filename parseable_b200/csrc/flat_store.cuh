@@ -243,4 +243,104 @@ __global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ 
   if (lane == 0) ok_out[ji] = bad ? 0 : 1;
 }
 
+
+// ---- DELTA_BINARY_PACKED (Parseable's p_timestamp, streams.rs:587-590) -> aligned 8-byte values ----
+// Only built when a query needs the VALUES of such a column (a time range that cuts a row group, a
+// projection of p_timestamp): footer statistics decide the injected range for every other query and
+// the column is then never read.  One warp per page: lane 0 walks the block headers (zigzag varints,
+// one bit width per miniblock), the warp unpacks a miniblock's deltas in parallel and turns them into
+// values with a shuffle scan carried across miniblocks.
+struct DeltaJob { uint32_t page; uint32_t _pad; uint64_t dst; };
+
+__device__ __forceinline__ bool rd_varint(const uint8_t* __restrict__ p, uint64_t& pos, uint64_t end, uint64_t& out) {
+  uint64_t v = 0;
+  for (int shift = 0; shift < 70; shift += 7) {
+    if (pos >= end) return false;
+    const uint32_t b = p[pos++];
+    if (shift < 64) v |= uint64_t(b & 0x7f) << shift;
+    if (!(b & 0x80)) { out = v; return true; }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
+                                                         const DeltaJob* __restrict__ jobs, uint32_t n_jobs, uint8_t* __restrict__ flat_base,
+                                                         uint8_t* __restrict__ ok_out) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ji = blockIdx.x * 4 + warp;
+  if (ji >= n_jobs) return;
+  const DeltaJob job = jobs[ji];
+  const DevPage pg = pages[job.page];
+  uint32_t ok = 1;
+  if (pg.def_len) {
+    if (lane == 0) ok = def_levels_all_valid(arena + pg.off + pg.def_off, pg.def_len, pg.num_rows) ? 1u : 0u;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+  }
+  if (!ok) { if (lane == 0) ok_out[ji] = 0; return; }
+  const uint8_t* p = arena + pg.off;
+  uint64_t pos = pg.val_off;
+  const uint64_t end = pg.len;
+  int64_t* out = reinterpret_cast<int64_t*>(flat_base + job.dst);
+  // page header
+  uint64_t bs = 0, nm = 0, total = 0, fz = 0;
+  uint32_t bad = 0;
+  if (lane == 0) {
+    if (!rd_varint(p, pos, end, bs) || !rd_varint(p, pos, end, nm) || !rd_varint(p, pos, end, total) || !rd_varint(p, pos, end, fz)) bad = 1;
+    if (!bad && (nm == 0 || nm > 32 || bs == 0 || bs % nm != 0 || (bs / nm) % 32 != 0 || bs > (1u << 20) || total != pg.num_rows)) bad = 1;
+  }
+  bad = __shfl_sync(0xffffffffu, bad, 0);
+  if (bad) { if (lane == 0) ok_out[ji] = pg.num_rows == 0 ? 1 : 0; return; }
+  bs = __shfl_sync(0xffffffffu, bs, 0);
+  nm = __shfl_sync(0xffffffffu, nm, 0);
+  fz = __shfl_sync(0xffffffffu, fz, 0);
+  pos = __shfl_sync(0xffffffffu, pos, 0);
+  const uint32_t vpm = uint32_t(bs / nm);   // values per miniblock, a multiple of 32
+  int64_t last = int64_t(fz >> 1) ^ -int64_t(fz & 1);
+  if (lane == 0 && pg.num_rows) out[0] = last;
+  uint32_t done = 1;                        // values written
+  const uint32_t nvals = pg.num_rows;
+  while (done < nvals && !bad) {
+    // block header: min delta + one bit width per miniblock (lane m keeps width m)
+    uint64_t mz = 0;
+    if (lane == 0) { if (!rd_varint(p, pos, end, mz) || pos + nm > end) bad = 1; }
+    bad = __shfl_sync(0xffffffffu, bad, 0);
+    if (bad) break;
+    mz = __shfl_sync(0xffffffffu, mz, 0);
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    const int64_t min_delta = int64_t(mz >> 1) ^ -int64_t(mz & 1);
+    const uint32_t mybw = lane < nm ? p[pos + lane] : 0u;
+    pos += nm;
+    for (uint32_t m = 0; m < nm && done < nvals; m++) {
+      const uint32_t bw = __shfl_sync(0xffffffffu, mybw, m);
+      if (bw > 64 || pos + (uint64_t(vpm) * bw) / 8 > end + 8) { bad = 1; break; }
+      const uint32_t take = nvals - done < vpm ? nvals - done : vpm;
+      for (uint32_t v0 = 0; v0 < take; v0 += 32) {
+        const uint32_t j = v0 + lane;
+        uint64_t d = 0;
+        if (bw && j < take) {
+          const uint64_t bit = uint64_t(j) * bw;
+          const uint8_t* q = p + pos + (bit >> 3);
+          const uint32_t sh = uint32_t(bit & 7);
+          d = load_u64_unaligned(q) >> sh;
+          if (sh + bw > 64) d |= uint64_t(q[8]) << (64 - sh);
+          if (bw < 64) d &= (1ull << bw) - 1ull;
+        }
+        // wrapping arithmetic like the reference's decoder
+        uint64_t x = j < take ? uint64_t(min_delta) + d : 0ull, incl = x;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((int)lane >= o) incl += t;
+        }
+        const uint64_t val = uint64_t(last) + incl;
+        if (j < take) out[done + j] = int64_t(val);
+        last = int64_t(__shfl_sync(0xffffffffu, val, 31));
+        if (take - v0 < 32) last = int64_t(__shfl_sync(0xffffffffu, val, (take - v0 - 1) & 31));
+      }
+      done += take;
+      pos += (uint64_t(vpm) * bw) / 8;
+    }
+  }
+  if (lane == 0) ok_out[ji] = bad ? 0 : 1;
+}
+
 }  // namespace pqb

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128) k_dict_entry_offsets(const uint8_t* __res
   uint8_t* tile = tiles[warp];
   const uint64_t end = ch.dict_off + ch.dict_len;
   uint64_t p = ch.dict_off;
-  uint32_t i = 0;
+  uint32_t i = 0, maxlen = 0;
   bool bad = false;
   while (i < ch.dict_n && !bad) {
     // stage [t0, t0 + kEntTile) with t0 = p rounded down to 16 (the arena is padded past every chunk)
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(128) k_dict_entry_offsets(const uint8_t* __res
         const uint32_t len = uint32_t(tile[rel]) | (uint32_t(tile[rel + 1]) << 8) | (uint32_t(tile[rel + 2]) << 16) |
                              (uint32_t(tile[rel + 3]) << 24);
         if (p + 4 + uint64_t(len) > end) { bad = true; break; }
+        if (len > maxlen) maxlen = len;
         out[i++] = p + 4;
         p += 4 + uint64_t(len);
       }
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(128) k_dict_entry_offsets(const uint8_t* __res
     bad = __shfl_sync(0xffffffffu, bad ? 1 : 0, 0) != 0;
     __syncwarp();
   }
+  if (lane == 0 && maxlen) atomicMax(err + 1, maxlen);   // longest entry of the column (sizes projected string buffers)
   if (bad) {
     // a corrupt dictionary: the remaining entries read as empty strings at the dictionary start (never
     // out of bounds); the query that asked for this table fails with PQ_ERR_CORRUPT

@@ -223,16 +223,25 @@ static std::vector<EntChunk> column_chunks(const Table& t, int tcol) {
   return v;
 }
 
-void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, cudaStream_t stream) {
+void launch_delta_to_plain8(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat_base, uint8_t* ok,
+                            cudaStream_t stream) {
+  if (!n_jobs) return;
+  k_delta_to_plain8<<<(n_jobs + 3) / 4, 128, 0, stream>>>(arena, pages, static_cast<const DeltaJob*>(jobs), n_jobs, flat_base, ok);
+  PQB_CUDA(cudaGetLastError());
+}
+
+void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, uint32_t* max_len, cudaStream_t stream) {
   std::vector<EntChunk> ch = column_chunks(t, tcol);
   if (ch.empty()) return;
   DevBuf<EntChunk> d_ch; d_ch.upload(ch, stream);
-  DevBuf<unsigned int> d_err; d_err.alloc(1, stream); d_err.zero();
+  DevBuf<unsigned int> d_err; d_err.alloc(2, stream); d_err.zero();
   k_dict_entry_offsets<<<uint32_t((ch.size() + 3) / 4), 128, 0, stream>>>(t.d_arena, d_ch.p, uint32_t(ch.size()), t.columns[tcol].kind, d_out, d_err.p);
   PQB_CUDA(cudaGetLastError());
-  unsigned int err = 0;
-  PQB_CUDA(cudaMemcpyAsync(&err, d_err.p, 4, cudaMemcpyDeviceToHost, stream));
+  unsigned int errs[2] = {0, 0};
+  PQB_CUDA(cudaMemcpyAsync(errs, d_err.p, 8, cudaMemcpyDeviceToHost, stream));
   PQB_CUDA(cudaStreamSynchronize(stream));
+  const unsigned int err = errs[0];
+  if (max_len) *max_len = t.columns[tcol].kind == DK_STR ? errs[1] : 8u;
   if (err) throw Error(PQ_ERR_CORRUPT, "column '" + t.columns[tcol].name + "': a string dictionary page runs past its end");
 }
 
@@ -564,6 +573,12 @@ void Query::run(const PqQueryDesc& d) {
     if (d.aggs[a].col < 0 || uint32_t(d.aggs[a].col) >= d.n_columns) throw Error(PQ_ERR_INVALID_ARG, "aggregate column out of range");
     col_used[d.aggs[a].col] = true;
   }
+  std::vector<bool> col_staged = col_used;   // predicate / key / aggregate inputs: staged per slab by the flat kernels
+  const bool want_rows = d.n_aggs == 0 && !(d.flags & PQ_QUERY_COUNT_ONLY);
+  for (uint32_t i = 0; want_rows && i < d.n_projection; i++) {
+    if (d.projection[i] < 0 || uint32_t(d.projection[i]) >= d.n_columns) throw Error(PQ_ERR_INVALID_ARG, "projection column out of range");
+    col_used[d.projection[i]] = true;        // only gathered for the selected rows
+  }
   // compact to kernel column slots
   std::vector<int> slot_of(d.n_columns, -1);
   std::vector<uint32_t> qcol_of_slot;
@@ -577,7 +592,13 @@ void Query::run(const PqQueryDesc& d) {
     plan.ncols = ncols;
   }
   std::vector<int> shape_cols(ncols);
-  for (uint32_t s = 0; s < ncols; s++) shape_cols[s] = tcol[qcol_of_slot[s]];
+  for (uint32_t s = 0; s < ncols; s++) {
+    shape_cols[s] = tcol[qcol_of_slot[s]];
+    plan.cols[s].staged = col_staged[qcol_of_slot[s]] ? 1 : 0;
+    // the VALUES of a DELTA_BINARY_PACKED column are needed (a range that cuts row groups, a projection of
+    // p_timestamp): its pages get row-addressable 8-byte copies, once per table
+    if (table->sides[shape_cols[s]].has_delta) table->ensure_plain8(shape_cols[s], stream);
+  }
   std::shared_ptr<Shape> shape = table->shape_for(shape_cols, stream);
   const std::vector<DevItem>& items = shape->items;
 
@@ -903,6 +924,7 @@ void Query::run(const PqQueryDesc& d) {
       uint32_t off = 0;
       for (uint32_t s = 0; s < ncols; s++) {
         FL.col_off[s] = off;
+        if (!plan.cols[s].staged) continue;
         const uint32_t cap = std::max<uint32_t>(shape->flat_plain8[s] ? S * 8 : 0, (S * shape->flat_max_bw[s] + 7) / 8);
         off += align_up(cap + 48, 128);   // + the bit phase of a piece that starts inside a page, + over-read slack
       }
@@ -996,9 +1018,10 @@ void Query::run(const PqQueryDesc& d) {
   if (smem_total > ctx.smem_optin()) throw Error(PQ_ERR_UNSUPPORTED, "query needs more shared memory than one SM has");
 
   // ---- selection bitmap / counts ----
-  const bool want_rows = !has_aggs && !(d.flags & PQ_QUERY_COUNT_ONLY);
-  if (want_rows && d.n_projection && !(d.flags & PQ_QUERY_EMIT_ROW_IDS))
-    throw Error(PQ_ERR_UNSUPPORTED, "projection of column values is not on the GPU path yet: ask for PQ_QUERY_EMIT_ROW_IDS or PQ_QUERY_COUNT_ONLY");
+  const bool projecting = want_rows && d.n_projection > 0;
+  if (projecting && n_general)
+    throw Error(PQ_ERR_UNSUPPORTED, "projection of column values needs a flat-store copy of every page it reads: pages with NULLs and PLAIN "
+                                    "(dictionary-fallback) strings are not projected on the GPU yet");
   plan.write_bitmap = want_rows ? 1 : 0;
   DevBuf<uint32_t> d_bitmap, d_item_counts;
   // k_scan ORs partial words into its bitmap regions: they start zeroed.  The flat filter kernel stores
@@ -1295,6 +1318,147 @@ void Query::run(const PqQueryDesc& d) {
     PQB_CUDA(cudaMemcpyAsync(&total, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
     metrics.d2h_bytes += 8 + sizeof(h_counters);
     const unsigned long long lim = d.limit >= 0 ? (unsigned long long)d.limit : ~0ull;
+    if (projecting) {
+      // ---- TableProvider::scan(projection): gather the projected columns of the selected rows ----
+      struct PC { uint32_t qcol; uint32_t slot; uint8_t kind; std::string name; int type; };
+      std::vector<PC> pcs;
+      for (uint32_t i = 0; i < d.n_projection; i++) {
+        const uint32_t qc = uint32_t(d.projection[i]);
+        pcs.push_back({qc, uint32_t(slot_of[qc]), plan.cols[slot_of[qc]].kind, d.columns[qc].name, out_type_of(qc)});
+        if (pcs.back().kind == DK_STR) table->ensure_ent_off(shape_cols[slot_of[qc]], stream);
+      }
+      if (d.flags & PQ_QUERY_EMIT_ROW_IDS) pcs.push_back({0, 0xffffffffu, DK_I64, "__row_id", PQ_T_I64});
+      const uint32_t npc = uint32_t(pcs.size());
+      std::shared_ptr<PinnedBlock> block;
+      ProjArgs pj{};
+      uint64_t nulls_off = 0, copy_bytes = 0;
+      uint32_t nbatches = 0;
+      const uint32_t wpb = (batch_rows + 31) / 32;
+      unsigned long long n_rows = 0;
+      DevBuf<uint8_t> d_block;
+      auto gather = [&](unsigned long long cap) {
+        nbatches = uint32_t((cap + batch_rows - 1) / batch_rows);
+        uint64_t off = 0;
+        auto take = [&](uint64_t bytes) { uint64_t o = off; off = (off + bytes + 63) & ~63ull; return o; };
+        nulls_off = take(uint64_t(npc) * nbatches * 4);
+        for (uint32_t c = 0; c < npc; c++) {
+          ProjCol& pc = pj.cols[c];
+          pc = ProjCol{};
+          pc.slot = pcs[c].slot;
+          pc.kind = pcs[c].kind;
+          pc.valid_off = take(uint64_t(nbatches) * wpb * 4);
+          if (pc.kind == DK_BOOL) pc.val_off = take(uint64_t(nbatches) * wpb * 4);
+          else if (pc.kind == DK_STR) pc.val_off = take((cap + 1) * 4);
+          else pc.val_off = take(cap * 8);
+        }
+        for (uint32_t c = 0; c < npc; c++) {
+          ProjCol& pc = pj.cols[c];
+          if (pc.kind != DK_STR) continue;
+          const ColSide& cs = table->sides[shape_cols[pc.slot]];
+          pc.ent = cs.d_ent_off;
+          const uint64_t bound = cap * uint64_t(cs.max_ent_len);
+          if (bound > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "projected strings of one result exceed 2 GiB: add a LIMIT");
+          pc.data_off = take(bound);
+        }
+        copy_bytes = off;
+        for (uint32_t c = 0; c < npc; c++)
+          if (pj.cols[c].kind == DK_STR) { pj.cols[c].src_off = take(cap * 8); pj.cols[c].len_off = take(cap * 4); }
+        d_block.alloc(off, stream);
+        PQB_CUDA(cudaMemsetAsync(d_block.p, 0, off, stream));
+        pj.arena = table->d_arena;
+        pj.flat = table->d_flat;
+        pj.fpages = table->d_flat_pages;
+        pj.chunks = shape->d_chunks;
+        pj.items = shape->d_items;
+        pj.bitmap = d_bitmap.p;
+        pj.item_counts = d_item_counts.p;
+        pj.item_base = d_item_base.p;
+        pj.out = d_block.p;
+        pj.nulls = reinterpret_cast<uint32_t*>(d_block.p + nulls_off);
+        pj.n_out = cap;
+        pj.n_items = uint32_t(items.size());
+        pj.plan_ncols = ncols;
+        pj.ncols = npc;
+        pj.batch_rows = batch_rows;
+        pj.words_per_batch = wpb;
+        pj.nbatches = nbatches;
+        const uint32_t grid = std::min<uint32_t>(uint32_t(items.size()), uint32_t(ctx.sm_count() * 8));
+        k_project<<<grid, 256, 0, stream>>>(pj);
+        launches++;
+        for (uint32_t c = 0; c < npc; c++) {
+          if (pj.cols[c].kind != DK_STR) continue;
+          // rows beyond the selected total have length 0: the scan over `cap` rows is exact
+          k_offsets_scan<<<1, 1024, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_block.p + pj.cols[c].len_off), uint32_t(cap),
+                                                 reinterpret_cast<int32_t*>(d_block.p + pj.cols[c].val_off));
+          k_project_bytes<<<uint32_t((cap * 32 + 255) / 256), 256, 0, stream>>>(pj, c, cap);
+          launches += 2;
+        }
+        PQB_CUDA(cudaGetLastError());
+        block = std::make_shared<PinnedBlock>();
+        block->p = ctx.pinned_acquire(copy_bytes);
+        block->bytes = copy_bytes;
+        PQB_CUDA(cudaMemcpyAsync(block->p, d_block.p, copy_bytes, cudaMemcpyDeviceToHost, stream));
+      };
+      if (!items.empty()) {
+        const unsigned long long hint = shape->last_total.load();
+        bool done = false;
+        if (hint != ~0ull) {
+          const unsigned long long cap = std::max<unsigned long long>(1, std::min(lim, hint + hint / 8 + 1024));
+          if (cap > 0x7ffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "more than 2^31 projected rows in one result: add a LIMIT");
+          gather(cap);
+          PQB_CUDA(cudaStreamSynchronize(stream));
+          if (std::min(total, lim) <= cap) { done = true; n_rows = std::min(total, lim); metrics.d2h_bytes += copy_bytes; }
+          else block.reset();
+        } else {
+          PQB_CUDA(cudaStreamSynchronize(stream));
+        }
+        if (!done) {
+          const unsigned long long keep = std::min(total, lim);
+          if (keep > 0x7ffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "more than 2^31 projected rows in one result: add a LIMIT");
+          if (keep) {
+            gather(keep);
+            PQB_CUDA(cudaStreamSynchronize(stream));
+            metrics.d2h_bytes += copy_bytes;
+          }
+          n_rows = keep;
+        }
+        shape->last_total.store(total);
+      }
+      PQB_CUDA(cudaEventRecord(t_all.b, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
+      metrics.rows_selected = total;
+      const uint32_t out_batches = n_rows ? uint32_t((n_rows + batch_rows - 1) / batch_rows) : 1u;
+      for (uint32_t b = 0; b < out_batches; b++) {
+        const unsigned long long r0 = uint64_t(b) * batch_rows;
+        const uint32_t nb = n_rows ? uint32_t(std::min<unsigned long long>(batch_rows, n_rows - r0)) : 0u;
+        OutBatch ob;
+        ob.rows = nb;
+        for (uint32_t c = 0; c < npc; c++) {
+          OutColumn oc;
+          oc.name = pcs[c].name;
+          oc.type = pcs[c].type;
+          if (nb) {
+            const ProjCol& pc = pj.cols[c];
+            oc.ext = block;
+            oc.ext_all = true;
+            oc.null_count = 0;   // flat pages hold no NULLs
+            oc.ext_validity_off = pc.valid_off + uint64_t(b) * wpb * 4;
+            if (pc.kind == DK_STR) { oc.ext_offsets_off = pc.val_off + r0 * 4; oc.ext_off = pc.data_off; }
+            else if (pc.kind == DK_BOOL) oc.ext_off = pc.val_off + uint64_t(b) * wpb * 4;
+            else oc.ext_off = pc.val_off + r0 * 8;
+          } else if (oc.type == PQ_T_UTF8) oc.offsets.assign(1, 0);
+          ob.cols.push_back(std::move(oc));
+        }
+        batches_.push_back(std::move(ob));
+      }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t_all.a, t_all.b);
+      metrics.device_ms = ms;
+      if (!items.empty() && nrg) { cudaEventElapsedTime(&ms, t_scan.a, t_scan.b); metrics.scan_kernel_ms = ms; }
+      metrics.kernel_launches = launches;
+      return;
+    }
     if (want_rows && !items.empty()) {
       unsigned long long hint = shape->last_total.load();
       bool done = false;

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -221,6 +222,7 @@ Table::~Table() {
     if (cs.d_ent_off) cudaFreeAsync(cs.d_ent_off, cudaStreamPerThread);
     if (cs.d_gid) cudaFreeAsync(cs.d_gid, cudaStreamPerThread);
     if (cs.d_key_hash) cudaFreeAsync(cs.d_key_hash, cudaStreamPerThread);
+    if (cs.d_delta_flat) cudaFreeAsync(cs.d_delta_flat, cudaStreamPerThread);
     if (cs.d_kd_offs) cudaFreeAsync(cs.d_kd_offs, cudaStreamPerThread);
     if (cs.d_kd_bytes) cudaFreeAsync(cs.d_kd_bytes, cudaStreamPerThread);
   }
@@ -258,6 +260,14 @@ static uint32_t rd_u32(const uint8_t* p) {
 void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std::string>& col_names,
                  uint32_t shard_index, uint32_t shard_count, cudaStream_t stream) {
   Context& ctx = Context::get();
+  const auto t_open = std::chrono::steady_clock::now();
+  const bool verbose = getenv("PQB_VERBOSE") && getenv("PQB_VERBOSE")[0] == '2';
+  auto mark = [&](const char* what) {
+    if (verbose) {
+      cudaStreamSynchronize(stream);
+      fprintf(stderr, "[pqb] table open +%.3f ms %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_open).count(), what);
+    }
+  };
   if (shard_count == 0) shard_count = 1;
   if (shard_index >= shard_count) throw Error(PQ_ERR_INVALID_ARG, "shard_index >= shard_count");
   // footers are parsed on a few host threads (one Parquet file per ingest minute: many small footers)
@@ -508,6 +518,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   for (size_t c = 0; c < columns.size(); c++)
     if (columns[c].kind == 0xff) columns[c].kind = 0xfe;  // present in no file: all NULL everywhere
 
+  mark("footers parsed, chunks planned");
   // ---- one HBM arena, 64 KiB of slack so staged windows may over-read ----
   arena_bytes = arena + (64u << 10);
   PQB_CUDA(cudaMallocAsync((void**)&d_arena, arena_bytes, stream));
@@ -526,8 +537,10 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   // mapped host memory directly) instead of hundreds of cudaMemcpyAsync calls
   std::vector<GatherCopy> gathers;
   std::vector<const uint8_t*> file_dev(files.size(), nullptr);  // device-visible alias of a page-locked image
+  const char* upl = getenv("PQB_UPLOAD");   // experiment switch: "memcpy" = one cudaMemcpyAsync per chunk (copy engines) instead of the gather kernel
+  const bool use_gather = !(upl && upl[0] == 'm');
   for (size_t f = 0; f < files.size(); f++) {
-    if (!file_pinned[f]) continue;
+    if (!file_pinned[f] || !use_gather) continue;
     void* dp = nullptr;
     if (cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(files[f]->data), 0) == cudaSuccess && dp &&
         ((uintptr_t(dp) ^ uintptr_t(files[f]->data)) & 15) == 0)
@@ -617,6 +630,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   };
   upload_to(copies, d_arena);
   if (!ccopies.empty()) upload_to(ccopies, d_comp);
+  mark("uploads queued (synchronised for this mark)");
   DecompJob* d_djobs = nullptr;
   unsigned long long* d_dflag = nullptr;
   if (!djobs.empty()) {
@@ -668,6 +682,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     }
     if (total_slabs > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "too many slabs for one table");
   }
+  mark("page headers walked");
   if (!pages.empty()) {
     PQB_CUDA(cudaMallocAsync((void**)&d_pages, pages.size() * sizeof(DevPage), stream));
     PQB_CUDA(cudaMemcpyAsync(d_pages, pages.data(), pages.size() * sizeof(DevPage), cudaMemcpyHostToDevice, stream));
@@ -785,13 +800,15 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     for (size_t g = 0; g < row_groups.size(); g++) {
       cs.base_per_rg[g] = uint32_t(tot);
       const TableChunk& tc = row_groups[g].chunks[c];
-      if (tc.present) { tot += tc.dict_n; cs.max_dict_n = std::max(cs.max_dict_n, tc.dict_n); }
+      if (tc.present) { tot += tc.dict_n; cs.max_dict_n = std::max(cs.max_dict_n, tc.dict_n); cs.has_delta |= tc.has_delta_pages; }
       if (tot > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "too many dictionary entries in column '" + columns[c].name + "'");
     }
     cs.total_entries = uint32_t(tot);
   }
+  mark("before flat store");
   build_flat_store(stream);
   PQB_CUDA(cudaStreamSynchronize(stream));
+  mark("flat store built");
 }
 
 // ---- flat store ----------------------------------------------------------------------------------
@@ -1023,8 +1040,58 @@ void Table::ensure_ent_off(int tcol, cudaStream_t stream) const {
   ColSide& cs = sides[tcol];
   if (cs.ent_ready) return;
   PQB_CUDA(cudaMallocAsync((void**)&cs.d_ent_off, std::max<uint64_t>(cs.total_entries, 1) * 8, stream));
-  launch_entry_offsets(*this, tcol, cs.d_ent_off, stream);   // synchronises: later queries run on other streams
+  launch_entry_offsets(*this, tcol, cs.d_ent_off, &cs.max_ent_len, stream);   // synchronises: later queries run on other streams
   cs.ent_ready = true;
+}
+
+void Table::ensure_plain8(int tcol, cudaStream_t stream) const {
+  std::lock_guard<std::mutex> lk(side_mu);
+  ColSide& cs = sides[tcol];
+  if (cs.delta_ready || !cs.has_delta) return;
+  const char* sw = getenv("PQB_FLAT");
+  if (sw && sw[0] == '0') { cs.delta_ready = true; return; }
+  struct Job { uint32_t page, pad; uint64_t dst; };   // == DeltaJob
+  std::vector<Job> jobs;
+  uint64_t off = 0;
+  if (flat_pages.size() != pages.size()) flat_pages.assign(pages.size(), FlatPageRec{});
+  for (const TableRowGroup& rg : row_groups) {
+    const TableChunk& tc = rg.chunks[tcol];
+    if (!tc.present) continue;
+    for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
+      const uint32_t pi = tc.pages.first_page + k;
+      if (pages[pi].enc != DE_DELTA || flat_pages[pi].fkind != FK_NONE) continue;
+      jobs.push_back({pi, 0u, off});
+      off = (off + uint64_t(pages[pi].num_rows) * 8 + 16 + 15) & ~15ull;
+    }
+  }
+  if (!jobs.empty()) {
+    PQB_CUDA(cudaMallocAsync((void**)&cs.d_delta_flat, off + 256, stream));
+    void* d_jobs = nullptr;
+    uint8_t* d_ok = nullptr;
+    PQB_CUDA(cudaMallocAsync(&d_jobs, jobs.size() * sizeof(Job), stream));
+    PQB_CUDA(cudaMallocAsync((void**)&d_ok, jobs.size(), stream));
+    PQB_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream));
+    launch_delta_to_plain8(d_arena, d_pages, d_jobs, uint32_t(jobs.size()), cs.d_delta_flat, d_ok, stream);
+    std::vector<uint8_t> ok(jobs.size());
+    PQB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, ok.size(), cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    PQB_CUDA(cudaFreeAsync(d_jobs, stream));
+    PQB_CUDA(cudaFreeAsync(d_ok, stream));
+    for (size_t i = 0; i < jobs.size(); i++) {
+      if (!ok[i]) continue;   // NULLs in the page: it stays with k_scan
+      FlatPageRec& fr = flat_pages[jobs[i].page];
+      // offsets are relative to d_flat (the kernels add them to that one base); the subtraction may wrap, the sum does not
+      fr.off = uint64_t(cs.d_delta_flat + jobs[i].dst) - uint64_t(d_flat);
+      fr.rows = pages[jobs[i].page].num_rows;
+      fr.bw = 64;
+      fr.fkind = FK_PLAIN8;
+    }
+    if (!d_flat_pages) PQB_CUDA(cudaMallocAsync((void**)&d_flat_pages, flat_pages.size() * sizeof(FlatPageRec), stream));
+    PQB_CUDA(cudaMemcpyAsync(d_flat_pages, flat_pages.data(), flat_pages.size() * sizeof(FlatPageRec), cudaMemcpyHostToDevice, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    shapes.clear();   // column sets with this column get new work items (flat now)
+  }
+  cs.delta_ready = true;
 }
 
 void Table::ensure_key(int tcol, cudaStream_t stream) const {

@@ -308,9 +308,14 @@ class StandardTableProvider:
 
     # -- TableProvider::scan -------------------------------------------------
     def scan(self, projection: Sequence[str] | None = None, filters: Iterable[Expr] = (), limit: int | None = None,
-             count_only: bool = False, row_ids: bool = True, batch_size: int = 0, flags: int = 0,
+             count_only: bool = False, row_ids: bool | None = None, batch_size: int = 0, flags: int = 0,
              poll: bool = False) -> QueryResult:
+        """``projection``: the columns to return for the selected rows (TableProvider::scan's projection);
+        without one the scan returns the selected row ordinals (``__row_id``).  ``row_ids=True`` appends
+        ``__row_id`` to a projection."""
         f = 0
+        if row_ids is None:
+            row_ids = not projection
         if count_only:
             f |= L.PQ_QUERY_COUNT_ONLY
         elif row_ids:
@@ -418,7 +423,7 @@ class Query:
         self._parse(sql)
 
     # --- tokenizer / parser ---
-    _TOK = re.compile(r"\s*(?:(\d+\.\d+(?:[eE][-+]?\d+)?|\d+)|'((?:[^']|'')*)'|\"([^\"]+)\"|([A-Za-z_][A-Za-z_0-9]*)|(<=|>=|<>|!=|[=<>(),*]))")
+    _TOK = re.compile(r"\s*(?:(-?\d+\.\d+(?:[eE][-+]?\d+)?|-?\d+)|'((?:[^']|'')*)'|\"([^\"]+)\"|([A-Za-z_][A-Za-z_0-9]*)|(<=|>=|<>|!=|[=<>(),*]))")
 
     def _parse(self, sql: str):
         toks, pos = [], 0
@@ -498,13 +503,11 @@ class Query:
             else:
                 item = Agg(t[1].lower(), self._next("id")[1])
             self._expect("op", ")")
-            if self._accept("kw", "AS"):
-                self._next("id")
-            return ("agg", item)
+            alias = self._next("id")[1] if self._accept("kw", "AS") else None
+            return ("agg", item, alias)
         name = self._next("id")[1]
-        if self._accept("kw", "AS"):
-            self._next("id")
-        return ("col", name)
+        alias = self._next("id")[1] if self._accept("kw", "AS") else None
+        return ("col", name, alias)
 
     def _or(self):
         e = self._and()
@@ -561,7 +564,9 @@ class Query:
                 self._i += 1
                 p = self._next("str")[1]
                 if self._accept("kw", "ESCAPE"):
-                    self._next("str")
+                    esc = self._next("str")[1]
+                    if esc != "\\":     # the matcher's escape character is the backslash (arrow-string's default)
+                        raise QueryError(L.PQ_ERR_UNSUPPORTED, f"LIKE ... ESCAPE {esc!r}: only the backslash is supported")
                 return a.like(p, negated=neg, case_insensitive=(t[1] == "ILIKE"))
         raise QueryError(L.PQ_ERR_UNSUPPORTED, f"unsupported predicate near {self._peek()!r}")
 
@@ -593,12 +598,43 @@ def execute(query: Query, provider: StandardTableProvider, is_streaming: bool = 
     reference hands batches over (Vec vs stream); the batches are the same."""
     aggs = [it[1] for it in query.select if it[0] == "agg"]
     cols = [it[1] for it in query.select if it[0] == "col"]
+    star = any(it[0] == "star" for it in query.select)
     filters = query.final_filters()
     if aggs:
+        if star:
+            raise QueryError(L.PQ_ERR_INVALID_ARG, "SELECT * next to an aggregate")
         extra = [c for c in cols if c not in query.group_by]
         if extra:
             raise QueryError(L.PQ_ERR_INVALID_ARG, f"column {extra[0]} must appear in GROUP BY")
-        return provider.aggregate(query.group_by, aggs, filters)
+        res = provider.aggregate(query.group_by, aggs, filters)
+        # output columns in SELECT order under their aliases; LIMIT applies to the groups
+        if res.batches:
+            t = res.table()
+            names, picked = [], []
+            for it in query.select:
+                if it[0] == "col":
+                    src = it[1]
+                else:
+                    a = it[1]
+                    src = "count(*)" if a.fn == "count_star" else f"{a.fn}({a.column})"
+                picked.append(t.column(src))
+                names.append(it[2] or src)
+            t = pa.table(picked, names=names)
+            if query.limit is not None:
+                t = t.slice(0, query.limit)
+            res.batches = t.to_batches(max_chunksize=20000) or res.batches[:1]
+            res.fields = names
+        return res
     if query.group_by:
         raise QueryError(L.PQ_ERR_UNSUPPORTED, "GROUP BY without aggregates")
-    return provider.scan(cols, filters, query.limit)
+    if star:
+        if not provider.schema:
+            raise QueryError(L.PQ_ERR_INVALID_ARG, "SELECT * needs the table schema")
+        cols = list(provider.schema.keys())
+    res = provider.scan(cols, filters, query.limit)
+    aliases = {it[1]: it[2] for it in query.select if it[0] == "col" and it[2]}
+    if aliases and res.batches:
+        names = [aliases.get(n, n) for n in res.batches[0].schema.names]
+        res.batches = [b.rename_columns(names) for b in res.batches]
+        res.fields = names
+    return res

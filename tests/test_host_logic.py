@@ -67,7 +67,8 @@ def test_sql_subset_parses_like_the_reference_queries():
     assert ops[2].lit.str[:7] == b"%can't%"                      # '' unescapes to '
     assert d.columns == ["level", "status", "message", "cpu"]
     assert Query("select count(*) from t where x <> 1.5e3").where.args[1].args[0] == 1500.0
-    assert Query('SELECT "weird col" FROM t').select == [("col", "weird col")]
+    assert Query('SELECT "weird col" FROM t').select == [("col", "weird col", None)]
+    assert Query('SELECT a AS x, SUM(b) AS s FROM t WHERE c > -3 GROUP BY a').select[1][2] == "s"
 
 
 @pytest.mark.parametrize("sql", ["SELECT a FROM t ORDER BY a", "SELECT a FROM t WHERE a BETWEEN 1 AND 2", "SELECT FROM t",
