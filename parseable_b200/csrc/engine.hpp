@@ -125,7 +125,15 @@ struct ColSide {
   uint32_t* d_kd_offs = nullptr;       // the same on the device (result assembly)
   uint8_t* d_kd_bytes = nullptr;
   uint32_t kd_max_len = 0;
-  uint64_t* d_key_hash = nullptr;      // 64-bit hash of every distinct value, group-id order (multi-GPU unification)
+  // multi-GPU: the numbering every rank of the communicator agreed on (unify_key), tagged with the communicator's epoch
+  bool glob_ready = false;
+  uint64_t glob_epoch = 0;
+  uint32_t glob_card = 0, glob_max_len = 0;
+  KeyDict glob_kd;
+  uint32_t* d_glob_gid = nullptr;
+  uint32_t* d_glob_kd_offs = nullptr;
+  uint8_t* d_glob_kd_bytes = nullptr;
+  uint64_t* d_key_hash = nullptr;
 };
 
 // What a query needs per SET of referenced columns, built once per (table, column set): the chunk
@@ -188,6 +196,7 @@ class Table {
   std::shared_ptr<Shape> shape_for(const std::vector<int>& tcols, cudaStream_t stream) const;
   void ensure_ent_off(int tcol, cudaStream_t stream) const;
   void ensure_key(int tcol, cudaStream_t stream) const;
+  void unify_key(int tcol, cudaStream_t stream) const;        // collective over the pq_comm communicator
   void ensure_plain8(int tcol, cudaStream_t stream) const;   // DELTA_BINARY_PACKED pages -> row-addressable 8-byte values
 
  private:
@@ -209,6 +218,7 @@ void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, uint32_t* m
 void launch_delta_to_plain8(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat_base, uint8_t* ok,
                             cudaStream_t stream);
 void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream);
+void unify_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream);
 
 // page-locked host block that result batches can alias (zero copy); returns to the pool when
 // the last batch that references it is released by the consumer

@@ -362,6 +362,81 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
   }
 }
 
+// Collective: every rank of the communicator calls it for the same key column at the same time.
+void unify_key_side(const Table& t, int tcol, ColSide& cs, cudaStream_t stream) {
+  const KeyDict& loc = cs.kd;
+  const uint32_t card_l = cs.card;
+  const int nr = comm_nranks(), me = comm_rank();
+  std::vector<unsigned long long> sizes(size_t(nr) * 2);
+  {
+    unsigned long long mine[2] = {card_l, loc.bytes.size()};
+    DevBuf<unsigned long long> dsend, drecv;
+    dsend.alloc(2, stream);
+    drecv.alloc(size_t(nr) * 2, stream);
+    PQB_CUDA(cudaMemcpyAsync(dsend.p, mine, 16, cudaMemcpyHostToDevice, stream));
+    comm_allgather_bytes(dsend.p, drecv.p, 16, stream);
+    PQB_CUDA(cudaMemcpyAsync(sizes.data(), drecv.p, size_t(nr) * 16, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+  }
+  unsigned long long cardmax = 0, bytesmax = 0;
+  for (int r = 0; r < nr; r++) { cardmax = std::max(cardmax, sizes[2 * r]); bytesmax = std::max(bytesmax, sizes[2 * r + 1]); }
+  const size_t per_rank = ((4 * (cardmax + 1) + bytesmax) + 15) & ~size_t(15);
+  std::vector<uint8_t> sendbuf(per_rank, 0), recvbuf(per_rank * nr);
+  std::memcpy(sendbuf.data(), loc.offs.data(), loc.offs.size() * 4);
+  if (!loc.bytes.empty()) std::memcpy(sendbuf.data() + 4 * (cardmax + 1), loc.bytes.data(), loc.bytes.size());
+  {
+    DevBuf<uint8_t> dsend, drecv;
+    dsend.upload(sendbuf, stream);
+    drecv.alloc(per_rank * nr, stream);
+    comm_allgather_bytes(dsend.p, drecv.p, per_rank, stream);
+    PQB_CUDA(cudaMemcpyAsync(recvbuf.data(), drecv.p, per_rank * nr, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+  }
+  std::map<std::string, uint32_t> ids;  // identical content + identical insertion order on every rank
+  std::vector<uint32_t> remap(std::max<uint32_t>(card_l, 1), 0);
+  KeyDict& glob = cs.glob_kd;
+  glob.offs.assign(1, 0);
+  glob.bytes.clear();
+  for (int r = 0; r < nr; r++) {
+    const uint8_t* base = recvbuf.data() + per_rank * r;
+    const uint32_t* offs = reinterpret_cast<const uint32_t*>(base);
+    const uint8_t* bytes = base + 4 * (cardmax + 1);
+    for (unsigned long long i = 0; i < sizes[2 * r]; i++) {
+      std::string v(reinterpret_cast<const char*>(bytes + offs[i]), offs[i + 1] - offs[i]);
+      auto it = ids.find(v);
+      if (it == ids.end()) {
+        it = ids.emplace(v, uint32_t(ids.size())).first;
+        glob.bytes.insert(glob.bytes.end(), v.begin(), v.end());
+        glob.offs.push_back(uint32_t(glob.bytes.size()));
+      }
+      if (r == me) remap[i] = it->second;
+    }
+  }
+  cs.glob_card = uint32_t(ids.size());
+  auto renew = [&](auto*& p, size_t bytes) {
+    if (p) PQB_CUDA(cudaFreeAsync(p, stream));
+    p = nullptr;
+    PQB_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(bytes, 16), stream));
+  };
+  renew(cs.d_glob_gid, size_t(cs.total_entries) * 4);
+  renew(cs.d_glob_kd_offs, glob.offs.size() * 4);
+  renew(cs.d_glob_kd_bytes, glob.bytes.size());
+  PQB_CUDA(cudaMemcpyAsync(cs.d_glob_kd_offs, glob.offs.data(), glob.offs.size() * 4, cudaMemcpyHostToDevice, stream));
+  if (!glob.bytes.empty()) PQB_CUDA(cudaMemcpyAsync(cs.d_glob_kd_bytes, glob.bytes.data(), glob.bytes.size(), cudaMemcpyHostToDevice, stream));
+  cs.glob_max_len = 0;
+  for (size_t g = 0; g + 1 < glob.offs.size(); g++) cs.glob_max_len = std::max(cs.glob_max_len, glob.offs[g + 1] - glob.offs[g]);
+  if (card_l && cs.total_entries) {
+    DevBuf<uint32_t> dremap;
+    dremap.upload(remap, stream);
+    k_gid_remap<<<std::min<uint32_t>(1024, (cs.total_entries + 255) / 256), 256, 0, stream>>>(cs.d_gid, cs.d_glob_gid, cs.total_entries, dremap.p, card_l);
+    PQB_CUDA(cudaGetLastError());
+  }
+  PQB_CUDA(cudaStreamSynchronize(stream));
+  (void)t; (void)tcol;
+  cs.glob_epoch = comm_epoch();
+  cs.glob_ready = true;
+}
+
 void Query::run(const PqQueryDesc& d) {
   const auto t_begin = std::chrono::steady_clock::now();
   const char* vb = getenv("PQB_VERBOSE"); const bool verbose = vb && vb[0] && vb[0] != '0';
@@ -771,8 +846,6 @@ void Query::run(const PqQueryDesc& d) {
   // ---- GROUP BY keys: interned per table column (cached with the table) ----
   struct QKey { const KeyDict* kd = nullptr; uint32_t card = 0; };
   std::vector<QKey> qk(d.n_group_by);
-  std::vector<std::unique_ptr<DevBuf<uint32_t>>> gid_q(d.n_group_by);   // multi-GPU: per-query globally numbered ids
-  std::vector<KeyDict> glob_kd(d.n_group_by);
   plan.nkeys = d.n_group_by;
   uint64_t launches = 0;
   for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++) {
@@ -789,70 +862,38 @@ void Query::run(const PqQueryDesc& d) {
     key.gid = cs.d_gid;
     qk[k].kd = &cs.kd;
     qk[k].card = cs.card;
-    if (!multi) continue;
-    // ---- multi-GPU: agree on one numbering: all-gather the packed distinct values, number them by
-    // first occurrence in rank order (identical on every rank), remap the local ids ----
-    const KeyDict& loc = cs.kd;
-    const uint32_t card_l = cs.card;
-    const int nr = comm_nranks(), me = comm_rank();
-    std::vector<unsigned long long> sizes(size_t(nr) * 2);
+  }
+  if (multi && d.n_group_by) {
+    // ---- multi-GPU: every rank must use ONE numbering of the key values.  The agreement (all-gather of the
+    // packed distinct values, numbered by first occurrence in rank order: identical on every rank, and hot-first
+    // because rank 0's ids are) is kept with the table column, tagged with the communicator's epoch; one tiny
+    // all-reduce per query checks that EVERY rank still holds it (a rank may have reopened its table) ----
+    uint32_t have = 1;
+    for (uint32_t k = 0; k < d.n_group_by; k++) {
+      if (plan.keys[k].kind == KK_BOOL) continue;
+      const ColSide& cs = table->sides[shape_cols[plan.keys[k].col]];
+      if (!cs.glob_ready || cs.glob_epoch != comm_epoch()) have = 0;
+    }
     {
-      unsigned long long mine[2] = {card_l, loc.bytes.size()};
-      DevBuf<unsigned long long> dsend, drecv;
-      dsend.alloc(2, stream);
-      drecv.alloc(size_t(nr) * 2, stream);
-      PQB_CUDA(cudaMemcpyAsync(dsend.p, mine, 16, cudaMemcpyHostToDevice, stream));
-      comm_allgather_bytes(dsend.p, drecv.p, 16, stream);
-      PQB_CUDA(cudaMemcpyAsync(sizes.data(), drecv.p, size_t(nr) * 16, cudaMemcpyDeviceToHost, stream));
+      DevBuf<unsigned long long> dflag;
+      dflag.alloc(1, stream);
+      unsigned long long f = have;
+      PQB_CUDA(cudaMemcpyAsync(dflag.p, &f, 8, cudaMemcpyHostToDevice, stream));
+      comm_allreduce_u64(dflag.p, 1, 1 /*min*/, stream);
+      PQB_CUDA(cudaMemcpyAsync(&f, dflag.p, 8, cudaMemcpyDeviceToHost, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
+      have = uint32_t(f);
     }
-    unsigned long long cardmax = 0, bytesmax = 0;
-    for (int r = 0; r < nr; r++) { cardmax = std::max(cardmax, sizes[2 * r]); bytesmax = std::max(bytesmax, sizes[2 * r + 1]); }
-    const size_t per_rank = ((4 * (cardmax + 1) + bytesmax) + 15) & ~size_t(15);
-    std::vector<uint8_t> sendbuf(per_rank, 0), recvbuf(per_rank * nr);
-    std::memcpy(sendbuf.data(), loc.offs.data(), loc.offs.size() * 4);
-    if (!loc.bytes.empty()) std::memcpy(sendbuf.data() + 4 * (cardmax + 1), loc.bytes.data(), loc.bytes.size());
-    {
-      DevBuf<uint8_t> dsend, drecv;
-      dsend.upload(sendbuf, stream);
-      drecv.alloc(per_rank * nr, stream);
-      comm_allgather_bytes(dsend.p, drecv.p, per_rank, stream);
-      PQB_CUDA(cudaMemcpyAsync(recvbuf.data(), drecv.p, per_rank * nr, cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaStreamSynchronize(stream));
-      metrics.d2h_bytes += per_rank * nr;
-      metrics.h2d_bytes += per_rank;
+    for (uint32_t k = 0; k < d.n_group_by; k++) {
+      DevKey& key = plan.keys[k];
+      if (key.kind == KK_BOOL) continue;
+      const int tc_i = shape_cols[key.col];
+      if (!have) table->unify_key(tc_i, stream);
+      const ColSide& cs = table->sides[tc_i];
+      key.gid = cs.d_glob_gid;
+      qk[k].kd = &cs.glob_kd;
+      qk[k].card = cs.glob_card;
     }
-    std::map<std::string, uint32_t> ids;  // identical content + identical insertion order on every rank
-    std::vector<uint32_t> remap(std::max<uint32_t>(card_l, 1), 0);
-    KeyDict& glob = glob_kd[k];
-    glob.offs.assign(1, 0);
-    for (int r = 0; r < nr; r++) {
-      const uint8_t* base = recvbuf.data() + per_rank * r;
-      const uint32_t* offs = reinterpret_cast<const uint32_t*>(base);
-      const uint8_t* bytes = base + 4 * (cardmax + 1);
-      for (unsigned long long i = 0; i < sizes[2 * r]; i++) {
-        std::string v(reinterpret_cast<const char*>(bytes + offs[i]), offs[i + 1] - offs[i]);
-        auto it = ids.find(v);
-        if (it == ids.end()) {
-          it = ids.emplace(v, uint32_t(ids.size())).first;
-          glob.bytes.insert(glob.bytes.end(), v.begin(), v.end());
-          glob.offs.push_back(uint32_t(glob.bytes.size()));
-        }
-        if (r == me) remap[i] = it->second;
-      }
-    }
-    gid_q[k] = std::make_unique<DevBuf<uint32_t>>();
-    gid_q[k]->alloc(std::max<uint32_t>(cs.total_entries, 1), stream);
-    if (card_l && cs.total_entries) {
-      DevBuf<uint32_t> dremap;
-      dremap.upload(remap, stream);
-      k_gid_remap<<<std::min<uint32_t>(1024, (cs.total_entries + 255) / 256), 256, 0, stream>>>(cs.d_gid, gid_q[k]->p, cs.total_entries, dremap.p, card_l);
-      launches++;
-      PQB_CUDA(cudaStreamSynchronize(stream));
-    }
-    key.gid = gid_q[k]->p;
-    qk[k].kd = &glob;
-    qk[k].card = uint32_t(ids.size());
   }
   // mixed-radix group slot: the smallest key varies fastest, so that with hot-first ids of the largest key
   // "slot < hot_slots" is "one of the hottest values of the largest key" (flat aggregate kernel)
@@ -1186,8 +1227,6 @@ void Query::run(const PqQueryDesc& d) {
       uint64_t off = 0;
       auto take = [&](uint64_t bytes) { uint64_t o = off; off = (off + bytes + 63) & ~63ull; return o; };
       const uint64_t nulls_off = take(uint64_t(ncolumns) * nbatches * 4);
-      std::vector<DevBuf<uint32_t>> kd_offs_q(d.n_group_by);
-      std::vector<DevBuf<uint8_t>> kd_bytes_q(d.n_group_by);
       for (uint32_t k = 0; k < d.n_group_by; k++) {
         FinishKey& fk = fa.keys[k];
         const uint8_t kind = plan.cols[plan.keys[k].col].kind;
@@ -1200,13 +1239,9 @@ void Query::run(const PqQueryDesc& d) {
         else fk.val_off = take(uint64_t(n_out) * 8);
         if (kind != DK_BOOL) {
           const ColSide& cs = table->sides[shape_cols[plan.keys[k].col]];
-          if (multi) {   // the globally agreed dictionary of this query
-            kd_offs_q[k].upload(qk[k].kd->offs, stream);
-            kd_bytes_q[k].alloc(std::max<size_t>(qk[k].kd->bytes.size(), 1), stream);
-            if (!qk[k].kd->bytes.empty())
-              PQB_CUDA(cudaMemcpyAsync(kd_bytes_q[k].p, qk[k].kd->bytes.data(), qk[k].kd->bytes.size(), cudaMemcpyHostToDevice, stream));
-            fk.kd_offs = kd_offs_q[k].p;
-            fk.kd_bytes = kd_bytes_q[k].p;
+          if (multi) {   // the dictionary every rank agreed on
+            fk.kd_offs = cs.d_glob_kd_offs;
+            fk.kd_bytes = cs.d_glob_kd_bytes;
           } else {
             fk.kd_offs = cs.d_kd_offs;
             fk.kd_bytes = cs.d_kd_bytes;
@@ -1225,8 +1260,7 @@ void Query::run(const PqQueryDesc& d) {
         if (fk.kind != DK_STR) continue;
         uint64_t max_len = 0;
         const KeyDict* kd = qk[k].kd;
-        if (multi) { for (size_t g = 0; g + 1 < kd->offs.size(); g++) max_len = std::max<uint64_t>(max_len, kd->offs[g + 1] - kd->offs[g]); }
-        else max_len = table->sides[shape_cols[plan.keys[k].col]].kd_max_len;
+        max_len = multi ? table->sides[shape_cols[plan.keys[k].col]].glob_max_len : table->sides[shape_cols[plan.keys[k].col]].kd_max_len;
         const uint64_t bound = std::min<uint64_t>(uint64_t(n_out) * max_len, uint64_t(n_out / std::max<uint32_t>(fk.card, 1) + 1) * kd->bytes.size());
         if (bound > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "group key strings of one result exceed 2 GiB");
         fk.data_off = take(bound);

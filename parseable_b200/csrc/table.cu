@@ -222,6 +222,9 @@ Table::~Table() {
     if (cs.d_ent_off) cudaFreeAsync(cs.d_ent_off, cudaStreamPerThread);
     if (cs.d_gid) cudaFreeAsync(cs.d_gid, cudaStreamPerThread);
     if (cs.d_key_hash) cudaFreeAsync(cs.d_key_hash, cudaStreamPerThread);
+    if (cs.d_glob_gid) cudaFreeAsync(cs.d_glob_gid, cudaStreamPerThread);
+    if (cs.d_glob_kd_offs) cudaFreeAsync(cs.d_glob_kd_offs, cudaStreamPerThread);
+    if (cs.d_glob_kd_bytes) cudaFreeAsync(cs.d_glob_kd_bytes, cudaStreamPerThread);
     if (cs.d_delta_flat) cudaFreeAsync(cs.d_delta_flat, cudaStreamPerThread);
     if (cs.d_kd_offs) cudaFreeAsync(cs.d_kd_offs, cudaStreamPerThread);
     if (cs.d_kd_bytes) cudaFreeAsync(cs.d_kd_bytes, cudaStreamPerThread);
@@ -1092,6 +1095,11 @@ void Table::ensure_plain8(int tcol, cudaStream_t stream) const {
     shapes.clear();   // column sets with this column get new work items (flat now)
   }
   cs.delta_ready = true;
+}
+
+void Table::unify_key(int tcol, cudaStream_t stream) const {
+  std::lock_guard<std::mutex> lk(side_mu);
+  unify_key_side(*this, tcol, sides[tcol], stream);
 }
 
 void Table::ensure_key(int tcol, cudaStream_t stream) const {

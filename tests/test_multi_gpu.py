@@ -19,8 +19,14 @@ def test_two_rank_allreduce_matches_oracle(small_files, tmp_path, built):
         pytest.skip("needs 2 GPUs")
     n = 2
     idfile = str(tmp_path / "nccl_id")
+    from parseable_b200 import synth
+    split = []
+    for tag, rate, rg in (("nn", 0.0, 5), ("nulls", 0.02, 7)):     # one row group each: rank 0's shard is NULL-free, rank 1's is not
+        p = str(tmp_path / f"one_{tag}.parquet")
+        synth.write_logs16(p, n_row_groups=1, first_rg=rg, rows_per_group=50_000, null_rate=rate)
+        split.append(p)
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "scripts", "mgpu_check.py"), str(r), str(n), idfile,
-                               small_files["nulls"], small_files["nn"]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                               small_files["nulls"], small_files["nn"], "--"] + split, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(n)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
