@@ -60,7 +60,8 @@ struct DevChunk {              // one column chunk (row group x referenced colum
 // Flat store (flat_store.cuh): the scan-ready copy of one data page.
 enum FlatKind : uint8_t { FK_NONE = 0, FK_INDEX = 1, FK_PLAIN8 = 2, FK_BITS = 3 };
 struct FlatPageRec {           // parallel to pages[]
-  uint64_t off;                // byte offset in the flat buffer, 16-byte aligned
+  uint64_t off;                // byte offset in the flat buffer, 16-byte aligned: one slot per ROW (NULL rows hold 0)
+  uint64_t voff;               // validity bitmap (1 bit per row, LSB first like Arrow), or ~0: the page holds no NULLs
   uint32_t rows;
   uint8_t bw;                  // FK_INDEX: bits per dictionary index; FK_BITS: 1
   uint8_t fkind;               // FlatKind: FK_INDEX dictionary indices, FK_PLAIN8 8-byte values, FK_BITS boolean values
@@ -77,7 +78,7 @@ struct DevItem {               // unit of CTA work: rows between two page bounda
   uint32_t poff[kMaxCols];     // flat items: row0 minus the page's first row (a piece may start inside a page)
   uint32_t fast;               // bit 0: every referenced column has exactly one, slab-indexed page over this item (k_scan);
                                // bit 1: ... exactly one page with a flat-store copy (k_flat_*)
-  uint32_t _pad;
+  uint32_t absent;             // flat items: bit s = column slot s is missing from this file (reads as all NULL)
 };
 constexpr uint32_t kItemSlabIndexed = 1u, kItemFlat = 2u;
 

@@ -261,9 +261,17 @@ __global__ void __launch_bounds__(256) k_project(const __grid_constant__ ProjArg
               reinterpret_cast<unsigned long long*>(f.out + pc.val_off)[pos] = item.global_row0 + r;
               continue;
             }
+            if ((item.absent >> pc.slot) & 1u) {   // column missing from this file: NULL
+              atomicAdd(&f.nulls[ci * f.nbatches + batch], 1u);
+              continue;
+            }
             const FlatPageRec fp = f.fpages[item.page[pc.slot]];
             const uint64_t row = uint64_t(item.poff[pc.slot]) + r;
-            atomicOr(reinterpret_cast<uint32_t*>(f.out + pc.valid_off) + vword, vbit);   // flat pages hold no NULLs
+            if (fp.voff != ~0ull && !((reinterpret_cast<const uint32_t*>(f.flat + fp.voff)[row >> 5] >> (row & 31)) & 1u)) {
+              atomicAdd(&f.nulls[ci * f.nbatches + batch], 1u);   // NULL row: value slot stays 0, string length 0
+              continue;
+            }
+            atomicOr(reinterpret_cast<uint32_t*>(f.out + pc.valid_off) + vword, vbit);
             if (fp.fkind == FK_PLAIN8) {
               reinterpret_cast<unsigned long long*>(f.out + pc.val_off)[pos] = reinterpret_cast<const unsigned long long*>(f.flat + fp.off)[row];
             } else if (fp.fkind == FK_BITS) {

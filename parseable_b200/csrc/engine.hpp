@@ -147,7 +147,7 @@ struct Shape {
   uint32_t n_flat = 0, n_general = 0, n_slab_fast = 0;
   uint32_t bitmap_words = 0;
   std::vector<uint32_t> max_bw, flat_max_bw;          // per slot
-  std::vector<uint8_t> has_dict, has_plain, has_delta, flat_plain8;
+  std::vector<uint8_t> has_dict, has_plain, has_delta, flat_plain8, flat_nullable;   // flat_nullable: some flat page of the slot carries a validity bitmap
   std::atomic<unsigned long long> last_total{~0ull};   // rows the last filter scan of this shape selected (sizes the next result)
   ~Shape();
 };
@@ -215,6 +215,7 @@ void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* j
                        cudaStream_t stream);
 // side-table builders (prep_kernels.cuh), defined in query.cu
 void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, uint32_t* max_len, cudaStream_t stream);
+void launch_page_has_nulls(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, uint8_t* out, cudaStream_t stream);
 void launch_delta_to_plain8(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat_base, uint8_t* ok,
                             cudaStream_t stream);
 void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream);

@@ -2,8 +2,9 @@
 // flat store (flat_store.cuh).  Same operator chain of the reference as k_scan
 //   DataSourceExec(Parquet) -> FilterExec -> AggregateExec(Partial)
 // (/root/reference/src/query/mod.rs:287), for the common case: every
-// referenced column of a work item has one NULL-free page with a flat copy.  Items that do not
-// qualify (NULLs, DELTA pages the time range cuts, PLAIN strings) stay with k_scan.
+// referenced column of a work item has pages with a flat copy (pages with NULLs carry a validity
+// bitmap and one slot per ROW; a column missing from a file reads as all NULL).  Items that do not
+// qualify (PLAIN strings, streams the flattener refused) stay with k_scan.
 //
 // Shape (both kernels): persistent CTAs, one PRODUCER warp and N consumer warps.  The producer's
 // elected lane pulls work items from the queue, and for every slab of an item stages the slab's
@@ -45,11 +46,13 @@ struct FlatLayout {              // dynamic shared memory of the flat kernels (b
   uint32_t nstages;
   uint32_t stage_bytes;
   uint32_t stage0;               // first stage buffer
-  uint32_t col_off[kMaxCols];    // column c inside a stage (16-byte aligned)
+  uint32_t col_off[kMaxCols];    // values of column c inside a stage (16-byte aligned)
+  uint32_t col_voff[kMaxCols];   // validity bits of column c inside a stage (columns that may hold NULLs)
   uint32_t acc;                  // hot accumulator table (k_flat_agg)
   uint32_t total;
 };
 
+constexpr uint32_t kColHasValid = 1u, kColAbsent = 2u;
 struct FlatStageCol {
   uint64_t dict8;                // flat-store offset of the aligned numeric dictionary (~0: none)
   uint32_t bw;                   // bits per value (FK_PLAIN8: 64, FK_BITS: 1)
@@ -57,7 +60,10 @@ struct FlatStageCol {
   uint32_t lut_base;
   uint32_t dict_n;
   uint32_t phase;                // bit of the staged bytes where row 0 of the slab starts (a piece may start inside a
-  uint32_t _pad;                 // page at a row that is not a multiple of 128: the copy starts at the 16 bytes below)
+                                 // page at a row that is not a multiple of 128: the copy starts at the 16 bytes below)
+  uint32_t vphase;               // the same for the validity bits
+  uint32_t flags;                // kColHasValid: the page holds NULLs (validity staged); kColAbsent: column missing from the file
+  uint32_t _pad;
 };
 struct FlatStage {
   uint32_t item;                 // 0xffffffff: the queue is empty, consumers leave
@@ -101,18 +107,24 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
     if (a.rg_live && !a.rg_live[rg]) continue;
     // lane c looks after column slot c
     FlatStageCol mycol{};
-    uint64_t mysrc = 0;
+    uint64_t mysrc = 0, myvsrc = 0;
     uint32_t mypoff = 0;
     if (lane < ncols) {
       const DevChunk& ch = a.chunks[rg * ncols + lane];
-      const FlatPageRec fp = a.fpages[item.page[lane]];
       mycol.dict8 = ch.dict8_off;
-      mycol.bw = fp.bw;
-      mycol.fkind = fp.fkind;
       mycol.lut_base = ch.lut_base;
       mycol.dict_n = ch.dict_n;
-      mysrc = fp.off;
-      mypoff = item.poff[lane];
+      if ((item.absent >> lane) & 1u) {
+        mycol.flags = kColAbsent;
+        mycol.fkind = FK_NONE;
+      } else {
+        const FlatPageRec fp = a.fpages[item.page[lane]];
+        mycol.bw = fp.bw;
+        mycol.fkind = fp.fkind;
+        mysrc = fp.off;
+        mypoff = item.poff[lane];
+        if (fp.voff != ~0ull) { mycol.flags = kColHasValid; myvsrc = fp.voff; }
+      }
     }
     // register LUTs of this item's row group: every lane fetches one LUT byte, one ballot per leaf
     uint32_t regmask = 0, mylut = 0;
@@ -128,19 +140,22 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
       regmask |= 1u << l;
     }
     const uint32_t nrows = item.nrows, bm0 = item.bitmap_word0;
+    const bool staged = lane < ncols && plan.cols[lane].staged && !(mycol.flags & kColAbsent);
     for (uint32_t r0 = 0; r0 < nrows; r0 += S) {
       const uint32_t R = nrows - r0 < S ? nrows - r0 : S;
       if (lane == 0) mbar_wait_spin(&ctl.empty[stage], par);
       __syncwarp();
       FlatStage& st = ctl.st[stage];
       // first bit of the slab in the page's flat copy; the copy starts at the 16-byte boundary below it
-      const uint64_t bit0 = uint64_t(mypoff + r0) * mycol.bw;
+      const uint64_t bit0 = uint64_t(mypoff + r0) * mycol.bw, vbit0 = uint64_t(mypoff) + r0;
       mycol.phase = uint32_t(bit0 & 127u);
+      mycol.vphase = uint32_t(vbit0 & 127u);
       // a column that is only projected is not staged: the gather after the scan reads its selected rows
-      uint32_t nb = (lane < ncols && plan.cols[lane].staged) ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
+      const uint32_t nb = staged ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
+      const uint32_t vnb = (staged && (mycol.flags & kColHasValid)) ? flat_col_bytes(mycol.vphase, 1, R) : 0u;
       if (lane < ncols) st.col[lane] = mycol;
       if (lane < plan.nleaves) st.lutreg[lane] = mylut;
-      uint32_t bytes = nb;
+      uint32_t bytes = nb + vnb;
       for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
       if (lane == 0) {
         st.item = id;
@@ -152,7 +167,9 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(&ctl.full[stage], bytes);
       __syncwarp();
-      if (nb) tma_load_1d(smem + L.stage0 + stage * L.stage_bytes + L.col_off[lane], a.flat + mysrc + ((bit0 >> 7) << 4), nb, &ctl.full[stage]);
+      uint8_t* base = smem + L.stage0 + stage * L.stage_bytes;
+      if (nb) tma_load_1d(base + L.col_off[lane], a.flat + mysrc + ((bit0 >> 7) << 4), nb, &ctl.full[stage]);
+      if (vnb) tma_load_1d(base + L.col_voff[lane], a.flat + myvsrc + ((vbit0 >> 7) << 4), vnb, &ctl.full[stage]);
       if (++stage == L.nstages) { stage = 0; par ^= 1u; }
     }
   }
@@ -173,39 +190,70 @@ __device__ __forceinline__ void flat_ctl_init(FlatCtl& ctl, uint32_t nstages, ui
   }
 }
 
+// ---- one staged column of the current slab ------------------------------------------------------
+struct ColCtx {
+  const uint32_t* colw;      // values: flat bits / 8-byte slots, whole words of the phase folded in
+  const uint32_t* vw;        // validity bits (nullptr: every row valid, unless `absent`)
+  uint32_t phase, vphase;    // remaining bit phases (0..31) of row 0
+  uint32_t bw, mask, dict_max, fkind;
+  bool absent;               // column missing from this file: every row NULL
+};
+__device__ __forceinline__ void col_ctx(ColCtx& c, const FlatStage& st, const uint8_t* base, const FlatLayout& L, uint32_t col) {
+  const FlatStageCol& sc = st.col[col];
+  c.colw = reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
+  c.phase = sc.phase & 31u;
+  c.vw = (sc.flags & kColHasValid) ? reinterpret_cast<const uint32_t*>(base + L.col_voff[col]) + (sc.vphase >> 5) : nullptr;
+  c.vphase = sc.vphase & 31u;
+  c.bw = sc.bw;
+  c.mask = sc.bw >= 32 ? 0xffffffffu : ((1u << sc.bw) - 1u);
+  c.dict_max = sc.dict_n ? sc.dict_n - 1 : 0u;   // a corrupt index must not leave the LUT (the reference's reader errors out)
+  c.fkind = sc.fkind;
+  c.absent = (sc.flags & kColAbsent) != 0;
+}
+__device__ __forceinline__ uint32_t col_index(const ColCtx& c, uint32_t row) {
+  uint32_t v = bits32_at(c.colw, c.phase + row * c.bw) & c.mask;   // bw == 0: mask == 0
+  return v < c.dict_max ? v : c.dict_max;
+}
+// validity of 32 consecutive rows starting at `row` / of one row
+__device__ __forceinline__ uint32_t col_valid32(const ColCtx& c, uint32_t row) {
+  if (c.absent) return 0u;
+  return c.vw ? bits32_at(c.vw, c.vphase + row) : 0xffffffffu;
+}
+__device__ __forceinline__ bool col_valid(const ColCtx& c, uint32_t row) {
+  if (c.absent) return false;
+  if (!c.vw) return true;
+  const uint32_t b = c.vphase + row;
+  return (c.vw[b >> 5] >> (b & 31)) & 1u;
+}
+
 // ---- leaves -------------------------------------------------------------------------------------
 // Everything a consumer needs about one leaf for the CURRENT slab; built once per slab (warp uniform)
 // so that the row loops below carry no interpretation: the switch on the page kind sits outside them.
+enum LeafMode : uint32_t { LM_FALSE = 0, LM_TRUE = 1, LM_REGLUT = 2, LM_MEMLUT = 3, LM_PLAIN8 = 4, LM_BITS = 5 };
 struct LeafCtx {
-  const uint32_t* colw;      // the column's staged slab (flat bits / 8-byte values), whole words of the phase folded in
+  ColCtx c;
   const uint8_t* lut;        // this leaf's LUT bytes for the chunk (global)
-  uint32_t phase;            // remaining bit phase (0..31) of row 0
-  uint32_t bw, fkind, dict_max;   // dict_max = entries - 1: a corrupt index must not leave the LUT (the reference's reader errors out)
-  uint32_t lutreg;           // reglut: the whole LUT, periodic with 2^bw
-  uint32_t mode;             // LeafMode
+  uint32_t lutreg;           // LM_REGLUT: the whole LUT, periodic with 2^bw
+  uint32_t mode;             // LeafMode: the answer for a NON-NULL row
   uint32_t cmp;
+  uint32_t lkind;            // DevLeafKind
   int64_t lit;               // literal (i64, bool 0/1, or f64 order key for DK_F64)
   bool f64;
 };
-enum LeafMode : uint32_t { LM_FALSE = 0, LM_TRUE = 1, LM_REGLUT = 2, LM_MEMLUT = 3, LM_PLAIN8 = 4, LM_BITS = 5 };
 
 __device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const DevScanArgs& a, const FlatStage& st,
                                          const uint8_t* stage_base, const FlatLayout& L, uint32_t l) {
   const DevLeaf& lf = plan.leaves[l];
   const uint32_t c = lf.col;
   const FlatStageCol& sc = st.col[c];
-  x.colw = reinterpret_cast<const uint32_t*>(stage_base + L.col_off[c]) + (sc.phase >> 5);
-  x.phase = sc.phase & 31u;
-  x.bw = sc.bw;
-  x.fkind = sc.fkind;
-  x.dict_max = sc.dict_n ? sc.dict_n - 1 : 0u;
+  col_ctx(x.c, st, stage_base, L, c);
   x.cmp = lf.cmp;
+  x.lkind = lf.kind;
   x.f64 = plan.cols[c].kind == DK_F64;
   x.lit = (x.f64 && lf.kind == LK_CMP) ? f64_order_key(uint64_t(lf.lit_i64)) : lf.lit_i64;
   x.lut = a.luts + lf.lut_off + sc.lut_base;
   x.lutreg = st.lutreg[l];
-  if (lf.kind == LK_IS_NULL) x.mode = LM_FALSE;            // flat pages hold no NULLs
-  else if (lf.kind == LK_IS_NOT_NULL) x.mode = LM_TRUE;
+  if (lf.kind == LK_IS_NULL || lf.kind == LK_IS_NOT_NULL || x.c.absent) x.mode = LM_FALSE;   // answered by the validity alone
   else if (sc.fkind == FK_INDEX) {
     if ((st.regmask >> l) & 1u) x.mode = LM_REGLUT;
     else if (sc.bw == 0) x.mode = x.lut[0] ? LM_TRUE : LM_FALSE;   // one-entry dictionary: no bits at all
@@ -218,36 +266,39 @@ __device__ __forceinline__ bool plain_cmp(uint64_t bits, const LeafCtx& x) {
   return cmp_i64(v, x.lit, x.cmp);
 }
 
-// the answer for ONE row; x.mode is warp uniform, so the switch costs one predictable branch
+// the comparison for ONE non-NULL row; x.mode is warp uniform, so the switch costs one predictable branch
 __device__ __forceinline__ bool leaf_row(const LeafCtx& x, uint32_t row) {
   switch (x.mode) {
     case LM_FALSE: return false;
     case LM_TRUE: return true;
-    case LM_REGLUT: return (__funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.colw, x.phase + row * x.bw)) & 1u) != 0;
-    case LM_MEMLUT: {
-      uint32_t v = bits32_at(x.colw, x.phase + row * x.bw) & (x.bw >= 32 ? 0xffffffffu : ((1u << x.bw) - 1u));
-      v = v < x.dict_max ? v : x.dict_max;
-      return x.lut[v] != 0;
-    }
-    case LM_PLAIN8: return plain_cmp(reinterpret_cast<const uint64_t*>(x.colw)[row], x);
+    case LM_REGLUT: return (__funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.c.colw, x.c.phase + row * x.c.bw)) & 1u) != 0;
+    case LM_MEMLUT: return x.lut[col_index(x.c, row)] != 0;
+    case LM_PLAIN8: return plain_cmp(reinterpret_cast<const uint64_t*>(x.c.colw)[row], x);
     default: {
-      const uint32_t pb = x.phase + row;
-      return cmp_i64(int64_t((x.colw[pb >> 5] >> (pb & 31)) & 1u), x.lit, x.cmp);
+      const uint32_t pb = x.c.phase + row;
+      return cmp_i64(int64_t((x.c.colw[pb >> 5] >> (pb & 31)) & 1u), x.lit, x.cmp);
     }
   }
 }
+// SQL truth of the leaf for one row: 1 TRUE, 0 FALSE, 2 NULL
+__device__ __forceinline__ uint32_t leaf_row3(const LeafCtx& x, uint32_t row) {
+  const bool v = col_valid(x.c, row);
+  if (x.lkind == LK_IS_NULL) return v ? 0u : 1u;
+  if (x.lkind == LK_IS_NOT_NULL) return v ? 1u : 0u;
+  if (!v) return 2u;
+  return leaf_row(x, row) ? 1u : 0u;
+}
 
-// knock the rows of `m` (bit k = row row0 + k) out that fail the leaf: one trip per surviving row
+// knock the rows of `m` (bit k = row row0 + k, all non-NULL) out that fail the comparison: one trip per surviving row
 __device__ __forceinline__ uint32_t leaf_survivors(const LeafCtx& x, uint32_t row0, uint32_t m) {
   uint32_t mm = m;
   if (x.mode == LM_MEMLUT) {
-    const uint32_t mask = x.bw >= 32 ? 0xffffffffu : ((1u << x.bw) - 1u);
-    const uint32_t bit0 = x.phase + row0 * x.bw;
+    const uint32_t bit0 = x.c.phase + row0 * x.c.bw;
     while (mm) {
       const uint32_t k = __ffs(mm) - 1;
       mm &= mm - 1;
-      uint32_t v = bits32_at(x.colw, bit0 + k * x.bw) & mask;
-      v = v < x.dict_max ? v : x.dict_max;
+      uint32_t v = bits32_at(x.c.colw, bit0 + k * x.c.bw) & x.c.mask;
+      v = v < x.c.dict_max ? v : x.c.dict_max;
       if (!x.lut[v]) m ^= 1u << k;
     }
     return m;
@@ -288,7 +339,8 @@ __device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w
   return m;
 }
 
-// dense evaluation of one leaf over the thread's 32 rows [32*tc, 32*tc + 32) (blocked mapping)
+// dense comparison of one leaf over the thread's 32 rows [32*tc, 32*tc + 32) (blocked mapping); NULL rows
+// hold slot value 0 and are masked by the caller
 __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, uint32_t R) {
   switch (x.mode) {
     case LM_FALSE: return 0u;
@@ -296,10 +348,10 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
     case LM_REGLUT:
     case LM_MEMLUT: {
       if (tc * 32 >= R) return 0u;   // a short slab (or a reduced slab size): nothing staged for this thread
-      const uint32_t* w = x.colw + tc * x.bw;
-      if (x.phase == 0) {
+      const uint32_t* w = x.c.colw + tc * x.c.bw;
+      if (x.c.phase == 0) {
         if (x.mode == LM_REGLUT) {
-          switch (x.bw) {
+          switch (x.c.bw) {
             case 0: return (x.lutreg & 1u) ? 0xffffffffu : 0u;
             case 1: return leaf_dense_bw<1, true>(w, x.lutreg, nullptr, 0);
             case 2: return leaf_dense_bw<2, true>(w, x.lutreg, nullptr, 0);
@@ -308,33 +360,32 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
             default: return leaf_dense_bw<5, true>(w, x.lutreg, nullptr, 0);
           }
         }
-        switch (x.bw) {
-          case 1: return leaf_dense_bw<1, false>(w, 0, x.lut, x.dict_max);
-          case 2: return leaf_dense_bw<2, false>(w, 0, x.lut, x.dict_max);
-          case 3: return leaf_dense_bw<3, false>(w, 0, x.lut, x.dict_max);
-          case 4: return leaf_dense_bw<4, false>(w, 0, x.lut, x.dict_max);
-          case 5: return leaf_dense_bw<5, false>(w, 0, x.lut, x.dict_max);
-          case 6: return leaf_dense_bw<6, false>(w, 0, x.lut, x.dict_max);
-          case 7: return leaf_dense_bw<7, false>(w, 0, x.lut, x.dict_max);
-          case 8: return leaf_dense_bw<8, false>(w, 0, x.lut, x.dict_max);
-          case 9: return leaf_dense_bw<9, false>(w, 0, x.lut, x.dict_max);
-          case 10: return leaf_dense_bw<10, false>(w, 0, x.lut, x.dict_max);
-          case 11: return leaf_dense_bw<11, false>(w, 0, x.lut, x.dict_max);
-          case 12: return leaf_dense_bw<12, false>(w, 0, x.lut, x.dict_max);
+        switch (x.c.bw) {
+          case 1: return leaf_dense_bw<1, false>(w, 0, x.lut, x.c.dict_max);
+          case 2: return leaf_dense_bw<2, false>(w, 0, x.lut, x.c.dict_max);
+          case 3: return leaf_dense_bw<3, false>(w, 0, x.lut, x.c.dict_max);
+          case 4: return leaf_dense_bw<4, false>(w, 0, x.lut, x.c.dict_max);
+          case 5: return leaf_dense_bw<5, false>(w, 0, x.lut, x.c.dict_max);
+          case 6: return leaf_dense_bw<6, false>(w, 0, x.lut, x.c.dict_max);
+          case 7: return leaf_dense_bw<7, false>(w, 0, x.lut, x.c.dict_max);
+          case 8: return leaf_dense_bw<8, false>(w, 0, x.lut, x.c.dict_max);
+          case 9: return leaf_dense_bw<9, false>(w, 0, x.lut, x.c.dict_max);
+          case 10: return leaf_dense_bw<10, false>(w, 0, x.lut, x.c.dict_max);
+          case 11: return leaf_dense_bw<11, false>(w, 0, x.lut, x.c.dict_max);
+          case 12: return leaf_dense_bw<12, false>(w, 0, x.lut, x.c.dict_max);
           default: break;
         }
       }
       // wide indices, or a piece that starts inside a page off the 32-bit grid: value by value
-      const uint32_t mask = x.bw >= 32 ? 0xffffffffu : ((1u << x.bw) - 1u);
-      uint32_t m = 0, bit = x.phase + tc * 32 * x.bw;
+      uint32_t m = 0, bit = x.c.phase + tc * 32 * x.c.bw;
       if (x.mode == LM_REGLUT) {
 #pragma unroll 4
-        for (int k = 0; k < 32; k++, bit += x.bw) m = __funnelshift_r(m, __funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.colw, bit)), 1);
+        for (int k = 0; k < 32; k++, bit += x.c.bw) m = __funnelshift_r(m, __funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.c.colw, bit)), 1);
       } else {
 #pragma unroll 4
-        for (int k = 0; k < 32; k++, bit += x.bw) {
-          uint32_t v = bits32_at(x.colw, bit) & mask;
-          v = v < x.dict_max ? v : x.dict_max;
+        for (int k = 0; k < 32; k++, bit += x.c.bw) {
+          uint32_t v = bits32_at(x.c.colw, bit) & x.c.mask;
+          v = v < x.c.dict_max ? v : x.c.dict_max;
           m = __funnelshift_r(m, uint32_t(x.lut[v]), 1);
         }
       }
@@ -342,14 +393,14 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
     }
     case LM_BITS: {
       if (tc * 32 >= R) return 0u;
-      const uint32_t word = bits32_at(x.colw, x.phase + tc * 32);
+      const uint32_t word = bits32_at(x.c.colw, x.c.phase + tc * 32);
       const uint32_t r1 = cmp_i64(1, x.lit, x.cmp) ? word : 0u, r0 = cmp_i64(0, x.lit, x.cmp) ? ~word : 0u;
       return r1 | r0;
     }
     default: {
       // LM_PLAIN8: transposed over the warp (lane L reads row base + 32 j + L: conflict free), lane j keeps word j
       const uint32_t lane = threadIdx.x & 31, wbase = (tc & ~31u) * 32;
-      const uint64_t* v8 = reinterpret_cast<const uint64_t*>(x.colw);
+      const uint64_t* v8 = reinterpret_cast<const uint64_t*>(x.c.colw);
       uint32_t mine = 0;
 #pragma unroll 4
       for (uint32_t j = 0; j < 32; j++) {
@@ -362,6 +413,23 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
     }
   }
 }
+
+// SQL three-valued logic on bit planes: t = TRUE rows, n = NULL rows (FALSE = neither); arrow's Kleene and / or
+struct Tri32 { uint32_t t, n; };
+__device__ __forceinline__ Tri32 tri_leaf(const LeafCtx& x, uint32_t V, uint32_t dense) {
+  if (x.lkind == LK_IS_NULL) return {~V, 0u};
+  if (x.lkind == LK_IS_NOT_NULL) return {V, 0u};
+  return {dense & V, ~V};
+}
+__device__ __forceinline__ Tri32 tri_and(Tri32 a, Tri32 b) {
+  const uint32_t fa = ~(a.t | a.n), fb = ~(b.t | b.n);
+  return {a.t & b.t, (a.n | b.n) & ~fa & ~fb};
+}
+__device__ __forceinline__ Tri32 tri_or(Tri32 a, Tri32 b) {
+  const uint32_t t = a.t | b.t;
+  return {t, (a.n | b.n) & ~t};
+}
+__device__ __forceinline__ Tri32 tri_not(Tri32 a) { return {~(a.t | a.n), a.n}; }
 
 // ---- k_flat_filter ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFilterThreads, 3)
@@ -388,18 +456,23 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
     uint32_t m = inr;
     if (plan.npred) {
       if (plan.conj) {
-        // conjunction: first leaf on every row, the others on the survivors only (or dense when many survive)
+        // conjunction: a row passes when every leaf is TRUE (a NULL leaf drops it).  First leaf on every row,
+        // the others on the survivors only (or dense when many survive)
         for (uint32_t l = 0; l < plan.nleaves; l++) {
           const uint32_t mx = l ? __reduce_max_sync(0xffffffffu, __popc(m)) : 32u;
           if (mx == 0) break;
           LeafCtx x;
           leaf_ctx(x, plan, a, st, base, L, l);
+          const uint32_t V = inr ? col_valid32(x.c, row0) : 0u;
+          if (x.lkind == LK_IS_NULL) { m &= ~V; continue; }
+          m &= V;
+          if (x.lkind == LK_IS_NOT_NULL) continue;
           if (mx > 10) m &= leaf_dense(x, tc, R);
           else m = leaf_survivors(x, row0, m);
         }
       } else {
-        // general boolean program (no NULLs on flat pages: two-valued logic)
-        uint32_t stk[kPredStack];
+        // general boolean program, SQL three-valued logic (NULLs come from validity bitmaps and NULL literals)
+        Tri32 stk[kPredStack];
         int sp = 0;
 #pragma unroll 1
         for (uint32_t i = 0; i < plan.npred; i++) {
@@ -407,12 +480,13 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
           if (op.kind == PK_LEAF) {
             LeafCtx x;
             leaf_ctx(x, plan, a, st, base, L, op.arg);
-            stk[sp++] = leaf_dense(x, tc, R);
-          } else if (op.kind == PK_CONST) stk[sp++] = op.arg == 1 ? 0xffffffffu : 0u;
-          else if (op.kind == PK_NOT) stk[sp - 1] = ~stk[sp - 1];
-          else { sp--; stk[sp - 1] = op.kind == PK_AND ? (stk[sp - 1] & stk[sp]) : (stk[sp - 1] | stk[sp]); }
+            const uint32_t V = inr ? col_valid32(x.c, row0) : 0u;
+            stk[sp++] = tri_leaf(x, V, leaf_dense(x, tc, R));
+          } else if (op.kind == PK_CONST) stk[sp++] = {op.arg == 1 ? 0xffffffffu : 0u, op.arg == 2 ? 0xffffffffu : 0u};
+          else if (op.kind == PK_NOT) stk[sp - 1] = tri_not(stk[sp - 1]);
+          else { sp--; stk[sp - 1] = op.kind == PK_AND ? tri_and(stk[sp - 1], stk[sp]) : tri_or(stk[sp - 1], stk[sp]); }
         }
-        m = stk[0] & inr;
+        m = stk[0].t & inr;
       }
     }
     if (plan.write_bitmap && row0 < R) a.bitmap[st.bitmap_word0 + (st.r0 >> 5) + tc] = m;
@@ -434,24 +508,6 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
 // decision that does not depend on the row (page kind, bit width, aggregate function, pointers) is
 // made once per pass, outside the row loop.
 constexpr int kAggRowsMax = 8;
-
-struct ColCtx {              // one staged column of the current slab
-  const uint32_t* colw;
-  uint32_t phase, bw, mask, dict_max, fkind;
-};
-__device__ __forceinline__ void col_ctx(ColCtx& c, const FlatStage& st, const uint8_t* base, const FlatLayout& L, uint32_t col) {
-  const FlatStageCol& sc = st.col[col];
-  c.colw = reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
-  c.phase = sc.phase & 31u;
-  c.bw = sc.bw;
-  c.mask = sc.bw >= 32 ? 0xffffffffu : ((1u << sc.bw) - 1u);
-  c.dict_max = sc.dict_n ? sc.dict_n - 1 : 0u;
-  c.fkind = sc.fkind;
-}
-__device__ __forceinline__ uint32_t col_index(const ColCtx& c, uint32_t row) {
-  uint32_t v = bits32_at(c.colw, c.phase + row * c.bw) & c.mask;   // bw == 0: mask == 0
-  return v < c.dict_max ? v : c.dict_max;
-}
 
 // shared-memory cells are 8 bytes like the global ones; per-CTA partial counts and the low words of
 // partial sums are updated with native 32-bit atomics
@@ -519,13 +575,19 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             LeafCtx x;
             leaf_ctx(x, plan, a, st, base, L, l);
             uint32_t m = 0;
+            if (!x.c.absent && !x.c.vw && x.lkind != LK_IS_NULL && x.lkind != LK_IS_NOT_NULL) {   // no NULLs in this slab: plain comparison
 #pragma unroll
-            for (int i = 0; i < kAggRowsMax; i++)
-              if ((sel >> i) & 1u) m |= (leaf_row(x, tc + i * kAggConsumers) ? 1u : 0u) << i;
+              for (int i = 0; i < kAggRowsMax; i++)
+                if ((sel >> i) & 1u) m |= (leaf_row(x, tc + i * kAggConsumers) ? 1u : 0u) << i;
+            } else {
+#pragma unroll
+              for (int i = 0; i < kAggRowsMax; i++)
+                if ((sel >> i) & 1u) m |= (leaf_row3(x, tc + i * kAggConsumers) == 1u ? 1u : 0u) << i;
+            }
             sel = m;
           }
         } else {
-          uint32_t stk[kPredStack];
+          Tri32 stk[kPredStack];
           int sp = 0;
 #pragma unroll 1
           for (uint32_t i = 0; i < plan.npred; i++) {
@@ -533,19 +595,23 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             if (op.kind == PK_LEAF) {
               LeafCtx x;
               leaf_ctx(x, plan, a, st, base, L, op.arg);
-              uint32_t m = 0;
+              Tri32 v{0u, 0u};
 #pragma unroll
               for (int j = 0; j < kAggRowsMax; j++)
-                if ((sel >> j) & 1u) m |= (leaf_row(x, tc + j * kAggConsumers) ? 1u : 0u) << j;
-              stk[sp++] = m;
-            } else if (op.kind == PK_CONST) stk[sp++] = op.arg == 1 ? 0xffu : 0u;
-            else if (op.kind == PK_NOT) stk[sp - 1] = ~stk[sp - 1];
-            else { sp--; stk[sp - 1] = op.kind == PK_AND ? (stk[sp - 1] & stk[sp]) : (stk[sp - 1] | stk[sp]); }
+                if ((sel >> j) & 1u) {
+                  const uint32_t t3 = leaf_row3(x, tc + j * kAggConsumers);
+                  v.t |= (t3 == 1u ? 1u : 0u) << j;
+                  v.n |= (t3 == 2u ? 1u : 0u) << j;
+                }
+              stk[sp++] = v;
+            } else if (op.kind == PK_CONST) stk[sp++] = {op.arg == 1 ? 0xffu : 0u, op.arg == 2 ? 0xffu : 0u};
+            else if (op.kind == PK_NOT) stk[sp - 1] = tri_not(stk[sp - 1]);
+            else { sp--; stk[sp - 1] = op.kind == PK_AND ? tri_and(stk[sp - 1], stk[sp]) : tri_or(stk[sp - 1], stk[sp]); }
           }
-          sel &= stk[0];
+          sel &= stk[0].t;
         }
       }
-      // ---- group slot of every selected row: one pass per key ----
+      // ---- group slot of every selected row: one pass per key; NULL is its own group (id == card) ----
       uint32_t slot[kAggRowsMax];
 #pragma unroll
       for (int i = 0; i < kAggRowsMax; i++) slot[i] = 0;
@@ -553,16 +619,26 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         const DevKey& key = plan.keys[k];
         ColCtx c;
         col_ctx(c, st, base, L, key.col);
-        const uint32_t stride = key.stride;
+        const uint32_t stride = key.stride, nullslot = key.card * key.stride;
+        const bool nullable = c.absent || c.vw != nullptr;
         if (key.kind == KK_BOOL) {
 #pragma unroll
           for (int i = 0; i < kAggRowsMax; i++)
-            if ((sel >> i) & 1u) { const uint32_t pb = c.phase + tc + i * kAggConsumers; slot[i] += ((c.colw[pb >> 5] >> (pb & 31)) & 1u) * stride; }
+            if ((sel >> i) & 1u) {
+              const uint32_t r = tc + i * kAggConsumers;
+              if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
+              const uint32_t pb = c.phase + r;
+              slot[i] += ((c.colw[pb >> 5] >> (pb & 31)) & 1u) * stride;
+            }
         } else {
           const uint32_t* __restrict__ gid = key.gid + st.col[key.col].lut_base;
 #pragma unroll
           for (int i = 0; i < kAggRowsMax; i++)
-            if ((sel >> i) & 1u) slot[i] += gid[col_index(c, tc + i * kAggConsumers)] * stride;
+            if ((sel >> i) & 1u) {
+              const uint32_t r = tc + i * kAggConsumers;
+              if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
+              slot[i] += gid[col_index(c, r)] * stride;
+            }
         }
       }
       // ---- COUNT(*) cell ----
@@ -572,22 +648,29 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
           if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[slot[i]]), 1u);   // a CTA sees < 2^32 rows: the low word never wraps
           else atomicAdd(&gacc[slot[i]], 1ull);
         }
-      // ---- one pass per aggregate ----
+      // ---- one pass per aggregate (NULL inputs contribute nothing) ----
       for (uint32_t g = 0; g < plan.naggs; g++) {
         const DevAgg& ag = plan.aggs[g];
         if (ag.fn == AG_COUNT_STAR) continue;
+        ColCtx c;
+        col_ctx(c, st, base, L, ag.col);
+        if (c.absent) continue;
+        uint32_t vsel = sel;   // selected rows whose input is not NULL
+        if (c.vw) {
+#pragma unroll
+          for (int i = 0; i < kAggRowsMax; i++)
+            if (((sel >> i) & 1u) && !col_valid(c, tc + i * kAggConsumers)) vsel &= ~(1u << i);
+        }
         if (ag.update_nn) {
           const uint32_t arr = 1 + plan.n_acc + ag.nn_slot;
 #pragma unroll
           for (int i = 0; i < kAggRowsMax; i++)
-            if ((sel >> i) & 1u) {
+            if ((vsel >> i) & 1u) {
               if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[arr * H + slot[i]]), 1u);
               else atomicAdd(&gacc[size_t(arr) * nslots + slot[i]], 1ull);
             }
         }
         if (ag.fn == AG_COUNT) continue;
-        ColCtx c;
-        col_ctx(c, st, base, L, ag.col);
         const bool plain = c.fkind == FK_PLAIN8;
         const uint64_t* __restrict__ dict = reinterpret_cast<const uint64_t*>(a.flat + st.col[ag.col].dict8);
         const uint64_t* v8 = reinterpret_cast<const uint64_t*>(c.colw);
@@ -599,7 +682,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         const uint32_t Hc = (plan.f64_global && (fn == AG_AVG || (fn == AG_SUM && f64))) ? 0u : Hw;
 #pragma unroll
         for (int i = 0; i < kAggRowsMax; i++) {
-          if (!((sel >> i) & 1u)) continue;
+          if (!((vsel >> i) & 1u)) continue;
           const uint32_t r = tc + i * kAggConsumers;
           const uint64_t bits = plain ? v8[r] : dict[col_index(c, r)];
           const bool hot = slot[i] < Hc;

@@ -94,67 +94,41 @@ __device__ inline bool def_levels_all_valid(const uint8_t* __restrict__ p, uint3
   return true;
 }
 
-enum FlatJobKind : uint32_t { FJ_HYBRID = 1, FJ_COPY8 = 2, FJ_BITS = 3, FJ_DICT8 = 4 };
+enum FlatJobKind : uint32_t { FJ_HYBRID = 1, FJ_COPY8 = 2, FJ_BITS = 3, FJ_DICT8 = 4, FJ_VALID = 5 };
 // FJ_HYBRID: RLE / bit-packed hybrid stream -> flat bits       (page)
 // FJ_COPY8 : PLAIN 8-byte values -> aligned copy               (page)
 // FJ_BITS  : PLAIN boolean bits -> aligned copy                (page)
 // FJ_DICT8 : numeric dictionary (8-byte entries) -> aligned copy (src = arena offset, rows = entries)
+// FJ_VALID : validity bitmap only (a DELTA page with NULLs: its values follow on demand, ensure_plain8)
+// A page with NULLs (vdst != ~0) also gets its validity bitmap (1 bit per ROW, from the definition
+// levels) and its values EXPANDED to one slot per row (NULL rows hold 0), so that row r of the page
+// is slot r whatever the NULLs: the scan needs no rank / prefix popcount.
 struct FlatStoreJob {
-  uint64_t src;      // FJ_DICT8: arena offset of the dictionary payload; otherwise unused
+  uint64_t src;      // FJ_DICT8: arena offset of the dictionary payload
   uint64_t dst;      // byte offset in the flat buffer (16-byte aligned)
+  uint64_t vdst;     // validity bitmap in the flat buffer, or ~0: the page holds no NULLs
+  uint64_t tmp;      // FJ_HYBRID with NULLs: scratch for the dense (non-null only) values, in the flat buffer
   uint32_t page;     // page index (page jobs)
   uint32_t kind;     // FlatJobKind
   uint32_t rows;     // FJ_DICT8: entries
   uint32_t _pad;
 };
 
-__global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
-                                                    const FlatStoreJob* __restrict__ jobs, uint32_t n_jobs,
-                                                    uint8_t* __restrict__ flat, uint8_t* __restrict__ ok_out) {
-  __shared__ __align__(16) uint8_t tiles[4][kFlatTile + 16];
-  __shared__ FlatRun runs_s[4][kFlatTileRuns];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ji = blockIdx.x * 4 + warp;
-  if (ji >= n_jobs) return;
-  const FlatStoreJob job = jobs[ji];
-  if (job.kind == FJ_DICT8) {
-    uint64_t* d = reinterpret_cast<uint64_t*>(flat + job.dst);
-    for (uint32_t i = lane; i < job.rows; i += 32) d[i] = load_u64_unaligned(arena + job.src + uint64_t(i) * 8);
-    if (lane == 0) ok_out[ji] = 1;
-    return;
-  }
-  const DevPage pg = pages[job.page];
-  // ---- NULL check: the flat form has exactly one value per row ----
-  uint32_t ok = 1;
-  if (pg.def_len) {
-    if (lane == 0) ok = def_levels_all_valid(arena + pg.off + pg.def_off, pg.def_len, pg.num_rows) ? 1u : 0u;
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-  }
-  if (!ok) { if (lane == 0) ok_out[ji] = 0; return; }
-  const uint8_t* vals = arena + pg.off + pg.val_off;
-  if (job.kind == FJ_COPY8) {
-    if (uint64_t(pg.val_off) + uint64_t(pg.num_rows) * 8 > pg.len) { if (lane == 0) ok_out[ji] = 0; return; }
-    uint64_t* d = reinterpret_cast<uint64_t*>(flat + job.dst);
-    for (uint32_t i = lane; i < pg.num_rows; i += 32) d[i] = load_u64_unaligned(vals + uint64_t(i) * 8);
-    if (lane == 0) ok_out[ji] = 1;
-    return;
-  }
-  if (job.kind == FJ_BITS) {
-    const uint32_t nw = (pg.num_rows + 31) >> 5;
-    if (uint64_t(pg.val_off) + ((pg.num_rows + 7) >> 3) > pg.len) { if (lane == 0) ok_out[ji] = 0; return; }
-    uint32_t* d = reinterpret_cast<uint32_t*>(flat + job.dst);
-    for (uint32_t i = lane; i < nw; i += 32) d[i] = load_u32_unaligned(vals + uint64_t(i) * 4);
-    if (lane == 0) ok_out[ji] = 1;
-    return;
-  }
-  // ---- FJ_HYBRID ----
-  const uint32_t bw = pg.bit_width;
-  const uint32_t nvals = pg.num_rows;
-  if (bw == 0) { if (lane == 0) ok_out[ji] = 1; return; }   // one-entry dictionary: no bits at all
-  uint32_t* dst = reinterpret_cast<uint32_t*>(flat + job.dst);
-  uint8_t* tile = tiles[warp];
-  FlatRun* runs = runs_s[warp];
-  const uint64_t s_begin = pg.off + pg.val_off, s_end = pg.off + pg.len;
+// 0: every definition level is 1; 1: the page holds NULLs; one thread per page
+__global__ void k_page_has_nulls(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages, uint32_t n_pages,
+                                 uint8_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pages) return;
+  const DevPage pg = pages[i];
+  out[i] = (pg.def_len && !def_levels_all_valid(arena + pg.off + pg.def_off, pg.def_len, pg.num_rows)) ? 1 : 0;
+}
+
+// One RLE / bit-packed hybrid stream [s_begin, s_end) of `nvals` values at `bw` bits -> flat bits at dst
+// (zeroed).  Warp cooperative; returns false for a stream the walker refuses.
+__device__ __noinline__ bool flatten_hybrid(const uint8_t* __restrict__ arena, uint64_t s_begin, uint64_t s_end, uint32_t bw,
+                                            uint32_t nvals, uint32_t* __restrict__ dst, uint8_t* tile, FlatRun* runs) {
+  const uint32_t lane = threadIdx.x & 31;
+  if (bw == 0 || nvals == 0) return true;   // a one-entry dictionary has no bits at all
   // walker state (lane 0 authoritative, broadcast every round)
   uint64_t p = s_begin;        // next unread stream byte: a run header, or the data of a bit-packed run in progress
   uint32_t row = 0;            // values emitted so far
@@ -240,9 +214,123 @@ __global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ 
       if (nruns == 0 && !refill && !bad && row < nvals) bad = 1;   // no progress: corrupt stream
     }
   }
-  if (lane == 0) ok_out[ji] = bad ? 0 : 1;
+  return !bad;
 }
 
+// non-null values of a page = set bits of its validity bitmap (warp cooperative)
+__device__ __forceinline__ uint32_t warp_count_valid(const uint32_t* __restrict__ valid, uint32_t rows) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t c = 0;
+  for (uint32_t w = lane; w < (rows + 31) / 32; w += 32) {
+    uint32_t x = valid[w];
+    if (w * 32 + 32 > rows) x &= (1u << (rows - w * 32)) - 1u;
+    c += __popc(x);
+  }
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
+// Dense (non-null only) values -> one slot per row.  get(k) = k-th dense value; put(r, v) stores row r.
+template <typename Get, typename Put>
+__device__ __forceinline__ void expand_rows(const uint32_t* __restrict__ valid, uint32_t rows, Get get, Put put) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  for (uint32_t r0 = 0; r0 < rows; r0 += 32) {
+    const uint32_t r = r0 + lane;
+    const uint32_t word = valid[r0 >> 5] & (rows - r0 >= 32 ? 0xffffffffu : ((1u << (rows - r0)) - 1u));
+    const bool v = (word >> lane) & 1u;
+    const uint32_t rank = base + __popc(word & ((1u << lane) - 1u));
+    put(r, v, v ? get(rank) : 0ull, word);
+    base += __popc(word);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
+                                                    const FlatStoreJob* __restrict__ jobs, uint32_t n_jobs,
+                                                    uint8_t* __restrict__ flat, uint8_t* __restrict__ ok_out) {
+  __shared__ __align__(16) uint8_t tiles[4][kFlatTile + 16];
+  __shared__ FlatRun runs_s[4][kFlatTileRuns];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ji = blockIdx.x * 4 + warp;
+  if (ji >= n_jobs) return;
+  const FlatStoreJob job = jobs[ji];
+  if (job.kind == FJ_DICT8) {
+    uint64_t* d = reinterpret_cast<uint64_t*>(flat + job.dst);
+    for (uint32_t i = lane; i < job.rows; i += 32) d[i] = load_u64_unaligned(arena + job.src + uint64_t(i) * 8);
+    if (lane == 0) ok_out[ji] = 1;
+    return;
+  }
+  const DevPage pg = pages[job.page];
+  uint8_t* tile = tiles[warp];
+  FlatRun* runs = runs_s[warp];
+  const bool has_nulls = job.vdst != ~0ull;
+  const uint32_t rows = pg.num_rows;
+  uint32_t* valid = reinterpret_cast<uint32_t*>(flat + job.vdst);
+  uint32_t nn = rows;   // non-null values
+  if (has_nulls) {
+    // definition levels (bit width 1) -> validity bitmap, 1 bit per row
+    if (!flatten_hybrid(arena, pg.off + pg.def_off, pg.off + pg.def_off + pg.def_len, 1, rows, valid, tile, runs)) {
+      if (lane == 0) ok_out[ji] = 0;
+      return;
+    }
+    __syncwarp();
+    __threadfence_block();
+    nn = warp_count_valid(valid, rows);
+  }
+  const uint8_t* vals = arena + pg.off + pg.val_off;
+  if (job.kind == FJ_VALID) { if (lane == 0) ok_out[ji] = 1; return; }
+  if (job.kind == FJ_COPY8) {
+    if (uint64_t(pg.val_off) + uint64_t(nn) * 8 > pg.len) { if (lane == 0) ok_out[ji] = 0; return; }
+    uint64_t* d = reinterpret_cast<uint64_t*>(flat + job.dst);
+    if (!has_nulls) {
+      for (uint32_t i = lane; i < rows; i += 32) d[i] = load_u64_unaligned(vals + uint64_t(i) * 8);
+    } else {
+      expand_rows(valid, rows, [&](uint32_t k) { return load_u64_unaligned(vals + uint64_t(k) * 8); },
+                  [&](uint32_t r, bool, uint64_t v, uint32_t) { if (r < rows) d[r] = v; });
+    }
+    if (lane == 0) ok_out[ji] = 1;
+    return;
+  }
+  if (job.kind == FJ_BITS) {
+    if (uint64_t(pg.val_off) + ((nn + 7) >> 3) > pg.len) { if (lane == 0) ok_out[ji] = 0; return; }
+    uint32_t* d = reinterpret_cast<uint32_t*>(flat + job.dst);
+    if (!has_nulls) {
+      const uint32_t nw = (rows + 31) >> 5;
+      for (uint32_t i = lane; i < nw; i += 32) d[i] = load_u32_unaligned(vals + uint64_t(i) * 4);
+    } else {
+      expand_rows(valid, rows, [&](uint32_t k) { return uint64_t((vals[k >> 3] >> (k & 7)) & 1u); },
+                  [&](uint32_t r, bool v, uint64_t x, uint32_t) {
+                    const uint32_t w = __ballot_sync(0xffffffffu, v && x);
+                    if (lane == 0) d[r >> 5] = w;
+                  });
+    }
+    if (lane == 0) ok_out[ji] = 1;
+    return;
+  }
+  // ---- FJ_HYBRID ----
+  const uint32_t bw = pg.bit_width;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(flat + job.dst);
+  const uint64_t s_begin = pg.off + pg.val_off, s_end = pg.off + pg.len;
+  bool ok;
+  if (!has_nulls) ok = flatten_hybrid(arena, s_begin, s_end, bw, rows, dst, tile, runs);
+  else {
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(flat + job.tmp);
+    ok = flatten_hybrid(arena, s_begin, s_end, bw, nn, tmp, tile, runs);
+    __syncwarp();
+    __threadfence_block();
+    if (ok && bw) {
+      const uint32_t mask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
+      expand_rows(valid, rows, [&](uint32_t k) { return uint64_t(bits32_at(tmp, k * bw) & mask); },
+                  [&](uint32_t r, bool v, uint64_t x, uint32_t) {
+                    if (!v || !x) return;
+                    const uint64_t bit = uint64_t(r) * bw;
+                    const uint32_t sh = uint32_t(bit & 31);
+                    atomicOr(&dst[bit >> 5], uint32_t(x) << sh);
+                    if (sh + bw > 32) atomicOr(&dst[(bit >> 5) + 1], uint32_t(x) >> (32 - sh));
+                  });
+    }
+  }
+  if (lane == 0) ok_out[ji] = ok ? 1 : 0;
+}
 
 // ---- DELTA_BINARY_PACKED (Parseable's p_timestamp, streams.rs:587-590) -> aligned 8-byte values ----
 // Only built when a query needs the VALUES of such a column (a time range that cuts a row group, a
@@ -250,7 +338,7 @@ __global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ 
 // the column is then never read.  One warp per page: lane 0 walks the block headers (zigzag varints,
 // one bit width per miniblock), the warp unpacks a miniblock's deltas in parallel and turns them into
 // values with a shuffle scan carried across miniblocks.
-struct DeltaJob { uint32_t page; uint32_t _pad; uint64_t dst; };
+struct DeltaJob { uint32_t page; uint32_t _pad; uint64_t dst; uint64_t vsrc /* validity bitmap of a page with NULLs (flat-base relative), or ~0 */; uint64_t tmp /* scratch for its dense values */; };
 
 __device__ __forceinline__ bool rd_varint(const uint8_t* __restrict__ p, uint64_t& pos, uint64_t end, uint64_t& out) {
   uint64_t v = 0;
@@ -271,34 +359,32 @@ __global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restri
   if (ji >= n_jobs) return;
   const DeltaJob job = jobs[ji];
   const DevPage pg = pages[job.page];
-  uint32_t ok = 1;
-  if (pg.def_len) {
-    if (lane == 0) ok = def_levels_all_valid(arena + pg.off + pg.def_off, pg.def_len, pg.num_rows) ? 1u : 0u;
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-  }
-  if (!ok) { if (lane == 0) ok_out[ji] = 0; return; }
+  // a page with NULLs holds only its non-null values: they are decoded densely, then spread over the row slots
+  const bool has_nulls = job.vsrc != ~0ull;
+  const uint32_t* valid = reinterpret_cast<const uint32_t*>(flat_base + job.vsrc);
+  const uint32_t nvals = has_nulls ? warp_count_valid(valid, pg.num_rows) : pg.num_rows;
   const uint8_t* p = arena + pg.off;
   uint64_t pos = pg.val_off;
   const uint64_t end = pg.len;
-  int64_t* out = reinterpret_cast<int64_t*>(flat_base + job.dst);
+  int64_t* final_out = reinterpret_cast<int64_t*>(flat_base + job.dst);
+  int64_t* out = has_nulls ? reinterpret_cast<int64_t*>(flat_base + job.tmp) : final_out;
   // page header
   uint64_t bs = 0, nm = 0, total = 0, fz = 0;
   uint32_t bad = 0;
   if (lane == 0) {
     if (!rd_varint(p, pos, end, bs) || !rd_varint(p, pos, end, nm) || !rd_varint(p, pos, end, total) || !rd_varint(p, pos, end, fz)) bad = 1;
-    if (!bad && (nm == 0 || nm > 32 || bs == 0 || bs % nm != 0 || (bs / nm) % 32 != 0 || bs > (1u << 20) || total != pg.num_rows)) bad = 1;
+    if (!bad && (nm == 0 || nm > 32 || bs == 0 || bs % nm != 0 || (bs / nm) % 32 != 0 || bs > (1u << 20) || total != nvals)) bad = 1;
   }
   bad = __shfl_sync(0xffffffffu, bad, 0);
-  if (bad) { if (lane == 0) ok_out[ji] = pg.num_rows == 0 ? 1 : 0; return; }
+  if (bad) { if (lane == 0) ok_out[ji] = 0; return; }
   bs = __shfl_sync(0xffffffffu, bs, 0);
   nm = __shfl_sync(0xffffffffu, nm, 0);
   fz = __shfl_sync(0xffffffffu, fz, 0);
   pos = __shfl_sync(0xffffffffu, pos, 0);
   const uint32_t vpm = uint32_t(bs / nm);   // values per miniblock, a multiple of 32
   int64_t last = int64_t(fz >> 1) ^ -int64_t(fz & 1);
-  if (lane == 0 && pg.num_rows) out[0] = last;
+  if (lane == 0 && nvals) out[0] = last;
   uint32_t done = 1;                        // values written
-  const uint32_t nvals = pg.num_rows;
   while (done < nvals && !bad) {
     // block header: min delta + one bit width per miniblock (lane m keeps width m)
     uint64_t mz = 0;
@@ -339,6 +425,12 @@ __global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restri
       done += take;
       pos += (uint64_t(vpm) * bw) / 8;
     }
+  }
+  if (has_nulls && !bad) {
+    __syncwarp();
+    __threadfence_block();
+    expand_rows(valid, pg.num_rows, [&](uint32_t k) { return uint64_t(out[k]); },
+                [&](uint32_t r, bool, uint64_t v, uint32_t) { if (r < pg.num_rows) final_out[r] = int64_t(v); });
   }
   if (lane == 0) ok_out[ji] = bad ? 0 : 1;
 }

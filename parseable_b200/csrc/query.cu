@@ -223,6 +223,12 @@ static std::vector<EntChunk> column_chunks(const Table& t, int tcol) {
   return v;
 }
 
+void launch_page_has_nulls(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, uint8_t* out, cudaStream_t stream) {
+  if (!n_pages) return;
+  k_page_has_nulls<<<(n_pages + 127) / 128, 128, 0, stream>>>(arena, pages, n_pages, out);
+  PQB_CUDA(cudaGetLastError());
+}
+
 void launch_delta_to_plain8(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat_base, uint8_t* ok,
                             cudaStream_t stream) {
   if (!n_jobs) return;
@@ -913,7 +919,8 @@ void Query::run(const PqQueryDesc& d) {
   const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
 
   // ---- which kernels run ----
-  const bool flat_ok = !has_null_const && !(getenv("PQB_FLAT_SCAN") && getenv("PQB_FLAT_SCAN")[0] == '0');
+  (void)has_null_const;   // the flat kernels evaluate SQL three-valued logic, NULL literals included
+  const bool flat_ok = !(getenv("PQB_FLAT_SCAN") && getenv("PQB_FLAT_SCAN")[0] == '0');
   plan.no_flat = flat_ok ? 0 : 1;
   const uint32_t n_flat = flat_ok ? shape->n_flat : 0;
   const uint32_t n_general = flat_ok ? shape->n_general : uint32_t(items.size());
@@ -965,9 +972,11 @@ void Query::run(const PqQueryDesc& d) {
       uint32_t off = 0;
       for (uint32_t s = 0; s < ncols; s++) {
         FL.col_off[s] = off;
+        FL.col_voff[s] = off;
         if (!plan.cols[s].staged) continue;
         const uint32_t cap = std::max<uint32_t>(shape->flat_plain8[s] ? S * 8 : 0, (S * shape->flat_max_bw[s] + 7) / 8);
         off += align_up(cap + 48, 128);   // + the bit phase of a piece that starts inside a page, + over-read slack
+        if (shape->flat_nullable[s]) { FL.col_voff[s] = off; off += align_up(S / 8 + 48, 128); }   // validity bits of pages with NULLs
       }
       return std::max<uint32_t>(off, 128);
     };
@@ -1061,8 +1070,8 @@ void Query::run(const PqQueryDesc& d) {
   // ---- selection bitmap / counts ----
   const bool projecting = want_rows && d.n_projection > 0;
   if (projecting && n_general)
-    throw Error(PQ_ERR_UNSUPPORTED, "projection of column values needs a flat-store copy of every page it reads: pages with NULLs and PLAIN "
-                                    "(dictionary-fallback) strings are not projected on the GPU yet");
+    throw Error(PQ_ERR_UNSUPPORTED, "projection of column values needs a flat-store copy of every page it reads: PLAIN (dictionary-fallback) "
+                                    "string pages are not projected on the GPU yet");
   plan.write_bitmap = want_rows ? 1 : 0;
   DevBuf<uint32_t> d_bitmap, d_item_counts;
   // k_scan ORs partial words into its bitmap regions: they start zeroed.  The flat filter kernel stores
@@ -1476,7 +1485,7 @@ void Query::run(const PqQueryDesc& d) {
             const ProjCol& pc = pj.cols[c];
             oc.ext = block;
             oc.ext_all = true;
-            oc.null_count = 0;   // flat pages hold no NULLs
+            oc.null_count = reinterpret_cast<const uint32_t*>(block->p + nulls_off)[c * nbatches + b];
             oc.ext_validity_off = pc.valid_off + uint64_t(b) * wpb * 4;
             if (pc.kind == DK_STR) { oc.ext_offsets_off = pc.val_off + r0 * 4; oc.ext_off = pc.data_off; }
             else if (pc.kind == DK_BOOL) oc.ext_off = pc.val_off + uint64_t(b) * wpb * 4;

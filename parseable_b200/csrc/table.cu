@@ -816,13 +816,28 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
 
 // ---- flat store ----------------------------------------------------------------------------------
 void Table::build_flat_store(cudaStream_t stream) {
-  flat_pages.assign(pages.size(), FlatPageRec{});
+  FlatPageRec blank{};
+  blank.voff = ~0ull;
+  flat_pages.assign(pages.size(), blank);
   const char* sw = getenv("PQB_FLAT");
   if ((sw && sw[0] == '0') || pages.empty()) return;   // A/B switch: everything through k_scan
-  struct J { uint64_t src, off; uint32_t page, kind, rows, zone; };
+  // which pages hold NULLs (their definition levels are not all 1)?
+  std::vector<uint8_t> has_nulls(pages.size(), 0);
+  {
+    uint8_t* d_nf = nullptr;
+    PQB_CUDA(cudaMallocAsync((void**)&d_nf, pages.size(), stream));
+    launch_page_has_nulls(d_arena, d_pages, uint32_t(pages.size()), d_nf, stream);
+    PQB_CUDA(cudaMemcpyAsync(has_nulls.data(), d_nf, pages.size(), cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    PQB_CUDA(cudaFreeAsync(d_nf, stream));
+  }
+  struct J { uint64_t src, off, voff, toff; uint32_t page, kind, rows, zone; };
   std::vector<J> js;
-  uint64_t zoff[2] = {0, 0};   // zone 0: hybrid outputs (zeroed, merged with atomicOr); zone 1: plain copies
+  // zone 0: zeroed (hybrid outputs and validity bitmaps are merged into it with atomicOr); zone 1: plain copies;
+  // zone 2: zeroed scratch for the dense values of index pages with NULLs
+  uint64_t zoff[3] = {0, 0, 0};
   auto take = [&](int zone, uint64_t bytes) { uint64_t o = zoff[zone]; zoff[zone] = (zoff[zone] + bytes + 16 + 15) & ~15ull; return o; };
+  const uint64_t kNone = ~0ull;
   for (TableRowGroup& rg : row_groups)
     for (size_t c = 0; c < rg.chunks.size(); c++) {
       TableChunk& tc = rg.chunks[c];
@@ -831,7 +846,7 @@ void Table::build_flat_store(cudaStream_t stream) {
       if (tc.dict_n && (kind == DK_I64 || kind == DK_F64)) {
         if (uint64_t(tc.dict_n) * 8 > tc.dict_len)
           throw Error(PQ_ERR_CORRUPT, "column '" + columns[c].name + "': dictionary page shorter than its entry count");
-        js.push_back({tc.dict_off, take(1, uint64_t(tc.dict_n) * 8), 0u, 4u /*FJ_DICT8*/, tc.dict_n, 1u});
+        js.push_back({tc.dict_off, take(1, uint64_t(tc.dict_n) * 8), kNone, kNone, 0u, 4u /*FJ_DICT8*/, tc.dict_n, 1u});
         tc.dict8_off = js.size() - 1;   // job index for now, resolved below
       }
       for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
@@ -839,35 +854,51 @@ void Table::build_flat_store(cudaStream_t stream) {
         const DevPage& pg = pages[pi];
         FlatPageRec& fr = flat_pages[pi];
         fr.rows = pg.num_rows;
+        const bool nul = has_nulls[pi] != 0;
+        const uint64_t vbytes = (uint64_t(pg.num_rows) + 31) / 32 * 4;
         if (pg.enc == DE_DICT || pg.enc == DE_RLE_BOOL) {
           fr.fkind = pg.enc == DE_DICT ? FK_INDEX : FK_BITS;
           fr.bw = pg.bit_width;
-          js.push_back({0, take(0, (uint64_t(pg.num_rows) * pg.bit_width + 7) / 8), pi, 1u /*FJ_HYBRID*/, pg.num_rows, 0u});
+          const uint64_t nb = (uint64_t(pg.num_rows) * pg.bit_width + 7) / 8;
+          J j{0, take(0, nb), kNone, kNone, pi, 1u /*FJ_HYBRID*/, pg.num_rows, 0u};
+          if (nul) { j.voff = take(0, vbytes); j.toff = take(2, nb); }
+          js.push_back(j);
         } else if (pg.enc == DE_PLAIN && (kind == DK_I64 || kind == DK_F64)) {
           fr.fkind = FK_PLAIN8;
           fr.bw = 64;
-          js.push_back({0, take(1, uint64_t(pg.num_rows) * 8), pi, 2u /*FJ_COPY8*/, pg.num_rows, 1u});
+          J j{0, take(1, uint64_t(pg.num_rows) * 8), kNone, kNone, pi, 2u /*FJ_COPY8*/, pg.num_rows, 1u};
+          if (nul) j.voff = take(0, vbytes);
+          js.push_back(j);
         } else if (pg.enc == DE_PLAIN && kind == DK_BOOL) {
           fr.fkind = FK_BITS;
           fr.bw = 1;
-          js.push_back({0, take(1, (uint64_t(pg.num_rows) + 31) / 32 * 4), pi, 3u /*FJ_BITS*/, pg.num_rows, 1u});
+          J j{0, take(1, vbytes), kNone, kNone, pi, 3u /*FJ_BITS*/, pg.num_rows, 1u};
+          if (nul) j.voff = take(0, vbytes);
+          js.push_back(j);
+        } else if (pg.enc == DE_DELTA && nul) {
+          // values on demand (ensure_plain8); the validity bitmap is built now
+          js.push_back({0, 0, take(0, vbytes), kNone, pi, 5u /*FJ_VALID*/, pg.num_rows, 0u});
         } else {
-          continue;   // DELTA pages, PLAIN strings: k_scan
+          continue;   // DELTA pages without NULLs (decoded on demand), PLAIN strings: k_scan
         }
       }
     }
   if (js.empty()) return;
   const uint64_t zone1 = (zoff[0] + 255) & ~255ull;
-  flat_bytes = zone1 + zoff[1] + 256;
+  const uint64_t zone2 = (zone1 + zoff[1] + 255) & ~255ull;
+  flat_bytes = zone2 + zoff[2] + 256;
   PQB_CUDA(cudaMallocAsync((void**)&d_flat, flat_bytes, stream));
   PQB_CUDA(cudaMemsetAsync(d_flat, 0, zone1, stream));
-  PQB_CUDA(cudaMemsetAsync(d_flat + zone1 + zoff[1], 0, 256, stream));
-  struct DevJob { uint64_t src, dst; uint32_t page, kind, rows, pad; };   // == FlatStoreJob
+  PQB_CUDA(cudaMemsetAsync(d_flat + zone2, 0, zoff[2] + 256, stream));
+  struct DevJob { uint64_t src, dst, vdst, tmp; uint32_t page, kind, rows, pad; };   // == FlatStoreJob
   std::vector<DevJob> dj(js.size());
   for (size_t i = 0; i < js.size(); i++) {
     const uint64_t dst = js[i].zone ? zone1 + js[i].off : js[i].off;
-    dj[i] = {js[i].src, dst, js[i].page, js[i].kind, js[i].rows, 0u};
-    if (js[i].kind != 4u) flat_pages[js[i].page].off = dst;
+    dj[i] = {js[i].src, dst, js[i].voff, js[i].toff == kNone ? kNone : zone2 + js[i].toff, js[i].page, js[i].kind, js[i].rows, 0u};
+    if (js[i].kind == 4u) continue;
+    FlatPageRec& fr = flat_pages[js[i].page];
+    fr.voff = js[i].voff;
+    if (js[i].kind != 5u) fr.off = dst;
   }
   for (TableRowGroup& rg : row_groups)
     for (TableChunk& tc : rg.chunks)
@@ -883,17 +914,17 @@ void Table::build_flat_store(cudaStream_t stream) {
   PQB_CUDA(cudaStreamSynchronize(stream));
   PQB_CUDA(cudaFreeAsync(d_jobs, stream));
   PQB_CUDA(cudaFreeAsync(d_ok, stream));
-  size_t n_ok = 0;
+  size_t n_ok = 0, n_nul = 0;
   for (size_t i = 0; i < dj.size(); i++) {
     if (dj[i].kind == 4u) continue;
-    if (ok[i]) n_ok++;
-    else flat_pages[dj[i].page].fkind = FK_NONE;   // NULLs in the page (or a stream the walker refused): k_scan reads the original
+    if (ok[i]) { n_ok += dj[i].kind != 5u; n_nul += dj[i].vdst != kNone; }
+    else { flat_pages[dj[i].page].fkind = FK_NONE; flat_pages[dj[i].page].voff = kNone; }   // a stream the walker refused: k_scan reads the original
   }
   flat_page_count = n_ok;
   PQB_CUDA(cudaMallocAsync((void**)&d_flat_pages, flat_pages.size() * sizeof(FlatPageRec), stream));
   PQB_CUDA(cudaMemcpyAsync(d_flat_pages, flat_pages.data(), flat_pages.size() * sizeof(FlatPageRec), cudaMemcpyHostToDevice, stream));
   if (getenv("PQB_VERBOSE"))
-    fprintf(stderr, "[pqb] flat store: %zu of %zu pages, %llu bytes (arena %llu)\n", n_ok, pages.size(),
+    fprintf(stderr, "[pqb] flat store: %zu of %zu pages (%zu with NULLs), %llu bytes (arena %llu)\n", n_ok, pages.size(), n_nul,
             (unsigned long long)flat_bytes, (unsigned long long)arena_bytes);
 }
 
@@ -908,6 +939,7 @@ std::shared_ptr<Shape> Table::shape_for(const std::vector<int>& tcols, cudaStrea
   const uint32_t nrg = uint32_t(row_groups.size());
   sh->max_bw.assign(ncols, 0); sh->flat_max_bw.assign(ncols, 0);
   sh->has_dict.assign(ncols, 0); sh->has_plain.assign(ncols, 0); sh->has_delta.assign(ncols, 0); sh->flat_plain8.assign(ncols, 0);
+  sh->flat_nullable.assign(ncols, 0);
   std::vector<DevChunk> chunks(size_t(nrg) * std::max<uint32_t>(ncols, 1));
   std::vector<std::vector<uint32_t>> bounds;
   std::vector<uint32_t> common;
@@ -973,9 +1005,11 @@ std::shared_ptr<Shape> Table::shape_for(const std::vector<int>& tcols, cudaStrea
       sh->bitmap_words += (it.nrows + 31) / 32 + 1;
       if (flat)
         for (uint32_t s = 0; s < ncols; s++) {
+          if ((it.absent >> s) & 1u) continue;
           const FlatPageRec& fr = flat_pages[it.page[s]];
           if (fr.fkind == FK_PLAIN8) sh->flat_plain8[s] = 1;
           else sh->flat_max_bw[s] = std::max<uint32_t>(sh->flat_max_bw[s], fr.bw);
+          if (fr.voff != ~0ull) sh->flat_nullable[s] = 1;
         }
       it.fast = (flat ? kItemFlat : (fast ? kItemSlabIndexed : 0u));
       sh->n_flat += flat ? 1 : 0;
@@ -995,7 +1029,7 @@ std::shared_ptr<Shape> Table::shape_for(const std::vector<int>& tcols, cudaStrea
       cuts.clear();
       for (uint32_t s = 0; s < ncols; s++) {
         const TableChunk& tc = rg.chunks[tcols[s]];
-        if (!tc.present) { flat = false; continue; }
+        if (!tc.present) { it.absent |= 1u << s; continue; }   // missing from this file: all NULL (schema adapter behaviour)
         it.page[s] = page_of(s, it.row0, uint32_t(i));
         const DevPage& pg = pages[it.page[s]];
         const bool whole = pg.first_row == it.row0 && pg.num_rows == it.nrows;
@@ -1019,7 +1053,9 @@ std::shared_ptr<Shape> Table::shape_for(const std::vector<int>& tcols, cudaStrea
         pc.row0 = r;
         pc.nrows = cut - r;
         pc.global_row0 = rg.global_row0 + r;
+        pc.absent = it.absent;
         for (uint32_t s = 0; s < ncols; s++) {
+          if ((it.absent >> s) & 1u) continue;
           pc.page[s] = page_of(s, r, uint32_t(i));
           pc.poff[s] = r - pages[pc.page[s]].first_row;
         }
@@ -1053,38 +1089,45 @@ void Table::ensure_plain8(int tcol, cudaStream_t stream) const {
   if (cs.delta_ready || !cs.has_delta) return;
   const char* sw = getenv("PQB_FLAT");
   if (sw && sw[0] == '0') { cs.delta_ready = true; return; }
-  struct Job { uint32_t page, pad; uint64_t dst; };   // == DeltaJob
+  struct Job { uint32_t page, pad; uint64_t dst, vsrc, tmp; };   // == DeltaJob; offsets relative to d_flat
   std::vector<Job> jobs;
   uint64_t off = 0;
-  if (flat_pages.size() != pages.size()) flat_pages.assign(pages.size(), FlatPageRec{});
+  FlatPageRec blank{};
+  blank.voff = ~0ull;
+  if (flat_pages.size() != pages.size()) flat_pages.assign(pages.size(), blank);
+  auto take = [&](uint64_t bytes) { uint64_t o = off; off = (off + bytes + 16 + 15) & ~15ull; return o; };
   for (const TableRowGroup& rg : row_groups) {
     const TableChunk& tc = rg.chunks[tcol];
     if (!tc.present) continue;
     for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
       const uint32_t pi = tc.pages.first_page + k;
       if (pages[pi].enc != DE_DELTA || flat_pages[pi].fkind != FK_NONE) continue;
-      jobs.push_back({pi, 0u, off});
-      off = (off + uint64_t(pages[pi].num_rows) * 8 + 16 + 15) & ~15ull;
+      if (pages[pi].def_len && flat_pages[pi].voff == ~0ull && !d_flat_pages) continue;   // no flat store at all: the NULL classification never ran
+      Job j{pi, 0u, take(uint64_t(pages[pi].num_rows) * 8), flat_pages[pi].voff, ~0ull};
+      if (j.vsrc != ~0ull) j.tmp = take(uint64_t(pages[pi].num_rows) * 8);
+      jobs.push_back(j);
     }
   }
   if (!jobs.empty()) {
     PQB_CUDA(cudaMallocAsync((void**)&cs.d_delta_flat, off + 256, stream));
+    // offsets are relative to d_flat (the kernels add them to that one base); the subtraction may wrap, the sum does not
+    const uint64_t rel = uint64_t(cs.d_delta_flat) - uint64_t(d_flat);
+    for (Job& j : jobs) { j.dst += rel; if (j.tmp != ~0ull) j.tmp += rel; }
     void* d_jobs = nullptr;
     uint8_t* d_ok = nullptr;
     PQB_CUDA(cudaMallocAsync(&d_jobs, jobs.size() * sizeof(Job), stream));
     PQB_CUDA(cudaMallocAsync((void**)&d_ok, jobs.size(), stream));
     PQB_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, stream));
-    launch_delta_to_plain8(d_arena, d_pages, d_jobs, uint32_t(jobs.size()), cs.d_delta_flat, d_ok, stream);
+    launch_delta_to_plain8(d_arena, d_pages, d_jobs, uint32_t(jobs.size()), d_flat, d_ok, stream);
     std::vector<uint8_t> ok(jobs.size());
     PQB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, ok.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     PQB_CUDA(cudaFreeAsync(d_jobs, stream));
     PQB_CUDA(cudaFreeAsync(d_ok, stream));
     for (size_t i = 0; i < jobs.size(); i++) {
-      if (!ok[i]) continue;   // NULLs in the page: it stays with k_scan
+      if (!ok[i]) continue;   // a stream the decoder refused: the page stays with k_scan
       FlatPageRec& fr = flat_pages[jobs[i].page];
-      // offsets are relative to d_flat (the kernels add them to that one base); the subtraction may wrap, the sum does not
-      fr.off = uint64_t(cs.d_delta_flat + jobs[i].dst) - uint64_t(d_flat);
+      fr.off = jobs[i].dst;
       fr.rows = pages[jobs[i].page].num_rows;
       fr.bw = 64;
       fr.fkind = FK_PLAIN8;

@@ -477,8 +477,40 @@ def test_projection_bool_plain_and_time_range(data_dir, built):
         assert got[c].to_pylist() == exp[c].to_pylist(), c
 
 
-def test_projection_of_null_pages_is_an_error_not_a_wrong_answer(env):
+@pytest.mark.parametrize("name", ["c1_status_eq", "is_null", "or_mixed", "not_or"])
+def test_projection_with_nulls(env, name):
+    """2 % NULLs in every column: validity bitmaps and values of the selected rows equal the oracle's take()."""
     path, ora, prov = env["nulls"]
-    with pytest.raises(QueryError) as e:
-        prov.scan(projection=["host"], filters=FILTERS["c1_status_eq"])
-    assert e.value.code == L.PQ_ERR_UNSUPPORTED
+    flt = FILTERS[name]
+    cols = ["p_timestamp", "host", "message", "latency_ms", "cpu", "duration_s", "level", "status"]
+    res = prov.scan(projection=cols, filters=flt, row_ids=True)
+    exp, ids = _project_expect(ora, flt, cols)
+    got = res.table()
+    assert got.num_rows == len(ids) > 0
+    assert np.array_equal(got["__row_id"].to_numpy(), ids)
+    for c in cols:
+        assert got[c].to_pylist() == exp[c].to_pylist(), c
+        assert got[c].null_count == exp[c].null_count, c
+
+
+def test_projection_of_a_column_missing_from_one_file(data_dir, built):
+    """Schema evolution: a column that only newer files have reads as NULL for the old ones (schema adapter
+    behaviour of the reference's scan), in filters, group keys, aggregates and projections."""
+    a = pa.table({"k": pa.array(["x", "y", "x", "z"] * 500), "v": pa.array(np.arange(2000, dtype=np.int64))})
+    b = pa.table({"k": pa.array(["y", "z"] * 800), "v": pa.array(np.arange(1600, dtype=np.int64) * 3),
+                  "extra": pa.array(np.where(np.arange(1600) % 5 == 0, None, np.arange(1600) * 0.5), pa.float64(), from_pandas=True)})
+    pa_, pb_ = os.path.join(data_dir, "evo_a.parquet"), os.path.join(data_dir, "evo_b.parquet")
+    pq.write_table(a, pa_, compression="NONE")
+    pq.write_table(b, pb_, compression="NONE")
+    full = pa.concat_tables([a.append_column("extra", pa.nulls(a.num_rows, pa.float64())), b])
+    ora = Oracle(full)
+    prov = StandardTableProvider([pa_, pb_], schema=full.schema)
+    for flt in ([col("extra") > 100.0], [col("extra").is_null()], [~(col("extra") > 100.0) | (col("k") == "x")]):
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt), flt
+    flt = [col("v") >= 1500]
+    got = prov.scan(projection=["k", "extra", "v"], filters=flt).table()
+    exp, ids = _project_expect(ora, flt, ["k", "extra", "v"])
+    for c in ["k", "extra", "v"]:
+        assert got[c].to_pylist() == exp[c].to_pylist(), c
+    keys, aggs = ["k"], [count_star(), count("extra"), sum_("extra"), max_("extra")]
+    assert_tables_equal(prov.aggregate(keys, aggs).table(), ora.group_by(keys, aggs, []), keys)
