@@ -58,14 +58,16 @@ struct DevChunk {              // one column chunk (row group x referenced colum
 };
 
 // Flat store (flat_store.cuh): the scan-ready copy of one data page.
-enum FlatKind : uint8_t { FK_NONE = 0, FK_INDEX = 1, FK_PLAIN8 = 2, FK_BITS = 3 };
+enum FlatKind : uint8_t { FK_NONE = 0, FK_INDEX = 1, FK_PLAIN8 = 2, FK_BITS = 3, FK_BYTES = 4 };
 struct FlatPageRec {           // parallel to pages[]
   uint64_t off;                // byte offset in the flat buffer, 16-byte aligned: one slot per ROW (NULL rows hold 0)
   uint64_t voff;               // validity bitmap (1 bit per row, LSB first like Arrow), or ~0: the page holds no NULLs
   uint32_t rows;
   uint8_t bw;                  // FK_INDEX: bits per dictionary index; FK_BITS: 1
-  uint8_t fkind;               // FlatKind: FK_INDEX dictionary indices, FK_PLAIN8 8-byte values, FK_BITS boolean values
+  uint8_t fkind;               // FlatKind: FK_INDEX dictionary indices, FK_PLAIN8 8-byte values, FK_BITS boolean values,
+                               // FK_BYTES PLAIN byte arrays: one u32 per row = where the row's bytes start, relative to `base`
   uint16_t _pad;
+  uint64_t base;               // FK_BYTES: arena offset of the page's values section (a value's 4-byte length sits right before its bytes)
 };
 
 struct DevItem {               // unit of CTA work: rows between two page boundaries common to all columns

@@ -272,7 +272,11 @@ __global__ void __launch_bounds__(256) k_project(const __grid_constant__ ProjArg
               continue;
             }
             atomicOr(reinterpret_cast<uint32_t*>(f.out + pc.valid_off) + vword, vbit);
-            if (fp.fkind == FK_PLAIN8) {
+            if (fp.fkind == FK_BYTES) {   // PLAIN byte array: the row's bytes inside the page
+              const uint64_t e = fp.base + reinterpret_cast<const uint32_t*>(f.flat + fp.off)[row];
+              reinterpret_cast<unsigned long long*>(f.out + pc.src_off)[pos] = e;
+              reinterpret_cast<uint32_t*>(f.out + pc.len_off)[pos] = load_u32_unaligned(f.arena + e - 4);
+            } else if (fp.fkind == FK_PLAIN8) {
               reinterpret_cast<unsigned long long*>(f.out + pc.val_off)[pos] = reinterpret_cast<const unsigned long long*>(f.flat + fp.off)[row];
             } else if (fp.fkind == FK_BITS) {
               const uint32_t v = (reinterpret_cast<const uint32_t*>(f.flat + fp.off)[row >> 5] >> (row & 31)) & 1u;

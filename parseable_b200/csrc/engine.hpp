@@ -119,6 +119,7 @@ struct ColSide {
   uint32_t card = 0;
   KeyDict kd;                          // distinct values in group-id order
   uint32_t max_ent_len = 0;            // longest dictionary entry (sizes projected string buffers)
+  uint32_t max_plain_len = 0;          // longest value of the column's PLAIN byte-array pages
   bool has_delta = false;              // some page of the column is DELTA_BINARY_PACKED
   bool delta_ready = false;            // ... and its pages have aligned 8-byte copies in d_delta_flat (ensure_plain8)
   uint8_t* d_delta_flat = nullptr;
@@ -212,7 +213,7 @@ void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void
                           DevSlabRec* recs, DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream);
 // launches k_flat_store (flat_store.cuh); jobs are FlatStoreJob records on the device
 void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat, uint8_t* ok,
-                       cudaStream_t stream);
+                       uint32_t* maxlen, cudaStream_t stream);
 // side-table builders (prep_kernels.cuh), defined in query.cu
 void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, uint32_t* max_len, cudaStream_t stream);
 void launch_page_has_nulls(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, uint8_t* out, cudaStream_t stream);

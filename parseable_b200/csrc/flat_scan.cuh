@@ -121,6 +121,7 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
         const FlatPageRec fp = a.fpages[item.page[lane]];
         mycol.bw = fp.bw;
         mycol.fkind = fp.fkind;
+        if (fp.fkind == FK_BYTES) mycol.dict8 = fp.base;   // PLAIN byte arrays: arena offset of the page's values section
         mysrc = fp.off;
         mypoff = item.poff[lane];
         if (fp.voff != ~0ull) { mycol.flags = kColHasValid; myvsrc = fp.voff; }
@@ -229,10 +230,13 @@ __device__ __forceinline__ bool col_valid(const ColCtx& c, uint32_t row) {
 // ---- leaves -------------------------------------------------------------------------------------
 // Everything a consumer needs about one leaf for the CURRENT slab; built once per slab (warp uniform)
 // so that the row loops below carry no interpretation: the switch on the page kind sits outside them.
-enum LeafMode : uint32_t { LM_FALSE = 0, LM_TRUE = 1, LM_REGLUT = 2, LM_MEMLUT = 3, LM_PLAIN8 = 4, LM_BITS = 5 };
+enum LeafMode : uint32_t { LM_FALSE = 0, LM_TRUE = 1, LM_REGLUT = 2, LM_MEMLUT = 3, LM_PLAIN8 = 4, LM_BITS = 5, LM_BYTES = 6 };
 struct LeafCtx {
   ColCtx c;
   const uint8_t* lut;        // this leaf's LUT bytes for the chunk (global)
+  const uint8_t* bytes;      // LM_BYTES: the page's values section (PLAIN byte arrays: [len][bytes]...)
+  const uint8_t* needle;     // LM_BYTES: string literal / cooked LIKE pattern
+  uint32_t needle_len, like_flags;
   uint32_t lutreg;           // LM_REGLUT: the whole LUT, periodic with 2^bw
   uint32_t mode;             // LeafMode: the answer for a NON-NULL row
   uint32_t cmp;
@@ -253,7 +257,12 @@ __device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const 
   x.lit = (x.f64 && lf.kind == LK_CMP) ? f64_order_key(uint64_t(lf.lit_i64)) : lf.lit_i64;
   x.lut = a.luts + lf.lut_off + sc.lut_base;
   x.lutreg = st.lutreg[l];
+  x.bytes = a.arena + sc.dict8;
+  x.needle = a.lit_pool + lf.str_off;
+  x.needle_len = lf.str_len;
+  x.like_flags = lf.flags;
   if (lf.kind == LK_IS_NULL || lf.kind == LK_IS_NOT_NULL || x.c.absent) x.mode = LM_FALSE;   // answered by the validity alone
+  else if (sc.fkind == FK_BYTES) x.mode = LM_BYTES;
   else if (sc.fkind == FK_INDEX) {
     if ((st.regmask >> l) & 1u) x.mode = LM_REGLUT;
     else if (sc.bw == 0) x.mode = x.lut[0] ? LM_TRUE : LM_FALSE;   // one-entry dictionary: no bits at all
@@ -274,6 +283,14 @@ __device__ __forceinline__ bool leaf_row(const LeafCtx& x, uint32_t row) {
     case LM_REGLUT: return (__funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.c.colw, x.c.phase + row * x.c.bw)) & 1u) != 0;
     case LM_MEMLUT: return x.lut[col_index(x.c, row)] != 0;
     case LM_PLAIN8: return plain_cmp(reinterpret_cast<const uint64_t*>(x.c.colw)[row], x);
+    case LM_BYTES: {
+      // the string itself (no dictionary to answer for it): arrow-ord / arrow-string semantics on the raw bytes
+      const uint8_t* sp = x.bytes + bits32_at(x.c.colw, x.c.phase + row * 32);
+      const uint32_t len = load_u32_unaligned(sp - 4);
+      if (x.lkind == LK_CMP) return cmp_result(cmp_bytes(sp, len, x.needle, x.needle_len), x.cmp);
+      const bool t = like_match(sp, len, x.needle, x.needle_len, x.cmp, (x.like_flags & 2u) != 0);
+      return (x.like_flags & 1u) ? !t : t;
+    }
     default: {
       const uint32_t pb = x.c.phase + row;
       return cmp_i64(int64_t((x.c.colw[pb >> 5] >> (pb & 31)) & 1u), x.lit, x.cmp);
@@ -341,10 +358,19 @@ __device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w
 
 // dense comparison of one leaf over the thread's 32 rows [32*tc, 32*tc + 32) (blocked mapping); NULL rows
 // hold slot value 0 and are masked by the caller
-__device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, uint32_t R) {
+__device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, uint32_t R, uint32_t need) {
   switch (x.mode) {
     case LM_FALSE: return 0u;
     case LM_TRUE: return 0xffffffffu;
+    case LM_BYTES: {   // only the rows in `need` (in range, not NULL: a NULL row owns no bytes)
+      uint32_t m = 0, mm = need;
+      while (mm) {
+        const uint32_t k = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (leaf_row(x, tc * 32 + k)) m |= 1u << k;
+      }
+      return m;
+    }
     case LM_REGLUT:
     case LM_MEMLUT: {
       if (tc * 32 >= R) return 0u;   // a short slab (or a reduced slab size): nothing staged for this thread
@@ -467,7 +493,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
           if (x.lkind == LK_IS_NULL) { m &= ~V; continue; }
           m &= V;
           if (x.lkind == LK_IS_NOT_NULL) continue;
-          if (mx > 10) m &= leaf_dense(x, tc, R);
+          if (mx > 10) m &= leaf_dense(x, tc, R, m);
           else m = leaf_survivors(x, row0, m);
         }
       } else {
@@ -481,7 +507,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
             LeafCtx x;
             leaf_ctx(x, plan, a, st, base, L, op.arg);
             const uint32_t V = inr ? col_valid32(x.c, row0) : 0u;
-            stk[sp++] = tri_leaf(x, V, leaf_dense(x, tc, R));
+            stk[sp++] = tri_leaf(x, V, leaf_dense(x, tc, R, inr & V));
           } else if (op.kind == PK_CONST) stk[sp++] = {op.arg == 1 ? 0xffffffffu : 0u, op.arg == 2 ? 0xffffffffu : 0u};
           else if (op.kind == PK_NOT) stk[sp - 1] = tri_not(stk[sp - 1]);
           else { sp--; stk[sp - 1] = op.kind == PK_AND ? tri_and(stk[sp - 1], stk[sp]) : tri_or(stk[sp - 1], stk[sp]); }

@@ -94,12 +94,13 @@ __device__ inline bool def_levels_all_valid(const uint8_t* __restrict__ p, uint3
   return true;
 }
 
-enum FlatJobKind : uint32_t { FJ_HYBRID = 1, FJ_COPY8 = 2, FJ_BITS = 3, FJ_DICT8 = 4, FJ_VALID = 5 };
+enum FlatJobKind : uint32_t { FJ_HYBRID = 1, FJ_COPY8 = 2, FJ_BITS = 3, FJ_DICT8 = 4, FJ_VALID = 5, FJ_BYTES = 6 };
 // FJ_HYBRID: RLE / bit-packed hybrid stream -> flat bits       (page)
 // FJ_COPY8 : PLAIN 8-byte values -> aligned copy               (page)
 // FJ_BITS  : PLAIN boolean bits -> aligned copy                (page)
 // FJ_DICT8 : numeric dictionary (8-byte entries) -> aligned copy (src = arena offset, rows = entries)
 // FJ_VALID : validity bitmap only (a DELTA page with NULLs: its values follow on demand, ensure_plain8)
+// FJ_BYTES : PLAIN BYTE_ARRAY page (dictionary fallback, streams.rs:584-631) -> u32 start of every row's bytes
 // A page with NULLs (vdst != ~0) also gets its validity bitmap (1 bit per ROW, from the definition
 // levels) and its values EXPANDED to one slot per row (NULL rows hold 0), so that row r of the page
 // is slot r whatever the NULLs: the scan needs no rank / prefix popcount.
@@ -246,7 +247,7 @@ __device__ __forceinline__ void expand_rows(const uint32_t* __restrict__ valid, 
 
 __global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
                                                     const FlatStoreJob* __restrict__ jobs, uint32_t n_jobs,
-                                                    uint8_t* __restrict__ flat, uint8_t* __restrict__ ok_out) {
+                                                    uint8_t* __restrict__ flat, uint8_t* __restrict__ ok_out, uint32_t* __restrict__ maxlen_out) {
   __shared__ __align__(16) uint8_t tiles[4][kFlatTile + 16];
   __shared__ FlatRun runs_s[4][kFlatTileRuns];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,6 +279,41 @@ __global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ 
   }
   const uint8_t* vals = arena + pg.off + pg.val_off;
   if (job.kind == FJ_VALID) { if (lane == 0) ok_out[ji] = 1; return; }
+  if (job.kind == FJ_BYTES) {
+    // [len][bytes][len][bytes]...: a chain, walked by lane 0 out of shared-memory tiles; NULL rows own no bytes
+    uint32_t* offs = reinterpret_cast<uint32_t*>(flat + job.dst);
+    const uint64_t v0 = pg.off + pg.val_off, vend = pg.off + pg.len;
+    uint64_t p = v0;
+    uint32_t r = 0, bad = 0, maxlen = 0;
+    while (r < rows && !bad) {
+      const uint64_t t0 = p & ~15ull;
+      for (uint32_t o = lane * 16; o < uint32_t(kFlatTile) + 16; o += 32 * 16)
+        *reinterpret_cast<uint4*>(tile + o) = *reinterpret_cast<const uint4*>(arena + t0 + o);
+      __syncwarp();
+      if (lane == 0) {
+        while (r < rows) {
+          if (has_nulls && !((valid[r >> 5] >> (r & 31)) & 1u)) { offs[r++] = 0; continue; }
+          if (p + 4 > vend) { bad = 1; break; }
+          const uint32_t rel = uint32_t(p - t0);
+          if (rel + 4 > uint32_t(kFlatTile)) break;   // next length prefix is outside this tile
+          const uint32_t len = uint32_t(tile[rel]) | (uint32_t(tile[rel + 1]) << 8) | (uint32_t(tile[rel + 2]) << 16) | (uint32_t(tile[rel + 3]) << 24);
+          if (p + 4 + uint64_t(len) > vend) { bad = 1; break; }
+          if (len > maxlen) maxlen = len;
+          offs[r++] = uint32_t(p + 4 - v0);
+          p += 4 + uint64_t(len);
+        }
+      }
+      r = __shfl_sync(0xffffffffu, r, 0);
+      p = __shfl_sync(0xffffffffu, p, 0);
+      bad = __shfl_sync(0xffffffffu, bad, 0);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      ok_out[ji] = bad ? 0 : 1;
+      if (maxlen_out) maxlen_out[ji] = maxlen;
+    }
+    return;
+  }
   if (job.kind == FJ_COPY8) {
     if (uint64_t(pg.val_off) + uint64_t(nn) * 8 > pg.len) { if (lane == 0) ok_out[ji] = 0; return; }
     uint64_t* d = reinterpret_cast<uint64_t*>(flat + job.dst);

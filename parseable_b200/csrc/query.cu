@@ -207,9 +207,9 @@ void launch_flatten_pages(const uint8_t* arena, const DevPage* pages, const void
 }
 
 void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat, uint8_t* ok,
-                       cudaStream_t stream) {
+                       uint32_t* maxlen, cudaStream_t stream) {
   if (!n_jobs) return;
-  k_flat_store<<<(n_jobs + 3) / 4, 128, 0, stream>>>(arena, pages, static_cast<const FlatStoreJob*>(jobs), n_jobs, flat, ok);
+  k_flat_store<<<(n_jobs + 3) / 4, 128, 0, stream>>>(arena, pages, static_cast<const FlatStoreJob*>(jobs), n_jobs, flat, ok, maxlen);
   PQB_CUDA(cudaGetLastError());
 }
 
@@ -699,6 +699,7 @@ void Query::run(const PqQueryDesc& d) {
         auto cost = [&](size_t l) {
           const uint32_t s = uint32_t(slot_of[leaves[l].qcol]);
           if (leaves[l].d.kind == LK_IS_NULL || leaves[l].d.kind == LK_IS_NOT_NULL) return 0u;
+          if (plan.cols[s].kind == DK_STR && shape->has_plain[s]) return 200u;   // PLAIN byte arrays: compared string by string, last
           return shape->flat_plain8[s] ? 64u : std::max<uint32_t>(shape->flat_max_bw[s], shape->max_bw[s]);
         };
         return cost(a) < cost(b);
@@ -799,8 +800,8 @@ void Query::run(const PqQueryDesc& d) {
     plan.cols[s].max_bw = shape->max_bw[s];
     if (shape->has_delta[s] && plan.cols[s].kind != DK_I64)
       throw Error(PQ_ERR_UNSUPPORTED, "column '" + cname + "': DELTA_BINARY_PACKED is decoded for INT64 columns only");
-    if (shape->has_plain[s] && plan.cols[s].kind == DK_STR)
-      throw Error(PQ_ERR_UNSUPPORTED, "column '" + cname + "': PLAIN (dictionary-fallback) string pages are not decoded on the GPU yet");
+    if (shape->has_plain[s] && plan.cols[s].kind == DK_STR && shape->n_general)
+      throw Error(PQ_ERR_UNSUPPORTED, "column '" + cname + "': PLAIN (dictionary-fallback) string pages without a flat-store copy are not decoded on the GPU");
   }
   plan.n_items = uint32_t(items.size());
   metrics.bytes_scanned = scanned_bytes;
@@ -1399,7 +1400,7 @@ void Query::run(const PqQueryDesc& d) {
           if (pc.kind != DK_STR) continue;
           const ColSide& cs = table->sides[shape_cols[pc.slot]];
           pc.ent = cs.d_ent_off;
-          const uint64_t bound = cap * uint64_t(cs.max_ent_len);
+          const uint64_t bound = cap * uint64_t(std::max(cs.max_ent_len, cs.max_plain_len));
           if (bound > 0x7fffffffull) throw Error(PQ_ERR_UNSUPPORTED, "projected strings of one result exceed 2 GiB: add a LIMIT");
           pc.data_off = take(bound);
         }

@@ -875,6 +875,14 @@ void Table::build_flat_store(cudaStream_t stream) {
           J j{0, take(1, vbytes), kNone, kNone, pi, 3u /*FJ_BITS*/, pg.num_rows, 1u};
           if (nul) j.voff = take(0, vbytes);
           js.push_back(j);
+        } else if (pg.enc == DE_PLAIN && kind == DK_STR) {
+          // dictionary-fallback strings: one u32 per row = where its bytes start inside the page
+          fr.fkind = FK_BYTES;
+          fr.bw = 32;
+          fr.base = pg.off + pg.val_off;
+          J j{0, take(1, uint64_t(pg.num_rows) * 4), kNone, kNone, pi, 6u /*FJ_BYTES*/, pg.num_rows, 1u};
+          if (nul) j.voff = take(0, vbytes);
+          js.push_back(j);
         } else if (pg.enc == DE_DELTA && nul) {
           // values on demand (ensure_plain8); the validity bitmap is built now
           js.push_back({0, 0, take(0, vbytes), kNone, pi, 5u /*FJ_VALID*/, pg.num_rows, 0u});
@@ -905,15 +913,30 @@ void Table::build_flat_store(cudaStream_t stream) {
       if (tc.present && tc.dict8_off != ~0ull) tc.dict8_off = dj[tc.dict8_off].dst;
   void* d_jobs = nullptr;
   uint8_t* d_ok = nullptr;
+  uint32_t* d_maxlen = nullptr;
+  bool any_bytes = false;
+  for (const DevJob& j : dj) any_bytes |= j.kind == 6u;
   PQB_CUDA(cudaMallocAsync(&d_jobs, dj.size() * sizeof(DevJob), stream));
   PQB_CUDA(cudaMallocAsync((void**)&d_ok, dj.size(), stream));
+  if (any_bytes) {
+    PQB_CUDA(cudaMallocAsync((void**)&d_maxlen, dj.size() * 4, stream));
+    PQB_CUDA(cudaMemsetAsync(d_maxlen, 0, dj.size() * 4, stream));
+  }
   PQB_CUDA(cudaMemcpyAsync(d_jobs, dj.data(), dj.size() * sizeof(DevJob), cudaMemcpyHostToDevice, stream));
-  launch_flat_store(d_arena, d_pages, d_jobs, uint32_t(dj.size()), d_flat, d_ok, stream);
+  launch_flat_store(d_arena, d_pages, d_jobs, uint32_t(dj.size()), d_flat, d_ok, d_maxlen, stream);
   std::vector<uint8_t> ok(dj.size());
+  std::vector<uint32_t> maxlen(any_bytes ? dj.size() : 0);
   PQB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, ok.size(), cudaMemcpyDeviceToHost, stream));
+  if (any_bytes) PQB_CUDA(cudaMemcpyAsync(maxlen.data(), d_maxlen, maxlen.size() * 4, cudaMemcpyDeviceToHost, stream));
   PQB_CUDA(cudaStreamSynchronize(stream));
   PQB_CUDA(cudaFreeAsync(d_jobs, stream));
   PQB_CUDA(cudaFreeAsync(d_ok, stream));
+  if (d_maxlen) PQB_CUDA(cudaFreeAsync(d_maxlen, stream));
+  for (size_t i = 0; i < maxlen.size(); i++)
+    if (dj[i].kind == 6u && ok[i]) {
+      ColSide& cs = sides[pages[dj[i].page].chunk_slot];
+      cs.max_plain_len = std::max(cs.max_plain_len, maxlen[i]);
+    }
   size_t n_ok = 0, n_nul = 0;
   for (size_t i = 0; i < dj.size(); i++) {
     if (dj[i].kind == 4u) continue;

@@ -514,3 +514,49 @@ def test_projection_of_a_column_missing_from_one_file(data_dir, built):
         assert got[c].to_pylist() == exp[c].to_pylist(), c
     keys, aggs = ["k"], [count_star(), count("extra"), sum_("extra"), max_("extra")]
     assert_tables_equal(prov.aggregate(keys, aggs).table(), ora.group_by(keys, aggs, []), keys)
+
+
+def test_plain_byte_array_pages(data_dir, built):
+    """Dictionary-fallback strings (streams.rs:584-631: dictionary on, 1 MiB limit): a `message` column whose chunk
+    flips from RLE_DICTIONARY to PLAIN BYTE_ARRAY pages mid-way, a column written PLAIN from the start, NULLs in both;
+    LIKE / comparisons / IS NULL on the raw bytes, projection of the strings, COUNT over them."""
+    rng = np.random.default_rng(23)
+    n = 180_000
+    words = np.array(["timeout", "retry", "upstream", "cache", "db", "panic", "ok", "queued", "δ-error", "reset"])
+    uniq = np.array([f"req-{i:06d} " + " ".join(words[rng.integers(0, len(words), 4)]) for i in range(70_000)], dtype=object)
+    msg = uniq[rng.integers(0, len(uniq), n)]                        # ~36-byte strings, 70 000 distinct: the dictionary passes 1 MiB
+    msg[rng.random(n) < 0.03] = None
+    tag = np.array([f"t{i % 977}-{'x' * (i % 7)}" for i in range(n)], dtype=object)
+    tag[rng.random(n) < 0.01] = None
+    t = pa.table({"id": pa.array(np.arange(n, dtype=np.int64)), "message": pa.array(msg, pa.string()), "tag": pa.array(tag, pa.string()),
+                  "v": pa.array(rng.integers(0, 100, n).astype(np.int64))})
+    p = os.path.join(data_dir, "plain_strings.parquet")
+    pq.write_table(t, p, compression="NONE", row_group_size=90_000, use_dictionary=["message", "v"], dictionary_pagesize_limit=1 << 20,
+                   data_page_size=256 << 10)
+    encs = {c.path_in_schema: set(c.encodings) for rg in range(2) for c in [pq.ParquetFile(p).metadata.row_group(rg).column(i) for i in range(4)]}
+    assert "PLAIN" in encs["message"] and "RLE_DICTIONARY" in encs["message"], encs      # the chunk really flips
+    ora = Oracle(t)
+    prov = StandardTableProvider([p], schema=t.schema)
+    flts = {
+        "like_contains": [col("message").like("%panic%")],
+        "like_and_dict": [col("message").like("%timeout%") & (col("v") < 10)],
+        "eq_plain_only": [col("tag") == "t5-xxxxx"],
+        "range": [(col("tag") >= "t90") & (col("tag") < "t91")],
+        "ilike_prefix": [col("message").ilike("REQ-0000%")],
+        "not_like_or_null": [col("message").like("%ok%", negated=True) | col("tag").is_null()],
+        "is_null": [col("message").is_null()],
+        "multibyte": [col("message").like("%δ-error%δ-error%")],
+    }
+    for name, flt in flts.items():
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt), name
+    flt = flts["like_and_dict"]
+    got = prov.scan(projection=["id", "message", "tag"], filters=flt).table()
+    exp, ids = _project_expect(ora, flt, ["id", "message", "tag"])
+    assert len(ids) > 100
+    for c in ["id", "message", "tag"]:
+        assert got[c].to_pylist() == exp[c].to_pylist(), c
+    keys, aggs = ["v"], [count_star(), count("message"), count("tag")]
+    assert_tables_equal(prov.aggregate(keys, aggs, flts["like_contains"]).table(), ora.group_by(keys, aggs, flts["like_contains"]), keys)
+    with pytest.raises(QueryError) as e:       # group keys need a dictionary (interned ids): refused, never mis-grouped
+        prov.aggregate(["message"], [count_star()])
+    assert e.value.code == L.PQ_ERR_UNSUPPORTED
