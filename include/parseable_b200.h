@@ -151,6 +151,16 @@ typedef struct {
   int32_t col; /* index into PqQueryDesc.columns; ignored for COUNT_STAR */
 } PqAgg;
 
+/* ---- computed GROUP BY keys: the counts / histogram API groups by DATE_BIN(<width>, p_timestamp, origin)
+ *      (src/query/mod.rs:623-680) ---- */
+typedef enum { PQ_KEY_COLUMN = 0, PQ_KEY_DATE_BIN = 1 } PqKeyKind;
+typedef struct {
+  int32_t kind;       /* PqKeyKind */
+  int32_t _pad;
+  int64_t width_ms;   /* DATE_BIN: stride in milliseconds (> 0) */
+  int64_t origin_ms;  /* DATE_BIN: origin, milliseconds since the epoch (the reference passes 1970-01-01) */
+} PqKeyExpr;
+
 /* ---- inputs ---- */
 typedef struct {
   const char* path;   /* file to read, or NULL when buf is given */
@@ -199,6 +209,10 @@ typedef struct {
   uint32_t shard_index;
   uint32_t shard_count; /* 0 or 1: no sharding */
   uint32_t flags;
+
+  /* NULL, or n_group_by entries: how group_by[k] becomes a key (plain column | DATE_BIN of a Timestamp / Int64 column);
+   * a DATE_BIN key comes back as a Timestamp(ms) column named date_bin(<column>) holding the bin start */
+  const PqKeyExpr* group_exprs;
 } PqQueryDesc;
 
 #define PQ_QUERY_COUNT_ONLY 1u    /* filter scan: only rows_selected is wanted, emit no batches */

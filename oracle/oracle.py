@@ -183,7 +183,19 @@ class Oracle:
         n = self.n
         sel = self.select(filters) if filters else None
         key_codes, key_valid, key_decode = [], [], []
-        for k in keys:
+        keys = list(keys)
+        for ki, k in enumerate(keys):
+            if hasattr(k, "width_ms"):
+                # DATE_BIN(width, column, origin): DataFusion's date_bin floors towards minus infinity
+                # (datafusion-functions 53.1.0 date_bin.rs: a negative remainder moves one stride down);
+                # /root/reference/src/query/mod.rs:623-680 is the call site (the counts API)
+                c = self.col(k.column)
+                codes = np.ascontiguousarray(np.floor_divide(c.values.astype(np.int64) - k.origin_ms, k.width_ms) * k.width_ms + k.origin_ms)
+                key_decode.append(("i64", pa.timestamp("ms")))
+                key_codes.append(codes)
+                key_valid.append(c.valid)
+                keys[ki] = k.name
+                continue
             c = self.col(k)
             if c.kind == "str":
                 arr = self.table[k].combine_chunks()

@@ -50,6 +50,10 @@ class PqColumn(C.Structure):
     _fields_ = [("name", C.c_char_p), ("type", C.c_int32), ("_pad", C.c_int32)]
 
 
+class PqKeyExpr(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("width_ms", C.c_int64), ("origin_ms", C.c_int64)]
+
+
 class PqQueryDesc(C.Structure):
     _fields_ = [
         ("table", C.c_void_p), ("files", C.POINTER(PqFile)), ("n_files", C.c_uint32),
@@ -60,7 +64,11 @@ class PqQueryDesc(C.Structure):
         ("aggs", C.POINTER(PqAgg)), ("n_aggs", C.c_uint32),
         ("limit", C.c_int64), ("batch_size", C.c_uint32),
         ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("flags", C.c_uint32),
+        ("group_exprs", C.POINTER(PqKeyExpr)),
     ]
+
+
+PQ_KEY_COLUMN, PQ_KEY_DATE_BIN = 0, 1
 
 
 class PqMetrics(C.Structure):

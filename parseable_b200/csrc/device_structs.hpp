@@ -135,7 +135,7 @@ struct DevAgg {
   uint8_t _pad[2];
 };
 
-enum DevKeyKind : uint8_t { KK_DICT_LUT = 0, KK_BOOL = 1 };
+enum DevKeyKind : uint8_t { KK_DICT_LUT = 0, KK_BOOL = 1, KK_BIN = 2 };   // KK_BIN: DATE_BIN of an Int64 / Timestamp column
 struct DevKey {
   uint8_t col;
   uint8_t kind;       // DevKeyKind
@@ -144,6 +144,8 @@ struct DevKey {
   uint32_t stride;    // mixed-radix stride of this key in the dense group slot
   uint32_t _pad2;
   const uint32_t* gid;  // gid LUT of the key column (u32 per dictionary entry, entry = chunk.lut_base + idx)
+  int64_t bin_base;     // KK_BIN: start of bin 0 (the lowest bin any scanned row group can hold, from footer statistics)
+  int64_t bin_width;    // KK_BIN: stride; group id = floor((value - bin_base) / bin_width)
 };
 
 enum ScanMode : uint32_t { SM_FILTER = 0, SM_AGG = 1 };

@@ -62,7 +62,8 @@ struct FinishKey {
   uint64_t data_off;           // strings: bytes
   uint32_t stride, card;
   uint32_t kind;               // DevKind
-  uint32_t _pad;
+  uint32_t is_bin;             // DATE_BIN key: value = bin_base + group id * bin_width
+  int64_t bin_base, bin_width;
 };
 struct FinishArgs {
   const unsigned long long* acc;
@@ -120,7 +121,8 @@ __global__ void k_agg_finish(const __grid_constant__ FinishArgs f) {
       if (valid && gid) atomicOr(reinterpret_cast<uint32_t*>(f.out + key.val_off) + word, bit);
     } else {
       unsigned long long v = 0;
-      if (valid) {
+      if (valid && key.is_bin) v = (unsigned long long)(key.bin_base + (long long)gid * key.bin_width);
+      else if (valid) {
         const uint8_t* p = key.kd_bytes + key.kd_offs[gid];
         for (int b = 0; b < 8; b++) v |= (unsigned long long)p[b] << (8 * b);
       }

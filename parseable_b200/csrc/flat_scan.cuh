@@ -656,6 +656,27 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
               const uint32_t pb = c.phase + r;
               slot[i] += ((c.colw[pb >> 5] >> (pb & 31)) & 1u) * stride;
             }
+        } else if (key.kind == KK_BIN) {
+          // DATE_BIN: the key is computed from the value.  value - bin_base >= 0 and < 2^53 (checked on the host from the
+          // footer statistics), so one double multiply and a fix-up replace a 64-bit division
+          const bool plain = c.fkind == FK_PLAIN8;
+          const uint64_t* __restrict__ dict = reinterpret_cast<const uint64_t*>(a.flat + st.col[key.col].dict8);
+          const uint64_t* v8 = reinterpret_cast<const uint64_t*>(c.colw);
+          const double inv = 1.0 / double(key.bin_width);
+          const long long w = key.bin_width, b0 = key.bin_base;
+#pragma unroll
+          for (int i = 0; i < kAggRowsMax; i++)
+            if ((sel >> i) & 1u) {
+              const uint32_t r = tc + i * kAggConsumers;
+              if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
+              const long long x = (long long)(plain ? v8[r] : dict[col_index(c, r)]) - b0;
+              long long q = (long long)(double(x) * inv);
+              long long rem = x - q * w;
+              if (rem < 0) { q--; rem += w; }
+              if (rem >= w) q++;
+              const uint32_t g = (q < 0 || q >= (long long)key.card) ? key.card - 1 : uint32_t(q);   // statistics were wrong: clamp, never out of the table
+              slot[i] += g * stride;
+            }
         } else {
           const uint32_t* __restrict__ gid = key.gid + st.col[key.col].lut_base;
 #pragma unroll

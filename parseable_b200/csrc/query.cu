@@ -851,7 +851,7 @@ void Query::run(const PqQueryDesc& d) {
   }
 
   // ---- GROUP BY keys: interned per table column (cached with the table) ----
-  struct QKey { const KeyDict* kd = nullptr; uint32_t card = 0; };
+  struct QKey { const KeyDict* kd = nullptr; uint32_t card = 0; bool is_bin = false; };
   std::vector<QKey> qk(d.n_group_by);
   plan.nkeys = d.n_group_by;
   uint64_t launches = 0;
@@ -859,6 +859,55 @@ void Query::run(const PqQueryDesc& d) {
     DevKey& key = plan.keys[k];
     key.col = uint8_t(slot_of[d.group_by[k]]);
     const uint8_t kind = plan.cols[key.col].kind;
+    if (d.group_exprs && d.group_exprs[k].kind == PQ_KEY_DATE_BIN) {
+      // ---- DATE_BIN(width, column, origin) (the counts / histogram API, src/query/mod.rs:623-680): the key is
+      // computed from the value; the bins any scanned row can fall into come from the footer statistics ----
+      const PqKeyExpr& gx = d.group_exprs[k];
+      const std::string& cname = table->columns[tcol[d.group_by[k]]].name;
+      if (kind != DK_I64) throw Error(PQ_ERR_INVALID_ARG, "DATE_BIN needs a Timestamp / Int64 column, '" + cname + "' is neither");
+      if (gx.width_ms <= 0) throw Error(PQ_ERR_INVALID_ARG, "DATE_BIN needs a positive stride");
+      int64_t vmin = INT64_MAX, vmax = INT64_MIN;
+      for (uint32_t g = 0; g < nrg_table; g++) {
+        if (!rg_live[g]) continue;
+        const TableChunk& tc = table->row_groups[g].chunks[shape_cols[key.col]];
+        if (!tc.present) continue;
+        const ColumnStats& st = tc.meta->stats;
+        if (st.null_count >= 0 && uint64_t(st.null_count) == uint64_t(tc.meta->num_values)) continue;   // all NULL: no bins
+        if (!st.has_min || !st.has_max || st.min.size() != 8 || st.max.size() != 8)
+          throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN over '" + cname + "' needs min / max statistics in the file footers");
+        int64_t mn, mx;
+        std::memcpy(&mn, st.min.data(), 8);
+        std::memcpy(&mx, st.max.data(), 8);
+        vmin = std::min(vmin, mn);
+        vmax = std::max(vmax, mx);
+      }
+      auto floordiv = [](int64_t a, int64_t b) { int64_t q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; };
+      int64_t bmin = 0, bmax = 0;
+      if (vmin <= vmax) {
+        if (vmin < gx.origin_ms - (int64_t(1) << 52) || vmax > gx.origin_ms + (int64_t(1) << 52))
+          throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN: values more than 2^52 ms away from the origin");
+        bmin = floordiv(vmin - gx.origin_ms, gx.width_ms);
+        bmax = floordiv(vmax - gx.origin_ms, gx.width_ms);
+      }
+      if (multi) {   // every rank needs the same bin 0 and the same number of bins
+        long long mm[2] = {(long long)bmin, -(long long)bmax};
+        if (vmin > vmax) { mm[0] = INT64_MAX; mm[1] = INT64_MAX; }
+        DevBuf<unsigned long long> dmm;
+        dmm.alloc(2, stream);
+        PQB_CUDA(cudaMemcpyAsync(dmm.p, mm, 16, cudaMemcpyHostToDevice, stream));
+        comm_allreduce_u64(dmm.p, 2, 1 /*signed min*/, stream);
+        PQB_CUDA(cudaMemcpyAsync(mm, dmm.p, 16, cudaMemcpyDeviceToHost, stream));
+        PQB_CUDA(cudaStreamSynchronize(stream));
+        if (mm[0] == INT64_MAX) { bmin = bmax = 0; } else { bmin = mm[0]; bmax = -mm[1]; }
+      }
+      if (bmax - bmin + 1 > (int64_t(1) << 24)) throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN: more than 2^24 bins in the scanned range");
+      key.kind = KK_BIN;
+      key.bin_width = gx.width_ms;
+      key.bin_base = gx.origin_ms + bmin * gx.width_ms;
+      qk[k].card = uint32_t(bmax - bmin + 1);
+      qk[k].is_bin = true;
+      continue;
+    }
     key.kind = kind == DK_BOOL ? KK_BOOL : KK_DICT_LUT;
     if (key.kind == KK_BOOL) { qk[k].card = 2; continue; }
     if (plan.cols[key.col].has_plain || plan.cols[key.col].has_delta)
@@ -877,7 +926,7 @@ void Query::run(const PqQueryDesc& d) {
     // all-reduce per query checks that EVERY rank still holds it (a rank may have reopened its table) ----
     uint32_t have = 1;
     for (uint32_t k = 0; k < d.n_group_by; k++) {
-      if (plan.keys[k].kind == KK_BOOL) continue;
+      if (plan.keys[k].kind != KK_DICT_LUT) continue;
       const ColSide& cs = table->sides[shape_cols[plan.keys[k].col]];
       if (!cs.glob_ready || cs.glob_epoch != comm_epoch()) have = 0;
     }
@@ -893,7 +942,7 @@ void Query::run(const PqQueryDesc& d) {
     }
     for (uint32_t k = 0; k < d.n_group_by; k++) {
       DevKey& key = plan.keys[k];
-      if (key.kind == KK_BOOL) continue;
+      if (key.kind != KK_DICT_LUT) continue;
       const int tc_i = shape_cols[key.col];
       if (!have) table->unify_key(tc_i, stream);
       const ColSide& cs = table->sides[tc_i];
@@ -927,6 +976,9 @@ void Query::run(const PqQueryDesc& d) {
   const uint32_t n_general = flat_ok ? shape->n_general : uint32_t(items.size());
   const uint32_t n_fast_items = shape->n_slab_fast;
 
+  for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++)
+    if (plan.keys[k].kind == KK_BIN && n_general)
+      throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN keys need a flat-store copy of every page the query reads");
   mark("side tables ready");
   // ---- shared-memory layout of k_scan (items the flat kernels do not take) ----
   SmemLayout L{};
@@ -1247,7 +1299,11 @@ void Query::run(const PqQueryDesc& d) {
         if (kind == DK_BOOL) fk.val_off = take(uint64_t(nbatches) * wpb * 4);
         else if (kind == DK_STR) fk.val_off = take((uint64_t(n_out) + 1) * 4);
         else fk.val_off = take(uint64_t(n_out) * 8);
-        if (kind != DK_BOOL) {
+        if (qk[k].is_bin) {
+          fk.is_bin = 1;
+          fk.bin_base = plan.keys[k].bin_base;
+          fk.bin_width = plan.keys[k].bin_width;
+        } else if (kind != DK_BOOL) {
           const ColSide& cs = table->sides[shape_cols[plan.keys[k].col]];
           if (multi) {   // the dictionary every rank agreed on
             fk.kd_offs = cs.d_glob_kd_offs;
@@ -1324,8 +1380,8 @@ void Query::run(const PqQueryDesc& d) {
           if (c < d.n_group_by) {
             const FinishKey& fk = fa.keys[c];
             const uint32_t qc = uint32_t(d.group_by[c]);
-            oc.name = d.columns[qc].name;
-            oc.type = out_type_of(qc);
+            oc.name = fk.is_bin ? std::string("date_bin(") + d.columns[qc].name + ")" : std::string(d.columns[qc].name);
+            oc.type = fk.is_bin ? PQ_T_TS_MS : out_type_of(qc);
             oc.ext_validity_off = fk.valid_off + uint64_t(b) * wpb * 4;
             if (fk.kind == DK_STR) { oc.ext_offsets_off = fk.val_off + uint64_t(r0) * 4; oc.ext_off = fk.data_off; }
             else if (fk.kind == DK_BOOL) oc.ext_off = fk.val_off + uint64_t(b) * wpb * 4;

@@ -98,6 +98,29 @@ _AGG_CODE = {"count_star": L.PQ_AGG_COUNT_STAR, "count": L.PQ_AGG_COUNT, "sum": 
              "min": L.PQ_AGG_MIN, "max": L.PQ_AGG_MAX, "avg": L.PQ_AGG_AVG}
 
 
+@dataclass(frozen=True)
+class DateBin:
+    """GROUP BY DATE_BIN(width, column, origin): the counts / histogram API of the reference
+    (src/query/mod.rs:623-680 builds `DATE_BIN('1m', p_timestamp, TIMESTAMP '1970-01-01 00:00:00+00')`)."""
+    width_ms: int
+    column: str = DEFAULT_TIMESTAMP_KEY
+    origin_ms: int = 0
+
+    @property
+    def name(self) -> str:
+        return f"date_bin({self.column})"
+
+
+_INTERVALS = {"s": 1000, "m": 60_000, "h": 3_600_000, "d": 86_400_000}
+
+
+def date_bin(width: str | int, column: str = DEFAULT_TIMESTAMP_KEY, origin_ms: int = 0) -> DateBin:
+    """``date_bin("5m")``: widths like the reference's '1m' | '5m' | '1h' | '1d', or milliseconds."""
+    if isinstance(width, str):
+        width = int(width[:-1]) * _INTERVALS[width[-1]]
+    return DateBin(int(width), column, origin_ms)
+
+
 def count_star(): return Agg("count_star")
 def count(c): return Agg("count", c)
 def sum_(c): return Agg("sum", c)
@@ -336,7 +359,13 @@ class StandardTableProvider:
             pred = e if pred is None else Expr("and", (pred, e))
         if pred is not None:
             d.compile_pred(pred, ops)
-        gb = [d.col_index(c) for c in group_by]
+        gb = [d.col_index(c.column if isinstance(c, DateBin) else c) for c in group_by]
+        gx = None
+        if any(isinstance(c, DateBin) for c in group_by):
+            gx = (L.PqKeyExpr * len(group_by))()
+            for i, c in enumerate(group_by):
+                if isinstance(c, DateBin):
+                    gx[i].kind, gx[i].width_ms, gx[i].origin_ms = L.PQ_KEY_DATE_BIN, c.width_ms, c.origin_ms
         ag = []
         for a in aggs:
             ag.append(L.PqAgg(fn=_AGG_CODE[a.fn], col=d.col_index(a.column) if a.column is not None else -1))
@@ -361,6 +390,8 @@ class StandardTableProvider:
         if gb:
             arr_gb = (C.c_int32 * len(gb))(*gb)
             desc.group_by, desc.n_group_by = arr_gb, len(gb)
+            if gx is not None:
+                desc.group_exprs = gx
         if ag:
             arr_ag = (L.PqAgg * len(ag))(*ag)
             desc.aggs, desc.n_aggs = arr_ag, len(ag)

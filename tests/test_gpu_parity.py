@@ -560,3 +560,24 @@ def test_plain_byte_array_pages(data_dir, built):
     with pytest.raises(QueryError) as e:       # group keys need a dictionary (interned ids): refused, never mis-grouped
         prov.aggregate(["message"], [count_star()])
     assert e.value.code == L.PQ_ERR_UNSUPPORTED
+
+
+# ---- the counts / histogram API: GROUP BY DATE_BIN(width, p_timestamp, origin) (src/query/mod.rs:623-680) ----
+@pytest.mark.parametrize("tag", ["nn", "nulls"])
+def test_date_bin_counts(env, tag):
+    from parseable_b200.query import date_bin
+    path, ora, prov = env[tag]
+    for width, extra, flt in (("1m", [], []), ("5m", ["level"], [col("status") == 200]), (7_000, ["status", "region"], [col("latency_ms") > 50])):
+        keys = [date_bin(width)] + extra
+        aggs = [count_star(), sum_("bytes"), max_("cpu")]
+        got = prov.aggregate(keys, aggs, flt).table()
+        exp = ora.group_by(keys, aggs, flt)
+        assert got.column_names[0] == "date_bin(p_timestamp)" and pa.types.is_timestamp(got.schema.field(0).type)
+        assert_tables_equal(got, exp, ["date_bin(p_timestamp)"] + extra)
+    # a time range that cuts the table plus bins: what the UI histogram asks for
+    ts = ora.table["p_timestamp"].drop_null().cast(pa.int64()).to_numpy()
+    lo, hi = int(np.quantile(ts, 0.2)), int(np.quantile(ts, 0.7))
+    from parseable_b200.query import Timestamp
+    rng_f = [col("p_timestamp") >= Timestamp(lo), col("p_timestamp") < Timestamp(hi)]
+    got = prov.aggregate([date_bin("1m")], [count_star()], rng_f).table()
+    assert_tables_equal(got, ora.group_by([date_bin("1m")], [count_star()], rng_f), ["date_bin(p_timestamp)"])
