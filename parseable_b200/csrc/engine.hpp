@@ -149,6 +149,7 @@ struct Shape {
   uint32_t bitmap_words = 0;
   std::vector<uint32_t> max_bw, flat_max_bw;          // per slot
   std::vector<uint8_t> has_dict, has_plain, has_delta, flat_plain8, flat_nullable;   // flat_nullable: some flat page of the slot carries a validity bitmap
+  std::string why_general;             // first reason an item could not go to the flat kernels (diagnostics)
   std::atomic<unsigned long long> last_total{~0ull};   // rows the last filter scan of this shape selected (sizes the next result)
   ~Shape();
 };
@@ -189,6 +190,7 @@ class Table {
   mutable std::vector<FlatPageRec> flat_pages;   // host copy, parallel to pages (ensure_plain8 adds entries later)
   mutable FlatPageRec* d_flat_pages = nullptr;
   uint64_t flat_page_count = 0;
+  bool nulls_classified = false;         // build_flat_store looked at every page's definition levels (voff == ~0 then means: no NULLs)
 
   // lazily built, query independent (the table is immutable once opened); guarded by side_mu
   mutable std::mutex side_mu;

@@ -87,8 +87,8 @@ __device__ __forceinline__ uint32_t flat_col_bytes(uint32_t phase, uint32_t bw, 
 
 // ---- producer: one warp; lane 0 owns the queue, the barriers and the TMA copies ------------------
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  // mbarrier.try_wait suspends the thread in hardware for a bounded time: no sleep / back-off code around it
-  while (!mbar_try_wait(bar, parity)) {}
+  // mbarrier.try_wait parks the thread in hardware until the phase completes or the hint runs out
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {}
 }
 
 __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout& L, const DevScanArgs& a, FlatCtl& ctl,
@@ -233,10 +233,10 @@ __device__ __forceinline__ bool col_valid(const ColCtx& c, uint32_t row) {
 enum LeafMode : uint32_t { LM_FALSE = 0, LM_TRUE = 1, LM_REGLUT = 2, LM_MEMLUT = 3, LM_PLAIN8 = 4, LM_BITS = 5, LM_BYTES = 6 };
 struct LeafCtx {
   ColCtx c;
-  const uint8_t* lut;        // this leaf's LUT bytes for the chunk (global)
-  const uint8_t* bytes;      // LM_BYTES: the page's values section (PLAIN byte arrays: [len][bytes]...)
-  const uint8_t* needle;     // LM_BYTES: string literal / cooked LIKE pattern
-  uint32_t needle_len, like_flags;
+  const uint8_t* lut;        // this leaf's LUT bytes for the chunk (global); LM_BYTES: the page's values section instead
+                             // (PLAIN byte arrays: [len][bytes]...)
+  const DevLeaf* lf;         // LM_BYTES: string literal / cooked LIKE pattern live in the plan + literal pool
+  const uint8_t* lit_pool;
   uint32_t lutreg;           // LM_REGLUT: the whole LUT, periodic with 2^bw
   uint32_t mode;             // LeafMode: the answer for a NON-NULL row
   uint32_t cmp;
@@ -257,12 +257,10 @@ __device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const 
   x.lit = (x.f64 && lf.kind == LK_CMP) ? f64_order_key(uint64_t(lf.lit_i64)) : lf.lit_i64;
   x.lut = a.luts + lf.lut_off + sc.lut_base;
   x.lutreg = st.lutreg[l];
-  x.bytes = a.arena + sc.dict8;
-  x.needle = a.lit_pool + lf.str_off;
-  x.needle_len = lf.str_len;
-  x.like_flags = lf.flags;
+  x.lf = &lf;
+  x.lit_pool = a.lit_pool;
   if (lf.kind == LK_IS_NULL || lf.kind == LK_IS_NOT_NULL || x.c.absent) x.mode = LM_FALSE;   // answered by the validity alone
-  else if (sc.fkind == FK_BYTES) x.mode = LM_BYTES;
+  else if (sc.fkind == FK_BYTES) { x.mode = LM_BYTES; x.lut = a.arena + sc.dict8; }
   else if (sc.fkind == FK_INDEX) {
     if ((st.regmask >> l) & 1u) x.mode = LM_REGLUT;
     else if (sc.bw == 0) x.mode = x.lut[0] ? LM_TRUE : LM_FALSE;   // one-entry dictionary: no bits at all
@@ -285,11 +283,12 @@ __device__ __forceinline__ bool leaf_row(const LeafCtx& x, uint32_t row) {
     case LM_PLAIN8: return plain_cmp(reinterpret_cast<const uint64_t*>(x.c.colw)[row], x);
     case LM_BYTES: {
       // the string itself (no dictionary to answer for it): arrow-ord / arrow-string semantics on the raw bytes
-      const uint8_t* sp = x.bytes + bits32_at(x.c.colw, x.c.phase + row * 32);
+      const uint8_t* sp = x.lut + bits32_at(x.c.colw, x.c.phase + row * 32);
       const uint32_t len = load_u32_unaligned(sp - 4);
-      if (x.lkind == LK_CMP) return cmp_result(cmp_bytes(sp, len, x.needle, x.needle_len), x.cmp);
-      const bool t = like_match(sp, len, x.needle, x.needle_len, x.cmp, (x.like_flags & 2u) != 0);
-      return (x.like_flags & 1u) ? !t : t;
+      const uint8_t* needle = x.lit_pool + x.lf->str_off;
+      if (x.lkind == LK_CMP) return cmp_result(cmp_bytes(sp, len, needle, x.lf->str_len), x.cmp);
+      const bool t = like_match(sp, len, needle, x.lf->str_len, x.cmp, (x.lf->flags & 2u) != 0);
+      return (x.lf->flags & 1u) ? !t : t;
     }
     default: {
       const uint32_t pb = x.c.phase + row;

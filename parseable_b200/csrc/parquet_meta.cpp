@@ -73,10 +73,11 @@ ColumnStats parse_stats(ThriftReader& r) {
       default: r.skip(t);
     }
   }
-  // Deprecated min/max are only trustworthy for signed-ordered types; callers
-  // that prune on them check the physical type.  Prefer min_value/max_value.
-  if (!s.has_min && has_old_min) { s.min = old_min; s.has_min = true; }
-  if (!s.has_max && has_old_max) { s.max = old_max; s.has_max = true; }
+  // The deprecated min / max (fields 1, 2) were written with SIGNED byte order for byte arrays by old writers:
+  // they are only kept as a fallback here and only USED for signed-ordered physical types
+  // (parse_column_meta drops them for BYTE_ARRAY / FIXED_LEN_BYTE_ARRAY / BOOLEAN below).
+  if (!s.has_min && has_old_min) { s.min = old_min; s.has_min = true; s.deprecated_min_max = true; }
+  if (!s.has_max && has_old_max) { s.max = old_max; s.has_max = true; s.deprecated_min_max = true; }
   return s;
 }
 
@@ -101,6 +102,12 @@ ColumnChunkMeta parse_column_meta(ThriftReader& r) {
       case 12: if (t == T_STRUCT) c.stats = parse_stats(r); else r.skip(t); break;
       default: r.skip(t);
     }
+  }
+  // deprecated statistics order non-numeric types the wrong way round (signed bytes): never prune on them
+  if (c.stats.deprecated_min_max && c.type != PT_INT32 && c.type != PT_INT64 && c.type != PT_FLOAT && c.type != PT_DOUBLE) {
+    c.stats.has_min = c.stats.has_max = false;
+    c.stats.min.clear();
+    c.stats.max.clear();
   }
   return c;
 }

@@ -28,6 +28,7 @@ struct ColumnStats {
   bool has_min = false, has_max = false;
   std::string min, max;  // PLAIN-encoded min_value / max_value
   int64_t null_count = -1;
+  bool deprecated_min_max = false;   // taken from the deprecated Statistics.min / max (fields 1, 2)
 };
 
 struct ColumnChunkMeta {

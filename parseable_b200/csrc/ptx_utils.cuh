@@ -35,6 +35,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint
+// (nanoseconds) runs out, instead of returning at once — a waiting warp then issues a handful of
+// instructions per wake-up, not a spin loop (profiles/k_flat_agg_r2a: the bare loop was 14 % of all
+// executed instructions)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // back off between polls: a spinning warp competes for issue slots with the warps it waits for
   // (profiles/k_scan_r1g: a third of all executed instructions were this loop)

@@ -309,12 +309,12 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
       for (uint32_t k = 0; k < tc.pages.n_pages; k++)
         if (t.flat_pages[tc.pages.first_page + k].fkind == FK_INDEX) { cand.push_back(g); cand.push_back(tc.pages.first_page + k); }
     }
-    const size_t npg = cand.size() / 2, want = std::min<size_t>(npg, 512);
+    const size_t npg = cand.size() / 2, want = std::min<size_t>(npg, 192);
     for (size_t i = 0; i < want; i++) {
       const size_t j = i * npg / want;
       const uint32_t g = cand[2 * j], pi = cand[2 * j + 1];
       const FlatPageRec& fr = t.flat_pages[pi];
-      sp.push_back({fr.off, std::min<uint32_t>(fr.rows, 4096), fr.bw, side.base_per_rg[g], t.row_groups[g].chunks[tcol].dict_n});
+      sp.push_back({fr.off, std::min<uint32_t>(fr.rows, 2048), fr.bw, side.base_per_rg[g], t.row_groups[g].chunks[tcol].dict_n});
     }
     if (!sp.empty()) {
       DevBuf<KeySamplePage> d_sp; d_sp.upload(sp, stream);
@@ -978,7 +978,7 @@ void Query::run(const PqQueryDesc& d) {
 
   for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++)
     if (plan.keys[k].kind == KK_BIN && n_general)
-      throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN keys need a flat-store copy of every page the query reads");
+      throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN keys need a flat-store copy of every page the query reads: " + shape->why_general);
   mark("side tables ready");
   // ---- shared-memory layout of k_scan (items the flat kernels do not take) ----
   SmemLayout L{};
@@ -1124,7 +1124,7 @@ void Query::run(const PqQueryDesc& d) {
   const bool projecting = want_rows && d.n_projection > 0;
   if (projecting && n_general)
     throw Error(PQ_ERR_UNSUPPORTED, "projection of column values needs a flat-store copy of every page it reads: PLAIN (dictionary-fallback) "
-                                    "string pages are not projected on the GPU yet");
+                                    "string pages are not projected on the GPU yet: " + shape->why_general);
   plan.write_bitmap = want_rows ? 1 : 0;
   DevBuf<uint32_t> d_bitmap, d_item_counts;
   // k_scan ORs partial words into its bitmap regions: they start zeroed.  The flat filter kernel stores

@@ -830,6 +830,7 @@ void Table::build_flat_store(cudaStream_t stream) {
     PQB_CUDA(cudaMemcpyAsync(has_nulls.data(), d_nf, pages.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     PQB_CUDA(cudaFreeAsync(d_nf, stream));
+    nulls_classified = true;
   }
   struct J { uint64_t src, off, voff, toff; uint32_t page, kind, rows, zone; };
   std::vector<J> js;
@@ -1059,7 +1060,12 @@ std::shared_ptr<Shape> Table::shape_for(const std::vector<int>& tcols, cudaStrea
         if (!whole || !(pg.flags & 1u)) fast = false;
         // every page of this column under the item needs a flat copy; their starts cut the item into pieces
         for (uint32_t pi = it.page[s]; pi < tc.pages.first_page + tc.pages.n_pages && pages[pi].first_row < row_end; pi++) {
-          if (flat_pages.empty() || flat_pages[pi].fkind == FK_NONE) flat = false;
+          if (flat_pages.empty() || flat_pages[pi].fkind == FK_NONE) {
+            flat = false;
+            if (sh->why_general.empty())
+              sh->why_general = "column '" + columns[tcols[s]].name + "', row group " + std::to_string(g) + ", page " + std::to_string(pi - tc.pages.first_page) +
+                                " (encoding " + std::to_string(pages[pi].enc) + ", " + std::to_string(pages[pi].num_rows) + " rows) has no flat-store copy";
+          }
           if (pages[pi].first_row > it.row0) cuts.push_back(pages[pi].first_row);
         }
       }
@@ -1125,7 +1131,7 @@ void Table::ensure_plain8(int tcol, cudaStream_t stream) const {
     for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
       const uint32_t pi = tc.pages.first_page + k;
       if (pages[pi].enc != DE_DELTA || flat_pages[pi].fkind != FK_NONE) continue;
-      if (pages[pi].def_len && flat_pages[pi].voff == ~0ull && !d_flat_pages) continue;   // no flat store at all: the NULL classification never ran
+      if (pages[pi].def_len && !nulls_classified) continue;   // nobody looked at the definition levels: the page may hold NULLs
       Job j{pi, 0u, take(uint64_t(pages[pi].num_rows) * 8), flat_pages[pi].voff, ~0ull};
       if (j.vsrc != ~0ull) j.tmp = take(uint64_t(pages[pi].num_rows) * 8);
       jobs.push_back(j);

@@ -54,7 +54,13 @@ class ThriftReader {
     uint8_t h = byte();
     elem = h & 0x0f;
     size = h >> 4;
-    if (size == 15) size = uint32_t(varint());
+    if (size == 15) {
+      const uint64_t n = varint();
+      // every element takes at least one byte: a count beyond the remaining bytes is a crafted / corrupt footer
+      // (callers reserve() on it)
+      if (n > uint64_t(end_ - p_)) throw ThriftError("thrift: list longer than the buffer");
+      size = uint32_t(n);
+    }
   }
   std::string binary() {
     uint64_t n = varint();
@@ -71,6 +77,7 @@ class ThriftReader {
     return d;
   }
   void skip(uint8_t type) {
+    struct Depth { int& d; Depth(int& x) : d(x) { if (++d > kMaxDepth) throw ThriftError("thrift: nesting too deep"); } ~Depth() { --d; } } guard(depth_);
     switch (type) {
       case T_TRUE: case T_FALSE: break;
       case T_BYTE: byte(); break;
@@ -90,6 +97,7 @@ class ThriftReader {
       }
       case T_MAP: {
         uint64_t n = varint();
+        if (n > uint64_t(end_ - p_)) throw ThriftError("thrift: map longer than the buffer");
         if (n) {
           uint8_t kv = byte();
           for (uint64_t i = 0; i < n; i++) { skip_elem(kv >> 4); skip_elem(kv & 0x0f); }
@@ -110,6 +118,8 @@ class ThriftReader {
   void skip_elem(uint8_t t) {
     if (t == T_TRUE || t == T_FALSE) byte(); else skip(t);
   }
+  static constexpr int kMaxDepth = 64;   // skip() / skip_struct() recurse on nested containers
+  int depth_ = 0;
   const uint8_t* p_;
   const uint8_t* end_;
   const uint8_t* begin_;
