@@ -282,6 +282,29 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------ GPU arm
+def pin_to_gpu_numa(local_rank: int) -> dict:
+    """Bind this rank to the CPU NUMA node its GPU hangs off, before any pinned host buffer is allocated
+    (first touch puts the file images on that node): at N > 1 the ranks' H2D copies then do not cross sockets."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "why": "no NUMA information for the GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "gpu": bdf}
+    except Exception as e:                               # best effort: never fail the bench over placement
+        return {"numa_node": None, "why": f"{type(e).__name__}: {e}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -424,8 +447,14 @@ def main():
     # ================= e2e: host buffers (page-locked file images), H2D + D2H inside every step =================
     e2e = None
     hfs = None
+    numa = None
     if not args.skip_e2e:
+        # the pinned file images are filled (first touch) from the NUMA node of this rank's GPU; the thread's affinity is
+        # restored right after, so that the CPU legs further down keep every core
+        aff = os.sched_getaffinity(0)
+        numa = pin_to_gpu_numa(local_rank)
         hfs = [HostFile(path=p, pinned=True) for p in files]
+        os.sched_setaffinity(0, aff)
         prov_e = StandardTableProvider(hfs, schema=sch)
         for _ in range(2):
             re_ = prov_e.aggregate(keys, aggs, tf, flags=ar_flag)
@@ -579,7 +608,7 @@ def main():
         "roofline": roof("k_flat_agg (+k_acc_reduce)", k_ms, algo_bytes, "k_flat_agg_dram_bytes_per_launch"),
         "allreduce_ms": sum(ar_ms) / len(ar_ms), "device_ms_per_step": sum(dev_ms) / len(dev_ms),
         "e2e": e2e, "gpu_launches": launches, "clocks": clk, "cpu_baseline": cpu_baseline,
-        "d2h_bytes_per_step_resident": d2h_res, "c2": c2,
+        "d2h_bytes_per_step_resident": d2h_res, "c2": c2, "numa": numa,
     }
     q = sorted(step_ms)
     line["step_ms_quantiles"] = {"p10": q[len(q) // 10], "p50": q[len(q) // 2], "p90": q[(len(q) * 9) // 10]}

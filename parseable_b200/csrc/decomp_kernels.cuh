@@ -145,7 +145,7 @@ __global__ void k_page_fixup(DevPage* __restrict__ pages, const uint32_t* __rest
   if (i >= n) return;
   DevPage p = pages[which[i]];
   const uint8_t* payload = arena + p.off;
-  uint32_t pos = 0;
+  uint32_t pos = p.val_off;   // v2 pages: the level bytes in front of the values (lengths from the page header); v1: 0
   if (p.def_len == 0xffffffffu) {  // v1 page of a nullable column: 4-byte length + RLE definition levels
     uint32_t dl = 0;
     if (p.len >= 4) dl = uint32_t(payload[0]) | (uint32_t(payload[1]) << 8) | (uint32_t(payload[2]) << 16) | (uint32_t(payload[3]) << 24);

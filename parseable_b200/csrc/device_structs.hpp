@@ -22,7 +22,8 @@ constexpr int kFastDirEntries = 16;   // slab index: run-directory entry budget 
 constexpr int kRecBatch = 16;         // slab records a CTA keeps in shared memory at a time
 
 // page value encodings as the kernels see them
-enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2, DE_RLE_BOOL = 3 };
+enum DevEnc : uint8_t { DE_DICT = 0, DE_PLAIN = 1, DE_DELTA = 2, DE_RLE_BOOL = 3,
+                        DE_DELTA_BYTES = 4, DE_DELTA_LEN_BYTES = 5 /* both only while a table opens: rewritten to DE_PLAIN */ };
 // DE_DICT and DE_RLE_BOOL carry an RLE / bit-packed hybrid value stream (staged + walked)
 #define PQB_ENC_HAS_STREAM(e) ((e) == ::pqb::DE_DICT || (e) == ::pqb::DE_RLE_BOOL)
 // ... and DE_DELTA pages are staged too (their own walker: block / miniblock headers)
@@ -44,6 +45,15 @@ struct DevPage {               // one data page
   uint32_t slab0;              // first record of this page in the table's slab index
   uint32_t flags;              // host copy only: bit 0 = every slab of the page is in the slab index
 };
+
+// DELTA_BYTE_ARRAY / DELTA_LENGTH_BYTE_ARRAY pages are rewritten as PLAIN BYTE_ARRAY pages at table open (flat_store.cuh)
+struct DbaJob {
+  uint32_t page;
+  uint32_t with_prefix;   // 1 DELTA_BYTE_ARRAY, 0 DELTA_LENGTH_BYTE_ARRAY (no prefix stream)
+  uint64_t len_tmp;       // scratch: prefix lengths [rows] then suffix lengths [rows] (u32), byte offset in the scratch buffer
+  uint64_t dst;           // k_dba_materialise: byte offset of the new page payload in the materialised buffer
+};
+struct DbaInfo { uint64_t bytes; uint32_t nvals; uint32_t data_pos; uint32_t ok; uint32_t _pad; };
 
 struct DevChunk {              // one column chunk (row group x referenced column)
   uint64_t dict_off;           // arena offset of the PLAIN dictionary payload
@@ -179,7 +189,9 @@ struct DevPlan {
   uint32_t fast_and;           // 1: the predicate is leaf AND leaf AND ... (1-4 CMP/LIKE leaves): specialised pass
   uint32_t conj;               // 1: the predicate is a pure conjunction of leaves (flat kernels: survivors-only evaluation)
   uint32_t hot_slots;          // flat aggregate kernel: group slots < hot_slots accumulate in shared memory
+  uint32_t lane_slots;         // flat aggregate kernel: the first lane_slots (hottest) group slots own one shared-memory cell per lane
   uint32_t flat_krows;         // flat aggregate kernel: rows per consumer thread per slab
+  uint32_t direct8;            // flat aggregate kernel: 8-byte values are read in place from the flat store, not staged
   uint32_t flat_slab_rows;     // rows per slab of the flat kernels
   uint32_t no_flat;            // 1: the flat kernels do not run (NULL literal in the predicate, PQB_FLAT_SCAN=0): k_scan takes every item
   uint32_t replicas;           // accumulator table copies in global memory; CTA b adds into copy b % replicas (merged by k_acc_reduce)

@@ -174,6 +174,7 @@ class Table {
   // scan kernel would otherwise derive by walking the run headers; see DESIGN.md
   DevSlabRec* d_slab_recs = nullptr;
   DirEntry* d_slab_dirs = nullptr;
+  uint8_t* d_strmat = nullptr;            // DELTA_BYTE_ARRAY pages rewritten as PLAIN BYTE_ARRAY pages (outside the arena: DevPage.off wraps)
   uint8_t* d_slab_flat = nullptr;         // flat bit-packed copies of run-heavy pages (k_flatten_pages)
   uint64_t slab_flat_bytes = 0;
   uint64_t total_slabs = 0;
@@ -218,6 +219,10 @@ void launch_flat_store(const uint8_t* arena, const DevPage* pages, const void* j
                        uint32_t* maxlen, cudaStream_t stream);
 // side-table builders (prep_kernels.cuh), defined in query.cu
 void launch_entry_offsets(const Table& t, int tcol, uint64_t* d_out, uint32_t* max_len, cudaStream_t stream);
+void launch_dba_lengths(const uint8_t* arena, const DevPage* pages, const DbaJob* jobs, uint32_t n_jobs, uint8_t* scratch, DbaInfo* info, cudaStream_t stream);
+void launch_dba_materialise(const uint8_t* arena, const DevPage* pages, const DbaJob* jobs, const DbaInfo* info, uint32_t n_jobs,
+                            const uint8_t* scratch, uint8_t* mat, cudaStream_t stream);
+void launch_check_flat_indices(const uint8_t* flat, const FlatPageRec* fpages, const uint32_t* dict_n, uint32_t n_pages, uint32_t* first_bad, cudaStream_t stream);
 void launch_page_has_nulls(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, uint8_t* out, cudaStream_t stream);
 void launch_delta_to_plain8(const uint8_t* arena, const DevPage* pages, const void* jobs, uint32_t n_jobs, uint8_t* flat_base, uint8_t* ok,
                             cudaStream_t stream);

@@ -14,8 +14,8 @@
 // stage back through its `empty` mbarrier.  No block barrier inside the loop, no run directory, no
 // header walk: value i of a page is bits [i*bw, (i+1)*bw).
 //
-// k_flat_filter: 8 consumer warps, a thread owns 32 consecutive rows = one word of the selection
-//   bitmap.  First leaf: all 32 indices unpacked with compile-time shifts; a dictionary of <= 32
+// k_flat_filter: 4 consumer warps, a thread owns two words of the selection bitmap per slab (32
+//   consecutive rows each; the per-slab set-up of a leaf is paid once for both).  First leaf: all 32 indices unpacked with compile-time shifts; a dictionary of <= 32
 //   entries keeps its whole LUT in ONE REGISTER (3 instructions per row: extract, rotate, funnel).
 //   Later leaves of a conjunction run only on the surviving rows.  HBM traffic = encoded bytes once
 //   + 1 bit per row.
@@ -36,9 +36,10 @@
 namespace pqb {
 
 constexpr int kFlatStagesMax = 4;
-constexpr int kFilterConsumerWarps = 8;
+constexpr int kFilterConsumerWarps = 4;
+constexpr int kFilterWords = 2;                                    // 32-row bitmap words per consumer thread per slab
 constexpr int kFilterThreads = 32 * (kFilterConsumerWarps + 1);
-constexpr int kFilterSlabRows = 32 * 32 * kFilterConsumerWarps;   // 8192: one 32-row word per consumer thread
+constexpr int kFilterSlabRows = 32 * 32 * kFilterWords * kFilterConsumerWarps;   // 8192
 constexpr int kAggThreads = 1024;
 constexpr int kAggConsumers = kAggThreads - 32;
 
@@ -52,7 +53,7 @@ struct FlatLayout {              // dynamic shared memory of the flat kernels (b
   uint32_t total;
 };
 
-constexpr uint32_t kColHasValid = 1u, kColAbsent = 2u;
+constexpr uint32_t kColHasValid = 1u, kColAbsent = 2u, kColDirect = 4u;
 struct FlatStageCol {
   uint64_t dict8;                // flat-store offset of the aligned numeric dictionary (~0: none)
   uint32_t bw;                   // bits per value (FK_PLAIN8: 64, FK_BITS: 1)
@@ -152,9 +153,16 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
       mycol.phase = uint32_t(bit0 & 127u);
       mycol.vphase = uint32_t(vbit0 & 127u);
       // a column that is only projected is not staged: the gather after the scan reads its selected rows
-      const uint32_t nb = staged ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
+      // plan.direct8 (k_flat_agg): 8-byte values are not staged -- a thread reads its rows' values straight from the flat
+      // store (row-interleaved threads: fully coalesced, each value used once); dict8 then carries where row 0 of the slab is
+      const bool direct = plan.direct8 && mycol.fkind == FK_PLAIN8;
+      const uint32_t nb = (staged && !direct) ? flat_col_bytes(mycol.phase, mycol.bw, R) : 0u;
       const uint32_t vnb = (staged && (mycol.flags & kColHasValid)) ? flat_col_bytes(mycol.vphase, 1, R) : 0u;
-      if (lane < ncols) st.col[lane] = mycol;
+      if (lane < ncols) {
+        FlatStageCol sc = mycol;
+        if (direct) { sc.dict8 = mysrc + uint64_t(mypoff + r0) * 8; sc.flags |= kColDirect; sc.phase = 0; }
+        st.col[lane] = sc;
+      }
       if (lane < plan.nleaves) st.lutreg[lane] = mylut;
       uint32_t bytes = nb + vnb;
       for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
@@ -199,9 +207,11 @@ struct ColCtx {
   uint32_t bw, mask, dict_max, fkind;
   bool absent;               // column missing from this file: every row NULL
 };
-__device__ __forceinline__ void col_ctx(ColCtx& c, const FlatStage& st, const uint8_t* base, const FlatLayout& L, uint32_t col) {
+__device__ __forceinline__ void col_ctx(ColCtx& c, const FlatStage& st, const uint8_t* base, const FlatLayout& L, uint32_t col,
+                                        const uint8_t* flat) {
   const FlatStageCol& sc = st.col[col];
-  c.colw = reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
+  c.colw = (sc.flags & kColDirect) ? reinterpret_cast<const uint32_t*>(flat + sc.dict8)   // 8-byte values read in place (k_flat_agg)
+                                   : reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
   c.phase = sc.phase & 31u;
   c.vw = (sc.flags & kColHasValid) ? reinterpret_cast<const uint32_t*>(base + L.col_voff[col]) + (sc.vphase >> 5) : nullptr;
   c.vphase = sc.vphase & 31u;
@@ -250,7 +260,7 @@ __device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const 
   const DevLeaf& lf = plan.leaves[l];
   const uint32_t c = lf.col;
   const FlatStageCol& sc = st.col[c];
-  col_ctx(x.c, st, stage_base, L, c);
+  col_ctx(x.c, st, stage_base, L, c, a.flat);
   x.cmp = lf.cmp;
   x.lkind = lf.kind;
   x.f64 = plan.cols[c].kind == DK_F64;
@@ -424,7 +434,7 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
     }
     default: {
       // LM_PLAIN8: transposed over the warp (lane L reads row base + 32 j + L: conflict free), lane j keeps word j
-      const uint32_t lane = threadIdx.x & 31, wbase = (tc & ~31u) * 32;
+      const uint32_t lane = threadIdx.x & 31, wbase = (tc - lane) * 32;   // the warp's 32 consecutive words: lane j owns word (tc - lane) + j
       const uint64_t* v8 = reinterpret_cast<const uint64_t*>(x.c.colw);
       uint32_t mine = 0;
 #pragma unroll 4
@@ -457,7 +467,7 @@ __device__ __forceinline__ Tri32 tri_or(Tri32 a, Tri32 b) {
 __device__ __forceinline__ Tri32 tri_not(Tri32 a) { return {~(a.t | a.n), a.n}; }
 
 // ---- k_flat_filter ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFilterThreads, 3)
+__global__ void __launch_bounds__(kFilterThreads, 6)
 k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   FlatCtl& ctl = *reinterpret_cast<FlatCtl*>(smem);
@@ -468,8 +478,10 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
     flat_producer(plan, L, a, ctl, smem, plan.flat_slab_rows);
     return;
   }
-  const uint32_t tc = threadIdx.x;      // consumer thread: rows [32 tc, 32 tc + 32) of every slab
-  const uint32_t row0 = tc * 32;
+  // consumer thread: bitmap words warp * 64 + h * 32 + lane (h = 0, 1) of every slab, rows [32 word, 32 word + 32)
+  uint32_t word[kFilterWords];
+#pragma unroll
+  for (int h = 0; h < kFilterWords; h++) word[h] = warp * 32 * kFilterWords + h * 32 + lane;
   uint32_t stage = 0, par = 0;
   for (;;) {
     mbar_wait_spin(&ctl.full[stage], par);
@@ -477,27 +489,39 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
     if (st.item == 0xffffffffu) break;
     const uint32_t R = st.R;
     const uint8_t* base = smem + L.stage0 + stage * L.stage_bytes;
-    const uint32_t inr = row0 >= R ? 0u : (R - row0 >= 32 ? 0xffffffffu : ((1u << (R - row0)) - 1u));
-    uint32_t m = inr;
+    uint32_t inr[kFilterWords], m[kFilterWords];
+#pragma unroll
+    for (int h = 0; h < kFilterWords; h++) {
+      const uint32_t row0 = word[h] * 32;
+      inr[h] = row0 >= R ? 0u : (R - row0 >= 32 ? 0xffffffffu : ((1u << (R - row0)) - 1u));
+      m[h] = inr[h];
+    }
     if (plan.npred) {
       if (plan.conj) {
         // conjunction: a row passes when every leaf is TRUE (a NULL leaf drops it).  First leaf on every row,
         // the others on the survivors only (or dense when many survive)
         for (uint32_t l = 0; l < plan.nleaves; l++) {
-          const uint32_t mx = l ? __reduce_max_sync(0xffffffffu, __popc(m)) : 32u;
+          uint32_t pc = 0;
+#pragma unroll
+          for (int h = 0; h < kFilterWords; h++) pc += __popc(m[h]);
+          const uint32_t mx = l ? __reduce_max_sync(0xffffffffu, pc) : 64u;
           if (mx == 0) break;
           LeafCtx x;
           leaf_ctx(x, plan, a, st, base, L, l);
-          const uint32_t V = inr ? col_valid32(x.c, row0) : 0u;
-          if (x.lkind == LK_IS_NULL) { m &= ~V; continue; }
-          m &= V;
-          if (x.lkind == LK_IS_NOT_NULL) continue;
-          if (mx > 10) m &= leaf_dense(x, tc, R, m);
-          else m = leaf_survivors(x, row0, m);
+          const bool dense = mx > 12;
+#pragma unroll
+          for (int h = 0; h < kFilterWords; h++) {
+            const uint32_t V = inr[h] ? col_valid32(x.c, word[h] * 32) : 0u;
+            if (x.lkind == LK_IS_NULL) { m[h] &= ~V; continue; }
+            m[h] &= V;
+            if (x.lkind == LK_IS_NOT_NULL) continue;
+            if (dense) m[h] &= leaf_dense(x, word[h], R, m[h]);
+            else m[h] = leaf_survivors(x, word[h] * 32, m[h]);
+          }
         }
       } else {
         // general boolean program, SQL three-valued logic (NULLs come from validity bitmaps and NULL literals)
-        Tri32 stk[kPredStack];
+        Tri32 stk[kFilterWords][kPredStack];
         int sp = 0;
 #pragma unroll 1
         for (uint32_t i = 0; i < plan.npred; i++) {
@@ -505,17 +529,37 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
           if (op.kind == PK_LEAF) {
             LeafCtx x;
             leaf_ctx(x, plan, a, st, base, L, op.arg);
-            const uint32_t V = inr ? col_valid32(x.c, row0) : 0u;
-            stk[sp++] = tri_leaf(x, V, leaf_dense(x, tc, R, inr & V));
-          } else if (op.kind == PK_CONST) stk[sp++] = {op.arg == 1 ? 0xffffffffu : 0u, op.arg == 2 ? 0xffffffffu : 0u};
-          else if (op.kind == PK_NOT) stk[sp - 1] = tri_not(stk[sp - 1]);
-          else { sp--; stk[sp - 1] = op.kind == PK_AND ? tri_and(stk[sp - 1], stk[sp]) : tri_or(stk[sp - 1], stk[sp]); }
+#pragma unroll
+            for (int h = 0; h < kFilterWords; h++) {
+              const uint32_t V = inr[h] ? col_valid32(x.c, word[h] * 32) : 0u;
+              stk[h][sp] = tri_leaf(x, V, leaf_dense(x, word[h], R, inr[h] & V));
+            }
+            sp++;
+          } else if (op.kind == PK_CONST) {
+#pragma unroll
+            for (int h = 0; h < kFilterWords; h++) stk[h][sp] = {op.arg == 1 ? 0xffffffffu : 0u, op.arg == 2 ? 0xffffffffu : 0u};
+            sp++;
+          } else if (op.kind == PK_NOT) {
+#pragma unroll
+            for (int h = 0; h < kFilterWords; h++) stk[h][sp - 1] = tri_not(stk[h][sp - 1]);
+          } else {
+            sp--;
+#pragma unroll
+            for (int h = 0; h < kFilterWords; h++)
+              stk[h][sp - 1] = op.kind == PK_AND ? tri_and(stk[h][sp - 1], stk[h][sp]) : tri_or(stk[h][sp - 1], stk[h][sp]);
+          }
         }
-        m = stk[0].t & inr;
+#pragma unroll
+        for (int h = 0; h < kFilterWords; h++) m[h] = stk[h][0].t & inr[h];
       }
     }
-    if (plan.write_bitmap && row0 < R) a.bitmap[st.bitmap_word0 + (st.r0 >> 5) + tc] = m;
-    const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(m));
+    uint32_t pc = 0;
+#pragma unroll
+    for (int h = 0; h < kFilterWords; h++) {
+      if (plan.write_bitmap && word[h] * 32 < R) a.bitmap[st.bitmap_word0 + (st.r0 >> 5) + word[h]] = m[h];
+      pc += __popc(m[h]);
+    }
+    const uint32_t cnt = __reduce_add_sync(0xffffffffu, pc);
     const uint32_t item = st.item;
     __syncwarp();
     if (lane == 0) {
@@ -532,7 +576,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
 // selection mask, then one pass per GROUP BY key into slot[], then one pass per aggregate.  Every
 // decision that does not depend on the row (page kind, bit width, aggregate function, pointers) is
 // made once per pass, outside the row loop.
-constexpr int kAggRowsMax = 8;
+constexpr int kAggRowsMax = 8;   // k_flat_agg<KR>: KR = 8, 4, 2 rows per thread and slab
 
 // shared-memory cells are 8 bytes like the global ones; per-CTA partial counts and the low words of
 // partial sums are updated with native 32-bit atomics
@@ -554,19 +598,27 @@ __device__ __forceinline__ void cell_min_max(unsigned long long* cell, bool hot,
   else atomicMax(reinterpret_cast<long long*>(cell), k);
 }
 
+// Cell index of a group slot inside the hot table.  The plan.lane_slots hottest groups (slots 0 .. T-1: the
+// hot-first numbering puts them there) own one cell PER LANE, so that the lanes of a warp never meet on them: on
+// skewed keys a fifth of a warp's rows belong to one group, and same-address shared-memory atomics (all the more the
+// 64-bit CAS loops behind f64 SUM and i64 MIN / MAX) retire one lane at a time.
+//   slot <  T : cell = slot * 32 + lane          slot >= T : cell = slot + 31 T
+// Cold slots (cell >= hot cells) go to the global table at cell - 31 T = slot.
+template <int KR>
 __global__ void __launch_bounds__(kAggThreads, 1)
 k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   FlatCtl& ctl = *reinterpret_cast<FlatCtl*>(smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t H = plan.hot_slots, nslots = plan.nslots;
+  const uint32_t H = plan.hot_slots, nslots = plan.nslots, T = plan.lane_slots;
+  const uint32_t Hs = H + 31u * T;   // cells per plane of the hot table
   const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
   unsigned long long* sacc = reinterpret_cast<unsigned long long*>(smem + L.acc);
   // this CTA's copy of the global table (plan.replicas copies spread same-address traffic over L2; k_acc_reduce merges them)
   unsigned long long* gacc = a.acc + size_t(blockIdx.x % plan.replicas) * cells * nslots;
   flat_ctl_init(ctl, L.nstages, kAggConsumers / 32);
-  for (uint32_t i = threadIdx.x; i < cells * H; i += kAggThreads) {
-    const uint32_t arr = i / H;
+  for (uint32_t i = threadIdx.x; i < cells * Hs; i += kAggThreads) {
+    const uint32_t arr = i / Hs;
     unsigned long long init = 0;
     if (arr >= 1 && arr < 1 + plan.n_acc) {
       const uint8_t k = plan.acc_init[arr - 1];
@@ -576,9 +628,10 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
   }
   __syncthreads();
   const uint32_t S = plan.flat_slab_rows;
-  // the shared-memory atomic unit retires ~1 lane-operation per 2 cycles; L2 reductions go down another path.
-  // Warps with (warp & 7) >= smem_share send even their hot slots to L2 (plan.smem_share of 8 warps use shared memory).
-  const uint32_t Hw = (warp & 7u) < plan.smem_share ? H : 0u;
+  // Warps with (warp & 7) >= smem_share send even their hot slots to L2 (experiment switch; default: all use shared memory).
+  const bool smem_warp = (warp & 7u) < plan.smem_share;
+  const uint32_t Hw = smem_warp ? Hs : 0u, Tw = smem_warp ? T : 0u;
+  unsigned long long* gadj = gacc - 31u * Tw;   // indexed by cell: gadj[cell] == gacc[slot] for a cold slot
   if (warp == kAggConsumers / 32) {
     flat_producer(plan, L, a, ctl, smem, S);
   } else {
@@ -593,7 +646,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
       // ---- rows of this thread, selection ----
       uint32_t sel = 0;
 #pragma unroll
-      for (int i = 0; i < kAggRowsMax; i++) sel |= (tc + i * kAggConsumers < R ? 1u : 0u) << i;
+      for (int i = 0; i < KR; i++) sel |= (tc + i * kAggConsumers < R ? 1u : 0u) << i;
       if (plan.npred && sel) {
         if (plan.conj) {
           for (uint32_t l = 0; l < plan.nleaves; l++) {
@@ -602,11 +655,11 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             uint32_t m = 0;
             if (!x.c.absent && !x.c.vw && x.lkind != LK_IS_NULL && x.lkind != LK_IS_NOT_NULL) {   // no NULLs in this slab: plain comparison
 #pragma unroll
-              for (int i = 0; i < kAggRowsMax; i++)
+              for (int i = 0; i < KR; i++)
                 if ((sel >> i) & 1u) m |= (leaf_row(x, tc + i * kAggConsumers) ? 1u : 0u) << i;
             } else {
 #pragma unroll
-              for (int i = 0; i < kAggRowsMax; i++)
+              for (int i = 0; i < KR; i++)
                 if ((sel >> i) & 1u) m |= (leaf_row3(x, tc + i * kAggConsumers) == 1u ? 1u : 0u) << i;
             }
             sel = m;
@@ -622,7 +675,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
               leaf_ctx(x, plan, a, st, base, L, op.arg);
               Tri32 v{0u, 0u};
 #pragma unroll
-              for (int j = 0; j < kAggRowsMax; j++)
+              for (int j = 0; j < KR; j++)
                 if ((sel >> j) & 1u) {
                   const uint32_t t3 = leaf_row3(x, tc + j * kAggConsumers);
                   v.t |= (t3 == 1u ? 1u : 0u) << j;
@@ -637,18 +690,18 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         }
       }
       // ---- group slot of every selected row: one pass per key; NULL is its own group (id == card) ----
-      uint32_t slot[kAggRowsMax];
+      uint32_t slot[KR];
 #pragma unroll
-      for (int i = 0; i < kAggRowsMax; i++) slot[i] = 0;
+      for (int i = 0; i < KR; i++) slot[i] = 0;
       for (uint32_t k = 0; k < plan.nkeys; k++) {
         const DevKey& key = plan.keys[k];
         ColCtx c;
-        col_ctx(c, st, base, L, key.col);
+        col_ctx(c, st, base, L, key.col, a.flat);
         const uint32_t stride = key.stride, nullslot = key.card * key.stride;
         const bool nullable = c.absent || c.vw != nullptr;
         if (key.kind == KK_BOOL) {
 #pragma unroll
-          for (int i = 0; i < kAggRowsMax; i++)
+          for (int i = 0; i < KR; i++)
             if ((sel >> i) & 1u) {
               const uint32_t r = tc + i * kAggConsumers;
               if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
@@ -664,7 +717,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
           const double inv = 1.0 / double(key.bin_width);
           const long long w = key.bin_width, b0 = key.bin_base;
 #pragma unroll
-          for (int i = 0; i < kAggRowsMax; i++)
+          for (int i = 0; i < KR; i++)
             if ((sel >> i) & 1u) {
               const uint32_t r = tc + i * kAggConsumers;
               if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
@@ -678,65 +731,93 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             }
         } else {
           const uint32_t* __restrict__ gid = key.gid + st.col[key.col].lut_base;
+          if (!nullable) {   // the loads of all rows in flight together
+            uint32_t g[KR];
 #pragma unroll
-          for (int i = 0; i < kAggRowsMax; i++)
-            if ((sel >> i) & 1u) {
-              const uint32_t r = tc + i * kAggConsumers;
-              if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
-              slot[i] += gid[col_index(c, r)] * stride;
-            }
+            for (int i = 0; i < KR; i++) g[i] = ((sel >> i) & 1u) ? gid[col_index(c, tc + i * kAggConsumers)] : 0u;
+#pragma unroll
+            for (int i = 0; i < KR; i++) slot[i] += g[i] * stride;
+          } else {
+#pragma unroll
+            for (int i = 0; i < KR; i++)
+              if ((sel >> i) & 1u) {
+                const uint32_t r = tc + i * kAggConsumers;
+                if (!col_valid(c, r)) { slot[i] += nullslot; continue; }
+                slot[i] += gid[col_index(c, r)] * stride;
+              }
+          }
         }
       }
+      // ---- slot -> cell (the hottest groups own a cell per lane) ----
+#pragma unroll
+      for (int i = 0; i < KR; i++) slot[i] = slot[i] < Tw ? slot[i] * 32u + lane : slot[i] + 31u * Tw;
       // ---- COUNT(*) cell ----
 #pragma unroll
-      for (int i = 0; i < kAggRowsMax; i++)
+      for (int i = 0; i < KR; i++)
         if ((sel >> i) & 1u) {
           if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[slot[i]]), 1u);   // a CTA sees < 2^32 rows: the low word never wraps
-          else atomicAdd(&gacc[slot[i]], 1ull);
+          else atomicAdd(&gadj[slot[i]], 1ull);
         }
       // ---- one pass per aggregate (NULL inputs contribute nothing) ----
       for (uint32_t g = 0; g < plan.naggs; g++) {
         const DevAgg& ag = plan.aggs[g];
         if (ag.fn == AG_COUNT_STAR) continue;
         ColCtx c;
-        col_ctx(c, st, base, L, ag.col);
+        col_ctx(c, st, base, L, ag.col, a.flat);
         if (c.absent) continue;
         uint32_t vsel = sel;   // selected rows whose input is not NULL
         if (c.vw) {
 #pragma unroll
-          for (int i = 0; i < kAggRowsMax; i++)
+          for (int i = 0; i < KR; i++)
             if (((sel >> i) & 1u) && !col_valid(c, tc + i * kAggConsumers)) vsel &= ~(1u << i);
         }
         if (ag.update_nn) {
           const uint32_t arr = 1 + plan.n_acc + ag.nn_slot;
 #pragma unroll
-          for (int i = 0; i < kAggRowsMax; i++)
+          for (int i = 0; i < KR; i++)
             if ((vsel >> i) & 1u) {
-              if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[arr * H + slot[i]]), 1u);
-              else atomicAdd(&gacc[size_t(arr) * nslots + slot[i]], 1ull);
+              if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[arr * Hs + slot[i]]), 1u);
+              else atomicAdd(&gadj[size_t(arr) * nslots + slot[i]], 1ull);
             }
         }
         if (ag.fn == AG_COUNT) continue;
         const bool plain = c.fkind == FK_PLAIN8;
         const uint64_t* __restrict__ dict = reinterpret_cast<const uint64_t*>(a.flat + st.col[ag.col].dict8);
         const uint64_t* v8 = reinterpret_cast<const uint64_t*>(c.colw);
-        unsigned long long* scell = sacc + size_t(1 + ag.acc_slot) * H;
-        unsigned long long* gcell = gacc + size_t(1 + ag.acc_slot) * nslots;
+        unsigned long long* scell = sacc + size_t(1 + ag.acc_slot) * Hs;
+        unsigned long long* gcell = gadj + size_t(1 + ag.acc_slot) * nslots;
         const bool f64 = ag.kind == DK_F64;
         const uint32_t fn = ag.fn;
         // f64 sums have no native shared-memory atomic (a CAS loop): plan.f64_global sends them to L2
         const uint32_t Hc = (plan.f64_global && (fn == AG_AVG || (fn == AG_SUM && f64))) ? 0u : Hw;
+        // the values first (all loads in flight together: a dictionary value is an L2 round trip), then the updates,
+        // one straight-line loop per aggregate function
+        uint64_t bits[KR];
+        if (plain) {
 #pragma unroll
-        for (int i = 0; i < kAggRowsMax; i++) {
-          if (!((vsel >> i) & 1u)) continue;
-          const uint32_t r = tc + i * kAggConsumers;
-          const uint64_t bits = plain ? v8[r] : dict[col_index(c, r)];
-          const bool hot = slot[i] < Hc;
-          unsigned long long* cell = hot ? scell + slot[i] : gcell + slot[i];
-          if (fn == AG_SUM && !f64) cell_add_u64(cell, hot, bits);                      // wrapping, like DataFusion's SUM(Int64)
-          else if (fn == AG_SUM) atomicAdd(reinterpret_cast<double*>(cell), __longlong_as_double((long long)bits));
-          else if (fn == AG_AVG) atomicAdd(reinterpret_cast<double*>(cell), f64 ? __longlong_as_double((long long)bits) : double((long long)bits));
-          else cell_min_max(cell, hot, fn == AG_MIN, f64 ? (long long)f64_order_key(bits) : (long long)bits);
+          for (int i = 0; i < KR; i++) bits[i] = ((vsel >> i) & 1u) ? v8[tc + i * kAggConsumers] : 0ull;
+        } else {
+#pragma unroll
+          for (int i = 0; i < KR; i++) bits[i] = ((vsel >> i) & 1u) ? dict[col_index(c, tc + i * kAggConsumers)] : 0ull;
+        }
+        if (fn == AG_SUM && !f64) {   // wrapping, like DataFusion's SUM(Int64)
+#pragma unroll
+          for (int i = 0; i < KR; i++)
+            if ((vsel >> i) & 1u) cell_add_u64(slot[i] < Hc ? scell + slot[i] : gcell + slot[i], slot[i] < Hc, bits[i]);
+        } else if (fn == AG_SUM || fn == AG_AVG) {
+#pragma unroll
+          for (int i = 0; i < KR; i++)
+            if ((vsel >> i) & 1u) {
+              const double v = (f64 || fn == AG_SUM) ? __longlong_as_double((long long)bits[i]) : double((long long)bits[i]);
+              atomicAdd(reinterpret_cast<double*>(slot[i] < Hc ? scell + slot[i] : gcell + slot[i]), v);
+            }
+        } else {
+          const bool is_min = fn == AG_MIN;
+#pragma unroll
+          for (int i = 0; i < KR; i++)
+            if ((vsel >> i) & 1u)
+              cell_min_max(slot[i] < Hc ? scell + slot[i] : gcell + slot[i], slot[i] < Hc, is_min,
+                           f64 ? (long long)f64_order_key(bits[i]) : (long long)bits[i]);
         }
       }
       const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(sel));
@@ -751,14 +832,15 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
   }
   // ---- flush the hot table ----
   __syncthreads();
-  for (uint32_t slot = threadIdx.x; slot < H; slot += kAggThreads) {
-    const unsigned long long rows = sacc[slot];
+  for (uint32_t cell = threadIdx.x; cell < Hs; cell += kAggThreads) {
+    const unsigned long long rows = sacc[cell];
     if (rows == 0) continue;
+    const uint32_t slot = cell < 32u * T ? cell >> 5 : cell - 31u * T;
     atomicAdd(&gacc[slot], rows);
     for (uint32_t arr = 0; arr < plan.n_acc; arr++)
-      acc_merge(&gacc[(1 + arr) * nslots + slot], plan.acc_init[arr], sacc[(1 + arr) * H + slot]);
+      acc_merge(&gacc[(1 + arr) * nslots + slot], plan.acc_init[arr], sacc[(1 + arr) * Hs + cell]);
     for (uint32_t k = 0; k < plan.n_nn; k++) {
-      const unsigned long long v = sacc[(1 + plan.n_acc + k) * H + slot];
+      const unsigned long long v = sacc[(1 + plan.n_acc + k) * Hs + cell];
       if (v) atomicAdd(&gacc[(1 + plan.n_acc + k) * nslots + slot], v);
     }
   }

@@ -368,6 +368,25 @@ __global__ void __launch_bounds__(128) k_flat_store(const uint8_t* __restrict__ 
   if (lane == 0) ok_out[ji] = ok ? 1 : 0;
 }
 
+// Every dictionary index of the flat store against its dictionary's entry count, once per table: the reference's
+// reader fails a file whose index leaves the dictionary, and nothing downstream has to trust the file after this
+// (the scan kernels still clamp: a LUT is never left).  One warp per page; first_bad = lowest failing page index.
+__global__ void __launch_bounds__(128) k_check_flat_indices(const uint8_t* __restrict__ flat, const FlatPageRec* __restrict__ fpages,
+                                                            const uint32_t* __restrict__ dict_n, uint32_t n_pages, uint32_t* __restrict__ first_bad) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t pi = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (pi >= n_pages) return;
+  const FlatPageRec fp = fpages[pi];
+  if (fp.fkind != FK_INDEX || fp.bw == 0) return;
+  const uint32_t limit = dict_n[pi] ? dict_n[pi] : 1u;             // NULL rows hold slot value 0
+  if (fp.bw < 32 && limit >= (1u << fp.bw)) return;                 // every bw-bit value is an entry
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(flat + fp.off);
+  const uint32_t mask = fp.bw >= 32 ? 0xffffffffu : ((1u << fp.bw) - 1u);
+  bool bad = false;
+  for (uint32_t i = lane; i < fp.rows; i += 32) bad |= (bits32_at(w, i * fp.bw) & mask) >= limit;
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMin(first_bad, pi);
+}
+
 // ---- DELTA_BINARY_PACKED (Parseable's p_timestamp, streams.rs:587-590) -> aligned 8-byte values ----
 // Only built when a query needs the VALUES of such a column (a time range that cuts a row group, a
 // projection of p_timestamp): footer statistics decide the injected range for every other query and
@@ -387,39 +406,33 @@ __device__ __forceinline__ bool rd_varint(const uint8_t* __restrict__ p, uint64_
   return false;
 }
 
-__global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
-                                                         const DeltaJob* __restrict__ jobs, uint32_t n_jobs, uint8_t* __restrict__ flat_base,
-                                                         uint8_t* __restrict__ ok_out) {
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ji = blockIdx.x * 4 + warp;
-  if (ji >= n_jobs) return;
-  const DeltaJob job = jobs[ji];
-  const DevPage pg = pages[job.page];
-  // a page with NULLs holds only its non-null values: they are decoded densely, then spread over the row slots
-  const bool has_nulls = job.vsrc != ~0ull;
-  const uint32_t* valid = reinterpret_cast<const uint32_t*>(flat_base + job.vsrc);
-  const uint32_t nvals = has_nulls ? warp_count_valid(valid, pg.num_rows) : pg.num_rows;
-  const uint8_t* p = arena + pg.off;
-  uint64_t pos = pg.val_off;
-  const uint64_t end = pg.len;
-  int64_t* final_out = reinterpret_cast<int64_t*>(flat_base + job.dst);
-  int64_t* out = has_nulls ? reinterpret_cast<int64_t*>(flat_base + job.tmp) : final_out;
-  // page header
+// One DELTA_BINARY_PACKED stream starting at p[pos]: header <block size> <miniblocks per block> <total count> <first value>,
+// then blocks of <min delta> <bit width per miniblock> <miniblocks>.  Warp cooperative; put(i, value) receives every
+// value (64-bit wrapping arithmetic like the reference's decoder; an INT32 stream is the low word).  `want`: the count the
+// caller expects, or ~0u to take the header's (returned through total_out, at most `cap`).  On return pos is the first
+// byte after the stream: the last miniblock that holds values is stored in full, later ones not at all.
+template <class Put>
+__device__ __forceinline__ bool dbp_decode_warp(const uint8_t* __restrict__ p, uint64_t& pos, const uint64_t end, uint32_t want,
+                                                uint32_t cap, uint32_t& total_out, Put put) {
+  const uint32_t lane = threadIdx.x & 31;
   uint64_t bs = 0, nm = 0, total = 0, fz = 0;
   uint32_t bad = 0;
   if (lane == 0) {
     if (!rd_varint(p, pos, end, bs) || !rd_varint(p, pos, end, nm) || !rd_varint(p, pos, end, total) || !rd_varint(p, pos, end, fz)) bad = 1;
-    if (!bad && (nm == 0 || nm > 32 || bs == 0 || bs % nm != 0 || (bs / nm) % 32 != 0 || bs > (1u << 20) || total != nvals)) bad = 1;
+    if (!bad && (nm == 0 || nm > 32 || bs == 0 || bs % nm != 0 || (bs / nm) % 32 != 0 || bs > (1u << 20))) bad = 1;
+    if (!bad && (want != ~0u ? total != want : total > cap)) bad = 1;
   }
   bad = __shfl_sync(0xffffffffu, bad, 0);
-  if (bad) { if (lane == 0) ok_out[ji] = 0; return; }
+  if (bad) return false;
   bs = __shfl_sync(0xffffffffu, bs, 0);
   nm = __shfl_sync(0xffffffffu, nm, 0);
   fz = __shfl_sync(0xffffffffu, fz, 0);
   pos = __shfl_sync(0xffffffffu, pos, 0);
+  const uint32_t nvals = uint32_t(__shfl_sync(0xffffffffu, total, 0));
+  total_out = nvals;
   const uint32_t vpm = uint32_t(bs / nm);   // values per miniblock, a multiple of 32
   int64_t last = int64_t(fz >> 1) ^ -int64_t(fz & 1);
-  if (lane == 0 && nvals) out[0] = last;
+  if (lane == 0 && nvals) put(0u, last);
   uint32_t done = 1;                        // values written
   while (done < nvals && !bad) {
     // block header: min delta + one bit width per miniblock (lane m keeps width m)
@@ -447,14 +460,13 @@ __global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restri
           if (sh + bw > 64) d |= uint64_t(q[8]) << (64 - sh);
           if (bw < 64) d &= (1ull << bw) - 1ull;
         }
-        // wrapping arithmetic like the reference's decoder
         uint64_t x = j < take ? uint64_t(min_delta) + d : 0ull, incl = x;
         for (int o = 1; o < 32; o <<= 1) {
           const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
           if ((int)lane >= o) incl += t;
         }
         const uint64_t val = uint64_t(last) + incl;
-        if (j < take) out[done + j] = int64_t(val);
+        if (j < take) put(done + j, int64_t(val));
         last = int64_t(__shfl_sync(0xffffffffu, val, 31));
         if (take - v0 < 32) last = int64_t(__shfl_sync(0xffffffffu, val, (take - v0 - 1) & 31));
       }
@@ -462,13 +474,141 @@ __global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restri
       pos += (uint64_t(vpm) * bw) / 8;
     }
   }
-  if (has_nulls && !bad) {
+  return !bad;
+}
+
+__global__ void __launch_bounds__(128) k_delta_to_plain8(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
+                                                         const DeltaJob* __restrict__ jobs, uint32_t n_jobs, uint8_t* __restrict__ flat_base,
+                                                         uint8_t* __restrict__ ok_out) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ji = blockIdx.x * 4 + warp;
+  if (ji >= n_jobs) return;
+  const DeltaJob job = jobs[ji];
+  const DevPage pg = pages[job.page];
+  // a page with NULLs holds only its non-null values: they are decoded densely, then spread over the row slots
+  const bool has_nulls = job.vsrc != ~0ull;
+  const uint32_t* valid = reinterpret_cast<const uint32_t*>(flat_base + job.vsrc);
+  const uint32_t nvals = has_nulls ? warp_count_valid(valid, pg.num_rows) : pg.num_rows;
+  const uint8_t* p = arena + pg.off;
+  uint64_t pos = pg.val_off;
+  int64_t* final_out = reinterpret_cast<int64_t*>(flat_base + job.dst);
+  int64_t* out = has_nulls ? reinterpret_cast<int64_t*>(flat_base + job.tmp) : final_out;
+  uint32_t total = 0;
+  const bool ok = dbp_decode_warp(p, pos, uint64_t(pg.len), nvals, nvals, total, [&](uint32_t i, int64_t v) { out[i] = v; });
+  if (has_nulls && ok) {
     __syncwarp();
     __threadfence_block();
     expand_rows(valid, pg.num_rows, [&](uint32_t k) { return uint64_t(out[k]); },
                 [&](uint32_t r, bool, uint64_t v, uint32_t) { if (r < pg.num_rows) final_out[r] = int64_t(v); });
   }
-  if (lane == 0) ok_out[ji] = bad ? 0 : 1;
+  if (lane == 0) ok_out[ji] = ok ? 1 : 0;
+}
+
+// ---- DELTA_BYTE_ARRAY / DELTA_LENGTH_BYTE_ARRAY (the fallback encoding of Parseable's custom-partition columns,
+// streams.rs:614-619) -> the same bytes as a PLAIN BYTE_ARRAY page ([u32 length][bytes]...), so that everything
+// downstream sees one kind of string page.  Two passes, one warp per page:
+//   k_dba_lengths     decodes the prefix / suffix length streams (DELTA_BINARY_PACKED INT32) into scratch and adds them up
+//   k_dba_materialise writes the page: the level bytes as they are, then every value = the first <prefix> bytes of
+//                     the previous value + its suffix (front coding is a chain: values one after the other, bytes in parallel)
+__global__ void __launch_bounds__(128) k_dba_lengths(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
+                                                     const DbaJob* __restrict__ jobs, uint32_t n_jobs, uint8_t* __restrict__ scratch,
+                                                     DbaInfo* __restrict__ info) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ji = blockIdx.x * 4 + warp;
+  if (ji >= n_jobs) return;
+  const DbaJob job = jobs[ji];
+  const DevPage pg = pages[job.page];
+  const uint8_t* p = arena + pg.off;
+  uint64_t pos = pg.val_off;
+  uint32_t* plen = reinterpret_cast<uint32_t*>(scratch + job.len_tmp);
+  uint32_t* slen = plen + pg.num_rows;
+  uint32_t n = 0, n2 = 0;
+  unsigned long long sum = 0;
+  bool ok = true;
+  if (pg.val_off >= pg.len) {   // an all-NULL page may carry no value bytes at all
+    n = 0;
+  } else {
+    if (job.with_prefix) {
+      ok = dbp_decode_warp(p, pos, uint64_t(pg.len), ~0u, pg.num_rows, n, [&](uint32_t i, int64_t v) { plen[i] = uint32_t(v); });
+      if (ok) ok = dbp_decode_warp(p, pos, uint64_t(pg.len), n, n, n2, [&](uint32_t i, int64_t v) { slen[i] = uint32_t(v); });
+    } else {
+      ok = dbp_decode_warp(p, pos, uint64_t(pg.len), ~0u, pg.num_rows, n, [&](uint32_t i, int64_t v) { slen[i] = uint32_t(v); });
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (ok) {
+      // lengths are non-negative INT32; a prefix may not be longer than the previous value; suffix bytes must be in the page
+      unsigned long long suf = 0;
+      uint32_t bad = 0, prev_len = 0;
+      for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t pl = (i < n && job.with_prefix) ? plen[i] : 0u, sl = i < n ? slen[i] : 0u;
+        if ((pl | sl) & 0x80000000u) bad = 1;
+        const uint32_t len = pl + sl;
+        const uint32_t before = __shfl_up_sync(0xffffffffu, len, 1);
+        if (i < n && pl > (lane ? before : prev_len)) bad = 1;
+        prev_len = __shfl_sync(0xffffffffu, len, 31);
+        sum += len;
+        suf += sl;
+      }
+      for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); suf += __shfl_xor_sync(0xffffffffu, suf, o); }
+      bad = __any_sync(0xffffffffu, bad);
+      if (bad || pos + suf > pg.len) ok = false;
+    }
+  }
+  if (lane == 0) info[ji] = {sum + 4ull * n, n, uint32_t(pos), ok ? 1u : 0u, 0u};
+}
+
+__global__ void __launch_bounds__(128) k_dba_materialise(const uint8_t* __restrict__ arena, const DevPage* __restrict__ pages,
+                                                         const DbaJob* __restrict__ jobs, const DbaInfo* __restrict__ info, uint32_t n_jobs,
+                                                         const uint8_t* __restrict__ scratch, uint8_t* __restrict__ mat) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ji = blockIdx.x * 4 + warp;
+  if (ji >= n_jobs) return;
+  const DbaJob job = jobs[ji];
+  const DbaInfo in = info[ji];
+  if (!in.ok) return;
+  const DevPage pg = pages[job.page];
+  const uint8_t* p = arena + pg.off;
+  uint8_t* out = mat + job.dst;
+  // level bytes first (the new page: definition levels at 0, values right after them)
+  for (uint32_t i = lane; i < pg.def_len; i += 32) out[i] = p[pg.def_off + i];
+  out += pg.def_len;
+  const uint32_t* plen = reinterpret_cast<const uint32_t*>(scratch + job.len_tmp);
+  const uint32_t* slen = plen + pg.num_rows;
+  const uint8_t* src = p + in.data_pos;    // suffixes, back to back
+  uint64_t o_base = 0, s_base = 0;         // bytes written / suffix bytes consumed before this group of 32 values
+  uint64_t prev = 0;                       // where the previous value's bytes start in `out`
+  for (uint32_t i0 = 0; i0 < in.nvals; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const uint32_t pl = (i < in.nvals && job.with_prefix) ? plen[i] : 0u, sl = i < in.nvals ? slen[i] : 0u;
+    // exclusive scans: every value's place in the output and in the suffix bytes is known without the chain
+    uint64_t o_inc = i < in.nvals ? uint64_t(pl) + sl + 4 : 0ull, s_inc = sl;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t a = __shfl_up_sync(0xffffffffu, o_inc, o), b = __shfl_up_sync(0xffffffffu, s_inc, o);
+      if ((int)lane >= o) { o_inc += a; s_inc += b; }
+    }
+    const uint64_t my_o = o_base + o_inc - (i < in.nvals ? uint64_t(pl) + sl + 4 : 0ull), my_s = s_base + s_inc - sl;
+    if (i < in.nvals) {   // the length word and the suffix do not depend on the chain
+      const uint32_t len = pl + sl;
+      uint8_t* w = out + my_o;
+      w[0] = uint8_t(len); w[1] = uint8_t(len >> 8); w[2] = uint8_t(len >> 16); w[3] = uint8_t(len >> 24);
+    }
+    const uint32_t cnt = in.nvals - i0 < 32 ? in.nvals - i0 : 32;
+    for (uint32_t k = 0; k < cnt; k++) {
+      const uint32_t kp = __shfl_sync(0xffffffffu, pl, k), ks = __shfl_sync(0xffffffffu, sl, k);
+      const uint64_t ko = __shfl_sync(0xffffffffu, my_o, k) + 4, ksrc = __shfl_sync(0xffffffffu, my_s, k);
+      for (uint32_t b = lane; b < ks; b += 32) out[ko + kp + b] = src[ksrc + b];
+      if (kp) {
+        __syncwarp();   // the previous value is complete (its prefix part was written one trip ago)
+        for (uint32_t b = lane; b < kp; b += 32) out[ko + b] = out[prev + b];
+      }
+      prev = ko;
+      __syncwarp();
+    }
+    o_base += __shfl_sync(0xffffffffu, o_inc, 31);
+    s_base += __shfl_sync(0xffffffffu, s_inc, 31);
+  }
 }
 
 }  // namespace pqb

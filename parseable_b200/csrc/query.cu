@@ -223,6 +223,22 @@ static std::vector<EntChunk> column_chunks(const Table& t, int tcol) {
   return v;
 }
 
+void launch_dba_lengths(const uint8_t* arena, const DevPage* pages, const DbaJob* jobs, uint32_t n_jobs, uint8_t* scratch, DbaInfo* info, cudaStream_t stream) {
+  if (!n_jobs) return;
+  k_dba_lengths<<<(n_jobs + 3) / 4, 128, 0, stream>>>(arena, pages, jobs, n_jobs, scratch, info);
+  PQB_CUDA(cudaGetLastError());
+}
+void launch_dba_materialise(const uint8_t* arena, const DevPage* pages, const DbaJob* jobs, const DbaInfo* info, uint32_t n_jobs,
+                            const uint8_t* scratch, uint8_t* mat, cudaStream_t stream) {
+  if (!n_jobs) return;
+  k_dba_materialise<<<(n_jobs + 3) / 4, 128, 0, stream>>>(arena, pages, jobs, info, n_jobs, scratch, mat);
+  PQB_CUDA(cudaGetLastError());
+}
+void launch_check_flat_indices(const uint8_t* flat, const FlatPageRec* fpages, const uint32_t* dict_n, uint32_t n_pages, uint32_t* first_bad, cudaStream_t stream) {
+  if (!n_pages) return;
+  k_check_flat_indices<<<(n_pages + 3) / 4, 128, 0, stream>>>(flat, fpages, dict_n, n_pages, first_bad);
+  PQB_CUDA(cudaGetLastError());
+}
 void launch_page_has_nulls(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, uint8_t* out, cudaStream_t stream) {
   if (!n_pages) return;
   k_page_has_nulls<<<(n_pages + 127) / 128, 128, 0, stream>>>(arena, pages, n_pages, out);
@@ -1021,13 +1037,15 @@ void Query::run(const PqQueryDesc& d) {
   FlatLayout FL{};
   if (n_flat) {
     const uint32_t ctl_bytes = align_up(uint32_t(sizeof(FlatCtl)), 128);
+    plan.direct8 = 0;
+    if (agg_kernel) { const char* e = getenv("PQB_AGG_DIRECT8"); plan.direct8 = (e && e[0] == '0') ? 0u : 1u; }   // A/B switch
     auto stage_bytes_for = [&](uint32_t S) {
       uint32_t off = 0;
       for (uint32_t s = 0; s < ncols; s++) {
         FL.col_off[s] = off;
         FL.col_voff[s] = off;
         if (!plan.cols[s].staged) continue;
-        const uint32_t cap = std::max<uint32_t>(shape->flat_plain8[s] ? S * 8 : 0, (S * shape->flat_max_bw[s] + 7) / 8);
+        const uint32_t cap = std::max<uint32_t>((shape->flat_plain8[s] && !plan.direct8) ? S * 8 : 0, (S * shape->flat_max_bw[s] + 7) / 8);
         off += align_up(cap + 48, 128);   // + the bit phase of a piece that starts inside a page, + over-read slack
         if (shape->flat_nullable[s]) { FL.col_voff[s] = off; off += align_up(S / 8 + 48, 128); }   // validity bits of pages with NULLs
       }
@@ -1035,8 +1053,10 @@ void Query::run(const PqQueryDesc& d) {
     };
     const uint32_t avail = uint32_t(ctx.smem_optin()) - ctl_bytes - 256;
     if (!agg_kernel) {
-      // three CTAs per SM: a CTA may use a third of the SM's shared memory
-      const uint32_t budget = (228u * 1024 - 3 * 1024) / 3 - ctl_bytes;
+      // five CTAs per SM (160 threads each): a CTA may use a fifth of the SM's shared memory
+      uint32_t ctas = 5;
+      if (const char* e = getenv("PQB_FILTER_CTAS")) ctas = std::max(1, std::min(8, atoi(e)));   // experiment switch
+      const uint32_t budget = (228u * 1024 - ctas * 1024) / ctas - ctl_bytes;
       uint32_t S = kFilterSlabRows;
       while (S > 1024 && 2 * stage_bytes_for(S) > budget) S >>= 1;
       FL.stage_bytes = stage_bytes_for(S);
@@ -1055,14 +1075,22 @@ void Query::run(const PqQueryDesc& d) {
       FL.nstages = 2;
       uint32_t left = avail - 2 * FL.stage_bytes;
       if (full + FL.stage_bytes <= left && FL.nstages < (uint32_t)kFlatStagesMax) { FL.nstages = 3; left -= FL.stage_bytes; }
-      plan.hot_slots = uint32_t(std::min<uint64_t>(plan.nslots, left / (cells * 8)));
-      if (const char* hs = getenv("PQB_HOT_SLOTS")) plan.hot_slots = std::min<uint32_t>(plan.hot_slots, uint32_t(atoi(hs)));   // experiment switch
+      // the hottest groups own a cell per lane (no same-address lanes inside a warp): 31 more cells each
+      const uint32_t cap = left / (cells * 8);
+      uint32_t T = 8;
+      if (const char* e = getenv("PQB_LANE_SLOTS")) T = uint32_t(std::max(0, atoi(e)));   // experiment switch
+      if (const char* e = getenv("PQB_F64_GLOBAL")) if (atoi(e)) T = 0;   // that experiment sends hot f64 cells to L2 by SLOT: no per-lane cells
+      T = std::min<uint32_t>(T, plan.nslots);
+      while (T && cap < 64u * T) T >>= 1;
+      plan.lane_slots = T;
+      plan.hot_slots = uint32_t(std::min<uint64_t>(plan.nslots, cap - 31u * T));
+      if (const char* hs = getenv("PQB_HOT_SLOTS")) plan.hot_slots = std::max(T, std::min<uint32_t>(plan.hot_slots, uint32_t(atoi(hs))));   // experiment switch
       plan.flat_slab_rows = S;
       plan.flat_krows = krows;
     }
     FL.stage0 = ctl_bytes;
     FL.acc = align_up(FL.stage0 + FL.nstages * FL.stage_bytes, 128);
-    FL.total = FL.acc + (agg_kernel ? plan.hot_slots * cells * 8 : 0);
+    FL.total = FL.acc + (agg_kernel ? (plan.hot_slots + 31u * plan.lane_slots) * cells * 8 : 0);
     if (FL.total > ctx.smem_optin()) throw Error(PQ_ERR_UNSUPPORTED, "query needs more shared memory than one SM has");
   }
 
@@ -1157,10 +1185,15 @@ void Query::run(const PqQueryDesc& d) {
   if (n_flat && nrg) {
     uint32_t grid;
     if (agg_kernel) {
-      PQB_CUDA(cudaFuncSetAttribute(k_flat_agg, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
       grid = std::min<uint32_t>(n_flat, uint32_t(ctx.sm_count()));
       if (const char* g = getenv("PQB_GRID")) grid = std::max(1, atoi(g));
-      k_flat_agg<<<grid, kAggThreads, FL.total, stream>>>(plan, FL, sa);
+      auto go = [&](auto kern) {
+        PQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
+        kern<<<grid, kAggThreads, FL.total, stream>>>(plan, FL, sa);
+      };
+      if (plan.flat_krows >= 8) go(k_flat_agg<8>);        // rows per thread and slab: the widest instantiation the stages leave room for
+      else if (plan.flat_krows >= 4) go(k_flat_agg<4>);
+      else go(k_flat_agg<2>);
     } else {
       PQB_CUDA(cudaFuncSetAttribute(k_flat_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
       int occ = 1;

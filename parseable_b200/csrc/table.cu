@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <exception>
 #include <thread>
 
 #include "decomp_kernels.cuh"
@@ -208,6 +209,26 @@ std::string describe_file(const PqFile& f) {
   return o;
 }
 
+// Temporary device buffers of the open path: dev_drop() frees (stream ordered) and clears the pointer; an UnwindGuard
+// frees whatever it still owns when an exception leaves its scope and synchronises the stream first, so that no copy
+// or kernel is in flight into memory the caller's destructor is about to hand back.
+template <class T>
+static void dev_drop(T*& p, cudaStream_t s) {
+  if (p) { cudaFreeAsync((void*)p, s); p = nullptr; }
+}
+struct UnwindGuard {
+  cudaStream_t s;
+  int n;
+  std::vector<void**> ptrs;
+  explicit UnwindGuard(cudaStream_t st) : s(st), n(std::uncaught_exceptions()) {}
+  template <class T> void own(T*& p) { ptrs.push_back(reinterpret_cast<void**>(&p)); }
+  ~UnwindGuard() {
+    if (std::uncaught_exceptions() <= n) return;
+    cudaStreamSynchronize(s);
+    for (void** p : ptrs) if (*p) { cudaFreeAsync(*p, s); *p = nullptr; }
+  }
+};
+
 // ---------------- Table ----------------
 Table::~Table() {
   // stream-ordered frees into the pool: a per-query table costs no device-wide synchronisation
@@ -216,6 +237,7 @@ Table::~Table() {
   if (d_slab_recs) cudaFreeAsync(d_slab_recs, cudaStreamPerThread);
   if (d_slab_dirs) cudaFreeAsync(d_slab_dirs, cudaStreamPerThread);
   if (d_slab_flat) cudaFreeAsync(d_slab_flat, cudaStreamPerThread);
+  if (d_strmat) cudaFreeAsync(d_strmat, cudaStreamPerThread);
   if (d_flat) cudaFreeAsync(d_flat, cudaStreamPerThread);
   if (d_flat_pages) cudaFreeAsync(d_flat_pages, cudaStreamPerThread);
   for (ColSide& cs : sides) {
@@ -385,8 +407,16 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
               tc.max_bw = std::max<uint32_t>(tc.max_bw, 1);
               break;
             case ENC_DELTA_BINARY_PACKED:
+              if (leaf.phys_type != PT_INT64) throw Error(PQ_ERR_UNSUPPORTED, "column '" + colname + "': DELTA_BINARY_PACKED on a non-INT64 column");
               dp.enc = DE_DELTA;
               tc.has_delta_pages = true;
+              break;
+            case ENC_DELTA_BYTE_ARRAY:
+            case ENC_DELTA_LENGTH_BYTE_ARRAY:
+              // front-coded strings (streams.rs:614-619): rewritten as a PLAIN page once the bytes are on the device
+              if (leaf.phys_type != PT_BYTE_ARRAY) throw Error(PQ_ERR_UNSUPPORTED, "column '" + colname + "': DELTA_BYTE_ARRAY on a non-BYTE_ARRAY column");
+              dp.enc = pi.encoding == ENC_DELTA_BYTE_ARRAY ? DE_DELTA_BYTES : DE_DELTA_LEN_BYTES;
+              tc.has_plain_pages = true;
               break;
             default:
               throw Error(PQ_ERR_UNSUPPORTED, "column '" + colname + "': page encoding " + std::to_string(pi.encoding) + " not supported");
@@ -480,28 +510,46 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
           for (const PageInfo& pi : pis) {
             const uint64_t slot = (arena + 15) & ~15ull;
             arena = slot + pi.uncompressed_size + 16;
+            uint64_t v2_levels = 0;
             if (pi.type == PAGE_DICTIONARY) {
               tc.dict_off = slot; tc.dict_len = pi.uncompressed_size; tc.dict_n = pi.num_values;
-            } else if (pi.type == PAGE_DATA) {
+            } else if (pi.type == PAGE_DATA || pi.type == PAGE_DATA_V2) {
               DevPage dp{};
               dp.off = slot; dp.len = pi.uncompressed_size; dp.num_rows = pi.num_values; dp.first_row = first_row;
               first_row += pi.num_values;
-              dp.def_len = leaf.max_def > 0 ? 0xffffffffu : 0;   // resolved by k_page_fixup from the decoded bytes
+              if (pi.type == PAGE_DATA) dp.def_len = leaf.max_def > 0 ? 0xffffffffu : 0;   // resolved by k_page_fixup from the decoded bytes
+              else {
+                // v2: the level bytes sit in front of the values, never compressed, their lengths in the header
+                v2_levels = uint64_t(pi.v2_rep_len) + pi.v2_def_len;
+                if (v2_levels > pi.compressed_size || v2_levels > pi.uncompressed_size) throw Error(PQ_ERR_CORRUPT, col_names[c] + ": v2 level bytes run past the page");
+                if (leaf.max_def > 0) { dp.def_off = pi.v2_rep_len; dp.def_len = pi.v2_def_len; }
+                dp.val_off = uint32_t(v2_levels);
+              }
               switch (pi.encoding) {
                 case ENC_PLAIN: dp.enc = DE_PLAIN; tc.has_plain_pages = true; break;
                 case ENC_RLE_DICTIONARY: case ENC_PLAIN_DICTIONARY: dp.enc = DE_DICT; tc.has_dict_pages = true; break;
-                case ENC_DELTA_BINARY_PACKED: dp.enc = DE_DELTA; tc.has_delta_pages = true; break;
+                case ENC_DELTA_BINARY_PACKED:
+                  if (leaf.phys_type != PT_INT64) throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': DELTA_BINARY_PACKED on a non-INT64 column");
+                  dp.enc = DE_DELTA; tc.has_delta_pages = true; break;
+                case ENC_DELTA_BYTE_ARRAY: case ENC_DELTA_LENGTH_BYTE_ARRAY:
+                  if (leaf.phys_type != PT_BYTE_ARRAY) throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': DELTA_BYTE_ARRAY on a non-BYTE_ARRAY column");
+                  dp.enc = pi.encoding == ENC_DELTA_BYTE_ARRAY ? DE_DELTA_BYTES : DE_DELTA_LEN_BYTES; tc.has_plain_pages = true; break;
                 case ENC_RLE:
                   if (leaf.phys_type != PT_BOOLEAN) throw Error(PQ_ERR_UNSUPPORTED, "RLE value encoding on a non-boolean column");
                   dp.enc = DE_RLE_BOOL; tc.has_dict_pages = true; break;
                 default: throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page encoding " + std::to_string(pi.encoding) + " not supported");
               }
               wj.prebuilt.push_back(dp);
-            } else if (pi.type == PAGE_DATA_V2) {
-              throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': compressed data page v2 (Parseable writes v1)");
             } else continue;
-            djobs.push_back({coff + pi.offset_in_chunk + pi.header_len, slot, pi.compressed_size, pi.uncompressed_size,
-                             uint32_t(pi.compressed_size == pi.uncompressed_size && cm.codec == CODEC_SNAPPY ? cm.codec : cm.codec), 0});
+            const uint64_t src = coff + pi.offset_in_chunk + pi.header_len;
+            if (pi.type == PAGE_DATA_V2) {
+              const uint32_t lv = uint32_t(v2_levels);
+              if (lv) djobs.push_back({src, slot, lv, lv, 0u, 0});                                     // levels: stored
+              djobs.push_back({src + lv, slot + lv, pi.compressed_size - lv, pi.uncompressed_size - lv,    // values: compressed unless the header says not
+                               pi.v2_compressed ? uint32_t(cm.codec) : 0u, 0});
+            } else {
+              djobs.push_back({src, slot, pi.compressed_size, pi.uncompressed_size, uint32_t(cm.codec), 0});
+            }
           }
           if (first_row != trg.num_rows) throw Error(PQ_ERR_CORRUPT, col_names[c] + ": page rows do not add up to the row group's");
           arena = (arena + 64 + 255) & ~255ull;
@@ -527,7 +575,9 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   PQB_CUDA(cudaMallocAsync((void**)&d_arena, arena_bytes, stream));
   // tail slack must be defined (walkers may look at it)
   PQB_CUDA(cudaMemsetAsync(d_arena + arena, 0, arena_bytes - arena, stream));
+  UnwindGuard unwind(stream);   // an error below: wait for the copies in flight, free the temporaries
   uint8_t* d_comp = nullptr;   // compressed chunks wait here for k_decompress_pages
+  unwind.own(d_comp);
   if (comp) PQB_CUDA(cudaMallocAsync((void**)&d_comp, comp + 256, stream));
 
   // ---- upload: straight from pinned caller buffers, else staged through pinned memory ----
@@ -570,7 +620,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     dim3 grid(uint32_t(gathers.size()), 4);
     k_gather_copy<<<grid, 256, 0, stream>>>(d_gathers, d_arena);
     PQB_CUDA(cudaGetLastError());
-    PQB_CUDA(cudaFreeAsync(d_gathers, stream));
+    dev_drop(d_gathers, stream);
   }
   if (!staged.empty()) {
     // gather into pinned staging slices with a few host threads, one cudaMemcpyAsync per slice;
@@ -636,6 +686,8 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   mark("uploads queued (synchronised for this mark)");
   DecompJob* d_djobs = nullptr;
   unsigned long long* d_dflag = nullptr;
+  unwind.own(d_djobs);
+  unwind.own(d_dflag);
   if (!djobs.empty()) {
     PQB_CUDA(cudaMallocAsync((void**)&d_djobs, djobs.size() * sizeof(DecompJob), stream));
     PQB_CUDA(cudaMallocAsync((void**)&d_dflag, 8, stream));
@@ -705,14 +757,14 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       k_page_fixup<<<uint32_t((fix.size() + 127) / 128), 128, 0, stream>>>(d_pages, d_fix, uint32_t(fix.size()), d_arena, d_dflag);
       PQB_CUDA(cudaGetLastError());
       PQB_CUDA(cudaMemcpyAsync(pages.data(), d_pages, pages.size() * sizeof(DevPage), cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaFreeAsync(d_fix, stream));
+      dev_drop(d_fix, stream);
     }
     unsigned long long flag = 0;
     PQB_CUDA(cudaMemcpyAsync(&flag, d_dflag, 8, cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
-    PQB_CUDA(cudaFreeAsync(d_djobs, stream));
-    PQB_CUDA(cudaFreeAsync(d_dflag, stream));
-    PQB_CUDA(cudaFreeAsync(d_comp, stream));
+    dev_drop(d_djobs, stream);
+    dev_drop(d_dflag, stream);
+    dev_drop(d_comp, stream);
     if (flag) throw Error(PQ_ERR_CORRUPT, "a compressed page did not decode to its declared size (LZ4_RAW / SNAPPY)");
     for (size_t j = 0; j < jobs.size(); j++)
       if (jobs[j].compressed) {
@@ -725,6 +777,61 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
           }
         }
       }
+  }
+  // ---- DELTA_BYTE_ARRAY / DELTA_LENGTH_BYTE_ARRAY pages -> PLAIN BYTE_ARRAY pages (device side, two passes) ----
+  {
+    std::vector<DbaJob> dj;
+    uint64_t tmp = 0;
+    for (size_t i = 0; i < pages.size(); i++)
+      if (pages[i].enc == DE_DELTA_BYTES || pages[i].enc == DE_DELTA_LEN_BYTES) {
+        dj.push_back({uint32_t(i), pages[i].enc == DE_DELTA_BYTES ? 1u : 0u, tmp, 0});
+        tmp += (uint64_t(pages[i].num_rows) * 8 + 15) & ~15ull;
+      }
+    if (!dj.empty()) {
+      DbaJob* d_jobs = nullptr;
+      DbaInfo* d_info = nullptr;
+      uint8_t* d_tmp = nullptr;
+      UnwindGuard tmp_guard(stream);
+      tmp_guard.own(d_jobs); tmp_guard.own(d_info); tmp_guard.own(d_tmp);
+      PQB_CUDA(cudaMallocAsync((void**)&d_jobs, dj.size() * sizeof(DbaJob), stream));
+      PQB_CUDA(cudaMallocAsync((void**)&d_info, dj.size() * sizeof(DbaInfo), stream));
+      PQB_CUDA(cudaMallocAsync((void**)&d_tmp, tmp + 16, stream));
+      PQB_CUDA(cudaMemcpyAsync(d_jobs, dj.data(), dj.size() * sizeof(DbaJob), cudaMemcpyHostToDevice, stream));
+      launch_dba_lengths(d_arena, d_pages, d_jobs, uint32_t(dj.size()), d_tmp, d_info, stream);
+      std::vector<DbaInfo> info(dj.size());
+      PQB_CUDA(cudaMemcpyAsync(info.data(), d_info, info.size() * sizeof(DbaInfo), cudaMemcpyDeviceToHost, stream));
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      uint64_t total = 0;
+      bool bad = false;
+      for (size_t j = 0; j < dj.size(); j++) {
+        const DevPage& pg = pages[dj[j].page];
+        if (!info[j].ok || uint64_t(pg.def_len) + info[j].bytes > 0xfffffff0ull) { bad = true; break; }
+        dj[j].dst = total;
+        total = (total + pg.def_len + info[j].bytes + 16 + 15) & ~15ull;
+      }
+      if (!bad) {
+        // staged windows and the row walker over-read like they do in the arena: same slack
+        PQB_CUDA(cudaMallocAsync((void**)&d_strmat, total + (64u << 10), stream));
+        PQB_CUDA(cudaMemsetAsync(d_strmat + total, 0, 64u << 10, stream));
+        PQB_CUDA(cudaMemcpyAsync(d_jobs, dj.data(), dj.size() * sizeof(DbaJob), cudaMemcpyHostToDevice, stream));
+        launch_dba_materialise(d_arena, d_pages, d_jobs, d_info, uint32_t(dj.size()), d_tmp, d_strmat, stream);
+        for (size_t j = 0; j < dj.size(); j++) {
+          DevPage& pg = pages[dj[j].page];
+          // the new payload lives outside the arena: offsets are relative to the arena base modulo 2^64
+          pg.off = uint64_t(reinterpret_cast<uintptr_t>(d_strmat) + dj[j].dst - reinterpret_cast<uintptr_t>(d_arena));
+          pg.def_off = 0;
+          pg.val_off = pg.def_len;
+          pg.len = uint32_t(pg.def_len + info[j].bytes);
+          pg.enc = DE_PLAIN;
+        }
+        PQB_CUDA(cudaMemcpyAsync(d_pages, pages.data(), pages.size() * sizeof(DevPage), cudaMemcpyHostToDevice, stream));
+      }
+      PQB_CUDA(cudaStreamSynchronize(stream));
+      dev_drop(d_jobs, stream);
+      dev_drop(d_info, stream);
+      dev_drop(d_tmp, stream);
+      if (bad) throw Error(PQ_ERR_CORRUPT, "a DELTA_BYTE_ARRAY page does not decode (length streams / prefixes out of range)");
+    }
   }
   // row groups whose columns all share their page boundaries: work items are simply the pages
   for (TableRowGroup& rg : row_groups) {
@@ -782,10 +889,10 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       launch_flatten_pages(d_arena, d_pages, d_jobs, uint32_t(fjobs.size()), d_slab_flat, d_slab_recs, d_slab_dirs, d_fast, stream);
       PQB_CUDA(cudaMemcpyAsync(fast.data(), d_fast, fast.size(), cudaMemcpyDeviceToHost, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
-      PQB_CUDA(cudaFreeAsync(d_jobs, stream));
+      dev_drop(d_jobs, stream);
     }
-    PQB_CUDA(cudaFreeAsync(d_caps, stream));
-    PQB_CUDA(cudaFreeAsync(d_fast, stream));
+    dev_drop(d_caps, stream);
+    dev_drop(d_fast, stream);
     for (size_t i = 0; i < pages.size(); i++) pages[i].flags = fast[i] == 1 ? 1u : 0u;
     if (getenv("PQB_VERBOSE")) {
       size_t h[5] = {0, 0, 0, 0, 0};
@@ -829,7 +936,7 @@ void Table::build_flat_store(cudaStream_t stream) {
     launch_page_has_nulls(d_arena, d_pages, uint32_t(pages.size()), d_nf, stream);
     PQB_CUDA(cudaMemcpyAsync(has_nulls.data(), d_nf, pages.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
-    PQB_CUDA(cudaFreeAsync(d_nf, stream));
+    dev_drop(d_nf, stream);
     nulls_classified = true;
   }
   struct J { uint64_t src, off, voff, toff; uint32_t page, kind, rows, zone; };
@@ -915,6 +1022,8 @@ void Table::build_flat_store(cudaStream_t stream) {
   void* d_jobs = nullptr;
   uint8_t* d_ok = nullptr;
   uint32_t* d_maxlen = nullptr;
+  UnwindGuard tmp_guard(stream);
+  tmp_guard.own(d_jobs); tmp_guard.own(d_ok); tmp_guard.own(d_maxlen);
   bool any_bytes = false;
   for (const DevJob& j : dj) any_bytes |= j.kind == 6u;
   PQB_CUDA(cudaMallocAsync(&d_jobs, dj.size() * sizeof(DevJob), stream));
@@ -930,23 +1039,55 @@ void Table::build_flat_store(cudaStream_t stream) {
   PQB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, ok.size(), cudaMemcpyDeviceToHost, stream));
   if (any_bytes) PQB_CUDA(cudaMemcpyAsync(maxlen.data(), d_maxlen, maxlen.size() * 4, cudaMemcpyDeviceToHost, stream));
   PQB_CUDA(cudaStreamSynchronize(stream));
-  PQB_CUDA(cudaFreeAsync(d_jobs, stream));
-  PQB_CUDA(cudaFreeAsync(d_ok, stream));
-  if (d_maxlen) PQB_CUDA(cudaFreeAsync(d_maxlen, stream));
+  dev_drop(d_jobs, stream);
+  dev_drop(d_ok, stream);
+  dev_drop(d_maxlen, stream);
   for (size_t i = 0; i < maxlen.size(); i++)
     if (dj[i].kind == 6u && ok[i]) {
       ColSide& cs = sides[pages[dj[i].page].chunk_slot];
       cs.max_plain_len = std::max(cs.max_plain_len, maxlen[i]);
     }
   size_t n_ok = 0, n_nul = 0;
+  const bool lenient = getenv("PQB_FLAT_LENIENT") != nullptr;   // debugging: keep a refused page on the k_scan path instead of failing the file
   for (size_t i = 0; i < dj.size(); i++) {
     if (dj[i].kind == 4u) continue;
     if (ok[i]) { n_ok += dj[i].kind != 5u; n_nul += dj[i].vdst != kNone; }
-    else { flat_pages[dj[i].page].fkind = FK_NONE; flat_pages[dj[i].page].voff = kNone; }   // a stream the walker refused: k_scan reads the original
+    else if (lenient) { flat_pages[dj[i].page].fkind = FK_NONE; flat_pages[dj[i].page].voff = kNone; }
+    else {
+      // a run header past the page, a length prefix past the page, a stream that stops early: the reference's reader fails such a file
+      const DevPage& pg = pages[dj[i].page];
+      throw Error(PQ_ERR_CORRUPT, "column '" + columns[pg.chunk_slot].name + "': the value stream of a data page (" + std::to_string(pg.num_rows) +
+                                      " rows, first row " + std::to_string(pg.first_row) + " of its row group) is malformed");
+    }
   }
   flat_page_count = n_ok;
   PQB_CUDA(cudaMallocAsync((void**)&d_flat_pages, flat_pages.size() * sizeof(FlatPageRec), stream));
   PQB_CUDA(cudaMemcpyAsync(d_flat_pages, flat_pages.data(), flat_pages.size() * sizeof(FlatPageRec), cudaMemcpyHostToDevice, stream));
+  {
+    // dictionary indices must stay inside their dictionary (checked once, here; the scan kernels only clamp)
+    std::vector<uint32_t> dn(pages.size(), 0);
+    for (const TableRowGroup& rg : row_groups)
+      for (const TableChunk& tc : rg.chunks)
+        if (tc.present)
+          for (uint32_t k = 0; k < tc.pages.n_pages; k++) dn[tc.pages.first_page + k] = tc.dict_n;
+    uint32_t* d_dn = nullptr;
+    uint32_t* d_bad = nullptr;
+    PQB_CUDA(cudaMallocAsync((void**)&d_dn, dn.size() * 4, stream));
+    PQB_CUDA(cudaMallocAsync((void**)&d_bad, 4, stream));
+    PQB_CUDA(cudaMemcpyAsync(d_dn, dn.data(), dn.size() * 4, cudaMemcpyHostToDevice, stream));
+    PQB_CUDA(cudaMemsetAsync(d_bad, 0xff, 4, stream));
+    launch_check_flat_indices(d_flat, d_flat_pages, d_dn, uint32_t(pages.size()), d_bad, stream);
+    uint32_t first_bad = ~0u;
+    PQB_CUDA(cudaMemcpyAsync(&first_bad, d_bad, 4, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    dev_drop(d_dn, stream);
+    dev_drop(d_bad, stream);
+    if (first_bad != ~0u) {
+      const DevPage& pg = pages[first_bad];
+      throw Error(PQ_ERR_CORRUPT, "column '" + columns[pg.chunk_slot].name + "': a dictionary index is outside the dictionary (" +
+                                      std::to_string(dn[first_bad]) + " entries)");
+    }
+  }
   if (getenv("PQB_VERBOSE"))
     fprintf(stderr, "[pqb] flat store: %zu of %zu pages (%zu with NULLs), %llu bytes (arena %llu)\n", n_ok, pages.size(), n_nul,
             (unsigned long long)flat_bytes, (unsigned long long)arena_bytes);
@@ -1151,8 +1292,8 @@ void Table::ensure_plain8(int tcol, cudaStream_t stream) const {
     std::vector<uint8_t> ok(jobs.size());
     PQB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, ok.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
-    PQB_CUDA(cudaFreeAsync(d_jobs, stream));
-    PQB_CUDA(cudaFreeAsync(d_ok, stream));
+    dev_drop(d_jobs, stream);
+    dev_drop(d_ok, stream);
     for (size_t i = 0; i < jobs.size(); i++) {
       if (!ok[i]) continue;   // a stream the decoder refused: the page stays with k_scan
       FlatPageRec& fr = flat_pages[jobs[i].page];

@@ -266,9 +266,12 @@ def test_arrow_default_pages_and_v2(data_dir, built):
     req = pa.schema([pa.field("k", pa.int64(), False), pa.field("v", pa.int64(), False), pa.field("f", pa.float64(), True),
                      pa.field("s", pa.string(), False), pa.field("b", pa.bool_(), True)])
     t = t.cast(req)
-    for ver, kw in (("1.0", {}), ("2.0", {}), ("1.0", {"use_dictionary": ["k", "s"], "data_page_size": 64 << 10})):
-        p = os.path.join(data_dir, f"arrow_default_{ver}_{len(kw)}.parquet")
-        pq.write_table(t, p, compression="NONE", data_page_version=ver, row_group_size=120_000, **kw)
+    # v2 pages keep their level bytes uncompressed in front of the (compressed) values
+    for ver, kw in (("1.0", {}), ("2.0", {}), ("1.0", {"use_dictionary": ["k", "s"], "data_page_size": 64 << 10}),
+                    ("2.0", {"compression": "LZ4"}), ("2.0", {"compression": "SNAPPY", "data_page_size": 64 << 10})):
+        p = os.path.join(data_dir, f"arrow_default_{ver}_{len(kw)}_{kw.get('compression', 'NONE')}.parquet")
+        kw = dict({"compression": "NONE"}, **kw)
+        pq.write_table(t, p, data_page_version=ver, row_group_size=120_000, **kw)
         ora = Oracle.from_parquet(p)
         prov = StandardTableProvider([p], schema=ora.table.schema)
         for flt in ([col("k") == 7], [(col("v") > 0) & (col("s") == "ccc")], [col("f") < -1.0], [col("b") == True],  # noqa: E712
@@ -514,6 +517,77 @@ def test_projection_of_a_column_missing_from_one_file(data_dir, built):
         assert got[c].to_pylist() == exp[c].to_pylist(), c
     keys, aggs = ["k"], [count_star(), count("extra"), sum_("extra"), max_("extra")]
     assert_tables_equal(prov.aggregate(keys, aggs).table(), ora.group_by(keys, aggs, []), keys)
+
+
+@pytest.mark.parametrize("variant", ["v1_none", "v2_lz4", "v1_snappy_small_pages"])
+def test_delta_byte_array_pages(data_dir, built, variant):
+    """Front-coded strings: DELTA_BYTE_ARRAY is the fallback encoding Parseable sets on custom-partition columns
+    (streams.rs:614-619), DELTA_LENGTH_BYTE_ARRAY its prefix-less sibling.  The pages are rewritten as PLAIN BYTE_ARRAY
+    pages on the device at table open; filters, projections and COUNTs then see the same strings as the oracle.
+    Sorted values (long shared prefixes), random values (no prefixes), empty strings, NULLs, multi-byte characters."""
+    rng = np.random.default_rng(31)
+    n = 150_000
+    part = np.array([f"tenant-{i // 37:05d}/zone-{i % 5}/δ{i % 3}" for i in range(n)], dtype=object)       # sorted: long shared prefixes
+    part[rng.random(n) < 0.02] = None
+    rnd = np.array(["".join(chr(97 + int(c)) for c in rng.integers(0, 26, int(k))) for k in rng.integers(0, 24, n)], dtype=object)   # incl. ""
+    rnd[rng.random(n) < 0.05] = None
+    t = pa.table({"id": pa.array(np.arange(n, dtype=np.int64)), "part": pa.array(part, pa.string()), "rnd": pa.array(rnd, pa.string()),
+                  "dl": pa.array(rnd, pa.string()), "v": pa.array(rng.integers(0, 100, n).astype(np.int64))})
+    kw = {"v1_none": dict(compression="NONE", data_page_version="1.0"),
+          "v2_lz4": dict(compression="LZ4", data_page_version="2.0"),
+          "v1_snappy_small_pages": dict(compression="SNAPPY", data_page_version="1.0", data_page_size=16 << 10)}[variant]
+    p = os.path.join(data_dir, f"delta_byte_array_{variant}.parquet")
+    pq.write_table(t, p, row_group_size=60_000, use_dictionary=["v"],
+                   column_encoding={"part": "DELTA_BYTE_ARRAY", "rnd": "DELTA_BYTE_ARRAY", "dl": "DELTA_LENGTH_BYTE_ARRAY"}, **kw)
+    md = pq.ParquetFile(p).metadata.row_group(0)
+    encs = {md.column(i).path_in_schema: set(md.column(i).encodings) for i in range(5)}
+    assert "DELTA_BYTE_ARRAY" in encs["part"] and "DELTA_LENGTH_BYTE_ARRAY" in encs["dl"], encs
+    ora = Oracle(t)
+    prov = StandardTableProvider([p], schema=t.schema)
+    flts = {
+        "eq": [col("part") == "tenant-00123/zone-4/δ1"],
+        "range": [(col("part") >= "tenant-02000") & (col("part") < "tenant-02010")],
+        "like_multibyte": [col("part").like("%/zone-3/δ0")],
+        "rnd_prefix": [col("rnd").like("ab%")],
+        "empty_string": [col("rnd") == ""],
+        "dl_suffix_and_dict": [col("dl").like("%zz") & (col("v") < 50)],
+        "is_null_or": [col("part").is_null() | (col("dl") == "q")],
+        "not_like": [col("rnd").like("%a%", negated=True)],
+    }
+    for name, flt in flts.items():
+        assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt), (variant, name)
+    for name in ("range", "rnd_prefix", "is_null_or"):
+        flt = flts[name]
+        got = prov.scan(projection=["id", "part", "rnd", "dl"], filters=flt, row_ids=True).table()
+        exp, ids = _project_expect(ora, flt, ["id", "part", "rnd", "dl"])
+        assert len(ids) > 10 and np.array_equal(got["__row_id"].to_numpy(), ids), (variant, name)
+        for c in ["id", "part", "rnd", "dl"]:
+            assert got[c].to_pylist() == exp[c].to_pylist(), (variant, name, c)
+    keys, aggs = ["v"], [count_star(), count("part"), count("dl")]
+    assert_tables_equal(prov.aggregate(keys, aggs, flts["rnd_prefix"]).table(), ora.group_by(keys, aggs, flts["rnd_prefix"]), keys)
+
+
+def test_corrupt_dictionary_index_is_refused(data_dir, built):
+    """A dictionary index outside the dictionary: the reference's Parquet reader fails the file; so does the table
+    open (every index of the flat store is checked once, on the device) -- never a read outside a LUT."""
+    rng = np.random.default_rng(41)
+    n = 50_000
+    t = pa.table({"k": pa.array(np.array(["a", "b", "c", "d", "e"])[rng.integers(0, 5, n)]), "v": pa.array(np.arange(n, dtype=np.int64))})
+    p = os.path.join(data_dir, "corrupt_index.parquet")
+    pq.write_table(t, p, compression="NONE", use_dictionary=["k"], data_page_size=1 << 20)
+    schema = pa.schema([pa.field("k", pa.string()), pa.field("v", pa.int64())])
+    assert StandardTableProvider([p], schema=schema).scan(filters=[col("k") == "c"], count_only=True).metrics["rows_selected"] == int((np.array(t["k"].to_pylist()) == "c").sum())
+    cm = pq.ParquetFile(p).metadata.row_group(0).column(0)
+    raw = bytearray(open(p, "rb").read())
+    mid = cm.data_page_offset + (cm.total_compressed_size - (cm.data_page_offset - (cm.dictionary_page_offset or cm.data_page_offset))) // 2
+    raw[mid:mid + 3] = b"\xff\xff\xff"          # 3-bit indices of a 5-entry dictionary: eight 7s
+    bad = os.path.join(data_dir, "corrupt_index_bad.parquet")
+    open(bad, "wb").write(bytes(raw))
+    with pytest.raises(QueryError) as e:
+        StandardTableProvider([bad], schema=schema).scan(filters=[col("k") == "c"], count_only=True)
+    assert e.value.code == L.PQ_ERR_CORRUPT and "dictionary" in str(e.value)
+    # a later query on a good file still works (the context is not poisoned)
+    assert StandardTableProvider([p], schema=schema).scan(filters=[col("v") < 10], count_only=True).metrics["rows_selected"] == 10
 
 
 def test_plain_byte_array_pages(data_dir, built):
