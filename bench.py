@@ -50,11 +50,14 @@ C2_WORKLOAD = "C2 scan+filter: WHERE level='ERROR' AND latency_ms>100 -> row ids
 
 
 # ------------------------------------------------------------------ data
+# Headline files are UNCOMPRESSED (north_star's decode list); PQB_BENCH_CODEC=LZ4 writes the same row groups
+# with Parseable's default codec (LZ4_RAW, src/cli.rs:441-448) for development probes (tests/scripts/open_probe.py)
+CODEC = os.environ.get("PQB_BENCH_CODEC", "NONE").upper()
 def _gen_one(args):
     path, first, n = args
     from parseable_b200 import synth
     if not os.path.exists(path):
-        synth.write_logs16(path, n_row_groups=n, first_rg=first, columns=COLS)
+        synth.write_logs16(path, n_row_groups=n, first_rg=first, columns=COLS, compression=CODEC)
     return path
 
 
@@ -62,7 +65,7 @@ def file_jobs(n_row_groups: int):
     jobs, g = [], 0
     while g < n_row_groups:
         n = min(RGS_PER_FILE, n_row_groups - g)
-        jobs.append((os.path.join(DATA_DIR, f"logs8_{g:06d}_{n}.parquet"), g, n))
+        jobs.append((os.path.join(DATA_DIR, f"logs8_{g:06d}_{n}{'' if CODEC == 'NONE' else '_' + CODEC.lower()}.parquet"), g, n))
         g += n
     return jobs
 

@@ -25,6 +25,20 @@ struct DecompJob {
   uint32_t _pad;
 };
 
+// literal run: `len` bytes that do not overlap.  Eight independent byte loads per lane and trip: the copy is latency
+// bound (a page of incompressible bit-packed indices or PLAIN doubles is one long literal run)
+__device__ __forceinline__ void warp_literal_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t len, uint32_t lane) {
+  uint32_t i = lane;
+  for (; i + 7 * 32 < len; i += 8 * 32) {
+    uint8_t b[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) b[k] = s[i + k * 32];
+#pragma unroll
+    for (int k = 0; k < 8; k++) d[i + k * 32] = b[k];
+  }
+  for (; i < len; i += 32) d[i] = s[i];
+}
+
 // match copy with LZ77 overlap semantics: the source pattern [dp-off, dp) already exists, bytes
 // beyond it repeat with period `off`
 __device__ __forceinline__ void warp_match_copy(uint8_t* d, uint32_t dp, uint32_t off, uint32_t len, uint32_t lane) {
@@ -47,7 +61,7 @@ __global__ void k_decompress_pages(const DecompJob* __restrict__ jobs, uint32_t 
   uint32_t sp = 0, dp = 0;
   bool bad = false;
   if (job.codec == 0) {
-    for (uint32_t i = lane; i < sn && i < dn; i += 32) d[i] = s[i];
+    warp_literal_copy(d, s, sn < dn ? sn : dn, lane);
     return;
   }
   if (job.codec == 7) {
@@ -60,7 +74,7 @@ __global__ void k_decompress_pages(const DecompJob* __restrict__ jobs, uint32_t 
         do { if (sp >= sn) { bad = true; break; } b = s[sp++]; lit += b; } while (b == 255);
       }
       if (bad || sp + lit > sn || dp + lit > dn) { bad = true; break; }
-      for (uint32_t i = lane; i < lit; i += 32) d[dp + i] = s[sp + i];
+      warp_literal_copy(d + dp, s + sp, lit, lane);
       sp += lit;
       dp += lit;
       if (sp >= sn) break;  // the last sequence carries literals only
@@ -103,7 +117,7 @@ __global__ void k_decompress_pages(const DecompJob* __restrict__ jobs, uint32_t 
           sp += nb;
         }
         if (sp + len > sn || dp + len > dn) { bad = true; break; }
-        for (uint32_t i = lane; i < len; i += 32) d[dp + i] = s[sp + i];
+        warp_literal_copy(d + dp, s + sp, len, lane);
         sp += len;
         dp += len;
         __syncwarp();

@@ -35,11 +35,20 @@
 
 namespace pqb {
 
-constexpr int kFlatStagesMax = 4;
+constexpr int kFlatStagesMax = 16;
 constexpr int kFilterConsumerWarps = 4;
+#ifndef PQB_WAIT_HINT
+#define PQB_WAIT_HINT 0
+#endif
+#ifndef PQB_FILTER_ROLL
+#define PQB_FILTER_ROLL 1   // 0: the two words of a thread unrolled (two copies of every leaf routine)
+#endif
+#ifndef PQB_FILTER_ILP
+#define PQB_FILTER_ILP 1   // 0: the serial funnel chain / one survivor per trip (A/B builds: make EXTRA=-DPQB_FILTER_ILP=0)
+#endif
 constexpr int kFilterWords = 2;                                    // 32-row bitmap words per consumer thread per slab
 constexpr int kFilterThreads = 32 * (kFilterConsumerWarps + 1);
-constexpr int kFilterSlabRows = 32 * 32 * kFilterWords * kFilterConsumerWarps;   // 8192
+constexpr int kFilterSlabRows = 32 * 32 * kFilterWords;   // 2048: one WARP's slab (k_flat_filter's stages are taken warp by warp)
 constexpr int kAggThreads = 1024;
 constexpr int kAggConsumers = kAggThreads - 32;
 
@@ -47,6 +56,7 @@ struct FlatLayout {              // dynamic shared memory of the flat kernels (b
   uint32_t nstages;
   uint32_t stage_bytes;
   uint32_t stage0;               // first stage buffer
+  uint32_t meta0, meta_stride;   // FlatStage records, one per stage, holding only the referenced columns
   uint32_t col_off[kMaxCols];    // values of column c inside a stage (16-byte aligned)
   uint32_t col_voff[kMaxCols];   // validity bits of column c inside a stage (columns that may hold NULLs)
   uint32_t acc;                  // hot accumulator table (k_flat_agg)
@@ -78,8 +88,13 @@ struct FlatStage {
 struct FlatCtl {
   uint64_t full[kFlatStagesMax];
   uint64_t empty[kFlatStagesMax];
-  FlatStage st[kFlatStagesMax];
+  uint32_t ticket;               // k_flat_filter: the next stage (in fill order) nobody has taken yet
+  uint32_t _pad[3];
 };
+// stage record s (the col[] tail is allocated for plan.ncols columns only: L.meta_stride)
+__device__ __forceinline__ FlatStage& flat_stage(uint8_t* smem, const FlatLayout& L, uint32_t s) {
+  return *reinterpret_cast<FlatStage*>(smem + L.meta0 + s * L.meta_stride);
+}
 
 __device__ __forceinline__ uint32_t flat_col_bytes(uint32_t phase, uint32_t bw, uint32_t rows) {
   const uint32_t nb = (phase + rows * bw + 7u) >> 3;
@@ -87,13 +102,27 @@ __device__ __forceinline__ uint32_t flat_col_bytes(uint32_t phase, uint32_t bw, 
 }
 
 // ---- producer: one warp; lane 0 owns the queue, the barriers and the TMA copies ------------------
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  // mbarrier.try_wait parks the thread in hardware until the phase completes or the hint runs out
-  while (!mbar_try_wait_hint(bar, parity, 100000u)) {}
+// Wait with a real back-off.  mbarrier.try_wait's suspend-time hint does not park the thread for long: ptxas turns it
+// into a four-instruction TRYWAIT / NANOSLEEP.SYNCS loop, and a waiting warp -- the producer waits for a free stage
+// most of its life -- ran that loop 10^8 times per launch: 15-18 % of all executed instructions, taken from the
+// scheduler it shares with seven or eight working warps (profiles/k_flat_agg_r2b, k_flat_filter_r2b).
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity, uint32_t max_ns) {
+#if PQB_WAIT_HINT
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {}   // A/B: the hint-only wait
+  return;
+#endif
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t ns = 64;
+  do {
+    __nanosleep(ns);
+    if (ns < max_ns) ns <<= 1;
+  } while (!mbar_try_wait(bar, parity));
 }
 
+// `takers`: how many consumers must see the end-of-queue record (k_flat_agg: 1, every warp reads every stage;
+// k_flat_filter: one per consumer warp, every warp takes stages of its own)
 __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout& L, const DevScanArgs& a, FlatCtl& ctl,
-                                           uint8_t* smem, uint32_t S) {
+                                           uint8_t* smem, uint32_t S, uint32_t takers, uint32_t wait_ns) {
   const uint32_t lane = threadIdx.x & 31;
   uint32_t stage = 0, par = 1;   // parity the next wait on empty[stage] needs; a fresh barrier counts as released
   const uint32_t ncols = plan.ncols;
@@ -145,9 +174,9 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
     const bool staged = lane < ncols && plan.cols[lane].staged && !(mycol.flags & kColAbsent);
     for (uint32_t r0 = 0; r0 < nrows; r0 += S) {
       const uint32_t R = nrows - r0 < S ? nrows - r0 : S;
-      if (lane == 0) mbar_wait_spin(&ctl.empty[stage], par);
+      if (lane == 0) mbar_wait_spin(&ctl.empty[stage], par, wait_ns);
       __syncwarp();
-      FlatStage& st = ctl.st[stage];
+      FlatStage& st = flat_stage(smem, L, stage);
       // first bit of the slab in the page's flat copy; the copy starts at the 16-byte boundary below it
       const uint64_t bit0 = uint64_t(mypoff + r0) * mycol.bw, vbit0 = uint64_t(mypoff) + r0;
       mycol.phase = uint32_t(bit0 & 127u);
@@ -183,9 +212,12 @@ __device__ __noinline__ void flat_producer(const DevPlan& plan, const FlatLayout
     }
   }
   if (lane == 0) {
-    mbar_wait_spin(&ctl.empty[stage], par);
-    ctl.st[stage].item = 0xffffffffu;
-    mbar_arrive(&ctl.full[stage]);
+    for (uint32_t t = 0; t < takers; t++) {
+      mbar_wait_spin(&ctl.empty[stage], par, wait_ns);
+      flat_stage(smem, L, stage).item = 0xffffffffu;
+      mbar_arrive(&ctl.full[stage]);
+      if (++stage == L.nstages) { stage = 0; par ^= 1u; }
+    }
   }
 }
 
@@ -193,25 +225,30 @@ __device__ __forceinline__ void flat_ctl_init(FlatCtl& ctl, uint32_t nstages, ui
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < nstages; s++) {
       mbar_init(&ctl.full[s], 1);
-      mbar_init(&ctl.empty[s], consumer_warps);
+      mbar_init(&ctl.empty[s], consumer_warps);   // arrivals that hand a stage back
     }
+    ctl.ticket = 0;
     mbar_fence_init();
   }
 }
 
 // ---- one staged column of the current slab ------------------------------------------------------
 struct ColCtx {
-  const uint32_t* colw;      // values: flat bits / 8-byte slots, whole words of the phase folded in
+  const uint32_t* colw;      // staged values (shared memory): flat bits / 8-byte slots, whole words of the phase folded in
+  const uint64_t* v8;        // 8-byte values of a PLAIN8 page: the staged ones, or (k_flat_agg) the flat store's in global memory.
+                             // Two pointers so that neither ever mixes address spaces (a mixed one makes every load generic)
   const uint32_t* vw;        // validity bits (nullptr: every row valid, unless `absent`)
   uint32_t phase, vphase;    // remaining bit phases (0..31) of row 0
   uint32_t bw, mask, dict_max, fkind;
   bool absent;               // column missing from this file: every row NULL
 };
+template <bool DIRECT8>
 __device__ __forceinline__ void col_ctx(ColCtx& c, const FlatStage& st, const uint8_t* base, const FlatLayout& L, uint32_t col,
                                         const uint8_t* flat) {
   const FlatStageCol& sc = st.col[col];
-  c.colw = (sc.flags & kColDirect) ? reinterpret_cast<const uint32_t*>(flat + sc.dict8)   // 8-byte values read in place (k_flat_agg)
-                                   : reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
+  c.colw = reinterpret_cast<const uint32_t*>(base + L.col_off[col]) + (sc.phase >> 5);
+  if (DIRECT8) c.v8 = reinterpret_cast<const uint64_t*>(flat + sc.dict8);   // k_flat_agg: 8-byte values read in place (only used on PLAIN8 pages)
+  else c.v8 = reinterpret_cast<const uint64_t*>(c.colw);
   c.phase = sc.phase & 31u;
   c.vw = (sc.flags & kColHasValid) ? reinterpret_cast<const uint32_t*>(base + L.col_voff[col]) + (sc.vphase >> 5) : nullptr;
   c.vphase = sc.vphase & 31u;
@@ -255,12 +292,13 @@ struct LeafCtx {
   bool f64;
 };
 
+template <bool DIRECT8>
 __device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const DevScanArgs& a, const FlatStage& st,
                                          const uint8_t* stage_base, const FlatLayout& L, uint32_t l) {
   const DevLeaf& lf = plan.leaves[l];
   const uint32_t c = lf.col;
   const FlatStageCol& sc = st.col[c];
-  col_ctx(x.c, st, stage_base, L, c, a.flat);
+  col_ctx<DIRECT8>(x.c, st, stage_base, L, c, a.flat);
   x.cmp = lf.cmp;
   x.lkind = lf.kind;
   x.f64 = plan.cols[c].kind == DK_F64;
@@ -290,7 +328,7 @@ __device__ __forceinline__ bool leaf_row(const LeafCtx& x, uint32_t row) {
     case LM_TRUE: return true;
     case LM_REGLUT: return (__funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.c.colw, x.c.phase + row * x.c.bw)) & 1u) != 0;
     case LM_MEMLUT: return x.lut[col_index(x.c, row)] != 0;
-    case LM_PLAIN8: return plain_cmp(reinterpret_cast<const uint64_t*>(x.c.colw)[row], x);
+    case LM_PLAIN8: return plain_cmp(x.c.v8[row], x);
     case LM_BYTES: {
       // the string itself (no dictionary to answer for it): arrow-ord / arrow-string semantics on the raw bytes
       const uint8_t* sp = x.lut + bits32_at(x.c.colw, x.c.phase + row * 32);
@@ -320,6 +358,22 @@ __device__ __forceinline__ uint32_t leaf_survivors(const LeafCtx& x, uint32_t ro
   uint32_t mm = m;
   if (x.mode == LM_MEMLUT) {
     const uint32_t bit0 = x.c.phase + row0 * x.c.bw;
+#if PQB_FILTER_ILP
+    // two survivors per trip: their index extractions and LUT probes overlap (one trip is a chain of
+    // shared load -> funnel -> global LUT byte)
+    while (mm) {
+      const uint32_t k0 = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const uint32_t k1 = mm ? __ffs(mm) - 1 : k0;
+      mm &= mm - 1;   // mm == 0 stays 0
+      uint32_t v0 = bits32_at(x.c.colw, bit0 + k0 * x.c.bw) & x.c.mask, v1 = bits32_at(x.c.colw, bit0 + k1 * x.c.bw) & x.c.mask;
+      v0 = v0 < x.c.dict_max ? v0 : x.c.dict_max;
+      v1 = v1 < x.c.dict_max ? v1 : x.c.dict_max;
+      const uint32_t t0 = x.lut[v0], t1 = x.lut[v1];
+      m &= ~((t0 ? 0u : 1u) << k0);
+      m &= ~((t1 ? 0u : 1u) << k1);   // k1 == k0 when there was only one: same answer twice
+    }
+#else
     while (mm) {
       const uint32_t k = __ffs(mm) - 1;
       mm &= mm - 1;
@@ -327,6 +381,7 @@ __device__ __forceinline__ uint32_t leaf_survivors(const LeafCtx& x, uint32_t ro
       v = v < x.c.dict_max ? v : x.c.dict_max;
       if (!x.lut[v]) m ^= 1u << k;
     }
+#endif
     return m;
   }
   if (x.mode == LM_TRUE) return m;
@@ -347,8 +402,28 @@ __device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w
 #pragma unroll
   for (int i = 0; i < BW; i++) x[i] = w[i];
   x[BW] = 0;
-  uint32_t m = 0;
   constexpr uint32_t mask = BW >= 32 ? 0xffffffffu : ((1u << BW) - 1u);
+#if PQB_FILTER_ILP
+  // four independent chains of eight (values 8c .. 8c+7 end up in the top byte of q[c]): the 32-step funnel chain was
+  // the longest dependency of the kernel (`wait` stalls in the profile), three PRMTs put the bytes together
+  uint32_t q[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    const int bit = k * BW, wi = bit >> 5, sh = bit & 31;
+    uint32_t v = (sh + BW <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
+    uint32_t t;
+    if (REGLUT) t = __funnelshift_r(lutreg, lutreg, v);
+    else {
+      v &= mask;
+      v = v < dict_max ? v : dict_max;
+      t = lut[v];
+    }
+    q[k >> 3] = __funnelshift_r(q[k >> 3], t, 1);
+  }
+  const uint32_t lo = __byte_perm(q[0], q[1], 0x0073), hi = __byte_perm(q[2], q[3], 0x7300);
+  return __byte_perm(lo, hi, 0x7610);
+#else
+  uint32_t m = 0;
 #pragma unroll
   for (int k = 0; k < 32; k++) {
     const int bit = k * BW, wi = bit >> 5, sh = bit & 31;
@@ -363,6 +438,7 @@ __device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w
     m = __funnelshift_r(m, t, 1);                          // shift the answer in from the top: after 32 steps bit k = value k
   }
   return m;
+#endif
 }
 
 // dense comparison of one leaf over the thread's 32 rows [32*tc, 32*tc + 32) (blocked mapping); NULL rows
@@ -435,7 +511,7 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
     default: {
       // LM_PLAIN8: transposed over the warp (lane L reads row base + 32 j + L: conflict free), lane j keeps word j
       const uint32_t lane = threadIdx.x & 31, wbase = (tc - lane) * 32;   // the warp's 32 consecutive words: lane j owns word (tc - lane) + j
-      const uint64_t* v8 = reinterpret_cast<const uint64_t*>(x.c.colw);
+      const uint64_t* v8 = x.c.v8;
       uint32_t mine = 0;
 #pragma unroll 4
       for (uint32_t j = 0; j < 32; j++) {
@@ -467,25 +543,34 @@ __device__ __forceinline__ Tri32 tri_or(Tri32 a, Tri32 b) {
 __device__ __forceinline__ Tri32 tri_not(Tri32 a) { return {~(a.t | a.n), a.n}; }
 
 // ---- k_flat_filter ------------------------------------------------------------------------------
+// CONJ: the predicate is a pure conjunction of leaves (or there is none) -- its own instantiation, without the
+// three-valued evaluation stack of general programs (registers, local memory and instruction-cache footprint)
+template <bool CONJ>
 __global__ void __launch_bounds__(kFilterThreads, 6)
-k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const DevScanArgs a) {
+k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const __grid_constant__ DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   FlatCtl& ctl = *reinterpret_cast<FlatCtl*>(smem);
-  flat_ctl_init(ctl, L.nstages, kFilterConsumerWarps);
+  flat_ctl_init(ctl, L.nstages, 1);
   __syncthreads();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == kFilterConsumerWarps) {   // the last warp produces
-    flat_producer(plan, L, a, ctl, smem, plan.flat_slab_rows);
+    flat_producer(plan, L, a, ctl, smem, plan.flat_slab_rows, kFilterConsumerWarps, 512);   // a stage comes back every ~1.5 us
     return;
   }
-  // consumer thread: bitmap words warp * 64 + h * 32 + lane (h = 0, 1) of every slab, rows [32 word, 32 word + 32)
+  // A stage is ONE warp's slab (<= 2048 rows): a consumer warp draws the next stage in fill order with a ticket,
+  // works through it alone and hands it back alone -- no warp ever waits for a slower one, and the ring is as deep as
+  // shared memory allows (L.nstages is a power of two).  Thread: bitmap words h * 32 + lane (h = 0, 1) of the slab.
   uint32_t word[kFilterWords];
 #pragma unroll
-  for (int h = 0; h < kFilterWords; h++) word[h] = warp * 32 * kFilterWords + h * 32 + lane;
-  uint32_t stage = 0, par = 0;
+  for (int h = 0; h < kFilterWords; h++) word[h] = h * 32 + lane;
+  const uint32_t stage_mask = L.nstages - 1, stage_shift = 31u - __clz(L.nstages);
   for (;;) {
-    mbar_wait_spin(&ctl.full[stage], par);
-    const FlatStage& st = ctl.st[stage];
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&ctl.ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const uint32_t stage = ticket & stage_mask, par = (ticket >> stage_shift) & 1u;
+    mbar_wait_spin(&ctl.full[stage], par, 256);
+    const FlatStage& st = flat_stage(smem, L, stage);
     if (st.item == 0xffffffffu) break;
     const uint32_t R = st.R;
     const uint8_t* base = smem + L.stage0 + stage * L.stage_bytes;
@@ -497,7 +582,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
       m[h] = inr[h];
     }
     if (plan.npred) {
-      if (plan.conj) {
+      if (CONJ) {
         // conjunction: a row passes when every leaf is TRUE (a NULL leaf drops it).  First leaf on every row,
         // the others on the survivors only (or dense when many survive)
         for (uint32_t l = 0; l < plan.nleaves; l++) {
@@ -507,8 +592,29 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
           const uint32_t mx = l ? __reduce_max_sync(0xffffffffu, pc) : 64u;
           if (mx == 0) break;
           LeafCtx x;
-          leaf_ctx(x, plan, a, st, base, L, l);
+          leaf_ctx<false>(x, plan, a, st, base, L, l);
           const bool dense = mx > 12;
+#if PQB_FILTER_ROLL
+          // ONE copy of the leaf code for both words (the loop is not unrolled; the word in hand rotates through
+          // registers): half the instruction-cache footprint of the hot path
+          uint32_t ma = m[0], mb = m[1], ia = inr[0], ib = inr[1], wa = word[0];
+#pragma unroll 1
+          for (int h = 0; h < kFilterWords; h++) {
+            const uint32_t V = ia ? col_valid32(x.c, wa * 32) : 0u;
+            if (x.lkind == LK_IS_NULL) ma &= ~V;
+            else {
+              ma &= V;
+              if (x.lkind != LK_IS_NOT_NULL) {
+                if (dense) ma &= leaf_dense(x, wa, R, ma);
+                else ma = leaf_survivors(x, wa * 32, ma);
+              }
+            }
+            uint32_t t = ma; ma = mb; mb = t;
+            t = ia; ia = ib; ib = t;
+            wa ^= word[0] ^ word[1];
+          }
+          m[0] = ma; m[1] = mb;
+#else
 #pragma unroll
           for (int h = 0; h < kFilterWords; h++) {
             const uint32_t V = inr[h] ? col_valid32(x.c, word[h] * 32) : 0u;
@@ -518,6 +624,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
             if (dense) m[h] &= leaf_dense(x, word[h], R, m[h]);
             else m[h] = leaf_survivors(x, word[h] * 32, m[h]);
           }
+#endif
         }
       } else {
         // general boolean program, SQL three-valued logic (NULLs come from validity bitmaps and NULL literals)
@@ -528,7 +635,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
           const DevPredOp op = plan.pred[i];
           if (op.kind == PK_LEAF) {
             LeafCtx x;
-            leaf_ctx(x, plan, a, st, base, L, op.arg);
+            leaf_ctx<false>(x, plan, a, st, base, L, op.arg);
 #pragma unroll
             for (int h = 0; h < kFilterWords; h++) {
               const uint32_t V = inr[h] ? col_valid32(x.c, word[h] * 32) : 0u;
@@ -566,7 +673,6 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
       mbar_arrive(&ctl.empty[stage]);
       if (cnt) atomicAdd(&a.item_counts[item], cnt);
     }
-    if (++stage == L.nstages) { stage = 0; par ^= 1u; }
   }
 }
 
@@ -606,7 +712,7 @@ __device__ __forceinline__ void cell_min_max(unsigned long long* cell, bool hot,
 // Cold slots (cell >= hot cells) go to the global table at cell - 31 T = slot.
 template <int KR>
 __global__ void __launch_bounds__(kAggThreads, 1)
-k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const DevScanArgs a) {
+k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const __grid_constant__ DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   FlatCtl& ctl = *reinterpret_cast<FlatCtl*>(smem);
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -633,13 +739,13 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
   const uint32_t Hw = smem_warp ? Hs : 0u, Tw = smem_warp ? T : 0u;
   unsigned long long* gadj = gacc - 31u * Tw;   // indexed by cell: gadj[cell] == gacc[slot] for a cold slot
   if (warp == kAggConsumers / 32) {
-    flat_producer(plan, L, a, ctl, smem, S);
+    flat_producer(plan, L, a, ctl, smem, S, 1, 2048);   // a slab takes tens of microseconds
   } else {
     const uint32_t tc = threadIdx.x;
     uint32_t stage = 0, par = 0;
     for (;;) {
-      mbar_wait_spin(&ctl.full[stage], par);
-      const FlatStage& st = ctl.st[stage];
+      mbar_wait_spin(&ctl.full[stage], par, 256);
+      const FlatStage& st = flat_stage(smem, L, stage);
       if (st.item == 0xffffffffu) break;
       const uint32_t R = st.R;
       const uint8_t* base = smem + L.stage0 + stage * L.stage_bytes;
@@ -651,7 +757,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         if (plan.conj) {
           for (uint32_t l = 0; l < plan.nleaves; l++) {
             LeafCtx x;
-            leaf_ctx(x, plan, a, st, base, L, l);
+            leaf_ctx<true>(x, plan, a, st, base, L, l);
             uint32_t m = 0;
             if (!x.c.absent && !x.c.vw && x.lkind != LK_IS_NULL && x.lkind != LK_IS_NOT_NULL) {   // no NULLs in this slab: plain comparison
 #pragma unroll
@@ -672,7 +778,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             const DevPredOp op = plan.pred[i];
             if (op.kind == PK_LEAF) {
               LeafCtx x;
-              leaf_ctx(x, plan, a, st, base, L, op.arg);
+              leaf_ctx<true>(x, plan, a, st, base, L, op.arg);
               Tri32 v{0u, 0u};
 #pragma unroll
               for (int j = 0; j < KR; j++)
@@ -696,7 +802,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
       for (uint32_t k = 0; k < plan.nkeys; k++) {
         const DevKey& key = plan.keys[k];
         ColCtx c;
-        col_ctx(c, st, base, L, key.col, a.flat);
+        col_ctx<true>(c, st, base, L, key.col, a.flat);
         const uint32_t stride = key.stride, nullslot = key.card * key.stride;
         const bool nullable = c.absent || c.vw != nullptr;
         if (key.kind == KK_BOOL) {
@@ -713,7 +819,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
           // footer statistics), so one double multiply and a fix-up replace a 64-bit division
           const bool plain = c.fkind == FK_PLAIN8;
           const uint64_t* __restrict__ dict = reinterpret_cast<const uint64_t*>(a.flat + st.col[key.col].dict8);
-          const uint64_t* v8 = reinterpret_cast<const uint64_t*>(c.colw);
+          const uint64_t* v8 = c.v8;
           const double inv = 1.0 / double(key.bin_width);
           const long long w = key.bin_width, b0 = key.bin_base;
 #pragma unroll
@@ -763,7 +869,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         const DevAgg& ag = plan.aggs[g];
         if (ag.fn == AG_COUNT_STAR) continue;
         ColCtx c;
-        col_ctx(c, st, base, L, ag.col, a.flat);
+        col_ctx<true>(c, st, base, L, ag.col, a.flat);
         if (c.absent) continue;
         uint32_t vsel = sel;   // selected rows whose input is not NULL
         if (c.vw) {
@@ -783,7 +889,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         if (ag.fn == AG_COUNT) continue;
         const bool plain = c.fkind == FK_PLAIN8;
         const uint64_t* __restrict__ dict = reinterpret_cast<const uint64_t*>(a.flat + st.col[ag.col].dict8);
-        const uint64_t* v8 = reinterpret_cast<const uint64_t*>(c.colw);
+        const uint64_t* v8 = c.v8;
         unsigned long long* scell = sacc + size_t(1 + ag.acc_slot) * Hs;
         unsigned long long* gcell = gadj + size_t(1 + ag.acc_slot) * nslots;
         const bool f64 = ag.kind == DK_F64;
