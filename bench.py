@@ -561,7 +561,9 @@ def main():
 
     def roof(kernel, kernel_ms, bytes_, traffic_key):
         ach = bytes_ / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(traffic_key),
+        # the ncu capture was taken at the default size: no figure for other table sizes
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(traffic_key) if args.row_groups == RGS_PER_GPU else None,
                 "kernel": kernel, "kernel_ms": kernel_ms, "algorithmic_bytes": bytes_, "peak_kind": peak_kind}
 
     if c2 is not None:

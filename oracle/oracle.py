@@ -156,6 +156,11 @@ class Oracle:
                 L.or_cmp_str(_ptr(c.offsets), _ptr(c.data), _ptr(c.valid), C.c_int64(n), op, s, len(s), _ptr(T), _ptr(N))
             elif c.kind == "f64":
                 L.or_cmp_f64(_ptr(c.values), _ptr(c.valid), C.c_int64(n), op, C.c_double(float(v)), _ptr(T), _ptr(N))
+            elif c.kind == "i64" and isinstance(v, float) and not (v == v and float(v).is_integer() and -2.0 ** 63 <= v < 2.0 ** 63):
+                # Int64 column vs a Float64 literal that is no integer: DataFusion's comparison coercion casts the COLUMN
+                # to Float64 (datafusion-expr type_coercion/binary: Int64 x Float64 -> Float64) and compares in totalOrder
+                vals = np.ascontiguousarray(c.values.astype(np.float64))
+                L.or_cmp_f64(_ptr(vals), _ptr(c.valid), C.c_int64(n), op, C.c_double(v), _ptr(T), _ptr(N))
             else:
                 L.or_cmp_i64(_ptr(c.values), _ptr(c.valid), C.c_int64(n), op, C.c_int64(int(v)), _ptr(T), _ptr(N))
             return T, N

@@ -192,6 +192,7 @@ struct DevPlan {
   uint32_t lane_slots;         // flat aggregate kernel: the first lane_slots (hottest) group slots own one shared-memory cell per lane
   uint32_t flat_krows;         // flat aggregate kernel: rows per consumer thread per slab
   uint32_t direct8;            // flat aggregate kernel: 8-byte values are read in place from the flat store, not staged
+  uint32_t dbg;                // measurement switches: bit 0 / 1 = k_flat_filter / k_flat_agg consumers hand every stage back untouched (PQB_FILTER_NOWORK, PQB_AGG_NOWORK: the supply-side limit)
   uint32_t flat_slab_rows;     // rows per slab of the flat kernels
   uint32_t no_flat;            // 1: the flat kernels do not run (NULL literal in the predicate, PQB_FLAT_SCAN=0): k_scan takes every item
   uint32_t replicas;           // accumulator table copies in global memory; CTA b adds into copy b % replicas (merged by k_acc_reduce)

@@ -46,7 +46,10 @@ constexpr int kFilterConsumerWarps = 4;
 #ifndef PQB_FILTER_ILP
 #define PQB_FILTER_ILP 1   // 0: the serial funnel chain / one survivor per trip (A/B builds: make EXTRA=-DPQB_FILTER_ILP=0)
 #endif
-constexpr int kFilterWords = 2;                                    // 32-row bitmap words per consumer thread per slab
+#ifndef PQB_FILTER_WORDS
+#define PQB_FILTER_WORDS 2
+#endif
+constexpr int kFilterWords = PQB_FILTER_WORDS;                     // 32-row bitmap words per consumer thread per slab
 constexpr int kFilterThreads = 32 * (kFilterConsumerWarps + 1);
 constexpr int kFilterSlabRows = 32 * 32 * kFilterWords;   // 2048: one WARP's slab (k_flat_filter's stages are taken warp by warp)
 constexpr int kAggThreads = 1024;
@@ -581,7 +584,7 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
       inr[h] = row0 >= R ? 0u : (R - row0 >= 32 ? 0xffffffffu : ((1u << (R - row0)) - 1u));
       m[h] = inr[h];
     }
-    if (plan.npred) {
+    if (plan.npred && !(plan.dbg & 1u)) {
       if (CONJ) {
         // conjunction: a row passes when every leaf is TRUE (a NULL leaf drops it).  First leaf on every row,
         // the others on the survivors only (or dense when many survive)
@@ -597,10 +600,11 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
 #if PQB_FILTER_ROLL
           // ONE copy of the leaf code for both words (the loop is not unrolled; the word in hand rotates through
           // registers): half the instruction-cache footprint of the hot path
-          uint32_t ma = m[0], mb = m[1], ia = inr[0], ib = inr[1], wa = word[0];
 #pragma unroll 1
           for (int h = 0; h < kFilterWords; h++) {
-            const uint32_t V = ia ? col_valid32(x.c, wa * 32) : 0u;
+            const uint32_t wa = h * 32 + lane;
+            uint32_t ma = m[0];
+            const uint32_t V = wa * 32 < R ? col_valid32(x.c, wa * 32) : 0u;
             if (x.lkind == LK_IS_NULL) ma &= ~V;
             else {
               ma &= V;
@@ -609,11 +613,10 @@ k_flat_filter(const __grid_constant__ DevPlan plan, const __grid_constant__ Flat
                 else ma = leaf_survivors(x, wa * 32, ma);
               }
             }
-            uint32_t t = ma; ma = mb; mb = t;
-            t = ia; ia = ib; ib = t;
-            wa ^= word[0] ^ word[1];
+#pragma unroll
+            for (int k = 0; k + 1 < kFilterWords; k++) m[k] = m[k + 1];   // rotate: after kFilterWords trips every word is back in its place
+            m[kFilterWords - 1] = ma;
           }
-          m[0] = ma; m[1] = mb;
 #else
 #pragma unroll
           for (int h = 0; h < kFilterWords; h++) {
@@ -686,22 +689,30 @@ constexpr int kAggRowsMax = 8;   // k_flat_agg<KR>: KR = 8, 4, 2 rows per thread
 
 // shared-memory cells are 8 bytes like the global ones; per-CTA partial counts and the low words of
 // partial sums are updated with native 32-bit atomics
-__device__ __forceinline__ void cell_add_u64(unsigned long long* cell, bool hot, unsigned long long v) {
+// `s` / `g`: the cell in the shared-memory table / in the global one, `hot` says which is meant.  Two pointers so
+// that each atomic is compiled for its address space (a pointer chosen at run time makes them generic: an address-space
+// test in front of every update, returning ATOM.E instead of RED for the cold cells).
+__device__ __forceinline__ void cell_add_u64(unsigned long long* s, unsigned long long* g, bool hot, unsigned long long v) {
   if (hot) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(cell);
+    uint32_t* w = reinterpret_cast<uint32_t*>(s);
     const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
     uint32_t carry = 0;
     if (lo) carry = uint32_t(atomicAdd(&w[0], lo) + lo) < lo ? 1u : 0u;
     if (hi + carry) atomicAdd(&w[1], hi + carry);
-  } else atomicAdd(cell, v);
+  } else atomicAdd(g, v);
 }
-__device__ __forceinline__ void cell_min_max(unsigned long long* cell, bool hot, bool is_min, long long k) {
+__device__ __forceinline__ void cell_add_f64(unsigned long long* s, unsigned long long* g, bool hot, double v) {
+  if (hot) atomicAdd(reinterpret_cast<double*>(s), v);   // no native shared-memory f64 add: a CAS loop
+  else atomicAdd(reinterpret_cast<double*>(g), v);
+}
+__device__ __forceinline__ void cell_min_max(unsigned long long* s, unsigned long long* g, bool hot, bool is_min, long long k) {
   if (hot) {   // 64-bit min / max in shared memory are CAS loops: skip when the row cannot improve the cell
-    const long long cur = *reinterpret_cast<volatile long long*>(cell);
+    const long long cur = *reinterpret_cast<volatile long long*>(s);
     if (is_min ? k >= cur : k <= cur) return;
-  }
-  if (is_min) atomicMin(reinterpret_cast<long long*>(cell), k);
-  else atomicMax(reinterpret_cast<long long*>(cell), k);
+    if (is_min) atomicMin(reinterpret_cast<long long*>(s), k);
+    else atomicMax(reinterpret_cast<long long*>(s), k);
+  } else if (is_min) atomicMin(reinterpret_cast<long long*>(g), k);
+  else atomicMax(reinterpret_cast<long long*>(g), k);
 }
 
 // Cell index of a group slot inside the hot table.  The plan.lane_slots hottest groups (slots 0 .. T-1: the
@@ -753,6 +764,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
       uint32_t sel = 0;
 #pragma unroll
       for (int i = 0; i < KR; i++) sel |= (tc + i * kAggConsumers < R ? 1u : 0u) << i;
+      if (plan.dbg & 2u) sel = 0;   // PQB_AGG_NOWORK: every slab handed back untouched (what producer + TMA can supply)
       if (plan.npred && sel) {
         if (plan.conj) {
           for (uint32_t l = 0; l < plan.nleaves; l++) {
@@ -909,21 +921,20 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         if (fn == AG_SUM && !f64) {   // wrapping, like DataFusion's SUM(Int64)
 #pragma unroll
           for (int i = 0; i < KR; i++)
-            if ((vsel >> i) & 1u) cell_add_u64(slot[i] < Hc ? scell + slot[i] : gcell + slot[i], slot[i] < Hc, bits[i]);
+            if ((vsel >> i) & 1u) cell_add_u64(scell + slot[i], gcell + slot[i], slot[i] < Hc, bits[i]);
         } else if (fn == AG_SUM || fn == AG_AVG) {
 #pragma unroll
           for (int i = 0; i < KR; i++)
             if ((vsel >> i) & 1u) {
               const double v = (f64 || fn == AG_SUM) ? __longlong_as_double((long long)bits[i]) : double((long long)bits[i]);
-              atomicAdd(reinterpret_cast<double*>(slot[i] < Hc ? scell + slot[i] : gcell + slot[i]), v);
+              cell_add_f64(scell + slot[i], gcell + slot[i], slot[i] < Hc, v);
             }
         } else {
           const bool is_min = fn == AG_MIN;
 #pragma unroll
           for (int i = 0; i < KR; i++)
             if ((vsel >> i) & 1u)
-              cell_min_max(slot[i] < Hc ? scell + slot[i] : gcell + slot[i], slot[i] < Hc, is_min,
-                           f64 ? (long long)f64_order_key(bits[i]) : (long long)bits[i]);
+              cell_min_max(scell + slot[i], gcell + slot[i], slot[i] < Hc, is_min, f64 ? (long long)f64_order_key(bits[i]) : (long long)bits[i]);
         }
       }
       const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(sel));

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <set>
 
@@ -564,9 +565,35 @@ void Query::run(const PqQueryDesc& d) {
             switch (kind) {
               case DK_I64:
                 if (op.lit.type == PQ_T_I64 || op.lit.type == PQ_T_TS_MS) lf.d.lit_i64 = op.lit.i64;
-                else if (op.lit.type == PQ_T_F64 && std::nearbyint(op.lit.f64) == op.lit.f64 && std::fabs(op.lit.f64) < 9.2e18)
+                else if (op.lit.type == PQ_T_F64 && std::nearbyint(op.lit.f64) == op.lit.f64 && op.lit.f64 >= -9223372036854775808.0 && op.lit.f64 < 9223372036854775808.0)
                   lf.d.lit_i64 = int64_t(op.lit.f64);
-                else throw Error(PQ_ERR_UNSUPPORTED, "Int64 column compared with a non-integer literal");
+                else if (op.lit.type == PQ_T_F64) {
+                  // DataFusion coerces the COLUMN to Float64 and compares there.  Against a literal that is no int64 this
+                  // has an exact integer restatement (a non-integer double is < 2^52 in magnitude, where the cast of
+                  // any int64 at or beyond it cannot cross it):  v > 100.5  <=>  v > 100,  v < 100.5  <=>  v < 101,
+                  // v = 100.5 never, v != 100.5 always (for non-NULL v).  NaN is the greatest value (totalOrder).
+                  const double L = op.lit.f64;
+                  const int64_t kMin = std::numeric_limits<int64_t>::min();
+                  auto never = [&] { lf.d.cmp = PQ_LT; lf.d.lit_i64 = kMin; };    // v < INT64_MIN
+                  auto always = [&] { lf.d.cmp = PQ_GE; lf.d.lit_i64 = kMin; };   // v >= INT64_MIN
+                  const bool above = std::isnan(L) || L >= 9223372036854775808.0;   // greater than every int64
+                  const bool below = L < -9223372036854775808.0;                     // less than every int64
+                  if (above || below) {
+                    const bool lt = op.cmp == PQ_LT || op.cmp == PQ_LE, gt = op.cmp == PQ_GT || op.cmp == PQ_GE;
+                    if (op.cmp == PQ_EQ) never();
+                    else if (op.cmp == PQ_NE) always();
+                    else if ((above && lt) || (below && gt)) always();
+                    else never();
+                  } else {
+                    const int64_t fl = int64_t(std::floor(L)), ce = fl + 1;   // |L| < 2^52
+                    switch (op.cmp) {
+                      case PQ_EQ: never(); break;
+                      case PQ_NE: always(); break;
+                      case PQ_GT: case PQ_GE: lf.d.cmp = PQ_GT; lf.d.lit_i64 = fl; break;
+                      default: lf.d.cmp = PQ_LT; lf.d.lit_i64 = ce; break;   // PQ_LT, PQ_LE
+                    }
+                  }
+                } else throw Error(PQ_ERR_INVALID_ARG, "Int64 column compared with a non-numeric literal");
                 break;
               case DK_F64:
                 if (op.lit.type == PQ_T_F64) lf.d.lit_i64 = int64_t(f64_bits(op.lit.f64));
@@ -1042,6 +1069,7 @@ void Query::run(const PqQueryDesc& d) {
     FL.meta0 = align_up(uint32_t(sizeof(FlatCtl)), 16);
     FL.meta_stride = meta_stride;
     plan.direct8 = 0;
+    plan.dbg = (getenv("PQB_FILTER_NOWORK") ? 1u : 0u) | (getenv("PQB_AGG_NOWORK") ? 2u : 0u);   // measurement: how fast can the producer + TMA feed the consumers?
     if (agg_kernel) plan.direct8 = 1;   // k_flat_agg reads 8-byte values in place (measured: 4 % faster than staging them, and room for twice the rows per slab)
     auto stage_bytes_for = [&](uint32_t S) {
       uint32_t off = 0;
@@ -1079,6 +1107,8 @@ void Query::run(const PqQueryDesc& d) {
       // one CTA per SM: the hot part of the accumulator table next to the stages
       const uint64_t full = uint64_t(plan.nslots) * cells * 8;
       uint32_t krows = 8;
+      if (const char* e = getenv("PQB_AGG_KROWS")) krows = std::max(1, std::min(8, atoi(e)));   // experiment switch
+      while (krows & (krows - 1)) krows &= krows - 1;
       while (krows > 1 && 2 * stage_bytes_for(kAggConsumers * krows) + std::min<uint64_t>(full, 96 * 1024) > avail) krows >>= 1;
       const uint32_t S = kAggConsumers * krows;
       FL.stage_bytes = stage_bytes_for(S);
@@ -1086,6 +1116,10 @@ void Query::run(const PqQueryDesc& d) {
       FL.nstages = 2;
       uint32_t left = avail - 2 * FL.stage_bytes;
       if (full + FL.stage_bytes <= left && FL.nstages < (uint32_t)kFlatStagesMax) { FL.nstages = 3; left -= FL.stage_bytes; }
+      if (const char* e = getenv("PQB_AGG_STAGES")) {   // experiment switch: a deeper ring at the price of hot slots
+        const uint32_t want = uint32_t(std::max(2, std::min(int(kFlatStagesMax), atoi(e))));
+        while (FL.nstages < want && left >= FL.stage_bytes + meta_stride + 64 * cells * 8) { FL.nstages++; left -= FL.stage_bytes + meta_stride; }
+      }
       // the hottest groups own a cell per lane (no same-address lanes inside a warp): 31 more cells each
       const uint32_t cap = left / (cells * 8);
       uint32_t T = 8;

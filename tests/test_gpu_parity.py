@@ -55,6 +55,10 @@ FILTERS = {
     "c2_level_and_latency": [(col("level") == "ERROR") & (col("latency_ms") > 100)],
     "c1_status_eq": [col("status") == 200],
     "f64_vs_int_literal": [col("duration_s") >= 1],
+    "i64_vs_fraction_gt": [col("latency_ms") > 100.5],               # the column is cast to Float64 (DataFusion): v > 100.5 <=> v > 100
+    "i64_vs_fraction_le_ne": [(col("latency_ms") <= 99.5) & (col("bytes") != 7.5)],
+    "i64_vs_fraction_eq_or": [(col("status") == 200.5) | (col("latency_ms") >= 1e19) | (col("bytes") < -0.5) | (col("status") > float("nan"))],   # all never true
+    "i64_vs_nan_lt": [(col("status") < float("nan")) & (col("latency_ms") < 3.25)],
     "or_mixed": [(col("level") == "FATAL") | (col("bytes") < 1000)],
     "not": [~(col("level") == "INFO")],
     "not_or": [~((col("status") == 200) | (col("cpu") >= 0.25))],
