@@ -25,18 +25,41 @@ struct DecompJob {
   uint32_t _pad;
 };
 
-// literal run: `len` bytes that do not overlap.  Eight independent byte loads per lane and trip: the copy is latency
-// bound (a page of incompressible bit-packed indices or PLAIN doubles is one long literal run)
+// literal run: `len` bytes that do not overlap, any alignment of source and destination.  A page of incompressible
+// bit-packed indices or PLAIN doubles is ONE literal run of 40-160 KB handled by one warp, so the copy must keep many
+// bytes in flight: the destination is walked in aligned 16-byte chunks, every lane builds its chunk from five aligned
+// source words with a funnel shift (the source sits at an arbitrary byte phase), four chunks per lane and trip.
 __device__ __forceinline__ void warp_literal_copy(uint8_t* __restrict__ d, const uint8_t* __restrict__ s, uint32_t len, uint32_t lane) {
-  uint32_t i = lane;
-  for (; i + 7 * 32 < len; i += 8 * 32) {
-    uint8_t b[8];
+  uint32_t head = uint32_t(-reinterpret_cast<uintptr_t>(d)) & 15u;   // bytes until d is 16-byte aligned
+  if (head > len) head = len;
+  if (lane < head) d[lane] = s[lane];
+  d += head; s += head; len -= head;
+  const uint32_t n16 = len >> 4;
+  if (n16) {
+    const uint32_t sh = (uint32_t(reinterpret_cast<uintptr_t>(s)) & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(s) & ~uintptr_t(3));
+    uint4* dw = reinterpret_cast<uint4*>(d);
+    uint32_t c = lane;
+    for (; c + 3 * 32 < n16; c += 4 * 32) {
+      uint32_t w[4][5];
 #pragma unroll
-    for (int k = 0; k < 8; k++) b[k] = s[i + k * 32];
+      for (int k = 0; k < 4; k++)
 #pragma unroll
-    for (int k = 0; k < 8; k++) d[i + k * 32] = b[k];
+        for (int j = 0; j < 5; j++) w[k][j] = (j < 4 || sh) ? sw[(c + k * 32) * 4 + j] : 0u;   // the fifth word only when the phase needs it (it may lie past the source)
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        dw[c + k * 32] = make_uint4(__funnelshift_r(w[k][0], w[k][1], sh), __funnelshift_r(w[k][1], w[k][2], sh),
+                                    __funnelshift_r(w[k][2], w[k][3], sh), __funnelshift_r(w[k][3], w[k][4], sh));
+    }
+    for (; c < n16; c += 32) {
+      uint32_t w[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) w[j] = (j < 4 || sh) ? sw[c * 4 + j] : 0u;
+      dw[c] = make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh), __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
+    }
   }
-  for (; i < len; i += 32) d[i] = s[i];
+  const uint32_t done = n16 << 4;
+  if (done + lane < len) d[done + lane] = s[done + lane];   // < 16 bytes left
 }
 
 // match copy with LZ77 overlap semantics: the source pattern [dp-off, dp) already exists, bytes

@@ -314,7 +314,7 @@ __device__ __forceinline__ void leaf_ctx(LeafCtx& x, const DevPlan& plan, const 
   else if (sc.fkind == FK_BYTES) { x.mode = LM_BYTES; x.lut = a.arena + sc.dict8; }
   else if (sc.fkind == FK_INDEX) {
     if ((st.regmask >> l) & 1u) x.mode = LM_REGLUT;
-    else if (sc.bw == 0) x.mode = x.lut[0] ? LM_TRUE : LM_FALSE;   // one-entry dictionary: no bits at all
+    else if (sc.bw == 0) x.mode = __ldg(x.lut) ? LM_TRUE : LM_FALSE;   // one-entry dictionary: no bits at all
     else x.mode = LM_MEMLUT;
   } else x.mode = sc.fkind == FK_PLAIN8 ? LM_PLAIN8 : LM_BITS;
 }
@@ -330,7 +330,7 @@ __device__ __forceinline__ bool leaf_row(const LeafCtx& x, uint32_t row) {
     case LM_FALSE: return false;
     case LM_TRUE: return true;
     case LM_REGLUT: return (__funnelshift_r(x.lutreg, x.lutreg, bits32_at(x.c.colw, x.c.phase + row * x.c.bw)) & 1u) != 0;
-    case LM_MEMLUT: return x.lut[col_index(x.c, row)] != 0;
+    case LM_MEMLUT: return __ldg(x.lut + col_index(x.c, row)) != 0;
     case LM_PLAIN8: return plain_cmp(x.c.v8[row], x);
     case LM_BYTES: {
       // the string itself (no dictionary to answer for it): arrow-ord / arrow-string semantics on the raw bytes
@@ -372,7 +372,7 @@ __device__ __forceinline__ uint32_t leaf_survivors(const LeafCtx& x, uint32_t ro
       uint32_t v0 = bits32_at(x.c.colw, bit0 + k0 * x.c.bw) & x.c.mask, v1 = bits32_at(x.c.colw, bit0 + k1 * x.c.bw) & x.c.mask;
       v0 = v0 < x.c.dict_max ? v0 : x.c.dict_max;
       v1 = v1 < x.c.dict_max ? v1 : x.c.dict_max;
-      const uint32_t t0 = x.lut[v0], t1 = x.lut[v1];
+      const uint32_t t0 = __ldg(x.lut + v0), t1 = __ldg(x.lut + v1);   // the LUTs, dictionaries and id tables are global and read-only: LDG, not a generic load
       m &= ~((t0 ? 0u : 1u) << k0);
       m &= ~((t1 ? 0u : 1u) << k1);   // k1 == k0 when there was only one: same answer twice
     }
@@ -382,7 +382,7 @@ __device__ __forceinline__ uint32_t leaf_survivors(const LeafCtx& x, uint32_t ro
       mm &= mm - 1;
       uint32_t v = bits32_at(x.c.colw, bit0 + k * x.c.bw) & x.c.mask;
       v = v < x.c.dict_max ? v : x.c.dict_max;
-      if (!x.lut[v]) m ^= 1u << k;
+      if (!__ldg(x.lut + v)) m ^= 1u << k;
     }
 #endif
     return m;
@@ -419,7 +419,7 @@ __device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w
     else {
       v &= mask;
       v = v < dict_max ? v : dict_max;
-      t = lut[v];
+      t = __ldg(lut + v);
     }
     q[k >> 3] = __funnelshift_r(q[k >> 3], t, 1);
   }
@@ -436,7 +436,7 @@ __device__ __forceinline__ uint32_t leaf_dense_bw(const uint32_t* __restrict__ w
     else {
       v &= mask;
       v = v < dict_max ? v : dict_max;
-      t = lut[v];
+      t = __ldg(lut + v);
     }
     m = __funnelshift_r(m, t, 1);                          // shift the answer in from the top: after 32 steps bit k = value k
   }
@@ -500,7 +500,7 @@ __device__ __forceinline__ uint32_t leaf_dense(const LeafCtx& x, uint32_t tc, ui
         for (int k = 0; k < 32; k++, bit += x.c.bw) {
           uint32_t v = bits32_at(x.c.colw, bit) & x.c.mask;
           v = v < x.c.dict_max ? v : x.c.dict_max;
-          m = __funnelshift_r(m, uint32_t(x.lut[v]), 1);
+          m = __funnelshift_r(m, uint32_t(__ldg(x.lut + v)), 1);
         }
       }
       return m;
@@ -839,7 +839,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             if ((sel >> i) & 1u) {
               const uint32_t r = tc + i * kAggConsumers;
               if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
-              const long long x = (long long)(plain ? v8[r] : dict[col_index(c, r)]) - b0;
+              const long long x = (long long)__ldg(plain ? v8 + r : dict + col_index(c, r)) - b0;
               long long q = (long long)(double(x) * inv);
               long long rem = x - q * w;
               if (rem < 0) { q--; rem += w; }
@@ -852,7 +852,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
           if (!nullable) {   // the loads of all rows in flight together
             uint32_t g[KR];
 #pragma unroll
-            for (int i = 0; i < KR; i++) g[i] = ((sel >> i) & 1u) ? gid[col_index(c, tc + i * kAggConsumers)] : 0u;
+            for (int i = 0; i < KR; i++) g[i] = ((sel >> i) & 1u) ? __ldg(gid + col_index(c, tc + i * kAggConsumers)) : 0u;
 #pragma unroll
             for (int i = 0; i < KR; i++) slot[i] += g[i] * stride;
           } else {
@@ -861,7 +861,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
               if ((sel >> i) & 1u) {
                 const uint32_t r = tc + i * kAggConsumers;
                 if (!col_valid(c, r)) { slot[i] += nullslot; continue; }
-                slot[i] += gid[col_index(c, r)] * stride;
+                slot[i] += __ldg(gid + col_index(c, r)) * stride;
               }
           }
         }
@@ -913,10 +913,10 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         uint64_t bits[KR];
         if (plain) {
 #pragma unroll
-          for (int i = 0; i < KR; i++) bits[i] = ((vsel >> i) & 1u) ? v8[tc + i * kAggConsumers] : 0ull;
+          for (int i = 0; i < KR; i++) bits[i] = ((vsel >> i) & 1u) ? __ldg(v8 + tc + i * kAggConsumers) : 0ull;   // in place in the flat store (global)
         } else {
 #pragma unroll
-          for (int i = 0; i < KR; i++) bits[i] = ((vsel >> i) & 1u) ? dict[col_index(c, tc + i * kAggConsumers)] : 0ull;
+          for (int i = 0; i < KR; i++) bits[i] = ((vsel >> i) & 1u) ? __ldg(dict + col_index(c, tc + i * kAggConsumers)) : 0ull;
         }
         if (fn == AG_SUM && !f64) {   // wrapping, like DataFusion's SUM(Int64)
 #pragma unroll

@@ -852,9 +852,20 @@ void Query::run(const PqQueryDesc& d) {
   if (allreduce && !comm_active()) throw Error(PQ_ERR_INVALID_ARG, "PQ_QUERY_ALLREDUCE without pq_comm_init_rank");
   const bool multi = agg_kernel && allreduce && comm_nranks() > 1;
   // an aggregated column whose footers promise null_count == 0 in every row group read: its non-null
-  // counter equals the group's row count, so the scan skips that atomic.  Decided per rank from local
-  // footers: under PQ_QUERY_ALLREDUCE the cells are summed across ranks and every rank must make the
-  // same choice, so the shortcut is off there.
+  // counter equals the group's row count, so the scan skips that atomic (and the table is 4 cells per group
+  // narrower on C4).  Under PQ_QUERY_ALLREDUCE the cells are summed across ranks and every rank must make the same
+  // choice: the per-rank footer verdicts are summed over the ranks first (one tiny all-reduce; a rank whose row
+  // groups were all pruned contributes zeros).
+  if (multi && ncols) {
+    std::vector<unsigned long long> f(ncols);
+    for (uint32_t s = 0; s < ncols; s++) f[s] = col_has_nulls[s] ? 1ull : 0ull;
+    DevBuf<unsigned long long> df;
+    df.upload(f, stream);
+    comm_allreduce_u64(df.p, ncols, 0 /*sum*/, stream);
+    PQB_CUDA(cudaMemcpyAsync(f.data(), df.p, ncols * 8, cudaMemcpyDeviceToHost, stream));
+    PQB_CUDA(cudaStreamSynchronize(stream));
+    for (uint32_t s = 0; s < ncols; s++) col_has_nulls[s] = f[s] != 0;
+  }
   std::vector<uint8_t> nn_is_rows(kMaxAggs, 0);
   {
     std::map<int, int> nn_of_col;   // one non-null counter array per aggregated column that may hold NULLs
@@ -862,7 +873,7 @@ void Query::run(const PqQueryDesc& d) {
       DevAgg& ag = plan.aggs[a];
       if (ag.fn == AG_COUNT_STAR) continue;
       ag.update_nn = 0;
-      if (!col_has_nulls[ag.col] && !allreduce) { nn_is_rows[a] = 1; continue; }
+      if (!col_has_nulls[ag.col]) { nn_is_rows[a] = 1; continue; }
       auto it = nn_of_col.find(int(ag.col));
       if (it == nn_of_col.end()) { it = nn_of_col.emplace(int(ag.col), int(nn_of_col.size())).first; ag.update_nn = 1; }
       ag.nn_slot = uint8_t(it->second);

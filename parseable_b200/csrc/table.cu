@@ -434,6 +434,8 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   };
   struct Copy { uint32_t file; uint64_t src_off; uint64_t dst_off; uint64_t bytes; };
   std::vector<Copy> copies, ccopies;   // -> arena, -> compressed staging buffer
+  struct PlainChunk { uint32_t file, rg, col; uint64_t file_off; };
+  std::vector<PlainChunk> plain_chunks;   // uncompressed chunks waiting for their place in the arena
   std::vector<DecompJob> djobs;
   uint64_t comp = 0;
   uint64_t arena = 0;
@@ -556,10 +558,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
           jobs.push_back(std::move(wj));
           continue;
         }
-        // same 16-byte phase as the source bytes: the gather kernel moves whole 16-byte vectors
-        tc.arena_off = arena + ((uintptr_t(hf.data) + tc.file_off) & 15);
-        arena = (tc.arena_off + tc.bytes + 64 + 255) & ~255ull;
-        copies.push_back({fi, tc.file_off, tc.arena_off, tc.bytes});
+        plain_chunks.push_back({fi, uint32_t(row_groups.size()), uint32_t(c), tc.file_off});   // placed below, in file order
         jobs.push_back({uint32_t(row_groups.size()), uint32_t(c), fi, {}, false});
       }
       total_rows += trg.num_rows;
@@ -568,6 +567,36 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   }
   for (size_t c = 0; c < columns.size(); c++)
     if (columns[c].kind == 0xff) columns[c].kind = 0xfe;  // present in no file: all NULL everywhere
+
+  // ---- arena places of the uncompressed chunks: in FILE order, neighbours that are close in the file keep their
+  // distance, so that one copy moves the whole span (and the unreferenced bytes in a small gap): a query over most
+  // columns uploads a file in one DMA transfer (53.9 GB/s measured on this box against 47 GB/s for the gather
+  // kernel's SM-issued reads); a span starts 256-byte aligned at the 16-byte phase of its source ----
+  {
+    std::sort(plain_chunks.begin(), plain_chunks.end(), [](const PlainChunk& a, const PlainChunk& b) {
+      return a.file != b.file ? a.file < b.file : a.file_off < b.file_off;
+    });
+    const uint64_t kGap = 128u << 10;
+    uint64_t span_src = 0, span_dst = 0, span_end = 0;   // of the open span (source offsets inside its file)
+    uint32_t span_file = ~0u;
+    auto close_span = [&]() {
+      if (span_file == ~0u) return;
+      copies.push_back({span_file, span_src, span_dst, span_end - span_src});
+      arena = (span_dst + (span_end - span_src) + 64 + 255) & ~255ull;
+    };
+    for (const PlainChunk& pc : plain_chunks) {
+      TableChunk& tc = row_groups[pc.rg].chunks[pc.col];
+      if (pc.file != span_file || (tc.file_off > span_end && tc.file_off - span_end > kGap)) {
+        close_span();
+        span_file = pc.file;
+        span_src = span_end = tc.file_off;
+        span_dst = arena + ((uintptr_t(files[pc.file]->data) + tc.file_off) & 15);
+      }
+      tc.arena_off = span_dst + (tc.file_off - span_src);
+      span_end = std::max(span_end, tc.file_off + tc.bytes);
+    }
+    close_span();
+  }
 
   mark("footers parsed, chunks planned");
   // ---- one HBM arena, 64 KiB of slack so staged windows may over-read ----
@@ -592,6 +621,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   std::vector<const uint8_t*> file_dev(files.size(), nullptr);  // device-visible alias of a page-locked image
   const char* upl = getenv("PQB_UPLOAD");   // experiment switch: "memcpy" = one cudaMemcpyAsync per chunk (copy engines) instead of the gather kernel
   const bool use_gather = !(upl && upl[0] == 'm');
+  const uint64_t kDmaMin = (upl && upl[0] == 'g') ? ~0ull : (2ull << 20);   // "gather": every span through the gather kernel (A/B)
   for (size_t f = 0; f < files.size(); f++) {
     if (!file_pinned[f] || !use_gather) continue;
     void* dp = nullptr;
@@ -604,11 +634,21 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     const Copy& cp = copies[k];
     const HostFile& hf = *files[cp.file];
     if (file_pinned[cp.file]) {
-      if (file_dev[cp.file]) gathers.push_back({file_dev[cp.file] + cp.src_off, cp.dst_off, cp.bytes});
+      // long spans: the copy engines (large PCIe reads); many short ones: one gather kernel (no per-copy launch cost)
+      if (file_dev[cp.file] && cp.bytes < kDmaMin) {
+        // pieces of 128 KiB (whole 16-byte vectors of the span's phase): the grid stays thousands of CTAs whatever the span sizes
+        const uint64_t kPiece = 128u << 10;
+        for (uint64_t o = 0; o < cp.bytes; o += kPiece)
+          gathers.push_back({file_dev[cp.file] + cp.src_off + o, cp.dst_off + o, std::min<uint64_t>(kPiece, cp.bytes - o)});
+      }
       else PQB_CUDA(cudaMemcpyAsync(d_arena + cp.dst_off, hf.data + cp.src_off, cp.bytes, cudaMemcpyHostToDevice, stream));
     } else {
-      staged.push_back(cp);
-      staged_orig.push_back(k);
+      // pieces of at most 8 MiB: the staging threads below share the work copy by copy
+      const uint64_t kPiece = 8ull << 20;
+      for (uint64_t o = 0; o < cp.bytes; o += kPiece) {
+        staged.push_back({cp.file, cp.src_off + o, cp.dst_off + o, std::min<uint64_t>(kPiece, cp.bytes - o)});
+        staged_orig.push_back(k);
+      }
     }
     h2d_bytes += cp.bytes;
   }
@@ -639,7 +679,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
       size_t j = i;
       uint64_t lo = staged[i].dst_off, hi = lo;
       while (j < staged.size() && staged[j].dst_off + staged[j].bytes - lo <= kSlice &&
-             (j == i || staged_orig[j] == staged_orig[j - 1] + 1)) {
+             (j == i || staged_orig[j] - staged_orig[j - 1] <= 1)) {
         hi = staged[j].dst_off + staged[j].bytes;
         j++;
       }
