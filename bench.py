@@ -70,7 +70,7 @@ def file_jobs(n_row_groups: int):
     return jobs
 
 
-def ensure_data(n_row_groups: int, rank: int = 0, world: int = 1) -> list[str]:
+def ensure_data(n_row_groups: int, rank: int = 0, world: int = 1, all_workers: bool = False) -> list[str]:
     """Row groups [0, n_row_groups) of the seeded logs16 generator (SURVEY §8d), generated on this box;
     rank r writes the files r, r + world, ... (its own shard)."""
     os.makedirs(DATA_DIR, exist_ok=True)
@@ -78,7 +78,7 @@ def ensure_data(n_row_groups: int, rank: int = 0, world: int = 1) -> list[str]:
     mine = [j for i, j in enumerate(jobs) if i % world == rank and not os.path.exists(j[0])]
     if mine:
         import multiprocessing as mp
-        workers = max(1, min(len(mine), ((os.cpu_count() or 2) - 2) // world))
+        workers = max(1, min(len(mine), ((os.cpu_count() or 2) - 2) // (1 if all_workers else world)))
         t = time.time()
         with mp.get_context("spawn").Pool(workers) as pool:
             pool.map(_gen_one, mine, chunksize=1)
@@ -252,7 +252,7 @@ def run_reference(args, rank: int, world: int):
         return
     import pyarrow as pa
     nrg = args.row_groups * world
-    files = ensure_data(nrg)
+    files = ensure_data(nrg, 0, world, all_workers=True)  # only rank 0's files are needed (the other ranks do not run)
     shard = files[0::world]                               # rank 0's files: the same bytes the GPU arm's rank 0 scans
     cores = os.cpu_count() or 1
     pa.set_cpu_count(cores)

@@ -750,7 +750,7 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
   const uint32_t Hw = smem_warp ? Hs : 0u, Tw = smem_warp ? T : 0u;
   unsigned long long* gadj = gacc - 31u * Tw;   // indexed by cell: gadj[cell] == gacc[slot] for a cold slot
   if (warp == kAggConsumers / 32) {
-    flat_producer(plan, L, a, ctl, smem, S, 1, 2048);   // a slab takes tens of microseconds
+    flat_producer(plan, L, a, ctl, smem, S, 1, 512);
   } else {
     const uint32_t tc = threadIdx.x;
     uint32_t stage = 0, par = 0;

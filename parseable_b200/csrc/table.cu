@@ -969,15 +969,24 @@ void Table::build_flat_store(cudaStream_t stream) {
   const char* sw = getenv("PQB_FLAT");
   if ((sw && sw[0] == '0') || pages.empty()) return;   // A/B switch: everything through k_scan
   // which pages hold NULLs (their definition levels are not all 1)?
+  // A chunk whose footer promises null_count == 0 (or whose column cannot hold NULLs: no definition levels) needs no
+  // look at the data: when that settles every page, nothing below waits for the upload -- the jobs are built and the
+  // flat store is allocated while the DMA is still in flight, and the kernels queue up behind it.  (Statistics that lie
+  // make the value stream of such a page come up short: the file is refused as malformed.)
   std::vector<uint8_t> has_nulls(pages.size(), 0);
-  {
+  bool need_look = false;
+  for (const TableRowGroup& rg : row_groups)
+    for (const TableChunk& tc : rg.chunks)
+      if (tc.present && tc.meta->stats.null_count != 0)
+        for (uint32_t k = 0; k < tc.pages.n_pages && !need_look; k++) need_look = pages[tc.pages.first_page + k].def_len != 0;
+  nulls_classified = true;
+  if (need_look) {
     uint8_t* d_nf = nullptr;
     PQB_CUDA(cudaMallocAsync((void**)&d_nf, pages.size(), stream));
     launch_page_has_nulls(d_arena, d_pages, uint32_t(pages.size()), d_nf, stream);
     PQB_CUDA(cudaMemcpyAsync(has_nulls.data(), d_nf, pages.size(), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     dev_drop(d_nf, stream);
-    nulls_classified = true;
   }
   struct J { uint64_t src, off, voff, toff; uint32_t page, kind, rows, zone; };
   std::vector<J> js;
