@@ -594,6 +594,57 @@ def test_corrupt_dictionary_index_is_refused(data_dir, built):
     assert StandardTableProvider([p], schema=schema).scan(filters=[col("v") < 10], count_only=True).metrics["rows_selected"] == 10
 
 
+def test_garbled_pages_fail_cleanly(data_dir, built):
+    """Bytes flipped inside dictionary and data pages (run headers, bit widths, definition levels, PLAIN values, LZ4
+    sequences): every open either answers or returns an error code -- no fault, no hang, and the CUDA context serves the
+    next query.  (What a reader must answer for garbled VALUES is undefined; that it survives is not.)"""
+    rng = np.random.default_rng(53)
+    n = 60_000
+    t = pa.table({
+        "k": pa.array(np.array(["a", "bb", "ccc", "dddd", "e"])[rng.integers(0, 5, n)]),
+        "v": pa.array(rng.integers(0, 1 << 40, n).astype(np.int64)),
+        "d": pa.array(np.where(rng.random(n) < 0.1, None, rng.integers(0, 300, n)), pa.int64(), from_pandas=True),
+        "s": pa.array([f"msg-{i % 4000:05d}-{'x' * (i % 9)}" for i in range(n)]),
+    })
+    schema = t.schema
+    good = {}
+    for codec in ("NONE", "LZ4"):
+        p = os.path.join(data_dir, f"garble_{codec}.parquet")
+        pq.write_table(t, p, compression=codec, use_dictionary=["k", "d"], data_page_size=32 << 10, row_group_size=30_000,
+                       column_encoding={"s": "DELTA_BYTE_ARRAY"})
+        good[codec] = p
+    flt = [(col("k") == "ccc") & (col("d") > 10) & col("s").like("%-x%")]
+    keys, aggs = ["k"], [count_star(), sum_("v"), max_("d")]
+    want = Oracle(t).count(flt)
+    outcomes = {"ok": 0, "error": 0}
+    for codec, p in good.items():
+        raw = open(p, "rb").read()
+        md = pq.ParquetFile(p).metadata
+        spans = [(md.row_group(g).column(c).dictionary_page_offset or md.row_group(g).column(c).data_page_offset,
+                  md.row_group(g).column(c).total_compressed_size) for g in range(md.num_row_groups) for c in range(md.num_columns)]
+        for trial in range(24):
+            b = bytearray(raw)
+            for _ in range(int(rng.integers(1, 4))):
+                lo, ln = spans[int(rng.integers(0, len(spans)))]
+                pos = lo + int(rng.integers(0, ln))
+                b[pos] = int(rng.integers(0, 256)) if trial % 3 else (b[pos] ^ 0xFF)
+            bad = os.path.join(data_dir, f"garbled_{codec}_{trial}.parquet")
+            open(bad, "wb").write(bytes(b))
+            try:
+                prov = StandardTableProvider([bad], schema=schema)
+                prov.scan(filters=flt, count_only=True)
+                prov.aggregate(keys, aggs, [col("v") >= 0])
+                prov.scan(projection=["s", "d"], filters=[col("k") == "e"], limit=50)
+                outcomes["ok"] += 1
+            except QueryError as e:
+                assert e.code < 0
+                outcomes["error"] += 1
+            os.remove(bad)
+            # the context still answers, exactly
+            assert StandardTableProvider([p], schema=schema).scan(filters=flt, count_only=True).metrics["rows_selected"] == want, (codec, trial)
+    assert outcomes["ok"] + outcomes["error"] == 48 and outcomes["error"] > 0, outcomes
+
+
 def test_plain_byte_array_pages(data_dir, built):
     """Dictionary-fallback strings (streams.rs:584-631: dictionary on, 1 MiB limit): a `message` column whose chunk
     flips from RLE_DICTIONARY to PLAIN BYTE_ARRAY pages mid-way, a column written PLAIN from the start, NULLs in both;
