@@ -266,6 +266,32 @@ def _files_array(files: Sequence[HostFile | str]):
     return hfs, arr
 
 
+def _staging_image(batches: list) -> "HostFile":
+    """In-RAM staging record batches -> one Parquet file image (newest row first)."""
+    import io
+
+    import pyarrow.parquet as pq
+
+    from . import synth
+    rev = [b.take(pa.array(range(b.num_rows - 1, -1, -1), pa.int64())) for b in reversed(batches)]
+    t = pa.Table.from_batches(rev)
+    buf = io.BytesIO()
+    kw = synth.parseable_writer_kwargs(t.column_names, time_col=DEFAULT_TIMESTAMP_KEY)
+    pq.write_table(t, buf, row_group_size=synth.ROW_GROUP, **kw)
+    return HostFile(data=buf.getvalue())
+
+
+def field_stats(provider: "StandardTableProvider", field: str, max_field_statistics: int = 50, filters: Iterable[Expr] = ()):
+    """Field statistics of one column like the reference's per-upload job (src/storage/field_stats.rs:298-330):
+    ``GROUP BY field -> COUNT(*)`` runs on the GPU over every row; the window functions of the SQL (SUM / COUNT OVER (),
+    ROW_NUMBER() OVER (ORDER BY value_count DESC)) range over the grouped result and stay above the scan.
+    Returns (total_count, distinct_count, [(value, count), ...] for the max_field_statistics most frequent values)."""
+    t = provider.aggregate([field], [count_star()], list(filters)).table()
+    vals, cnts = t[field].to_pylist(), t["count(*)"].to_pylist()
+    order = sorted(range(len(vals)), key=lambda i: -cnts[i])          # stable: ties keep the scan's (dictionary) order
+    return sum(cnts), len(vals), [(vals[i], cnts[i]) for i in order[:max_field_statistics]]
+
+
 class DeviceTable:
     """Encoded column chunks resident in HBM (pq_table_open): the hot tier of
     src/hottier.rs, one level closer to the kernels."""
@@ -322,7 +348,22 @@ class StandardTableProvider:
     """
 
     def __init__(self, source: DeviceTable | Sequence[HostFile | str], schema: pa.Schema | dict | None = None,
-                 shard_index: int = 0, shard_count: int = 1):
+                 shard_index: int = 0, shard_count: int = 1, staging_batches: Sequence[pa.RecordBatch] = (),
+                 staging_parquet: Sequence[str] = ()):
+        # ---- get_staging_execution_plan (stream_schema_provider.rs:242-298): data still in staging ----
+        # staging Parquet files: newest first by file name, scanned like any other file; in-RAM staging batches: reversed
+        # (batch order and row order, `reversed_mem_table` :686-695) and turned into ONE in-memory Parquet image with the
+        # stream's writer properties -- the conversion Parseable itself runs when it flushes staging
+        # (streams.rs:572-631) -- so that the GPU path stays the only reader.  They come first in the file list, like
+        # the reference's plan order (staging arrow, staging parquet, then hot tier / object store).
+        extra: list = []
+        if staging_batches:
+            extra.append(_staging_image(list(staging_batches)))
+        extra += sorted(staging_parquet, reverse=True)
+        if extra:
+            if isinstance(source, DeviceTable):
+                raise QueryError(L.PQ_ERR_INVALID_ARG, "staging data joins a file list, not a resident table")
+            source = extra + list(source)
         self.source = source
         if isinstance(schema, pa.Schema):
             schema = {f.name: f.type for f in schema}

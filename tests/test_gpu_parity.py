@@ -645,6 +645,53 @@ def test_garbled_pages_fail_cleanly(data_dir, built):
     assert outcomes["ok"] + outcomes["error"] == 48 and outcomes["error"] > 0, outcomes
 
 
+def test_staging_branch_and_field_stats(data_dir, built):
+    """get_staging_execution_plan (stream_schema_provider.rs:242-298): in-RAM staging batches (reversed, as one Parquet
+    image) and staging Parquet files (newest name first) join the scan; field statistics (field_stats.rs:298-330):
+    GROUP BY + COUNT(*) on the GPU, total / distinct / top-k above it."""
+    from parseable_b200.query import field_stats
+    rng = np.random.default_rng(61)
+
+    def mk(n, t0):
+        return pa.table({"p_timestamp": pa.array((t0 - np.arange(n)).astype(np.int64), pa.timestamp("ms")),
+                         "k": pa.array(np.array(["x", "y", "z", None], dtype=object)[rng.integers(0, 4, n)], pa.string()),
+                         "v": pa.array(rng.integers(0, 1000, n).astype(np.int64))})
+    old, s1, s2 = mk(5000, 1_700_000_000_000), mk(700, 1_700_000_300_000), mk(900, 1_700_000_400_000)
+    ram = [mk(40, 1_700_000_500_000 + i * 1000).to_batches()[0] for i in range(5)]
+    paths = {}
+    for name, tab in (("old", old), ("stage-0001", s1), ("stage-0002", s2)):
+        paths[name] = os.path.join(data_dir, f"{name}.parquet")
+        pq.write_table(tab, paths[name], compression="NONE")
+    prov = StandardTableProvider([paths["old"]], schema=old.schema, staging_batches=ram,
+                                 staging_parquet=[paths["stage-0001"], paths["stage-0002"]])
+    # the reference's plan order: reversed in-RAM batches, staging files newest name first, then the rest
+    rev = pa.Table.from_batches([b.take(pa.array(range(b.num_rows - 1, -1, -1), pa.int64())) for b in reversed(ram)])
+    full = pa.concat_tables([rev, s2, s1, old])
+    ora = Oracle(full)
+    flt = [(col("v") < 300) & col("k").is_not_null()]
+    assert prov.scan(filters=flt, count_only=True).metrics["rows_selected"] == ora.count(flt)
+    got = prov.scan(projection=["p_timestamp", "k", "v"], filters=flt, row_ids=True).table()
+    exp, ids = _project_expect(ora, flt, ["p_timestamp", "k", "v"])
+    assert np.array_equal(got["__row_id"].to_numpy(), ids)
+    for c in ["p_timestamp", "k", "v"]:
+        assert got[c].to_pylist() == exp[c].to_pylist(), c
+    keys, aggs = ["k"], [count_star(), sum_("v")]
+    assert_tables_equal(prov.aggregate(keys, aggs).table(), ora.group_by(keys, aggs, []), keys)
+    # field statistics: the reference's own known answers (field_stats.rs:927-1066)
+    gold = StandardTableProvider([os.path.join(GOLD, "field_stats_10rows.parquet")],
+                                 schema={"name": pa.string(), "score": pa.float64(), "active": pa.bool_(), "created_at": pa.timestamp("ms"),
+                                         "single_value": pa.string(), "id": pa.int64()})
+    total, distinct, top = field_stats(gold, "name", 3)
+    assert (total, distinct) == (10, 7) and top[0] == ("Alice", 3) and top[1] == ("Bob", 2) and len(top) == 3
+    total, distinct, top = field_stats(gold, "single_value")
+    assert (total, distinct, top) == (10, 1, [("constant", 10)])
+    total, distinct, top = field_stats(gold, "active")
+    assert (total, distinct) == (10, 3) and top[0] == (True, 6)
+    total, distinct, top = field_stats(prov, "k", 2)
+    cnt = {k: c for k, c in zip(*[x.to_pylist() for x in ora.group_by(["k"], [count_star()], []).columns])}
+    assert total == full.num_rows and distinct == 4 and top[0][1] == max(cnt.values())
+
+
 def test_plain_byte_array_pages(data_dir, built):
     """Dictionary-fallback strings (streams.rs:584-631: dictionary on, 1 MiB limit): a `message` column whose chunk
     flips from RLE_DICTIONARY to PLAIN BYTE_ARRAY pages mid-way, a column written PLAIN from the start, NULLs in both;
