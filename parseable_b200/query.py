@@ -391,6 +391,26 @@ class StandardTableProvider:
                   batch_size: int = 0, flags: int = 0) -> QueryResult:
         return self._run(list(filters), list(group_by), list(aggs), [], None, batch_size, flags)
 
+    def count_distinct(self, group_by: Sequence[str], column: str, filters: Iterable[Expr] = ()) -> pa.Table:
+        """``SELECT keys, COUNT(DISTINCT column)`` (Parseable's alerts use it: src/alerts/alert_enums.rs:216-223).
+        The distinct values of a dictionary-encoded column are its interned ids: the GPU runs
+        ``GROUP BY keys, column -> COUNT(*)`` (every row, one pass) and the per-key number of non-NULL ``column`` groups is
+        counted over that small result above the scan.  NULLs do not count, an empty input yields 0 for the global form."""
+        t = self.aggregate(list(group_by) + [column], [count_star()], filters).table()
+        name = f"count(distinct {column})"
+        if not group_by:
+            n = sum(1 for v in t[column].to_pylist() if v is not None) if t.num_rows else 0
+            return pa.table({name: pa.array([n], pa.int64())})
+        if t.num_rows == 0:
+            return pa.table({**{k: t[k] for k in group_by}, name: pa.array([], pa.int64())})
+        seen: dict = {}
+        for row in zip(*[t[k].to_pylist() for k in group_by], t[column].to_pylist()):
+            key, v = row[:-1], row[-1]
+            seen[key] = seen.get(key, 0) + (0 if v is None else 1)
+        cols = {k: pa.array([key[i] for key in seen], t[k].type) for i, k in enumerate(group_by)}
+        cols[name] = pa.array(list(seen.values()), pa.int64())
+        return pa.table(cols)
+
     def _run(self, filters, group_by, aggs, projection, limit, batch_size, flags, poll: bool = False) -> QueryResult:
         lib = L.load()
         d = _Desc()

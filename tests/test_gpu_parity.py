@@ -687,6 +687,14 @@ def test_staging_branch_and_field_stats(data_dir, built):
     assert (total, distinct, top) == (10, 1, [("constant", 10)])
     total, distinct, top = field_stats(gold, "active")
     assert (total, distinct) == (10, 3) and top[0] == (True, 6)
+    # COUNT(DISTINCT ...) of the alerts (alert_enums.rs:216-223): distinct values are interned ids
+    cd = prov.count_distinct(["k"], "v", [col("v") < 50]).sort_by([("k", "ascending")])
+    import pyarrow.compute as pc
+    ft = full.filter(pc.less(full["v"], 50))
+    ref = ft.group_by(["k"]).aggregate([("v", "count_distinct")]).sort_by([("k", "ascending")])
+    assert cd["k"].to_pylist() == ref["k"].to_pylist() and cd["count(distinct v)"].to_pylist() == ref["v_count_distinct"].to_pylist()
+    assert prov.count_distinct([], "k").column(0).to_pylist() == [3]          # NULL does not count
+    assert prov.count_distinct([], "k", [col("v") < 0]).column(0).to_pylist() == [0]
     total, distinct, top = field_stats(prov, "k", 2)
     cnt = {k: c for k, c in zip(*[x.to_pylist() for x in ora.group_by(["k"], [count_star()], []).columns])}
     assert total == full.num_rows and distinct == 4 and top[0][1] == max(cnt.values())
