@@ -3,8 +3,9 @@
 //   DataSourceExec(Parquet) -> FilterExec -> AggregateExec(Partial)
 // (/root/reference/src/query/mod.rs:287), for the common case: every
 // referenced column of a work item has pages with a flat copy (pages with NULLs carry a validity
-// bitmap and one slot per ROW; a column missing from a file reads as all NULL).  Items that do not
-// qualify (PLAIN strings, streams the flattener refused) stay with k_scan.
+// bitmap and one slot per ROW; a column missing from a file reads as all NULL).  A file whose value
+// streams the flattener refuses is refused as corrupt at table open (PQB_FLAT_LENIENT keeps such
+// pages on k_scan for debugging).
 //
 // Shape (both kernels): persistent CTAs, one PRODUCER warp and N consumer warps.  The producer's
 // elected lane pulls work items from the queue, and for every slab of an item stages the slab's
@@ -14,16 +15,21 @@
 // stage back through its `empty` mbarrier.  No block barrier inside the loop, no run directory, no
 // header walk: value i of a page is bits [i*bw, (i+1)*bw).
 //
-// k_flat_filter: 4 consumer warps, a thread owns two words of the selection bitmap per slab (32
-//   consecutive rows each; the per-slab set-up of a leaf is paid once for both).  First leaf: all 32 indices unpacked with compile-time shifts; a dictionary of <= 32
-//   entries keeps its whole LUT in ONE REGISTER (3 instructions per row: extract, rotate, funnel).
-//   Later leaves of a conjunction run only on the surviving rows.  HBM traffic = encoded bytes once
-//   + 1 bit per row.
-// k_flat_agg: 31 consumer warps, one CTA per SM so that the hot part of the accumulator table
-//   (group slots < plan.hot_slots; group ids are numbered hot-first) lives in shared memory
-//   next to the stages; cold slots go to L2 with fire-and-forget reductions.  Rows are dealt to
-//   threads interleaved (lane L of a warp takes row base + L): PLAIN 8-byte values are read without
-//   bank conflicts and neighbouring lanes share their index words.
+// k_flat_filter<CONJ>: 4 consumer warps; a STAGE IS ONE WARP'S SLAB (2048 rows) and a consumer warp
+//   draws the next stage in fill order with a shared-memory ticket, so no warp waits for a slower one
+//   and the ring is 8-16 stages deep.  A thread owns two words of the selection bitmap per slab (32
+//   consecutive rows each), evaluated by one rolled copy of the leaf code.  First leaf: all 32 indices
+//   unpacked with compile-time shifts; a dictionary of <= 32 entries keeps its whole LUT in ONE REGISTER
+//   (3 instructions per row: extract, rotate, funnel).  Later leaves of a conjunction run only on the
+//   surviving rows.  HBM traffic = encoded bytes once + 1 bit per row.
+// k_flat_agg<KR>: 31 consumer warps, one CTA per SM so that the hot part of the accumulator table
+//   (group slots < plan.hot_slots; group ids are numbered hot-first; the very hottest own a cell per
+//   lane) lives in shared memory next to the stages; cold slots go to L2 with fire-and-forget
+//   reductions.  Rows are dealt to threads interleaved (lane L of a warp takes row base + L):
+//   neighbouring lanes share their index words, and 8-byte values are read in place from the flat
+//   store, fully coalesced.  Every pointer stays in ONE address space (a pointer that may be shared or
+//   global makes every access through it generic: that cost 20-25 % on both kernels before it was
+//   found in the SASS).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -931,10 +937,21 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             }
         } else {
           const bool is_min = fn == AG_MIN;
+          // MIN(x), MAX(x) next to each other: one pass over the values feeds both cells (the second aggregate of a
+          // column never owns the non-null counter, so nothing else of its pass is left)
+          const DevAgg& nx = plan.aggs[g + 1 < plan.naggs ? g + 1 : g];
+          const bool pair = g + 1 < plan.naggs && nx.col == ag.col && (nx.fn == AG_MIN || nx.fn == AG_MAX) && !nx.update_nn;
+          unsigned long long* scell2 = sacc + size_t(1 + nx.acc_slot) * Hs;
+          unsigned long long* gcell2 = gadj + size_t(1 + nx.acc_slot) * nslots;
+          const bool is_min2 = nx.fn == AG_MIN;
 #pragma unroll
           for (int i = 0; i < KR; i++)
-            if ((vsel >> i) & 1u)
-              cell_min_max(scell + slot[i], gcell + slot[i], slot[i] < Hc, is_min, f64 ? (long long)f64_order_key(bits[i]) : (long long)bits[i]);
+            if ((vsel >> i) & 1u) {
+              const long long k = f64 ? (long long)f64_order_key(bits[i]) : (long long)bits[i];
+              cell_min_max(scell + slot[i], gcell + slot[i], slot[i] < Hc, is_min, k);
+              if (pair) cell_min_max(scell2 + slot[i], gcell2 + slot[i], slot[i] < Hc, is_min2, k);
+            }
+          if (pair) g++;
         }
       }
       const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(sel));

@@ -99,3 +99,25 @@ def test_arrow_types_map_to_abi_types():
     assert _pq_type(pa.dictionary(pa.int32(), pa.string())) == L.PQ_T_UTF8
     assert _pq_type(pa.float64()) == L.PQ_T_F64 and _pq_type(pa.bool_()) == L.PQ_T_BOOL and _pq_type(pa.int64()) == L.PQ_T_I64
     assert _pq_type(pa.list_(pa.int64())) == L.PQ_T_NULL and _pq_type(None) == L.PQ_T_NULL
+
+
+def test_staging_batches_become_one_reversed_parquet_image():
+    """reversed_mem_table (stream_schema_provider.rs:686-695): batches newest first, rows inside a batch reversed; the
+    image is written the way the stream writes Parquet (DELTA_BINARY_PACKED time column, dictionaries elsewhere)."""
+    import io
+
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    from parseable_b200.query import _staging_image
+    batches = [pa.table({"p_timestamp": pa.array(np.arange(5) + 10 * i, pa.timestamp("ms")),
+                         "k": pa.array(["a", "b", None, "a", "c"])}).to_batches()[0] for i in range(3)]
+    hf = _staging_image(batches)
+    pf = pq.ParquetFile(io.BytesIO(hf._buf.raw[:hf.size]))
+    t = pf.read()
+    assert t["p_timestamp"].cast(pa.int64()).to_pylist() == [24, 23, 22, 21, 20, 14, 13, 12, 11, 10, 4, 3, 2, 1, 0]
+    assert t["k"].to_pylist() == ["c", "a", None, "b", "a"] * 3
+    md = pf.metadata.row_group(0)
+    encs = {md.column(i).path_in_schema: set(md.column(i).encodings) for i in range(md.num_columns)}
+    assert "DELTA_BINARY_PACKED" in encs["p_timestamp"] and "RLE_DICTIONARY" in encs["k"]
