@@ -854,17 +854,28 @@ void Query::run(const PqQueryDesc& d) {
   // an aggregated column whose footers promise null_count == 0 in every row group read: its non-null
   // counter equals the group's row count, so the scan skips that atomic (and the table is 4 cells per group
   // narrower on C4).  Under PQ_QUERY_ALLREDUCE the cells are summed across ranks and every rank must make the same
-  // choice: the per-rank footer verdicts are summed over the ranks first (one tiny all-reduce; a rank whose row
-  // groups were all pruned contributes zeros).
-  if (multi && ncols) {
-    std::vector<unsigned long long> f(ncols);
-    for (uint32_t s = 0; s < ncols; s++) f[s] = col_has_nulls[s] ? 1ull : 0ull;
+  // choice: the per-rank footer verdicts are summed over the ranks first (a rank whose row groups were all pruned
+  // contributes zeros).  The same tiny all-reduce carries whether every rank still holds the agreed numbering of the
+  // GROUP BY key values (kept with the table column, tagged with the communicator's epoch; a rank may have reopened its
+  // table): ONE collective and one round trip per query for both agreements.
+  bool keys_agreed = true;
+  if (multi) {
+    std::vector<unsigned long long> f(1 + ncols, 0ull);
+    for (uint32_t k = 0; k < d.n_group_by; k++) {
+      if (d.group_exprs && d.group_exprs[k].kind == PQ_KEY_DATE_BIN) continue;
+      const uint32_t s = uint32_t(slot_of[d.group_by[k]]);
+      if (plan.cols[s].kind == DK_BOOL) continue;
+      const ColSide& cs = table->sides[shape_cols[s]];
+      if (!cs.glob_ready || cs.glob_epoch != comm_epoch()) f[0] = 1;   // this rank lacks an agreement
+    }
+    for (uint32_t s = 0; s < ncols; s++) f[1 + s] = col_has_nulls[s] ? 1ull : 0ull;
     DevBuf<unsigned long long> df;
     df.upload(f, stream);
-    comm_allreduce_u64(df.p, ncols, 0 /*sum*/, stream);
-    PQB_CUDA(cudaMemcpyAsync(f.data(), df.p, ncols * 8, cudaMemcpyDeviceToHost, stream));
+    comm_allreduce_u64(df.p, f.size(), 0 /*sum*/, stream);
+    PQB_CUDA(cudaMemcpyAsync(f.data(), df.p, f.size() * 8, cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
-    for (uint32_t s = 0; s < ncols; s++) col_has_nulls[s] = f[s] != 0;
+    keys_agreed = f[0] == 0;
+    for (uint32_t s = 0; s < ncols; s++) col_has_nulls[s] = f[1 + s] != 0;
   }
   std::vector<uint8_t> nn_is_rows(kMaxAggs, 0);
   {
@@ -976,24 +987,8 @@ void Query::run(const PqQueryDesc& d) {
   if (multi && d.n_group_by) {
     // ---- multi-GPU: every rank must use ONE numbering of the key values.  The agreement (all-gather of the
     // packed distinct values, numbered by first occurrence in rank order: identical on every rank, and hot-first
-    // because rank 0's ids are) is kept with the table column, tagged with the communicator's epoch; one tiny
-    // all-reduce per query checks that EVERY rank still holds it (a rank may have reopened its table) ----
-    uint32_t have = 1;
-    for (uint32_t k = 0; k < d.n_group_by; k++) {
-      if (plan.keys[k].kind != KK_DICT_LUT) continue;
-      const ColSide& cs = table->sides[shape_cols[plan.keys[k].col]];
-      if (!cs.glob_ready || cs.glob_epoch != comm_epoch()) have = 0;
-    }
-    {
-      DevBuf<unsigned long long> dflag;
-      dflag.alloc(1, stream);
-      unsigned long long f = have;
-      PQB_CUDA(cudaMemcpyAsync(dflag.p, &f, 8, cudaMemcpyHostToDevice, stream));
-      comm_allreduce_u64(dflag.p, 1, 1 /*min*/, stream);
-      PQB_CUDA(cudaMemcpyAsync(&f, dflag.p, 8, cudaMemcpyDeviceToHost, stream));
-      PQB_CUDA(cudaStreamSynchronize(stream));
-      have = uint32_t(f);
-    }
+    // because rank 0's ids are) is kept with the table column; `keys_agreed` (above) says whether EVERY rank holds it ----
+    const uint32_t have = keys_agreed ? 1u : 0u;
     for (uint32_t k = 0; k < d.n_group_by; k++) {
       DevKey& key = plan.keys[k];
       if (key.kind != KK_DICT_LUT) continue;
