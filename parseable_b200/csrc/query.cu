@@ -19,6 +19,8 @@
 #include <limits>
 #include <map>
 #include <set>
+#include <string_view>
+#include <unordered_map>
 
 #include "engine.hpp"
 #include "prep_kernels.cuh"
@@ -415,7 +417,14 @@ void unify_key_side(const Table& t, int tcol, ColSide& cs, cudaStream_t stream) 
     PQB_CUDA(cudaMemcpyAsync(recvbuf.data(), drecv.p, per_rank * nr, cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
   }
-  std::map<std::string, uint32_t> ids;  // identical content + identical insertion order on every rank
+  // ids by first occurrence in rank order: identical content + identical order on every rank.  Views into the received
+  // bytes (no copies), one hash probe per value
+  std::unordered_map<std::string_view, uint32_t> ids;
+  {
+    size_t total = 0;
+    for (int r = 0; r < nr; r++) total += size_t(sizes[2 * r]);
+    ids.reserve(total);
+  }
   std::vector<uint32_t> remap(std::max<uint32_t>(card_l, 1), 0);
   KeyDict& glob = cs.glob_kd;
   glob.offs.assign(1, 0);
@@ -425,7 +434,7 @@ void unify_key_side(const Table& t, int tcol, ColSide& cs, cudaStream_t stream) 
     const uint32_t* offs = reinterpret_cast<const uint32_t*>(base);
     const uint8_t* bytes = base + 4 * (cardmax + 1);
     for (unsigned long long i = 0; i < sizes[2 * r]; i++) {
-      std::string v(reinterpret_cast<const char*>(bytes + offs[i]), offs[i + 1] - offs[i]);
+      const std::string_view v(reinterpret_cast<const char*>(bytes + offs[i]), offs[i + 1] - offs[i]);
       auto it = ids.find(v);
       if (it == ids.end()) {
         it = ids.emplace(v, uint32_t(ids.size())).first;
