@@ -156,6 +156,7 @@ struct DevKey {
   const uint32_t* gid;  // gid LUT of the key column (u32 per dictionary entry, entry = chunk.lut_base + idx)
   int64_t bin_base;     // KK_BIN: start of bin 0 (the lowest bin any scanned row group can hold, from footer statistics)
   int64_t bin_width;    // KK_BIN: stride; group id = floor((value - bin_base) / bin_width)
+  uint64_t wstride;     // the same stride in 64 bits (hashed group-by: the mixed radix may be wider than the dense table)
 };
 
 enum ScanMode : uint32_t { SM_FILTER = 0, SM_AGG = 1 };
@@ -198,6 +199,8 @@ struct DevPlan {
   uint32_t replicas;           // accumulator table copies in global memory; CTA b adds into copy b % replicas (merged by k_acc_reduce)
   uint32_t smem_share;         // of every 8 consumer warps of k_flat_agg, how many keep hot slots in shared memory (the rest use L2)
   uint32_t f64_global;         // 1: f64 SUM / AVG cells always go to L2 (no native shared-memory f64 atomic)
+  uint32_t hashed;             // 1: the key space is wider than the dense table: group cells are found through DevScanArgs.hkeys
+  uint32_t hmask;              // hashed: table capacity - 1 (nslots == capacity)
 };
 
 // Accumulator table layout (device, 8-byte cells, struct of arrays over nslots):
@@ -218,6 +221,7 @@ struct DevScanArgs {
   uint32_t* bitmap;            // selection bitmap, per-item word regions
   uint32_t* item_counts;       // selected rows per item
   unsigned long long* acc;     // accumulator table (global)
+  unsigned long long* hkeys;   // hashed group-by: wide group id per accumulator slot (~0: empty)
   unsigned long long* counters;  // [0] rows selected, [1] error flag, [2] work-queue head
   // the table's slab index (fast items)
   const DevSlabRec* slab_recs;       // [page.slab0 + k]

@@ -61,12 +61,14 @@ struct FinishKey {
   uint64_t len_off;            // strings: u32 length per row (scratch, device only)
   uint64_t data_off;           // strings: bytes
   uint32_t stride, card;
+  uint64_t wstride;            // stride in 64 bits (hashed group-by decodes the wide id)
   uint32_t kind;               // DevKind
   uint32_t is_bin;             // DATE_BIN key: value = bin_base + group id * bin_width
   int64_t bin_base, bin_width;
 };
 struct FinishArgs {
   const unsigned long long* acc;
+  const unsigned long long* wide;   // hashed group-by: wide group id per slot (nullptr: the slot is the id)
   const uint32_t* out_slot;
   uint8_t* out;                // the result block
   uint32_t* nulls;             // [(nkeys + naggs) * nbatches] inside the block
@@ -111,7 +113,7 @@ __global__ void k_agg_finish(const __grid_constant__ FinishArgs f) {
   }
   for (uint32_t k = 0; k < f.nkeys; k++) {
     const FinishKey& key = f.keys[k];
-    const uint32_t gid = (slot / key.stride) % (key.card + 1);
+    const uint32_t gid = uint32_t(((f.wide ? f.wide[slot] : uint64_t(slot)) / key.wstride) % (key.card + 1));
     const bool valid = gid != key.card;   // NULL is its own group (field_stats.rs:1009-1037)
     if (valid) atomicOr(reinterpret_cast<uint32_t*>(f.out + key.valid_off) + word, bit);
     else atomicAdd(&f.nulls[k * f.nbatches + batch], 1u);
@@ -170,7 +172,7 @@ __global__ void k_key_gather(const __grid_constant__ FinishArgs f, uint32_t k) {
   const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= f.n_out) return;
   const FinishKey& key = f.keys[k];
-  const uint32_t gid = (f.out_slot[i] / key.stride) % (key.card + 1);
+  const uint32_t gid = uint32_t(((f.wide ? f.wide[f.out_slot[i]] : uint64_t(f.out_slot[i])) / key.wstride) % (key.card + 1));
   if (gid == key.card) return;
   const uint32_t a = key.kd_offs[gid], n = key.kd_offs[gid + 1] - a;
   uint8_t* dst = f.out + key.data_off + reinterpret_cast<const int32_t*>(f.out + key.val_off)[i];

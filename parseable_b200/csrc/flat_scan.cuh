@@ -33,6 +33,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "decode_core.cuh"
 #include "device_structs.hpp"
 #include "flat_store.cuh"
@@ -727,7 +729,26 @@ __device__ __forceinline__ void cell_min_max(unsigned long long* s, unsigned lon
 // 64-bit CAS loops behind f64 SUM and i64 MIN / MAX) retire one lane at a time.
 //   slot <  T : cell = slot * 32 + lane          slot >= T : cell = slot + 31 T
 // Cold slots (cell >= hot cells) go to the global table at cell - 31 T = slot.
-template <int KR>
+// HASHED instantiation: the cell of a group whose wide id (mixed radix with 64-bit strides) does not fit the dense
+// table.  Open addressing, linear probing; keys only ever go from EMPTY to one value, so a stale EMPTY read is
+// caught by the CAS.  A full table raises counters[1] = 100 (the host reports it, nothing is written out of bounds).
+constexpr unsigned long long kHashEmpty = ~0ull;
+__device__ __forceinline__ uint32_t agg_hash_slot(unsigned long long* __restrict__ keys, uint32_t mask, uint64_t wide, unsigned long long* counters) {
+  uint32_t h = uint32_t(mix64(wide)) & mask;
+  for (uint32_t probes = 0; probes <= mask; probes++) {
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(keys + h);
+    if (cur == wide) return h;
+    if (cur == kHashEmpty) {
+      const unsigned long long prev = atomicCAS(keys + h, kHashEmpty, (unsigned long long)wide);
+      if (prev == kHashEmpty || prev == wide) return h;
+    }
+    h = (h + 1) & mask;
+  }
+  atomicExch(&counters[1], 100ull);
+  return 0u;
+}
+
+template <int KR, bool HASHED>
 __global__ void __launch_bounds__(kAggThreads, 1)
 k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLayout L, const __grid_constant__ DevScanArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -814,14 +835,17 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         }
       }
       // ---- group slot of every selected row: one pass per key; NULL is its own group (id == card) ----
-      uint32_t slot[KR];
+      // HASHED: the mixed radix of the group ids is wider than the dense table (64-bit strides); the row's group
+      // finds its cell through the open-addressing table a.hkeys (agg_hash_slot)
+      using slot_t = typename std::conditional<HASHED, uint64_t, uint32_t>::type;
+      slot_t slot[KR];
 #pragma unroll
       for (int i = 0; i < KR; i++) slot[i] = 0;
       for (uint32_t k = 0; k < plan.nkeys; k++) {
         const DevKey& key = plan.keys[k];
         ColCtx c;
         col_ctx<true>(c, st, base, L, key.col, a.flat);
-        const uint32_t stride = key.stride, nullslot = key.card * key.stride;
+        const slot_t stride = HASHED ? slot_t(key.wstride) : slot_t(key.stride), nullslot = slot_t(key.card) * stride;
         const bool nullable = c.absent || c.vw != nullptr;
         if (key.kind == KK_BOOL) {
 #pragma unroll
@@ -872,15 +896,19 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
           }
         }
       }
-      // ---- slot -> cell (the hottest groups own a cell per lane) ----
+      // ---- slot -> cell (the hottest groups own a cell per lane; HASHED: the group's place in the hash table) ----
+      uint32_t cell[KR];
 #pragma unroll
-      for (int i = 0; i < KR; i++) slot[i] = slot[i] < Tw ? slot[i] * 32u + lane : slot[i] + 31u * Tw;
+      for (int i = 0; i < KR; i++) {
+        if (HASHED) cell[i] = ((sel >> i) & 1u) ? agg_hash_slot(a.hkeys, plan.hmask, uint64_t(slot[i]), a.counters) : 0u;
+        else cell[i] = uint32_t(slot[i]) < Tw ? uint32_t(slot[i]) * 32u + lane : uint32_t(slot[i]) + 31u * Tw;
+      }
       // ---- COUNT(*) cell ----
 #pragma unroll
       for (int i = 0; i < KR; i++)
         if ((sel >> i) & 1u) {
-          if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[slot[i]]), 1u);   // a CTA sees < 2^32 rows: the low word never wraps
-          else atomicAdd(&gadj[slot[i]], 1ull);
+          if (cell[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[cell[i]]), 1u);   // a CTA sees < 2^32 rows: the low word never wraps
+          else atomicAdd(&gadj[cell[i]], 1ull);
         }
       // ---- one pass per aggregate (NULL inputs contribute nothing) ----
       for (uint32_t g = 0; g < plan.naggs; g++) {
@@ -900,8 +928,8 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
 #pragma unroll
           for (int i = 0; i < KR; i++)
             if ((vsel >> i) & 1u) {
-              if (slot[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[arr * Hs + slot[i]]), 1u);
-              else atomicAdd(&gadj[size_t(arr) * nslots + slot[i]], 1ull);
+              if (cell[i] < Hw) atomicAdd(reinterpret_cast<uint32_t*>(&sacc[arr * Hs + cell[i]]), 1u);
+              else atomicAdd(&gadj[size_t(arr) * nslots + cell[i]], 1ull);
             }
         }
         if (ag.fn == AG_COUNT) continue;
@@ -927,13 +955,13 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
         if (fn == AG_SUM && !f64) {   // wrapping, like DataFusion's SUM(Int64)
 #pragma unroll
           for (int i = 0; i < KR; i++)
-            if ((vsel >> i) & 1u) cell_add_u64(scell + slot[i], gcell + slot[i], slot[i] < Hc, bits[i]);
+            if ((vsel >> i) & 1u) cell_add_u64(scell + cell[i], gcell + cell[i], cell[i] < Hc, bits[i]);
         } else if (fn == AG_SUM || fn == AG_AVG) {
 #pragma unroll
           for (int i = 0; i < KR; i++)
             if ((vsel >> i) & 1u) {
               const double v = (f64 || fn == AG_SUM) ? __longlong_as_double((long long)bits[i]) : double((long long)bits[i]);
-              cell_add_f64(scell + slot[i], gcell + slot[i], slot[i] < Hc, v);
+              cell_add_f64(scell + cell[i], gcell + cell[i], cell[i] < Hc, v);
             }
         } else {
           const bool is_min = fn == AG_MIN;
@@ -948,8 +976,8 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
           for (int i = 0; i < KR; i++)
             if ((vsel >> i) & 1u) {
               const long long k = f64 ? (long long)f64_order_key(bits[i]) : (long long)bits[i];
-              cell_min_max(scell + slot[i], gcell + slot[i], slot[i] < Hc, is_min, k);
-              if (pair) cell_min_max(scell2 + slot[i], gcell2 + slot[i], slot[i] < Hc, is_min2, k);
+              cell_min_max(scell + cell[i], gcell + cell[i], cell[i] < Hc, is_min, k);
+              if (pair) cell_min_max(scell2 + cell[i], gcell2 + cell[i], cell[i] < Hc, is_min2, k);
             }
           if (pair) g++;
         }

@@ -1019,9 +1019,27 @@ void Query::run(const PqQueryDesc& d) {
     for (uint32_t k : korder) {
       plan.keys[k].card = qk[k].card;
       plan.keys[k].stride = uint32_t(nslots64);
+      plan.keys[k].wstride = nslots64;
+      if (nslots64 > (1ull << 62) / (uint64_t(qk[k].card) + 1)) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key space wider than 2^62 combinations");
       nslots64 *= uint64_t(qk[k].card) + 1;
-      if (nslots64 > (1ull << 26)) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key space too large for the dense accumulator table");
     }
+  }
+  // A key space wider than the dense table (2^26 slots): the groups that actually occur are found through a hash
+  // table on the wide id (DataFusion's GroupValues hashes the key tuple); its capacity is twice the
+  // groups that can occur (<= rows scanned, <= combinations), so it never runs full below the 2^27-slot ceiling.
+  plan.hashed = 0;
+  plan.hmask = 0;
+  if (nslots64 > (1ull << 26)) {
+    if (allreduce || multi)
+      throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY key space too large for the dense accumulator table the ranks all-reduce (hashed tables are per rank)");
+    uint64_t rows_bound = 0;
+    for (uint32_t g = 0; g < nrg_table; g++) if (rg_live[g]) rows_bound += table->row_groups[g].num_rows;
+    uint64_t cap = 1024;
+    while (cap < 2 * std::min<uint64_t>(nslots64, std::max<uint64_t>(rows_bound, 1)) && cap < (1ull << 27)) cap <<= 1;
+    if (cap * (1 + plan.n_acc + plan.n_nn) * 8 > (24ull << 30)) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY: the hashed accumulator table would exceed 24 GiB");
+    plan.hashed = 1;
+    plan.hmask = uint32_t(cap - 1);
+    nslots64 = cap;
   }
   plan.nslots = uint32_t(nslots64);
   const uint32_t cells = 1 + plan.n_acc + plan.n_nn;
@@ -1037,6 +1055,8 @@ void Query::run(const PqQueryDesc& d) {
   for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++)
     if (plan.keys[k].kind == KK_BIN && n_general)
       throw Error(PQ_ERR_UNSUPPORTED, "DATE_BIN keys need a flat-store copy of every page the query reads: " + shape->why_general);
+  if (agg_kernel && plan.hashed && n_general)
+    throw Error(PQ_ERR_UNSUPPORTED, "a hashed GROUP BY needs a flat-store copy of every page the query reads: " + shape->why_general);
   mark("side tables ready");
   // ---- shared-memory layout of k_scan (items the flat kernels do not take) ----
   SmemLayout L{};
@@ -1120,9 +1140,9 @@ void Query::run(const PqQueryDesc& d) {
       plan.hot_slots = 0;
     } else {
       // one CTA per SM: the hot part of the accumulator table next to the stages
-      const uint64_t full = uint64_t(plan.nslots) * cells * 8;
-      uint32_t krows = 8;
-      if (const char* e = getenv("PQB_AGG_KROWS")) krows = std::max(1, std::min(8, atoi(e)));   // experiment switch
+      const uint64_t full = plan.hashed ? 0 : uint64_t(plan.nslots) * cells * 8;   // hashed: no hot table in shared memory
+      uint32_t krows = plan.hashed ? 4 : 8;   // the hashed instantiation exists for 4 rows per thread (64-bit slots: registers)
+      if (const char* e = plan.hashed ? nullptr : getenv("PQB_AGG_KROWS")) krows = std::max(1, std::min(8, atoi(e)));   // experiment switch
       while (krows & (krows - 1)) krows &= krows - 1;
       while (krows > 1 && 2 * stage_bytes_for(kAggConsumers * krows) + std::min<uint64_t>(full, 96 * 1024) > avail) krows >>= 1;
       const uint32_t S = kAggConsumers * krows;
@@ -1142,9 +1162,10 @@ void Query::run(const PqQueryDesc& d) {
       if (const char* e = getenv("PQB_F64_GLOBAL")) if (atoi(e)) T = 0;   // that experiment sends hot f64 cells to L2 by SLOT: no per-lane cells
       T = std::min<uint32_t>(T, plan.nslots);
       while (T && cap < 64u * T) T >>= 1;
+      if (plan.hashed) T = 0;
       plan.lane_slots = T;
-      plan.hot_slots = uint32_t(std::min<uint64_t>(plan.nslots, cap - 31u * T));
-      if (const char* hs = getenv("PQB_HOT_SLOTS")) plan.hot_slots = std::max(T, std::min<uint32_t>(plan.hot_slots, uint32_t(atoi(hs))));   // experiment switch
+      plan.hot_slots = plan.hashed ? 0u : uint32_t(std::min<uint64_t>(plan.nslots, cap - 31u * T));
+      if (const char* hs = plan.hashed ? nullptr : getenv("PQB_HOT_SLOTS")) plan.hot_slots = std::max(T, std::min<uint32_t>(plan.hot_slots, uint32_t(atoi(hs))));   // experiment switch
       plan.flat_slab_rows = S;
       plan.flat_krows = krows;
     }
@@ -1180,7 +1201,7 @@ void Query::run(const PqQueryDesc& d) {
   }
 
   // ---- accumulators ----
-  DevBuf<unsigned long long> d_acc;
+  DevBuf<unsigned long long> d_acc, d_hkeys;
   size_t smem_total = smem_fixed;
   plan.replicas = 1;
   plan.smem_share = 8;
@@ -1195,6 +1216,11 @@ void Query::run(const PqQueryDesc& d) {
       uint32_t r = uint32_t(std::min<uint64_t>(32, (48ull << 20) / std::max<uint64_t>(tbytes, 1)));
       if (const char* e = getenv("PQB_REPLICAS")) r = uint32_t(atoi(e));
       plan.replicas = std::max<uint32_t>(1, std::min<uint32_t>(r, uint32_t(ctx.sm_count())));
+    }
+    if (plan.hashed) {
+      plan.replicas = 1;
+      d_hkeys.alloc(plan.nslots, stream);
+      PQB_CUDA(cudaMemsetAsync(d_hkeys.p, 0xff, size_t(plan.nslots) * 8, stream));
     }
     d_acc.alloc(size_t(plan.nslots) * cells * plan.replicas, stream);
     {
@@ -1238,6 +1264,7 @@ void Query::run(const PqQueryDesc& d) {
   sa.bitmap = d_bitmap.p;
   sa.item_counts = d_item_counts.p;
   sa.acc = d_acc.p;
+  sa.hkeys = d_hkeys.p;
   sa.counters = d_counters.p;
   sa.slab_recs = table->d_slab_recs;
   sa.slab_dirs = table->d_slab_dirs;
@@ -1251,9 +1278,10 @@ void Query::run(const PqQueryDesc& d) {
         PQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
         kern<<<grid, kAggThreads, FL.total, stream>>>(plan, FL, sa);
       };
-      if (plan.flat_krows >= 8) go(k_flat_agg<8>);        // rows per thread and slab: the widest instantiation the stages leave room for
-      else if (plan.flat_krows >= 4) go(k_flat_agg<4>);
-      else go(k_flat_agg<2>);
+      if (plan.hashed) go(k_flat_agg<4, true>);           // key space wider than the dense table: cells through the hash table
+      else if (plan.flat_krows >= 8) go(k_flat_agg<8, false>);   // rows per thread and slab: the widest instantiation the stages leave room for
+      else if (plan.flat_krows >= 4) go(k_flat_agg<4, false>);
+      else go(k_flat_agg<2, false>);
     } else {
       auto go = [&](auto kern) {
         PQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx.smem_optin())));
@@ -1347,6 +1375,7 @@ void Query::run(const PqQueryDesc& d) {
     PQB_CUDA(cudaMemcpyAsync(h_counters, d_counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
     metrics.d2h_bytes += 16 + sizeof(h_counters);
+    if (plan.hashed && h_counters[1] == 100) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY: more distinct groups than the hashed accumulator table holds (2^26)");
     if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
     const uint32_t n_out = uint32_t(totals[0]);
     metrics.rows_selected = totals[1];
@@ -1391,6 +1420,7 @@ void Query::run(const PqQueryDesc& d) {
         const uint8_t kind = plan.cols[plan.keys[k].col].kind;
         fk.kind = kind;
         fk.stride = plan.keys[k].stride;
+        fk.wstride = plan.keys[k].wstride;
         fk.card = qk[k].card;
         fk.valid_off = take(uint64_t(nbatches) * wpb * 4);
         if (kind == DK_BOOL) fk.val_off = take(uint64_t(nbatches) * wpb * 4);
@@ -1435,6 +1465,7 @@ void Query::run(const PqQueryDesc& d) {
       d_block.alloc(off, stream);
       PQB_CUDA(cudaMemsetAsync(d_block.p, 0, copy_bytes, stream));
       fa.acc = d_acc.p;
+      fa.wide = plan.hashed ? d_hkeys.p : nullptr;
       fa.out_slot = d_out_slot.p;
       fa.out = d_block.p;
       fa.nulls = reinterpret_cast<uint32_t*>(d_block.p + nulls_off);

@@ -124,6 +124,10 @@ AGGS = {
     "f64_key": (["duration_s"], [count_star()], [col("latency_ms") < 40]),
     "filtered_c3": (["host"], [count_star(), sum_("bytes")], [(col("level") == "ERROR") & (col("latency_ms") > 100)]),
     "ts_minmax": (["service"], [min_("latency_ms"), max_("latency_ms"), count("host")], []),
+    # key space 10 000 x 1 000 x 5 000 (x NULL): wider than the dense table, the groups that occur are hashed
+    "hashed_wide_keys": (["host", "path", "pod"], [count_star(), sum_("bytes"), min_("latency_ms"), max_("cpu"), sum_("duration_s"),
+                                                    avg("score"), count("mem_gb")], [col("level") != "DEBUG"]),
+    "hashed_four_keys": (["pod", "path", "service", "status"], [count_star(), max_("latency_ms")], []),
 }
 
 
