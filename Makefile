@@ -16,7 +16,7 @@ LIB       ?= parseable_b200/libparseable_b200.so
 EXTRA     ?=
 
 CU_SRCS   := $(CSRC)/table.cu $(CSRC)/query.cu
-CPP_SRCS  := $(CSRC)/parquet_meta.cpp $(CSRC)/arrow_export.cpp $(CSRC)/capi.cpp $(CSRC)/comm.cpp
+CPP_SRCS  := $(CSRC)/parquet_meta.cpp $(CSRC)/arrow_export.cpp $(CSRC)/capi.cpp $(CSRC)/comm.cpp $(CSRC)/planning.cpp
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.hpp $(CSRC)/*.cuh include/*.h)
 

@@ -271,6 +271,77 @@ void pq_host_free(void* p);
  * footer/page-header reader can be checked against an independent reader without a GPU. */
 int64_t pq_file_describe(const PqFile* file, char* out, uint64_t cap);
 
+/* ---- scan planning on the C side (no GPU work): which manifests / files reach the scan ----
+ * What StandardTableProvider::scan does above create_parquet_physical_plan:
+ *   time bounds of the filters      src/query/stream_schema_provider.rs:884-940 (extract_timestamp_bound, PartialTimeFilter)
+ *   Snapshot::manifests             src/catalog/snapshot.rs:40-71
+ *   is_overlapping_query            src/query/stream_schema_provider.rs:750-775
+ *   is_within_staging_window        :842-864
+ *   can_be_pruned / satisfy_constraints   :955-1043 (TypedStatistics, src/catalog/column.rs:52-68)
+ *   collect_from_snapshot           :449-510 (newest first, pruning, LIMIT truncation)
+ *   partitioned_files + statistics merge   :351-446, src/catalog/column.rs:70-198
+ *   supports_filters_pushdown       :665-683, 866-882
+ * The Rust host may keep doing this itself; these entry points let a shim hand the manifest over instead. */
+#define PQ_T_TS_NS 6 /* planning only: Timestamp(Nanosecond) literal in PqLiteral.i64 */
+
+typedef struct {
+  const char* column; /* NULL: the filter is not `column <cmp> literal` (never prunes, never a time bound) */
+  int32_t cmp;        /* PqCmp */
+  int32_t _pad;
+  PqLiteral lit;
+} PqPlanFilter;
+
+typedef enum { PQ_STAT_NONE = 0, PQ_STAT_BOOL = 1, PQ_STAT_INT = 2, PQ_STAT_FLOAT = 3, PQ_STAT_STRING = 4 } PqStatKind;
+typedef struct {
+  const char* column;
+  int32_t kind; /* PqStatKind; PQ_STAT_NONE: the manifest holds no statistics for the column */
+  int32_t _pad;
+  int64_t min_i, max_i; /* BOOL (0/1), INT */
+  double min_f, max_f;  /* FLOAT */
+  const char* min_s;    /* STRING, not NUL-terminated */
+  uint64_t min_s_len;
+  const char* max_s;
+  uint64_t max_s_len;
+} PqColumnStat;
+
+typedef struct {
+  const char* path;
+  uint64_t num_rows;
+  uint64_t file_size;
+  const PqColumnStat* stats;
+  uint32_t n_stats;
+  uint32_t _pad;
+} PqManifestFile;
+
+typedef struct {
+  int64_t time_lower_ns; /* naive UTC, nanoseconds since the epoch */
+  int64_t time_upper_ns;
+} PqManifestItem;
+
+typedef enum { PQ_BOUND_LOW = 0, PQ_BOUND_HIGH = 1, PQ_BOUND_EQ = 2 } PqBoundKind;
+typedef struct {
+  int32_t kind;     /* PqBoundKind */
+  int32_t included; /* LOW / HIGH: the bound itself belongs to the range */
+  int64_t time_ns;
+} PqTimeBound;
+
+/* One bound per filter that is `column <cmp> timestamp literal` (a Utf8 literal only on `time_partition`).
+ * Returns the number of bounds written (<= n), or a negative status. */
+int32_t pq_plan_time_bounds(const PqPlanFilter* filters, uint32_t n, const char* time_partition, PqTimeBound* out);
+/* keep[i] = 1 when manifest item i can hold rows inside every bound */
+int32_t pq_plan_manifests(const PqManifestItem* items, uint32_t n, const PqTimeBound* bounds, uint32_t n_bounds, uint8_t* keep);
+int32_t pq_plan_is_overlapping_query(const PqManifestItem* items, uint32_t n, const PqTimeBound* bounds, uint32_t n_bounds);
+int32_t pq_plan_within_staging_window(const PqTimeBound* bounds, uint32_t n_bounds, int64_t now_ns);
+/* files in manifest order (oldest first) -> out_index: the files to scan, newest first, without those whose
+ * statistics rule a filter out, cut once `limit` rows are covered (limit < 0: none).  Returns how many. */
+int64_t pq_plan_collect_files(const PqManifestFile* files, uint32_t n_files, const PqPlanFilter* filters, uint32_t n_filters,
+                              int64_t limit, uint32_t* out_index);
+/* a [min, max] of one column merged over two files; returns 1 and fills *out, or 0 when the ranges cannot be merged
+ * (different kinds, an inverted or NaN float range): the planner then skips min / max for that column */
+int32_t pq_plan_merge_stat(const PqColumnStat* a, const PqColumnStat* b, PqColumnStat* out);
+/* exact[i] = 1: the scan alone answers filter i (minute-aligned time comparison), 0: Inexact */
+int32_t pq_plan_pushdown(const PqPlanFilter* filters, uint32_t n, uint8_t* exact);
+
 /* ---- multi-GPU: one process per GPU, NCCL communicator owned by the library ---- */
 #define PQ_COMM_ID_BYTES 128
 int pq_comm_unique_id(uint8_t id[PQ_COMM_ID_BYTES]);

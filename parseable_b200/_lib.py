@@ -70,6 +70,34 @@ class PqQueryDesc(C.Structure):
 
 PQ_KEY_COLUMN, PQ_KEY_DATE_BIN = 0, 1
 
+# ---- scan planning on the C side (csrc/planning.cpp) ----
+PQ_T_TS_NS = 6
+PQ_STAT_NONE, PQ_STAT_BOOL, PQ_STAT_INT, PQ_STAT_FLOAT, PQ_STAT_STRING = range(5)
+PQ_BOUND_LOW, PQ_BOUND_HIGH, PQ_BOUND_EQ = range(3)
+
+
+class PqPlanFilter(C.Structure):
+    _fields_ = [("column", C.c_char_p), ("cmp", C.c_int32), ("_pad", C.c_int32), ("lit", PqLiteral)]
+
+
+class PqColumnStat(C.Structure):
+    _fields_ = [("column", C.c_char_p), ("kind", C.c_int32), ("_pad", C.c_int32), ("min_i", C.c_int64), ("max_i", C.c_int64),
+                ("min_f", C.c_double), ("max_f", C.c_double), ("min_s", C.c_char_p), ("min_s_len", C.c_uint64),
+                ("max_s", C.c_char_p), ("max_s_len", C.c_uint64)]
+
+
+class PqManifestFile(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("num_rows", C.c_uint64), ("file_size", C.c_uint64), ("stats", C.POINTER(PqColumnStat)),
+                ("n_stats", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class PqManifestItem(C.Structure):
+    _fields_ = [("time_lower_ns", C.c_int64), ("time_upper_ns", C.c_int64)]
+
+
+class PqTimeBound(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("included", C.c_int32), ("time_ns", C.c_int64)]
+
 
 class PqMetrics(C.Structure):
     _fields_ = [
@@ -113,6 +141,8 @@ EXPORTS = [
     "pq_query_open", "pq_query_next", "pq_query_stream", "pq_query_metrics", "pq_last_error", "pq_query_close",
     "pq_comm_unique_id", "pq_comm_init_rank", "pq_comm_destroy",
     "pq_host_alloc", "pq_host_free", "pq_file_describe",
+    "pq_plan_time_bounds", "pq_plan_manifests", "pq_plan_is_overlapping_query", "pq_plan_within_staging_window",
+    "pq_plan_collect_files", "pq_plan_merge_stat", "pq_plan_pushdown",
 ]
 
 _lib = None
@@ -169,5 +199,20 @@ def load() -> C.CDLL:
     lib.pq_host_free.restype = None
     lib.pq_file_describe.argtypes = [C.POINTER(PqFile), C.c_char_p, C.c_uint64]
     lib.pq_file_describe.restype = C.c_int64
+    lib.pq_plan_time_bounds.argtypes = [C.POINTER(PqPlanFilter), C.c_uint32, C.c_char_p, C.POINTER(PqTimeBound)]
+    lib.pq_plan_time_bounds.restype = C.c_int32
+    lib.pq_plan_manifests.argtypes = [C.POINTER(PqManifestItem), C.c_uint32, C.POINTER(PqTimeBound), C.c_uint32, C.POINTER(C.c_uint8)]
+    lib.pq_plan_manifests.restype = C.c_int32
+    lib.pq_plan_is_overlapping_query.argtypes = [C.POINTER(PqManifestItem), C.c_uint32, C.POINTER(PqTimeBound), C.c_uint32]
+    lib.pq_plan_is_overlapping_query.restype = C.c_int32
+    lib.pq_plan_within_staging_window.argtypes = [C.POINTER(PqTimeBound), C.c_uint32, C.c_int64]
+    lib.pq_plan_within_staging_window.restype = C.c_int32
+    lib.pq_plan_collect_files.argtypes = [C.POINTER(PqManifestFile), C.c_uint32, C.POINTER(PqPlanFilter), C.c_uint32, C.c_int64,
+                                          C.POINTER(C.c_uint32)]
+    lib.pq_plan_collect_files.restype = C.c_int64
+    lib.pq_plan_merge_stat.argtypes = [C.POINTER(PqColumnStat), C.POINTER(PqColumnStat), C.POINTER(PqColumnStat)]
+    lib.pq_plan_merge_stat.restype = C.c_int32
+    lib.pq_plan_pushdown.argtypes = [C.POINTER(PqPlanFilter), C.c_uint32, C.POINTER(C.c_uint8)]
+    lib.pq_plan_pushdown.restype = C.c_int32
     _lib = lib
     return lib

@@ -41,13 +41,15 @@ def test_struct_layouts_match_header(lib, tmp_path):
     """The header is valid plain C and the ctypes mirror has the same struct sizes gcc computes."""
     import subprocess
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "parseable_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "parseable_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(PqLiteral),sizeof(PqPredOp),sizeof(PqAgg),sizeof(PqFile),sizeof(PqColumn),sizeof(PqQueryDesc),'
-                   'sizeof(PqMetrics),sizeof(struct ArrowArray),sizeof(struct ArrowSchema));return 0;}\n')
+                   'sizeof(PqMetrics),sizeof(struct ArrowArray),sizeof(struct ArrowSchema),sizeof(PqPlanFilter),sizeof(PqColumnStat),'
+                   'sizeof(PqManifestFile),sizeof(PqManifestItem),sizeof(PqTimeBound));return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    mirror = [L.PqLiteral, L.PqPredOp, L.PqAgg, L.PqFile, L.PqColumn, L.PqQueryDesc, L.PqMetrics, L.ArrowArray, L.ArrowSchema]
+    mirror = [L.PqLiteral, L.PqPredOp, L.PqAgg, L.PqFile, L.PqColumn, L.PqQueryDesc, L.PqMetrics, L.ArrowArray, L.ArrowSchema,
+              L.PqPlanFilter, L.PqColumnStat, L.PqManifestFile, L.PqManifestItem, L.PqTimeBound]
     assert sizes == [C.sizeof(m) for m in mirror]
 
 

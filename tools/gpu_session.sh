@@ -1,3 +1,4 @@
 set -x
 mkdir -p gpurun_out
-PQB_BENCH_CODEC=LZ4 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_lz4.csv python tests/scripts/open_probe.py 480 > gpurun_out/lz4_probe.log 2>&1; tail -3 gpurun_out/lz4_probe.log
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv | tail -1
+( time timeout -s KILL 900 python -m pytest tests -m gpu -x -q --durations=8 ) > gpurun_out/gputests.log 2>&1; tail -25 gpurun_out/gputests.log
