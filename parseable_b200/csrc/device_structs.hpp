@@ -68,7 +68,8 @@ struct DevChunk {              // one column chunk (row group x referenced colum
 };
 
 // Flat store (flat_store.cuh): the scan-ready copy of one data page.
-enum FlatKind : uint8_t { FK_NONE = 0, FK_INDEX = 1, FK_PLAIN8 = 2, FK_BITS = 3, FK_BYTES = 4 };
+enum FlatKind : uint8_t { FK_NONE = 0, FK_INDEX = 1, FK_PLAIN8 = 2, FK_BITS = 3, FK_BYTES = 4,
+                          FK_IDS = 5 };   // FK_IDS (per query): u32 group id per row of a GROUP BY column's page without a dictionary
 struct FlatPageRec {           // parallel to pages[]
   uint64_t off;                // byte offset in the flat buffer, 16-byte aligned: one slot per ROW (NULL rows hold 0)
   uint64_t voff;               // validity bitmap (1 bit per row, LSB first like Arrow), or ~0: the page holds no NULLs

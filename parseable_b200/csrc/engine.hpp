@@ -135,6 +135,14 @@ struct ColSide {
   uint32_t* d_glob_kd_offs = nullptr;
   uint8_t* d_glob_kd_bytes = nullptr;
   uint64_t* d_key_hash = nullptr;
+  // GROUP BY on a column with pages that have no dictionary (PLAIN fallback, PLAIN / DELTA numerics): every ROW of those
+  // pages is an entry behind the dictionary entries; d_gid / d_glob_gid then hold, per such page, one group id per row --
+  // the page's "id page", staged by the aggregate kernel like 32-bit dictionary indices (FK_IDS)
+  uint32_t key_entries = 0;            // entries d_gid covers (== total_entries when the column has only dictionary pages)
+  uint32_t n_dict_pad = 0;             // first row entry (total_entries rounded up to 4)
+  uint64_t* d_row_ent = nullptr;       // where every row entry's value sits (relative to the arena, ~0: NULL / padding)
+  struct KeyRowPage { uint32_t page; uint32_t ebase; };   // page index, first entry of its rows relative to n_dict_pad
+  std::vector<KeyRowPage> key_row_pages;
 };
 
 // What a query needs per SET of referenced columns, built once per (table, column set): the chunk

@@ -879,7 +879,16 @@ k_flat_agg(const __grid_constant__ DevPlan plan, const __grid_constant__ FlatLay
             }
         } else {
           const uint32_t* __restrict__ gid = key.gid + st.col[key.col].lut_base;
-          if (!nullable) {   // the loads of all rows in flight together
+          if (c.fkind == FK_IDS) {   // a page without a dictionary: its rows were interned when the table column became a key, the staged words ARE the ids
+#pragma unroll
+            for (int i = 0; i < KR; i++)
+              if ((sel >> i) & 1u) {
+                const uint32_t r = tc + i * kAggConsumers;
+                if (nullable && !col_valid(c, r)) { slot[i] += nullslot; continue; }
+                const uint32_t g = bits32_at(c.colw, c.phase + r * 32u);
+                slot[i] += (g < key.card ? g : key.card - 1u) * stride;   // never out of the table
+              }
+          } else if (!nullable) {   // the loads of all rows in flight together
             uint32_t g[KR];
 #pragma unroll
             for (int i = 0; i < KR; i++) g[i] = ((sel >> i) & 1u) ? __ldg(gid + col_index(c, tc + i * kAggConsumers)) : 0u;

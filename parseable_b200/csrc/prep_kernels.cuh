@@ -129,6 +129,18 @@ __global__ void k_leaf_luts(DevPrepArgs a, const __grid_constant__ DevPlan plan)
 }
 
 // ---- GROUP BY key interning (per table column, query independent) ----
+// "Entries" of a key column: the dictionary entries of every row group, then -- for columns with pages that have no
+// dictionary (PLAIN fallback of an overflowed dictionary, PLAIN / DELTA numerics) -- every ROW of those pages.  An entry
+// is where its value's bytes sit relative to the arena (a row's 8-byte slot of the flat store lies outside the arena:
+// the offset wraps, arena + offset does not); ~0 marks a NULL row / padding.
+struct EntView {
+  const uint64_t* dict;   // [0, n_dict): dictionary entries
+  const uint64_t* rows;   // [n_dict, ...): rows of the column's non-dictionary pages
+  uint32_t n_dict;
+};
+__device__ __forceinline__ uint64_t ent_at(const EntView& v, uint32_t ge) { return ge < v.n_dict ? v.dict[ge] : v.rows[ge - v.n_dict]; }
+constexpr uint64_t kNoEntry = ~0ull;
+
 struct DevKeyTable {
   unsigned long long* slots;  // 0 empty, else (hash32 << 32) | (column entry index + 1)
   uint32_t* gid_of_slot;
@@ -136,7 +148,7 @@ struct DevKeyTable {
   uint32_t* counter;          // [0] distinct count, [1] overflow flag
   uint32_t cap_mask;
   uint32_t kind;              // DevKind
-  const uint64_t* ent;        // entry offsets of the column
+  EntView ent;                // entry offsets of the column
   uint32_t* gid;              // out: group id per column entry
 };
 
@@ -148,42 +160,75 @@ __device__ __forceinline__ bool entry_equal(const uint8_t* arena, uint64_t oa, u
   return true;
 }
 
-// mode 0: insert + number; mode 1: lookup -> gid[].  grid.x = column chunks in [c0, c0 + gridDim.x)
+// mode 0: insert + number; mode 1: lookup -> gid[]
+__device__ __forceinline__ void intern_entry(const uint8_t* __restrict__ arena, const DevKeyTable& t, uint32_t ge, int mode) {
+  const uint64_t off = ent_at(t.ent, ge);
+  if (off == kNoEntry) return;
+  uint32_t len = entry_len(arena, off, (uint8_t)t.kind);
+  uint64_t h = t.kind == DK_STR ? hash_bytes(arena + off, len) : mix64(load_u64_unaligned(arena + off));
+  uint32_t h32 = uint32_t(h >> 32);
+  unsigned long long word = ((unsigned long long)h32 << 32) | (unsigned long long)(ge + 1);
+  uint32_t slot = uint32_t(h) & t.cap_mask;
+  uint32_t probes = 0;
+  for (;;) {
+    unsigned long long cur = t.slots[slot];
+    if (cur == 0 && mode == 0) {
+      unsigned long long prev = atomicCAS(&t.slots[slot], 0ull, word);
+      if (prev == 0) {
+        uint32_t gid = atomicAdd(&t.counter[0], 1u);
+        t.gid_of_slot[slot] = gid;
+        t.rep_of_gid[gid] = ge;
+        break;
+      }
+      cur = prev;
+    }
+    if (cur == 0) { atomicExch(&t.counter[1], 2u); break; }  // lookup miss: cannot happen
+    if (uint32_t(cur >> 32) == h32) {
+      uint32_t other = uint32_t(cur & 0xffffffffull) - 1;
+      if (other == ge || entry_equal(arena, off, ent_at(t.ent, other), len, (uint8_t)t.kind)) {
+        if (mode == 1) t.gid[ge] = t.gid_of_slot[slot];
+        break;
+      }
+    }
+    slot = (slot + 1) & t.cap_mask;
+    if (++probes > t.cap_mask) { atomicExch(&t.counter[1], 1u); break; }
+  }
+}
+
+// dictionary entries.  grid.x = column chunks in [c0, c0 + gridDim.x)
 __global__ void k_key_intern(const uint8_t* __restrict__ arena, const EntChunk* __restrict__ chunks, uint32_t c0, DevKeyTable t, int mode) {
   const EntChunk ch = chunks[c0 + blockIdx.x];
   if (!ch.present || ch.dict_n == 0) return;
-  for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) {
-    uint32_t ge = ch.base + e;
-    uint64_t off = t.ent[ge];
-    uint32_t len = entry_len(arena, off, (uint8_t)t.kind);
-    uint64_t h = t.kind == DK_STR ? hash_bytes(arena + off, len) : mix64(load_u64_unaligned(arena + off));
-    uint32_t h32 = uint32_t(h >> 32);
-    unsigned long long word = ((unsigned long long)h32 << 32) | (unsigned long long)(ge + 1);
-    uint32_t slot = uint32_t(h) & t.cap_mask;
-    uint32_t probes = 0;
-    for (;;) {
-      unsigned long long cur = t.slots[slot];
-      if (cur == 0 && mode == 0) {
-        unsigned long long prev = atomicCAS(&t.slots[slot], 0ull, word);
-        if (prev == 0) {
-          uint32_t gid = atomicAdd(&t.counter[0], 1u);
-          t.gid_of_slot[slot] = gid;
-          t.rep_of_gid[gid] = ge;
-          break;
-        }
-        cur = prev;
-      }
-      if (cur == 0) { atomicExch(&t.counter[1], 2u); break; }  // lookup miss: cannot happen
-      if (uint32_t(cur >> 32) == h32) {
-        uint32_t other = uint32_t(cur & 0xffffffffull) - 1;
-        if (other == ge || entry_equal(arena, off, t.ent[other], len, (uint8_t)t.kind)) {
-          if (mode == 1) t.gid[ge] = t.gid_of_slot[slot];
-          break;
-        }
-      }
-      slot = (slot + 1) & t.cap_mask;
-      if (++probes > t.cap_mask) { atomicExch(&t.counter[1], 1u); break; }
+  for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < ch.dict_n; e += gridDim.y * blockDim.x) intern_entry(arena, t, ch.base + e, mode);
+}
+
+// rows of the column's non-dictionary pages: where every row's value sits (k_row_entries), then the same interning
+struct RowPage {
+  uint64_t off;      // flat-store offset of the page's slots (FK_PLAIN8: 8 bytes per row; FK_BYTES: u32 per row, relative to `base`)
+  uint64_t voff;     // validity bits, ~0: no NULLs
+  uint64_t base;     // FK_BYTES: arena offset of the page's values section
+  uint32_t rows;
+  uint32_t ebase;    // first entry of the page inside EntView.rows (a multiple of 4: the id page is a TMA source)
+  uint32_t fkind;
+  uint32_t _pad;
+};
+__global__ void k_row_entries(const uint8_t* __restrict__ flat, const RowPage* __restrict__ rp, uint32_t n_pages, uint64_t flat_minus_arena,
+                              uint64_t* __restrict__ out) {
+  for (uint32_t p = blockIdx.x; p < n_pages; p += gridDim.x) {
+    const RowPage pg = rp[p];
+    const uint32_t* vw = pg.voff == ~0ull ? nullptr : reinterpret_cast<const uint32_t*>(flat + pg.voff);
+    for (uint32_t r = threadIdx.x; r < pg.rows; r += blockDim.x) {
+      const bool valid = !vw || ((vw[r >> 5] >> (r & 31)) & 1u);
+      uint64_t e = kNoEntry;
+      if (valid) e = pg.fkind == FK_PLAIN8 ? flat_minus_arena + pg.off + uint64_t(r) * 8 : pg.base + reinterpret_cast<const uint32_t*>(flat + pg.off)[r];
+      out[pg.ebase + r] = e;
     }
+  }
+}
+__global__ void k_row_intern(const uint8_t* __restrict__ arena, const RowPage* __restrict__ rp, uint32_t n_pages, DevKeyTable t, int mode) {
+  for (uint32_t p = blockIdx.x; p < n_pages; p += gridDim.x) {
+    const uint32_t rows = rp[p].rows, e0 = t.ent.n_dict + rp[p].ebase;
+    for (uint32_t r = threadIdx.x; r < rows; r += blockDim.x) intern_entry(arena, t, e0 + r, mode);
   }
 }
 
@@ -326,17 +371,17 @@ __global__ void k_compact_row_ids(const uint32_t* __restrict__ bitmap, const Dev
 }
 
 // key value export: lengths, then bytes at host-computed offsets
-__global__ void k_key_lens(const uint8_t* arena, const uint64_t* ent_off, const uint32_t* rep_of_gid, uint32_t card,
+__global__ void k_key_lens(const uint8_t* arena, EntView ent, const uint32_t* rep_of_gid, uint32_t card,
                            uint8_t kind, uint32_t* lens) {
   uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= card) return;
-  lens[g] = entry_len(arena, ent_off[rep_of_gid[g]], kind);
+  lens[g] = entry_len(arena, ent_at(ent, rep_of_gid[g]), kind);
 }
-__global__ void k_key_bytes(const uint8_t* arena, const uint64_t* ent_off, const uint32_t* rep_of_gid, uint32_t card,
+__global__ void k_key_bytes(const uint8_t* arena, EntView ent, const uint32_t* rep_of_gid, uint32_t card,
                             uint8_t kind, const uint32_t* offsets, uint8_t* out) {
   uint32_t g = blockIdx.x;
   if (g >= card) return;
-  uint64_t off = ent_off[rep_of_gid[g]];
+  uint64_t off = ent_at(ent, rep_of_gid[g]);
   uint32_t len = entry_len(arena, off, kind);
   for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) out[offsets[g] + i] = arena[off + i];
 }

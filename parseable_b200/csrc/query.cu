@@ -278,15 +278,50 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
   std::vector<EntChunk> ch = column_chunks(t, tcol);
   const uint32_t nrg = uint32_t(ch.size());
   const uint32_t n = side.total_entries;
-  PQB_CUDA(cudaMallocAsync((void**)&side.d_gid, std::max<uint64_t>(n, 1) * 4, stream));
+  // ---- pages without a dictionary: their rows are entries too ----
+  std::vector<RowPage> rowpages;
+  side.key_row_pages.clear();
+  side.n_dict_pad = (n + 3u) & ~3u;
+  uint64_t row_entries = 0;
+  for (uint32_t g = 0; g < nrg; g++) {
+    const TableChunk& tc = t.row_groups[g].chunks[tcol];
+    if (!tc.present) continue;
+    for (uint32_t k = 0; k < tc.pages.n_pages; k++) {
+      const uint32_t pi = tc.pages.first_page + k;
+      const DevPage& dp = t.pages[pi];
+      if (dp.enc == DE_DICT || dp.enc == DE_RLE_BOOL) continue;
+      const FlatPageRec* fr = pi < t.flat_pages.size() ? &t.flat_pages[pi] : nullptr;
+      if (!fr || (fr->fkind != FK_PLAIN8 && fr->fkind != FK_BYTES))
+        throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + t.columns[tcol].name + "': a page without a dictionary has no flat-store copy to take the keys from");
+      rowpages.push_back(RowPage{fr->off, fr->voff, fr->base, fr->rows, uint32_t(row_entries), fr->fkind, 0u});
+      side.key_row_pages.push_back({pi, uint32_t(row_entries)});
+      row_entries += (uint64_t(fr->rows) + 3u) & ~3ull;
+    }
+  }
+  if (uint64_t(side.n_dict_pad) + row_entries > 0xfffffff0ull) throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + t.columns[tcol].name + "': more than 2^32 key entries");
+  const uint32_t n_all = rowpages.empty() ? n : uint32_t(side.n_dict_pad + row_entries);
+  side.key_entries = n_all;
+  PQB_CUDA(cudaMallocAsync((void**)&side.d_gid, std::max<uint64_t>(n_all, 1) * 4, stream));
+  PQB_CUDA(cudaMemsetAsync(side.d_gid, 0, std::max<uint64_t>(n_all, 1) * 4, stream));
   side.card = 0;
   side.kd = KeyDict{};
   side.kd.offs.assign(1, 0);
-  if (!n || !nrg) { PQB_CUDA(cudaStreamSynchronize(stream)); return; }
+  if (!n_all || !nrg) { PQB_CUDA(cudaStreamSynchronize(stream)); return; }
   DevBuf<EntChunk> d_ch; d_ch.upload(ch, stream);
+  DevBuf<RowPage> d_rp;
+  if (!rowpages.empty()) {
+    d_rp.upload(rowpages, stream);
+    PQB_CUDA(cudaMallocAsync((void**)&side.d_row_ent, row_entries * 8, stream));
+    PQB_CUDA(cudaMemsetAsync(side.d_row_ent, 0xff, row_entries * 8, stream));   // padding between pages: no entry
+    k_row_entries<<<uint32_t(std::min<size_t>(rowpages.size(), 65535)), 256, 0, stream>>>(t.d_flat, d_rp.p, uint32_t(rowpages.size()),
+                                                                                         uint64_t(t.d_flat) - uint64_t(t.d_arena), side.d_row_ent);
+    PQB_CUDA(cudaGetLastError());
+  }
+  const EntView ent{side.d_ent_off, side.d_row_ent, rowpages.empty() ? n : side.n_dict_pad};
   const uint32_t maxn = std::max<uint32_t>(side.max_dict_n, 1);
   uint64_t cap = 64;
   while (cap < 4ull * maxn) cap <<= 1;
+  while (cap < std::min<uint64_t>(2 * row_entries, 1ull << 22)) cap <<= 1;   // rows: start where a column of mostly distinct values needs few redos
   DevBuf<uint32_t> rep;
   uint32_t card = 0;
   for (;;) {
@@ -294,13 +329,16 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
     DevBuf<uint32_t> gid_of_slot; gid_of_slot.alloc(cap, stream);
     DevBuf<uint32_t> rep_try; rep_try.alloc(cap, stream);
     DevBuf<uint32_t> counter; counter.alloc(2, stream); counter.zero();
-    DevKeyTable kt{slots.p, gid_of_slot.p, rep_try.p, counter.p, uint32_t(cap - 1), kkind, side.d_ent_off, side.d_gid};
+    DevKeyTable kt{slots.p, gid_of_slot.p, rep_try.p, counter.p, uint32_t(cap - 1), kkind, ent, side.d_gid};
     const uint32_t gy = std::min<uint32_t>((maxn + 255) / 256, 64);
-    for (int mode = 0; mode < 2; mode++)
-      for (uint32_t c0 = 0; c0 < nrg; c0 += 32768) {
+    for (int mode = 0; mode < 2; mode++) {
+      for (uint32_t c0 = 0; n && c0 < nrg; c0 += 32768) {
         dim3 grid(std::min<uint32_t>(32768, nrg - c0), gy);
         k_key_intern<<<grid, 256, 0, stream>>>(t.d_arena, d_ch.p, c0, kt, mode);
       }
+      if (!rowpages.empty())
+        k_row_intern<<<uint32_t(std::min<size_t>(rowpages.size(), 65535)), 256, 0, stream>>>(t.d_arena, d_rp.p, uint32_t(rowpages.size()), kt, mode);
+    }
     PQB_CUDA(cudaGetLastError());
     uint32_t cnt[2];
     PQB_CUDA(cudaMemcpyAsync(cnt, counter.p, 8, cudaMemcpyDeviceToHost, stream));
@@ -351,7 +389,7 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
       std::vector<uint32_t> remap(card), nrep(card);
       for (uint32_t i = 0; i < card; i++) { remap[order[i]] = i; nrep[i] = hrep[order[i]]; }
       DevBuf<uint32_t> d_remap; d_remap.upload(remap, stream);
-      k_gid_remap<<<std::min<uint32_t>(1024, (n + 255) / 256), 256, 0, stream>>>(side.d_gid, side.d_gid, n, d_remap.p, card);
+      k_gid_remap<<<std::min<uint32_t>(1024, (n_all + 255) / 256), 256, 0, stream>>>(side.d_gid, side.d_gid, n_all, d_remap.p, card);
       PQB_CUDA(cudaMemcpyAsync(rep.p, nrep.data(), size_t(card) * 4, cudaMemcpyHostToDevice, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
     }
@@ -362,7 +400,7 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
   if (card) {
     DevBuf<uint32_t> lens;
     lens.alloc(card, stream);
-    k_key_lens<<<(card + 255) / 256, 256, 0, stream>>>(t.d_arena, side.d_ent_off, rep.p, card, kkind, lens.p);
+    k_key_lens<<<(card + 255) / 256, 256, 0, stream>>>(t.d_arena, ent, rep.p, card, kkind, lens.p);
     std::vector<uint32_t> hl(card);
     PQB_CUDA(cudaMemcpyAsync(hl.data(), lens.p, card * 4ull, cudaMemcpyDeviceToHost, stream));
     PQB_CUDA(cudaStreamSynchronize(stream));
@@ -374,7 +412,7 @@ void build_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
     doffs.upload(loc.offs, stream);
     DevBuf<uint8_t> dbytes;
     dbytes.alloc(std::max<uint64_t>(tot, 1), stream);
-    k_key_bytes<<<card, 64, 0, stream>>>(t.d_arena, side.d_ent_off, rep.p, card, kkind, doffs.p, dbytes.p);
+    k_key_bytes<<<card, 64, 0, stream>>>(t.d_arena, ent, rep.p, card, kkind, doffs.p, dbytes.p);
     loc.bytes.resize(tot);
     if (tot) PQB_CUDA(cudaMemcpyAsync(loc.bytes.data(), dbytes.p, tot, cudaMemcpyDeviceToHost, stream));
     // the result assembly reads the dictionary on the device
@@ -450,17 +488,18 @@ void unify_key_side(const Table& t, int tcol, ColSide& cs, cudaStream_t stream) 
     p = nullptr;
     PQB_CUDA(cudaMallocAsync((void**)&p, std::max<size_t>(bytes, 16), stream));
   };
-  renew(cs.d_glob_gid, size_t(cs.total_entries) * 4);
+  const uint32_t n_ent = cs.key_entries ? cs.key_entries : cs.total_entries;   // rows of pages without a dictionary are entries too
+  renew(cs.d_glob_gid, size_t(n_ent) * 4);
   renew(cs.d_glob_kd_offs, glob.offs.size() * 4);
   renew(cs.d_glob_kd_bytes, glob.bytes.size());
   PQB_CUDA(cudaMemcpyAsync(cs.d_glob_kd_offs, glob.offs.data(), glob.offs.size() * 4, cudaMemcpyHostToDevice, stream));
   if (!glob.bytes.empty()) PQB_CUDA(cudaMemcpyAsync(cs.d_glob_kd_bytes, glob.bytes.data(), glob.bytes.size(), cudaMemcpyHostToDevice, stream));
   cs.glob_max_len = 0;
   for (size_t g = 0; g + 1 < glob.offs.size(); g++) cs.glob_max_len = std::max(cs.glob_max_len, glob.offs[g + 1] - glob.offs[g]);
-  if (card_l && cs.total_entries) {
+  if (card_l && n_ent) {
     DevBuf<uint32_t> dremap;
     dremap.upload(remap, stream);
-    k_gid_remap<<<std::min<uint32_t>(1024, (cs.total_entries + 255) / 256), 256, 0, stream>>>(cs.d_gid, cs.d_glob_gid, cs.total_entries, dremap.p, card_l);
+    k_gid_remap<<<std::min<uint32_t>(1024, (n_ent + 255) / 256), 256, 0, stream>>>(cs.d_gid, cs.d_glob_gid, n_ent, dremap.p, card_l);
     PQB_CUDA(cudaGetLastError());
   }
   PQB_CUDA(cudaStreamSynchronize(stream));
@@ -927,6 +966,7 @@ void Query::run(const PqQueryDesc& d) {
   // ---- GROUP BY keys: interned per table column (cached with the table) ----
   struct QKey { const KeyDict* kd = nullptr; uint32_t card = 0; bool is_bin = false; };
   std::vector<QKey> qk(d.n_group_by);
+  std::vector<uint8_t> row_keys(d.n_group_by, 0);   // the key column has pages without a dictionary: per-row ids (FK_IDS pages)
   plan.nkeys = d.n_group_by;
   uint64_t launches = 0;
   for (uint32_t k = 0; agg_kernel && k < d.n_group_by; k++) {
@@ -984,8 +1024,18 @@ void Query::run(const PqQueryDesc& d) {
     }
     key.kind = kind == DK_BOOL ? KK_BOOL : KK_DICT_LUT;
     if (key.kind == KK_BOOL) { qk[k].card = 2; continue; }
-    if (plan.cols[key.col].has_plain || plan.cols[key.col].has_delta)
-      throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has PLAIN (dictionary-fallback) pages; only dictionary-encoded keys are on the GPU path");
+    if (plan.cols[key.col].has_plain || plan.cols[key.col].has_delta) {
+      // Pages without a dictionary (PLAIN fallback of an overflowed dictionary, PLAIN / DELTA numerics): ensure_key interns
+      // their ROWS next to the dictionary entries; the aggregate kernel then stages the pages' ids instead of their values,
+      // so nothing else of this query may read the column's values
+      for (uint32_t l = 0; l < nleaves; l++)
+        if (plan.leaves[l].col == key.col && (plan.leaves[l].kind == LK_CMP || plan.leaves[l].kind == LK_LIKE))
+          throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has pages without a dictionary and is also filtered on: not on the GPU path");
+      for (uint32_t a = 0; a < d.n_aggs; a++)
+        if (plan.aggs[a].fn >= AG_SUM && plan.aggs[a].col == key.col)
+          throw Error(PQ_ERR_UNSUPPORTED, "GROUP BY column '" + table->columns[tcol[d.group_by[k]]].name + "' has pages without a dictionary and is also aggregated: not on the GPU path");
+      row_keys[k] = 1;
+    }
     const int tc_i = shape_cols[key.col];
     table->ensure_key(tc_i, stream);
     const ColSide& cs = table->sides[tc_i];
@@ -1007,6 +1057,36 @@ void Query::run(const PqQueryDesc& d) {
       key.gid = cs.d_glob_gid;
       qk[k].kd = &cs.glob_kd;
       qk[k].card = cs.glob_card;
+    }
+  }
+  // ---- id pages of key columns with pages that have no dictionary: this query's copy of the flat page table, with
+  // those pages pointing into the column's id array (local or agreed numbering) ----
+  DevBuf<FlatPageRec> d_kpages;
+  std::vector<uint32_t> key_bw32(ncols, 0);
+  {
+    bool any = false;
+    for (uint32_t k = 0; k < d.n_group_by; k++) any = any || row_keys[k];
+    if (any) {
+      std::vector<FlatPageRec> fp;
+      {
+        std::lock_guard<std::mutex> lk(table->side_mu);
+        fp = table->flat_pages;
+        for (uint32_t k = 0; k < d.n_group_by; k++) {
+          if (!row_keys[k]) continue;
+          const DevKey& key = plan.keys[k];
+          const ColSide& cs = table->sides[shape_cols[key.col]];
+          key_bw32[key.col] = 32;
+          for (const ColSide::KeyRowPage& rp : cs.key_row_pages) {
+            FlatPageRec& r = fp[rp.page];
+            r.fkind = FK_IDS;
+            r.bw = 32;
+            // relative to d_flat like every flat page (the subtraction may wrap, base + offset does not); 16-byte aligned: ebase is a multiple of 4
+            r.off = uint64_t(key.gid) + 4ull * (uint64_t(cs.n_dict_pad) + rp.ebase) - uint64_t(table->d_flat);
+          }
+        }
+      }
+      d_kpages.upload(fp, stream);
+      metrics.h2d_bytes += fp.size() * sizeof(FlatPageRec);
     }
   }
   // mixed-radix group slot: the smallest key varies fastest, so that with hot-first ids of the largest key
@@ -1112,7 +1192,7 @@ void Query::run(const PqQueryDesc& d) {
         FL.col_off[s] = off;
         FL.col_voff[s] = off;
         if (!plan.cols[s].staged) continue;
-        const uint32_t cap = std::max<uint32_t>((shape->flat_plain8[s] && !plan.direct8) ? S * 8 : 0, (S * shape->flat_max_bw[s] + 7) / 8);
+        const uint32_t cap = std::max<uint32_t>((shape->flat_plain8[s] && !plan.direct8) ? S * 8 : 0, (S * std::max(shape->flat_max_bw[s], key_bw32[s]) + 7) / 8);
         off += align_up(cap + 48, 128);   // + the bit phase of a piece that starts inside a page, + over-read slack
         if (shape->flat_nullable[s]) { FL.col_voff[s] = off; off += align_up(S / 8 + 48, 128); }   // validity bits of pages with NULLs
       }
@@ -1260,7 +1340,7 @@ void Query::run(const PqQueryDesc& d) {
   sa.lit_pool = d_lit.p;
   sa.rg_live = pruned ? d_live.p : nullptr;
   sa.flat = table->d_flat;
-  sa.fpages = table->d_flat_pages;
+  sa.fpages = d_kpages.p ? d_kpages.p : table->d_flat_pages;
   sa.bitmap = d_bitmap.p;
   sa.item_counts = d_item_counts.p;
   sa.acc = d_acc.p;

@@ -243,6 +243,7 @@ Table::~Table() {
   for (ColSide& cs : sides) {
     if (cs.d_ent_off) cudaFreeAsync(cs.d_ent_off, cudaStreamPerThread);
     if (cs.d_gid) cudaFreeAsync(cs.d_gid, cudaStreamPerThread);
+    if (cs.d_row_ent) cudaFreeAsync(cs.d_row_ent, cudaStreamPerThread);
     if (cs.d_key_hash) cudaFreeAsync(cs.d_key_hash, cudaStreamPerThread);
     if (cs.d_glob_gid) cudaFreeAsync(cs.d_glob_gid, cudaStreamPerThread);
     if (cs.d_glob_kd_offs) cudaFreeAsync(cs.d_glob_kd_offs, cudaStreamPerThread);

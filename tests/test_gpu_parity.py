@@ -746,9 +746,41 @@ def test_plain_byte_array_pages(data_dir, built):
         assert got[c].to_pylist() == exp[c].to_pylist(), c
     keys, aggs = ["v"], [count_star(), count("message"), count("tag")]
     assert_tables_equal(prov.aggregate(keys, aggs, flts["like_contains"]).table(), ora.group_by(keys, aggs, flts["like_contains"]), keys)
-    with pytest.raises(QueryError) as e:       # group keys need a dictionary (interned ids): refused, never mis-grouped
-        prov.aggregate(["message"], [count_star()])
+    # GROUP BY on pages without a dictionary: the rows are interned next to the dictionary entries of the chunk that
+    # flipped (one numbering for both page kinds), NULL is its own group
+    for keys, aggs, flt in ((["message"], [count_star(), sum_("v"), count("tag")], []),
+                            (["tag"], [count_star(), max_("id")], [col("v") < 50]),
+                            (["tag", "v"], [count_star(), min_("id")], [col("message").like("%db%")]),
+                            (["message", "tag"], [count_star()], [])):                     # 70 001 x 978 combinations: hashed
+        assert_tables_equal(prov.aggregate(keys, aggs, flt).table(), ora.group_by(keys, aggs, flt), keys)
+    with pytest.raises(QueryError) as e:       # the id pages stand in for the values: filtering the same column is refused, never mis-evaluated
+        prov.aggregate(["message"], [count_star()], [col("message").like("%ok%")])
     assert e.value.code == L.PQ_ERR_UNSUPPORTED
+
+
+def test_group_by_numeric_columns_without_dictionary(data_dir, built):
+    """GROUP BY on PLAIN Int64 / Float64 pages and on the DELTA_BINARY_PACKED time column (no dictionary anywhere):
+    every row is interned by value; field statistics run exactly such queries over every field
+    (src/storage/field_stats.rs:298-330)."""
+    rng = np.random.default_rng(31)
+    n = 150_000
+    ts = (1_700_000_000_000 - np.cumsum(rng.integers(0, 2, n))).astype(np.int64)          # long runs of equal stamps
+    x = np.round(rng.standard_normal(n), 1) + 0.0                                          # ~80 distinct doubles (no -0.0: it would sort next to 0.0)
+    v = rng.integers(-40, 40, n).astype(np.int64) * 10**12
+    xs = pa.array(np.where(rng.random(n) < 0.05, None, x), pa.float64(), from_pandas=True)
+    t = pa.table({"p_timestamp": pa.array(ts, pa.timestamp("ms")), "v": pa.array(v), "x": xs,
+                  "s": pa.array(rng.choice(["a", "bb", "ccc"], n)), "w": pa.array(rng.integers(0, 1000, n).astype(np.int64))})
+    p = os.path.join(data_dir, "plain_numeric_keys.parquet")
+    pq.write_table(t, p, compression="NONE", row_group_size=60_000, use_dictionary=["s"],
+                   column_encoding={"p_timestamp": "DELTA_BINARY_PACKED", "v": "PLAIN", "x": "PLAIN", "w": "PLAIN"}, data_page_size=128 << 10)
+    ora = Oracle(t)
+    prov = StandardTableProvider([p], schema=t.schema)
+    for keys, aggs, flt in ((["v"], [count_star(), sum_("w"), min_("x")], []),
+                            (["x"], [count_star(), max_("w")], [col("s") != "a"]),
+                            (["p_timestamp"], [count_star(), sum_("w")], []),
+                            (["s", "v"], [count_star(), avg("w"), min_("x")], [col("w") < 500]),   # (AVG of the symmetric x cancels to ~1e-17: no relative tolerance fits)
+                            (["v", "w", "p_timestamp"], [count_star(), max_("x")], [])):    # 80 x 1000 x ~75 000 combinations: hashed
+        assert_tables_equal(prov.aggregate(keys, aggs, flt).table(), ora.group_by(keys, aggs, flt), keys)
 
 
 # ---- the counts / histogram API: GROUP BY DATE_BIN(width, p_timestamp, origin) (src/query/mod.rs:623-680) ----
