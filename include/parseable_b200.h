@@ -257,6 +257,13 @@ int pq_query_next(PqQuery* q, int partition, struct ArrowArray* out, struct Arro
  * it (or drain it) before pq_query_close; the batches it produced stay valid on their own. */
 int pq_query_stream(PqQuery* q, int partition, struct ArrowArrayStream* out);
 int pq_query_metrics(PqQuery* q, PqMetrics* out);
+/* The whole result (every batch, whatever pq_query_next already handed out) as JSON text formatted on the GPU: what
+ * QueryResponse::to_json builds from the batches on the CPU (src/response.rs:31-58, src/utils/arrow/mod.rs:49-64:
+ * arrow_json::ArrayWriter conventions -- NULL values leave their key out, Timestamp(ms) as ISO-8601, floats shortest
+ * round-trip).  flags 0: one JSON array `[{...},{...}]`; PQ_JSON_LINES: one object per line (NDJSON).  *out stays valid
+ * until the next pq_query_json call on q or pq_query_close. */
+#define PQ_JSON_LINES 1u
+int pq_query_json(PqQuery* q, uint32_t flags, const char** out, uint64_t* len);
 const char* pq_last_error(PqQuery* q); /* q == NULL: last error of the calling thread */
 void pq_query_close(PqQuery* q);
 

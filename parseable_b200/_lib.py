@@ -25,6 +25,7 @@ PQ_EQ, PQ_NE, PQ_LT, PQ_LE, PQ_GT, PQ_GE = range(6)
 PQ_LIKE_NEGATED, PQ_LIKE_CASE_INSENSITIVE = 1, 2
 PQ_AGG_COUNT_STAR, PQ_AGG_COUNT, PQ_AGG_SUM, PQ_AGG_MIN, PQ_AGG_MAX, PQ_AGG_AVG = range(6)
 PQ_QUERY_COUNT_ONLY, PQ_QUERY_ALLREDUCE, PQ_QUERY_EMIT_ROW_IDS = 1, 2, 4
+PQ_JSON_LINES = 1
 PQ_COMM_ID_BYTES = 128
 
 
@@ -138,7 +139,7 @@ class ArrowArrayStream(C.Structure):
 EXPORTS = [
     "pq_init", "pq_shutdown", "pq_version", "pq_device_count",
     "pq_table_open", "pq_table_rows", "pq_table_device_bytes", "pq_table_close",
-    "pq_query_open", "pq_query_next", "pq_query_stream", "pq_query_metrics", "pq_last_error", "pq_query_close",
+    "pq_query_open", "pq_query_next", "pq_query_stream", "pq_query_json", "pq_query_metrics", "pq_last_error", "pq_query_close",
     "pq_comm_unique_id", "pq_comm_init_rank", "pq_comm_destroy",
     "pq_host_alloc", "pq_host_free", "pq_file_describe",
     "pq_plan_time_bounds", "pq_plan_manifests", "pq_plan_is_overlapping_query", "pq_plan_within_staging_window",
@@ -182,6 +183,8 @@ def load() -> C.CDLL:
     lib.pq_query_next.restype = C.c_int
     lib.pq_query_stream.argtypes = [C.c_void_p, C.c_int, C.POINTER(ArrowArrayStream)]
     lib.pq_query_stream.restype = C.c_int
+    lib.pq_query_json.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.pq_query_json.restype = C.c_int
     lib.pq_query_metrics.argtypes = [C.c_void_p, C.POINTER(PqMetrics)]
     lib.pq_query_metrics.restype = C.c_int
     lib.pq_last_error.argtypes = [C.c_void_p]

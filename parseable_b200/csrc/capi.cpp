@@ -158,6 +158,11 @@ int pq_query_stream(PqQuery* q, int partition, struct ArrowArrayStream* out) {
   return PQ_OK;
 }
 
+int pq_query_json(PqQuery* q, uint32_t flags, const char** out, uint64_t* len) {
+  if (!q || !q->q || !out || !len) return PQ_ERR_INVALID_ARG;
+  return guard([&] { q->q->json(flags, out, len); return PQ_OK; }, &q->error);
+}
+
 int pq_query_metrics(PqQuery* q, PqMetrics* out) {
   if (!q || !q->q || !out) return PQ_ERR_INVALID_ARG;
   *out = q->q->metrics;

@@ -242,6 +242,7 @@ void unify_key_side(const Table& t, int tcol, ColSide& side, cudaStream_t stream
 struct PinnedBlock {
   uint8_t* p = nullptr;
   size_t bytes = 0;
+  uint8_t* dev = nullptr;   // the device block this one was copied from, while the query keeps it (JSON egress reads it there)
   ~PinnedBlock();
 };
 
@@ -271,6 +272,9 @@ class Query {
   ~Query();
   int next(int partition, ArrowArray* out, ArrowSchema* schema);
   void schema(ArrowSchema* out) const;   // of the result batches (an empty struct when the query produced none)
+  // every batch of the result as JSON text formatted on the device (json_egress.cuh); the bytes stay valid until the
+  // next call or the query is closed
+  void json(uint32_t flags, const char** out, uint64_t* len);
   PqMetrics metrics{};
   std::string error;
 
@@ -278,6 +282,9 @@ class Query {
   void run(const PqQueryDesc& d);
   std::unique_ptr<Table> owned_table_;
   std::vector<OutBatch> batches_;
+  std::vector<std::shared_ptr<PinnedBlock>> dev_blocks_;   // result blocks whose device copy is kept until the query closes
+  std::shared_ptr<PinnedBlock> json_block_;
+  uint32_t batch_rows_ = 20000;
   size_t next_batch_ = 0;
   bool schema_only_done_ = false;
 };

@@ -26,6 +26,7 @@
 #include "prep_kernels.cuh"
 #include "scan_kernel.cuh"
 #include "flat_scan.cuh"
+#include "json_egress.cuh"
 #include "egress_kernels.cuh"
 
 namespace pqb {
@@ -38,6 +39,7 @@ struct DevBuf {
   size_t n = 0;
   cudaStream_t s = nullptr;
   void alloc(size_t count, cudaStream_t stream) {
+    if (p) { cudaFreeAsync(p, s); p = nullptr; }   // a second alloc (a retry with a larger capacity) replaces the first
     n = count;
     s = stream;
     if (count) PQB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), stream));
@@ -49,6 +51,8 @@ struct DevBuf {
   void zero() { if (n) PQB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   ~DevBuf() { if (p) cudaFreeAsync(p, s); }
 };
+
+constexpr uint64_t kKeepDeviceResult = 1ull << 30;   // result blocks up to this size stay on the device until the query closes
 
 struct Timer {
   cudaEvent_t a, b;
@@ -193,7 +197,10 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) & ~(a - 1); }
 Query::Query(const PqQueryDesc& d) {
   run(d);
 }
-Query::~Query() = default;
+Query::~Query() {
+  for (auto& b : dev_blocks_)
+    if (b && b->dev) { cudaFree(b->dev); b->dev = nullptr; }
+}
 
 void launch_slab_index(const uint8_t* arena, const DevPage* pages, uint32_t n_pages, const uint32_t* col_caps, DevSlabRec* recs,
                        DirEntry* dirs, uint8_t* page_fast, cudaStream_t stream) {
@@ -1415,6 +1422,7 @@ void Query::run(const PqQueryDesc& d) {
 
   // ---- results ----
   const uint32_t batch_rows = d.batch_size ? d.batch_size : 20000;
+  batch_rows_ = batch_rows;
   unsigned long long h_counters[4] = {0, 0, 0, 0};
   if (agg_kernel) {
     // multi-GPU: the partial tables meet in ONE grouped all-reduce: one NCCL launch,
@@ -1573,6 +1581,7 @@ void Query::run(const PqQueryDesc& d) {
       PQB_CUDA(cudaMemcpyAsync(block->p, d_block.p, copy_bytes, cudaMemcpyDeviceToHost, stream));
       PQB_CUDA(cudaEventRecord(t_all.b, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
+      if (copy_bytes <= kKeepDeviceResult) { block->dev = d_block.p; d_block.p = nullptr; dev_blocks_.push_back(block); }   // JSON egress formats it where it is
       metrics.d2h_bytes += copy_bytes;
       metrics.groups = n_out;
       const uint32_t* nulls = reinterpret_cast<const uint32_t*>(block->p + nulls_off);
@@ -1735,6 +1744,7 @@ void Query::run(const PqQueryDesc& d) {
       PQB_CUDA(cudaEventRecord(t_all.b, stream));
       PQB_CUDA(cudaStreamSynchronize(stream));
       if (h_counters[1]) throw Error(PQ_ERR_CORRUPT, "corrupt or unsupported page encoding met on the device (code " + std::to_string(h_counters[1]) + ")");
+      if (block && d_block.p && copy_bytes <= kKeepDeviceResult) { block->dev = d_block.p; d_block.p = nullptr; dev_blocks_.push_back(block); }
       metrics.rows_selected = total;
       const uint32_t out_batches = n_rows ? uint32_t((n_rows + batch_rows - 1) / batch_rows) : 1u;
       for (uint32_t b = 0; b < out_batches; b++) {
@@ -1860,6 +1870,103 @@ void Query::schema(ArrowSchema* out) const {
   if (!batches_.empty()) { export_batch(batches_[0], nullptr, out); return; }
   OutBatch none;
   export_batch(none, nullptr, out);
+}
+
+// JSON egress (json_egress.cuh): all batches of the result, formatted on the device.
+void Query::json(uint32_t flags, const char** out, uint64_t* len) {
+  Context& ctx = Context::get();
+  cudaStream_t stream = cudaStreamPerThread;
+  const bool lines = (flags & PQ_JSON_LINES) != 0;
+  unsigned long long n = 0;
+  for (const OutBatch& b : batches_) n += uint64_t(b.rows);
+  json_block_.reset();
+  auto finish_empty = [&]() {
+    json_block_ = std::make_shared<PinnedBlock>();
+    json_block_->p = ctx.pinned_acquire(16);
+    json_block_->bytes = lines ? 0 : 2;
+    if (!lines) { json_block_->p[0] = '['; json_block_->p[1] = ']'; }
+    *out = reinterpret_cast<const char*>(json_block_->p);
+    *len = json_block_->bytes;
+  };
+  if (n == 0 || batches_.empty() || batches_[0].cols.empty()) { finish_empty(); return; }
+  const OutBatch* first = nullptr;
+  for (const OutBatch& b : batches_) if (b.rows) { first = &b; break; }
+  const size_t ncols = first->cols.size();
+  if (ncols > size_t(kJsonMaxCols)) throw Error(PQ_ERR_UNSUPPORTED, "JSON egress: more than 64 result columns");
+  JsonArgs ja{};
+  ja.ncols = uint32_t(ncols);
+  ja.n_rows = n;
+  ja.lines = lines ? 1u : 0u;
+  ja.batch_rows = batch_rows_;
+  ja.words_per_batch = (batch_rows_ + 31) / 32;
+  size_t nonempty = 0;
+  for (const OutBatch& b : batches_) nonempty += b.rows ? 1 : 0;
+  std::vector<uint8_t> keys;
+  std::vector<DevBuf<uint8_t>> temps(ncols * 3);
+  for (size_t c = 0; c < ncols; c++) {
+    const OutColumn& oc = first->cols[c];
+    JsonCol& jc = ja.cols[c];
+    jc.type = oc.type == PQ_T_F64 ? JT_F64 : oc.type == PQ_T_BOOL ? JT_BOOL : oc.type == PQ_T_UTF8 ? JT_UTF8 : oc.type == PQ_T_TS_MS ? JT_TS_MS : JT_I64;
+    // "name": with the name escaped like any string
+    jc.key_off = uint32_t(keys.size());
+    keys.push_back('"');
+    { std::vector<char> e(oc.name.size() * 6 + 1);
+      const uint32_t k = jf_escape(reinterpret_cast<const uint8_t*>(oc.name.data()), uint32_t(oc.name.size()), e.data());
+      keys.insert(keys.end(), e.begin(), e.begin() + k); }
+    keys.push_back('"'); keys.push_back(':');
+    jc.key_len = uint32_t(keys.size()) - jc.key_off;
+    bool any_nulls = false;
+    for (const OutBatch& b : batches_) if (b.rows) any_nulls = any_nulls || b.cols[c].null_count != 0;
+    if (oc.ext_all) {
+      // device-assembled result: one regular layout over all batches (values and offsets contiguous, bit-packed buffers per batch)
+      const uint8_t* base = oc.ext->dev ? oc.ext->dev : oc.ext->p;   // the kept device block, or the mapped page-locked copy
+      jc.values = base + oc.ext_off;
+      jc.validity = any_nulls ? reinterpret_cast<const uint32_t*>(base + oc.ext_validity_off) : nullptr;
+      jc.offsets = oc.type == PQ_T_UTF8 ? reinterpret_cast<const int32_t*>(base + oc.ext_offsets_off) : nullptr;
+    } else if (oc.ext) {
+      if (oc.null_count || oc.type == PQ_T_UTF8 || oc.type == PQ_T_BOOL) throw Error(PQ_ERR_UNSUPPORTED, "JSON egress: result layout not supported");
+      jc.values = oc.ext->p + oc.ext_off;   // 8-byte values of all batches, contiguous (row ids)
+    } else {
+      // a small host-built batch (a global aggregate over zero rows, COUNT(*) only): its buffers go up as they are
+      if (nonempty != 1) throw Error(PQ_ERR_UNSUPPORTED, "JSON egress: result layout not supported");
+      ja.batch_rows = 0x7fffffffu;
+      ja.words_per_batch = 0;
+      std::vector<uint8_t> v = oc.values;
+      if (v.empty()) v.assign(8, 0);
+      temps[3 * c].upload(v, stream);
+      jc.values = temps[3 * c].p;
+      if (oc.null_count) { temps[3 * c + 1].upload(oc.validity, stream); jc.validity = reinterpret_cast<const uint32_t*>(temps[3 * c + 1].p); }
+      if (oc.type == PQ_T_UTF8) {
+        std::vector<uint8_t> o(oc.offsets.size() * 4);
+        std::memcpy(o.data(), oc.offsets.data(), o.size());
+        temps[3 * c + 2].upload(o, stream);
+        jc.offsets = reinterpret_cast<const int32_t*>(temps[3 * c + 2].p);
+      }
+    }
+  }
+  DevBuf<uint8_t> d_keys; d_keys.upload(keys, stream);
+  ja.keys = d_keys.p;
+  DevBuf<uint32_t> d_lens; d_lens.alloc(n, stream);
+  DevBuf<long long> d_offs; d_offs.alloc(n + 1, stream);
+  const uint32_t grid = uint32_t((n + 255) / 256);
+  k_json_sizes<<<grid, 256, 0, stream>>>(ja, d_lens.p);
+  k_json_scan<<<1, 1024, 0, stream>>>(d_lens.p, n, d_offs.p, lines ? 0 : 1);
+  long long total = 0;
+  PQB_CUDA(cudaMemcpyAsync(&total, d_offs.p + n, 8, cudaMemcpyDeviceToHost, stream));
+  PQB_CUDA(cudaStreamSynchronize(stream));
+  DevBuf<char> d_out; d_out.alloc(size_t(total) + 16, stream);
+  k_json_write<<<grid, 256, 0, stream>>>(ja, d_offs.p, d_out.p);
+  PQB_CUDA(cudaGetLastError());
+  json_block_ = std::make_shared<PinnedBlock>();
+  json_block_->p = ctx.pinned_acquire(size_t(total) + 16);
+  json_block_->bytes = size_t(total);
+  PQB_CUDA(cudaMemcpyAsync(json_block_->p, d_out.p, size_t(total), cudaMemcpyDeviceToHost, stream));
+  PQB_CUDA(cudaStreamSynchronize(stream));
+  if (!lines) { json_block_->p[0] = '['; json_block_->p[total - 1] = ']'; }   // the last row's ',' closes the array
+  metrics.d2h_bytes += uint64_t(total);
+  metrics.kernel_launches += 3;
+  *out = reinterpret_cast<const char*>(json_block_->p);
+  *len = uint64_t(total);
 }
 
 int Query::next(int partition, ArrowArray* out, ArrowSchema* schema) {

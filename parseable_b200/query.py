@@ -333,6 +333,21 @@ class QueryResult:
     batches: list[pa.RecordBatch]
     metrics: dict
     fields: list[str] = field(default_factory=list)
+    json_text: bytes | None = None      # the result as JSON text formatted on the GPU (pq_query_json), when asked for
+
+    def to_json(self, with_fields: bool = False, fill_null: bool = False):
+        """QueryResponse::to_json (src/response.rs:31-58) over the GPU-formatted records: the list of row objects,
+        optionally with every field present (NULL filled in) and wrapped with the field list."""
+        import json as _json
+        if self.json_text is None:
+            raise ValueError("run the query with json='array' or json='lines'")
+        txt = self.json_text.decode()
+        rows = _json.loads(txt) if txt.startswith("[") else [_json.loads(line) for line in txt.splitlines() if line]
+        if fill_null:
+            for r in rows:
+                for f in self.fields:
+                    r.setdefault(f, None)
+        return {"fields": self.fields, "records": rows} if with_fields else rows
 
     def table(self) -> pa.Table:
         if not self.batches:
@@ -373,7 +388,7 @@ class StandardTableProvider:
     # -- TableProvider::scan -------------------------------------------------
     def scan(self, projection: Sequence[str] | None = None, filters: Iterable[Expr] = (), limit: int | None = None,
              count_only: bool = False, row_ids: bool | None = None, batch_size: int = 0, flags: int = 0,
-             poll: bool = False) -> QueryResult:
+             poll: bool = False, json: str | None = None) -> QueryResult:
         """``projection``: the columns to return for the selected rows (TableProvider::scan's projection);
         without one the scan returns the selected row ordinals (``__row_id``).  ``row_ids=True`` appends
         ``__row_id`` to a projection."""
@@ -384,12 +399,12 @@ class StandardTableProvider:
             f |= L.PQ_QUERY_COUNT_ONLY
         elif row_ids:
             f |= L.PQ_QUERY_EMIT_ROW_IDS
-        return self._run(list(filters), [], [], list(projection or []), limit, batch_size, f | flags, poll=poll)
+        return self._run(list(filters), [], [], list(projection or []), limit, batch_size, f | flags, poll=poll, json=json)
 
     # -- FilterExec + AggregateExec folded into the same call ----------------
     def aggregate(self, group_by: Sequence[str], aggs: Sequence[Agg], filters: Iterable[Expr] = (),
-                  batch_size: int = 0, flags: int = 0) -> QueryResult:
-        return self._run(list(filters), list(group_by), list(aggs), [], None, batch_size, flags)
+                  batch_size: int = 0, flags: int = 0, json: str | None = None) -> QueryResult:
+        return self._run(list(filters), list(group_by), list(aggs), [], None, batch_size, flags, json=json)
 
     def count_distinct(self, group_by: Sequence[str], column: str, filters: Iterable[Expr] = ()) -> pa.Table:
         """``SELECT keys, COUNT(DISTINCT column)`` (Parseable's alerts use it: src/alerts/alert_enums.rs:216-223).
@@ -411,7 +426,7 @@ class StandardTableProvider:
         cols[name] = pa.array(list(seen.values()), pa.int64())
         return pa.table(cols)
 
-    def _run(self, filters, group_by, aggs, projection, limit, batch_size, flags, poll: bool = False) -> QueryResult:
+    def _run(self, filters, group_by, aggs, projection, limit, batch_size, flags, poll: bool = False, json: str | None = None) -> QueryResult:
         lib = L.load()
         d = _Desc()
         ops: list = []
@@ -489,11 +504,18 @@ class StandardTableProvider:
                     batches = list(pa.RecordBatchReader._import_from_c(C.addressof(stream_c)))
                 except pa.ArrowException as e:
                     raise QueryError(L.PQ_ERR_CUDA, (lib.pq_last_error(h) or str(e).encode()).decode()) from e
+            json_text = None
+            if json is not None:      # the same result as JSON text, formatted on the GPU
+                jp, jn = C.c_void_p(), C.c_uint64()
+                rc = lib.pq_query_json(h, L.PQ_JSON_LINES if json == "lines" else 0, C.byref(jp), C.byref(jn))
+                if rc != L.PQ_OK:
+                    raise QueryError(rc, (lib.pq_last_error(h) or b"").decode())
+                json_text = C.string_at(jp.value, jn.value) if jn.value else b""
             m = L.PqMetrics()
             lib.pq_query_metrics(h, C.byref(m))
         finally:
             lib.pq_query_close(h)
-        return QueryResult(batches, m.as_dict(), [f.name for f in batches[0].schema] if batches else [])
+        return QueryResult(batches, m.as_dict(), [f.name for f in batches[0].schema] if batches else [], json_text)
 
 
 # ----------------------------------------------------------------------------- Query / execute

@@ -802,3 +802,79 @@ def test_date_bin_counts(env, tag):
     rng_f = [col("p_timestamp") >= Timestamp(lo), col("p_timestamp") < Timestamp(hi)]
     got = prov.aggregate([date_bin("1m")], [count_star()], rng_f).table()
     assert_tables_equal(got, ora.group_by([date_bin("1m")], [count_star()], rng_f), ["date_bin(p_timestamp)"])
+
+
+# ---- JSON egress formatted on the device (pq_query_json; the reference: record_batches_to_json + QueryResponse::to_json,
+#      src/utils/arrow/mod.rs:49-64, src/response.rs:31-58) ----
+def _json_expect(table: pa.Table):
+    """Rows the way arrow_json::ArrayWriter writes them: NULL values leave their key out, non-finite floats are null,
+    Timestamp(ms) is chrono's NaiveDateTime text."""
+    import datetime as dt
+    cols = {n: table[n].to_pylist() for n in table.column_names}
+    ts_cols = {n for n in table.column_names if pa.types.is_timestamp(table.schema.field(n).type)}
+    raw_ts = {n: table[n].cast(pa.int64()).to_pylist() for n in ts_cols}
+    rows = []
+    for i in range(table.num_rows):
+        r = {}
+        for n in table.column_names:
+            v = cols[n][i]
+            if v is None:
+                continue
+            if n in ts_cols:
+                ms = raw_ts[n][i]
+                t = dt.datetime(1970, 1, 1) + dt.timedelta(milliseconds=ms)
+                v = t.strftime("%Y-%m-%dT%H:%M:%S") + (f".{ms % 1000:03d}" if ms % 1000 else "")
+            elif isinstance(v, float) and (math.isnan(v) or math.isinf(v)):
+                v = None
+            r[n] = v
+        rows.append(r)
+    return rows
+
+
+@pytest.mark.gpu
+def test_json_egress_on_device(data_dir, built):
+    rng = np.random.default_rng(41)
+    n = 50_000
+    ts = (1_700_000_000_000 - np.cumsum(rng.integers(0, 3, n)) * 250).astype(np.int64)      # some stamps on whole seconds, some not
+    x = rng.standard_normal(n) * 10.0 ** rng.integers(-8, 18, n)
+    x[rng.random(n) < 0.01] = np.nan
+    x[rng.random(n) < 0.005] = np.inf
+    s = rng.choice(np.array(['plain', 'quote " \\ back', "tab\tnl\n", "δέλτα ✓ 😀", "", "ctl\x01\x1f", "a/b"], dtype=object), n)
+    s[rng.random(n) < 0.05] = None
+    t = pa.table({"p_timestamp": pa.array(ts, pa.timestamp("ms")),
+                  "x": pa.array(np.where(rng.random(n) < 0.03, None, x), pa.float64(), from_pandas=False),
+                  "v": pa.array(rng.integers(-2**62, 2**62, n).astype(np.int64)),
+                  "flag": pa.array(np.where(rng.random(n) < 0.1, None, rng.random(n) < 0.5), pa.bool_()),
+                  "s": pa.array(s, pa.string()), "k": pa.array(rng.integers(0, 7, n).astype(np.int64))})
+    p = os.path.join(data_dir, "json_egress.parquet")
+    pq.write_table(t, p, compression="NONE", row_group_size=20_000, use_dictionary=["s", "k"],
+                   column_encoding={"p_timestamp": "DELTA_BINARY_PACKED", "x": "PLAIN", "v": "PLAIN"}, data_page_size=64 << 10)
+    ora = Oracle(t)
+    prov = StandardTableProvider([p], schema=t.schema)
+    flt = [col("k") < 5]
+    for mode in ("array", "lines"):
+        res = prov.scan(projection=t.column_names, filters=flt, batch_size=7_000, json=mode)       # several batches, one text
+        assert res.json_text[:1] == (b"[" if mode == "array" else b"{")
+        got = res.to_json()
+        exp = _json_expect(res.table())
+        assert len(got) == len(exp) == ora.count(flt) > 30_000
+        assert got == exp
+    # floats print shortest round-trip: the text parses back to the very same doubles (checked above through ==), and no
+    # longer than repr
+    txt = prov.scan(projection=["x"], filters=[col("k") == 1], json="lines").json_text.decode()
+    for line, v in zip(txt.splitlines()[:2000], [r for r in prov.scan(projection=["x"], filters=[col("k") == 1]).table()["x"].to_pylist()][:2000]):
+        if v is not None and math.isfinite(v):
+            assert len(line) <= len('{"x":' + repr(v) + "}") + 2, (line, v)
+    # aggregate results (assembled on the device, formatted where they are), NULL group included; row ids; empty results
+    keys, aggs = ["s", "flag"], [count_star(), sum_("v"), min_("x"), avg("k"), max_("v")]
+    res = prov.aggregate(keys, aggs, [col("k") > 0], json="array")
+    srt = lambda rows: sorted(rows, key=lambda r: json.dumps(r, sort_keys=True))   # noqa: E731
+    assert srt(res.to_json()) == srt(_json_expect(res.table()))
+    filled = res.to_json(with_fields=True, fill_null=True)
+    assert filled["fields"] == res.table().column_names and all(set(r) == set(filled["fields"]) for r in filled["records"])
+    res = prov.scan(filters=[col("k") == 6], json="lines")
+    assert [r["__row_id"] for r in res.to_json()] == list(ora.row_ids([col("k") == 6]))
+    assert prov.scan(projection=["v"], filters=[col("k") == 99], json="array").json_text == b"[]"
+    assert prov.scan(projection=["v"], filters=[col("k") == 99], json="lines").json_text == b""
+    res = prov.aggregate([], [count_star(), sum_("v")], [col("k") == 99], json="array")              # one host-built row: COUNT 0, SUM NULL
+    assert res.to_json() == [{"count(*)": 0}]
