@@ -40,7 +40,7 @@ oracle/liboracle.so: oracle/oracle.c
 tools: tools/libdecode_core_host.so tools/libzstd_host.so tools/libjson_host.so
 tools/libjson_host.so: tools/json_host.cpp $(CSRC)/json_egress.cuh $(CSRC)/ryu_f64.cuh $(CSRC)/ryu_tables.inc
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -Wno-maybe-uninitialized -I$(CSRC) -o $@ $<
-tools/libzstd_host.so: tools/zstd_host.cpp $(CSRC)/zstd_decode.cuh
+tools/libzstd_host.so: tools/zstd_host.cpp $(CSRC)/zstd_decode.cuh $(CSRC)/inflate_decode.cuh
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -I$(CSRC) -o $@ $<
 tools/libdecode_core_host.so: tools/decode_core_host.cpp $(CSRC)/decode_core.cuh $(CSRC)/device_structs.hpp
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Wall -I$(CSRC) -o $@ $<

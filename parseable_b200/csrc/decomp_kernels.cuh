@@ -1,6 +1,6 @@
 // Page decompression on the GPU: LZ4_RAW (Parseable's default codec,
 // /root/reference/src/cli.rs:441-448), SNAPPY (what the reference's CI pins,
-// docker-compose-test.yaml:45) and ZSTD (zstd_decode.cuh; k_decompress_zstd below).  The reference gets these from the lz4_flex 0.13 /
+// docker-compose-test.yaml:45), ZSTD and GZIP (zstd_decode.cuh, inflate_decode.cuh; k_decompress_zstd below).  The reference gets these from the lz4_flex 0.13 /
 // snap 1.1 crates through parquet 58.1.0; here one warp
 // decodes one page: every lane parses the (tiny) sequence headers redundantly — the
 // loads broadcast — and the 32 lanes share the literal / match copies.
@@ -13,6 +13,7 @@
 #include <cstdint>
 
 #include "device_structs.hpp"
+#include "inflate_decode.cuh"
 #include "zstd_decode.cuh"
 
 namespace pqb {
@@ -174,20 +175,25 @@ __global__ void k_decompress_pages(const DecompJob* __restrict__ jobs, uint32_t 
   if ((bad || dp != dn) && lane == 0) atomicExch(&counters[0], 1ull);
 }
 
-// ZSTD pages (codec 6): persistent warps draw pages from a counter; every warp owns one ZstdWs (tables + the literals
-// of one block) in global memory.  zstd_decode.cuh holds the format.
+// ZSTD (codec 6) and GZIP (codec 2) pages: persistent warps draw pages from a counter; every warp owns one workspace
+// (tables + the literals of one zstd block) in global memory.  zstd_decode.cuh / inflate_decode.cuh hold the formats.
+union HeavyWs {
+  ZstdWs z;
+  InflateWs g;
+};
 __global__ void __launch_bounds__(128) k_decompress_zstd(const DecompJob* __restrict__ jobs, uint32_t njobs, const uint8_t* __restrict__ src_base,
                                                          uint8_t* __restrict__ arena, unsigned long long* __restrict__ counters,
-                                                         ZstdWs* __restrict__ ws, unsigned int* __restrict__ next) {
+                                                         HeavyWs* __restrict__ ws, unsigned int* __restrict__ next) {
   const uint32_t lane = threadIdx.x & 31;
-  ZstdWs& w = ws[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)];
+  HeavyWs& w = ws[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)];
   for (;;) {
     uint32_t j = 0;
     if (lane == 0) j = atomicAdd(next, 1u);
     j = __shfl_sync(0xffffffffu, j, 0);
     if (j >= njobs) break;
     const DecompJob job = jobs[j];
-    const bool ok = zstd_decode(w, src_base + job.src_off, job.src_len, arena + job.dst_off, job.dst_len);
+    const bool ok = job.codec == 2u ? gzip_decode(w.g, src_base + job.src_off, job.src_len, arena + job.dst_off, job.dst_len)
+                                    : zstd_decode(w.z, src_base + job.src_off, job.src_len, arena + job.dst_off, job.dst_len);
     if (!ok && lane == 0) atomicExch(&counters[0], 1ull);
     __syncwarp();
   }

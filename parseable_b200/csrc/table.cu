@@ -488,9 +488,9 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
         if (leaf_of[c] < 0) continue;
         const ColumnChunkMeta& cm = g.columns[leaf_of[c]];
         const bool compressed = cm.codec != CODEC_UNCOMPRESSED;
-        if (compressed && cm.codec != CODEC_LZ4_RAW && cm.codec != CODEC_SNAPPY && cm.codec != CODEC_ZSTD)
+        if (compressed && cm.codec != CODEC_LZ4_RAW && cm.codec != CODEC_SNAPPY && cm.codec != CODEC_ZSTD && cm.codec != CODEC_GZIP)
           throw Error(PQ_ERR_UNSUPPORTED, "column '" + col_names[c] + "': page compression codec " + std::to_string(cm.codec) +
-                                              " is not decoded on the GPU (LZ4_RAW, SNAPPY, ZSTD and UNCOMPRESSED are)");
+                                              " is not decoded on the GPU (LZ4_RAW, SNAPPY, ZSTD, GZIP and UNCOMPRESSED are)");
         tc.present = true;
         tc.leaf = leaf_of[c];
         tc.meta = &cm;
@@ -727,7 +727,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
   mark("uploads queued (synchronised for this mark)");
   DecompJob* d_djobs = nullptr;
   unsigned long long* d_dflag = nullptr;
-  ZstdWs* d_zws = nullptr;
+  HeavyWs* d_zws = nullptr;
   unsigned int* d_znext = nullptr;
   unwind.own(d_djobs);
   unwind.own(d_dflag);
@@ -737,15 +737,15 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     PQB_CUDA(cudaMallocAsync((void**)&d_djobs, djobs.size() * sizeof(DecompJob), stream));
     PQB_CUDA(cudaMallocAsync((void**)&d_dflag, 8, stream));
     PQB_CUDA(cudaMemsetAsync(d_dflag, 0, 8, stream));
-    // ZSTD pages are sorted behind the others: their decoder is a kernel of its own (persistent warps, one workspace each)
-    const uint32_t n_other = uint32_t(std::stable_partition(djobs.begin(), djobs.end(), [](const DecompJob& j) { return j.codec != uint32_t(CODEC_ZSTD); }) - djobs.begin());
+    // ZSTD / GZIP pages are sorted behind the others: their decoders are a kernel of their own (persistent warps, one workspace each)
+    const uint32_t n_other = uint32_t(std::stable_partition(djobs.begin(), djobs.end(), [](const DecompJob& j) { return j.codec != uint32_t(CODEC_ZSTD) && j.codec != uint32_t(CODEC_GZIP); }) - djobs.begin());
     const uint32_t n_zstd = uint32_t(djobs.size()) - n_other;
     PQB_CUDA(cudaMemcpyAsync(d_djobs, djobs.data(), djobs.size() * sizeof(DecompJob), cudaMemcpyHostToDevice, stream));
     if (n_other) k_decompress_pages<<<(n_other + 3) / 4, 128, 0, stream>>>(d_djobs, n_other, d_comp, d_arena, d_dflag);
     PQB_CUDA(cudaGetLastError());
     if (n_zstd) {
       const uint32_t blocks = std::min<uint32_t>((n_zstd + 3) / 4, uint32_t(ctx.sm_count()) * 2u);
-      PQB_CUDA(cudaMallocAsync((void**)&d_zws, size_t(blocks) * 4 * sizeof(ZstdWs), stream));
+      PQB_CUDA(cudaMallocAsync((void**)&d_zws, size_t(blocks) * 4 * sizeof(HeavyWs), stream));
       PQB_CUDA(cudaMallocAsync((void**)&d_znext, 4, stream));
       PQB_CUDA(cudaMemsetAsync(d_znext, 0, 4, stream));
       k_decompress_zstd<<<blocks, 128, 0, stream>>>(d_djobs + n_other, n_zstd, d_comp, d_arena, d_dflag, d_zws, d_znext);
@@ -823,7 +823,7 @@ void Table::open(const PqFile* in_files, uint32_t n_files, const std::vector<std
     dev_drop(d_zws, stream);
     dev_drop(d_znext, stream);
     dev_drop(d_comp, stream);
-    if (flag) throw Error(PQ_ERR_CORRUPT, "a compressed page did not decode to its declared size (LZ4_RAW / SNAPPY / ZSTD)");
+    if (flag) throw Error(PQ_ERR_CORRUPT, "a compressed page did not decode to its declared size (LZ4_RAW / SNAPPY / ZSTD / GZIP)");
     for (size_t j = 0; j < jobs.size(); j++)
       if (jobs[j].compressed) {
         TableChunk& tc = row_groups[jobs[j].rg].chunks[jobs[j].col];

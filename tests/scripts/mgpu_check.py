@@ -49,6 +49,8 @@ def main():
         ([], [count_star(), sum_("bytes"), min_("cpu")], [col("level") == "ERROR"]),
         ([], [count_star()], [(col("level") == "ERROR") & (col("latency_ms") > 100)]),
         (["region"], [count_star()], [col("level") == "NOPE"]),
+        # a key column without a dictionary (PLAIN doubles): the rows are interned per rank, the numbering agreed across ranks
+        (["status", "cpu"], [count_star(), max_("bytes")], [col("latency_ms") > 150]),
     ]
     for keys, aggs, flt in cases:
         print(f"rank {rank}: case {keys} {len(aggs)} aggs", flush=True)

@@ -277,7 +277,8 @@ def test_arrow_default_pages_and_v2(data_dir, built):
     # v2 pages keep their level bytes uncompressed in front of the (compressed) values
     for ver, kw in (("1.0", {}), ("2.0", {}), ("1.0", {"use_dictionary": ["k", "s"], "data_page_size": 64 << 10}),
                     ("2.0", {"compression": "LZ4"}), ("2.0", {"compression": "SNAPPY", "data_page_size": 64 << 10}),
-                    ("2.0", {"compression": "ZSTD"}), ("1.0", {"compression": "ZSTD", "compression_level": 9, "data_page_size": 64 << 10})):
+                    ("2.0", {"compression": "ZSTD"}), ("1.0", {"compression": "ZSTD", "compression_level": 9, "data_page_size": 64 << 10}),
+                    ("2.0", {"compression": "GZIP", "data_page_size": 256 << 10})):
         p = os.path.join(data_dir, f"arrow_default_{ver}_{len(kw)}_{kw.get('compression', 'NONE')}.parquet")
         kw = dict({"compression": "NONE"}, **kw)
         pq.write_table(t, p, data_page_version=ver, row_group_size=120_000, **kw)
@@ -333,18 +334,18 @@ def test_errors_are_codes_not_crashes(env, data_dir):
     with pytest.raises(QueryError) as ei:
         prov.scan(filters=[col("level") == 5], count_only=True)
     assert ei.value.code == L.PQ_ERR_INVALID_ARG
-    gz = os.path.join(data_dir, "gzip.parquet")
-    synth.write_logs16(gz, n_row_groups=1, rows_per_group=10_000, compression="GZIP", columns=["level", "status"])
+    gz = os.path.join(data_dir, "brotli.parquet")
+    synth.write_logs16(gz, n_row_groups=1, rows_per_group=10_000, compression="BROTLI", columns=["level", "status"])
     with pytest.raises(QueryError) as ei:
         StandardTableProvider([gz], schema={"level": pa.string()}).scan(filters=[col("level") == "INFO"], count_only=True)
     assert ei.value.code == L.PQ_ERR_UNSUPPORTED and "codec" in ei.value.message
 
 
-@pytest.mark.parametrize("codec", ["LZ4_RAW", "SNAPPY", "ZSTD"])
+@pytest.mark.parametrize("codec", ["LZ4_RAW", "SNAPPY", "ZSTD", "GZIP"])
 @pytest.mark.parametrize("null_rate", [0.0, 0.02])
 def test_compressed_pages_decoded_on_gpu(data_dir, built, codec, null_rate):
     """Parseable's default codec is lz4_raw (src/cli.rs:441-448), its CI pins snappy
-    (docker-compose-test.yaml:45), zstd is another legal P_PARQUET_COMPRESSION_ALGO (src/option.rs:62-86):
+    (docker-compose-test.yaml:45), zstd and gzip are other legal P_PARQUET_COMPRESSION_ALGO values (src/option.rs:62-86):
     pages are decompressed on the GPU (one warp per page) into the arena, then the same scan runs."""
     p = os.path.join(data_dir, f"comp_{codec}_{int(null_rate * 100)}.parquet")
     synth.write_logs16(p, n_row_groups=2, rows_per_group=60_000, null_rate=null_rate, compression=codec)

@@ -1,4 +1,4 @@
-"""The ZSTD page decoder (parseable_b200/csrc/zstd_decode.cuh) compiled for the host -- the same source the GPU
+"""The ZSTD and GZIP page decoders (parseable_b200/csrc/zstd_decode.cuh, inflate_decode.cuh) compiled for the host -- the same source the GPU
 runs with 32 lanes -- against pyarrow's zstd: every block / literals / sequence mode the encoder emits at its levels,
 multi-block inputs, empty and one-byte pages, Parquet pages out of a zstd file, and garbled input (no fault).
 ZSTD is a legal P_PARQUET_COMPRESSION_ALGO of the reference (src/option.rs:62-86)."""
@@ -19,13 +19,14 @@ def zs():
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", ROOT, "tools"])
     lib = ctypes.CDLL(so)
-    lib.zs_host_decode.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64]
-    lib.zs_host_decode.restype = ctypes.c_int
+    for f in (lib.zs_host_decode, lib.gz_host_decode):
+        f.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64]
+        f.restype = ctypes.c_int
 
-    def decode(comp: bytes, n: int):
+    def decode(comp: bytes, n: int, gz: bool = False):
         src = np.frombuffer(comp, dtype=np.uint8).copy() if comp else np.zeros(1, np.uint8)
         dst = np.zeros(max(n, 1), np.uint8)
-        ok = lib.zs_host_decode(src.ctypes.data, len(comp), dst.ctypes.data, n)
+        ok = (lib.gz_host_decode if gz else lib.zs_host_decode)(src.ctypes.data, len(comp), dst.ctypes.data, n)
         return ok == 1, dst[:n].tobytes()
     return decode
 
@@ -123,3 +124,40 @@ def test_pages_of_a_zstd_parquet_file(zs, tmp_path, built):
         assert codec == 6 and pg["uncompressed_size"] == len(want) == png["uncompressed_size"]
         ok, out = zs(comp, pg["uncompressed_size"])
         assert ok and out == want
+
+
+# ---- GZIP (codec 2): gzip members around DEFLATE ----
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_gzip_decoder_matches_zlib(zs, level):
+    import gzip
+    import zlib
+    for name, data in _inputs():
+        for how in ("arrow", "gzip", "fixed", "stored+members"):
+            if how == "arrow":
+                comp = pa.Codec("gzip", compression_level=level).compress(data, asbytes=True)
+            elif how == "gzip":
+                comp = gzip.compress(data, compresslevel=level)
+            elif how == "fixed":                       # fixed Huffman blocks only
+                co = zlib.compressobj(level, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)
+                comp = co.compress(data) + co.flush()
+            else:                                      # stored blocks, then a second member
+                h = len(data) // 2
+                comp = gzip.compress(data[:h], compresslevel=0) + gzip.compress(data[h:], compresslevel=level)
+            ok, out = zs(comp, len(data), gz=True)
+            assert ok and out == data, (name, level, how, len(data), len(comp))
+
+
+def test_gzip_garbled_input_is_refused_without_faults(zs):
+    import gzip
+    rng = np.random.default_rng(9)
+    data = b"".join(b"%d,%d;" % (i % 97, i * i % 1013) for i in range(40_000))
+    comp = gzip.compress(data, compresslevel=6)
+    assert not zs(comp, len(data) - 1, gz=True)[0] and not zs(comp, len(data) + 1, gz=True)[0]
+    assert not zs(comp[:-9], len(data), gz=True)[0] and not zs(b"\x00" * 32, 10, gz=True)[0]
+    refused = 0
+    for _ in range(300):
+        g = bytearray(comp)
+        for _ in range(int(rng.integers(1, 4))):
+            g[int(rng.integers(0, len(g)))] ^= 1 << int(rng.integers(0, 8))
+        refused += 0 if zs(bytes(g), len(data), gz=True)[0] else 1     # CRC-32 is not verified: a flip inside literals may pass
+    assert refused > 50
