@@ -602,7 +602,7 @@ def test_corrupt_dictionary_index_is_refused(data_dir, built):
 
 def test_garbled_pages_fail_cleanly(data_dir, built):
     """Bytes flipped inside dictionary and data pages (run headers, bit widths, definition levels, PLAIN values, LZ4
-    sequences): every open either answers or returns an error code -- no fault, no hang, and the CUDA context serves the
+    sequences, ZSTD / GZIP streams): every open either answers or returns an error code -- no fault, no hang, and the CUDA context serves the
     next query.  (What a reader must answer for garbled VALUES is undefined; that it survives is not.)"""
     rng = np.random.default_rng(53)
     n = 60_000
@@ -614,7 +614,7 @@ def test_garbled_pages_fail_cleanly(data_dir, built):
     })
     schema = t.schema
     good = {}
-    for codec in ("NONE", "LZ4"):
+    for codec in ("NONE", "LZ4", "ZSTD", "GZIP"):
         p = os.path.join(data_dir, f"garble_{codec}.parquet")
         pq.write_table(t, p, compression=codec, use_dictionary=["k", "d"], data_page_size=32 << 10, row_group_size=30_000,
                        column_encoding={"s": "DELTA_BYTE_ARRAY"})
@@ -648,7 +648,7 @@ def test_garbled_pages_fail_cleanly(data_dir, built):
             os.remove(bad)
             # the context still answers, exactly
             assert StandardTableProvider([p], schema=schema).scan(filters=flt, count_only=True).metrics["rows_selected"] == want, (codec, trial)
-    assert outcomes["ok"] + outcomes["error"] == 48 and outcomes["error"] > 0, outcomes
+    assert outcomes["ok"] + outcomes["error"] == 96 and outcomes["error"] > 0, outcomes
 
 
 def test_staging_branch_and_field_stats(data_dir, built):
