@@ -1932,10 +1932,15 @@ void Query::json(uint32_t flags, const char** out, uint64_t* len) {
       ja.batch_rows = 0x7fffffffu;
       ja.words_per_batch = 0;
       std::vector<uint8_t> v = oc.values;
-      if (v.empty()) v.assign(8, 0);
+      v.resize(std::max<size_t>((v.size() + 7) & ~size_t(7), 8), 0);   // 8-byte values / whole words of bit-packed booleans
       temps[3 * c].upload(v, stream);
       jc.values = temps[3 * c].p;
-      if (oc.null_count) { temps[3 * c + 1].upload(oc.validity, stream); jc.validity = reinterpret_cast<const uint32_t*>(temps[3 * c + 1].p); }
+      if (oc.null_count) {
+        std::vector<uint8_t> vv = oc.validity;
+        vv.resize((vv.size() + 7) & ~size_t(7), 0);   // the kernel reads whole 32-bit words
+        temps[3 * c + 1].upload(vv, stream);
+        jc.validity = reinterpret_cast<const uint32_t*>(temps[3 * c + 1].p);
+      }
       if (oc.type == PQ_T_UTF8) {
         std::vector<uint8_t> o(oc.offsets.size() * 4);
         std::memcpy(o.data(), oc.offsets.data(), o.size());

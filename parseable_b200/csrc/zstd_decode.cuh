@@ -71,20 +71,61 @@ ZS_FN uint64_t zs_bits_le(const uint8_t* p, uint32_t nbits, uint64_t bitoff) {
   for (uint32_t i = 0; i < need; i++) v |= uint64_t(q[i]) << (8u * i);
   return (v >> sh) & ((1ull << nbits) - 1ull);
 }
-// backward bit stream: `off` is the number of unread bits below the cursor; may go negative at the very end
-// (the bits below the start of the stream read as zero)
-ZS_FN uint64_t zs_rbits(const uint8_t* p, uint32_t nbits, int64_t& off) {
-  off -= int64_t(nbits);
-  if (off >= 0) return zs_bits_le(p, nbits, uint64_t(off));
-  const int64_t real = int64_t(nbits) + off;   // bits that exist
-  if (real <= 0) return 0;
-  const uint64_t v = zs_bits_le(p, uint32_t(real), 0);
-  return (-off) >= 64 ? 0 : (v << uint32_t(-off));
+// Backward bit stream over p[0 .. len): `off` is the number of unread bits below the cursor (it may go negative at the
+// very end: the bits below the start of the stream read as zero).  Reads go through a 64-bit window of the stream held
+// in registers: one (aligned, on the device) load per ~64 bits consumed instead of a byte-wise assembly per field.
+struct ZsR {
+  const uint8_t* p;
+  uint32_t len;
+  int64_t off;
+  uint64_t win;       // bits [wbase, wbase + 64) of the stream (fewer at a short stream's end)
+  int64_t wbase;      // multiple of 8; -1: nothing loaded
+};
+ZS_FN uint32_t zs_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {   // low word of (hi:lo) >> sh, sh in {0, 8, 16, 24}
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
 }
-// start of a backward stream: position of the end mark in the last byte; < 0: corrupt
-ZS_FN int64_t zs_rstart(const uint8_t* p, uint32_t len) {
-  if (!len || p[len - 1] == 0) return -1;
-  return int64_t(len) * 8 - (8 - zs_highbit(p[len - 1]));
+ZS_FN uint64_t zs_load_window(const uint8_t* p, uint32_t len, uint64_t byte) {   // up to 8 bytes at p[byte ..], little endian
+#if defined(__CUDA_ARCH__) || defined(ZS_TEST_ALIGNED)   // (the host build takes this path only in the test harness that checks it)
+  if (byte + 12 <= len) {   // three aligned words hold the eight bytes, whatever the byte phase; they stay inside p[0 .. len) plus at most 3 bytes below p (the buffer's base is aligned)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p + byte);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t sh = uint32_t(a & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return (uint64_t(zs_funnel_r(w1, w2, sh)) << 32) | zs_funnel_r(w0, w1, sh);
+  }
+#endif
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < 8 && byte + i < len; i++) v |= uint64_t(p[byte + i]) << (8u * i);
+  return v;
+}
+ZS_FN uint64_t zs_rbits(ZsR& r, uint32_t nbits) {   // nbits <= 32
+  r.off -= int64_t(nbits);
+  if (nbits == 0) return 0;
+  if (r.off >= 0) {
+    if (r.wbase < 0 || r.off < r.wbase || r.off + int64_t(nbits) > r.wbase + 64) {
+      // reads walk downwards: a window that ends at the byte above this field serves the following ones too
+      int64_t b = ((r.off + int64_t(nbits) + 7) & ~int64_t(7)) - 64;
+      if (b < 0) b = 0;
+      r.wbase = b;
+      r.win = zs_load_window(r.p, r.len, uint64_t(b >> 3));
+    }
+    return (r.win >> uint32_t(r.off - r.wbase)) & ((1ull << nbits) - 1ull);
+  }
+  const int64_t real = int64_t(nbits) + r.off;   // bits that exist
+  if (real <= 0) return 0;
+  const uint64_t v = zs_bits_le(r.p, uint32_t(real), 0);
+  return (-r.off) >= 64 ? 0 : (v << uint32_t(-r.off));
+}
+// start of a backward stream: position of the end mark in the last byte; off < 0: corrupt
+ZS_FN ZsR zs_rstart(const uint8_t* p, uint32_t len) {
+  ZsR r{p, len, -1, 0, -1};
+  if (!len || p[len - 1] == 0) return r;
+  r.off = int64_t(len) * 8 - (8 - zs_highbit(p[len - 1]));
+  return r;
 }
 
 // ---- FSE ---------------------------------------------------------------------------------------
@@ -224,18 +265,18 @@ ZS_FN_NOINLINE uint32_t zs_huf_tree(ZstdWs& w, const uint8_t* p, uint32_t len) {
     if (!zs_fse_build(w.wt, w.freq, nsym, log)) return 0;
     const uint8_t* bs = q + hdr;
     const uint32_t bl = hb - hdr;
-    int64_t off = zs_rstart(bs, bl);
-    if (off < 0) return 0;
-    uint32_t s1 = uint32_t(zs_rbits(bs, log, off)), s2 = uint32_t(zs_rbits(bs, log, off));
+    ZsR r = zs_rstart(bs, bl);
+    if (r.off < 0) return 0;
+    uint32_t s1 = uint32_t(zs_rbits(r, log)), s2 = uint32_t(zs_rbits(r, log));
     for (;;) {
       if (n >= 254) return 0;
       w.weights[n++] = w.wt.sym[s1];
-      s1 = w.wt.base[s1] + uint32_t(zs_rbits(bs, w.wt.nbits[s1], off));
-      if (off < 0) { w.weights[n++] = w.wt.sym[s2]; break; }
+      s1 = w.wt.base[s1] + uint32_t(zs_rbits(r, w.wt.nbits[s1]));
+      if (r.off < 0) { w.weights[n++] = w.wt.sym[s2]; break; }
       if (n >= 254) return 0;
       w.weights[n++] = w.wt.sym[s2];
-      s2 = w.wt.base[s2] + uint32_t(zs_rbits(bs, w.wt.nbits[s2], off));
-      if (off < 0) { w.weights[n++] = w.wt.sym[s1]; break; }
+      s2 = w.wt.base[s2] + uint32_t(zs_rbits(r, w.wt.nbits[s2]));
+      if (r.off < 0) { w.weights[n++] = w.wt.sym[s1]; break; }
     }
     used = 1 + hb;
   }
@@ -245,18 +286,18 @@ ZS_FN_NOINLINE uint32_t zs_huf_tree(ZstdWs& w, const uint8_t* p, uint32_t len) {
 }
 // one Huffman stream -> exactly `n` literals
 ZS_FN_NOINLINE bool zs_huf_stream(const ZstdWs& w, const uint8_t* p, uint32_t len, uint8_t* out, uint32_t n) {
-  int64_t off = zs_rstart(p, len);
-  if (off < 0) return false;
+  ZsR r = zs_rstart(p, len);
+  if (r.off < 0) return false;
   const uint32_t L = w.huf_log, mask = (1u << L) - 1u;
-  uint32_t st = uint32_t(zs_rbits(p, L, off));
+  uint32_t st = uint32_t(zs_rbits(r, L));
   uint32_t i = 0;
-  while (off > -int64_t(L)) {
+  while (r.off > -int64_t(L)) {
     if (i >= n) return false;
     out[i++] = w.huf_sym[st];
     const uint32_t nb = w.huf_nb[st];
-    st = ((st << nb) + uint32_t(zs_rbits(p, nb, off))) & mask;
+    st = ((st << nb) + uint32_t(zs_rbits(r, nb))) & mask;
   }
-  return off == -int64_t(L) && i == n;
+  return r.off == -int64_t(L) && i == n;
 }
 
 // ---- copies (shared by the lanes of the warp) ----------------------------------------------------
@@ -455,23 +496,23 @@ ZS_FN_NOINLINE uint64_t zs_block(ZstdWs& w, const uint8_t* p, uint32_t len, uint
   if (pos >= len) return BAD;
   const uint8_t* bs = p + pos;
   const uint32_t bl = len - pos;
-  int64_t off = zs_rstart(bs, bl);
-  if (off < 0) return BAD;
-  uint32_t sl = uint32_t(zs_rbits(bs, w.ll.log, off)), so = uint32_t(zs_rbits(bs, w.of.log, off)), sm = uint32_t(zs_rbits(bs, w.ml.log, off));
-  if (off < 0) return BAD;
+  ZsR r = zs_rstart(bs, bl);
+  if (r.off < 0) return BAD;
+  uint32_t sl = uint32_t(zs_rbits(r, w.ll.log)), so = uint32_t(zs_rbits(r, w.of.log)), sm = uint32_t(zs_rbits(r, w.ml.log));
+  if (r.off < 0) return BAD;
   uint32_t lp = 0;   // literals consumed
   for (uint32_t i = 0; i < nseq; i++) {
     const uint32_t oc = w.of.sym[so], lc = w.ll.sym[sl], mc = w.ml.sym[sm];
     if (oc > 31 || lc > 35 || mc > 52) return BAD;
-    const uint64_t ov = (1ull << oc) + zs_rbits(bs, oc, off);
-    const uint32_t mlen = zs_ml_base(mc) + uint32_t(zs_rbits(bs, zs_ml_bits(mc), off));
-    const uint32_t llen = zs_ll_base(lc) + uint32_t(zs_rbits(bs, zs_ll_bits(lc), off));
-    if (off < 0) return BAD;
+    const uint64_t ov = (1ull << oc) + zs_rbits(r, oc);
+    const uint32_t mlen = zs_ml_base(mc) + uint32_t(zs_rbits(r, zs_ml_bits(mc)));
+    const uint32_t llen = zs_ll_base(lc) + uint32_t(zs_rbits(r, zs_ll_bits(lc)));
+    if (r.off < 0) return BAD;
     if (i + 1 < nseq) {
-      sl = w.ll.base[sl] + uint32_t(zs_rbits(bs, w.ll.nbits[sl], off));
-      sm = w.ml.base[sm] + uint32_t(zs_rbits(bs, w.ml.nbits[sm], off));
-      so = w.of.base[so] + uint32_t(zs_rbits(bs, w.of.nbits[so], off));
-      if (off < 0) return BAD;
+      sl = w.ll.base[sl] + uint32_t(zs_rbits(r, w.ll.nbits[sl]));
+      sm = w.ml.base[sm] + uint32_t(zs_rbits(r, w.ml.nbits[sm]));
+      so = w.of.base[so] + uint32_t(zs_rbits(r, w.of.nbits[so]));
+      if (r.off < 0) return BAD;
     }
     uint64_t offset;
     if (ov > 3) {
@@ -499,7 +540,7 @@ ZS_FN_NOINLINE uint64_t zs_block(ZstdWs& w, const uint8_t* p, uint32_t len, uint
     dp += mlen;
     ZS_SYNC();
   }
-  if (off != 0) return BAD;
+  if (r.off != 0) return BAD;
   const uint32_t rest = regen - lp;
   if (dp + rest > dn) return BAD;
   zs_copy(dst + dp, lit + lp, rest);
