@@ -1,6 +1,5 @@
-# memcheck of the kernels added in the last sessions (ZSTD / GZIP decoders, hashed and row-key GROUP BY, JSON egress)
+# last GPU session of the round: the parity suite on the final build, then the ZSTD open probe with the windowed bit reader
 set -x
 mkdir -p gpurun_out
-( time timeout -s KILL 420 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q \
-   -k "compressed_pages_decoded_on_gpu or hashed or without_dictionary or json_egress or plain_byte_array or garbled" ) > gpurun_out/memcheck_r2k.log 2>&1
-echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|Error" gpurun_out/memcheck_r2k.log | head -20; tail -5 gpurun_out/memcheck_r2k.log
+( time timeout -s KILL 300 python -m pytest tests -m gpu -x -q ) > gpurun_out/gputests_r2l.log 2>&1; tail -6 gpurun_out/gputests_r2l.log
+PQB_BENCH_CODEC=ZSTD timeout -s KILL 120 python tests/scripts/open_probe.py 48 2>&1 | grep -E "^step|generated" | tail -5
