@@ -518,6 +518,18 @@ class StandardTableProvider:
         return QueryResult(batches, m.as_dict(), [f.name for f in batches[0].schema] if batches else [], json_text)
 
 
+def flatten_objects_for_count(objects: list[dict]) -> list[dict]:
+    """src/query/mod.rs:858-902 (kept "for later" by the reference; its six unit tests pin it): JSON rows that all carry
+    the one same ``COUNT...`` key -- per-partition / per-node COUNT results -- fold into one row with their sum; anything
+    else passes through untouched.  On the GPU path the same fold is the all-reduce of the partial tables."""
+    if not objects:
+        return objects
+    first_key = next(iter(objects[0]), None)
+    if all(all(k.startswith("COUNT") for k in o) for o in objects) and all(all(k == first_key for k in o) for o in objects):
+        return [{first_key: sum(int(v) for o in objects for v in o.values())}]
+    return objects
+
+
 # ----------------------------------------------------------------------------- Query / execute
 @dataclass
 class TimeRange:

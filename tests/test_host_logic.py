@@ -121,3 +121,17 @@ def test_staging_batches_become_one_reversed_parquet_image():
     md = pf.metadata.row_group(0)
     encs = {md.column(i).path_in_schema: set(md.column(i).encodings) for i in range(md.num_columns)}
     assert "DELTA_BINARY_PACKED" in encs["p_timestamp"] and "RLE_DICTIONARY" in encs["k"]
+
+
+def test_flatten_objects_for_count_reference_vectors():
+    """The six unit tests of /root/reference/src/query/mod.rs:1006-1090, value for value."""
+    from parseable_b200.query import flatten_objects_for_count as f
+    assert f([{"COUNT(*)": 1}, {"COUNT(*)": 2}, {"COUNT(*)": 3}]) == [{"COUNT(*)": 6}]                      # test_flat_simple
+    assert f([]) == []                                                                                     # test_flat_empty
+    assert f([{"COUNT(ALPHA)": 1}, {"COUNT(ALPHA)": 2}]) == [{"COUNT(ALPHA)": 3}]                           # test_flat_same_multi
+    v = [{"COUNT(ALPHA)": 1}, {"COUNT(BETA)": 2}]
+    assert f(list(v)) == v                                                                                 # test_flat_diff_multi
+    v = [{"Num": 1}, {"Num": 2}, {"Num": 3}]
+    assert f(list(v)) == v                                                                                 # test_flat_fail
+    v = [{"Num": 1, "COUNT(*)": 1}, {"Num": 2, "COUNT(*)": 2}, {"Num": 3, "COUNT(*)": 3}]
+    assert f(list(v)) == v                                                                                 # test_flat_multi_key
